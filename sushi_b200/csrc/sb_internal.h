@@ -1,0 +1,108 @@
+// Internal declarations shared by the translation units of libsushi_b200.so.
+// Nothing here is part of the ABI (see include/sushi_b200.h for that).
+#pragma once
+#include <cuda_runtime.h>
+#include <cufft.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include <map>
+
+#include "sushi_b200.h"
+
+namespace sb {
+
+// ---- error plumbing ---------------------------------------------------------
+void set_error(const char* fmt, ...);
+#define SB_FAIL(code, ...) do { sb::set_error(__VA_ARGS__); return (code); } while (0)
+#define SB_CUDA(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { \
+    sb::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    return SB_ECUDA; } } while (0)
+#define SB_CUFFT(expr) do { cufftResult r__ = (expr); if (r__ != CUFFT_SUCCESS) { \
+    sb::set_error("%s failed: cufft error %d (%s:%d)", #expr, (int)r__, __FILE__, __LINE__); \
+    return SB_ECUDA; } } while (0)
+#define SB_TRY(expr) do { int rc__ = (expr); if (rc__ != SB_OK) return rc__; } while (0)
+
+// ---- per-kernel accounting --------------------------------------------------
+struct ProfEntry { double ms = 0.0; int64_t launches = 0; };
+struct PendingEvent { int name_id; cudaEvent_t a, b; };
+
+// ---- query descriptor as the kernels see it ----------------------------------
+// One query = one find_substream call (reference wav.py:177-188) reduced to
+// integer sample offsets.  itemBase / partBase are exclusive prefix sums over the
+// batch: item = (query, lag block k), part = (query, template partition p).
+struct QueryDesc {
+    int64_t toff;      // template start in the template stream
+    int64_t tlen;      // template length n
+    int64_t lag0;      // first candidate position in the image stream
+    int64_t nlags;     // number of candidate positions L
+    int64_t itemBase;  // first item of this query in the batch-wide item list
+    int64_t partBase;  // first partition spectrum of this query
+    int32_t P;         // ceil(n / B)
+    int32_t k0;        // lag0 / B
+    int32_t nk;        // number of lag blocks touched
+    int32_t pad_;
+};
+
+struct Ctx {
+    bool inited = false;
+    int device = -1;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    int B = 16384;                 // lag-block size (samples); FFT size is 2B
+    int chunk_items = 1024;        // items per MAC/C2R/normalise chunk
+    int64_t max_parts = 16384;     // template partition spectra kept per super-chunk
+
+    // scratch (grown on demand)
+    float2* d_parts = nullptr;  int64_t parts_cap = 0;     // [parts][B+1] complex (in-place R2C)
+    float2* d_items = nullptr;  int64_t items_cap = 0;     // [items][B+1] complex (in-place C2R)
+    QueryDesc* d_desc = nullptr; int64_t desc_cap = 0;
+    unsigned long long* d_keys = nullptr; int64_t keys_cap = 0;
+    float* d_diff = nullptr; int64_t* d_idx = nullptr; int64_t res_cap = 0;
+    // pinned staging
+    QueryDesc* h_desc = nullptr; int64_t h_desc_cap = 0;
+    float* h_diff = nullptr; int64_t* h_idx = nullptr; int64_t h_res_cap = 0;
+
+    std::map<std::pair<int, int64_t>, cufftHandle> plans;   // (type, batch) -> plan for size 2B
+
+    // timers / profile
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    cudaEvent_t ev_desc = nullptr;   // marks the last H2D copy out of h_desc
+    bool prof_on = false;
+    std::vector<std::string> prof_names;
+    std::vector<ProfEntry> prof;
+    std::vector<PendingEvent> pending;
+    std::vector<cudaEvent_t> event_pool;
+    int64_t launches = 0;
+};
+
+Ctx& ctx();
+int prof_id(const char* name);
+void prof_begin(int id, cudaEvent_t* a, cudaEvent_t* b);
+void prof_end(int id, cudaEvent_t a, cudaEvent_t b);
+int prof_collect();
+
+// RAII-free bracket used around every kernel class
+struct ProfScope {
+    int id; cudaEvent_t a = nullptr, b = nullptr; bool on;
+    explicit ProfScope(const char* name, int nlaunch = 1);
+    ~ProfScope();
+};
+
+int get_plan(int type, int64_t batch, cufftHandle* out);
+void drop_plans();
+
+}  // namespace sb
+
+// The opaque stream handle of the ABI.
+struct sb_stream {
+    int64_t n = 0;
+    int dtype = SB_U8;
+    void* d_raw = nullptr;        // n samples (u8 or f32)
+    double* d_psum = nullptr;     // [n+1] running sum of samples        (exact for u8)
+    double* d_psq = nullptr;      // [n+1] running sum of squared samples (exact for u8)
+    // block spectra for lag-block size specB: [nblk][specB+1] complex64
+    float2* d_spec = nullptr;
+    int specB = 0;
+    int64_t nblk = 0;
+};

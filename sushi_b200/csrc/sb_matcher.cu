@@ -1,0 +1,419 @@
+// The matcher: WavStream.find_substream (reference wav.py:177-188), i.e.
+// cv2.matchTemplate(TM_SQDIFF_NORMED) + first-index argmin, for batches of
+// independent queries against a resident stream.
+//
+// Formulation: uniformly partitioned overlap-save.  The image
+// stream is cut into lag blocks of B positions; block spectra X_k = FFT_2B(image[kB
+// .. kB+2B) - c) are built once per stream.  A template of n samples is cut into
+// P = ceil(n/B) partitions T_p (zero padded to 2B).  For lag block k
+//     corr_k = IFFT_2B( sum_p conj(T^_p) * X^_{k+p} )[0 .. B)
+// is the centred cross-correlation at positions kB .. kB+B-1; the un-centred
+// sum(I*T), the window energy sum(I^2) and sum(T^2) come from exact running sums,
+// and OpenCV's normalisation rule + float32 rounding + first-index argmin are
+// applied in the same kernel that reads the correlation back.
+#include "sb_internal.h"
+#include <algorithm>
+#include <cstring>
+
+namespace sb { int ensure_spectra(sb_stream* s); }
+using namespace sb;
+
+namespace {
+
+// ---- template partitions -------------------------------------------------------
+// One CTA chunk writes 2048 floats of one partition row (row stride 2B+2 floats).
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_gather_parts(const T* __restrict__ tmpl, const QueryDesc* __restrict__ desc, int q_begin, int q_end,
+               int64_t part_first, int B, float c, float* __restrict__ rows, int chunks_per_row) {
+    __shared__ int s_q;
+    const int64_t row = blockIdx.x / chunks_per_row;
+    const int chunk = blockIdx.x % chunks_per_row;
+    const int64_t part = part_first + row;
+    if (threadIdx.x == 0) {                         // largest q with partBase <= part
+        int lo = q_begin, hi = q_end - 1;
+        while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (desc[mid].partBase <= part) lo = mid; else hi = mid - 1; }
+        s_q = lo;
+    }
+    __syncthreads();
+    const QueryDesc d = desc[s_q];
+    const int64_t p = part - d.partBase;
+    const int64_t seg0 = p * B;                     // offset of this partition inside the template
+    float* out = rows + row * (int64_t)(2 * B + 2);
+    const int i0 = chunk * 2048 + threadIdx.x * 2;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        int i = i0 + r * 512;
+        if (i < 2 * B) {
+            float2 v;
+            v.x = (i < B && seg0 + i < d.tlen) ? (float)tmpl[d.toff + seg0 + i] - c : 0.f;
+            v.y = (i + 1 < B && seg0 + i + 1 < d.tlen) ? (float)tmpl[d.toff + seg0 + i + 1] - c : 0.f;
+            *reinterpret_cast<float2*>(out + i) = v;
+        }
+    }
+}
+
+// ---- item lookup ---------------------------------------------------------------
+__device__ __forceinline__ int find_query(const QueryDesc* __restrict__ desc, int q_begin, int q_end, int64_t item) {
+    int lo = q_begin, hi = q_end - 1;
+    while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (desc[mid].itemBase <= item) lo = mid; else hi = mid - 1; }
+    return lo;
+}
+
+// ---- spectral multiply-accumulate ------------------------------------------------
+// Y[item][bin] = sum_p conj(T^[part(q,p)][bin]) * X^[k+p][bin]
+constexpr int MAC_THREADS = 256;
+constexpr int MAC_BINS = 1024;          // bins per CTA
+__global__ void __launch_bounds__(MAC_THREADS)
+k_spectral_mac(const float2* __restrict__ That, int64_t part_first, const float2* __restrict__ Xhat, int64_t nblk,
+               const QueryDesc* __restrict__ desc, int q_begin, int q_end, int64_t item_first,
+               int B, float2* __restrict__ Y, int chunks_per_item) {
+    __shared__ int s_q;
+    const int64_t it = blockIdx.x / chunks_per_item;
+    const int chunk = blockIdx.x % chunks_per_item;
+    const int64_t item = item_first + it;
+    if (threadIdx.x == 0) s_q = find_query(desc, q_begin, q_end, item);
+    __syncthreads();
+    const QueryDesc d = desc[s_q];
+    const int64_t k = d.k0 + (item - d.itemBase);
+    const int nb = B + 1;
+    int P = d.P;
+    if (k + P > nblk) P = (int)(nblk - k);          // blocks past the stream end are all zero
+    const float2* tp = That + (d.partBase - part_first) * (int64_t)nb;
+    const float2* xp = Xhat + k * (int64_t)nb;
+    float2* y = Y + it * (int64_t)nb;
+    const int b0 = chunk * MAC_BINS + threadIdx.x;
+    float2 acc[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) acc[r] = make_float2(0.f, 0.f);
+    for (int p = 0; p < P; ++p) {
+        const float2* t = tp + (int64_t)p * nb;
+        const float2* x = xp + (int64_t)p * nb;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            int b = b0 + r * MAC_THREADS;
+            if (b < nb) {
+                float2 tv = __ldg(t + b), xv = __ldg(x + b);
+                acc[r].x += tv.x * xv.x + tv.y * xv.y;
+                acc[r].y += tv.x * xv.y - tv.y * xv.x;
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        int b = b0 + r * MAC_THREADS;
+        if (b < nb) y[b] = acc[r];
+    }
+}
+
+// ---- normalise + argmin ----------------------------------------------------------
+// OpenCV's rule for TM_SQDIFF_NORMED (imgproc/templmatch.cpp, common_matchTemplate;
+// behaviour pinned by tests/golden): with corr the float32-rounded sum(I*T),
+//   num = max(wnd - 2*corr + tsum2, 0);  t = sqrt(wnd) * sqrt(tsum2)  (t = 0 if wnd is ~0)
+//   out = |num| < t ? num/t : 1           -> float32
+__device__ __forceinline__ float sqdiff_normed(double corr_centred, double wsum, double wsq,
+                                               double c, double tsum, double tsq, double n_c2, double tnorm) {
+    // undo the centring exactly: sum(I*T) = sum(I'T') + c*sum(I_w) + c*sum(T) - n*c^2
+    const double sit = corr_centred + c * wsum + c * tsum - n_c2;
+    const double corr = (double)(float)sit;
+    double num = wsq - 2.0 * corr + tsq;
+    num = fmax(num, 0.0);
+    const double diff2 = fmax(wsq, 0.0);
+    double t = (diff2 <= fmin(0.5, 10.0 * 1.1920928955078125e-07 * wsq)) ? 0.0 : sqrt(diff2) * tnorm;
+    double out = (fabs(num) < t) ? num / t : 1.0;
+    return (float)out;
+}
+
+__device__ __forceinline__ unsigned long long pack_key(float v, unsigned int rel) {
+    return ((unsigned long long)__float_as_uint(v) << 32) | rel;     // v >= 0: bit pattern is monotone
+}
+
+constexpr int NORM_THREADS = 256;
+constexpr int NORM_LAGS = 2048;          // lags per CTA
+__global__ void __launch_bounds__(NORM_THREADS)
+k_normalise_argmin(const float* __restrict__ corr_rows, const double* __restrict__ ipsum, const double* __restrict__ ipsq,
+                   const double* __restrict__ tpsum, const double* __restrict__ tpsq,
+                   const QueryDesc* __restrict__ desc, int q_begin, int q_end, int64_t item_first,
+                   int B, float cval, unsigned long long* __restrict__ keys, float* __restrict__ curve_out,
+                   int chunks_per_item) {
+    __shared__ int s_q;
+    __shared__ unsigned long long s_best[NORM_THREADS / 32];
+    const int64_t it = blockIdx.x / chunks_per_item;
+    const int chunk = blockIdx.x % chunks_per_item;
+    const int64_t item = item_first + it;
+    if (threadIdx.x == 0) s_q = find_query(desc, q_begin, q_end, item);
+    __syncthreads();
+    const int q = s_q;
+    const QueryDesc d = desc[q];
+    const int64_t k = d.k0 + (item - d.itemBase);
+    const int64_t n = d.tlen;
+    const double c = (double)cval;
+    const double tsum = tpsum[d.toff + n] - tpsum[d.toff];
+    const double tsq = tpsq[d.toff + n] - tpsq[d.toff];
+    const double tnorm = sqrt(tsq);
+    const double n_c2 = (double)n * c * c;
+    const double scale = 1.0 / (double)(2 * B);      // cuFFT transforms are unnormalised
+    const float* row = corr_rows + it * (int64_t)(2 * B + 2);
+    const int64_t jlo = d.lag0, jhi = d.lag0 + d.nlags;   // valid positions [jlo, jhi)
+    unsigned long long best = ~0ull;
+    const int m0 = chunk * NORM_LAGS + threadIdx.x;
+#pragma unroll 4
+    for (int r = 0; r < NORM_LAGS / NORM_THREADS; ++r) {
+        const int m = m0 + r * NORM_THREADS;
+        const int64_t j = k * B + m;
+        if (m < B && j >= jlo && j < jhi) {
+            const double cc = (double)row[m] * scale;
+            const double wsum = ipsum[j + n] - ipsum[j];
+            const double wsq = ipsq[j + n] - ipsq[j];
+            const float v = sqdiff_normed(cc, wsum, wsq, c, tsum, tsq, n_c2, tnorm);
+            if (curve_out) curve_out[j - jlo] = v;
+            const unsigned long long key = pack_key(v, (unsigned int)(j - jlo));
+            best = key < best ? key : best;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+        best = other < best ? other : best;
+    }
+    if ((threadIdx.x & 31) == 0) s_best[threadIdx.x >> 5] = best;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int w = 1; w < NORM_THREADS / 32; ++w) best = s_best[w] < best ? s_best[w] : best;
+        if (best != ~0ull) atomicMin(keys + q, best);
+    }
+}
+
+__global__ void k_unpack_results(const unsigned long long* __restrict__ keys, int64_t count,
+                                 float* __restrict__ diff, int64_t* __restrict__ idx) {
+    int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < count) {
+        unsigned long long k = keys[q];
+        diff[q] = __uint_as_float((unsigned int)(k >> 32));
+        idx[q] = (int64_t)(unsigned int)(k & 0xffffffffull);
+    }
+}
+
+template <typename T>
+int grow(T** p, int64_t* cap, int64_t need, bool pinned = false) {
+    if (need <= *cap) return SB_OK;
+    Ctx& c = ctx();
+    cudaStreamSynchronize(c.stream);
+    if (*p) { if (pinned) cudaFreeHost(*p); else cudaFree(*p); *p = nullptr; *cap = 0; }
+    int64_t ncap = std::max<int64_t>(need, 16);
+    cudaError_t e = pinned ? cudaMallocHost((void**)p, sizeof(T) * ncap) : cudaMalloc((void**)p, sizeof(T) * ncap);
+    if (e != cudaSuccess) SB_FAIL(SB_ENOMEM, "allocation of %lld bytes failed: %s", (long long)(sizeof(T) * ncap), cudaGetErrorString(e));
+    *cap = ncap;
+    return SB_OK;
+}
+
+// Validate + plan a batch on the host. Fills c.h_desc[0..count).
+int plan_batch(const sb_stream* image, const sb_stream* tmpl, int64_t count,
+               const int64_t* toff, const int64_t* tlen, const int64_t* lag0, const int64_t* nlags,
+               int64_t* total_items, int64_t* total_parts, int64_t* max_query_parts) {
+    Ctx& c = ctx();
+    const int B = c.B;
+    SB_CUDA(cudaEventSynchronize(c.ev_desc));       // previous batch has finished reading h_desc
+    if (c.h_desc_cap < count) {
+        if (c.h_desc) { cudaStreamSynchronize(c.stream); cudaFreeHost(c.h_desc); c.h_desc = nullptr; c.h_desc_cap = 0; }
+        SB_CUDA(cudaMallocHost((void**)&c.h_desc, sizeof(QueryDesc) * std::max<int64_t>(count, 64)));
+        c.h_desc_cap = std::max<int64_t>(count, 64);
+    }
+    int64_t items = 0, parts = 0, maxp = 0;
+    for (int64_t q = 0; q < count; ++q) {
+        const int64_t n = tlen[q], L = nlags[q], o = toff[q], s = lag0[q];
+        if (n < 1 || L < 1) SB_FAIL(SB_EINVAL, "query %lld: template length %lld / lag count %lld must be >= 1", (long long)q, (long long)n, (long long)L);
+        if (o < 0 || o + n > tmpl->n) SB_FAIL(SB_EINVAL, "query %lld: template [%lld,+%lld) outside template stream of %lld samples", (long long)q, (long long)o, (long long)n, (long long)tmpl->n);
+        if (s < 0 || s + L - 1 + n > image->n) SB_FAIL(SB_EINVAL, "query %lld: search span [%lld,+%lld)+%lld outside image stream of %lld samples", (long long)q, (long long)s, (long long)L, (long long)n, (long long)image->n);
+        if (L > 0xffffffffll) SB_FAIL(SB_EINVAL, "query %lld: more than 2^32 lags", (long long)q);
+        QueryDesc& d = c.h_desc[q];
+        d.toff = o; d.tlen = n; d.lag0 = s; d.nlags = L;
+        d.P = (int32_t)((n + B - 1) / B);
+        d.k0 = (int32_t)(s / B);
+        d.nk = (int32_t)((s + L - 1) / B - d.k0 + 1);
+        d.itemBase = items; d.partBase = parts; d.pad_ = 0;
+        items += d.nk; parts += d.P;
+        maxp = std::max<int64_t>(maxp, d.P);
+    }
+    *total_items = items; *total_parts = parts; *max_query_parts = maxp;
+    return SB_OK;
+}
+
+// Core: descriptors on host (validated here), results to device arrays d_diff/d_idx.
+int run_batch(const sb_stream* image_c, const sb_stream* tmpl, int64_t count,
+              const int64_t* toff, const int64_t* tlen, const int64_t* lag0, const int64_t* nlags,
+              float* d_diff, int64_t* d_idx, float* d_curve) {
+    Ctx& c = ctx();
+    sb_stream* image = const_cast<sb_stream*>(image_c);
+    if (image->dtype != tmpl->dtype) SB_FAIL(SB_EINVAL, "image and template streams differ in sample type");
+    const int B = c.B, nb = B + 1;
+    int64_t total_items = 0, total_parts = 0, maxp = 0;
+    SB_TRY(plan_batch(image, tmpl, count, toff, tlen, lag0, nlags, &total_items, &total_parts, &maxp));
+    SB_TRY(ensure_spectra(image));
+
+    SB_TRY(grow(&c.d_desc, &c.desc_cap, count));
+    SB_TRY(grow(&c.d_keys, &c.keys_cap, count));
+    SB_CUDA(cudaMemcpyAsync(c.d_desc, c.h_desc, sizeof(QueryDesc) * count, cudaMemcpyHostToDevice, c.stream));
+    SB_CUDA(cudaEventRecord(c.ev_desc, c.stream));
+    SB_CUDA(cudaMemsetAsync(c.d_keys, 0xff, sizeof(unsigned long long) * count, c.stream));
+
+    const int64_t parts_cap_want = std::max<int64_t>(std::min<int64_t>(total_parts, c.max_parts), maxp);
+    SB_TRY(grow(&c.d_parts, &c.parts_cap, parts_cap_want * nb));
+    const int64_t chunk = std::min<int64_t>(c.chunk_items, total_items);
+    SB_TRY(grow(&c.d_items, &c.items_cap, chunk * nb));
+
+    const float cval = image->dtype == SB_U8 ? 128.f : 0.5f;
+    const int gchunks = (2 * B + 2047) / 2048;
+    const int mchunks = (nb + MAC_BINS - 1) / MAC_BINS;
+    const int nchunks = (B + NORM_LAGS - 1) / NORM_LAGS;
+
+    // super-chunks of whole queries whose partition spectra fit the parts buffer
+    int64_t qb = 0;
+    while (qb < count) {
+        int64_t qe = qb, np = 0;
+        while (qe < count && np + c.h_desc[qe].P <= parts_cap_want) { np += c.h_desc[qe].P; ++qe; }
+        if (qe == qb) SB_FAIL(SB_ENOMEM, "internal: partition buffer too small");
+        const int64_t part_first = c.h_desc[qb].partBase;
+        // 1. template partitions -> spectra (in place)
+        const int64_t sub = 4096;
+        for (int64_t p0 = 0; p0 < np; p0 += sub) {
+            const int64_t rows = std::min<int64_t>(sub, np - p0);
+            float* dst = reinterpret_cast<float*>(c.d_parts + p0 * nb);
+            {
+                ProfScope ps("gather_parts");
+                if (tmpl->dtype == SB_U8)
+                    k_gather_parts<uint8_t><<<(unsigned)(rows * gchunks), 256, 0, c.stream>>>(
+                        static_cast<const uint8_t*>(tmpl->d_raw), c.d_desc, (int)qb, (int)qe, part_first + p0, B, cval, dst, gchunks);
+                else
+                    k_gather_parts<float><<<(unsigned)(rows * gchunks), 256, 0, c.stream>>>(
+                        static_cast<const float*>(tmpl->d_raw), c.d_desc, (int)qb, (int)qe, part_first + p0, B, cval, dst, gchunks);
+            }
+            cufftHandle plan;
+            SB_TRY(get_plan(CUFFT_R2C, rows, &plan));
+            {
+                ProfScope ps("cufft_r2c_parts", 0);
+                SB_CUFFT(cufftExecR2C(plan, dst, reinterpret_cast<cufftComplex*>(dst)));
+            }
+        }
+        // 2. items of these queries in fixed-size chunks
+        const int64_t item_lo = c.h_desc[qb].itemBase;
+        const int64_t item_hi = (qe < count) ? c.h_desc[qe].itemBase : total_items;
+        for (int64_t i0 = item_lo; i0 < item_hi; i0 += chunk) {
+            const int64_t ni = std::min<int64_t>(chunk, item_hi - i0);
+            {
+                ProfScope ps("spectral_mac");
+                k_spectral_mac<<<(unsigned)(ni * mchunks), MAC_THREADS, 0, c.stream>>>(
+                    c.d_parts, part_first, image->d_spec, image->nblk, c.d_desc, (int)qb, (int)qe, i0, B, c.d_items, mchunks);
+            }
+            cufftHandle plan;
+            SB_TRY(get_plan(CUFFT_C2R, ni, &plan));
+            {
+                ProfScope ps("cufft_c2r_items", 0);
+                SB_CUFFT(cufftExecC2R(plan, reinterpret_cast<cufftComplex*>(c.d_items), reinterpret_cast<float*>(c.d_items)));
+            }
+            {
+                ProfScope ps("normalise_argmin");
+                k_normalise_argmin<<<(unsigned)(ni * nchunks), NORM_THREADS, 0, c.stream>>>(
+                    reinterpret_cast<const float*>(c.d_items), image->d_psum, image->d_psq, tmpl->d_psum, tmpl->d_psq,
+                    c.d_desc, (int)qb, (int)qe, i0, B, cval, c.d_keys, d_curve, nchunks);
+            }
+        }
+        qb = qe;
+    }
+    {
+        ProfScope ps("unpack_results");
+        k_unpack_results<<<(unsigned)((count + 255) / 256), 256, 0, c.stream>>>(c.d_keys, count, d_diff, d_idx);
+    }
+    SB_CUDA(cudaGetLastError());
+    return SB_OK;
+}
+
+int check_common(const char* who, const sb_stream* image, const sb_stream* tmpl, int64_t count) {
+    Ctx& c = ctx();
+    if (!c.inited) SB_FAIL(SB_ESTATE, "%s: library not initialised (call sb_init)", who);
+    if (!image || !tmpl) SB_FAIL(SB_EINVAL, "%s: NULL stream", who);
+    if (count < 0) SB_FAIL(SB_EINVAL, "%s: negative count", who);
+    return SB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sb_find_batch(const sb_stream* image, const sb_stream* tmpl, int64_t count,
+                  const int64_t* tmpl_off, const int64_t* tmpl_len,
+                  const int64_t* lag0, const int64_t* nlags,
+                  float* diff_out, int64_t* idx_out) {
+    SB_TRY(check_common("sb_find_batch", image, tmpl, count));
+    if (count == 0) return SB_OK;
+    if (!tmpl_off || !tmpl_len || !lag0 || !nlags || !diff_out || !idx_out) SB_FAIL(SB_EINVAL, "sb_find_batch: NULL array");
+    Ctx& c = ctx();
+    if (c.res_cap < count) {
+        cudaStreamSynchronize(c.stream);
+        cudaFree(c.d_diff); cudaFree(c.d_idx); c.d_diff = nullptr; c.d_idx = nullptr; c.res_cap = 0;
+        SB_CUDA(cudaMalloc(&c.d_diff, sizeof(float) * count));
+        SB_CUDA(cudaMalloc(&c.d_idx, sizeof(int64_t) * count));
+        c.res_cap = count;
+    }
+    if (c.h_res_cap < count) {
+        cudaFreeHost(c.h_diff); cudaFreeHost(c.h_idx); c.h_diff = nullptr; c.h_idx = nullptr; c.h_res_cap = 0;
+        SB_CUDA(cudaMallocHost((void**)&c.h_diff, sizeof(float) * count));
+        SB_CUDA(cudaMallocHost((void**)&c.h_idx, sizeof(int64_t) * count));
+        c.h_res_cap = count;
+    }
+    SB_TRY(run_batch(image, tmpl, count, tmpl_off, tmpl_len, lag0, nlags, c.d_diff, c.d_idx, nullptr));
+    SB_CUDA(cudaMemcpyAsync(c.h_diff, c.d_diff, sizeof(float) * count, cudaMemcpyDeviceToHost, c.stream));
+    SB_CUDA(cudaMemcpyAsync(c.h_idx, c.d_idx, sizeof(int64_t) * count, cudaMemcpyDeviceToHost, c.stream));
+    SB_CUDA(cudaStreamSynchronize(c.stream));
+    memcpy(diff_out, c.h_diff, sizeof(float) * count);
+    memcpy(idx_out, c.h_idx, sizeof(int64_t) * count);
+    return SB_OK;
+}
+
+int sb_find_batch_device(const sb_stream* image, const sb_stream* tmpl, int64_t count,
+                         const int64_t* tmpl_off, const int64_t* tmpl_len,
+                         const int64_t* lag0, const int64_t* nlags,
+                         float* d_diff_out, int64_t* d_idx_out) {
+    SB_TRY(check_common("sb_find_batch_device", image, tmpl, count));
+    if (count == 0) return SB_OK;
+    if (!tmpl_off || !tmpl_len || !lag0 || !nlags || !d_diff_out || !d_idx_out) SB_FAIL(SB_EINVAL, "sb_find_batch_device: NULL array");
+    return run_batch(image, tmpl, count, tmpl_off, tmpl_len, lag0, nlags, d_diff_out, d_idx_out, nullptr);
+}
+
+int sb_find(const sb_stream* image, const void* tmpl_host, int64_t tmpl_len,
+            int64_t lag0, int64_t nlags, float* diff_out, int64_t* idx_out) {
+    Ctx& c = ctx();
+    if (!c.inited) SB_FAIL(SB_ESTATE, "sb_find: library not initialised (call sb_init)");
+    if (!image || !tmpl_host) SB_FAIL(SB_EINVAL, "sb_find: NULL argument");
+    sb_stream* t = nullptr;
+    SB_TRY(sb_stream_create(tmpl_host, tmpl_len, image->dtype, &t));
+    const int64_t zero = 0;
+    int rc = sb_find_batch(image, t, 1, &zero, &tmpl_len, &lag0, &nlags, diff_out, idx_out);
+    sb_stream_destroy(t);
+    return rc;
+}
+
+int sb_match_curve(const sb_stream* image, const sb_stream* tmpl,
+                   int64_t tmpl_off, int64_t tmpl_len, int64_t lag0, int64_t nlags,
+                   float* curve_out) {
+    SB_TRY(check_common("sb_match_curve", image, tmpl, 1));
+    if (!curve_out) SB_FAIL(SB_EINVAL, "sb_match_curve: NULL output");
+    if (nlags < 1) SB_FAIL(SB_EINVAL, "sb_match_curve: nlags < 1");
+    Ctx& c = ctx();
+    float* d_curve = nullptr; float* d_diff = nullptr; int64_t* d_idx = nullptr;
+    SB_CUDA(cudaMalloc(&d_curve, sizeof(float) * nlags));
+    SB_CUDA(cudaMalloc(&d_diff, sizeof(float)));
+    SB_CUDA(cudaMalloc(&d_idx, sizeof(int64_t)));
+    int rc = run_batch(image, tmpl, 1, &tmpl_off, &tmpl_len, &lag0, &nlags, d_diff, d_idx, d_curve);
+    if (rc == SB_OK) {
+        cudaError_t e = cudaMemcpyAsync(curve_out, d_curve, sizeof(float) * nlags, cudaMemcpyDeviceToHost, c.stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c.stream);
+        if (e != cudaSuccess) { set_error("sb_match_curve: D2H: %s", cudaGetErrorString(e)); rc = SB_ECUDA; }
+    }
+    cudaStreamSynchronize(c.stream);
+    cudaFree(d_curve); cudaFree(d_diff); cudaFree(d_idx);
+    return rc;
+}
+
+}  // extern "C"

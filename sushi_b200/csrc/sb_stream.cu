@@ -1,0 +1,288 @@
+// Resident streams: upload, running sums (the integral image OpenCV rebuilds on
+// every matchTemplate call, reference wav.py:185), and the per-stream block
+// spectra that every query against the stream shares.
+#include "sb_internal.h"
+
+using namespace sb;
+
+namespace {
+
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 16;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;   // 4096 samples per CTA
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Phase A: per-tile totals of x and x^2 in fp64 (exact integers for u8 input).
+template <typename T>
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_tile_totals(const T* __restrict__ x, int64_t n, double* __restrict__ tsum, double* __restrict__ tsq) {
+    __shared__ double s_a[SCAN_THREADS / 32], s_b[SCAN_THREADS / 32];
+    const int64_t base = (int64_t)blockIdx.x * SCAN_TILE;
+    double a = 0.0, b = 0.0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        int64_t j = base + (int64_t)i * SCAN_THREADS + threadIdx.x;   // coalesced
+        if (j < n) { double v = (double)x[j]; a += v; b += v * v; }
+    }
+    a = warp_sum(a); b = warp_sum(b);
+    if ((threadIdx.x & 31) == 0) { s_a[threadIdx.x >> 5] = a; s_b[threadIdx.x >> 5] = b; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double ta = 0.0, tb = 0.0;
+        for (int w = 0; w < SCAN_THREADS / 32; ++w) { ta += s_a[w]; tb += s_b[w]; }
+        tsum[blockIdx.x] = ta; tsq[blockIdx.x] = tb;
+    }
+}
+
+// Phase B: exclusive scan of the tile totals (one CTA walks them in 1024-wide slabs).
+__global__ void __launch_bounds__(1024)
+k_scan_tile_totals(double* __restrict__ tsum, double* __restrict__ tsq, int64_t ntiles) {
+    __shared__ double s_a[32], s_b[32];
+    __shared__ double carry_a, carry_b;
+    if (threadIdx.x == 0) { carry_a = 0.0; carry_b = 0.0; }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int64_t base = 0; base < ntiles; base += 1024) {
+        int64_t j = base + threadIdx.x;
+        double a = j < ntiles ? tsum[j] : 0.0, b = j < ntiles ? tsq[j] : 0.0;
+        double ia = a, ib = b;                          // inclusive warp scan
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            double ta = __shfl_up_sync(0xffffffffu, ia, o), tb = __shfl_up_sync(0xffffffffu, ib, o);
+            if (lane >= o) { ia += ta; ib += tb; }
+        }
+        if (lane == 31) { s_a[warp] = ia; s_b[warp] = ib; }
+        __syncthreads();
+        if (warp == 0) {
+            double wa = s_a[lane], wb = s_b[lane];
+            double xa = wa, xb = wb;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                double ta = __shfl_up_sync(0xffffffffu, xa, o), tb = __shfl_up_sync(0xffffffffu, xb, o);
+                if (lane >= o) { xa += ta; xb += tb; }
+            }
+            s_a[lane] = xa - wa; s_b[lane] = xb - wb;   // exclusive warp offsets
+        }
+        __syncthreads();
+        double ea = carry_a + s_a[warp] + (ia - a), eb = carry_b + s_b[warp] + (ib - b);
+        if (j < ntiles) { tsum[j] = ea; tsq[j] = eb; }
+        __syncthreads();
+        if (threadIdx.x == 1023) { carry_a = ea + a; carry_b = eb + b; }
+        __syncthreads();
+    }
+}
+
+// Phase C: in-tile inclusive scan + tile offset -> psum[i+1], psq[i+1].
+// Thread t owns SCAN_ITEMS consecutive samples (vector load for u8).
+template <typename T>
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_tile_scan(const T* __restrict__ x, int64_t n, const double* __restrict__ osum, const double* __restrict__ osq,
+            double* __restrict__ psum, double* __restrict__ psq) {
+    __shared__ double s_a[SCAN_THREADS / 32], s_b[SCAN_THREADS / 32];
+    const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+    double va[SCAN_ITEMS], vb[SCAN_ITEMS];
+    double a = 0.0, b = 0.0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        int64_t j = base + i;
+        double v = j < n ? (double)x[j] : 0.0;
+        a += v; b += v * v;
+        va[i] = a; vb[i] = b;
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double ia = a, ib = b;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        double ta = __shfl_up_sync(0xffffffffu, ia, o), tb = __shfl_up_sync(0xffffffffu, ib, o);
+        if (lane >= o) { ia += ta; ib += tb; }
+    }
+    if (lane == 31) { s_a[warp] = ia; s_b[warp] = ib; }
+    __syncthreads();
+    double wa = 0.0, wb = 0.0;
+    for (int w = 0; w < warp; ++w) { wa += s_a[w]; wb += s_b[w]; }
+    const double offa = osum[blockIdx.x] + wa + (ia - a);
+    const double offb = osq[blockIdx.x] + wb + (ib - b);
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        int64_t j = base + i;
+        if (j < n) { psum[j + 1] = offa + va[i]; psq[j + 1] = offb + vb[i]; }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { psum[0] = 0.0; psq[0] = 0.0; }
+}
+
+// Centred float rows for the block spectra: row k holds image[kB .. kB+2B) - c,
+// zero beyond the end of the stream; rows are (2B+2) floats apart (in-place R2C).
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_gather_blocks(const T* __restrict__ x, int64_t n, int B, float c, float* __restrict__ rows,
+                int64_t k_first, int chunks_per_row) {
+    const int64_t row = blockIdx.x / chunks_per_row;
+    const int chunk = blockIdx.x % chunks_per_row;
+    const int64_t k = k_first + row;
+    float* out = rows + row * (int64_t)(2 * B + 2);
+    const int i0 = chunk * 2048 + threadIdx.x * 2;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        int i = i0 + r * 512;
+        if (i < 2 * B) {
+            int64_t j = k * B + i;
+            float2 v;
+            v.x = j < n ? (float)x[j] - c : 0.f;
+            v.y = j + 1 < n ? (float)x[j + 1] - c : 0.f;
+            *reinterpret_cast<float2*>(out + i) = v;
+        }
+    }
+}
+
+template <typename T>
+int build_prefix(sb_stream* s) {
+    Ctx& c = ctx();
+    const int64_t n = s->n;
+    const int64_t ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    double* d_t = nullptr;
+    SB_CUDA(cudaMalloc(&d_t, sizeof(double) * 2 * ntiles));
+    double* tsum = d_t; double* tsq = d_t + ntiles;
+    const T* x = static_cast<const T*>(s->d_raw);
+    {
+        ProfScope ps("scan_tile_totals");
+        k_tile_totals<T><<<(unsigned)ntiles, SCAN_THREADS, 0, c.stream>>>(x, n, tsum, tsq);
+    }
+    {
+        ProfScope ps("scan_tile_offsets");
+        k_scan_tile_totals<<<1, 1024, 0, c.stream>>>(tsum, tsq, ntiles);
+    }
+    {
+        ProfScope ps("scan_tiles");
+        k_tile_scan<T><<<(unsigned)ntiles, SCAN_THREADS, 0, c.stream>>>(x, n, tsum, tsq, s->d_psum, s->d_psq);
+    }
+    SB_CUDA(cudaGetLastError());
+    SB_CUDA(cudaStreamSynchronize(c.stream));
+    cudaFree(d_t);
+    return SB_OK;
+}
+
+int stream_finish(sb_stream* s) {
+    SB_CUDA(cudaMalloc(&s->d_psum, sizeof(double) * (s->n + 1)));
+    SB_CUDA(cudaMalloc(&s->d_psq, sizeof(double) * (s->n + 1)));
+    if (s->dtype == SB_U8) return build_prefix<uint8_t>(s);
+    return build_prefix<float>(s);
+}
+
+int stream_alloc(int64_t n, int dtype, sb_stream** out, const char* who) {
+    Ctx& c = ctx();
+    if (!c.inited) SB_FAIL(SB_ESTATE, "%s: library not initialised (call sb_init)", who);
+    if (!out) SB_FAIL(SB_EINVAL, "%s: NULL output handle", who);
+    if (n < 1) SB_FAIL(SB_EINVAL, "%s: stream length %lld < 1", who, (long long)n);
+    if (dtype != SB_U8 && dtype != SB_F32) SB_FAIL(SB_EINVAL, "%s: unknown dtype %d", who, dtype);
+    sb_stream* s = new (std::nothrow) sb_stream();
+    if (!s) SB_FAIL(SB_ENOMEM, "%s: out of host memory", who);
+    s->n = n; s->dtype = dtype;
+    const size_t esz = dtype == SB_U8 ? 1 : 4;
+    cudaError_t e = cudaMalloc(&s->d_raw, esz * n + 16);
+    if (e != cudaSuccess) { delete s; SB_FAIL(SB_ENOMEM, "%s: cudaMalloc(%lld): %s", who, (long long)(esz * n), cudaGetErrorString(e)); }
+    *out = s;
+    return SB_OK;
+}
+
+}  // namespace
+
+namespace sb {
+
+// Build (or fetch) the block spectra of `s` for the current block size.
+int ensure_spectra(sb_stream* s) {
+    Ctx& c = ctx();
+    if (s->d_spec && s->specB == c.B) return SB_OK;
+    if (s->d_spec) { cudaStreamSynchronize(c.stream); cudaFree(s->d_spec); s->d_spec = nullptr; }
+    const int B = c.B;
+    const int64_t nblk = (s->n + B - 1) / B;
+    SB_CUDA(cudaMalloc(&s->d_spec, sizeof(float2) * (size_t)nblk * (B + 1)));
+    const int chunks = (2 * B + 2047) / 2048;
+    const int64_t sub = 1024;                        // rows per cuFFT call
+    for (int64_t k = 0; k < nblk; k += sub) {
+        const int64_t rows = (nblk - k) < sub ? (nblk - k) : sub;
+        float* dst = reinterpret_cast<float*>(s->d_spec + k * (B + 1));
+        {
+            ProfScope ps("gather_blocks");
+            if (s->dtype == SB_U8)
+                k_gather_blocks<uint8_t><<<(unsigned)(rows * chunks), 256, 0, c.stream>>>(
+                    static_cast<const uint8_t*>(s->d_raw), s->n, B, 128.f, dst, k, chunks);
+            else
+                k_gather_blocks<float><<<(unsigned)(rows * chunks), 256, 0, c.stream>>>(
+                    static_cast<const float*>(s->d_raw), s->n, B, 0.5f, dst, k, chunks);
+        }
+        cufftHandle plan;
+        SB_TRY(get_plan(CUFFT_R2C, rows, &plan));
+        {
+            ProfScope ps("cufft_r2c_blocks", 0);
+            SB_CUFFT(cufftExecR2C(plan, dst, reinterpret_cast<cufftComplex*>(dst)));
+        }
+    }
+    SB_CUDA(cudaGetLastError());
+    s->specB = B; s->nblk = nblk;
+    return SB_OK;
+}
+
+}  // namespace sb
+
+extern "C" {
+
+int sb_stream_create(const void* host_samples, int64_t n, int dtype, sb_stream** out) {
+    if (!host_samples) SB_FAIL(SB_EINVAL, "sb_stream_create: NULL samples");
+    SB_TRY(stream_alloc(n, dtype, out, "sb_stream_create"));
+    sb_stream* s = *out;
+    Ctx& c = ctx();
+    const size_t esz = dtype == SB_U8 ? 1 : 4;
+    cudaError_t e = cudaMemcpyAsync(s->d_raw, host_samples, esz * n, cudaMemcpyHostToDevice, c.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c.stream);
+    if (e != cudaSuccess) { sb_stream_destroy(s); *out = nullptr; SB_FAIL(SB_ECUDA, "sb_stream_create: H2D copy: %s", cudaGetErrorString(e)); }
+    int rc = stream_finish(s);
+    if (rc != SB_OK) { sb_stream_destroy(s); *out = nullptr; }
+    return rc;
+}
+
+int sb_stream_create_device(const void* dev_samples, int64_t n, int dtype, sb_stream** out) {
+    if (!dev_samples) SB_FAIL(SB_EINVAL, "sb_stream_create_device: NULL samples");
+    SB_TRY(stream_alloc(n, dtype, out, "sb_stream_create_device"));
+    sb_stream* s = *out;
+    Ctx& c = ctx();
+    const size_t esz = dtype == SB_U8 ? 1 : 4;
+    cudaError_t e = cudaMemcpyAsync(s->d_raw, dev_samples, esz * n, cudaMemcpyDeviceToDevice, c.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c.stream);
+    if (e != cudaSuccess) { sb_stream_destroy(s); *out = nullptr; SB_FAIL(SB_ECUDA, "sb_stream_create_device: D2D copy: %s", cudaGetErrorString(e)); }
+    int rc = stream_finish(s);
+    if (rc != SB_OK) { sb_stream_destroy(s); *out = nullptr; }
+    return rc;
+}
+
+int sb_stream_destroy(sb_stream* s) {
+    if (!s) return SB_OK;
+    Ctx& c = ctx();
+    if (c.inited) cudaStreamSynchronize(c.stream);
+    cudaFree(s->d_raw); cudaFree(s->d_psum); cudaFree(s->d_psq); cudaFree(s->d_spec);
+    delete s;
+    return SB_OK;
+}
+
+const void* sb_stream_device_ptr(const sb_stream* s) { return s ? s->d_raw : nullptr; }
+int64_t sb_stream_length(const sb_stream* s) { return s ? s->n : -1; }
+int sb_stream_dtype(const sb_stream* s) { return s ? s->dtype : -1; }
+
+int sb_stream_read(const sb_stream* s, int64_t off, int64_t n, void* host_out) {
+    Ctx& c = ctx();
+    if (!c.inited) SB_FAIL(SB_ESTATE, "sb_stream_read: library not initialised");
+    if (!s || !host_out) SB_FAIL(SB_EINVAL, "sb_stream_read: NULL argument");
+    if (off < 0 || n < 0 || off + n > s->n) SB_FAIL(SB_EINVAL, "sb_stream_read: range [%lld,+%lld) outside stream of %lld",
+                                                     (long long)off, (long long)n, (long long)s->n);
+    const size_t esz = s->dtype == SB_U8 ? 1 : 4;
+    SB_CUDA(cudaMemcpyAsync(host_out, static_cast<const char*>(s->d_raw) + esz * off, esz * n,
+                            cudaMemcpyDeviceToHost, c.stream));
+    SB_CUDA(cudaStreamSynchronize(c.stream));
+    return SB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,441 @@
+"""Drop-in replacement for the reference's audio stream class (reference wav.py:104-188).
+
+Same constructor, attributes and methods as the reference ``WavStream`` so that
+``sushi.py``'s ``calculate_shifts`` (sushi.py:400-508) runs unchanged on top of it:
+
+    WavStream(path, sample_rate=12000, sample_type='uint8')        wav.py:108
+    .data .sample_rate .sample_count .padding_size .duration_seconds
+    .get_substream(start, end)                  -> ndarray view     wav.py:168-171
+    .find_substream(pattern, center, window)    -> (np.float32, float)   wav.py:177-188
+
+The arithmetic of find_substream -- OpenCV's matchTemplate(TM_SQDIFF_NORMED) and
+the argmin -- runs on the GPU behind the C ABI in include/sushi_b200.h.  All time ->
+sample conversions stay here, in Python, written exactly as the reference writes
+them, so the integer offsets handed to the library are bit-identical.
+"""
+import ctypes
+import logging
+import math
+import os
+import struct
+import weakref
+from time import time
+
+import numpy as np
+
+from . import _native
+from .common import SushiError, clip
+
+WAVE_FORMAT_PCM = 0x0001
+WAVE_FORMAT_EXTENSIBLE = 0xFFFE
+
+_DTYPES = {'uint8': (np.uint8, _native.SB_U8), 'float32': (np.float32, _native.SB_F32)}
+
+# live streams, so that a pattern that is a *view* of some stream's .data (what
+# get_substream / np.split return, sushi.py:417,445) is recognised and handed to the
+# GPU as an (offset, length) descriptor instead of being uploaded again.
+_live_streams = weakref.WeakSet()
+
+
+class DownmixedWavFile(object):
+    """RIFF/WAVE reader + int16/int24 decode + channel averaging (wav.py:15-101).
+
+    Header walking stays on the host (survey row a10); decode/downmix of the PCM
+    payload is done by ``readframes`` on the host for the streaming loader and by
+    the GPU loader kernels for whole-file loads.
+    """
+
+    def __init__(self, path):
+        self._file = open(path, 'rb')
+        self.channels_count = self.framerate = self.sample_width = self.frame_size = None
+        self.frames_count = None
+        try:
+            head = self._file.read(12)
+            if len(head) < 12 or head[0:4] != b'RIFF':
+                raise SushiError('File does not start with RIFF id')
+            if head[8:12] != b'WAVE':
+                raise SushiError('Not a WAVE file')
+            file_size = os.path.getsize(path)
+            have_fmt = have_data = False
+            while True:
+                hdr = self._file.read(8)
+                if len(hdr) < 8:
+                    break
+                name, size = hdr[0:4], struct.unpack('<L', hdr[4:8])[0]
+                if name == b'fmt ':
+                    self._read_fmt_chunk(self._file.read(size + (size & 1)))
+                    have_fmt = True
+                    continue
+                if name == b'data':
+                    if file_size > 0xFFFFFFFF:
+                        # >4 GiB "broken" wav: trust the file size, not the 32-bit chunk size (wav.py:42-44)
+                        self.frames_count = (file_size - self._file.tell()) // self.frame_size
+                    else:
+                        self.frames_count = size // self.frame_size
+                    self.data_offset = self._file.tell()
+                    have_data = True
+                    break
+                self._file.seek(size + (size & 1), os.SEEK_CUR)
+            if not have_fmt or not have_data:
+                raise SushiError('Invalid WAV file')
+        except Exception:
+            self.close()
+            raise
+
+    def __del__(self):
+        self.close()
+
+    def close(self):
+        f = getattr(self, '_file', None)
+        if f:
+            f.close()
+            self._file = None
+
+    def _read_fmt_chunk(self, payload):
+        tag, self.channels_count, self.framerate, _, _ = struct.unpack('<HHLLH', payload[:14])
+        if tag not in (WAVE_FORMAT_PCM, WAVE_FORMAT_EXTENSIBLE):
+            raise SushiError('unknown format: {0}'.format(tag))
+        bits = struct.unpack('<H', payload[14:16])[0]
+        self.sample_width = (bits + 7) // 8
+        self.frame_size = self.channels_count * self.sample_width
+
+    def read_raw(self, count):
+        return self._file.read(count * self.frame_size)
+
+    def readframes(self, count):
+        """Decode `count` frames to mono float32 (wav.py:64-91)."""
+        if not count:
+            return np.zeros(0, np.float32)
+        return decode_downmix(self.read_raw(count), self.sample_width, self.channels_count)
+
+
+def decode_downmix(raw, sample_width, channels):
+    """bytes -> float32 mono; int24 keeps the top 16 bits (wav.py:68-74); channels are
+    summed left to right in float32, then divided (wav.py:88-90)."""
+    if sample_width == 2:
+        pcm = np.frombuffer(raw, dtype='<i2', count=len(raw) // 2)
+    elif sample_width == 3:
+        b = np.frombuffer(raw, dtype=np.uint8, count=(len(raw) // 3) * 3).reshape(-1, 3)
+        pcm = (b[:, 1].astype(np.uint16) | (b[:, 2].astype(np.uint16) << 8)).view(np.int16)
+    else:
+        raise SushiError('Unsupported sample width: {0}'.format(sample_width))
+    samples = pcm.astype(np.float32)
+    if channels == 1:
+        return samples
+    frames = len(samples) // channels
+    if frames * channels != len(samples):
+        logging.error("Length of audio channels didn't match. This might result in broken output")
+    acc = samples[0::channels][:frames].copy()
+    for ch in range(1, channels):
+        acc += samples[ch::channels][:frames]
+    acc /= np.float32(channels)
+    return acc
+
+
+def nearest_index_map(n_in, n_out):
+    """Source index of every output sample of cv2.resize(..., INTER_NEAREST) on a
+    (1, n_in) row resized to (1, n_out): floor(x * (1 / (n_out / n_in))) in fp64,
+    clamped to n_in-1 (OpenCV resizeNN; pinned against cv2 in tests)."""
+    inv = 1.0 / (float(n_out) / float(n_in))
+    idx = np.floor(np.arange(n_out, dtype=np.float64) * inv).astype(np.int64)
+    np.minimum(idx, n_in - 1, out=idx)
+    return idx
+
+
+def py2_round(x):
+    """round() as Python 2 does it (half away from zero) -- the reference is py2 code (wav.py:127)."""
+    return math.floor(x + 0.5) if x >= 0 else -math.floor(-x + 0.5)
+
+
+def normalise_host(data, sample_type):
+    """Median-clip normalisation of a padded float32 (1,N) array, in place semantics of
+    wav.py:145-156 (float32 arithmetic throughout, medians over the padded array)."""
+    flat = data.reshape(-1)
+    max_value = np.float32(np.median(flat[flat >= 0])) * np.float32(3)
+    min_value = np.float32(np.median(flat[flat <= 0])) * np.float32(3)
+    np.clip(data, min_value, max_value, out=data)
+    data -= min_value
+    data /= (max_value - min_value)
+    if sample_type == 'uint8':
+        data *= np.float32(255.0)
+        data += np.float32(0.5)
+        data = data.astype(np.uint8)
+    return data, float(min_value), float(max_value)
+
+
+class WavStream(object):
+    READ_CHUNK_SIZE = 1  # seconds per resample chunk (wav.py:105)
+    PADDING_SECONDS = 10
+
+    def __init__(self, path, sample_rate=12000, sample_type='uint8', device=None):
+        if sample_type not in _DTYPES:
+            raise SushiError('Unknown sample type of WAV stream, must be uint8 or float32')
+        self._handle = None
+        before_read = time()
+        stream = DownmixedWavFile(path)
+        try:
+            self._load(stream, sample_rate, sample_type)
+        except SushiError:
+            raise
+        except Exception as e:
+            raise SushiError('Error while loading {0}: {1}'.format(path, e))
+        finally:
+            stream.close()
+        self._upload(device)
+        logging.info('Done reading WAV {0} in {1}s'.format(path, time() - before_read))
+
+    # -- construction -----------------------------------------------------------------
+    def _load(self, stream, sample_rate, sample_type):
+        framerate = stream.framerate
+        total_seconds = stream.frames_count / float(framerate)
+        downsample_rate = sample_rate / float(framerate)
+        self.sample_count = math.ceil(total_seconds * sample_rate)
+        self.sample_rate = sample_rate
+        self.sample_type = sample_type
+        self.padding_size = 10 * framerate          # file-rate samples, as in wav.py:120
+        total = int(self.PADDING_SECONDS * 2 * framerate + self.sample_count)
+        # np.empty in the reference; fresh pages read as zero, so do ours
+        data = np.zeros((1, total), np.float32)
+        chunk_frames = int(self.READ_CHUNK_SIZE * framerate)
+        pos = self.padding_size
+        seconds_read = 0
+        maps = {}
+        while seconds_read < total_seconds:
+            mono = stream.readframes(chunk_frames)
+            new_length = int(py2_round(len(mono) * downsample_rate))
+            if downsample_rate != 1 and len(mono):
+                key = (len(mono), new_length)
+                if key not in maps:
+                    maps[key] = nearest_index_map(*key)
+                mono = mono[maps[key]]
+            data[0, pos:pos + new_length] = mono
+            pos += new_length
+            seconds_read += self.READ_CHUNK_SIZE
+        data[0, 0:self.padding_size] = data[0, self.padding_size]
+        data[0, -self.padding_size:] = data[0, -self.padding_size - 1]
+        self.data, self.min_value, self.max_value = normalise_host(data, sample_type)
+
+    @classmethod
+    def from_pcm(cls, pcm, framerate, sample_rate=12000, sample_type='uint8', channels=1, device=None):
+        """Build a stream from an in-memory int16 array (frames x channels, interleaved) --
+        the same pipeline as a file load without the RIFF walk (synthetic benches/tests)."""
+        class _Mem(object):
+            pass
+        pcm = np.ascontiguousarray(pcm, dtype='<i2')
+        mem = _Mem()
+        mem.framerate, mem.channels_count, mem.sample_width = framerate, channels, 2
+        mem.frame_size = 2 * channels
+        mem.frames_count = pcm.size // channels
+        raw = pcm.reshape(-1).view(np.uint8)
+        state = {'pos': 0}
+
+        def readframes(count):
+            a = state['pos']
+            b = min(a + count * mem.frame_size, raw.size)
+            state['pos'] = b
+            return decode_downmix(raw[a:b].tobytes(), 2, channels)
+        mem.readframes = readframes
+        self = object.__new__(cls)
+        self._handle = None
+        if sample_type not in _DTYPES:
+            raise SushiError('Unknown sample type of WAV stream, must be uint8 or float32')
+        self._load(mem, sample_rate, sample_type)
+        self._upload(device)
+        return self
+
+    @classmethod
+    def from_array(cls, data, sample_rate, padding_size, sample_count, device=None):
+        """Wrap an already-normalised (1,N) uint8/float32 array (what WavStream.data holds)."""
+        data = np.ascontiguousarray(data)
+        if data.ndim != 2 or data.shape[0] != 1 or data.dtype not in (np.uint8, np.float32):
+            raise SushiError('from_array expects a (1,N) uint8 or float32 array')
+        self = object.__new__(cls)
+        self._handle = None
+        self.data = data
+        self.sample_rate = sample_rate
+        self.sample_type = 'uint8' if data.dtype == np.uint8 else 'float32'
+        self.padding_size = int(padding_size)
+        self.sample_count = sample_count
+        self.min_value = self.max_value = None
+        self._upload(device)
+        return self
+
+    @classmethod
+    def from_device(cls, dev_ptr, n, sample_type, sample_rate, padding_size, sample_count, host_mirror=None, device=None):
+        """Wrap n normalised samples that already sit in GPU memory (e.g. an NCCL broadcast buffer);
+        they are copied device-to-device into a library-owned stream.  `host_mirror` optionally
+        provides .data for get_substream views; without it only the planned/batched calls work."""
+        self = object.__new__(cls)
+        self._handle = None
+        self.data = host_mirror
+        self.sample_rate = sample_rate
+        self.sample_type = sample_type
+        self.padding_size = int(padding_size)
+        self.sample_count = sample_count
+        self.min_value = self.max_value = None
+        lib = _native.lib(device)
+        h = ctypes.c_void_p()
+        _native.check(lib.sb_stream_create_device(ctypes.c_void_p(int(dev_ptr)), int(n), _DTYPES[sample_type][1],
+                                                  ctypes.byref(h)), 'sb_stream_create_device')
+        self._handle = h
+        self._lib = lib
+        self._base = host_mirror.__array_interface__['data'][0] if host_mirror is not None else 0
+        if host_mirror is not None:
+            _live_streams.add(self)
+        return self
+
+    @property
+    def device_ptr(self):
+        return self._lib.sb_stream_device_ptr(self._handle)
+
+    def find_planned_device(self, src_stream, toff, tlen, lag0, nlags, d_diff_ptr, d_idx_ptr):
+        """Enqueue a planned batch; results (float32[count], int64[count]) land in device memory."""
+        arrs = [np.ascontiguousarray(x, dtype=np.int64) for x in (toff, tlen, lag0, nlags)]
+        _native.check(self._lib.sb_find_batch_device(
+            self._handle, src_stream._handle, len(arrs[0]),
+            *[x.ctypes.data_as(_native.c_i64p) for x in arrs],
+            ctypes.c_void_p(int(d_diff_ptr)), ctypes.c_void_p(int(d_idx_ptr))), 'sb_find_batch_device')
+
+    def _upload(self, device):
+        lib = _native.lib(device)
+        h = ctypes.c_void_p()
+        _native.check(lib.sb_stream_create(self.data.ctypes.data_as(ctypes.c_void_p), self.data.shape[1],
+                                           _DTYPES[self.sample_type][1], ctypes.byref(h)), 'sb_stream_create')
+        self._handle = h
+        self._lib = lib
+        self._base = self.data.__array_interface__['data'][0]
+        _live_streams.add(self)
+
+    def close(self):
+        if getattr(self, '_handle', None) is not None and self._handle:
+            self._lib.sb_stream_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- the reference's surface ----------------------------------------------------------
+    @property
+    def duration_seconds(self):
+        return self.sample_count / self.sample_rate
+
+    def _get_sample_for_time(self, timestamp):
+        # REAL sample for a time, padding included (wav.py:173-175); int() truncates toward zero
+        return int(self.sample_rate * timestamp) + self.padding_size
+
+    def get_substream(self, start, end):
+        start_off = self._get_sample_for_time(start)
+        end_off = self._get_sample_for_time(end)
+        return self.data[:, start_off:end_off]
+
+    def _window(self, pattern_len, window_center, window_size):
+        """Integer search span of one find_substream call: (start_time, first sample, sample count)."""
+        start_time = clip(window_center - window_size, -self.PADDING_SECONDS, self.duration_seconds)
+        end_time = clip(window_center + window_size, 0, self.duration_seconds + self.PADDING_SECONDS)
+        start_sample = self._get_sample_for_time(start_time)
+        end_sample = self._get_sample_for_time(end_time) + pattern_len
+        lo, hi, _ = slice(start_sample, end_sample).indices(self.data.shape[1])   # numpy slice rules (wav.py:184)
+        return start_time, lo, max(hi - lo, 0)
+
+    def _locate(self, pattern):
+        """(stream, offset) if `pattern` is a contiguous view into a live stream's .data, else None."""
+        if not isinstance(pattern, np.ndarray) or pattern.ndim != 2 or pattern.shape[0] != 1:
+            return None
+        if pattern.shape[1] > 1 and pattern.strides[1] != pattern.itemsize:
+            return None
+        addr = pattern.__array_interface__['data'][0]
+        for s in _live_streams:
+            if s._handle and s.data.dtype == pattern.dtype:
+                off = addr - s._base
+                if 0 <= off and off + pattern.nbytes <= s.data.nbytes and off % s.data.itemsize == 0:
+                    return s, off // s.data.itemsize
+        return None
+
+    def find_substream(self, pattern, window_center, window_size):
+        n = len(pattern[0])
+        if pattern.dtype != self.data.dtype:
+            raise SushiError('pattern dtype {0} does not match stream dtype {1}'.format(pattern.dtype, self.data.dtype))
+        start_time, lo, span = self._window(n, window_center, window_size)
+        if n < 1 or span < 1:
+            raise SushiError('find_substream: empty pattern or empty search span')
+        diff = ctypes.c_float()
+        idx = ctypes.c_int64()
+        where = self._locate(pattern)
+        if span >= n:
+            if where is not None:
+                src, off = where
+                a = (ctypes.c_int64 * 4)(off, n, lo, span - n + 1)
+                _native.check(self._lib.sb_find_batch(
+                    self._handle, src._handle, 1,
+                    ctypes.cast(ctypes.byref(a, 0), _native.c_i64p), ctypes.cast(ctypes.byref(a, 8), _native.c_i64p),
+                    ctypes.cast(ctypes.byref(a, 16), _native.c_i64p), ctypes.cast(ctypes.byref(a, 24), _native.c_i64p),
+                    ctypes.byref(diff), ctypes.byref(idx)), 'sb_find_batch')
+            else:
+                pat = np.ascontiguousarray(pattern[0])
+                _native.check(self._lib.sb_find(self._handle, pat.ctypes.data_as(ctypes.c_void_p), n, lo,
+                                                span - n + 1, ctypes.byref(diff), ctypes.byref(idx)), 'sb_find')
+        else:
+            # search span shorter than the pattern: cv2.matchTemplate silently swaps image and
+            # template (survey appendix A); mirror that instead of failing
+            if where is None:
+                tmp = WavStream.from_array(np.ascontiguousarray(pattern), self.sample_rate, 0, n)
+                src, off = tmp, 0
+            else:
+                src, off = where
+            a = (ctypes.c_int64 * 4)(lo, span, off, n - span + 1)
+            _native.check(self._lib.sb_find_batch(
+                src._handle, self._handle, 1,
+                ctypes.cast(ctypes.byref(a, 0), _native.c_i64p), ctypes.cast(ctypes.byref(a, 8), _native.c_i64p),
+                ctypes.cast(ctypes.byref(a, 16), _native.c_i64p), ctypes.cast(ctypes.byref(a, 24), _native.c_i64p),
+                ctypes.byref(diff), ctypes.byref(idx)), 'sb_find_batch')
+        return np.float32(diff.value), start_time + (idx.value / float(self.sample_rate))
+
+    # -- batched surface (what the sharded benchmark and the batched shift solver use) ------
+    def plan_queries(self, src_stream, starts, ends, centers, windows):
+        """Integer descriptors of many find_substream calls at once.
+
+        Query q searches src_stream.get_substream(starts[q], ends[q]) in this stream around
+        centers[q] +- windows[q].  Returns (tmpl_off, tmpl_len, lag0, nlags, start_times) as
+        int64/float64 arrays, computed with the same scalar code as find_substream.
+        """
+        count = len(starts)
+        toff = np.empty(count, np.int64); tlen = np.empty(count, np.int64)
+        lag0 = np.empty(count, np.int64); nlags = np.empty(count, np.int64)
+        t0 = np.empty(count, np.float64)
+        total_src = src_stream.data.shape[1]
+        for q in range(count):
+            a, b, _ = slice(src_stream._get_sample_for_time(starts[q]),
+                            src_stream._get_sample_for_time(ends[q])).indices(total_src)
+            n = max(b - a, 0)
+            st, lo, span = self._window(n, centers[q], windows[q])
+            if n < 1 or span < n:
+                raise SushiError('query {0}: pattern of {1} samples does not fit its search span of {2}'.format(q, n, span))
+            toff[q], tlen[q], lag0[q], nlags[q], t0[q] = a, n, lo, span - n + 1, st
+        return toff, tlen, lag0, nlags, t0
+
+    def find_substream_batch(self, src_stream, starts, ends, centers, windows):
+        """Batched find_substream: returns (diffs float32[count], times float64[count])."""
+        toff, tlen, lag0, nlags, t0 = self.plan_queries(src_stream, starts, ends, centers, windows)
+        diff, idx = self.find_planned(src_stream, toff, tlen, lag0, nlags)
+        return diff, t0 + idx / float(self.sample_rate)
+
+    def find_planned(self, src_stream, toff, tlen, lag0, nlags):
+        count = len(toff)
+        diff = np.empty(count, np.float32)
+        idx = np.empty(count, np.int64)
+        arrs = [np.ascontiguousarray(x, dtype=np.int64) for x in (toff, tlen, lag0, nlags)]
+        _native.check(self._lib.sb_find_batch(
+            self._handle, src_stream._handle, count,
+            *[x.ctypes.data_as(_native.c_i64p) for x in arrs],
+            diff.ctypes.data_as(_native.c_f32p), idx.ctypes.data_as(_native.c_i64p)), 'sb_find_batch')
+        return diff, idx
+
+    def match_curve(self, src_stream, toff, tlen, lag0, nlags):
+        """Whole TM_SQDIFF_NORMED curve of one query (parity tests / debugging)."""
+        out = np.empty(int(nlags), np.float32)
+        _native.check(self._lib.sb_match_curve(self._handle, src_stream._handle, int(toff), int(tlen), int(lag0),
+                                               int(nlags), out.ctypes.data_as(_native.c_f32p)), 'sb_match_curve')
+        return out

@@ -1,0 +1,216 @@
+"""GPU parity proper: the CUDA path, called through the C ABI, against (1) the reference's frozen
+golden outputs, (2) the oracle (live cv2) on the same seeded inputs, (3) known answers and
+size-independent properties at BASELINE sizes.  Tolerances are north_star's: shift within +-1
+destination sample (1/12000 s), diff within 1e-5."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from sushi_b200 import WavStream, SushiError, synth, _native
+from tests.helpers import oracle_stream_from_pcm
+
+pytestmark = pytest.mark.gpu
+
+SHIFT_TOL = 1.0 / 12000 + 1e-9
+DIFF_TOL = 1e-5
+
+
+def gpu_stream_like(ref):
+    return WavStream.from_array(ref.data, ref.sample_rate, ref.padding_size, ref.sample_count)
+
+
+@pytest.fixture(scope='module')
+def pair(golden_matcher):
+    out = {}
+    for stype in ('uint8', 'float32'):
+        rs = oracle_stream_from_pcm(golden_matcher['src_pcm'], 12000, 1, 12000, stype)
+        rd = oracle_stream_from_pcm(golden_matcher['dst_pcm'], 12000, 1, 12000, stype)
+        out[stype] = (rs, rd, gpu_stream_like(rs), gpu_stream_like(rd))
+    return out
+
+
+@pytest.mark.parametrize('stype', ['uint8', 'float32'])
+def test_find_substream_matches_reference_golden(gpu_lib, golden_matcher, pair, stype):
+    g = golden_matcher
+    _, _, src, dst = pair[stype]
+    for q, (a, b, c, w) in enumerate(g['queries']):
+        d, t = dst.find_substream(src.get_substream(a, b), c, w)
+        assert isinstance(d, np.float32) and isinstance(t, float)
+        assert abs(float(d) - float(g['diff_' + stype][q])) <= DIFF_TOL, (q, d, g['diff_' + stype][q])
+        assert abs(t - g['time_' + stype][q]) <= SHIFT_TOL, (q, t, g['time_' + stype][q])
+
+
+@pytest.mark.parametrize('stype', ['uint8', 'float32'])
+def test_whole_curve_matches_reference_golden(gpu_lib, golden_matcher, pair, stype):
+    g = golden_matcher
+    _, _, src, dst = pair[stype]
+    for qi in (0, 2):
+        a, b, c, w = g['queries'][qi]
+        s0, s1, stride = [int(v) for v in g['curve{0}_{1}_s0'.format(qi, stype)]]
+        toff = src._get_sample_for_time(a)
+        n = src._get_sample_for_time(b) - toff
+        curve = dst.match_curve(src, toff, n, s0, s1 - s0 - n + 1)
+        want = g['curve{0}_{1}'.format(qi, stype)]
+        assert np.abs(curve[::stride] - want).max() <= DIFF_TOL
+        assert abs(int(curve.argmin()) - int(want.argmin()) * stride) <= stride
+
+
+@pytest.mark.parametrize('stype', ['uint8', 'float32'])
+@pytest.mark.parametrize('block', [1024, 4096, 16384])
+def test_live_oracle_random_queries(gpu_lib, pair, stype, block):
+    """Random (event, centre, window) queries: GPU vs the oracle's cv2 call, for several lag-block
+    sizes (every size must give the same answer: values do not depend on the blocking)."""
+    rs, rd, src, dst = pair[stype]
+    _native.check(gpu_lib.sb_set_block_size(block))
+    try:
+        rng = np.random.default_rng(block)
+        for _ in range(12):
+            a = float(rng.uniform(0.0, 20.0))
+            ln = float(rng.choice([0.05, 0.5, 1.0, 3.0, 3.9]))
+            b = min(a + ln, 24.0)
+            c = float(a + rng.uniform(-3, 3))
+            w = float(rng.choice([0.3, 1.5, 5.0, 10.0, 30.0]))
+            pat_ref = rs.get_substream(a, b)
+            d_ref, t_ref = rd.find_substream(pat_ref, c, w)
+            d, t = dst.find_substream(src.get_substream(a, b), c, w)
+            assert abs(float(d) - float(d_ref)) <= DIFF_TOL, (a, b, c, w)
+            assert abs(t - t_ref) <= SHIFT_TOL, (a, b, c, w, t, t_ref)
+    finally:
+        _native.check(gpu_lib.sb_set_block_size(16384))
+
+
+def test_raw_ndarray_pattern_and_halves(gpu_lib, pair):
+    """pattern may be any (1,n) ndarray: np.split halves (sushi.py:445) and detached copies."""
+    rs, rd, src, dst = pair['uint8']
+    tv = src.get_substream(6.1, 7.05)
+    left, right = np.split(tv, [len(tv[0]) // 2], axis=1)
+    tv_r = rs.get_substream(6.1, 7.05)
+    left_r, right_r = np.split(tv_r, [len(tv_r[0]) // 2], axis=1)
+    for p, pr in ((left, left_r), (right, right_r), (tv.copy(), tv_r)):
+        d, t = dst.find_substream(p, 7.6, 10.0)
+        d_ref, t_ref = rd.find_substream(pr, 7.6, 10.0)
+        assert abs(float(d) - float(d_ref)) <= DIFF_TOL and abs(t - t_ref) <= SHIFT_TOL
+
+
+def test_degenerate_inputs(gpu_lib, golden_matcher):
+    """Zero-energy windows, zero template, constants, periodic ties."""
+    g = golden_matcher
+    mk = lambda arr: WavStream.from_array(np.ascontiguousarray(arr), 12000, 0, arr.shape[1])
+    z = mk(np.zeros((1, 64), np.uint8))
+    seven = mk(np.full((1, 8), 7, np.uint8))
+    nine = mk(np.full((1, 64), 9, np.uint8))
+    ramp = mk((np.arange(64) % 8).astype(np.uint8)[None, :])
+    assert np.array_equal(z.match_curve(seven, 0, 8, 0, 57), g['deg_zero_window'])
+    assert np.array_equal(nine.match_curve(z, 0, 8, 0, 57), g['deg_zero_template'])
+    assert np.abs(nine.match_curve(seven, 0, 8, 0, 57) - g['deg_const_7_vs_9']).max() <= 1e-6
+    cur = ramp.match_curve(ramp, 0, 16, 0, 49)
+    assert np.abs(cur - g['deg_periodic']).max() <= 1e-6
+    diff, idx = ramp.find_planned(ramp, [0], [16], [0], [49])
+    assert idx[0] == 0 and diff[0] == 0.0            # FIRST of the equal minima
+    # exact copy -> 0 at the right place
+    diff, idx = ramp.find_planned(ramp, [8], [24], [0], [41])
+    assert diff[0] == 0.0 and idx[0] == 0
+
+
+def test_search_span_shorter_than_pattern_swaps_like_cv2(gpu_lib, pair):
+    rs, rd, src, dst = pair['uint8']
+    # 12 s pattern near the end of a 24 s stream with a small window: span < pattern
+    a, b, c, w = 8.0, 23.0, 33.5, 0.2
+    pat_ref = rs.get_substream(a, b)
+    d_ref, t_ref = rd.find_substream(pat_ref, c, w)
+    d, t = dst.find_substream(src.get_substream(a, b), c, w)
+    assert abs(float(d) - float(d_ref)) <= DIFF_TOL and abs(t - t_ref) <= SHIFT_TOL
+
+
+def test_batch_equals_singles_and_is_order_independent(gpu_lib, pair):
+    rs, rd, src, dst = pair['uint8']
+    starts = np.array([1.0, 2.5, 6.0, 9.0, 12.0, 15.5, 18.0])
+    ends = starts + np.array([2.0, 0.7, 3.5, 1.1, 2.2, 3.0, 1.0])
+    centers = starts + 1.5
+    windows = np.array([10.0, 1.5, 10.0, 30.0, 5.0, 10.0, 1.5])
+    diffs, times = dst.find_substream_batch(src, starts, ends, centers, windows)
+    for q in range(len(starts)):
+        d, t = dst.find_substream(src.get_substream(starts[q], ends[q]), centers[q], windows[q])
+        assert d == diffs[q] and t == times[q]
+    perm = np.array([3, 0, 6, 2, 5, 1, 4])
+    d2, t2 = dst.find_substream_batch(src, starts[perm], ends[perm], centers[perm], windows[perm])
+    assert np.array_equal(d2, diffs[perm]) and np.array_equal(t2, times[perm])
+
+
+def test_argument_errors_are_reported(gpu_lib, pair):
+    rs, rd, src, dst = pair['uint8']
+    with pytest.raises(SushiError):
+        dst.find_planned(src, [0], [100], [0], [dst.data.shape[1]])        # span past the end
+    with pytest.raises(SushiError):
+        dst.find_planned(src, [-1], [100], [0], [10])
+    with pytest.raises(SushiError):
+        dst.find_planned(src, [0], [0], [0], [10])
+    _, _, srcf, _ = pair['float32']
+    with pytest.raises(SushiError):
+        dst.find_planned(srcf, [0], [100], [0], [10])                       # dtype mismatch
+    with pytest.raises(SushiError):
+        dst.find_substream(srcf.get_substream(1.0, 2.0), 1.5, 1.0)
+
+
+def test_config1_constant_shift_recovered(gpu_lib):
+    """BASELINE config 1: 100 events, 60 s streams, +1.5 s, +-10 s: every event -> 1.5 s +- 1 sample,
+    and identical to the oracle event by event."""
+    src_pcm, dst_pcm = synth.make_pair(60.0, 0, 1.5)
+    starts, ends = synth.make_events(100, 60.0, 0, 1.0, 4.0)
+    for stype in ('uint8', 'float32'):
+        rs = oracle_stream_from_pcm(src_pcm, 12000, 1, 12000, stype)
+        rd = oracle_stream_from_pcm(dst_pcm, 12000, 1, 12000, stype)
+        src, dst = gpu_stream_like(rs), gpu_stream_like(rd)
+        diffs, times = dst.find_substream_batch(src, starts, ends, starts, np.full(len(starts), 10.0))
+        ok = ends + 1.5 < 60.0
+        assert np.all(np.abs((times - starts)[ok] - 1.5) <= SHIFT_TOL)
+        for q in range(0, len(starts), 7):
+            d_ref, t_ref = rd.find_substream(rs.get_substream(starts[q], ends[q]), starts[q], 10.0)
+            assert abs(float(diffs[q]) - float(d_ref)) <= DIFF_TOL and abs(times[q] - t_ref) <= SHIFT_TOL
+
+
+def test_config2_size_properties(gpu_lib):
+    """BASELINE config 2 shape (2 x 30 min, +-60 s) on a reduced event count: shift recovery as a
+    size-independent property, plus oracle spot checks at full window size."""
+    dur = 1800.0
+    src_pcm, dst_pcm = synth.make_pair(dur, 1, -7.25)
+    src = WavStream.from_pcm(src_pcm, 12000)
+    dst = WavStream.from_pcm(dst_pcm, 12000)
+    starts, ends = synth.make_events(2000, dur, 1)
+    sel = np.arange(0, 2000, 10)
+    diffs, times = dst.find_substream_batch(src, starts[sel], ends[sel], starts[sel], np.full(len(sel), 60.0))
+    ok = (starts[sel] - 7.25 > 0)
+    assert np.all(np.abs((times - starts[sel])[ok] + 7.25) <= SHIFT_TOL)
+    assert np.all(diffs[ok] < 0.2)
+    from oracle.ref_matcher import RefStream
+    rs = RefStream(src.data, 12000, src.padding_size, src.sample_count)
+    rd = RefStream(dst.data, 12000, dst.padding_size, dst.sample_count)
+    for q in (3, 77, 150):
+        e = sel[q]
+        d_ref, t_ref = rd.find_substream(rs.get_substream(starts[e], ends[e]), starts[e], 60.0)
+        assert abs(float(diffs[q]) - float(d_ref)) <= DIFF_TOL and abs(times[q] - t_ref) <= SHIFT_TOL
+
+
+def test_long_template_wide_window(gpu_lib):
+    """config-5 corner: 30 s event, +-600 s span (14.4 M lags, 22 partitions)."""
+    dur = 1500.0
+    src_pcm, dst_pcm = synth.make_pair(dur, 2, 101.0)
+    src = WavStream.from_pcm(src_pcm, 12000)
+    dst = WavStream.from_pcm(dst_pcm, 12000)
+    d, t = dst.find_substream(src.get_substream(700.0, 730.0), 700.0, 600.0)
+    assert abs((t - 700.0) - 101.0) <= SHIFT_TOL
+    from oracle.ref_matcher import RefStream
+    rs = RefStream(src.data, 12000, src.padding_size, src.sample_count)
+    rd = RefStream(dst.data, 12000, dst.padding_size, dst.sample_count)
+    d_ref, t_ref = rd.find_substream(rs.get_substream(700.0, 730.0), 700.0, 600.0)
+    assert abs(float(d) - float(d_ref)) <= DIFF_TOL and abs(t - t_ref) <= SHIFT_TOL
+
+
+def test_running_sums_are_exact_for_uint8(gpu_lib):
+    """A flat stream of 255s, 3 M samples: window energy must be exactly n*255^2 everywhere, so an
+    exact copy gives diff == 0 at lag 0 and the curve is identically 0."""
+    n = 3_000_000
+    s = WavStream.from_array(np.full((1, n), 255, np.uint8), 12000, 0, n)
+    cur = s.match_curve(s, 1_000_000, 50_000, 2_900_000, 50_001)
+    assert np.all(cur == 0.0)
