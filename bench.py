@@ -126,11 +126,31 @@ def _cpu_run(chunk):
     return out
 
 
+def effective_cores():
+    """Host cores this process may actually use: affinity mask capped by the cgroup CPU quota."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+    for path in ('/sys/fs/cgroup/cpu.max', '/sys/fs/cgroup/cpu/cpu.cfs_quota_us'):
+        try:
+            txt = open(path).read().split()
+            if path.endswith('cpu.max'):
+                if txt[0] != 'max':
+                    n = min(n, max(1, int(float(txt[0]) / float(txt[1]))))
+            else:
+                quota = float(txt[0])
+                period = float(open('/sys/fs/cgroup/cpu/cpu.cfs_period_us').read())
+                if quota > 0:
+                    n = min(n, max(1, int(quota / period)))
+            break
+        except (OSError, ValueError, IndexError):
+            continue
+    return n
+
+
 def cpu_events_per_s(src, dst, starts, ends, window, budget_s, cores=None):
     """Throughput of the reference's CPU path on a bounded sample of the workload's events."""
     import multiprocessing as mp
     from oracle.ref_matcher import RefStream
-    cores = cores or os.cpu_count()
+    cores = cores or effective_cores()
     _CPU['src'] = RefStream(src.data, SAMPLE_RATE, src.padding_size, src.sample_count)
     _CPU['dst'] = RefStream(dst.data, SAMPLE_RATE, dst.padding_size, dst.sample_count)
     _cpu_init()

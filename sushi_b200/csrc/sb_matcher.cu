@@ -20,12 +20,24 @@ using namespace sb;
 
 namespace {
 
+// ---- centring constants ---------------------------------------------------------
+// Both operands are centred before the fp32 FFTs (it keeps the transform error relative to
+// the signal's variation instead of its offset): the image stream on a = mean of the whole
+// stream, every template on b = its own mean.  For uint8 data a and b are rounded to
+// integers so the centred samples stay exactly representable; the centring is undone
+// exactly in the normalise kernel from the running sums:
+//     sum(I*T) = sum(I'T') + b*sum(I_w) + a*sum(T) - n*a*b
+template <typename T> __device__ __forceinline__ float centre_of(double sum, double count);
+template <> __device__ __forceinline__ float centre_of<uint8_t>(double sum, double count) { return (float)rint(sum / count); }
+template <> __device__ __forceinline__ float centre_of<float>(double sum, double count) { return (float)(sum / count); }
+
 // ---- template partitions -------------------------------------------------------
 // One CTA chunk writes 2048 floats of one partition row (row stride 2B+2 floats).
 template <typename T>
 __global__ void __launch_bounds__(256)
-k_gather_parts(const T* __restrict__ tmpl, const QueryDesc* __restrict__ desc, int q_begin, int q_end,
-               int64_t part_first, int B, float c, float* __restrict__ rows, int chunks_per_row) {
+k_gather_parts(const T* __restrict__ tmpl, const double* __restrict__ tpsum,
+               const QueryDesc* __restrict__ desc, int q_begin, int q_end,
+               int64_t part_first, int B, float* __restrict__ rows, int chunks_per_row) {
     __shared__ int s_q;
     const int64_t row = blockIdx.x / chunks_per_row;
     const int chunk = blockIdx.x % chunks_per_row;
@@ -37,6 +49,7 @@ k_gather_parts(const T* __restrict__ tmpl, const QueryDesc* __restrict__ desc, i
     }
     __syncthreads();
     const QueryDesc d = desc[s_q];
+    const float b = centre_of<T>(tpsum[d.toff + d.tlen] - tpsum[d.toff], (double)d.tlen);
     const int64_t p = part - d.partBase;
     const int64_t seg0 = p * B;                     // offset of this partition inside the template
     float* out = rows + row * (int64_t)(2 * B + 2);
@@ -46,8 +59,8 @@ k_gather_parts(const T* __restrict__ tmpl, const QueryDesc* __restrict__ desc, i
         int i = i0 + r * 512;
         if (i < 2 * B) {
             float2 v;
-            v.x = (i < B && seg0 + i < d.tlen) ? (float)tmpl[d.toff + seg0 + i] - c : 0.f;
-            v.y = (i + 1 < B && seg0 + i + 1 < d.tlen) ? (float)tmpl[d.toff + seg0 + i + 1] - c : 0.f;
+            v.x = (i < B && seg0 + i < d.tlen) ? (float)tmpl[d.toff + seg0 + i] - b : 0.f;
+            v.y = (i + 1 < B && seg0 + i + 1 < d.tlen) ? (float)tmpl[d.toff + seg0 + i + 1] - b : 0.f;
             *reinterpret_cast<float2*>(out + i) = v;
         }
     }
@@ -111,32 +124,58 @@ k_spectral_mac(const float2* __restrict__ That, int64_t part_first, const float2
 // behaviour pinned by tests/golden): with corr the float32-rounded sum(I*T),
 //   num = max(wnd - 2*corr + tsum2, 0);  t = sqrt(wnd) * sqrt(tsum2)  (t = 0 if wnd is ~0)
 //   out = |num| < t ? num/t : 1           -> float32
+// One rsqrt replaces the sqrt+divide pair: t = p*rsqrt(p), num/t = num*rsqrt(p), p = wnd*tsum2.
 __device__ __forceinline__ float sqdiff_normed(double corr_centred, double wsum, double wsq,
-                                               double c, double tsum, double tsq, double n_c2, double tnorm) {
-    // undo the centring exactly: sum(I*T) = sum(I'T') + c*sum(I_w) + c*sum(T) - n*c^2
-    const double sit = corr_centred + c * wsum + c * tsum - n_c2;
+                                               double a, double b, double tsum, double tsq, double n_ab) {
+    // undo the centring: sum(I*T) = sum(I'T') + b*sum(I_w) + a*sum(T) - n*a*b
+    const double sit = corr_centred + b * wsum + a * tsum - n_ab;
     const double corr = (double)(float)sit;
     double num = wsq - 2.0 * corr + tsq;
     num = fmax(num, 0.0);
-    const double diff2 = fmax(wsq, 0.0);
-    double t = (diff2 <= fmin(0.5, 10.0 * 1.1920928955078125e-07 * wsq)) ? 0.0 : sqrt(diff2) * tnorm;
-    double out = (fabs(num) < t) ? num / t : 1.0;
-    return (float)out;
+    const double p = wsq * tsq;
+    if (!(wsq > 0.0) || wsq <= fmin(0.5, 10.0 * 1.1920928955078125e-07 * wsq) || !(p > 0.0)) return 1.0f;   // t == 0
+    const double r = rsqrt(p);
+    const double t = p * r;
+    return (num < t) ? (float)(num * r) : 1.0f;
 }
 
 __device__ __forceinline__ unsigned long long pack_key(float v, unsigned int rel) {
     return ((unsigned long long)__float_as_uint(v) << 32) | rel;     // v >= 0: bit pattern is monotone
 }
 
+// The per-lag window sums sum(I) and sum(I^2) over [j, j+n) are NOT read from the fp64
+// running-sum arrays (32 B per lag of HBM traffic); each CTA takes one exact base value
+// from them and then slides the window through its lags with a block-wide scan of
+//   delta_j = I[j+n]^k - I[j]^k,  k = 1, 2
+// computed from the raw samples (2 B per lag for uint8).  For uint8 the deltas and their
+// 2048-lag partial sums are exact in int32; for float32 streams the scan runs in fp64.
 constexpr int NORM_THREADS = 256;
-constexpr int NORM_LAGS = 2048;          // lags per CTA
+constexpr int NORM_PER = 8;                          // consecutive lags per thread
+constexpr int NORM_LAGS = NORM_THREADS * NORM_PER;   // 2048 lags per CTA
+
+template <typename T> struct Slide;
+template <> struct Slide<uint8_t> {
+    typedef int acc_t;                                // exact: |delta| <= 65025, 2048 of them < 2^31
+    static __device__ __forceinline__ int sq(uint8_t hi, uint8_t lo) { return (int)hi * hi - (int)lo * lo; }
+    static __device__ __forceinline__ int ln(uint8_t hi, uint8_t lo) { return (int)hi - (int)lo; }
+};
+template <> struct Slide<float> {
+    typedef double acc_t;
+    static __device__ __forceinline__ double sq(float hi, float lo) { return (double)hi * hi - (double)lo * lo; }
+    static __device__ __forceinline__ double ln(float hi, float lo) { return (double)hi - (double)lo; }
+};
+
+template <typename T>
 __global__ void __launch_bounds__(NORM_THREADS)
-k_normalise_argmin(const float* __restrict__ corr_rows, const double* __restrict__ ipsum, const double* __restrict__ ipsq,
+k_normalise_argmin(const float* __restrict__ corr_rows, const T* __restrict__ img, int64_t img_n,
+                   const double* __restrict__ ipsum, const double* __restrict__ ipsq,
                    const double* __restrict__ tpsum, const double* __restrict__ tpsq,
                    const QueryDesc* __restrict__ desc, int q_begin, int q_end, int64_t item_first,
-                   int B, float cval, unsigned long long* __restrict__ keys, float* __restrict__ curve_out,
+                   int B, unsigned long long* __restrict__ keys, float* __restrict__ curve_out,
                    int chunks_per_item) {
+    typedef typename Slide<T>::acc_t acc_t;
     __shared__ int s_q;
+    __shared__ acc_t s_wq[NORM_THREADS / 32], s_ws[NORM_THREADS / 32];
     __shared__ unsigned long long s_best[NORM_THREADS / 32];
     const int64_t it = blockIdx.x / chunks_per_item;
     const int chunk = blockIdx.x % chunks_per_item;
@@ -147,25 +186,66 @@ k_normalise_argmin(const float* __restrict__ corr_rows, const double* __restrict
     const QueryDesc d = desc[q];
     const int64_t k = d.k0 + (item - d.itemBase);
     const int64_t n = d.tlen;
-    const double c = (double)cval;
+    const int64_t jlo = d.lag0, jhi = d.lag0 + d.nlags;   // valid positions [jlo, jhi)
+    const int m_blk = chunk * NORM_LAGS;                  // first lag of this CTA inside the block row
+    const int64_t j_blk = k * B + m_blk;
+    if (m_blk >= B || j_blk >= jhi || j_blk + NORM_LAGS <= jlo) return;   // nothing valid here (uniform)
+
     const double tsum = tpsum[d.toff + n] - tpsum[d.toff];
     const double tsq = tpsq[d.toff + n] - tpsq[d.toff];
-    const double tnorm = sqrt(tsq);
-    const double n_c2 = (double)n * c * c;
+    const double a = (double)centre_of<T>(ipsum[img_n], (double)img_n);
+    const double b = (double)centre_of<T>(tsum, (double)n);
+    const double n_ab = (double)n * a * b;
     const double scale = 1.0 / (double)(2 * B);      // cuFFT transforms are unnormalised
-    const float* row = corr_rows + it * (int64_t)(2 * B + 2);
-    const int64_t jlo = d.lag0, jhi = d.lag0 + d.nlags;   // valid positions [jlo, jhi)
+    // the scan starts at the first lag of this CTA that can be valid, so that its base window
+    // [jb, jb+n) lies inside the stream
+    const int64_t jb = j_blk > jlo ? j_blk : jlo;
+    const double base_ws = ipsum[jb + n] - ipsum[jb];
+    const double base_wq = ipsq[jb + n] - ipsq[jb];
+
+    // thread t owns lags j0 .. j0+7; delta_i moves the window from j0+i to j0+i+1
+    const int m0 = m_blk + threadIdx.x * NORM_PER;
+    const int64_t j0 = k * B + m0;
+    acc_t dq[NORM_PER], ds[NORM_PER];
+    acc_t tq = 0, ts = 0;
+#pragma unroll
+    for (int i = 0; i < NORM_PER; ++i) {
+        const int64_t j = j0 + i;
+        acc_t eq = 0, es = 0;
+        if (j >= jb && j + n < img_n) {               // deltas before jb are not part of the scan
+            const T lo = img[j], hi = img[j + n];
+            eq = Slide<T>::sq(hi, lo); es = Slide<T>::ln(hi, lo);
+        }
+        dq[i] = tq; ds[i] = ts;                       // exclusive prefix inside the thread
+        tq += eq; ts += es;
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    acc_t iq = tq, is = ts;                           // inclusive warp scan of the thread totals
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        acc_t uq = __shfl_up_sync(0xffffffffu, iq, o), us = __shfl_up_sync(0xffffffffu, is, o);
+        if (lane >= o) { iq += uq; is += us; }
+    }
+    if (lane == 31) { s_wq[warp] = iq; s_ws[warp] = is; }
+    __syncthreads();
+    acc_t oq = iq - tq, os = is - ts;
+    for (int w = 0; w < warp; ++w) { oq += s_wq[w]; os += s_ws[w]; }
+
     unsigned long long best = ~0ull;
-    const int m0 = chunk * NORM_LAGS + threadIdx.x;
-#pragma unroll 4
-    for (int r = 0; r < NORM_LAGS / NORM_THREADS; ++r) {
-        const int m = m0 + r * NORM_THREADS;
-        const int64_t j = k * B + m;
-        if (m < B && j >= jlo && j < jhi) {
-            const double cc = (double)row[m] * scale;
-            const double wsum = ipsum[j + n] - ipsum[j];
-            const double wsq = ipsq[j + n] - ipsq[j];
-            const float v = sqdiff_normed(cc, wsum, wsq, c, tsum, tsq, n_c2, tnorm);
+    const float* row = corr_rows + it * (int64_t)(2 * B + 2) + m0;
+    float cc[NORM_PER];
+#pragma unroll
+    for (int i = 0; i < NORM_PER; i += 2) {
+        const float2 v = (m0 + i < B) ? *reinterpret_cast<const float2*>(row + i) : make_float2(0.f, 0.f);
+        cc[i] = v.x; cc[i + 1] = v.y;
+    }
+#pragma unroll
+    for (int i = 0; i < NORM_PER; ++i) {
+        const int64_t j = j0 + i;
+        if (m0 + i < B && j >= jlo && j < jhi) {
+            const double wsq = base_wq + (double)(oq + dq[i]);
+            const double wsum = base_ws + (double)(os + ds[i]);
+            const float v = sqdiff_normed((double)cc[i] * scale, wsum, wsq, a, b, tsum, tsq, n_ab);
             if (curve_out) curve_out[j - jlo] = v;
             const unsigned long long key = pack_key(v, (unsigned int)(j - jlo));
             best = key < best ? key : best;
@@ -176,7 +256,7 @@ k_normalise_argmin(const float* __restrict__ corr_rows, const double* __restrict
         unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
         best = other < best ? other : best;
     }
-    if ((threadIdx.x & 31) == 0) s_best[threadIdx.x >> 5] = best;
+    if (lane == 0) s_best[warp] = best;
     __syncthreads();
     if (threadIdx.x == 0) {
 #pragma unroll
@@ -263,7 +343,6 @@ int run_batch(const sb_stream* image_c, const sb_stream* tmpl, int64_t count,
     const int64_t chunk = std::min<int64_t>(c.chunk_items, total_items);
     SB_TRY(grow(&c.d_items, &c.items_cap, chunk * nb));
 
-    const float cval = image->dtype == SB_U8 ? 128.f : 0.5f;
     const int gchunks = (2 * B + 2047) / 2048;
     const int mchunks = (nb + MAC_BINS - 1) / MAC_BINS;
     const int nchunks = (B + NORM_LAGS - 1) / NORM_LAGS;
@@ -284,10 +363,10 @@ int run_batch(const sb_stream* image_c, const sb_stream* tmpl, int64_t count,
                 ProfScope ps("gather_parts");
                 if (tmpl->dtype == SB_U8)
                     k_gather_parts<uint8_t><<<(unsigned)(rows * gchunks), 256, 0, c.stream>>>(
-                        static_cast<const uint8_t*>(tmpl->d_raw), c.d_desc, (int)qb, (int)qe, part_first + p0, B, cval, dst, gchunks);
+                        static_cast<const uint8_t*>(tmpl->d_raw), tmpl->d_psum, c.d_desc, (int)qb, (int)qe, part_first + p0, B, dst, gchunks);
                 else
                     k_gather_parts<float><<<(unsigned)(rows * gchunks), 256, 0, c.stream>>>(
-                        static_cast<const float*>(tmpl->d_raw), c.d_desc, (int)qb, (int)qe, part_first + p0, B, cval, dst, gchunks);
+                        static_cast<const float*>(tmpl->d_raw), tmpl->d_psum, c.d_desc, (int)qb, (int)qe, part_first + p0, B, dst, gchunks);
             }
             cufftHandle plan;
             SB_TRY(get_plan(CUFFT_R2C, rows, &plan));
@@ -314,9 +393,16 @@ int run_batch(const sb_stream* image_c, const sb_stream* tmpl, int64_t count,
             }
             {
                 ProfScope ps("normalise_argmin");
-                k_normalise_argmin<<<(unsigned)(ni * nchunks), NORM_THREADS, 0, c.stream>>>(
-                    reinterpret_cast<const float*>(c.d_items), image->d_psum, image->d_psq, tmpl->d_psum, tmpl->d_psq,
-                    c.d_desc, (int)qb, (int)qe, i0, B, cval, c.d_keys, d_curve, nchunks);
+                if (image->dtype == SB_U8)
+                    k_normalise_argmin<uint8_t><<<(unsigned)(ni * nchunks), NORM_THREADS, 0, c.stream>>>(
+                        reinterpret_cast<const float*>(c.d_items), static_cast<const uint8_t*>(image->d_raw), image->n,
+                        image->d_psum, image->d_psq, tmpl->d_psum, tmpl->d_psq,
+                        c.d_desc, (int)qb, (int)qe, i0, B, c.d_keys, d_curve, nchunks);
+                else
+                    k_normalise_argmin<float><<<(unsigned)(ni * nchunks), NORM_THREADS, 0, c.stream>>>(
+                        reinterpret_cast<const float*>(c.d_items), static_cast<const float*>(image->d_raw), image->n,
+                        image->d_psum, image->d_psq, tmpl->d_psum, tmpl->d_psq,
+                        c.d_desc, (int)qb, (int)qe, i0, B, c.d_keys, d_curve, nchunks);
             }
         }
         qb = qe;

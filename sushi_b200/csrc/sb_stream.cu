@@ -119,8 +119,9 @@ k_tile_scan(const T* __restrict__ x, int64_t n, const double* __restrict__ osum,
 // zero beyond the end of the stream; rows are (2B+2) floats apart (in-place R2C).
 template <typename T>
 __global__ void __launch_bounds__(256)
-k_gather_blocks(const T* __restrict__ x, int64_t n, int B, float c, float* __restrict__ rows,
+k_gather_blocks(const T* __restrict__ x, int64_t n, const double* __restrict__ psum, int B, float* __restrict__ rows,
                 int64_t k_first, int chunks_per_row) {
+    const float c = sizeof(T) == 1 ? (float)rint(psum[n] / (double)n) : (float)(psum[n] / (double)n);   // = centre_of<T>
     const int64_t row = blockIdx.x / chunks_per_row;
     const int chunk = blockIdx.x % chunks_per_row;
     const int64_t k = k_first + row;
@@ -210,10 +211,10 @@ int ensure_spectra(sb_stream* s) {
             ProfScope ps("gather_blocks");
             if (s->dtype == SB_U8)
                 k_gather_blocks<uint8_t><<<(unsigned)(rows * chunks), 256, 0, c.stream>>>(
-                    static_cast<const uint8_t*>(s->d_raw), s->n, B, 128.f, dst, k, chunks);
+                    static_cast<const uint8_t*>(s->d_raw), s->n, s->d_psum, B, dst, k, chunks);
             else
                 k_gather_blocks<float><<<(unsigned)(rows * chunks), 256, 0, c.stream>>>(
-                    static_cast<const float*>(s->d_raw), s->n, B, 0.5f, dst, k, chunks);
+                    static_cast<const float*>(s->d_raw), s->n, s->d_psum, B, dst, k, chunks);
         }
         cufftHandle plan;
         SB_TRY(get_plan(CUFFT_R2C, rows, &plan));
