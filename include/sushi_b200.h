@@ -70,6 +70,11 @@ int sb_sync(void);
  * chunk).  Changing the block size drops cached block spectra. */
 int sb_set_block_size(int block);
 int sb_get_block_size(void);
+/* Engine behind sb_find*: 1 (default) = the fused lag-block kernel (spectral multiply, inverse FFT
+ * in shared memory, normalisation and argmin in one launch; lag blocks of 8192 or 16384), 0 = the
+ * cuFFT-planned pipeline (any block size; kept as the cross-check and for odd block sizes). */
+int sb_set_engine(int engine);
+int sb_get_engine(void);
 /* Lag blocks processed per multiply / inverse-FFT / normalise launch (>= 1). */
 int sb_set_chunk_items(int items);
 

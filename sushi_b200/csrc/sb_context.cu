@@ -62,6 +62,49 @@ int prof_collect() {
     return SB_OK;
 }
 
+namespace {
+std::multimap<size_t, void*> g_free_blocks;      // cached, not in use
+std::map<void*, size_t> g_live_blocks;           // handed out
+size_t g_cached_bytes = 0;
+const size_t kMaxCachedBytes = (size_t)24 << 30;
+}
+
+int pool_alloc(void** out, size_t bytes) {
+    bytes = (bytes + 255) & ~(size_t)255;
+    auto it = g_free_blocks.find(bytes);
+    if (it != g_free_blocks.end()) {
+        *out = it->second; g_cached_bytes -= bytes; g_free_blocks.erase(it);
+        g_live_blocks[*out] = bytes;
+        return SB_OK;
+    }
+    cudaError_t e = cudaMalloc(out, bytes);
+    if (e != cudaSuccess) {                         // give cached blocks back and retry once
+        pool_release_all();
+        e = cudaMalloc(out, bytes);
+    }
+    if (e != cudaSuccess) { cudaGetLastError(); SB_FAIL(SB_ENOMEM, "device allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e)); }
+    g_live_blocks[*out] = bytes;
+    return SB_OK;
+}
+
+void pool_free(void* p) {
+    if (!p) return;
+    auto it = g_live_blocks.find(p);
+    if (it == g_live_blocks.end()) { cudaFree(p); return; }
+    const size_t bytes = it->second;
+    g_live_blocks.erase(it);
+    if (g_cached_bytes + bytes > kMaxCachedBytes) { cudaFree(p); return; }
+    // blocks are only reused by work enqueued later on the same (single) library stream
+    g_free_blocks.emplace(bytes, p); g_cached_bytes += bytes;
+}
+
+void pool_release_all() {
+    Ctx& c = ctx();
+    if (c.stream) cudaStreamSynchronize(c.stream);
+    for (auto& kv : g_free_blocks) cudaFree(kv.second);
+    g_free_blocks.clear(); g_cached_bytes = 0;
+}
+
 int get_plan(int type, int64_t batch, cufftHandle* out) {
     Ctx& c = ctx();
     auto key = std::make_pair(type, batch);
@@ -134,6 +177,8 @@ int sb_shutdown(void) {
     cudaStreamSynchronize(c.stream);
     prof_collect();
     drop_plans();
+    pool_release_all();
+    fused_release_tables();
     cudaFree(c.d_parts); cudaFree(c.d_items); cudaFree(c.d_desc); cudaFree(c.d_keys);
     cudaFree(c.d_diff); cudaFree(c.d_idx);
     cudaFreeHost(c.h_desc); cudaFreeHost(c.h_diff); cudaFreeHost(c.h_idx);
@@ -166,6 +211,12 @@ int sb_set_block_size(int block) {
     return SB_OK;
 }
 int sb_get_block_size(void) { return ctx().B; }
+int sb_set_engine(int engine) {
+    if (engine != 0 && engine != 1) SB_FAIL(SB_EINVAL, "sb_set_engine: %d is neither 0 (cuFFT pipeline) nor 1 (fused kernel)", engine);
+    ctx().engine = engine;
+    return SB_OK;
+}
+int sb_get_engine(void) { return ctx().engine; }
 int sb_set_chunk_items(int items) {
     if (items < 1 || items > (1 << 20)) SB_FAIL(SB_EINVAL, "sb_set_chunk_items: %d out of range", items);
     ctx().chunk_items = items;

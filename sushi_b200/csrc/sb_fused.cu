@@ -1,0 +1,485 @@
+// Fused lag-block kernel: for one (query, lag block) item a CTA
+//   1. accumulates Y[bin] = sum_p conj(T^_p[bin]) * X^_{k+p}[bin] straight from L2 into registers,
+//   2. packs the Hermitian half spectrum into a half-size complex sequence in shared memory,
+//   3. runs the inverse FFT entirely in shared memory (Stockham, radix 32 x {32|16} x 16),
+//   4. slides the window sums through its lags, screens every lag in fp32 and evaluates only the
+//      lags that can still be the minimum with OpenCV's rule in fp64, and
+//   5. merges its (value, first index) into the query's result with one 64-bit atomicMin.
+// The B-long correlation block never touches HBM (the cuFFT pipeline in sb_matcher.cu writes and
+// re-reads it twice); the only global traffic is the spectra (L2 resident) and 2 B per lag of raw
+// samples.  See DESIGN.md section 4 for the roofline of each phase.
+#include "sb_internal.h"
+#include <cmath>
+#include <vector>
+
+using namespace sb;
+
+namespace {
+
+// ---------------------------------------------------------------- small complex helpers
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+
+// exp(+2*pi*i*q/32), q = 0..15
+__device__ constexpr float kC32[16] = {
+    1.0f, 0.98078528040323043f, 0.92387953251128674f, 0.83146961230254524f,
+    0.70710678118654752f, 0.55557023301960218f, 0.38268343236508978f, 0.19509032201612825f,
+    0.0f, -0.19509032201612825f, -0.38268343236508978f, -0.55557023301960218f,
+    -0.70710678118654752f, -0.83146961230254524f, -0.92387953251128674f, -0.98078528040323043f};
+__device__ constexpr float kS32[16] = {
+    0.0f, 0.19509032201612825f, 0.38268343236508978f, 0.55557023301960218f,
+    0.70710678118654752f, 0.83146961230254524f, 0.92387953251128674f, 0.98078528040323043f,
+    1.0f, 0.98078528040323043f, 0.92387953251128674f, 0.83146961230254524f,
+    0.70710678118654752f, 0.55557023301960218f, 0.38268343236508978f, 0.19509032201612825f};
+
+// d * exp(+2*pi*i*q/32) with q a compile-time constant after unrolling
+__device__ __forceinline__ float2 rot32(float2 d, int q) {
+    if (q == 0) return d;
+    if (q == 8) return make_float2(-d.y, d.x);
+    if (q == 4) { const float h = 0.70710678118654752f; return make_float2((d.x - d.y) * h, (d.x + d.y) * h); }
+    if (q == 12) { const float h = 0.70710678118654752f; return make_float2(-(d.x + d.y) * h, (d.x - d.y) * h); }
+    return make_float2(d.x * kC32[q] - d.y * kS32[q], d.x * kS32[q] + d.y * kC32[q]);
+}
+
+// In-register inverse DFT of R points (sign +, unnormalised), decimation in frequency: natural
+// order in, bit-reversed order out (the caller indexes the outputs through brev<R>).
+template <int R>
+__device__ __forceinline__ void dft_dif(float2 (&v)[R]) {
+#pragma unroll
+    for (int h = R / 2; h >= 1; h >>= 1) {
+#pragma unroll
+        for (int g = 0; g < R; g += 2 * h) {
+#pragma unroll
+            for (int a = 0; a < h; ++a) {
+                const float2 x = v[g + a], y = v[g + a + h];
+                v[g + a] = cadd(x, y);
+                v[g + a + h] = rot32(csub(x, y), a * (16 / h));
+            }
+        }
+    }
+}
+template <int R> __device__ __forceinline__ constexpr int brev(int r) {
+    int o = 0;
+    for (int b = 1; b < R; b <<= 1) { o = (o << 1) | (r & 1); r >>= 1; }
+    return o;
+}
+
+// one padding slot per 32 complex values keeps the radix-32 scatter of pass 1 conflict free
+__device__ __forceinline__ int pad(int i) { return i + (i >> 5); }
+
+// ---------------------------------------------------------------- configuration
+template <int LOGN> struct Cfg;
+template <> struct Cfg<14> {   // B = 16384 lags per item
+    static constexpr int N = 16384, T = 512, R1 = 32, R2 = 32, R3 = 16, MINB = 1;
+};
+template <> struct Cfg<13> {   // B = 8192 lags per item
+    static constexpr int N = 8192, T = 256, R1 = 32, R2 = 16, R3 = 16, MINB = 2;
+};
+
+struct FusedTables {
+    const float2* w;      // [N/2+1]   exp(+i*pi*m/N)            (Hermitian unpacking)
+    const float2* t2;     // [R2][32]  exp(+2*pi*i*r*k/(32*R2))   (pass 2, k = lane)
+    const float2* a3;     // [R3][32]  exp(+2*pi*i*r*k/N), k = lane            (pass 3, low part)
+    const float2* b3;     // [R3][32]  exp(+2*pi*i*r*kh*32/N), kh = k / 32     (pass 3, high part)
+};
+
+// ---------------------------------------------------------------- exact per-lag value (fp64)
+__device__ __forceinline__ float sqdiff_exact(double corr_centred, double wsum, double wsq,
+                                              double a, double b, double tsum, double tsq, double n_ab) {
+    const double sit = corr_centred + b * wsum + a * tsum - n_ab;
+    const double corr = (double)(float)sit;          // OpenCV keeps sum(I*T) as float32
+    double num = wsq - 2.0 * corr + tsq;
+    num = fmax(num, 0.0);
+    const double p = wsq * tsq;
+    if (!(wsq > 0.0) || wsq <= fmin(0.5, 10.0 * 1.1920928955078125e-07 * wsq) || !(p > 0.0)) return 1.0f;
+    const double r = rsqrt(p);
+    const double t = p * r;
+    return (num < t) ? (float)(num * r) : 1.0f;
+}
+
+template <typename S> struct Acc;
+template <> struct Acc<uint8_t> {
+    typedef int type;
+    static __device__ __forceinline__ int sq(uint8_t hi, uint8_t lo) { return (int)hi * hi - (int)lo * lo; }
+    static __device__ __forceinline__ int ln(uint8_t hi, uint8_t lo) { return (int)hi - (int)lo; }
+    static __device__ __forceinline__ float centre(double sum, double cnt) { return (float)rint(sum / cnt); }
+};
+template <> struct Acc<float> {
+    typedef double type;
+    static __device__ __forceinline__ double sq(float hi, float lo) { return (double)hi * hi - (double)lo * lo; }
+    static __device__ __forceinline__ double ln(float hi, float lo) { return (double)hi - (double)lo; }
+    static __device__ __forceinline__ float centre(double sum, double cnt) { return (float)(sum / cnt); }
+};
+
+constexpr float kScreenMargin = 8e-6f;   // > 2 x fp32 screening error + one float32 ulp at 1.0
+
+// ---------------------------------------------------------------- the kernel
+template <int LOGN, typename S>
+__global__ void __launch_bounds__(Cfg<LOGN>::T, Cfg<LOGN>::MINB)
+k_match_fused(const float2* __restrict__ That, int64_t part_first,
+              const float2* __restrict__ Xhat, int64_t nblk,
+              const S* __restrict__ img, int64_t img_n,
+              const double* __restrict__ ipsum, const double* __restrict__ ipsq,
+              const double* __restrict__ tpsum, const double* __restrict__ tpsq,
+              const QueryDesc* __restrict__ desc, int q_begin, int q_end, int64_t item_first,
+              FusedTables tab, unsigned long long* __restrict__ keys, float* __restrict__ curve_out) {
+    typedef Cfg<LOGN> C;
+    typedef typename Acc<S>::type acc_t;
+    constexpr int N = C::N, T = C::T, B = C::N;
+    constexpr int NB = B + 1;                       // bins per spectrum row
+    constexpr int LAGS_PER_ROUND = T * 8;           // 8 consecutive lags per thread per round
+    constexpr int ROUNDS = B / LAGS_PER_ROUND;      // 4
+    constexpr int NW = T / 32;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* buf = reinterpret_cast<float2*>(smem_raw);                  // pad(N) complex values
+    acc_t* s_wq = reinterpret_cast<acc_t*>(buf + pad(N) + 1);           // [ROUNDS*NW] warp totals / offsets
+    acc_t* s_ws = s_wq + ROUNDS * NW;
+    float* s_min = reinterpret_cast<float*>(s_ws + ROUNDS * NW);        // [NW]
+    unsigned long long* s_best = reinterpret_cast<unsigned long long*>(s_min + NW + (NW & 1));   // [NW]
+    __shared__ int s_q;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t item = item_first + blockIdx.x;
+    if (tid == 0) {
+        int lo = q_begin, hi = q_end - 1;
+        while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (desc[mid].itemBase <= item) lo = mid; else hi = mid - 1; }
+        s_q = lo;
+    }
+    __syncthreads();
+    const int q = s_q;
+    const QueryDesc d = desc[q];
+    const int64_t k = d.k0 + (item - d.itemBase);
+
+    // ---------------- 1+2. spectral multiply-accumulate and Hermitian packing ---------------
+    {
+        int P = d.P;
+        if (k + P > nblk) P = (int)(nblk - k);      // blocks past the end of the stream are zero
+        const float2* tp = That + (d.partBase - part_first) * (int64_t)NB;
+        const float2* xp = Xhat + k * (int64_t)NB;
+        constexpr int U = 4;                        // bin pairs in flight per thread
+        for (int m0 = tid; m0 <= B / 2; m0 += U * T) {
+            float2 ym[U], yp[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) { ym[u] = make_float2(0.f, 0.f); yp[u] = make_float2(0.f, 0.f); }
+            for (int p = 0; p < P; ++p) {
+                const float2* t = tp + (int64_t)p * NB;
+                const float2* x = xp + (int64_t)p * NB;
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int m = m0 + u * T;
+                    if (m <= B / 2) {
+                        const float2 t1 = __ldg(t + m), x1 = __ldg(x + m);
+                        const float2 t2 = __ldg(t + (B - m)), x2 = __ldg(x + (B - m));
+                        ym[u].x += t1.x * x1.x + t1.y * x1.y;  ym[u].y += t1.x * x1.y - t1.y * x1.x;
+                        yp[u].x += t2.x * x2.x + t2.y * x2.y;  yp[u].y += t2.x * x2.y - t2.y * x2.x;
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int m = m0 + u * T;
+                if (m <= B / 2) {
+                    const float2 w = __ldg(tab.w + m);                 // exp(+i*pi*m/B)
+                    // Z[m]   = (Ym + conj(Yp)) + i*(Ym - conj(Yp))*w
+                    const float2 e = make_float2(ym[u].x + yp[u].x, ym[u].y - yp[u].y);
+                    const float2 o = cmul(make_float2(ym[u].x - yp[u].x, ym[u].y + yp[u].y), w);
+                    buf[pad(m)] = make_float2(e.x - o.y, e.y + o.x);
+                    if (m > 0 && m < B / 2) {
+                        // Z[B-m] = conj(e) + i*(Yp - conj(Ym))*(-conj(w)) = conj(e) + i*conj(o)
+                        buf[pad(B - m)] = make_float2(e.x + o.y, -e.y + o.x);
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---------------- 3. inverse FFT of N complex points in shared memory -------------------
+    // Stockham passes: butterfly j reads in[j + r*N/R], twiddles by exp(2*pi*i*r*k/(Ns*R)),
+    // k = j mod Ns, and writes out[(j-k)*R + k + r*Ns]; every value sits in a register between
+    // the two barriers, so the pass is in place.
+    {   // pass 1: R1 = 32, Ns = 1 (no twiddles); one butterfly per thread
+        constexpr int R = C::R1;
+        static_assert(N / R == T, "pass 1: one butterfly per thread");
+        float2 v[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) v[r] = buf[pad(tid + r * (N / R))];
+        __syncthreads();
+        dft_dif<R>(v);
+#pragma unroll
+        for (int r = 0; r < R; ++r) buf[pad(tid * R + r)] = v[brev<R>(r)];
+        __syncthreads();
+    }
+    {   // pass 2: Ns = 32, k = lane
+        constexpr int R = C::R2, Ns = C::R1, PER = (N / R) / T;
+        float2 v[PER][R];
+#pragma unroll
+        for (int b = 0; b < PER; ++b)
+#pragma unroll
+            for (int r = 0; r < R; ++r) v[b][r] = buf[pad(tid + b * T + r * (N / R))];
+        __syncthreads();
+#pragma unroll
+        for (int b = 0; b < PER; ++b) {
+            const int j = tid + b * T;
+#pragma unroll
+            for (int r = 1; r < R; ++r) v[b][r] = cmul(v[b][r], __ldg(tab.t2 + r * 32 + lane));
+            dft_dif<R>(v[b]);
+            const int j0 = (j - lane) * R + lane;
+#pragma unroll
+            for (int r = 0; r < R; ++r) buf[pad(j0 + r * Ns)] = v[b][brev<R>(r)];
+        }
+        __syncthreads();
+    }
+    {   // pass 3: Ns = R1*R2, k = j (j < Ns); only the first half of the outputs is needed:
+        // z[0 .. N/2) carries the B valid lags of the 2B-point real sequence
+        constexpr int R = C::R3, Ns = C::R1 * C::R2, PER = (N / R) / T;
+        static_assert(N / R == Ns, "pass 3 is the last pass");
+        float2 v[PER][R];
+#pragma unroll
+        for (int b = 0; b < PER; ++b)
+#pragma unroll
+            for (int r = 0; r < R; ++r) v[b][r] = buf[pad(tid + b * T + r * (N / R))];
+        __syncthreads();
+#pragma unroll
+        for (int b = 0; b < PER; ++b) {
+            const int j = tid + b * T;
+            const int kh = j >> 5;
+#pragma unroll
+            for (int r = 1; r < R; ++r)
+                v[b][r] = cmul(v[b][r], cmul(__ldg(tab.a3 + r * 32 + lane), __ldg(tab.b3 + r * 32 + kh)));
+            dft_dif<R>(v[b]);
+#pragma unroll
+            for (int r = 0; r < R / 2; ++r) buf[pad(j + r * Ns)] = v[b][brev<R>(r)];
+        }
+        __syncthreads();
+    }
+    // now buf[pad(i)] = (x[2i], x[2i+1]) for i < N/2: correlation at lags 2i, 2i+1 (times 2B)
+
+    // ---------------- 4. window sums, fp32 screening, fp64 exact evaluation -----------------
+    const int64_t n = d.tlen;
+    const int64_t jlo = d.lag0, jhi = d.lag0 + d.nlags;
+    const int64_t j_blk = k * B;
+    const int64_t jb = j_blk > jlo ? j_blk : jlo;          // first lag of this item that can be valid
+    const double tsum = tpsum[d.toff + n] - tpsum[d.toff];
+    const double tsq = tpsq[d.toff + n] - tpsq[d.toff];
+    const double a = (double)Acc<S>::centre(ipsum[img_n], (double)img_n);
+    const double b = (double)Acc<S>::centre(tsum, (double)n);
+    const double n_ab = (double)n * a * b;
+    const double scale = 1.0 / (double)(2 * B);
+    const double base_ws = ipsum[jb + n] - ipsum[jb];
+    const double base_wq = ipsq[jb + n] - ipsq[jb];
+
+    // thread-local sliding deltas: round c, lags j_blk + c*LAGS_PER_ROUND + tid*8 + i
+    acc_t pq[ROUNDS], ps[ROUNDS];                   // exclusive offsets of this thread's 8-lag runs
+    {
+        acc_t tq[ROUNDS], ts[ROUNDS];
+#pragma unroll
+        for (int c = 0; c < ROUNDS; ++c) {
+            const int64_t j0 = j_blk + c * LAGS_PER_ROUND + tid * 8;
+            acc_t aq = 0, as = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int64_t j = j0 + i;
+                if (j >= jb && j + n < img_n) {
+                    const S lo = img[j], hi = img[j + n];
+                    aq += Acc<S>::sq(hi, lo); as += Acc<S>::ln(hi, lo);
+                }
+            }
+            tq[c] = aq; ts[c] = as;
+            acc_t iq = aq, is = as;                 // inclusive warp scan
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                acc_t uq = __shfl_up_sync(0xffffffffu, iq, o), us = __shfl_up_sync(0xffffffffu, is, o);
+                if (lane >= o) { iq += uq; is += us; }
+            }
+            if (lane == 31) { s_wq[c * NW + warp] = iq; s_ws[c * NW + warp] = is; }
+            pq[c] = iq - aq; ps[c] = is - as;
+        }
+        __syncthreads();
+        if (warp == 0) {                            // exclusive scan over the ROUNDS*NW warp totals
+            acc_t carry_q = 0, carry_s = 0;
+            for (int e0 = 0; e0 < ROUNDS * NW; e0 += 32) {
+                const int e = e0 + lane;
+                acc_t vq = e < ROUNDS * NW ? s_wq[e] : 0, vs = e < ROUNDS * NW ? s_ws[e] : 0;
+                acc_t iq = vq, is = vs;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    acc_t uq = __shfl_up_sync(0xffffffffu, iq, o), us = __shfl_up_sync(0xffffffffu, is, o);
+                    if (lane >= o) { iq += uq; is += us; }
+                }
+                if (e < ROUNDS * NW) { s_wq[e] = carry_q + iq - vq; s_ws[e] = carry_s + is - vs; }
+                carry_q += __shfl_sync(0xffffffffu, iq, 31); carry_s += __shfl_sync(0xffffffffu, is, 31);
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int c = 0; c < ROUNDS; ++c) { pq[c] += s_wq[c * NW + warp]; ps[c] += s_ws[c * NW + warp]; }
+    }
+
+    // fp32 screening of every lag this thread owns
+    const float f_tsq = (float)tsq, f_bwq = (float)base_wq, f_b = (float)b;
+    const float f_k0 = (float)(b * base_ws + a * tsum - n_ab);
+    const float f_scale = (float)scale;
+    float vf[ROUNDS][8];
+    float tmin = 2.0f;
+#pragma unroll
+    for (int c = 0; c < ROUNDS; ++c) {
+        const int i0 = (c * LAGS_PER_ROUND + tid * 8) >> 1;          // complex index of the first lag pair
+        float cc[8];
+#pragma unroll
+        for (int h = 0; h < 4; ++h) { const float2 z = buf[pad(i0 + h)]; cc[2 * h] = z.x; cc[2 * h + 1] = z.y; }
+        const int64_t j0 = j_blk + c * LAGS_PER_ROUND + tid * 8;
+        acc_t rq = pq[c], rs = ps[c];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int64_t j = j0 + i;
+            float v = 2.0f;                                           // sentinel: not a valid lag
+            if (j >= jlo && j < jhi) {
+                const float wq = f_bwq + (float)rq;
+                const float sit = fmaf(cc[i], f_scale, fmaf(f_b, (float)rs, f_k0));
+                const float num = fmaxf((wq + f_tsq) - 2.0f * sit, 0.0f);
+                const float pr = wq * f_tsq;
+                v = pr > 0.0f ? fminf(num * rsqrtf(pr), 1.0f) : 1.0f;
+            }
+            vf[c][i] = v;
+            tmin = fminf(tmin, v);
+            if (j >= jb && j + n < img_n) {                           // same deltas as above
+                const S lo = img[j], hi = img[j + n];
+                rq += Acc<S>::sq(hi, lo); rs += Acc<S>::ln(hi, lo);
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tmin = fminf(tmin, __shfl_xor_sync(0xffffffffu, tmin, o));
+    if (lane == 0) s_min[warp] = tmin;
+    __syncthreads();
+    float bmin = s_min[0];
+#pragma unroll
+    for (int w = 1; w < NW; ++w) bmin = fminf(bmin, s_min[w]);
+    const float thr = curve_out ? 1.5f : bmin + kScreenMargin;       // debug curve: evaluate everything
+
+    unsigned long long best = ~0ull;
+#pragma unroll
+    for (int c = 0; c < ROUNDS; ++c) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (vf[c][i] <= thr) {
+                const int m = c * LAGS_PER_ROUND + tid * 8 + i;
+                const int64_t j = j_blk + m;
+                const float2 z = buf[pad(m >> 1)];
+                const double cc = (double)((m & 1) ? z.y : z.x) * scale;
+                const double wsum = ipsum[j + n] - ipsum[j];
+                const double wsq = ipsq[j + n] - ipsq[j];
+                const float v = sqdiff_exact(cc, wsum, wsq, a, b, tsum, tsq, n_ab);
+                if (curve_out) curve_out[j - jlo] = v;
+                const unsigned long long key = ((unsigned long long)__float_as_uint(v) << 32) | (unsigned int)(j - jlo);
+                best = key < best ? key : best;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+        best = other < best ? other : best;
+    }
+    if (lane == 0) s_best[warp] = best;
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < NW; ++w) best = s_best[w] < best ? s_best[w] : best;
+        if (best != ~0ull) atomicMin(keys + q, best);
+    }
+}
+
+// ---------------------------------------------------------------- host side
+template <int LOGN> size_t fused_smem_bytes() {
+    typedef Cfg<LOGN> C;
+    const size_t padded = (size_t)(C::N + (C::N >> 5) + 1);
+    const size_t nw = C::T / 32, rounds = C::N / (C::T * 8);
+    return padded * sizeof(float2) + 2 * rounds * nw * sizeof(double) + (nw + 2) * sizeof(float) + nw * sizeof(unsigned long long) + 64;
+}
+
+struct TableSet { float2* dev = nullptr; FusedTables tab; };
+TableSet g_tables[2];     // [0]: LOGN 13, [1]: LOGN 14
+
+template <int LOGN> int ensure_tables(FusedTables* out) {
+    typedef Cfg<LOGN> C;
+    TableSet& ts = g_tables[LOGN - 13];
+    if (!ts.dev) {
+        const int N = C::N;
+        const size_t nw = N / 2 + 1, n2 = (size_t)C::R2 * 32, n3 = (size_t)C::R3 * 32;
+        std::vector<float2> h(nw + n2 + 2 * n3);
+        const double pi = 3.14159265358979323846;
+        for (size_t m = 0; m < nw; ++m) h[m] = make_float2((float)cos(pi * m / N), (float)sin(pi * m / N));
+        for (int r = 0; r < C::R2; ++r)
+            for (int k = 0; k < 32; ++k) {
+                const double ang = 2.0 * pi * r * k / (32.0 * C::R2);
+                h[nw + r * 32 + k] = make_float2((float)cos(ang), (float)sin(ang));
+            }
+        for (int r = 0; r < C::R3; ++r)
+            for (int k = 0; k < 32; ++k) {
+                const double al = 2.0 * pi * r * k / N, ah = 2.0 * pi * r * (k * 32.0) / N;
+                h[nw + n2 + r * 32 + k] = make_float2((float)cos(al), (float)sin(al));
+                h[nw + n2 + n3 + r * 32 + k] = make_float2((float)cos(ah), (float)sin(ah));
+            }
+        SB_CUDA(cudaMalloc(&ts.dev, h.size() * sizeof(float2)));
+        SB_CUDA(cudaMemcpy(ts.dev, h.data(), h.size() * sizeof(float2), cudaMemcpyHostToDevice));
+        ts.tab.w = ts.dev; ts.tab.t2 = ts.dev + nw; ts.tab.a3 = ts.dev + nw + n2; ts.tab.b3 = ts.dev + nw + n2 + n3;
+    }
+    *out = ts.tab;
+    return SB_OK;
+}
+
+template <int LOGN, typename S>
+int launch_typed(const sb_stream* image, const sb_stream* tmpl, const float2* d_parts, int64_t part_first,
+                 const QueryDesc* d_desc, int q_begin, int q_end, int64_t item_first, int64_t n_items,
+                 unsigned long long* d_keys, float* d_curve) {
+    Ctx& c = ctx();
+    FusedTables tab;
+    SB_TRY(ensure_tables<LOGN>(&tab));
+    static bool attr_set = false;
+    const size_t smem = fused_smem_bytes<LOGN>();
+    if (!attr_set) {
+        SB_CUDA(cudaFuncSetAttribute(k_match_fused<LOGN, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    const int64_t max_grid = 1 << 30;
+    for (int64_t i0 = 0; i0 < n_items; i0 += max_grid) {
+        const int64_t ni = std::min<int64_t>(max_grid, n_items - i0);
+        k_match_fused<LOGN, S><<<(unsigned)ni, Cfg<LOGN>::T, smem, c.stream>>>(
+            d_parts, part_first, image->d_spec, image->nblk, static_cast<const S*>(image->d_raw), image->n,
+            image->d_psum, image->d_psq, tmpl->d_psum, tmpl->d_psq, d_desc, q_begin, q_end, item_first + i0,
+            tab, d_keys, d_curve);
+    }
+    SB_CUDA(cudaGetLastError());
+    return SB_OK;
+}
+
+}  // namespace
+
+namespace sb {
+
+bool fused_supports(int B) { return B == 16384 || B == 8192; }
+
+int launch_match_fused(const sb_stream* image, const sb_stream* tmpl, const float2* d_parts, int64_t part_first,
+                       const QueryDesc* d_desc, int q_begin, int q_end, int64_t item_first, int64_t n_items,
+                       unsigned long long* d_keys, float* d_curve) {
+    const int B = ctx().B;
+    const bool u8 = image->dtype == SB_U8;
+    if (B == 16384)
+        return u8 ? launch_typed<14, uint8_t>(image, tmpl, d_parts, part_first, d_desc, q_begin, q_end, item_first, n_items, d_keys, d_curve)
+                  : launch_typed<14, float>(image, tmpl, d_parts, part_first, d_desc, q_begin, q_end, item_first, n_items, d_keys, d_curve);
+    if (B == 8192)
+        return u8 ? launch_typed<13, uint8_t>(image, tmpl, d_parts, part_first, d_desc, q_begin, q_end, item_first, n_items, d_keys, d_curve)
+                  : launch_typed<13, float>(image, tmpl, d_parts, part_first, d_desc, q_begin, q_end, item_first, n_items, d_keys, d_curve);
+    SB_FAIL(SB_EINVAL, "fused engine supports lag blocks of 8192 or 16384 samples, not %d", B);
+}
+
+void fused_release_tables() {
+    for (auto& t : g_tables) { if (t.dev) cudaFree(t.dev); t.dev = nullptr; }
+}
+
+}  // namespace sb

@@ -10,6 +10,8 @@
 
 #include "sushi_b200.h"
 
+struct sb_stream;
+
 namespace sb {
 
 // ---- error plumbing ---------------------------------------------------------
@@ -50,7 +52,8 @@ struct Ctx {
     int sm_count = 148;
     cudaStream_t stream = nullptr;
     int B = 16384;                 // lag-block size (samples); FFT size is 2B
-    int chunk_items = 1024;        // items per MAC/C2R/normalise chunk
+    int chunk_items = 1024;        // items per MAC/C2R/normalise chunk (cuFFT engine)
+    int engine = 1;                // 1: fused lag-block kernel (sb_fused.cu), 0: cuFFT pipeline
     int64_t max_parts = 16384;     // template partition spectra kept per super-chunk
 
     // scratch (grown on demand)
@@ -88,6 +91,18 @@ struct ProfScope {
     explicit ProfScope(const char* name, int nlaunch = 1);
     ~ProfScope();
 };
+
+// Size-keyed pool of device blocks: streams are created and destroyed per batch by some
+// callers; cudaMalloc/cudaFree (which synchronise the device) must not sit on that path.
+int pool_alloc(void** out, size_t bytes);
+void pool_free(void* p);
+void pool_release_all();
+
+bool fused_supports(int B);
+int launch_match_fused(const sb_stream* image, const sb_stream* tmpl, const float2* d_parts, int64_t part_first,
+                       const QueryDesc* d_desc, int q_begin, int q_end, int64_t item_first, int64_t n_items,
+                       unsigned long long* d_keys, float* d_curve);
+void fused_release_tables();
 
 int get_plan(int type, int64_t batch, cufftHandle* out);
 void drop_plans();

@@ -340,8 +340,9 @@ int run_batch(const sb_stream* image_c, const sb_stream* tmpl, int64_t count,
 
     const int64_t parts_cap_want = std::max<int64_t>(std::min<int64_t>(total_parts, c.max_parts), maxp);
     SB_TRY(grow(&c.d_parts, &c.parts_cap, parts_cap_want * nb));
+    const bool use_fused = c.engine == 1 && fused_supports(B);
     const int64_t chunk = std::min<int64_t>(c.chunk_items, total_items);
-    SB_TRY(grow(&c.d_items, &c.items_cap, chunk * nb));
+    if (!use_fused) SB_TRY(grow(&c.d_items, &c.items_cap, chunk * nb));
 
     const int gchunks = (2 * B + 2047) / 2048;
     const int mchunks = (nb + MAC_BINS - 1) / MAC_BINS;
@@ -375,9 +376,14 @@ int run_batch(const sb_stream* image_c, const sb_stream* tmpl, int64_t count,
                 SB_CUFFT(cufftExecR2C(plan, dst, reinterpret_cast<cufftComplex*>(dst)));
             }
         }
-        // 2. items of these queries in fixed-size chunks
+        // 2. items of these queries
         const int64_t item_lo = c.h_desc[qb].itemBase;
         const int64_t item_hi = (qe < count) ? c.h_desc[qe].itemBase : total_items;
+        if (use_fused) {
+            ProfScope ps("match_fused");
+            SB_TRY(launch_match_fused(image, tmpl, c.d_parts, part_first, c.d_desc, (int)qb, (int)qe,
+                                      item_lo, item_hi - item_lo, c.d_keys, d_curve));
+        } else
         for (int64_t i0 = item_lo; i0 < item_hi; i0 += chunk) {
             const int64_t ni = std::min<int64_t>(chunk, item_hi - i0);
             {

@@ -146,7 +146,7 @@ int build_prefix(sb_stream* s) {
     const int64_t n = s->n;
     const int64_t ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
     double* d_t = nullptr;
-    SB_CUDA(cudaMalloc(&d_t, sizeof(double) * 2 * ntiles));
+    SB_TRY(pool_alloc((void**)&d_t, sizeof(double) * 2 * ntiles));
     double* tsum = d_t; double* tsq = d_t + ntiles;
     const T* x = static_cast<const T*>(s->d_raw);
     {
@@ -162,14 +162,13 @@ int build_prefix(sb_stream* s) {
         k_tile_scan<T><<<(unsigned)ntiles, SCAN_THREADS, 0, c.stream>>>(x, n, tsum, tsq, s->d_psum, s->d_psq);
     }
     SB_CUDA(cudaGetLastError());
-    SB_CUDA(cudaStreamSynchronize(c.stream));
-    cudaFree(d_t);
+    pool_free(d_t);            // reused only by later work on the same stream
     return SB_OK;
 }
 
 int stream_finish(sb_stream* s) {
-    SB_CUDA(cudaMalloc(&s->d_psum, sizeof(double) * (s->n + 1)));
-    SB_CUDA(cudaMalloc(&s->d_psq, sizeof(double) * (s->n + 1)));
+    SB_TRY(pool_alloc((void**)&s->d_psum, sizeof(double) * (s->n + 1)));
+    SB_TRY(pool_alloc((void**)&s->d_psq, sizeof(double) * (s->n + 1)));
     if (s->dtype == SB_U8) return build_prefix<uint8_t>(s);
     return build_prefix<float>(s);
 }
@@ -184,8 +183,7 @@ int stream_alloc(int64_t n, int dtype, sb_stream** out, const char* who) {
     if (!s) SB_FAIL(SB_ENOMEM, "%s: out of host memory", who);
     s->n = n; s->dtype = dtype;
     const size_t esz = dtype == SB_U8 ? 1 : 4;
-    cudaError_t e = cudaMalloc(&s->d_raw, esz * n + 16);
-    if (e != cudaSuccess) { delete s; SB_FAIL(SB_ENOMEM, "%s: cudaMalloc(%lld): %s", who, (long long)(esz * n), cudaGetErrorString(e)); }
+    if (pool_alloc(&s->d_raw, esz * n + 16) != SB_OK) { delete s; return SB_ENOMEM; }
     *out = s;
     return SB_OK;
 }
@@ -198,10 +196,10 @@ namespace sb {
 int ensure_spectra(sb_stream* s) {
     Ctx& c = ctx();
     if (s->d_spec && s->specB == c.B) return SB_OK;
-    if (s->d_spec) { cudaStreamSynchronize(c.stream); cudaFree(s->d_spec); s->d_spec = nullptr; }
+    if (s->d_spec) { pool_free(s->d_spec); s->d_spec = nullptr; }
     const int B = c.B;
     const int64_t nblk = (s->n + B - 1) / B;
-    SB_CUDA(cudaMalloc(&s->d_spec, sizeof(float2) * (size_t)nblk * (B + 1)));
+    SB_TRY(pool_alloc((void**)&s->d_spec, sizeof(float2) * (size_t)nblk * (B + 1)));
     const int chunks = (2 * B + 2047) / 2048;
     const int64_t sub = 1024;                        // rows per cuFFT call
     for (int64_t k = 0; k < nblk; k += sub) {
@@ -263,8 +261,8 @@ int sb_stream_create_device(const void* dev_samples, int64_t n, int dtype, sb_st
 int sb_stream_destroy(sb_stream* s) {
     if (!s) return SB_OK;
     Ctx& c = ctx();
-    if (c.inited) cudaStreamSynchronize(c.stream);
-    cudaFree(s->d_raw); cudaFree(s->d_psum); cudaFree(s->d_psq); cudaFree(s->d_spec);
+    (void)c;
+    pool_free(s->d_raw); pool_free(s->d_psum); pool_free(s->d_psq); pool_free(s->d_spec);
     delete s;
     return SB_OK;
 }
