@@ -46,7 +46,9 @@ __device__ __forceinline__ float2 rot32(float2 d, int q) {
 
 // In-register inverse DFT of R points (sign +, unnormalised), decimation in frequency: natural
 // order in, bit-reversed order out (the caller indexes the outputs through brev<R>).
-template <int R>
+// With FIRST_HALF only the outputs X[0 .. R/2) are produced (they sit at the even positions of
+// the bit-reversed result), so the subtractions of the last stage are skipped.
+template <int R, bool FIRST_HALF = false>
 __device__ __forceinline__ void dft_dif(float2 (&v)[R]) {
 #pragma unroll
     for (int h = R / 2; h >= 1; h >>= 1) {
@@ -56,7 +58,7 @@ __device__ __forceinline__ void dft_dif(float2 (&v)[R]) {
             for (int a = 0; a < h; ++a) {
                 const float2 x = v[g + a], y = v[g + a + h];
                 v[g + a] = cadd(x, y);
-                v[g + a + h] = rot32(csub(x, y), a * (16 / h));
+                if (!(FIRST_HALF && h == 1)) v[g + a + h] = rot32(csub(x, y), a * (16 / h));
             }
         }
     }
@@ -116,30 +118,40 @@ template <> struct Acc<float> {
 
 constexpr float kScreenMargin = 8e-6f;   // > 2 x fp32 screening error + one float32 ulp at 1.0
 
+// 8 consecutive samples starting at element index e (any alignment) as one 64-bit word
+__device__ __forceinline__ unsigned long long load8(const uint8_t* __restrict__ p, int64_t e) {
+    const int64_t a8 = e & ~(int64_t)7;
+    const unsigned sh = (unsigned)(e & 7) * 8u;
+    const unsigned long long w0 = __ldg(reinterpret_cast<const unsigned long long*>(p + a8));
+    if (sh == 0) return w0;
+    const unsigned long long w1 = __ldg(reinterpret_cast<const unsigned long long*>(p + a8 + 8));
+    return (w0 >> sh) | (w1 << (64u - sh));
+}
+
 // ---------------------------------------------------------------- the kernel
 template <int LOGN, typename S>
 __global__ void __launch_bounds__(Cfg<LOGN>::T, Cfg<LOGN>::MINB)
 k_match_fused(const float2* __restrict__ That, int64_t part_first,
               const float2* __restrict__ Xhat, int64_t nblk,
               const S* __restrict__ img, int64_t img_n,
-              const double* __restrict__ ipsum, const double* __restrict__ ipsq,
-              const double* __restrict__ tpsum, const double* __restrict__ tpsq,
+              const double2* __restrict__ ipfx, const double2* __restrict__ tpfx,
               const QueryDesc* __restrict__ desc, int q_begin, int q_end, int64_t item_first,
               FusedTables tab, unsigned long long* __restrict__ keys, float* __restrict__ curve_out) {
     typedef Cfg<LOGN> C;
-    typedef typename Acc<S>::type acc_t;
     constexpr int N = C::N, T = C::T, B = C::N;
     constexpr int NB = B + 1;                       // bins per spectrum row
     constexpr int LAGS_PER_ROUND = T * 8;           // 8 consecutive lags per thread per round
     constexpr int ROUNDS = B / LAGS_PER_ROUND;      // 4
     constexpr int NW = T / 32;
+    constexpr int NT2 = C::R2 * 32, NT3 = C::R3 * 32;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* buf = reinterpret_cast<float2*>(smem_raw);                  // pad(N) complex values
-    acc_t* s_wq = reinterpret_cast<acc_t*>(buf + pad(N) + 1);           // [ROUNDS*NW] warp totals / offsets
-    acc_t* s_ws = s_wq + ROUNDS * NW;
-    float* s_min = reinterpret_cast<float*>(s_ws + ROUNDS * NW);        // [NW]
-    unsigned long long* s_best = reinterpret_cast<unsigned long long*>(s_min + NW + (NW & 1));   // [NW]
+    float2* s_t2 = buf + pad(N) + 1;                                    // twiddle tables
+    float2* s_a3 = s_t2 + NT2;
+    float2* s_b3 = s_a3 + NT3;
+    unsigned long long* s_best = reinterpret_cast<unsigned long long*>(s_b3 + NT3);   // [NW]
+    float* s_min = reinterpret_cast<float*>(s_best + NW);               // [NW]
     __shared__ int s_q;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -149,6 +161,9 @@ k_match_fused(const float2* __restrict__ That, int64_t part_first,
         while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (desc[mid].itemBase <= item) lo = mid; else hi = mid - 1; }
         s_q = lo;
     }
+    // stage the FFT twiddle tables (16 KB) while the lookup resolves
+    for (int i = tid; i < NT2; i += T) s_t2[i] = __ldg(tab.t2 + i);
+    for (int i = tid; i < NT3; i += T) { s_a3[i] = __ldg(tab.a3 + i); s_b3[i] = __ldg(tab.b3 + i); }
     __syncthreads();
     const int q = s_q;
     const QueryDesc d = desc[q];
@@ -160,40 +175,50 @@ k_match_fused(const float2* __restrict__ That, int64_t part_first,
         if (k + P > nblk) P = (int)(nblk - k);      // blocks past the end of the stream are zero
         const float2* tp = That + (d.partBase - part_first) * (int64_t)NB;
         const float2* xp = Xhat + k * (int64_t)NB;
-        constexpr int U = 4;                        // bin pairs in flight per thread
-        for (int m0 = tid; m0 <= B / 2; m0 += U * T) {
+        constexpr int U = 8;                        // bin pairs in flight per thread
+        static_assert((B / 2) % (U * T) == 0, "pair loop must tile B/2");
+        // pairs (m, B-m), m = 1 .. B/2-1, plus m = 0 whose partner is the Nyquist bin B
+        for (int m0 = tid; m0 < B / 2; m0 += U * T) {
             float2 ym[U], yp[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) { ym[u] = make_float2(0.f, 0.f); yp[u] = make_float2(0.f, 0.f); }
             for (int p = 0; p < P; ++p) {
                 const float2* t = tp + (int64_t)p * NB;
                 const float2* x = xp + (int64_t)p * NB;
+                float2 t1[U], x1[U], t2[U], x2[U];
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const int m = m0 + u * T;
-                    if (m <= B / 2) {
-                        const float2 t1 = __ldg(t + m), x1 = __ldg(x + m);
-                        const float2 t2 = __ldg(t + (B - m)), x2 = __ldg(x + (B - m));
-                        ym[u].x += t1.x * x1.x + t1.y * x1.y;  ym[u].y += t1.x * x1.y - t1.y * x1.x;
-                        yp[u].x += t2.x * x2.x + t2.y * x2.y;  yp[u].y += t2.x * x2.y - t2.y * x2.x;
-                    }
+                    t1[u] = __ldg(t + m); x1[u] = __ldg(x + m);
+                    t2[u] = __ldg(t + (B - m)); x2[u] = __ldg(x + (B - m));
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    ym[u].x += t1[u].x * x1[u].x + t1[u].y * x1[u].y;  ym[u].y += t1[u].x * x1[u].y - t1[u].y * x1[u].x;
+                    yp[u].x += t2[u].x * x2[u].x + t2[u].y * x2[u].y;  yp[u].y += t2[u].x * x2[u].y - t2[u].y * x2[u].x;
                 }
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int m = m0 + u * T;
-                if (m <= B / 2) {
-                    const float2 w = __ldg(tab.w + m);                 // exp(+i*pi*m/B)
-                    // Z[m]   = (Ym + conj(Yp)) + i*(Ym - conj(Yp))*w
-                    const float2 e = make_float2(ym[u].x + yp[u].x, ym[u].y - yp[u].y);
-                    const float2 o = cmul(make_float2(ym[u].x - yp[u].x, ym[u].y + yp[u].y), w);
-                    buf[pad(m)] = make_float2(e.x - o.y, e.y + o.x);
-                    if (m > 0 && m < B / 2) {
-                        // Z[B-m] = conj(e) + i*(Yp - conj(Ym))*(-conj(w)) = conj(e) + i*conj(o)
-                        buf[pad(B - m)] = make_float2(e.x + o.y, -e.y + o.x);
-                    }
-                }
+                const float2 w = __ldg(tab.w + m);                     // exp(+i*pi*m/B)
+                // Z[m]   = (Ym + conj(Yp)) + i*(Ym - conj(Yp))*w
+                const float2 e = make_float2(ym[u].x + yp[u].x, ym[u].y - yp[u].y);
+                const float2 o = cmul(make_float2(ym[u].x - yp[u].x, ym[u].y + yp[u].y), w);
+                buf[pad(m)] = make_float2(e.x - o.y, e.y + o.x);
+                // Z[B-m] = conj(e) + i*conj(o)   (w^(B-m) = -conj(w^m))
+                if (m > 0) buf[pad(B - m)] = make_float2(e.x + o.y, -e.y + o.x);
             }
+        }
+        if (tid < 32) {                             // the self-paired bin m = B/2 (w = i): Z = 2*conj(Y)
+            float2 y = make_float2(0.f, 0.f);
+            for (int p = lane; p < P; p += 32) {
+                const float2 t1 = __ldg(tp + (int64_t)p * NB + B / 2), x1 = __ldg(xp + (int64_t)p * NB + B / 2);
+                y.x += t1.x * x1.x + t1.y * x1.y;  y.y += t1.x * x1.y - t1.y * x1.x;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { y.x += __shfl_xor_sync(0xffffffffu, y.x, o); y.y += __shfl_xor_sync(0xffffffffu, y.y, o); }
+            if (lane == 0) buf[pad(B / 2)] = make_float2(2.f * y.x, -2.f * y.y);
         }
     }
     __syncthreads();
@@ -226,7 +251,7 @@ k_match_fused(const float2* __restrict__ That, int64_t part_first,
         for (int b = 0; b < PER; ++b) {
             const int j = tid + b * T;
 #pragma unroll
-            for (int r = 1; r < R; ++r) v[b][r] = cmul(v[b][r], __ldg(tab.t2 + r * 32 + lane));
+            for (int r = 1; r < R; ++r) v[b][r] = cmul(v[b][r], s_t2[r * 32 + lane]);
             dft_dif<R>(v[b]);
             const int j0 = (j - lane) * R + lane;
 #pragma unroll
@@ -250,8 +275,8 @@ k_match_fused(const float2* __restrict__ That, int64_t part_first,
             const int kh = j >> 5;
 #pragma unroll
             for (int r = 1; r < R; ++r)
-                v[b][r] = cmul(v[b][r], cmul(__ldg(tab.a3 + r * 32 + lane), __ldg(tab.b3 + r * 32 + kh)));
-            dft_dif<R>(v[b]);
+                v[b][r] = cmul(v[b][r], cmul(s_a3[r * 32 + lane], s_b3[r * 32 + kh]));
+            dft_dif<R, true>(v[b]);
 #pragma unroll
             for (int r = 0; r < R / 2; ++r) buf[pad(j + r * Ns)] = v[b][brev<R>(r)];
         }
@@ -260,96 +285,70 @@ k_match_fused(const float2* __restrict__ That, int64_t part_first,
     // now buf[pad(i)] = (x[2i], x[2i+1]) for i < N/2: correlation at lags 2i, 2i+1 (times 2B)
 
     // ---------------- 4. window sums, fp32 screening, fp64 exact evaluation -----------------
+    // Every thread owns runs of 8 consecutive lags.  The exact window sums at the first lag of a
+    // run come from the interleaved fp64 running sums (two 16-byte loads per run); inside the run
+    // the window slides on the raw samples: W[j+1] = W[j] + I[j+n]^k - I[j]^k.
     const int64_t n = d.tlen;
     const int64_t jlo = d.lag0, jhi = d.lag0 + d.nlags;
     const int64_t j_blk = k * B;
-    const int64_t jb = j_blk > jlo ? j_blk : jlo;          // first lag of this item that can be valid
-    const double tsum = tpsum[d.toff + n] - tpsum[d.toff];
-    const double tsq = tpsq[d.toff + n] - tpsq[d.toff];
-    const double a = (double)Acc<S>::centre(ipsum[img_n], (double)img_n);
+    const double2 t_hi = tpfx[d.toff + n], t_lo = tpfx[d.toff];
+    const double tsum = t_hi.x - t_lo.x, tsq = t_hi.y - t_lo.y;
+    const double a = (double)Acc<S>::centre(ipfx[img_n].x, (double)img_n);
     const double b = (double)Acc<S>::centre(tsum, (double)n);
     const double n_ab = (double)n * a * b;
     const double scale = 1.0 / (double)(2 * B);
-    const double base_ws = ipsum[jb + n] - ipsum[jb];
-    const double base_wq = ipsq[jb + n] - ipsq[jb];
+    const double k_const = a * tsum - n_ab;
+    const float f_tsq = (float)tsq, f_b = (float)b, f_scale = (float)scale;
+    const bool interior = j_blk >= jlo && j_blk + B <= jhi;           // every lag of the item is valid
 
-    // thread-local sliding deltas: round c, lags j_blk + c*LAGS_PER_ROUND + tid*8 + i
-    acc_t pq[ROUNDS], ps[ROUNDS];                   // exclusive offsets of this thread's 8-lag runs
-    {
-        acc_t tq[ROUNDS], ts[ROUNDS];
-#pragma unroll
-        for (int c = 0; c < ROUNDS; ++c) {
-            const int64_t j0 = j_blk + c * LAGS_PER_ROUND + tid * 8;
-            acc_t aq = 0, as = 0;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int64_t j = j0 + i;
-                if (j >= jb && j + n < img_n) {
-                    const S lo = img[j], hi = img[j + n];
-                    aq += Acc<S>::sq(hi, lo); as += Acc<S>::ln(hi, lo);
-                }
-            }
-            tq[c] = aq; ts[c] = as;
-            acc_t iq = aq, is = as;                 // inclusive warp scan
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                acc_t uq = __shfl_up_sync(0xffffffffu, iq, o), us = __shfl_up_sync(0xffffffffu, is, o);
-                if (lane >= o) { iq += uq; is += us; }
-            }
-            if (lane == 31) { s_wq[c * NW + warp] = iq; s_ws[c * NW + warp] = is; }
-            pq[c] = iq - aq; ps[c] = is - as;
-        }
-        __syncthreads();
-        if (warp == 0) {                            // exclusive scan over the ROUNDS*NW warp totals
-            acc_t carry_q = 0, carry_s = 0;
-            for (int e0 = 0; e0 < ROUNDS * NW; e0 += 32) {
-                const int e = e0 + lane;
-                acc_t vq = e < ROUNDS * NW ? s_wq[e] : 0, vs = e < ROUNDS * NW ? s_ws[e] : 0;
-                acc_t iq = vq, is = vs;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    acc_t uq = __shfl_up_sync(0xffffffffu, iq, o), us = __shfl_up_sync(0xffffffffu, is, o);
-                    if (lane >= o) { iq += uq; is += us; }
-                }
-                if (e < ROUNDS * NW) { s_wq[e] = carry_q + iq - vq; s_ws[e] = carry_s + is - vs; }
-                carry_q += __shfl_sync(0xffffffffu, iq, 31); carry_s += __shfl_sync(0xffffffffu, is, 31);
-            }
-        }
-        __syncthreads();
-#pragma unroll
-        for (int c = 0; c < ROUNDS; ++c) { pq[c] += s_wq[c * NW + warp]; ps[c] += s_ws[c * NW + warp]; }
-    }
-
-    // fp32 screening of every lag this thread owns
-    const float f_tsq = (float)tsq, f_bwq = (float)base_wq, f_b = (float)b;
-    const float f_k0 = (float)(b * base_ws + a * tsum - n_ab);
-    const float f_scale = (float)scale;
     float vf[ROUNDS][8];
     float tmin = 2.0f;
 #pragma unroll
     for (int c = 0; c < ROUNDS; ++c) {
-        const int i0 = (c * LAGS_PER_ROUND + tid * 8) >> 1;          // complex index of the first lag pair
-        float cc[8];
+        const int m0 = c * LAGS_PER_ROUND + tid * 8;
+        const int64_t j0 = j_blk + m0;
 #pragma unroll
-        for (int h = 0; h < 4; ++h) { const float2 z = buf[pad(i0 + h)]; cc[2 * h] = z.x; cc[2 * h + 1] = z.y; }
-        const int64_t j0 = j_blk + c * LAGS_PER_ROUND + tid * 8;
-        acc_t rq = pq[c], rs = ps[c];
+        for (int i = 0; i < 8; ++i) vf[c][i] = 2.0f;                  // sentinel: not a valid lag
+        if (j0 < jhi && j0 + 8 > jlo) {                               // the run holds a valid lag
+            const double2 p_hi = ipfx[j0 + n], p_lo = ipfx[j0];
+            const double w0s = p_hi.x - p_lo.x, w0q = p_hi.y - p_lo.y;
+            const float f_w0q = (float)w0q;
+            const float f_k0 = (float)(b * w0s + k_const);
+            float cc[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int64_t j = j0 + i;
-            float v = 2.0f;                                           // sentinel: not a valid lag
-            if (j >= jlo && j < jhi) {
-                const float wq = f_bwq + (float)rq;
-                const float sit = fmaf(cc[i], f_scale, fmaf(f_b, (float)rs, f_k0));
-                const float num = fmaxf((wq + f_tsq) - 2.0f * sit, 0.0f);
-                const float pr = wq * f_tsq;
-                v = pr > 0.0f ? fminf(num * rsqrtf(pr), 1.0f) : 1.0f;
-            }
-            vf[c][i] = v;
-            tmin = fminf(tmin, v);
-            if (j >= jb && j + n < img_n) {                           // same deltas as above
-                const S lo = img[j], hi = img[j + n];
-                rq += Acc<S>::sq(hi, lo); rs += Acc<S>::ln(hi, lo);
+            for (int h = 0; h < 4; ++h) { const float2 z = buf[pad((m0 >> 1) + h)]; cc[2 * h] = z.x; cc[2 * h + 1] = z.y; }
+            if (sizeof(S) == 1) {
+                const uint8_t* img8 = reinterpret_cast<const uint8_t*>(img);
+                const unsigned long long lo8 = __ldg(reinterpret_cast<const unsigned long long*>(img8 + j0));   // j0 % 8 == 0
+                const unsigned long long hi8 = load8(img8, j0 + n);
+                int rq = 0, rs = 0;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float wq = f_w0q + (float)rq;
+                    const float sit = fmaf(cc[i], f_scale, fmaf(f_b, (float)rs, f_k0));
+                    const float num = fmaxf((wq + f_tsq) - 2.0f * sit, 0.0f);
+                    const float pr = wq * f_tsq;
+                    const float v = pr > 0.0f ? fminf(num * rsqrtf(pr), 1.0f) : 1.0f;
+                    if (interior || (j0 + i >= jlo && j0 + i < jhi)) { vf[c][i] = v; tmin = fminf(tmin, v); }
+                    const int lo = (int)((lo8 >> (8 * i)) & 0xffu), hi = (int)((hi8 >> (8 * i)) & 0xffu);
+                    rq += hi * hi - lo * lo; rs += hi - lo;
+                }
+            } else {
+                double rq = 0.0, rs = 0.0;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int64_t j = j0 + i;
+                    const float wq = f_w0q + (float)rq;
+                    const float sit = fmaf(cc[i], f_scale, fmaf(f_b, (float)rs, f_k0));
+                    const float num = fmaxf((wq + f_tsq) - 2.0f * sit, 0.0f);
+                    const float pr = wq * f_tsq;
+                    const float v = pr > 0.0f ? fminf(num * rsqrtf(pr), 1.0f) : 1.0f;
+                    if (j >= jlo && j < jhi) { vf[c][i] = v; tmin = fminf(tmin, v); }
+                    if (j + n < img_n) {
+                        const double lo = (double)img[j], hi = (double)img[j + n];
+                        rq += hi * hi - lo * lo; rs += hi - lo;
+                    }
+                }
             }
         }
     }
@@ -372,9 +371,8 @@ k_match_fused(const float2* __restrict__ That, int64_t part_first,
                 const int64_t j = j_blk + m;
                 const float2 z = buf[pad(m >> 1)];
                 const double cc = (double)((m & 1) ? z.y : z.x) * scale;
-                const double wsum = ipsum[j + n] - ipsum[j];
-                const double wsq = ipsq[j + n] - ipsq[j];
-                const float v = sqdiff_exact(cc, wsum, wsq, a, b, tsum, tsq, n_ab);
+                const double2 p_hi = ipfx[j + n], p_lo = ipfx[j];
+                const float v = sqdiff_exact(cc, p_hi.x - p_lo.x, p_hi.y - p_lo.y, a, b, tsum, tsq, n_ab);
                 if (curve_out) curve_out[j - jlo] = v;
                 const unsigned long long key = ((unsigned long long)__float_as_uint(v) << 32) | (unsigned int)(j - jlo);
                 best = key < best ? key : best;
@@ -398,8 +396,8 @@ k_match_fused(const float2* __restrict__ That, int64_t part_first,
 template <int LOGN> size_t fused_smem_bytes() {
     typedef Cfg<LOGN> C;
     const size_t padded = (size_t)(C::N + (C::N >> 5) + 1);
-    const size_t nw = C::T / 32, rounds = C::N / (C::T * 8);
-    return padded * sizeof(float2) + 2 * rounds * nw * sizeof(double) + (nw + 2) * sizeof(float) + nw * sizeof(unsigned long long) + 64;
+    const size_t nw = C::T / 32;
+    return (padded + C::R2 * 32 + 2 * C::R3 * 32) * sizeof(float2) + nw * sizeof(unsigned long long) + nw * sizeof(float) + 64;
 }
 
 struct TableSet { float2* dev = nullptr; FusedTables tab; };
@@ -451,7 +449,7 @@ int launch_typed(const sb_stream* image, const sb_stream* tmpl, const float2* d_
         const int64_t ni = std::min<int64_t>(max_grid, n_items - i0);
         k_match_fused<LOGN, S><<<(unsigned)ni, Cfg<LOGN>::T, smem, c.stream>>>(
             d_parts, part_first, image->d_spec, image->nblk, static_cast<const S*>(image->d_raw), image->n,
-            image->d_psum, image->d_psq, tmpl->d_psum, tmpl->d_psq, d_desc, q_begin, q_end, item_first + i0,
+            image->d_pfx, tmpl->d_pfx, d_desc, q_begin, q_end, item_first + i0,
             tab, d_keys, d_curve);
     }
     SB_CUDA(cudaGetLastError());

@@ -114,8 +114,7 @@ struct sb_stream {
     int64_t n = 0;
     int dtype = SB_U8;
     void* d_raw = nullptr;        // n samples (u8 or f32)
-    double* d_psum = nullptr;     // [n+1] running sum of samples        (exact for u8)
-    double* d_psq = nullptr;      // [n+1] running sum of squared samples (exact for u8)
+    double2* d_pfx = nullptr;     // [n+1] running sums: .x = sum of samples, .y = sum of squares (exact for u8)
     // block spectra for lag-block size specB: [nblk][specB+1] complex64
     float2* d_spec = nullptr;
     int specB = 0;

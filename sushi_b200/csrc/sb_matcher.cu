@@ -35,7 +35,7 @@ template <> __device__ __forceinline__ float centre_of<float>(double sum, double
 // One CTA chunk writes 2048 floats of one partition row (row stride 2B+2 floats).
 template <typename T>
 __global__ void __launch_bounds__(256)
-k_gather_parts(const T* __restrict__ tmpl, const double* __restrict__ tpsum,
+k_gather_parts(const T* __restrict__ tmpl, const double2* __restrict__ tpfx,
                const QueryDesc* __restrict__ desc, int q_begin, int q_end,
                int64_t part_first, int B, float* __restrict__ rows, int chunks_per_row) {
     __shared__ int s_q;
@@ -49,7 +49,7 @@ k_gather_parts(const T* __restrict__ tmpl, const double* __restrict__ tpsum,
     }
     __syncthreads();
     const QueryDesc d = desc[s_q];
-    const float b = centre_of<T>(tpsum[d.toff + d.tlen] - tpsum[d.toff], (double)d.tlen);
+    const float b = centre_of<T>(tpfx[d.toff + d.tlen].x - tpfx[d.toff].x, (double)d.tlen);
     const int64_t p = part - d.partBase;
     const int64_t seg0 = p * B;                     // offset of this partition inside the template
     float* out = rows + row * (int64_t)(2 * B + 2);
@@ -168,8 +168,7 @@ template <> struct Slide<float> {
 template <typename T>
 __global__ void __launch_bounds__(NORM_THREADS)
 k_normalise_argmin(const float* __restrict__ corr_rows, const T* __restrict__ img, int64_t img_n,
-                   const double* __restrict__ ipsum, const double* __restrict__ ipsq,
-                   const double* __restrict__ tpsum, const double* __restrict__ tpsq,
+                   const double2* __restrict__ ipfx, const double2* __restrict__ tpfx,
                    const QueryDesc* __restrict__ desc, int q_begin, int q_end, int64_t item_first,
                    int B, unsigned long long* __restrict__ keys, float* __restrict__ curve_out,
                    int chunks_per_item) {
@@ -191,17 +190,19 @@ k_normalise_argmin(const float* __restrict__ corr_rows, const T* __restrict__ im
     const int64_t j_blk = k * B + m_blk;
     if (m_blk >= B || j_blk >= jhi || j_blk + NORM_LAGS <= jlo) return;   // nothing valid here (uniform)
 
-    const double tsum = tpsum[d.toff + n] - tpsum[d.toff];
-    const double tsq = tpsq[d.toff + n] - tpsq[d.toff];
-    const double a = (double)centre_of<T>(ipsum[img_n], (double)img_n);
+    const double2 t_hi = tpfx[d.toff + n], t_lo = tpfx[d.toff];
+    const double tsum = t_hi.x - t_lo.x;
+    const double tsq = t_hi.y - t_lo.y;
+    const double a = (double)centre_of<T>(ipfx[img_n].x, (double)img_n);
     const double b = (double)centre_of<T>(tsum, (double)n);
     const double n_ab = (double)n * a * b;
     const double scale = 1.0 / (double)(2 * B);      // cuFFT transforms are unnormalised
     // the scan starts at the first lag of this CTA that can be valid, so that its base window
     // [jb, jb+n) lies inside the stream
     const int64_t jb = j_blk > jlo ? j_blk : jlo;
-    const double base_ws = ipsum[jb + n] - ipsum[jb];
-    const double base_wq = ipsq[jb + n] - ipsq[jb];
+    const double2 b_hi = ipfx[jb + n], b_lo = ipfx[jb];
+    const double base_ws = b_hi.x - b_lo.x;
+    const double base_wq = b_hi.y - b_lo.y;
 
     // thread t owns lags j0 .. j0+7; delta_i moves the window from j0+i to j0+i+1
     const int m0 = m_blk + threadIdx.x * NORM_PER;
@@ -364,10 +365,10 @@ int run_batch(const sb_stream* image_c, const sb_stream* tmpl, int64_t count,
                 ProfScope ps("gather_parts");
                 if (tmpl->dtype == SB_U8)
                     k_gather_parts<uint8_t><<<(unsigned)(rows * gchunks), 256, 0, c.stream>>>(
-                        static_cast<const uint8_t*>(tmpl->d_raw), tmpl->d_psum, c.d_desc, (int)qb, (int)qe, part_first + p0, B, dst, gchunks);
+                        static_cast<const uint8_t*>(tmpl->d_raw), tmpl->d_pfx, c.d_desc, (int)qb, (int)qe, part_first + p0, B, dst, gchunks);
                 else
                     k_gather_parts<float><<<(unsigned)(rows * gchunks), 256, 0, c.stream>>>(
-                        static_cast<const float*>(tmpl->d_raw), tmpl->d_psum, c.d_desc, (int)qb, (int)qe, part_first + p0, B, dst, gchunks);
+                        static_cast<const float*>(tmpl->d_raw), tmpl->d_pfx, c.d_desc, (int)qb, (int)qe, part_first + p0, B, dst, gchunks);
             }
             cufftHandle plan;
             SB_TRY(get_plan(CUFFT_R2C, rows, &plan));
@@ -402,12 +403,12 @@ int run_batch(const sb_stream* image_c, const sb_stream* tmpl, int64_t count,
                 if (image->dtype == SB_U8)
                     k_normalise_argmin<uint8_t><<<(unsigned)(ni * nchunks), NORM_THREADS, 0, c.stream>>>(
                         reinterpret_cast<const float*>(c.d_items), static_cast<const uint8_t*>(image->d_raw), image->n,
-                        image->d_psum, image->d_psq, tmpl->d_psum, tmpl->d_psq,
+                        image->d_pfx, tmpl->d_pfx,
                         c.d_desc, (int)qb, (int)qe, i0, B, c.d_keys, d_curve, nchunks);
                 else
                     k_normalise_argmin<float><<<(unsigned)(ni * nchunks), NORM_THREADS, 0, c.stream>>>(
                         reinterpret_cast<const float*>(c.d_items), static_cast<const float*>(image->d_raw), image->n,
-                        image->d_psum, image->d_psq, tmpl->d_psum, tmpl->d_psq,
+                        image->d_pfx, tmpl->d_pfx,
                         c.d_desc, (int)qb, (int)qe, i0, B, c.d_keys, d_curve, nchunks);
             }
         }

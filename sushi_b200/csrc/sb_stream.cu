@@ -82,7 +82,7 @@ k_scan_tile_totals(double* __restrict__ tsum, double* __restrict__ tsq, int64_t 
 template <typename T>
 __global__ void __launch_bounds__(SCAN_THREADS)
 k_tile_scan(const T* __restrict__ x, int64_t n, const double* __restrict__ osum, const double* __restrict__ osq,
-            double* __restrict__ psum, double* __restrict__ psq) {
+            double2* __restrict__ pfx) {
     __shared__ double s_a[SCAN_THREADS / 32], s_b[SCAN_THREADS / 32];
     const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
     double va[SCAN_ITEMS], vb[SCAN_ITEMS];
@@ -110,18 +110,18 @@ k_tile_scan(const T* __restrict__ x, int64_t n, const double* __restrict__ osum,
 #pragma unroll
     for (int i = 0; i < SCAN_ITEMS; ++i) {
         int64_t j = base + i;
-        if (j < n) { psum[j + 1] = offa + va[i]; psq[j + 1] = offb + vb[i]; }
+        if (j < n) pfx[j + 1] = make_double2(offa + va[i], offb + vb[i]);
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) { psum[0] = 0.0; psq[0] = 0.0; }
+    if (blockIdx.x == 0 && threadIdx.x == 0) pfx[0] = make_double2(0.0, 0.0);
 }
 
 // Centred float rows for the block spectra: row k holds image[kB .. kB+2B) - c,
 // zero beyond the end of the stream; rows are (2B+2) floats apart (in-place R2C).
 template <typename T>
 __global__ void __launch_bounds__(256)
-k_gather_blocks(const T* __restrict__ x, int64_t n, const double* __restrict__ psum, int B, float* __restrict__ rows,
+k_gather_blocks(const T* __restrict__ x, int64_t n, const double2* __restrict__ pfx, int B, float* __restrict__ rows,
                 int64_t k_first, int chunks_per_row) {
-    const float c = sizeof(T) == 1 ? (float)rint(psum[n] / (double)n) : (float)(psum[n] / (double)n);   // = centre_of<T>
+    const float c = sizeof(T) == 1 ? (float)rint(pfx[n].x / (double)n) : (float)(pfx[n].x / (double)n);   // = centre_of<T>
     const int64_t row = blockIdx.x / chunks_per_row;
     const int chunk = blockIdx.x % chunks_per_row;
     const int64_t k = k_first + row;
@@ -159,7 +159,7 @@ int build_prefix(sb_stream* s) {
     }
     {
         ProfScope ps("scan_tiles");
-        k_tile_scan<T><<<(unsigned)ntiles, SCAN_THREADS, 0, c.stream>>>(x, n, tsum, tsq, s->d_psum, s->d_psq);
+        k_tile_scan<T><<<(unsigned)ntiles, SCAN_THREADS, 0, c.stream>>>(x, n, tsum, tsq, s->d_pfx);
     }
     SB_CUDA(cudaGetLastError());
     pool_free(d_t);            // reused only by later work on the same stream
@@ -167,8 +167,7 @@ int build_prefix(sb_stream* s) {
 }
 
 int stream_finish(sb_stream* s) {
-    SB_TRY(pool_alloc((void**)&s->d_psum, sizeof(double) * (s->n + 1)));
-    SB_TRY(pool_alloc((void**)&s->d_psq, sizeof(double) * (s->n + 1)));
+    SB_TRY(pool_alloc((void**)&s->d_pfx, sizeof(double2) * (s->n + 1)));
     if (s->dtype == SB_U8) return build_prefix<uint8_t>(s);
     return build_prefix<float>(s);
 }
@@ -209,10 +208,10 @@ int ensure_spectra(sb_stream* s) {
             ProfScope ps("gather_blocks");
             if (s->dtype == SB_U8)
                 k_gather_blocks<uint8_t><<<(unsigned)(rows * chunks), 256, 0, c.stream>>>(
-                    static_cast<const uint8_t*>(s->d_raw), s->n, s->d_psum, B, dst, k, chunks);
+                    static_cast<const uint8_t*>(s->d_raw), s->n, s->d_pfx, B, dst, k, chunks);
             else
                 k_gather_blocks<float><<<(unsigned)(rows * chunks), 256, 0, c.stream>>>(
-                    static_cast<const float*>(s->d_raw), s->n, s->d_psum, B, dst, k, chunks);
+                    static_cast<const float*>(s->d_raw), s->n, s->d_pfx, B, dst, k, chunks);
         }
         cufftHandle plan;
         SB_TRY(get_plan(CUFFT_R2C, rows, &plan));
@@ -262,7 +261,7 @@ int sb_stream_destroy(sb_stream* s) {
     if (!s) return SB_OK;
     Ctx& c = ctx();
     (void)c;
-    pool_free(s->d_raw); pool_free(s->d_psum); pool_free(s->d_psq); pool_free(s->d_spec);
+    pool_free(s->d_raw); pool_free(s->d_pfx); pool_free(s->d_spec);
     delete s;
     return SB_OK;
 }
