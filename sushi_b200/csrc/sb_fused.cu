@@ -135,7 +135,7 @@ k_match_fused(const float2* __restrict__ That, int64_t part_first,
               const float2* __restrict__ Xhat, int64_t nblk,
               const S* __restrict__ img, int64_t img_n,
               const double2* __restrict__ ipfx, const double2* __restrict__ tpfx,
-              const QueryDesc* __restrict__ desc, int q_begin, int q_end, int64_t item_first,
+              const QueryDesc* __restrict__ desc, const int* __restrict__ item_query, int64_t item_first,
               FusedTables tab, unsigned long long* __restrict__ keys, float* __restrict__ curve_out) {
     typedef Cfg<LOGN> C;
     constexpr int N = C::N, T = C::T, B = C::N;
@@ -152,20 +152,13 @@ k_match_fused(const float2* __restrict__ That, int64_t part_first,
     float2* s_b3 = s_a3 + NT3;
     unsigned long long* s_best = reinterpret_cast<unsigned long long*>(s_b3 + NT3);   // [NW]
     float* s_min = reinterpret_cast<float*>(s_best + NW);               // [NW]
-    __shared__ int s_q;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t item = item_first + blockIdx.x;
-    if (tid == 0) {
-        int lo = q_begin, hi = q_end - 1;
-        while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (desc[mid].itemBase <= item) lo = mid; else hi = mid - 1; }
-        s_q = lo;
-    }
-    // stage the FFT twiddle tables (16 KB) while the lookup resolves
+    const int q = __ldg(item_query + blockIdx.x);     // which query this lag block belongs to
+    // stage the FFT twiddle tables (16 KB); first needed in pass 2, several barriers from here
     for (int i = tid; i < NT2; i += T) s_t2[i] = __ldg(tab.t2 + i);
     for (int i = tid; i < NT3; i += T) { s_a3[i] = __ldg(tab.a3 + i); s_b3[i] = __ldg(tab.b3 + i); }
-    __syncthreads();
-    const int q = s_q;
     const QueryDesc d = desc[q];
     const int64_t k = d.k0 + (item - d.itemBase);
 
@@ -301,6 +294,20 @@ k_match_fused(const float2* __restrict__ That, int64_t part_first,
     const float f_tsq = (float)tsq, f_b = (float)b, f_scale = (float)scale;
     const bool interior = j_blk >= jlo && j_blk + B <= jhi;           // every lag of the item is valid
 
+    // exact window sums at the head of each run, fetched up front (two 16-byte loads per run)
+    double w0s[ROUNDS], w0q[ROUNDS];
+    bool live[ROUNDS];
+#pragma unroll
+    for (int c = 0; c < ROUNDS; ++c) {
+        const int64_t j0 = j_blk + c * LAGS_PER_ROUND + tid * 8;
+        live[c] = j0 < jhi && j0 + 8 > jlo;                           // the run holds a valid lag
+        w0s[c] = 0.0; w0q[c] = 0.0;
+        if (live[c]) {
+            const double2 p_hi = ipfx[j0 + n], p_lo = ipfx[j0];
+            w0s[c] = p_hi.x - p_lo.x; w0q[c] = p_hi.y - p_lo.y;
+        }
+    }
+
     float vf[ROUNDS][8];
     float tmin = 2.0f;
 #pragma unroll
@@ -309,11 +316,9 @@ k_match_fused(const float2* __restrict__ That, int64_t part_first,
         const int64_t j0 = j_blk + m0;
 #pragma unroll
         for (int i = 0; i < 8; ++i) vf[c][i] = 2.0f;                  // sentinel: not a valid lag
-        if (j0 < jhi && j0 + 8 > jlo) {                               // the run holds a valid lag
-            const double2 p_hi = ipfx[j0 + n], p_lo = ipfx[j0];
-            const double w0s = p_hi.x - p_lo.x, w0q = p_hi.y - p_lo.y;
-            const float f_w0q = (float)w0q;
-            const float f_k0 = (float)(b * w0s + k_const);
+        if (live[c]) {
+            const float f_w0q = (float)w0q[c];
+            const float f_k0 = (float)(b * w0s[c] + k_const);
             float cc[8];
 #pragma unroll
             for (int h = 0; h < 4; ++h) { const float2 z = buf[pad((m0 >> 1) + h)]; cc[2 * h] = z.x; cc[2 * h + 1] = z.y; }
@@ -361,23 +366,25 @@ k_match_fused(const float2* __restrict__ That, int64_t part_first,
     for (int w = 1; w < NW; ++w) bmin = fminf(bmin, s_min[w]);
     const float thr = curve_out ? 1.5f : bmin + kScreenMargin;       // debug curve: evaluate everything
 
+    // lags that can still be the minimum (bit c*8+i), then ONE copy of the fp64 path
+    unsigned cand = 0;
+#pragma unroll
+    for (int c = 0; c < ROUNDS; ++c)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) cand |= (vf[c][i] <= thr) ? (1u << (c * 8 + i)) : 0u;
     unsigned long long best = ~0ull;
-#pragma unroll
-    for (int c = 0; c < ROUNDS; ++c) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            if (vf[c][i] <= thr) {
-                const int m = c * LAGS_PER_ROUND + tid * 8 + i;
-                const int64_t j = j_blk + m;
-                const float2 z = buf[pad(m >> 1)];
-                const double cc = (double)((m & 1) ? z.y : z.x) * scale;
-                const double2 p_hi = ipfx[j + n], p_lo = ipfx[j];
-                const float v = sqdiff_exact(cc, p_hi.x - p_lo.x, p_hi.y - p_lo.y, a, b, tsum, tsq, n_ab);
-                if (curve_out) curve_out[j - jlo] = v;
-                const unsigned long long key = ((unsigned long long)__float_as_uint(v) << 32) | (unsigned int)(j - jlo);
-                best = key < best ? key : best;
-            }
-        }
+    while (cand) {
+        const int bit = __ffs(cand) - 1;
+        cand &= cand - 1;
+        const int m = (bit >> 3) * LAGS_PER_ROUND + tid * 8 + (bit & 7);
+        const int64_t j = j_blk + m;
+        const float2 z = buf[pad(m >> 1)];
+        const double cc = (double)((m & 1) ? z.y : z.x) * scale;
+        const double2 p_hi = ipfx[j + n], p_lo = ipfx[j];
+        const float v = sqdiff_exact(cc, p_hi.x - p_lo.x, p_hi.y - p_lo.y, a, b, tsum, tsq, n_ab);
+        if (curve_out) curve_out[j - jlo] = v;
+        const unsigned long long key = ((unsigned long long)__float_as_uint(v) << 32) | (unsigned int)(j - jlo);
+        best = key < best ? key : best;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -431,6 +438,18 @@ template <int LOGN> int ensure_tables(FusedTables* out) {
     return SB_OK;
 }
 
+// item_query[i] = query of item (item_first + i): one CTA per query fills its own range
+__global__ void k_fill_item_query(const QueryDesc* __restrict__ desc, int q_begin, int64_t item_first,
+                                  int* __restrict__ item_query) {
+    const int q = q_begin + blockIdx.x;
+    const int64_t base = desc[q].itemBase - item_first;
+    const int nk = desc[q].nk;
+    for (int i = threadIdx.x; i < nk; i += blockDim.x) item_query[base + i] = q;
+}
+
+int* g_item_query = nullptr;
+int64_t g_item_query_cap = 0;
+
 template <int LOGN, typename S>
 int launch_typed(const sb_stream* image, const sb_stream* tmpl, const float2* d_parts, int64_t part_first,
                  const QueryDesc* d_desc, int q_begin, int q_end, int64_t item_first, int64_t n_items,
@@ -444,12 +463,20 @@ int launch_typed(const sb_stream* image, const sb_stream* tmpl, const float2* d_
         SB_CUDA(cudaFuncSetAttribute(k_match_fused<LOGN, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
+    if (g_item_query_cap < n_items) {
+        cudaStreamSynchronize(c.stream);
+        cudaFree(g_item_query); g_item_query = nullptr; g_item_query_cap = 0;
+        SB_CUDA(cudaMalloc(&g_item_query, sizeof(int) * (size_t)n_items));
+        g_item_query_cap = n_items;
+    }
+    k_fill_item_query<<<(unsigned)(q_end - q_begin), 128, 0, c.stream>>>(d_desc, q_begin, item_first, g_item_query);
+    c.launches += 1;
     const int64_t max_grid = 1 << 30;
     for (int64_t i0 = 0; i0 < n_items; i0 += max_grid) {
         const int64_t ni = std::min<int64_t>(max_grid, n_items - i0);
         k_match_fused<LOGN, S><<<(unsigned)ni, Cfg<LOGN>::T, smem, c.stream>>>(
             d_parts, part_first, image->d_spec, image->nblk, static_cast<const S*>(image->d_raw), image->n,
-            image->d_pfx, tmpl->d_pfx, d_desc, q_begin, q_end, item_first + i0,
+            image->d_pfx, tmpl->d_pfx, d_desc, g_item_query + i0, item_first + i0,
             tab, d_keys, d_curve);
     }
     SB_CUDA(cudaGetLastError());
@@ -478,6 +505,7 @@ int launch_match_fused(const sb_stream* image, const sb_stream* tmpl, const floa
 
 void fused_release_tables() {
     for (auto& t : g_tables) { if (t.dev) cudaFree(t.dev); t.dev = nullptr; }
+    cudaFree(g_item_query); g_item_query = nullptr; g_item_query_cap = 0;
 }
 
 }  // namespace sb
