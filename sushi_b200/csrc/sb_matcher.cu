@@ -426,6 +426,7 @@ int check_common(const char* who, const sb_stream* image, const sb_stream* tmpl,
     Ctx& c = ctx();
     if (!c.inited) SB_FAIL(SB_ESTATE, "%s: library not initialised (call sb_init)", who);
     if (!image || !tmpl) SB_FAIL(SB_EINVAL, "%s: NULL stream", who);
+    if (!image->d_pfx || !tmpl->d_pfx) SB_FAIL(SB_EINVAL, "%s: stream has no running sums (a raw sb_load_pcm stream must go through sb_normalise)", who);
     if (count < 0) SB_FAIL(SB_EINVAL, "%s: negative count", who);
     return SB_OK;
 }

@@ -191,6 +191,8 @@ int stream_alloc(int64_t n, int dtype, sb_stream** out, const char* who) {
 
 namespace sb {
 
+int stream_finish_public(sb_stream* s) { return stream_finish(s); }
+
 // Build (or fetch) the block spectra of `s` for the current block size.
 int ensure_spectra(sb_stream* s) {
     Ctx& c = ctx();

@@ -167,22 +167,62 @@ class WavStream(object):
     READ_CHUNK_SIZE = 1  # seconds per resample chunk (wav.py:105)
     PADDING_SECONDS = 10
 
-    def __init__(self, path, sample_rate=12000, sample_type='uint8', device=None):
+    def __init__(self, path, sample_rate=12000, sample_type='uint8', device=None, loader='gpu'):
+        """loader='gpu' (default): decode / resample / pad / normalise on the GPU (sb_load_pcm +
+        sb_normalise); loader='host' runs the NumPy mirror of the same arithmetic and uploads the
+        result (kept as the cross-check; both give bit-identical .data)."""
         if sample_type not in _DTYPES:
             raise SushiError('Unknown sample type of WAV stream, must be uint8 or float32')
         self._handle = None
         before_read = time()
         stream = DownmixedWavFile(path)
         try:
-            self._load(stream, sample_rate, sample_type)
+            if loader == 'gpu':
+                pcm = stream.read_raw(stream.frames_count)
+                self._load_gpu(pcm, stream.frames_count, stream.channels_count, stream.sample_width,
+                               stream.framerate, sample_rate, sample_type, device)
+            else:
+                self._load(stream, sample_rate, sample_type)
+                self._upload(device)
         except SushiError:
             raise
         except Exception as e:
             raise SushiError('Error while loading {0}: {1}'.format(path, e))
         finally:
             stream.close()
-        self._upload(device)
         logging.info('Done reading WAV {0} in {1}s'.format(path, time() - before_read))
+
+    def _load_gpu(self, pcm, frames, channels, sample_width, framerate, sample_rate, sample_type, device):
+        """wav.py:108-156 on the GPU: geometry here (same scalar code as the reference), arithmetic
+        in sb_load_pcm / sb_normalise; .data is then mirrored back for get_substream views."""
+        if sample_width not in (2, 3):
+            raise SushiError('Unsupported sample width: {0}'.format(sample_width))
+        frames = min(frames, len(pcm) // (channels * sample_width))
+        total_seconds = frames / float(framerate)
+        self.sample_count = math.ceil(total_seconds * sample_rate)
+        self.sample_rate = sample_rate
+        self.sample_type = sample_type
+        self.padding_size = 10 * framerate
+        total = int(self.PADDING_SECONDS * 2 * framerate + self.sample_count)
+        lib = _native.lib(device)
+        raw = ctypes.c_void_p()
+        buf = np.frombuffer(pcm, dtype=np.uint8)
+        _native.check(lib.sb_load_pcm(buf.ctypes.data_as(ctypes.c_void_p), frames, channels, sample_width,
+                                      framerate, sample_rate, self.padding_size, total, ctypes.byref(raw)), 'sb_load_pcm')
+        h = ctypes.c_void_p()
+        lo, hi = ctypes.c_float(), ctypes.c_float()
+        try:
+            _native.check(lib.sb_normalise(raw, _DTYPES[sample_type][1], ctypes.byref(h), ctypes.byref(lo),
+                                           ctypes.byref(hi)), 'sb_normalise')
+        finally:
+            lib.sb_stream_destroy(raw)
+        self.min_value, self.max_value = lo.value, hi.value
+        self._handle = h
+        self._lib = lib
+        self.data = np.empty((1, total), _DTYPES[sample_type][0])
+        _native.check(lib.sb_stream_read(h, 0, total, self.data.ctypes.data_as(ctypes.c_void_p)), 'sb_stream_read')
+        self._base = self.data.__array_interface__['data'][0]
+        _live_streams.add(self)
 
     # -- construction -----------------------------------------------------------------
     def _load(self, stream, sample_rate, sample_type):
@@ -216,12 +256,20 @@ class WavStream(object):
         self.data, self.min_value, self.max_value = normalise_host(data, sample_type)
 
     @classmethod
-    def from_pcm(cls, pcm, framerate, sample_rate=12000, sample_type='uint8', channels=1, device=None):
+    def from_pcm(cls, pcm, framerate, sample_rate=12000, sample_type='uint8', channels=1, device=None, loader='gpu'):
         """Build a stream from an in-memory int16 array (frames x channels, interleaved) --
         the same pipeline as a file load without the RIFF walk (synthetic benches/tests)."""
         class _Mem(object):
             pass
         pcm = np.ascontiguousarray(pcm, dtype='<i2')
+        if sample_type not in _DTYPES:
+            raise SushiError('Unknown sample type of WAV stream, must be uint8 or float32')
+        if loader == 'gpu':
+            self = object.__new__(cls)
+            self._handle = None
+            self._load_gpu(pcm.reshape(-1).view(np.uint8).tobytes(), pcm.size // channels, channels, 2,
+                           framerate, sample_rate, sample_type, device)
+            return self
         mem = _Mem()
         mem.framerate, mem.channels_count, mem.sample_width = framerate, channels, 2
         mem.frame_size = 2 * channels

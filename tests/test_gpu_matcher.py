@@ -243,3 +243,52 @@ def test_running_sums_are_exact_for_uint8(gpu_lib):
     s = WavStream.from_array(np.full((1, n), 255, np.uint8), 12000, 0, n)
     cur = s.match_curve(s, 1_000_000, 50_000, 2_900_000, 50_001)
     assert np.all(cur == cur[0]) and 0.0 <= cur[0] < 1e-7
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU loader (sb_load_pcm + sb_normalise) against the reference's golden loader outputs
+# ---------------------------------------------------------------------------------------------
+from tests.test_oracle_golden import LOADER_CASES   # noqa: E402
+
+
+@pytest.mark.parametrize('name', LOADER_CASES)
+@pytest.mark.parametrize('stype', ['uint8', 'float32'])
+def test_gpu_loader_matches_reference_golden(gpu_lib, golden_loader, name, stype):
+    g = golden_loader
+    fr, ch, sr = [int(v) for v in g[name + '_spec']]
+    s = WavStream.from_pcm(g[name + '_pcm'], fr, sr, stype, channels=ch, loader='gpu')
+    ref = g['{0}_{1}_data'.format(name, stype)]
+    rate, count, pad = [int(v) for v in g['{0}_{1}_meta'.format(name, stype)]]
+    assert (s.sample_rate, int(s.sample_count), s.padding_size) == (rate, count, pad)
+    assert s.data.dtype == ref.dtype and s.data.shape == ref.shape
+    assert np.array_equal(s.data, ref)                       # bit-exact, float32 included
+
+
+def test_gpu_loader_equals_host_mirror_on_long_stream(gpu_lib):
+    """10 minutes of stereo 44.1 kHz: the GPU loader and the NumPy mirror (itself pinned to the
+    reference golden vectors) agree bit for bit, medians over ~9 M samples included."""
+    fr = 44100
+    base = synth.programme_audio(fr * 600, 9, rate=fr)
+    pcm = np.stack([base, np.roll(base, 3) // 2], 1)
+    for stype in ('uint8', 'float32'):
+        a = WavStream.from_pcm(pcm, fr, 12000, stype, channels=2, loader='gpu')
+        b = WavStream.from_pcm(pcm, fr, 12000, stype, channels=2, loader='host')
+        assert np.array_equal(a.data, b.data)
+        assert a.sample_count == b.sample_count and a.padding_size == b.padding_size
+        assert abs(a.min_value - b.min_value) == 0 and abs(a.max_value - b.max_value) == 0
+
+
+def test_wav_file_load_int24(gpu_lib, tmp_path):
+    """RIFF file with 24-bit samples through the public constructor (GPU loader) vs the oracle."""
+    import struct
+    from oracle import ref_loader
+    fr, ch, frames = 48000, 2, 48000 * 2
+    rng = np.random.default_rng(4)
+    vals = rng.integers(-2 ** 23, 2 ** 23, frames * ch, dtype=np.int64)
+    payload = b''.join(int(v & 0xFFFFFF).to_bytes(3, 'little') for v in vals)
+    hdr = b'RIFF' + struct.pack('<L', 36 + len(payload)) + b'WAVE' + b'fmt ' + struct.pack('<LHHLLHH', 16, 1, ch, fr, fr * ch * 3, ch * 3, 24)
+    p = str(tmp_path / 'x24.wav')
+    open(p, 'wb').write(hdr + b'data' + struct.pack('<L', len(payload)) + payload)
+    want, count, pad = ref_loader.load_wav(p, 12000, 'uint8')
+    got = WavStream(p, 12000, 'uint8')
+    assert np.array_equal(got.data, want) and got.sample_count == count and got.padding_size == pad
