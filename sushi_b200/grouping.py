@@ -1,0 +1,220 @@
+"""The grouping heuristics that sit either side of the matcher (reference sushi.py:67-216,309-397).
+They decide which events are correlated (search groups) and post-process the (shift, diff) pairs the
+matcher returns.  Behaviour follows the reference function for function; the reference's own unit
+tests for them (tests/main.py:34-165) are ported in tests/test_grouping.py.
+
+Events are duck-typed: anything with start/end/shift/diff/linked and set_shift/link_event works
+(ScriptEvent here, subs.ScriptEventBase in the reference, FakeEvent in its tests).
+"""
+import logging
+
+import numpy as np
+
+from .common import SushiError, format_time
+
+ALLOWED_ERROR = 0.01       # sushi.py:39
+MAX_GROUP_STD = 0.025      # sushi.py:40
+
+
+def interpolate_nones(data, points):
+    """Fill None entries of `data` by linear interpolation over `points`, edges held (sushi.py:71-93)."""
+    data = data if isinstance(data, (list, tuple, set)) else list(data)
+    known = {p: v for p, v in zip(points, data) if v is not None}
+    if not known:
+        return []
+    missing = sorted({p for p, v in zip(points, data) if v is None and p not in known})
+    if not any(v is None for v in data):
+        return data
+    xs = sorted(known)
+    filled = np.interp(missing, xs, [known[x] for x in xs]) if missing else []
+    known.update(zip(missing, filled))
+    return [known[p] if v is None else v for p, v in zip(points, data)]
+
+
+def running_median(values, window_size):
+    """Median filter whose radius shrinks towards both ends (sushi.py:97-107)."""
+    if window_size % 2 != 1:
+        raise SushiError('Median window size should be odd')
+    half = window_size // 2
+    count = len(values)
+    out = []
+    for i in range(count):
+        r = min(half, i, count - i - 1)
+        out.append(np.median(values[i - r:i + r + 1]))
+    return out
+
+
+def smooth_events(events, radius):
+    if not radius:
+        return
+    smoothed = running_median([e.shift for e in events], radius * 2 + 1)
+    for e, s in zip(events, smoothed):
+        e.set_shift(s, e.diff)
+
+
+def detect_groups(events_iter):
+    """Split at every jump of more than ALLOWED_ERROR between neighbours (sushi.py:120-127)."""
+    groups = []
+    last = None
+    for e in events_iter:
+        if last is None or abs(e.shift - last.shift) > ALLOWED_ERROR:
+            groups.append([])
+        groups[-1].append(e)
+        last = e
+    if not groups:
+        raise StopIteration      # the reference calls next() on an empty iterator here
+    return groups
+
+
+def groups_from_chapters(events, times):
+    """One group per chapter; groups made only of linked events move to their parents' groups
+    (sushi.py:130-161)."""
+    logging.info('Chapter start points: {0}'.format([format_time(t) for t in times]))
+    bounds = iter(list(times[1:]) + [36000000000])
+    limit = next(bounds)
+    groups = [[]]
+    for e in events:
+        if e.end > limit:
+            groups.append([])
+            while e.end > limit:
+                limit = next(bounds)
+        groups[-1].append(e)
+    groups = [g for g in groups if g]
+    orphaned = [g for g in groups if all(e.linked for e in g)]
+    if orphaned:
+        for g in orphaned:
+            for e in g:
+                parent = e.get_link_chain_end()
+                next(h for h in groups if parent in h).append(e)
+            del g[:]
+        groups = [g for g in groups if g]
+        for g in groups:
+            g.sort(key=lambda e: e.start)
+    return groups
+
+
+def split_broken_groups(groups):
+    """Chapter groups whose shifts disagree (std > MAX_GROUP_STD) fall back to automatic grouping,
+    then neighbours that agree are merged again (sushi.py:164-187)."""
+    fixed = []
+    any_broken = False
+    for g in groups:
+        std = np.std([e.shift for e in g])
+        if std > MAX_GROUP_STD:
+            logging.warning('Shift is not consistent between {0} and {1}, most likely chapters are wrong (std: {2}). '
+                            'Switching to automatic grouping.'.format(format_time(g[0].start), format_time(g[-1].end), std))
+            fixed.extend(detect_groups(g))
+            any_broken = True
+        else:
+            fixed.append(g)
+    if not any_broken:
+        return fixed
+    merged = [list(fixed[0])]
+    for g in fixed[1:]:
+        tail = merged[-1]
+        if abs(tail[-1].shift - g[0].shift) >= ALLOWED_ERROR \
+                or np.std([e.shift for e in g + tail]) >= MAX_GROUP_STD:
+            merged.append([])
+        merged[-1].extend(g)
+    return merged
+
+
+def fix_near_borders(events):
+    """Events at either end whose diff is far from the typical one are linked to the first sane
+    event inwards (sushi.py:190-215)."""
+    def sweep(seq, median_diff):
+        limit = min(np.median([e.diff for e in seq[:10]]), median_diff)
+        broken = []
+        for e in seq:
+            if 0.2 < (e.diff / limit) < 5:
+                for b in broken:
+                    b.link_event(e)
+                return len(broken)
+            broken.append(e)
+        return 0
+
+    median_diff = np.median([e.diff for e in events])
+    n = sweep(events, median_diff)
+    if n:
+        logging.info('Fixing {0} border events right after {1}'.format(n, format_time(events[0].start)))
+    n = sweep(list(reversed(events)), median_diff)
+    if n:
+        logging.info('Fixing {0} border events right before {1}'.format(n, format_time(events[-1].end)))
+
+
+def average_shifts(events):
+    """Weighted mean shift of the unlinked events, weights 1 - diff (sushi.py:309-316)."""
+    events = [e for e in events if not e.linked]
+    avg = np.average([e.shift for e in events], weights=[1 - e.diff for e in events])
+    for e in events:
+        e.set_shift(avg, e.diff)
+    return avg
+
+
+def merge_short_lines_into_groups(events, chapter_times, max_ts_duration, max_ts_distance):
+    """Short (typesetting) lines that follow each other closely are searched as one group; long lines
+    are searched alone (sushi.py:319-349)."""
+    events = events if isinstance(events, (list, tuple)) else list(events)
+    bounds = iter(list(chapter_times[1:]) + [100000000])
+    next_chapter = next(bounds)
+    taken = set()
+    groups = []
+    for idx, e in enumerate(events):
+        if idx in taken:
+            continue
+        while e.end > next_chapter:
+            next_chapter = next(bounds)
+        if e.duration > max_ts_duration:
+            groups.append([e])
+            taken.add(idx)
+            continue
+        group, group_end = [e], e.end
+        i = idx + 1
+        while i < len(events) and abs(group_end - events[i].start) < max_ts_distance:
+            if events[i].end < next_chapter and events[i].duration <= max_ts_duration:
+                taken.add(i)
+                group.append(events[i])
+                group_end = max(group_end, events[i].end)
+            i += 1
+        groups.append(group)
+    return groups
+
+
+def prepare_search_groups(events, source_duration, chapter_times, max_ts_duration, max_ts_distance):
+    """Link what must not be searched (comments, zero-length lines, lines past the end of the audio,
+    exact duplicates), group the rest, and link groups nested inside earlier ones (sushi.py:352-397)."""
+    last_unlinked = None
+    for idx, e in enumerate(events):
+        if e.is_comment or (e.end == e.start and not (e.start + e.duration / 2.0) > source_duration):
+            target = events[idx + 1] if idx + 1 < len(events) else last_unlinked
+            if not e.is_comment:
+                logging.info('{0}: skipped because zero duration'.format(format_time(e.start)))
+            e.link_event(target)
+            continue
+        if (e.start + e.duration / 2.0) > source_duration:
+            logging.info('Event time outside of audio range, ignoring: %s' % e)
+            e.link_event(last_unlinked)
+            continue
+        twin = None
+        for x in reversed(events[:idx]):
+            if x.start != e.start:
+                break
+            if not x.linked and x.end == e.end:
+                twin = x
+                break
+        if twin is not None:
+            e.link_event(twin)
+        else:
+            last_unlinked = e
+
+    groups = merge_short_lines_into_groups([e for e in events if not e.linked], chapter_times,
+                                           max_ts_duration, max_ts_distance)
+    kept = []
+    for idx, g in enumerate(groups):
+        outer = next((x for x in reversed(groups[:idx]) if x[0].start <= g[0].start and x[-1].end >= g[-1].end), None)
+        if outer is None:
+            kept.append(g)
+        else:
+            for e in g:
+                e.link_event(outer[0])
+    return kept

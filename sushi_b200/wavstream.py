@@ -441,6 +441,25 @@ class WavStream(object):
                 ctypes.byref(diff), ctypes.byref(idx)), 'sb_find_batch')
         return np.float32(diff.value), start_time + (idx.value / float(self.sample_rate))
 
+    def find_substream_many(self, queries):
+        """[(pattern, center, window), ...] -> [(np.float32, float), ...] in ONE launch when every
+        pattern is a view into a resident stream of the same source (the whole/left/right probes of
+        the shift solver, sushi.py:450-452); otherwise falls back to one call each."""
+        plan = []
+        src = None
+        for pattern, center, window in queries:
+            where = self._locate(pattern) if pattern.dtype == self.data.dtype else None
+            n = len(pattern[0])
+            start_time, lo, span = self._window(n, center, window)
+            if where is None or (src is not None and where[0] is not src) or n < 1 or span < n:
+                return [self.find_substream(*q) for q in queries]
+            src = where[0]
+            plan.append((where[1], n, lo, span - n + 1, start_time))
+        toff, tlen, lag0, nlags, t0 = zip(*plan)
+        diff, idx = self.find_planned(src, toff, tlen, lag0, nlags)
+        rate = float(self.sample_rate)
+        return [(np.float32(diff[q]), t0[q] + (int(idx[q]) / rate)) for q in range(len(plan))]
+
     # -- batched surface (what the sharded benchmark and the batched shift solver use) ------
     def plan_queries(self, src_stream, starts, ends, centers, windows):
         """Integer descriptors of many find_substream calls at once.
