@@ -466,22 +466,34 @@ class WavStream(object):
 
         Query q searches src_stream.get_substream(starts[q], ends[q]) in this stream around
         centers[q] +- windows[q].  Returns (tmpl_off, tmpl_len, lag0, nlags, start_times) as
-        int64/float64 arrays, computed with the same scalar code as find_substream.
+        int64/float64 arrays.  Vectorised, but operation for operation the scalar code of
+        get_substream / find_substream (wav.py:168-184): float64 product, truncation toward zero,
+        min-then-max clipping, NumPy slice clamping -- so the integers are identical
+        (tests/test_host_logic.py checks this against the scalar path).
         """
-        count = len(starts)
-        toff = np.empty(count, np.int64); tlen = np.empty(count, np.int64)
-        lag0 = np.empty(count, np.int64); nlags = np.empty(count, np.int64)
-        t0 = np.empty(count, np.float64)
-        total_src = src_stream.data.shape[1]
-        for q in range(count):
-            a, b, _ = slice(src_stream._get_sample_for_time(starts[q]),
-                            src_stream._get_sample_for_time(ends[q])).indices(total_src)
-            n = max(b - a, 0)
-            st, lo, span = self._window(n, centers[q], windows[q])
-            if n < 1 or span < n:
-                raise SushiError('query {0}: pattern of {1} samples does not fit its search span of {2}'.format(q, n, span))
-            toff[q], tlen[q], lag0[q], nlags[q], t0[q] = a, n, lo, span - n + 1, st
-        return toff, tlen, lag0, nlags, t0
+        starts = np.asarray(starts, np.float64); ends = np.asarray(ends, np.float64)
+        centers = np.asarray(centers, np.float64); windows = np.asarray(windows, np.float64)
+
+        def sample_for_time(stream, t):                       # wav.py:173-175
+            return np.trunc(stream.sample_rate * t).astype(np.int64) + stream.padding_size
+
+        def slice_bounds(lo, hi, total):                      # what data[:, lo:hi] resolves to
+            lo = np.where(lo < 0, np.maximum(lo + total, 0), np.minimum(lo, total))
+            hi = np.where(hi < 0, np.maximum(hi + total, 0), np.minimum(hi, total))
+            return lo, np.maximum(hi - lo, 0)
+
+        toff, tlen = slice_bounds(sample_for_time(src_stream, starts), sample_for_time(src_stream, ends),
+                                  src_stream.data.shape[1])
+        dur = self.duration_seconds
+        t0 = np.maximum(np.minimum(centers - windows, dur), -self.PADDING_SECONDS)           # wav.py:178
+        t1 = np.maximum(np.minimum(centers + windows, dur + self.PADDING_SECONDS), 0)        # wav.py:179
+        lag0, span = slice_bounds(sample_for_time(self, t0), sample_for_time(self, t1) + tlen, self.data.shape[1])
+        bad = np.nonzero((tlen < 1) | (span < tlen))[0]
+        if len(bad):
+            q = int(bad[0])
+            raise SushiError('query {0}: pattern of {1} samples does not fit its search span of {2}'.format(
+                q, int(tlen[q]), int(span[q])))
+        return toff, tlen, lag0, span - tlen + 1, t0
 
     def find_substream_batch(self, src_stream, starts, ends, centers, windows):
         """Batched find_substream: returns (diffs float32[count], times float64[count])."""

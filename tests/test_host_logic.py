@@ -119,3 +119,27 @@ def test_query_planning_matches_reference_calls(golden_shifts, stype):
             view = ref.data[:, a:b]
             assert st == st_ref and span == view.shape[1]
             assert lo == (view.__array_interface__['data'][0] - ref.data.__array_interface__['data'][0]) // ref.data.itemsize
+
+
+def test_vectorised_planning_equals_scalar_path():
+    """plan_queries (NumPy) against the scalar _window/_get_sample_for_time code, including windows
+    clipped at both ends, negative times and the sub-sample rounding cases of int(rate * t)."""
+    rng = np.random.default_rng(0)
+    mk = lambda n: object.__new__(WavStream)
+    src, dst = mk(0), mk(0)
+    for s, count in ((src, 300.37), (dst, 299.2)):
+        s.sample_rate, s.padding_size = 12000, 120000
+        s.sample_count = int(np.ceil(count * 12000))
+        s.data = np.zeros((1, 240000 + s.sample_count), np.uint8)
+        s._handle = None
+    starts = np.concatenate([rng.uniform(0, 295, 400), [0.0, 0.001, 299.0, 150.12345678]])
+    starts = np.round(starts * 100) / 100
+    ends = starts + rng.uniform(0.5, 4.0, len(starts))
+    centers = starts + rng.uniform(-20, 20, len(starts))
+    windows = rng.choice([1.5, 10.0, 60.0, 400.0], len(starts))
+    toff, tlen, lag0, nlags, t0 = dst.plan_queries(src, starts, ends, centers, windows)
+    for q in range(len(starts)):
+        a, b = src._get_sample_for_time(starts[q]), src._get_sample_for_time(ends[q])
+        lo, hi, _ = slice(a, b).indices(src.data.shape[1])
+        st, l0, span = dst._window(hi - lo, centers[q], windows[q])
+        assert (toff[q], tlen[q], lag0[q], nlags[q], t0[q]) == (lo, hi - lo, l0, span - (hi - lo) + 1, st)
