@@ -196,7 +196,8 @@ def prepare_search_groups(events, source_duration, chapter_times, max_ts_duratio
             e.link_event(last_unlinked)
             continue
         twin = None
-        for x in reversed(events[:idx]):
+        for j in range(idx - 1, -1, -1):          # walk back while the start time is the same
+            x = events[j]
             if x.start != e.start:
                 break
             if not x.linked and x.end == e.end:
@@ -209,9 +210,26 @@ def prepare_search_groups(events, source_duration, chapter_times, max_ts_duratio
 
     groups = merge_short_lines_into_groups([e for e in events if not e.linked], chapter_times,
                                            max_ts_duration, max_ts_distance)
+    # a group nested inside an earlier group is linked to it (nearest such group first).  When the
+    # groups are ordered by start time -- the reference assumes sorted scripts -- "nearest earlier
+    # group that ends at or after this one" is a previous-greater-or-equal query: a monotonic stack
+    # answers it in O(N) instead of the reference's O(N^2) scan; unsorted input takes the scan.
     kept = []
+    ordered = all(groups[i][0].start <= groups[i + 1][0].start for i in range(len(groups) - 1))
+    stack = []                                    # indices with strictly decreasing group end
     for idx, g in enumerate(groups):
-        outer = next((x for x in reversed(groups[:idx]) if x[0].start <= g[0].start and x[-1].end >= g[-1].end), None)
+        if ordered:
+            while stack and groups[stack[-1]][-1].end < g[-1].end:
+                stack.pop()
+            outer = groups[stack[-1]] if stack else None
+            stack.append(idx)
+        else:
+            outer = None
+            for j in range(idx - 1, -1, -1):
+                x = groups[j]
+                if x[0].start <= g[0].start and x[-1].end >= g[-1].end:
+                    outer = x
+                    break
         if outer is None:
             kept.append(g)
         else:

@@ -78,3 +78,34 @@ def test_prepare_search_groups_links_comments_duplicates_and_nested():
     assert ev[6]._link is ev[5] or ev[6].linked   # beyond the audio -> last unlinked (sushi.py:361-364)
     assert ev[5]._link is ev[4]              # nested inside an earlier group (sushi.py:386-396)
     assert [[e.source_index for e in grp] for grp in groups] == [[0], [4], [7, 8], [9]]   # short lines merged
+
+
+def test_nested_group_linking_fast_path_equals_reference_scan():
+    """The monotonic-stack search for the enclosing group (sorted scripts) gives the same links as the
+    reference's backwards scan (sushi.py:386-396), including ties and chains of nesting."""
+    rng = np.random.default_rng(12)
+    for trial in range(30):
+        starts = np.sort(np.round(rng.uniform(0, 60, 80), 2))
+        ends = starts + np.round(rng.choice([0.5, 1.0, 3.0, 8.0, 20.0], 80), 2)
+        a = [ScriptEvent(i, float(s), float(e)) for i, (s, e) in enumerate(zip(starts, ends))]
+        b = [ScriptEvent(i, float(s), float(e)) for i, (s, e) in enumerate(zip(starts, ends))]
+        got = prepare_search_groups(a, 1000.0, [], 0.417, 0.417)
+        # the reference's literal scan on the copy
+        from sushi_b200.grouping import merge_short_lines_into_groups
+        last = None
+        for idx, e in enumerate(b):
+            twin = next((x for x in reversed(b[:idx]) if x.start == e.start and not x.linked and x.end == e.end), None) \
+                if idx and b[idx - 1].start == e.start else None
+            if twin:
+                e.link_event(twin)
+        groups = merge_short_lines_into_groups([e for e in b if not e.linked], [], 0.417, 0.417)
+        want = []
+        for idx, g in enumerate(groups):
+            outer = next((x for x in reversed(groups[:idx]) if x[0].start <= g[0].start and x[-1].end >= g[-1].end), None)
+            if outer is None:
+                want.append(g)
+            else:
+                for e in g:
+                    e.link_event(outer[0])
+        assert [[e.source_index for e in g] for g in got] == [[e.source_index for e in g] for g in want]
+        assert [(e._link.source_index if e.linked else -1) for e in a] == [(e._link.source_index if e.linked else -1) for e in b]
