@@ -1,7 +1,9 @@
-// Fused lag-block kernel: for one (query, lag block) item a CTA
+// Fused lag-block kernel, 16 values per thread (64 registers, 32 resident warps per SM) -- the
+// occupancy-oriented sibling of sb_fused.cu; same phases, same arithmetic, four Stockham passes of
+// radix 16 x 16 x 16 x {4|2} instead of three.  For one (query, lag block) item a CTA
 //   1. accumulates Y[bin] = sum_p conj(T^_p[bin]) * X^_{k+p}[bin] straight from L2 into registers,
 //   2. packs the Hermitian half spectrum into a half-size complex sequence in shared memory,
-//   3. runs the inverse FFT entirely in shared memory (Stockham, radix 32 x {32|16} x 16),
+//   3. runs the inverse FFT entirely in shared memory (Stockham, radix 16 x 16 x 16 x {4|2}),
 //   4. slides the window sums through its lags, screens every lag in fp32 and evaluates only the
 //      lags that can still be the minimum with OpenCV's rule in fp64, and
 //   5. merges its (value, first index) into the query's result with one 64-bit atomicMin.
@@ -22,24 +24,29 @@ namespace {
 
 // ---------------------------------------------------------------- configuration
 template <int LOGN> struct Cfg;
-template <> struct Cfg<14> {   // B = 16384 lags per item
-    static constexpr int N = 16384, T = 512, R1 = 32, R2 = 32, R3 = 16, MINB = 1;
+template <> struct Cfg<14> {   // B = 16384 lags per item, one CTA of 1024 threads per SM
+    static constexpr int N = 16384, T = 1024, R4 = 4, MINB = 1;
 };
-template <> struct Cfg<13> {   // B = 8192 lags per item
-    static constexpr int N = 8192, T = 256, R1 = 32, R2 = 16, R3 = 16, MINB = 2;
+template <> struct Cfg<13> {   // B = 8192 lags per item, two CTAs of 512 threads per SM
+    static constexpr int N = 8192, T = 512, R4 = 2, MINB = 2;
 };
 
 struct FusedTables {
-    const float2* w;      // [N/2+1]   exp(+i*pi*m/N)            (Hermitian unpacking)
-    const float2* t2;     // [R2][32]  exp(+2*pi*i*r*k/(32*R2))   (pass 2, k = lane)
-    const float2* a3;     // [R3][32]  exp(+2*pi*i*r*k/N), k = lane            (pass 3, low part)
-    const float2* b3;     // [R3][32]  exp(+2*pi*i*r*kh*32/N), kh = k / 32     (pass 3, high part)
+    const float2* w;      // [N/2+1]    exp(+i*pi*m/N)                       (Hermitian unpacking)
+    const float2* t2;     // [16][16]   exp(+2*pi*i*r*k/256),  k = j & 15      (pass 2)
+    const float2* a3;     // [16][32]   exp(+2*pi*i*r*k/4096), k = lane        (pass 3, low part)
+    const float2* b3;     // [16][8]    exp(+2*pi*i*r*kh/128), kh = (j>>5)&7   (pass 3, high part)
+    const float2* a4;     // [R4][32]   exp(+2*pi*i*r*k/N),    k = lane        (pass 4, low part)
+    const float2* b4;     // [R4][128]  exp(+2*pi*i*r*kh*32/N), kh = j >> 5    (pass 4, high part)
 };
+
+// one padding slot per 16 complex values keeps the radix-16 scatter of pass 1 conflict free
+__device__ __forceinline__ int pad16(int i) { return i + (i >> 4); }
 
 // ---------------------------------------------------------------- the kernel
 template <int LOGN, typename S>
 __global__ void __launch_bounds__(Cfg<LOGN>::T, Cfg<LOGN>::MINB)
-k_match_fused(const float2* __restrict__ That, int64_t part_first,
+k_match_fused16(const float2* __restrict__ That, int64_t part_first,
               const float2* __restrict__ Xhat, int64_t nblk,
               const S* __restrict__ img, int64_t img_n,
               const double2* __restrict__ ipfx, const double2* __restrict__ tpfx,
@@ -51,14 +58,17 @@ k_match_fused(const float2* __restrict__ That, int64_t part_first,
     constexpr int LAGS_PER_ROUND = T * 8;           // 8 consecutive lags per thread per round
     constexpr int ROUNDS = B / LAGS_PER_ROUND;      // 4
     constexpr int NW = T / 32;
-    constexpr int NT2 = C::R2 * 32, NT3 = C::R3 * 32;
+    constexpr int R4 = C::R4;
+    constexpr int NT2 = 16 * 16, NA3 = 16 * 32, NB3 = 16 * 8, NA4 = R4 * 32, NB4 = R4 * 128;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float2* buf = reinterpret_cast<float2*>(smem_raw);                  // pad(N) complex values
-    float2* s_t2 = buf + pad(N) + 1;                                    // twiddle tables
+    float2* buf = reinterpret_cast<float2*>(smem_raw);                  // pad16(N) complex values
+    float2* s_t2 = buf + pad16(N) + 1;                                  // twiddle tables
     float2* s_a3 = s_t2 + NT2;
-    float2* s_b3 = s_a3 + NT3;
-    unsigned long long* s_best = reinterpret_cast<unsigned long long*>(s_b3 + NT3);   // [NW]
+    float2* s_b3 = s_a3 + NA3;
+    float2* s_a4 = s_b3 + NB3;
+    float2* s_b4 = s_a4 + NA4;
+    unsigned long long* s_best = reinterpret_cast<unsigned long long*>(s_b4 + NB4);   // [NW]
     float* s_min = reinterpret_cast<float*>(s_best + NW);               // [NW]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -66,7 +76,10 @@ k_match_fused(const float2* __restrict__ That, int64_t part_first,
     const int q = __ldg(item_query + blockIdx.x);     // which query this lag block belongs to
     // stage the FFT twiddle tables (16 KB); first needed in pass 2, several barriers from here
     for (int i = tid; i < NT2; i += T) s_t2[i] = __ldg(tab.t2 + i);
-    for (int i = tid; i < NT3; i += T) { s_a3[i] = __ldg(tab.a3 + i); s_b3[i] = __ldg(tab.b3 + i); }
+    for (int i = tid; i < NA3; i += T) s_a3[i] = __ldg(tab.a3 + i);
+    for (int i = tid; i < NB3; i += T) s_b3[i] = __ldg(tab.b3 + i);
+    for (int i = tid; i < NA4; i += T) s_a4[i] = __ldg(tab.a4 + i);
+    for (int i = tid; i < NB4; i += T) s_b4[i] = __ldg(tab.b4 + i);
     const QueryDesc d = desc[q];
     const int64_t k = d.k0 + (item - d.itemBase);
 
@@ -76,7 +89,7 @@ k_match_fused(const float2* __restrict__ That, int64_t part_first,
         if (k + P > nblk) P = (int)(nblk - k);      // blocks past the end of the stream are zero
         const float2* tp = That + (d.partBase - part_first) * (int64_t)NB;
         const float2* xp = Xhat + k * (int64_t)NB;
-        constexpr int U = 8;                        // bin pairs in flight per thread
+        constexpr int U = 2;                        // bin pairs in flight per thread
         static_assert((B / 2) % (U * T) == 0, "pair loop must tile B/2");
         // pairs (m, B-m), m = 1 .. B/2-1, plus m = 0 whose partner is the Nyquist bin B
         for (int m0 = tid; m0 < B / 2; m0 += U * T) {
@@ -106,9 +119,9 @@ k_match_fused(const float2* __restrict__ That, int64_t part_first,
                 // Z[m]   = (Ym + conj(Yp)) + i*(Ym - conj(Yp))*w
                 const float2 e = make_float2(ym[u].x + yp[u].x, ym[u].y - yp[u].y);
                 const float2 o = cmul(make_float2(ym[u].x - yp[u].x, ym[u].y + yp[u].y), w);
-                buf[pad(m)] = make_float2(e.x - o.y, e.y + o.x);
+                buf[pad16(m)] = make_float2(e.x - o.y, e.y + o.x);
                 // Z[B-m] = conj(e) + i*conj(o)   (w^(B-m) = -conj(w^m))
-                if (m > 0) buf[pad(B - m)] = make_float2(e.x + o.y, -e.y + o.x);
+                if (m > 0) buf[pad16(B - m)] = make_float2(e.x + o.y, -e.y + o.x);
             }
         }
         if (tid < 32) {                             // the self-paired bin m = B/2 (w = i): Z = 2*conj(Y)
@@ -119,7 +132,7 @@ k_match_fused(const float2* __restrict__ That, int64_t part_first,
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) { y.x += __shfl_xor_sync(0xffffffffu, y.x, o); y.y += __shfl_xor_sync(0xffffffffu, y.y, o); }
-            if (lane == 0) buf[pad(B / 2)] = make_float2(2.f * y.x, -2.f * y.y);
+            if (lane == 0) buf[pad16(B / 2)] = make_float2(2.f * y.x, -2.f * y.y);
         }
     }
     __syncthreads();
@@ -128,62 +141,68 @@ k_match_fused(const float2* __restrict__ That, int64_t part_first,
     // Stockham passes: butterfly j reads in[j + r*N/R], twiddles by exp(2*pi*i*r*k/(Ns*R)),
     // k = j mod Ns, and writes out[(j-k)*R + k + r*Ns]; every value sits in a register between
     // the two barriers, so the pass is in place.
-    {   // pass 1: R1 = 32, Ns = 1 (no twiddles); one butterfly per thread
-        constexpr int R = C::R1;
-        static_assert(N / R == T, "pass 1: one butterfly per thread");
-        float2 v[R];
+    {   // pass 1: radix 16, Ns = 1 (no twiddles); one butterfly per thread
+        static_assert(N / 16 == T, "one radix-16 butterfly per thread");
+        float2 v[16];
 #pragma unroll
-        for (int r = 0; r < R; ++r) v[r] = buf[pad(tid + r * (N / R))];
+        for (int r = 0; r < 16; ++r) v[r] = buf[pad16(tid + r * T)];
         __syncthreads();
-        dft_dif<R>(v);
+        dft_dif<16>(v);
 #pragma unroll
-        for (int r = 0; r < R; ++r) buf[pad(tid * R + r)] = v[brev<R>(r)];
+        for (int r = 0; r < 16; ++r) buf[pad16(tid * 16 + r)] = v[brev<16>(r)];
         __syncthreads();
     }
-    {   // pass 2: Ns = 32, k = lane
-        constexpr int R = C::R2, Ns = C::R1, PER = (N / R) / T;
-        float2 v[PER][R];
+    {   // pass 2: radix 16, Ns = 16, k = j & 15
+        float2 v[16];
+#pragma unroll
+        for (int r = 0; r < 16; ++r) v[r] = buf[pad16(tid + r * T)];
+        __syncthreads();
+        const int k = tid & 15;
+#pragma unroll
+        for (int r = 1; r < 16; ++r) v[r] = cmul(v[r], s_t2[r * 16 + k]);
+        dft_dif<16>(v);
+        const int j0 = (tid - k) * 16 + k;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) buf[pad16(j0 + r * 16)] = v[brev<16>(r)];
+        __syncthreads();
+    }
+    {   // pass 3: radix 16, Ns = 256, k = j & 255 = kh * 32 + lane
+        float2 v[16];
+#pragma unroll
+        for (int r = 0; r < 16; ++r) v[r] = buf[pad16(tid + r * T)];
+        __syncthreads();
+        const int k = tid & 255, kh = k >> 5;
+#pragma unroll
+        for (int r = 1; r < 16; ++r) v[r] = cmul(v[r], cmul(s_a3[r * 32 + lane], s_b3[r * 8 + kh]));
+        dft_dif<16>(v);
+        const int j0 = (tid - k) * 16 + k;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) buf[pad16(j0 + r * 256)] = v[brev<16>(r)];
+        __syncthreads();
+    }
+    {   // pass 4: radix R4, Ns = 4096, k = j (j < 4096); only the first half of the outputs is
+        // needed: z[0 .. N/2) carries the B valid lags of the 2B-point real sequence
+        constexpr int Ns = 4096, PER = Ns / T;
+        static_assert(N / R4 == Ns, "pass 4 is the last pass");
+        float2 v[PER][R4];
 #pragma unroll
         for (int b = 0; b < PER; ++b)
 #pragma unroll
-            for (int r = 0; r < R; ++r) v[b][r] = buf[pad(tid + b * T + r * (N / R))];
-        __syncthreads();
-#pragma unroll
-        for (int b = 0; b < PER; ++b) {
-            const int j = tid + b * T;
-#pragma unroll
-            for (int r = 1; r < R; ++r) v[b][r] = cmul(v[b][r], s_t2[r * 32 + lane]);
-            dft_dif<R>(v[b]);
-            const int j0 = (j - lane) * R + lane;
-#pragma unroll
-            for (int r = 0; r < R; ++r) buf[pad(j0 + r * Ns)] = v[b][brev<R>(r)];
-        }
-        __syncthreads();
-    }
-    {   // pass 3: Ns = R1*R2, k = j (j < Ns); only the first half of the outputs is needed:
-        // z[0 .. N/2) carries the B valid lags of the 2B-point real sequence
-        constexpr int R = C::R3, Ns = C::R1 * C::R2, PER = (N / R) / T;
-        static_assert(N / R == Ns, "pass 3 is the last pass");
-        float2 v[PER][R];
-#pragma unroll
-        for (int b = 0; b < PER; ++b)
-#pragma unroll
-            for (int r = 0; r < R; ++r) v[b][r] = buf[pad(tid + b * T + r * (N / R))];
+            for (int r = 0; r < R4; ++r) v[b][r] = buf[pad16(tid + b * T + r * Ns)];
         __syncthreads();
 #pragma unroll
         for (int b = 0; b < PER; ++b) {
             const int j = tid + b * T;
             const int kh = j >> 5;
 #pragma unroll
-            for (int r = 1; r < R; ++r)
-                v[b][r] = cmul(v[b][r], cmul(s_a3[r * 32 + lane], s_b3[r * 32 + kh]));
-            dft_dif<R, true>(v[b]);
+            for (int r = 1; r < R4; ++r) v[b][r] = cmul(v[b][r], cmul(s_a4[r * 32 + lane], s_b4[r * 128 + kh]));
+            dft_dif<R4, true>(v[b]);
 #pragma unroll
-            for (int r = 0; r < R / 2; ++r) buf[pad(j + r * Ns)] = v[b][brev<R>(r)];
+            for (int r = 0; r < R4 / 2; ++r) buf[pad16(j + r * Ns)] = v[b][brev<R4>(r)];
         }
         __syncthreads();
     }
-    // now buf[pad(i)] = (x[2i], x[2i+1]) for i < N/2: correlation at lags 2i, 2i+1 (times 2B)
+    // now buf[pad16(i)] = (x[2i], x[2i+1]) for i < N/2: correlation at lags 2i, 2i+1 (times 2B)
 
     // ---------------- 4. window sums, fp32 screening, fp64 exact evaluation -----------------
     // Every thread owns runs of 8 consecutive lags.  The exact window sums at the first lag of a
@@ -229,7 +248,7 @@ k_match_fused(const float2* __restrict__ That, int64_t part_first,
             const float f_k0 = (float)(b * w0s[c] + k_const);
             float cc[8];
 #pragma unroll
-            for (int h = 0; h < 4; ++h) { const float2 z = buf[pad((m0 >> 1) + h)]; cc[2 * h] = z.x; cc[2 * h + 1] = z.y; }
+            for (int h = 0; h < 4; ++h) { const float2 z = buf[pad16((m0 >> 1) + h)]; cc[2 * h] = z.x; cc[2 * h + 1] = z.y; }
             if (sizeof(S) == 1) {
                 const uint8_t* img8 = reinterpret_cast<const uint8_t*>(img);
                 const unsigned long long lo8 = __ldg(reinterpret_cast<const unsigned long long*>(img8 + j0));   // j0 % 8 == 0
@@ -286,7 +305,7 @@ k_match_fused(const float2* __restrict__ That, int64_t part_first,
         cand &= cand - 1;
         const int m = (bit >> 3) * LAGS_PER_ROUND + tid * 8 + (bit & 7);
         const int64_t j = j_blk + m;
-        const float2 z = buf[pad(m >> 1)];
+        const float2 z = buf[pad16(m >> 1)];
         const double cc = (double)((m & 1) ? z.y : z.x) * scale;
         const double2 p_hi = ipfx[j + n], p_lo = ipfx[j];
         const float v = sqdiff_exact(cc, p_hi.x - p_lo.x, p_hi.y - p_lo.y, a, b, tsum, tsq, n_ab);
@@ -310,9 +329,10 @@ k_match_fused(const float2* __restrict__ That, int64_t part_first,
 // ---------------------------------------------------------------- host side
 template <int LOGN> size_t fused_smem_bytes() {
     typedef Cfg<LOGN> C;
-    const size_t padded = (size_t)(C::N + (C::N >> 5) + 1);
+    const size_t padded = (size_t)(C::N + (C::N >> 4) + 1);
+    const size_t tables = 16 * 16 + 16 * 32 + 16 * 8 + C::R4 * 32 + C::R4 * 128;
     const size_t nw = C::T / 32;
-    return (padded + C::R2 * 32 + 2 * C::R3 * 32) * sizeof(float2) + nw * sizeof(unsigned long long) + nw * sizeof(float) + 64;
+    return (padded + tables) * sizeof(float2) + nw * sizeof(unsigned long long) + nw * sizeof(float) + 64;
 }
 
 struct TableSet { float2* dev = nullptr; FusedTables tab; };
@@ -322,32 +342,33 @@ template <int LOGN> int ensure_tables(FusedTables* out) {
     typedef Cfg<LOGN> C;
     TableSet& ts = g_tables[LOGN - 13];
     if (!ts.dev) {
-        const int N = C::N;
-        const size_t nw = N / 2 + 1, n2 = (size_t)C::R2 * 32, n3 = (size_t)C::R3 * 32;
-        std::vector<float2> h(nw + n2 + 2 * n3);
+        const int N = C::N, R4 = C::R4;
+        const size_t nw = N / 2 + 1;
+        std::vector<float2> h;
         const double pi = 3.14159265358979323846;
-        for (size_t m = 0; m < nw; ++m) h[m] = make_float2((float)cos(pi * m / N), (float)sin(pi * m / N));
-        for (int r = 0; r < C::R2; ++r)
-            for (int k = 0; k < 32; ++k) {
-                const double ang = 2.0 * pi * r * k / (32.0 * C::R2);
-                h[nw + r * 32 + k] = make_float2((float)cos(ang), (float)sin(ang));
-            }
-        for (int r = 0; r < C::R3; ++r)
-            for (int k = 0; k < 32; ++k) {
-                const double al = 2.0 * pi * r * k / N, ah = 2.0 * pi * r * (k * 32.0) / N;
-                h[nw + n2 + r * 32 + k] = make_float2((float)cos(al), (float)sin(al));
-                h[nw + n2 + n3 + r * 32 + k] = make_float2((float)cos(ah), (float)sin(ah));
-            }
+        auto push = [&](double ang) { h.push_back(make_float2((float)cos(ang), (float)sin(ang))); };
+        for (size_t m = 0; m < nw; ++m) push(pi * m / N);
+        const size_t o_t2 = h.size();
+        for (int r = 0; r < 16; ++r) for (int k = 0; k < 16; ++k) push(2.0 * pi * r * k / 256.0);
+        const size_t o_a3 = h.size();
+        for (int r = 0; r < 16; ++r) for (int k = 0; k < 32; ++k) push(2.0 * pi * r * k / 4096.0);
+        const size_t o_b3 = h.size();
+        for (int r = 0; r < 16; ++r) for (int k = 0; k < 8; ++k) push(2.0 * pi * r * k / 128.0);
+        const size_t o_a4 = h.size();
+        for (int r = 0; r < R4; ++r) for (int k = 0; k < 32; ++k) push(2.0 * pi * r * k / N);
+        const size_t o_b4 = h.size();
+        for (int r = 0; r < R4; ++r) for (int k = 0; k < 128; ++k) push(2.0 * pi * r * (k * 32.0) / N);
         SB_CUDA(cudaMalloc(&ts.dev, h.size() * sizeof(float2)));
         SB_CUDA(cudaMemcpy(ts.dev, h.data(), h.size() * sizeof(float2), cudaMemcpyHostToDevice));
-        ts.tab.w = ts.dev; ts.tab.t2 = ts.dev + nw; ts.tab.a3 = ts.dev + nw + n2; ts.tab.b3 = ts.dev + nw + n2 + n3;
+        ts.tab.w = ts.dev; ts.tab.t2 = ts.dev + o_t2; ts.tab.a3 = ts.dev + o_a3; ts.tab.b3 = ts.dev + o_b3;
+        ts.tab.a4 = ts.dev + o_a4; ts.tab.b4 = ts.dev + o_b4;
     }
     *out = ts.tab;
     return SB_OK;
 }
 
 // item_query[i] = query of item (item_first + i): one CTA per query fills its own range
-__global__ void k_fill_item_query(const QueryDesc* __restrict__ desc, int q_begin, int64_t item_first,
+__global__ void k_fill_item_query16(const QueryDesc* __restrict__ desc, int q_begin, int64_t item_first,
                                   int* __restrict__ item_query) {
     const int q = q_begin + blockIdx.x;
     const int64_t base = desc[q].itemBase - item_first;
@@ -355,8 +376,8 @@ __global__ void k_fill_item_query(const QueryDesc* __restrict__ desc, int q_begi
     for (int i = threadIdx.x; i < nk; i += blockDim.x) item_query[base + i] = q;
 }
 
-int* g_item_query = nullptr;
-int64_t g_item_query_cap = 0;
+int* g_item_query16 = nullptr;
+int64_t g_item_query16_cap = 0;
 
 template <int LOGN, typename S>
 int launch_typed(const sb_stream* image, const sb_stream* tmpl, const float2* d_parts, int64_t part_first,
@@ -371,23 +392,23 @@ int launch_typed(const sb_stream* image, const sb_stream* tmpl, const float2* d_
     static const size_t extra = getenv("SB_FUSED_EXTRA_SMEM") ? (size_t)atol(getenv("SB_FUSED_EXTRA_SMEM")) : 0;
     const size_t smem = fused_smem_bytes<LOGN>() + extra;
     if (!attr_set) {
-        SB_CUDA(cudaFuncSetAttribute(k_match_fused<LOGN, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SB_CUDA(cudaFuncSetAttribute(k_match_fused16<LOGN, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
-    if (g_item_query_cap < n_items) {
+    if (g_item_query16_cap < n_items) {
         cudaStreamSynchronize(c.stream);
-        cudaFree(g_item_query); g_item_query = nullptr; g_item_query_cap = 0;
-        SB_CUDA(cudaMalloc(&g_item_query, sizeof(int) * (size_t)n_items));
-        g_item_query_cap = n_items;
+        cudaFree(g_item_query16); g_item_query16 = nullptr; g_item_query16_cap = 0;
+        SB_CUDA(cudaMalloc(&g_item_query16, sizeof(int) * (size_t)n_items));
+        g_item_query16_cap = n_items;
     }
-    k_fill_item_query<<<(unsigned)(q_end - q_begin), 128, 0, c.stream>>>(d_desc, q_begin, item_first, g_item_query);
+    k_fill_item_query16<<<(unsigned)(q_end - q_begin), 128, 0, c.stream>>>(d_desc, q_begin, item_first, g_item_query16);
     c.launches += 1;
     const int64_t max_grid = 1 << 30;
     for (int64_t i0 = 0; i0 < n_items; i0 += max_grid) {
         const int64_t ni = std::min<int64_t>(max_grid, n_items - i0);
-        k_match_fused<LOGN, S><<<(unsigned)ni, Cfg<LOGN>::T, smem, c.stream>>>(
+        k_match_fused16<LOGN, S><<<(unsigned)ni, Cfg<LOGN>::T, smem, c.stream>>>(
             d_parts, part_first, image->d_spec, image->nblk, static_cast<const S*>(image->d_raw), image->n,
-            image->d_pfx, tmpl->d_pfx, d_desc, g_item_query + i0, item_first + i0,
+            image->d_pfx, tmpl->d_pfx, d_desc, g_item_query16 + i0, item_first + i0,
             tab, d_keys, d_curve);
     }
     SB_CUDA(cudaGetLastError());
@@ -398,9 +419,7 @@ int launch_typed(const sb_stream* image, const sb_stream* tmpl, const float2* d_
 
 namespace sb {
 
-bool fused_supports(int B) { return B == 16384 || B == 8192; }
-
-int launch_match_fused(const sb_stream* image, const sb_stream* tmpl, const float2* d_parts, int64_t part_first,
+int launch_match_fused16(const sb_stream* image, const sb_stream* tmpl, const float2* d_parts, int64_t part_first,
                        const QueryDesc* d_desc, int q_begin, int q_end, int64_t item_first, int64_t n_items,
                        unsigned long long* d_keys, float* d_curve) {
     const int B = ctx().B;
@@ -414,9 +433,9 @@ int launch_match_fused(const sb_stream* image, const sb_stream* tmpl, const floa
     SB_FAIL(SB_EINVAL, "fused engine supports lag blocks of 8192 or 16384 samples, not %d", B);
 }
 
-void fused_release_tables() {
+void fused16_release_tables() {
     for (auto& t : g_tables) { if (t.dev) cudaFree(t.dev); t.dev = nullptr; }
-    cudaFree(g_item_query); g_item_query = nullptr; g_item_query_cap = 0;
+    cudaFree(g_item_query16); g_item_query16 = nullptr; g_item_query16_cap = 0;
 }
 
 }  // namespace sb

@@ -91,18 +91,19 @@ def test_fused_engine_equals_cufft_engine(gpu_lib, pair, stype, block):
         toff, n = src._get_sample_for_time(6.1), 11400
         lag0, nlags = 70000, 150001
         curves, results = [], []
-        for engine in (0, 1):
+        for engine in (0, 1, 2):
             _native.check(gpu_lib.sb_set_engine(engine))
             curves.append(dst.match_curve(src, toff, n, lag0, nlags))
             results.append(dst.find_planned(src, [toff, toff + 5000, 100], [n, 3000, 48000],
                                             [lag0, 1000, 0], [nlags, 300000, 200000]))
-        assert np.abs(curves[0] - curves[1]).max() <= 2e-6
-        assert np.abs(results[0][0] - results[1][0]).max() <= 2e-6
-        assert np.abs(results[0][1] - results[1][1]).max() <= 1
-        # the batch result is the first-index minimum of the engine's own curve
-        _native.check(gpu_lib.sb_set_engine(1))
-        d, i = dst.find_planned(src, [toff], [n], [lag0], [nlags])
-        assert i[0] == int(curves[1].argmin()) and d[0] == curves[1].min()
+        for e in (1, 2):
+            assert np.abs(curves[0] - curves[e]).max() <= 2e-6
+            assert np.abs(results[0][0] - results[e][0]).max() <= 2e-6
+            assert np.abs(results[0][1] - results[e][1]).max() <= 1
+            # the batch result is the first-index minimum of the engine's own curve
+            _native.check(gpu_lib.sb_set_engine(e))
+            d, i = dst.find_planned(src, [toff], [n], [lag0], [nlags])
+            assert i[0] == int(curves[e].argmin()) and d[0] == curves[e].min()
     finally:
         _native.check(gpu_lib.sb_set_engine(1))
         _native.check(gpu_lib.sb_set_block_size(16384))
