@@ -189,7 +189,7 @@ class ClockSampler(object):
         self.proc = None
         try:
             self.proc = subprocess.Popen(
-                ['nvidia-smi', '--query-gpu=' + self.FIELDS, '--format=csv,noheader,nounits', '-lms', '100',
+                ['nvidia-smi', '--query-gpu=' + self.FIELDS, '--format=csv,noheader,nounits', '-lms', '50',
                  '-i', str(gpu_index)], stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
@@ -433,8 +433,18 @@ def run_b200(args):
         dom_name, (dom_ms, dom_n) = dom
         dom_ms_step = dom_ms / args.steps
         achieved = step_bytes / (dom_ms_step / 1e3) / 1e9 if dom_ms_step > 0 else 0.0
+        # DRAM bytes of the dominant kernel from the committed `ncu --set full` capture of this same
+        # workload (profiles/traffic.json, written by tools/ncu_traffic.py); null when no capture matches
+        traffic = None
+        try:
+            tr = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json')))
+            key = '%s/%s/%s/B%d' % (args.workload, stype, dom_name, lib.sb_get_block_size())
+            if key in tr:
+                traffic = tr[key]['dram_bytes_per_launch']
+        except (OSError, ValueError, KeyError):
+            pass
         roof = {'bound': 'hbm', 'kernel': dom_name, 'achieved': round(achieved, 2), 'peak': peak, 'unit': 'GB/s',
-                'frac': round(achieved / peak, 5), 'traffic': None, 'peak_source': peak_src,
+                'frac': round(achieved / peak, 5), 'traffic': traffic, 'peak_source': peak_src,
                 'launches_per_step': dom_n / args.steps, 'avg_launch_ms': round(dom_ms / max(dom_n, 1), 5),
                 'algorithmic_bytes_per_step': step_bytes,
                 'whole_step': {'achieved': round(step_bytes / (ms_step / 1e3) / 1e9, 2),
@@ -507,7 +517,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--workload', default='config2', choices=sorted(WORKLOADS))
