@@ -77,6 +77,9 @@ int sb_set_engine(int engine);
 int sb_get_engine(void);
 /* Lag blocks processed per multiply / inverse-FFT / normalise launch (>= 1). */
 int sb_set_chunk_items(int items);
+/* Template partition spectra kept resident per pass over a batch (>= 1); batches needing more are
+ * processed in several passes of whole queries. */
+int sb_set_max_parts(int64_t parts);
 
 /* The library's CUDA stream (a cudaStream_t) so that a host framework can order its own
  * work (e.g. an NCCL broadcast issued through torch.distributed) on the same stream. */

@@ -32,6 +32,7 @@ PROTOTYPES = {
     'sb_get_block_size': (ctypes.c_int, []),
     'sb_set_chunk_items': (ctypes.c_int, [ctypes.c_int]),
     'sb_set_engine': (ctypes.c_int, [ctypes.c_int]),
+    'sb_set_max_parts': (ctypes.c_int, [c_i64]),
     'sb_get_engine': (ctypes.c_int, []),
     'sb_get_stream': (c_vp, []),
     'sb_pinned_alloc': (ctypes.c_int, [c_i64, ctypes.POINTER(c_vp)]),

@@ -218,6 +218,11 @@ int sb_set_engine(int engine) {
     return SB_OK;
 }
 int sb_get_engine(void) { return ctx().engine; }
+int sb_set_max_parts(int64_t parts) {
+    if (parts < 1) SB_FAIL(SB_EINVAL, "sb_set_max_parts: %lld < 1", (long long)parts);
+    ctx().max_parts = parts;
+    return SB_OK;
+}
 int sb_set_chunk_items(int items) {
     if (items < 1 || items > (1 << 20)) SB_FAIL(SB_EINVAL, "sb_set_chunk_items: %d out of range", items);
     ctx().chunk_items = items;

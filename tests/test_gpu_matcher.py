@@ -293,3 +293,76 @@ def test_wav_file_load_int24(gpu_lib, tmp_path):
     want, count, pad = ref_loader.load_wav(p, 12000, 'uint8')
     got = WavStream(p, 12000, 'uint8')
     assert np.array_equal(got.data, want) and got.sample_count == count and got.padding_size == pad
+
+
+# ---------------------------------------------------------------------------------------------
+# edge cases: empty and ragged inputs, minimum sizes, batch splitting
+# ---------------------------------------------------------------------------------------------
+def _cv2_curve(image_row, templ_row):
+    import cv2
+    return cv2.matchTemplate(image_row[None, :], templ_row[None, :], cv2.TM_SQDIFF_NORMED)[0]
+
+
+def test_empty_batch_is_a_no_op(gpu_lib, pair):
+    rs, rd, src, dst = pair['uint8']
+    d, i = dst.find_planned(src, [], [], [], [])
+    assert len(d) == 0 and len(i) == 0
+
+
+@pytest.mark.parametrize('engine', [0, 1, 2])
+def test_minimum_sizes_and_ragged_edges(gpu_lib, engine):
+    """n = 1 templates, single-lag searches, streams shorter than one lag block, searches that end on
+    the last sample, spans that straddle exactly one block boundary."""
+    rng = np.random.default_rng(engine)
+    _native.check(gpu_lib.sb_set_engine(engine))
+    try:
+        for total in (7, 1000, 16384, 16385, 40000):
+            img = rng.integers(0, 256, total, dtype=np.uint8)
+            tm = rng.integers(0, 256, 5000, dtype=np.uint8)
+            s_img = WavStream.from_array(img[None, :], 12000, 0, total)
+            s_tm = WavStream.from_array(tm[None, :], 12000, 0, len(tm))
+            cases = [(0, 1, 0, total), (3, 1, total - 1, 1), (10, min(5, total), 0, total - min(5, total) + 1)]
+            if total >= 1000:
+                cases += [(100, 999, total - 999, 1), (0, 257, 3, total - 257 - 3 + 1)]
+            if total > 16384:
+                cases += [(5, 300, 16384 - 150, 151), (5, 300, 16383, 2), (7, 4000, 16000, total - 4000 - 16000 + 1)]
+            for toff, n, lag0, nlags in cases:
+                want = _cv2_curve(img[lag0:lag0 + nlags + n - 1], tm[toff:toff + n])
+                got = s_img.match_curve(s_tm, toff, n, lag0, nlags)
+                assert got.shape == want.shape
+                assert np.abs(got - want).max() <= 1e-5, (total, toff, n, lag0, nlags)
+                d, i = s_img.find_planned(s_tm, [toff], [n], [lag0], [nlags])
+                assert abs(float(d[0]) - float(want.min())) <= 1e-5
+                assert want[int(i[0])] - want.min() <= 2e-6          # a minimiser (ties on random data are rare)
+    finally:
+        _native.check(gpu_lib.sb_set_engine(1))
+
+
+def test_batch_split_into_several_passes(gpu_lib, pair):
+    """More template partitions than the resident budget: the batch runs in several passes of whole
+    queries and still returns what the single-pass run returns."""
+    rs, rd, src, dst = pair['uint8']
+    starts = np.linspace(0.5, 19.0, 40)
+    ends = starts + np.tile([0.3, 1.7, 3.2, 4.0], 10)
+    centers, windows = starts + 1.0, np.full(40, 10.0)
+    want = dst.find_substream_batch(src, starts, ends, centers, windows)
+    _native.check(gpu_lib.sb_set_block_size(8192))
+    try:
+        _native.check(gpu_lib.sb_set_max_parts(7))
+        got = dst.find_substream_batch(src, starts, ends, centers, windows)
+    finally:
+        _native.check(gpu_lib.sb_set_max_parts(16384))
+        _native.check(gpu_lib.sb_set_block_size(16384))
+    assert np.abs(got[0] - want[0]).max() <= 2e-6 and np.abs(got[1] - want[1]).max() <= SHIFT_TOL
+
+
+def test_float32_stream_with_arbitrary_range(gpu_lib):
+    """from_array accepts any float32 data, not only [0,1]: values around 1000 with a small variation
+    (a hard case for the centring) still match cv2 to 1e-5."""
+    rng = np.random.default_rng(3)
+    img = (1000.0 + 5.0 * rng.standard_normal(60000)).astype(np.float32)
+    s = WavStream.from_array(img[None, :], 12000, 0, len(img))
+    want = _cv2_curve(img[2000:2000 + 30000 + 4999], img[20000:25000])
+    got = s.match_curve(s, 20000, 5000, 2000, 30000)
+    assert np.abs(got - want).max() <= 1e-5
+    assert int(got.argmin()) == 18000 and got.min() <= 1e-6
