@@ -324,7 +324,9 @@ def test_minimum_sizes_and_ragged_edges(gpu_lib, engine):
             cases = [(0, 1, 0, total), (3, 1, total - 1, 1), (10, min(5, total), 0, total - min(5, total) + 1)]
             if total >= 1000:
                 cases += [(100, 999, total - 999, 1), (0, 257, 3, total - 257 - 3 + 1)]
-            if total > 16384:
+            if total == 16385:
+                cases += [(5, 2, 16383, 1), (5, 1, 16384, 1), (0, 300, 16000, 86)]
+            if total >= 40000:
                 cases += [(5, 300, 16384 - 150, 151), (5, 300, 16383, 2), (7, 4000, 16000, total - 4000 - 16000 + 1)]
             for toff, n, lag0, nlags in cases:
                 want = _cv2_curve(img[lag0:lag0 + nlags + n - 1], tm[toff:toff + n])
