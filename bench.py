@@ -35,7 +35,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-from sushi_b200 import _hostmem, synth      # noqa: E402
+from sushi_b200 import _hostmem, parallel, synth      # noqa: E402
 from sushi_b200.wavstream import WavStream   # noqa: E402
 
 _hostmem.keep_heap()
@@ -250,8 +250,7 @@ def run_b200(args):
     src_h, dst_h, lists = make_inputs(wl, stype, 1 if strong else world)
     if strong:
         starts_all, ends_all = lists[0]
-        per = (len(starts_all) + world - 1) // world
-        my = slice(rank * per, min((rank + 1) * per, len(starts_all)))        # contiguous shard
+        my = slice(*parallel.shard_bounds(len(starts_all), world, rank))      # contiguous shard
         starts, ends = starts_all[my], ends_all[my]
         total_events = len(starts_all)
     else:
@@ -303,11 +302,7 @@ def run_b200(args):
         if rank == 0:
             src_t.copy_(torch.from_numpy(src_p[0]))
             dst_t.copy_(torch.from_numpy(dst_p[0]))
-        out_diff = torch.empty(count, dtype=torch.float32, device='cuda')
-        out_idx = torch.empty(count, dtype=torch.int64, device='cuda')
-        counts = [None] * world
-        dist.all_gather_object(counts, count)
-        maxc = max(counts)
+        maxc = max(parallel.shard_sizes(total_events, world)) if strong else count
         pad_diff = torch.zeros(maxc, dtype=torch.float32, device='cuda')
         pad_idx = torch.zeros(maxc, dtype=torch.int64, device='cuda')
         all_diff = torch.empty(world * maxc, dtype=torch.float32, device='cuda')

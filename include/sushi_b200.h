@@ -139,6 +139,13 @@ int sb_find_batch_device(const sb_stream* image, const sb_stream* tmpl, int64_t 
                          const int64_t* lag0, const int64_t* nlags,
                          float* d_diff_out, int64_t* d_idx_out);
 
+/* Whole curves of `count` queries, concatenated in query order into curves_out[sum(nlags)] (host).
+ * Every lag is evaluated with the exact fp64 rule.  Because a value depends only on (template,
+ * absolute position), a curve over a wider range answers any sub-range query exactly: the shift
+ * solver uses this to precompute the next groups' searches in one launch (sushi_b200/shifts.py). */
+int sb_match_curves(const sb_stream* image, const sb_stream* tmpl, int64_t count,
+                    const int64_t* tmpl_off, const int64_t* tmpl_len,
+                    const int64_t* lag0, const int64_t* nlags, float* curves_out);
 /* The whole curve of one query (debug / parity tests): curve_out[nlags]. */
 int sb_match_curve(const sb_stream* image, const sb_stream* tmpl,
                    int64_t tmpl_off, int64_t tmpl_len, int64_t lag0, int64_t nlags,

@@ -309,7 +309,7 @@ k_match_fused16(const float2* __restrict__ That, int64_t part_first,
         const double cc = (double)((m & 1) ? z.y : z.x) * scale;
         const double2 p_hi = ipfx[j + n], p_lo = ipfx[j];
         const float v = sqdiff_exact(cc, p_hi.x - p_lo.x, p_hi.y - p_lo.y, a, b, tsum, tsq, n_ab);
-        if (curve_out) curve_out[j - jlo] = v;
+        if (curve_out) curve_out[d.curveOff + (j - jlo)] = v;
         const unsigned long long key = ((unsigned long long)__float_as_uint(v) << 32) | (unsigned int)(j - jlo);
         best = key < best ? key : best;
     }

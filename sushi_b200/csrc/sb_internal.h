@@ -40,6 +40,7 @@ struct QueryDesc {
     int64_t nlags;     // number of candidate positions L
     int64_t itemBase;  // first item of this query in the batch-wide item list
     int64_t partBase;  // first partition spectrum of this query
+    int64_t curveOff;  // where this query's curve starts in the curve buffer (curve mode only)
     int32_t P;         // ceil(n / B)
     int32_t k0;        // lag0 / B
     int32_t nk;        // number of lag blocks touched

@@ -44,13 +44,12 @@ __device__ __forceinline__ float decode_frame(const unsigned char* __restrict__ 
 // content sample o (o in [0, written)) of the resampled stream
 __device__ __forceinline__ float content_sample(const unsigned char* __restrict__ pcm, const ResampleGeom g,
                                                 int64_t o, int channels, int width) {
-    int64_t c; int x, len; double ifx; int out_len;
+    int64_t c; int x, len; double ifx;
     if (g.out_full > 0 && o < g.nfull * (int64_t)g.out_full) {
-        c = o / g.out_full; x = (int)(o - c * g.out_full); len = g.framerate; ifx = g.ifx_full; out_len = g.out_full;
+        c = o / g.out_full; x = (int)(o - c * g.out_full); len = g.framerate; ifx = g.ifx_full;
     } else {
-        c = g.nfull; x = (int)(o - g.nfull * (int64_t)g.out_full); len = g.len_last; ifx = g.ifx_last; out_len = g.out_last;
+        c = g.nfull; x = (int)(o - g.nfull * (int64_t)g.out_full); len = g.len_last; ifx = g.ifx_last;
     }
-    (void)out_len;
     int sx = x;
     if (g.resample) {
         sx = (int)floor((double)x * ifx);                                    // OpenCV resizeNN: cvFloor(x * ifx)

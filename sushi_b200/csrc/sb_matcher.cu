@@ -247,7 +247,7 @@ k_normalise_argmin(const float* __restrict__ corr_rows, const T* __restrict__ im
             const double wsq = base_wq + (double)(oq + dq[i]);
             const double wsum = base_ws + (double)(os + ds[i]);
             const float v = sqdiff_normed((double)cc[i] * scale, wsum, wsq, a, b, tsum, tsq, n_ab);
-            if (curve_out) curve_out[j - jlo] = v;
+            if (curve_out) curve_out[d.curveOff + (j - jlo)] = v;
             const unsigned long long key = pack_key(v, (unsigned int)(j - jlo));
             best = key < best ? key : best;
         }
@@ -301,7 +301,7 @@ int plan_batch(const sb_stream* image, const sb_stream* tmpl, int64_t count,
         SB_CUDA(cudaMallocHost((void**)&c.h_desc, sizeof(QueryDesc) * std::max<int64_t>(count, 64)));
         c.h_desc_cap = std::max<int64_t>(count, 64);
     }
-    int64_t items = 0, parts = 0, maxp = 0;
+    int64_t items = 0, parts = 0, maxp = 0, curve_total = 0;
     for (int64_t q = 0; q < count; ++q) {
         const int64_t n = tlen[q], L = nlags[q], o = toff[q], s = lag0[q];
         if (n < 1 || L < 1) SB_FAIL(SB_EINVAL, "query %lld: template length %lld / lag count %lld must be >= 1", (long long)q, (long long)n, (long long)L);
@@ -313,7 +313,8 @@ int plan_batch(const sb_stream* image, const sb_stream* tmpl, int64_t count,
         d.P = (int32_t)((n + B - 1) / B);
         d.k0 = (int32_t)(s / B);
         d.nk = (int32_t)((s + L - 1) / B - d.k0 + 1);
-        d.itemBase = items; d.partBase = parts; d.pad_ = 0;
+        d.itemBase = items; d.partBase = parts; d.pad_ = 0; d.curveOff = curve_total;
+        curve_total += L;
         items += d.nk; parts += d.P;
         maxp = std::max<int64_t>(maxp, d.P);
     }
@@ -489,26 +490,36 @@ int sb_find(const sb_stream* image, const void* tmpl_host, int64_t tmpl_len,
     return rc;
 }
 
+int sb_match_curves(const sb_stream* image, const sb_stream* tmpl, int64_t count,
+                    const int64_t* tmpl_off, const int64_t* tmpl_len,
+                    const int64_t* lag0, const int64_t* nlags, float* curves_out) {
+    SB_TRY(check_common("sb_match_curves", image, tmpl, count));
+    if (count == 0) return SB_OK;
+    if (!tmpl_off || !tmpl_len || !lag0 || !nlags || !curves_out) SB_FAIL(SB_EINVAL, "sb_match_curves: NULL array");
+    int64_t total = 0;
+    for (int64_t q = 0; q < count; ++q) {
+        if (nlags[q] < 1) SB_FAIL(SB_EINVAL, "sb_match_curves: query %lld has nlags < 1", (long long)q);
+        total += nlags[q];
+    }
+    Ctx& c = ctx();
+    float* d_curve = nullptr; float* d_diff = nullptr; int64_t* d_idx = nullptr;
+    SB_TRY(pool_alloc((void**)&d_curve, sizeof(float) * total));
+    int rc = pool_alloc((void**)&d_diff, sizeof(float) * count);
+    if (rc == SB_OK) rc = pool_alloc((void**)&d_idx, sizeof(int64_t) * count);
+    if (rc == SB_OK) rc = run_batch(image, tmpl, count, tmpl_off, tmpl_len, lag0, nlags, d_diff, d_idx, d_curve);
+    if (rc == SB_OK) {
+        cudaError_t e = cudaMemcpyAsync(curves_out, d_curve, sizeof(float) * total, cudaMemcpyDeviceToHost, c.stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c.stream);
+        if (e != cudaSuccess) { set_error("sb_match_curves: D2H: %s", cudaGetErrorString(e)); rc = SB_ECUDA; }
+    }
+    pool_free(d_curve); pool_free(d_diff); pool_free(d_idx);
+    return rc;
+}
+
 int sb_match_curve(const sb_stream* image, const sb_stream* tmpl,
                    int64_t tmpl_off, int64_t tmpl_len, int64_t lag0, int64_t nlags,
                    float* curve_out) {
-    SB_TRY(check_common("sb_match_curve", image, tmpl, 1));
-    if (!curve_out) SB_FAIL(SB_EINVAL, "sb_match_curve: NULL output");
-    if (nlags < 1) SB_FAIL(SB_EINVAL, "sb_match_curve: nlags < 1");
-    Ctx& c = ctx();
-    float* d_curve = nullptr; float* d_diff = nullptr; int64_t* d_idx = nullptr;
-    SB_CUDA(cudaMalloc(&d_curve, sizeof(float) * nlags));
-    SB_CUDA(cudaMalloc(&d_diff, sizeof(float)));
-    SB_CUDA(cudaMalloc(&d_idx, sizeof(int64_t)));
-    int rc = run_batch(image, tmpl, 1, &tmpl_off, &tmpl_len, &lag0, &nlags, d_diff, d_idx, d_curve);
-    if (rc == SB_OK) {
-        cudaError_t e = cudaMemcpyAsync(curve_out, d_curve, sizeof(float) * nlags, cudaMemcpyDeviceToHost, c.stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(c.stream);
-        if (e != cudaSuccess) { set_error("sb_match_curve: D2H: %s", cudaGetErrorString(e)); rc = SB_ECUDA; }
-    }
-    cudaStreamSynchronize(c.stream);
-    cudaFree(d_curve); cudaFree(d_diff); cudaFree(d_idx);
-    return rc;
+    return sb_match_curves(image, tmpl, 1, &tmpl_off, &tmpl_len, &lag0, &nlags, curve_out);
 }
 
 }  // extern "C"

@@ -5,7 +5,9 @@ log lines, so the grouping heuristics before and after it see identical results.
 Differences are purely in how the matcher is called: the reference issues 1 + 3 (+ 3) dependent
 find_substream calls per search group; here the three probes of a check (whole group, left half,
 right half -- sushi.py:445-452) go to the GPU as one batch when the stream supports it
-(WavStream.find_substream_many).  Streams are duck-typed: anything with get_substream /
+(WavStream.find_substream_many), and the fast-path searches of the coming groups are precomputed
+48 at a time as whole curves (WavStream.speculate_fast_path) from which each call is answered
+exactly.  Streams are duck-typed: anything with get_substream /
 find_substream / duration_seconds / sample_rate works (the tests also run this solver on the
 CPU oracle's streams and compare with the reference's golden results).
 """
@@ -42,8 +44,12 @@ def _probe_triple(dst_stream, audio, left, right, right_offset, center, window):
     return diff, whole_time, left_time, right_time, agreed
 
 
-def calculate_shifts(src_stream, dst_stream, groups_list, normal_window, max_window, rewind_thresh):
+def calculate_shifts(src_stream, dst_stream, groups_list, normal_window, max_window, rewind_thresh,
+                     speculative=True):
     committed, pending = [], []
+    # streams that can precompute the coming fast-path searches in one launch expose this hook; the
+    # results they then return are the ones a live call would return (see WavStream.speculate_fast_path)
+    speculate = getattr(dst_stream, 'speculate_fast_path', None) if speculative else None
     window = normal_window
     idx = 0
     while idx < len(groups_list):
@@ -62,6 +68,8 @@ def calculate_shifts(src_stream, dst_stream, groups_list, normal_window, max_win
                     logging.info('{0}-{1}: outside of audio range'.format(format_time(rest[0].start), format_time(rest[-1].end)))
                 break
             if SMALL_WINDOW < window:
+                if speculate is not None:
+                    speculate(src_stream, groups_list, idx, anchor, SMALL_WINDOW)
                 diff, found = dst_stream.find_substream(audio, origin + anchor, SMALL_WINDOW)
             if found is not None and abs((found - origin) - anchor) <= ALLOWED_ERROR:
                 # the shift did not move: commit straight away (sushi.py:434-443)

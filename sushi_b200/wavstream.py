@@ -413,6 +413,9 @@ class WavStream(object):
         idx = ctypes.c_int64()
         where = self._locate(pattern)
         if span >= n:
+            cached = self._from_cache(where, n, lo, span - n + 1)
+            if cached is not None:
+                return np.float32(cached[0]), start_time + (cached[1] / float(self.sample_rate))
             if where is not None:
                 src, off = where
                 a = (ctypes.c_int64 * 4)(off, n, lo, span - n + 1)
@@ -511,6 +514,59 @@ class WavStream(object):
             *[x.ctypes.data_as(_native.c_i64p) for x in arrs],
             diff.ctypes.data_as(_native.c_f32p), idx.ctypes.data_as(_native.c_i64p)), 'sb_find_batch')
         return diff, idx
+
+    def match_curves(self, src_stream, toff, tlen, lag0, nlags):
+        """Whole curves of several queries from one launch: list of float32 arrays."""
+        arrs = [np.ascontiguousarray(x, dtype=np.int64) for x in (toff, tlen, lag0, nlags)]
+        out = np.empty(int(arrs[3].sum()), np.float32)
+        _native.check(self._lib.sb_match_curves(self._handle, src_stream._handle, len(arrs[0]),
+                                                *[x.ctypes.data_as(_native.c_i64p) for x in arrs],
+                                                out.ctypes.data_as(_native.c_f32p)), 'sb_match_curves')
+        cuts = np.cumsum(arrs[3])[:-1]
+        return np.split(out, cuts)
+
+    # -- speculation for the sequential shift solver ------------------------------------------
+    SPECULATE_GROUPS = 48        # groups precomputed per launch
+    SPECULATE_MARGIN = 0.35      # seconds of slack either side of the predicted search span
+
+    def speculate_fast_path(self, src_stream, groups, idx, anchor, window):
+        """Hint from calculate_shifts: groups[idx:] are about to be searched one by one around
+        start + anchor with +-window (the fast path, sushi.py:431-432).  Precompute, in ONE launch, the
+        curves of the next groups over a slightly wider span; find_substream then answers from them.
+        A curve value depends only on (template, absolute position), so a cached curve answers any
+        contained range with exactly the value and first-index argmin a live call returns."""
+        cache = self.__dict__.setdefault('_curve_cache', {})
+        first = groups[idx]
+        key0 = (src_stream._get_sample_for_time(first[0].start), src_stream._get_sample_for_time(first[-1].end))
+        if key0 in cache:
+            return
+        cache.clear()                                        # predictions made for an older anchor
+        batch = groups[idx:idx + self.SPECULATE_GROUPS]
+        starts = np.array([g[0].start for g in batch], np.float64)
+        ends = np.array([g[-1].end for g in batch], np.float64)
+        try:
+            toff, tlen, lag0, nlags, _ = self.plan_queries(src_stream, starts, ends, starts + anchor,
+                                                           np.full(len(batch), window + self.SPECULATE_MARGIN))
+        except SushiError:
+            return                                           # some group does not fit: let the live path decide
+        curves = self.match_curves(src_stream, toff, tlen, lag0, nlags)
+        for q in range(len(batch)):
+            cache[(int(toff[q]), int(toff[q] + tlen[q]))] = (src_stream, int(lag0[q]), curves[q])
+
+    def _from_cache(self, where, n, lo, nlags):
+        cache = self.__dict__.get('_curve_cache')
+        if not cache or where is None:
+            return None
+        hit = cache.get((where[1], where[1] + n))
+        if hit is None or hit[0] is not where[0]:
+            return None
+        _, c_lo, curve = hit
+        a = lo - c_lo
+        if a < 0 or a + nlags > len(curve):
+            return None
+        part = curve[a:a + nlags]
+        i = int(part.argmin())                               # first of equal minima, like the kernel
+        return part[i], i
 
     def match_curve(self, src_stream, toff, tlen, lag0, nlags):
         """Whole TM_SQDIFF_NORMED curve of one query (parity tests / debugging)."""

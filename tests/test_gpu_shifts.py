@@ -84,3 +84,40 @@ def test_find_substream_many_equals_singles(gpu_lib, golden_matcher):
     # a detached copy cannot be located: falls back to per-call uploads, same answers
     many2 = dst.find_substream_many([(tv.copy(), 7.6, 10.0)] + qs[1:])
     assert many2[0] == many[0]
+
+
+@pytest.mark.parametrize('name', ['const', 'jump', 'rewind'])
+def test_speculative_solver_is_bit_identical_to_live_calls(gpu_lib, golden_shifts, name):
+    """Answering the fast-path searches from precomputed curves changes nothing: same shifts, same
+    diffs (bit for bit), same links, as the run that issues every find_substream live."""
+    g = golden_shifts
+    src_pcm, dst_pcm, ev, params = scenario_inputs(g, name)
+    out = []
+    for speculative in (False, True):
+        src = WavStream.from_pcm(src_pcm, 12000)
+        dst = WavStream.from_pcm(dst_pcm, 12000)
+        events = [ScriptEvent(i, float(a), float(b)) for i, (a, b) in enumerate(ev)]
+        groups = prepare_search_groups(events, src.duration_seconds, [], 0.417, 0.417)
+        calculate_shifts(src, dst, groups, float(params[0]), float(params[1]), int(params[2]), speculative=speculative)
+        out.append([(e.shift, float(e.diff), e._link.source_index if e.linked else -1) for e in events])
+        if speculative:
+            assert dst.__dict__.get('_curve_cache')           # the speculation path was exercised
+    assert out[0] == out[1]
+
+
+def test_cached_curve_answers_equal_live_answers(gpu_lib, golden_matcher):
+    rs = oracle_stream_from_pcm(golden_matcher['src_pcm'], 12000, 1, 12000, 'uint8')
+    rd = oracle_stream_from_pcm(golden_matcher['dst_pcm'], 12000, 1, 12000, 'uint8')
+    src = WavStream.from_array(rs.data, 12000, rs.padding_size, rs.sample_count)
+    dst = WavStream.from_array(rd.data, 12000, rd.padding_size, rd.sample_count)
+    groups = [[ScriptEvent(i, a, a + 1.3)] for i, a in enumerate(np.arange(1.0, 19.0, 1.7))]
+    live = [dst.find_substream(src.get_substream(grp[0].start, grp[0].end), grp[0].start + 1.5 + 0.003 * i, 1.5)
+            for i, grp in enumerate(groups)]
+    dst.speculate_fast_path(src, groups, 0, 1.5, 1.5)
+    cached = [dst.find_substream(src.get_substream(grp[0].start, grp[0].end), grp[0].start + 1.5 + 0.003 * i, 1.5)
+              for i, grp in enumerate(groups)]
+    assert live == cached
+    # a range outside the cached span falls back to a live call and still agrees with the oracle
+    d, t = dst.find_substream(src.get_substream(1.0, 2.3), 6.0, 1.5)
+    d_ref, t_ref = rd.find_substream(rs.get_substream(1.0, 2.3), 6.0, 1.5)
+    assert abs(float(d) - float(d_ref)) <= 1e-5 and abs(t - t_ref) <= SAMPLE
