@@ -58,7 +58,12 @@ k_match_fused(const float2* __restrict__ That, int64_t part_first,
     float2* s_t2 = buf + pad(N) + 1;                                    // twiddle tables
     float2* s_a3 = s_t2 + NT2;
     float2* s_b3 = s_a3 + NT3;
-    unsigned long long* s_best = reinterpret_cast<unsigned long long*>(s_b3 + NT3);   // [NW]
+    // 16-byte aligned staging area for cp.async (the padded FFT buffer has an odd number of float2)
+    unsigned char* stage = smem_raw + (((size_t)(pad(N) + 1 + NT2 + 2 * NT3) * sizeof(float2) + 15) & ~(size_t)15);
+    double2* s_base = reinterpret_cast<double2*>(stage);                // [ROUNDS][NW][2] exact running sums
+    unsigned char* s_lo = reinterpret_cast<unsigned char*>(s_base + ROUNDS * NW * 2);   // image[j_blk .. +B+16)
+    unsigned char* s_hi = s_lo + B + 16;                                // image[(j_blk+n)&~15 .. +B+48)
+    unsigned long long* s_best = reinterpret_cast<unsigned long long*>(s_hi + B + 48);  // [NW]
     float* s_min = reinterpret_cast<float*>(s_best + NW);               // [NW]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -69,6 +74,25 @@ k_match_fused(const float2* __restrict__ That, int64_t part_first,
     for (int i = tid; i < NT3; i += T) { s_a3[i] = __ldg(tab.a3 + i); s_b3[i] = __ldg(tab.b3 + i); }
     const QueryDesc d = desc[q];
     const int64_t k = d.k0 + (item - d.itemBase);
+
+    // ---------------- 0. stage what the epilogue needs (uint8 streams) ----------------------
+    // The two byte windows the sliding sums read (image[j] and image[j+n] over this lag block)
+    // and one exact (sum, sum of squares) pair per warp-round from the fp64 running sums go to
+    // shared memory now, asynchronously; their latency hides behind the MAC and the FFT.
+    if (sizeof(S) == 1) {
+        const unsigned char* img8 = reinterpret_cast<const unsigned char*>(img);
+        const int64_t j_blk0 = k * B, hi0 = (j_blk0 + d.tlen) & ~(int64_t)15;
+        const int64_t limit = (img_n + 16) & ~(int64_t)15;               // allocation has 16 bytes of slack
+        for (int ch = tid; ch < (B + 16) / 16; ch += T)
+            if (j_blk0 + 16 * (int64_t)ch + 16 <= limit) cp_async16(s_lo + 16 * ch, img8 + j_blk0 + 16 * (int64_t)ch);
+        for (int ch = tid; ch < (B + 48) / 16; ch += T)
+            if (hi0 + 16 * (int64_t)ch + 16 <= limit) cp_async16(s_hi + 16 * ch, img8 + hi0 + 16 * (int64_t)ch);
+        if (tid < ROUNDS * NW * 2) {
+            const int c = tid / (NW * 2), w = (tid >> 1) % NW, which = tid & 1;
+            const int64_t jw = j_blk0 + c * LAGS_PER_ROUND + w * 256;    // first lag of warp w in round c
+            if (jw < d.lag0 + d.nlags) cp_async16(s_base + tid, ipfx + jw + (which ? d.tlen : 0));
+        }
+    }
 
     // ---------------- 1+2. spectral multiply-accumulate and Hermitian packing ---------------
     {
@@ -181,6 +205,7 @@ k_match_fused(const float2* __restrict__ That, int64_t part_first,
 #pragma unroll
             for (int r = 0; r < R / 2; ++r) buf[pad(j + r * Ns)] = v[b][brev<R>(r)];
         }
+        cp_async_commit_wait_all();                 // step 0's copies landed long ago; the barrier publishes them
         __syncthreads();
     }
     // now buf[pad(i)] = (x[2i], x[2i+1]) for i < N/2: correlation at lags 2i, 2i+1 (times 2B)
@@ -202,65 +227,85 @@ k_match_fused(const float2* __restrict__ That, int64_t part_first,
     const float f_tsq = (float)tsq, f_b = (float)b, f_scale = (float)scale;
     const bool interior = j_blk >= jlo && j_blk + B <= jhi;           // every lag of the item is valid
 
-    // exact window sums at the head of each run, fetched up front (two 16-byte loads per run)
-    double w0s[ROUNDS], w0q[ROUNDS];
-    bool live[ROUNDS];
-#pragma unroll
-    for (int c = 0; c < ROUNDS; ++c) {
-        const int64_t j0 = j_blk + c * LAGS_PER_ROUND + tid * 8;
-        live[c] = j0 < jhi && j0 + 8 > jlo;                           // the run holds a valid lag
-        w0s[c] = 0.0; w0q[c] = 0.0;
-        if (live[c]) {
-            const double2 p_hi = ipfx[j0 + n], p_lo = ipfx[j0];
-            w0s[c] = p_hi.x - p_lo.x; w0q[c] = p_hi.y - p_lo.y;
-        }
-    }
-
     float vf[ROUNDS][8];
     float tmin = 2.0f;
+    if (sizeof(S) == 1) {
+        // uint8: everything comes from shared memory.  Per round each warp covers 256 consecutive lags;
+        // lane l owns the run of 8 lags starting at jw + 8l.  Window sums at the head of a run = exact
+        // warp base + exclusive intra-warp scan of the runs' integer totals (dp4a), then slide by 1.
+        const int hi_off = (int)((j_blk + n) & 15);
 #pragma unroll
-    for (int c = 0; c < ROUNDS; ++c) {
-        const int m0 = c * LAGS_PER_ROUND + tid * 8;
-        const int64_t j0 = j_blk + m0;
+        for (int c = 0; c < ROUNDS; ++c) {
+            const int m0 = c * LAGS_PER_ROUND + tid * 8;
+            const int64_t j0 = j_blk + m0;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) vf[c][i] = 2.0f;                  // sentinel: not a valid lag
-        if (live[c]) {
-            const float f_w0q = (float)w0q[c];
-            const float f_k0 = (float)(b * w0s[c] + k_const);
+            for (int i = 0; i < 8; ++i) vf[c][i] = 2.0f;              // sentinel: not a valid lag
+            const int64_t jw = j_blk + c * LAGS_PER_ROUND + warp * 256;
+            if (jw >= jhi || jw + 256 <= jlo) continue;               // no valid lag in this warp-round (warp-uniform)
+            const unsigned long long lo8 = *reinterpret_cast<const unsigned long long*>(s_lo + m0);
+            const int hb = hi_off + m0;                                // byte offset into s_hi, any alignment
+            const unsigned long long h0 = *reinterpret_cast<const unsigned long long*>(s_hi + (hb & ~7));
+            const unsigned long long h1 = *reinterpret_cast<const unsigned long long*>(s_hi + (hb & ~7) + 8);
+            const unsigned sh = (unsigned)(hb & 7) * 8u;
+            const unsigned long long hi8 = sh ? ((h0 >> sh) | (h1 << (64u - sh))) : h0;
+            const unsigned la = (unsigned)lo8, lb = (unsigned)(lo8 >> 32), ha = (unsigned)hi8, hb2 = (unsigned)(hi8 >> 32);
+            int tq = (int)__dp4a(ha, ha, __dp4a(hb2, hb2, 0u)) - (int)__dp4a(la, la, __dp4a(lb, lb, 0u));
+            int ts = (int)__dp4a(ha, 0x01010101u, __dp4a(hb2, 0x01010101u, 0u)) - (int)__dp4a(la, 0x01010101u, __dp4a(lb, 0x01010101u, 0u));
+            int iq = tq, is = ts;                                      // inclusive scan over the lanes
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int uq = __shfl_up_sync(0xffffffffu, iq, o), us = __shfl_up_sync(0xffffffffu, is, o);
+                if (lane >= o) { iq += uq; is += us; }
+            }
+            const double2 b_lo = s_base[(c * NW + warp) * 2], b_hi = s_base[(c * NW + warp) * 2 + 1];
+            const double w0s = (b_hi.x - b_lo.x) + (double)(is - ts);
+            const double w0q = (b_hi.y - b_lo.y) + (double)(iq - tq);
+            const float f_w0q = (float)w0q;
+            const float f_k0 = (float)(b * w0s + k_const);
             float cc[8];
 #pragma unroll
             for (int h = 0; h < 4; ++h) { const float2 z = buf[pad((m0 >> 1) + h)]; cc[2 * h] = z.x; cc[2 * h + 1] = z.y; }
-            if (sizeof(S) == 1) {
-                const uint8_t* img8 = reinterpret_cast<const uint8_t*>(img);
-                const unsigned long long lo8 = __ldg(reinterpret_cast<const unsigned long long*>(img8 + j0));   // j0 % 8 == 0
-                const unsigned long long hi8 = load8(img8, j0 + n);
-                int rq = 0, rs = 0;
+            int rq = 0, rs = 0;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const float wq = f_w0q + (float)rq;
-                    const float sit = fmaf(cc[i], f_scale, fmaf(f_b, (float)rs, f_k0));
-                    const float num = fmaxf((wq + f_tsq) - 2.0f * sit, 0.0f);
-                    const float pr = wq * f_tsq;
-                    const float v = pr > 0.0f ? fminf(num * rsqrtf(pr), 1.0f) : 1.0f;
-                    if (interior || (j0 + i >= jlo && j0 + i < jhi)) { vf[c][i] = v; tmin = fminf(tmin, v); }
-                    const int lo = (int)((lo8 >> (8 * i)) & 0xffu), hi = (int)((hi8 >> (8 * i)) & 0xffu);
+            for (int i = 0; i < 8; ++i) {
+                const float wq = f_w0q + (float)rq;
+                const float sit = fmaf(cc[i], f_scale, fmaf(f_b, (float)rs, f_k0));
+                const float num = fmaxf((wq + f_tsq) - 2.0f * sit, 0.0f);
+                const float pr = wq * f_tsq;
+                const float v = pr > 0.0f ? fminf(num * rsqrt_fast(pr), 1.0f) : 1.0f;
+                if (interior || (j0 + i >= jlo && j0 + i < jhi)) { vf[c][i] = v; tmin = fminf(tmin, v); }
+                const int lo = (int)((lo8 >> (8 * i)) & 0xffu), hi = (int)((hi8 >> (8 * i)) & 0xffu);
+                rq += hi * hi - lo * lo; rs += hi - lo;
+            }
+        }
+    } else {
+        // float32 streams: exact fp64 base per run straight from the running sums, slide in fp64
+#pragma unroll
+        for (int c = 0; c < ROUNDS; ++c) {
+            const int m0 = c * LAGS_PER_ROUND + tid * 8;
+            const int64_t j0 = j_blk + m0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) vf[c][i] = 2.0f;
+            if (!(j0 < jhi && j0 + 8 > jlo)) continue;
+            const double2 p_hi = ipfx[j0 + n], p_lo = ipfx[j0];
+            const float f_w0q = (float)(p_hi.y - p_lo.y);
+            const float f_k0 = (float)(b * (p_hi.x - p_lo.x) + k_const);
+            float cc[8];
+#pragma unroll
+            for (int h = 0; h < 4; ++h) { const float2 z = buf[pad((m0 >> 1) + h)]; cc[2 * h] = z.x; cc[2 * h + 1] = z.y; }
+            double rq = 0.0, rs = 0.0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int64_t j = j0 + i;
+                const float wq = f_w0q + (float)rq;
+                const float sit = fmaf(cc[i], f_scale, fmaf(f_b, (float)rs, f_k0));
+                const float num = fmaxf((wq + f_tsq) - 2.0f * sit, 0.0f);
+                const float pr = wq * f_tsq;
+                const float v = pr > 0.0f ? fminf(num * rsqrt_fast(pr), 1.0f) : 1.0f;
+                if (j >= jlo && j < jhi) { vf[c][i] = v; tmin = fminf(tmin, v); }
+                if (j + n < img_n) {
+                    const double lo = (double)img[j], hi = (double)img[j + n];
                     rq += hi * hi - lo * lo; rs += hi - lo;
-                }
-            } else {
-                double rq = 0.0, rs = 0.0;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int64_t j = j0 + i;
-                    const float wq = f_w0q + (float)rq;
-                    const float sit = fmaf(cc[i], f_scale, fmaf(f_b, (float)rs, f_k0));
-                    const float num = fmaxf((wq + f_tsq) - 2.0f * sit, 0.0f);
-                    const float pr = wq * f_tsq;
-                    const float v = pr > 0.0f ? fminf(num * rsqrtf(pr), 1.0f) : 1.0f;
-                    if (j >= jlo && j < jhi) { vf[c][i] = v; tmin = fminf(tmin, v); }
-                    if (j + n < img_n) {
-                        const double lo = (double)img[j], hi = (double)img[j + n];
-                        rq += hi * hi - lo * lo; rs += hi - lo;
-                    }
                 }
             }
         }
@@ -312,7 +357,9 @@ template <int LOGN> size_t fused_smem_bytes() {
     typedef Cfg<LOGN> C;
     const size_t padded = (size_t)(C::N + (C::N >> 5) + 1);
     const size_t nw = C::T / 32;
-    return (padded + C::R2 * 32 + 2 * C::R3 * 32) * sizeof(float2) + nw * sizeof(unsigned long long) + nw * sizeof(float) + 64;
+    const size_t rounds = C::N / (C::T * 8);
+    return (padded + C::R2 * 32 + 2 * C::R3 * 32) * sizeof(float2) + nw * sizeof(unsigned long long)
+         + 16 + rounds * nw * 2 * sizeof(double2) + (C::N + 16) + (C::N + 48) + nw * sizeof(float) + 64;
 }
 
 struct TableSet { float2* dev = nullptr; FusedTables tab; };

@@ -103,4 +103,20 @@ __device__ __forceinline__ unsigned long long load8(const uint8_t* __restrict__ 
 }
 
 
+// single MUFU.RSQ (the operands here are ~1e18, never subnormal)
+__device__ __forceinline__ float rsqrt_fast(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// 16-byte asynchronous global->shared copy (LDGSTS); both addresses 16-byte aligned
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(s), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
 }  // namespace sbf
