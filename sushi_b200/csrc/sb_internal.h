@@ -82,11 +82,9 @@ struct Ctx {
 
 Ctx& ctx();
 int prof_id(const char* name);
-void prof_begin(int id, cudaEvent_t* a, cudaEvent_t* b);
-void prof_end(int id, cudaEvent_t a, cudaEvent_t b);
 int prof_collect();
 
-// RAII-free bracket used around every kernel class
+// RAII bracket around every kernel class: counts launches, and records CUDA events when profiling is on
 struct ProfScope {
     int id; cudaEvent_t a = nullptr, b = nullptr; bool on;
     explicit ProfScope(const char* name, int nlaunch = 1);
