@@ -15,3 +15,5 @@ from .grouping import (prepare_search_groups, merge_short_lines_into_groups, gro
                        interpolate_nones, running_median)
 
 __version__ = '0.1.0'
+from .script import AssScript, SrtScript, AssEvent, SrtEvent, load_script   # noqa: F401,E402
+from .pipeline import shift_events, shift_script   # noqa: F401,E402

@@ -121,3 +121,35 @@ def test_cached_curve_answers_equal_live_answers(gpu_lib, golden_matcher):
     d, t = dst.find_substream(src.get_substream(1.0, 2.3), 6.0, 1.5)
     d_ref, t_ref = rd.find_substream(rs.get_substream(1.0, 2.3), 6.0, 1.5)
     assert abs(float(d) - float(d_ref)) <= 1e-5 and abs(t - t_ref) <= SAMPLE
+
+
+def test_shift_script_end_to_end(gpu_lib, tmp_path):
+    """WAV + ASS in, shifted ASS out (sushi.py:660-726 without demux/keyframes): stereo 48 kHz files go
+    through the GPU loader, the events through the solver and the heuristics, and every dialogue line
+    lands on the known shift; comments follow the line they are linked to."""
+    import wave
+    from sushi_b200 import shift_script, AssScript
+    dur, shift = 70.0, 2.25
+    src12, dst12 = synth.make_pair(dur, 31, shift)
+    for name, pcm in (('src.wav', src12), ('dst.wav', dst12)):
+        up = np.repeat(pcm, 4)                                   # 48 kHz whose nearest-resample is the 12 kHz signal
+        st = np.stack([up, up], 1)
+        with wave.open(str(tmp_path / name), 'wb') as w:
+            w.setnchannels(2); w.setsampwidth(2); w.setframerate(48000); w.writeframes(st.tobytes())
+    starts, ends = synth.make_events(24, dur - 8.0, 31, 0.8, 3.0, 1.5)
+    from sushi_b200.common import format_time
+    lines = ['[Script Info]', 'Title: t', '', '[V4+ Styles]', AssScript.STYLES_FORMAT,
+             'Style: Default,Arial,20,&H00FFFFFF,&H000000FF,&H00000000,&H00000000,0,0,0,0,100,100,0,0,1,2,2,2,10,10,10,1',
+             '', '[Events]', AssScript.EVENTS_FORMAT]
+    for i, (a, b) in enumerate(zip(starts, ends)):
+        kind = 'Comment' if i == 5 else 'Dialogue'
+        lines.append('{0}: 0,{1},{2},Default,,0,0,0,,line {3}, with a comma'.format(kind, format_time(a), format_time(b), i))
+    (tmp_path / 'in.ass').write_text('\n'.join(lines), encoding='utf-8')
+    script, groups = shift_script(str(tmp_path / 'src.wav'), str(tmp_path / 'dst.wav'), str(tmp_path / 'in.ass'),
+                                  str(tmp_path / 'out.ass'))
+    out = AssScript.from_file(str(tmp_path / 'out.ass'))
+    assert len(out.events) == len(starts) and len(groups) == 1
+    for e, a, b in zip(out.events, starts, ends):
+        # ASS stores centiseconds: the written time is the shifted time rounded to 0.01 s
+        assert abs(e.start - (round(a * 100) / 100 + shift)) <= 0.011 and abs(e.end - (round(b * 100) / 100 + shift)) <= 0.011
+    assert out.events[5].is_comment and out.events[0].text == 'line 0, with a comma'

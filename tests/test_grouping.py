@@ -126,3 +126,14 @@ def test_average_shifts_is_weighted_by_one_minus_diff():
     a.linked = b.linked = None
     avg = grouping.average_shifts([a, b])
     assert abs(avg - (1.0 * 0.5 + 2.0 * 1.0) / 1.5) < 1e-12 and a.shift == b.shift == avg
+
+
+def test_vectorised_running_median_equals_the_loop():
+    import numpy as np
+    rng = np.random.default_rng(0)
+    for n in (1, 2, 5, 7, 8, 50, 501):
+        vals = list(rng.normal(0, 1, n))
+        for w in (1, 3, 7, 11):
+            half = w // 2
+            want = [np.median(vals[i - min(half, i, n - i - 1):i + min(half, i, n - i - 1) + 1]) for i in range(n)]
+            assert grouping.running_median(vals, w) == want
