@@ -156,12 +156,19 @@ k_match_fused(const float2* __restrict__ That, int64_t part_first,
         constexpr int R = C::R1;
         static_assert(N / R == T, "pass 1: one butterfly per thread");
         float2 v[R];
+        // pad(i + 32c) = pad(i) + 33c: every address below is one base plus a compile-time offset
+        {
+            const float2* src = buf + pad(tid);
 #pragma unroll
-        for (int r = 0; r < R; ++r) v[r] = buf[pad(tid + r * (N / R))];
+            for (int r = 0; r < R; ++r) v[r] = src[r * ((N / R) + (N / R) / 32)];
+        }
         __syncthreads();
         dft_dif<R>(v);
+        {
+            float2* dst = buf + tid * (R + 1);              // pad(tid*32 + r) = 33*tid + r
 #pragma unroll
-        for (int r = 0; r < R; ++r) buf[pad(tid * R + r)] = v[brev<R>(r)];
+            for (int r = 0; r < R; ++r) dst[r] = v[brev<R>(r)];
+        }
         __syncthreads();
     }
     {   // pass 2: Ns = 32, k = lane
@@ -170,7 +177,7 @@ k_match_fused(const float2* __restrict__ That, int64_t part_first,
 #pragma unroll
         for (int b = 0; b < PER; ++b)
 #pragma unroll
-            for (int r = 0; r < R; ++r) v[b][r] = buf[pad(tid + b * T + r * (N / R))];
+            for (int r = 0; r < R; ++r) v[b][r] = buf[pad(tid) + (b * T + r * (N / R)) / 32 * 33];
         __syncthreads();
 #pragma unroll
         for (int b = 0; b < PER; ++b) {
@@ -180,7 +187,7 @@ k_match_fused(const float2* __restrict__ That, int64_t part_first,
             dft_dif<R>(v[b]);
             const int j0 = (j - lane) * R + lane;
 #pragma unroll
-            for (int r = 0; r < R; ++r) buf[pad(j0 + r * Ns)] = v[b][brev<R>(r)];
+            for (int r = 0; r < R; ++r) buf[pad(j0) + r * (Ns / 32 * 33)] = v[b][brev<R>(r)];
         }
         __syncthreads();
     }
@@ -192,7 +199,7 @@ k_match_fused(const float2* __restrict__ That, int64_t part_first,
 #pragma unroll
         for (int b = 0; b < PER; ++b)
 #pragma unroll
-            for (int r = 0; r < R; ++r) v[b][r] = buf[pad(tid + b * T + r * (N / R))];
+            for (int r = 0; r < R; ++r) v[b][r] = buf[pad(tid) + (b * T + r * (N / R)) / 32 * 33];
         __syncthreads();
 #pragma unroll
         for (int b = 0; b < PER; ++b) {
@@ -203,7 +210,7 @@ k_match_fused(const float2* __restrict__ That, int64_t part_first,
                 v[b][r] = cmul(v[b][r], cmul(s_a3[r * 32 + lane], s_b3[r * 32 + kh]));
             dft_dif<R, true>(v[b]);
 #pragma unroll
-            for (int r = 0; r < R / 2; ++r) buf[pad(j + r * Ns)] = v[b][brev<R>(r)];
+            for (int r = 0; r < R / 2; ++r) buf[pad(tid) + (b * T + r * Ns) / 32 * 33] = v[b][brev<R>(r)];
         }
         cp_async_commit_wait_all();                 // step 0's copies landed long ago; the barrier publishes them
         __syncthreads();
@@ -264,7 +271,7 @@ k_match_fused(const float2* __restrict__ That, int64_t part_first,
             const float f_k0 = (float)(b * w0s + k_const);
             float cc[8];
 #pragma unroll
-            for (int h = 0; h < 4; ++h) { const float2 z = buf[pad((m0 >> 1) + h)]; cc[2 * h] = z.x; cc[2 * h + 1] = z.y; }
+            for (int h = 0; h < 4; ++h) { const float2 z = buf[pad(m0 >> 1) + h]; cc[2 * h] = z.x; cc[2 * h + 1] = z.y; }
             int rq = 0, rs = 0;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -292,7 +299,7 @@ k_match_fused(const float2* __restrict__ That, int64_t part_first,
             const float f_k0 = (float)(b * (p_hi.x - p_lo.x) + k_const);
             float cc[8];
 #pragma unroll
-            for (int h = 0; h < 4; ++h) { const float2 z = buf[pad((m0 >> 1) + h)]; cc[2 * h] = z.x; cc[2 * h + 1] = z.y; }
+            for (int h = 0; h < 4; ++h) { const float2 z = buf[pad(m0 >> 1) + h]; cc[2 * h] = z.x; cc[2 * h + 1] = z.y; }
             double rq = 0.0, rs = 0.0;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
