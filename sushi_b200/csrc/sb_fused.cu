@@ -130,9 +130,9 @@ k_match_fused(const float2* __restrict__ That, int64_t part_first,
                 // Z[m]   = (Ym + conj(Yp)) + i*(Ym - conj(Yp))*w
                 const float2 e = make_float2(ym[u].x + yp[u].x, ym[u].y - yp[u].y);
                 const float2 o = cmul(make_float2(ym[u].x - yp[u].x, ym[u].y + yp[u].y), w);
-                buf[pad(m)] = make_float2(e.x - o.y, e.y + o.x);
+                buf[pad(m0) + u * (T / 32 * 33)] = make_float2(e.x - o.y, e.y + o.x);
                 // Z[B-m] = conj(e) + i*conj(o)   (w^(B-m) = -conj(w^m))
-                if (m > 0) buf[pad(B - m)] = make_float2(e.x + o.y, -e.y + o.x);
+                if (m > 0) buf[pad(B - m0) - u * (T / 32 * 33)] = make_float2(e.x + o.y, -e.y + o.x);
             }
         }
         if (tid < 32) {                             // the self-paired bin m = B/2 (w = i): Z = 2*conj(Y)
@@ -245,10 +245,12 @@ k_match_fused(const float2* __restrict__ That, int64_t part_first,
         for (int c = 0; c < ROUNDS; ++c) {
             const int m0 = c * LAGS_PER_ROUND + tid * 8;
             const int64_t j0 = j_blk + m0;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) vf[c][i] = 2.0f;              // sentinel: not a valid lag
             const int64_t jw = j_blk + c * LAGS_PER_ROUND + warp * 256;
-            if (jw >= jhi || jw + 256 <= jlo) continue;               // no valid lag in this warp-round (warp-uniform)
+            if (jw >= jhi || jw + 256 <= jlo) {                       // no valid lag in this warp-round (warp-uniform)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) vf[c][i] = 2.0f;
+                continue;
+            }
             const unsigned long long lo8 = *reinterpret_cast<const unsigned long long*>(s_lo + m0);
             const int hb = hi_off + m0;                                // byte offset into s_hi, any alignment
             const unsigned long long h0 = *reinterpret_cast<const unsigned long long*>(s_hi + (hb & ~7));
@@ -279,8 +281,11 @@ k_match_fused(const float2* __restrict__ That, int64_t part_first,
                 const float sit = fmaf(cc[i], f_scale, fmaf(f_b, (float)rs, f_k0));
                 const float num = fmaxf((wq + f_tsq) - 2.0f * sit, 0.0f);
                 const float pr = wq * f_tsq;
-                const float v = pr > 0.0f ? fminf(num * rsqrt_fast(pr), 1.0f) : 1.0f;
-                if (interior || (j0 + i >= jlo && j0 + i < jhi)) { vf[c][i] = v; tmin = fminf(tmin, v); }
+                // pr == 0 (silent window or template): rsqrt -> inf, num*inf -> inf or NaN, fminf(.,1) -> 1
+                const float v = fminf(num * rsqrt_fast(pr), 1.0f);
+                if (interior) { vf[c][i] = v; tmin = fminf(tmin, v); }
+                else if (j0 + i >= jlo && j0 + i < jhi) { vf[c][i] = v; tmin = fminf(tmin, v); }
+                else vf[c][i] = 2.0f;                                  // sentinel: not a valid lag
                 const int lo = (int)((lo8 >> (8 * i)) & 0xffu), hi = (int)((hi8 >> (8 * i)) & 0xffu);
                 rq += hi * hi - lo * lo; rs += hi - lo;
             }
@@ -308,7 +313,7 @@ k_match_fused(const float2* __restrict__ That, int64_t part_first,
                 const float sit = fmaf(cc[i], f_scale, fmaf(f_b, (float)rs, f_k0));
                 const float num = fmaxf((wq + f_tsq) - 2.0f * sit, 0.0f);
                 const float pr = wq * f_tsq;
-                const float v = pr > 0.0f ? fminf(num * rsqrt_fast(pr), 1.0f) : 1.0f;
+                const float v = fminf(num * rsqrt_fast(pr), 1.0f);
                 if (j >= jlo && j < jhi) { vf[c][i] = v; tmin = fminf(tmin, v); }
                 if (j + n < img_n) {
                     const double lo = (double)img[j], hi = (double)img[j + n];
@@ -317,6 +322,7 @@ k_match_fused(const float2* __restrict__ That, int64_t part_first,
             }
         }
     }
+    const float my_min = tmin;                                        // this thread's own best
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) tmin = fminf(tmin, __shfl_xor_sync(0xffffffffu, tmin, o));
     if (lane == 0) s_min[warp] = tmin;
@@ -328,10 +334,12 @@ k_match_fused(const float2* __restrict__ That, int64_t part_first,
 
     // lags that can still be the minimum (bit c*8+i), then ONE copy of the fp64 path
     unsigned cand = 0;
+    if (my_min <= thr) {
 #pragma unroll
-    for (int c = 0; c < ROUNDS; ++c)
+        for (int c = 0; c < ROUNDS; ++c)
 #pragma unroll
-        for (int i = 0; i < 8; ++i) cand |= (vf[c][i] <= thr) ? (1u << (c * 8 + i)) : 0u;
+            for (int i = 0; i < 8; ++i) cand |= (vf[c][i] <= thr) ? (1u << (c * 8 + i)) : 0u;
+    }
     unsigned long long best = ~0ull;
     while (cand) {
         const int bit = __ffs(cand) - 1;
