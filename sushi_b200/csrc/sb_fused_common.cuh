@@ -1,5 +1,5 @@
-// Device helpers shared by the fused lag-block kernels (sb_fused.cu: 32 values per thread,
-// sb_fused16.cu: 16 values per thread).
+// Device helpers of the fused lag-block kernel (sb_fused.cu): complex arithmetic, in-register DFTs,
+// the exact per-lag formula, async-copy wrappers.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>

@@ -54,7 +54,7 @@ struct Ctx {
     cudaStream_t stream = nullptr;
     int B = 16384;                 // lag-block size (samples); FFT size is 2B
     int chunk_items = 1024;        // items per MAC/C2R/normalise chunk (cuFFT engine)
-    int engine = 1;                // 1: fused kernel, 32 values/thread (sb_fused.cu); 2: fused, 16 values/thread (sb_fused16.cu); 0: cuFFT pipeline
+    int engine = 1;                // 1: fused lag-block kernel (sb_fused.cu), 0: cuFFT pipeline
     int64_t max_parts = 16384;     // template partition spectra kept per super-chunk
 
     // scratch (grown on demand)
@@ -102,10 +102,6 @@ int launch_match_fused(const sb_stream* image, const sb_stream* tmpl, const floa
                        const QueryDesc* d_desc, int q_begin, int q_end, int64_t item_first, int64_t n_items,
                        unsigned long long* d_keys, float* d_curve);
 void fused_release_tables();
-int launch_match_fused16(const sb_stream* image, const sb_stream* tmpl, const float2* d_parts, int64_t part_first,
-                         const QueryDesc* d_desc, int q_begin, int q_end, int64_t item_first, int64_t n_items,
-                         unsigned long long* d_keys, float* d_curve);
-void fused16_release_tables();
 
 int get_plan(int type, int64_t batch, cufftHandle* out);
 void drop_plans();

@@ -342,7 +342,7 @@ int run_batch(const sb_stream* image_c, const sb_stream* tmpl, int64_t count,
 
     const int64_t parts_cap_want = std::max<int64_t>(std::min<int64_t>(total_parts, c.max_parts), maxp);
     SB_TRY(grow(&c.d_parts, &c.parts_cap, parts_cap_want * nb));
-    const bool use_fused = (c.engine == 1 || c.engine == 2) && fused_supports(B);
+    const bool use_fused = c.engine == 1 && fused_supports(B);
     const int64_t chunk = std::min<int64_t>(c.chunk_items, total_items);
     if (!use_fused) SB_TRY(grow(&c.d_items, &c.items_cap, chunk * nb));
 
@@ -383,9 +383,8 @@ int run_batch(const sb_stream* image_c, const sb_stream* tmpl, int64_t count,
         const int64_t item_hi = (qe < count) ? c.h_desc[qe].itemBase : total_items;
         if (use_fused) {
             ProfScope ps("match_fused");
-            SB_TRY((c.engine == 2 ? launch_match_fused16 : launch_match_fused)(
-                image, tmpl, c.d_parts, part_first, c.d_desc, (int)qb, (int)qe,
-                item_lo, item_hi - item_lo, c.d_keys, d_curve));
+            SB_TRY(launch_match_fused(image, tmpl, c.d_parts, part_first, c.d_desc, (int)qb, (int)qe,
+                                      item_lo, item_hi - item_lo, c.d_keys, d_curve));
         } else
         for (int64_t i0 = item_lo; i0 < item_hi; i0 += chunk) {
             const int64_t ni = std::min<int64_t>(chunk, item_hi - i0);

@@ -91,12 +91,12 @@ def test_fused_engine_equals_cufft_engine(gpu_lib, pair, stype, block):
         toff, n = src._get_sample_for_time(6.1), 11400
         lag0, nlags = 70000, 150001
         curves, results = [], []
-        for engine in (0, 1, 2):
+        for engine in (0, 1):
             _native.check(gpu_lib.sb_set_engine(engine))
             curves.append(dst.match_curve(src, toff, n, lag0, nlags))
             results.append(dst.find_planned(src, [toff, toff + 5000, 100], [n, 3000, 48000],
                                             [lag0, 1000, 0], [nlags, 300000, 200000]))
-        for e in (1, 2):
+        for e in (1,):
             assert np.abs(curves[0] - curves[e]).max() <= 2e-6
             assert np.abs(results[0][0] - results[e][0]).max() <= 2e-6
             assert np.abs(results[0][1] - results[e][1]).max() <= 1
@@ -309,7 +309,7 @@ def test_empty_batch_is_a_no_op(gpu_lib, pair):
     assert len(d) == 0 and len(i) == 0
 
 
-@pytest.mark.parametrize('engine', [0, 1, 2])
+@pytest.mark.parametrize('engine', [0, 1])
 def test_minimum_sizes_and_ragged_edges(gpu_lib, engine):
     """n = 1 templates, single-lag searches, streams shorter than one lag block, searches that end on
     the last sample, spans that straddle exactly one block boundary."""
