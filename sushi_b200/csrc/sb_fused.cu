@@ -36,6 +36,86 @@ struct FusedTables {
     const float2* b3;     // [R3][32]  exp(+2*pi*i*r*kh*32/N), kh = k / 32     (pass 3, high part)
 };
 
+// ---------------------------------------------------------------- the FFT
+// Unnormalised inverse DFT (sign +) of N complex points held in shared memory in the padded layout
+// buf[pad(i)].  Stockham passes: butterfly j reads in[j + r*N/R], twiddles by exp(2*pi*i*r*k/(Ns*R)),
+// k = j mod Ns, and writes out[(j-k)*R + k + r*Ns]; every value sits in a register between the two
+// barriers of a pass, so the transform is in place and the output is in natural order.
+// Must be entered after a barrier that made buf visible; ends with a barrier.
+template <int LOGN, bool HALF>
+__device__ __forceinline__ void ifft_smem(float2* __restrict__ buf, const float2* __restrict__ s_t2,
+                                          const float2* __restrict__ s_a3, const float2* __restrict__ s_b3) {
+    typedef Cfg<LOGN> C;
+    constexpr int N = C::N, T = C::T;
+    const int tid = threadIdx.x, lane = tid & 31;
+    // Stockham passes: butterfly j reads in[j + r*N/R], twiddles by exp(2*pi*i*r*k/(Ns*R)),
+    // k = j mod Ns, and writes out[(j-k)*R + k + r*Ns]; every value sits in a register between
+    // the two barriers, so the pass is in place.
+    {   // pass 1: R1 = 32, Ns = 1 (no twiddles); one butterfly per thread
+        constexpr int R = C::R1;
+        static_assert(N / R == T, "pass 1: one butterfly per thread");
+        float2 v[R];
+        // pad(i + 32c) = pad(i) + 33c: every address below is one base plus a compile-time offset
+        {
+            const float2* src = buf + pad(tid);
+#pragma unroll
+            for (int r = 0; r < R; ++r) v[r] = src[r * ((N / R) + (N / R) / 32)];
+        }
+        __syncthreads();
+        dft_dif<R>(v);
+        {
+            float2* dst = buf + tid * (R + 1);              // pad(tid*32 + r) = 33*tid + r
+#pragma unroll
+            for (int r = 0; r < R; ++r) dst[r] = v[brev<R>(r)];
+        }
+        __syncthreads();
+    }
+    {   // pass 2: Ns = 32, k = lane
+        constexpr int R = C::R2, Ns = C::R1, PER = (N / R) / T;
+        float2 v[PER][R];
+#pragma unroll
+        for (int b = 0; b < PER; ++b)
+#pragma unroll
+            for (int r = 0; r < R; ++r) v[b][r] = buf[pad(tid) + (b * T + r * (N / R)) / 32 * 33];
+        __syncthreads();
+#pragma unroll
+        for (int b = 0; b < PER; ++b) {
+            const int j = tid + b * T;
+#pragma unroll
+            for (int r = 1; r < R; ++r) v[b][r] = cmul(v[b][r], s_t2[r * 32 + lane]);
+            dft_dif<R>(v[b]);
+            const int j0 = (j - lane) * R + lane;
+#pragma unroll
+            for (int r = 0; r < R; ++r) buf[pad(j0) + r * (Ns / 32 * 33)] = v[b][brev<R>(r)];
+        }
+        __syncthreads();
+    }
+    {   // pass 3: Ns = R1*R2, k = j (j < Ns).  HALF: only the first half of the outputs is needed
+        // (z[0 .. N/2) carries the B valid lags of the 2B-point real sequence)
+        constexpr int R = C::R3, Ns = C::R1 * C::R2, PER = (N / R) / T;
+        static_assert(N / R == Ns, "pass 3 is the last pass");
+        float2 v[PER][R];
+#pragma unroll
+        for (int b = 0; b < PER; ++b)
+#pragma unroll
+            for (int r = 0; r < R; ++r) v[b][r] = buf[pad(tid) + (b * T + r * (N / R)) / 32 * 33];
+        __syncthreads();
+#pragma unroll
+        for (int b = 0; b < PER; ++b) {
+            const int j = tid + b * T;
+            const int kh = j >> 5;
+#pragma unroll
+            for (int r = 1; r < R; ++r)
+                v[b][r] = cmul(v[b][r], cmul(s_a3[r * 32 + lane], s_b3[r * 32 + kh]));
+            dft_dif<R, HALF>(v[b]);
+#pragma unroll
+            for (int r = 0; r < (HALF ? R / 2 : R); ++r) buf[pad(tid) + (b * T + r * Ns) / 32 * 33] = v[b][brev<R>(r)];
+        }
+        if (HALF) cp_async_commit_wait_all();       // the fused kernel's staged copies landed long ago; the barrier publishes them
+        __syncthreads();
+    }
+}
+
 // ---------------------------------------------------------------- the kernel
 template <int LOGN, typename S>
 __global__ void __launch_bounds__(Cfg<LOGN>::T, Cfg<LOGN>::MINB)
@@ -149,72 +229,7 @@ k_match_fused(const float2* __restrict__ That, int64_t part_first,
     __syncthreads();
 
     // ---------------- 3. inverse FFT of N complex points in shared memory -------------------
-    // Stockham passes: butterfly j reads in[j + r*N/R], twiddles by exp(2*pi*i*r*k/(Ns*R)),
-    // k = j mod Ns, and writes out[(j-k)*R + k + r*Ns]; every value sits in a register between
-    // the two barriers, so the pass is in place.
-    {   // pass 1: R1 = 32, Ns = 1 (no twiddles); one butterfly per thread
-        constexpr int R = C::R1;
-        static_assert(N / R == T, "pass 1: one butterfly per thread");
-        float2 v[R];
-        // pad(i + 32c) = pad(i) + 33c: every address below is one base plus a compile-time offset
-        {
-            const float2* src = buf + pad(tid);
-#pragma unroll
-            for (int r = 0; r < R; ++r) v[r] = src[r * ((N / R) + (N / R) / 32)];
-        }
-        __syncthreads();
-        dft_dif<R>(v);
-        {
-            float2* dst = buf + tid * (R + 1);              // pad(tid*32 + r) = 33*tid + r
-#pragma unroll
-            for (int r = 0; r < R; ++r) dst[r] = v[brev<R>(r)];
-        }
-        __syncthreads();
-    }
-    {   // pass 2: Ns = 32, k = lane
-        constexpr int R = C::R2, Ns = C::R1, PER = (N / R) / T;
-        float2 v[PER][R];
-#pragma unroll
-        for (int b = 0; b < PER; ++b)
-#pragma unroll
-            for (int r = 0; r < R; ++r) v[b][r] = buf[pad(tid) + (b * T + r * (N / R)) / 32 * 33];
-        __syncthreads();
-#pragma unroll
-        for (int b = 0; b < PER; ++b) {
-            const int j = tid + b * T;
-#pragma unroll
-            for (int r = 1; r < R; ++r) v[b][r] = cmul(v[b][r], s_t2[r * 32 + lane]);
-            dft_dif<R>(v[b]);
-            const int j0 = (j - lane) * R + lane;
-#pragma unroll
-            for (int r = 0; r < R; ++r) buf[pad(j0) + r * (Ns / 32 * 33)] = v[b][brev<R>(r)];
-        }
-        __syncthreads();
-    }
-    {   // pass 3: Ns = R1*R2, k = j (j < Ns); only the first half of the outputs is needed:
-        // z[0 .. N/2) carries the B valid lags of the 2B-point real sequence
-        constexpr int R = C::R3, Ns = C::R1 * C::R2, PER = (N / R) / T;
-        static_assert(N / R == Ns, "pass 3 is the last pass");
-        float2 v[PER][R];
-#pragma unroll
-        for (int b = 0; b < PER; ++b)
-#pragma unroll
-            for (int r = 0; r < R; ++r) v[b][r] = buf[pad(tid) + (b * T + r * (N / R)) / 32 * 33];
-        __syncthreads();
-#pragma unroll
-        for (int b = 0; b < PER; ++b) {
-            const int j = tid + b * T;
-            const int kh = j >> 5;
-#pragma unroll
-            for (int r = 1; r < R; ++r)
-                v[b][r] = cmul(v[b][r], cmul(s_a3[r * 32 + lane], s_b3[r * 32 + kh]));
-            dft_dif<R, true>(v[b]);
-#pragma unroll
-            for (int r = 0; r < R / 2; ++r) buf[pad(tid) + (b * T + r * Ns) / 32 * 33] = v[b][brev<R>(r)];
-        }
-        cp_async_commit_wait_all();                 // step 0's copies landed long ago; the barrier publishes them
-        __syncthreads();
-    }
+    ifft_smem<LOGN, true>(buf, s_t2, s_a3, s_b3);
     // now buf[pad(i)] = (x[2i], x[2i+1]) for i < N/2: correlation at lags 2i, 2i+1 (times 2B)
 
     // ---------------- 4. window sums, fp32 screening, fp64 exact evaluation -----------------
@@ -367,6 +382,83 @@ k_match_fused(const float2* __restrict__ That, int64_t part_first,
     }
 }
 
+// ---------------------------------------------------------------- forward spectra
+// Real-to-complex transform of 2B centred samples per row, written as the B+1 bins every other
+// kernel expects (same layout and scaling as an unnormalised R2C of size 2B).  It is the inverse
+// kernel's machinery run backwards: z[n] = x[2n] + i*x[2n+1], Z = conj(IFFT(conj(z))), then
+//   X[k] = Xe + conj(w^k)*Xo,  X[B-k] = conj(Xe - conj(w^k)*Xo),
+//   Xe = (Z[k] + conj(Z[B-k]))/2,  Xo = -i*(Z[k] - conj(Z[B-k]))/2,  w = exp(i*pi/B).
+// Rows are either the lag blocks of a stream (MODE 0: samples [kB, kB+2B), centred on the stream
+// mean) or the partitions of the batch's templates (MODE 1: B samples + B zeros, centred on the
+// template's own mean) -- the gather, the centring and the FFT are one pass over the data.
+template <int LOGN, typename S, int MODE>
+__global__ void __launch_bounds__(Cfg<LOGN>::T, Cfg<LOGN>::MINB)
+k_forward_rows(const S* __restrict__ src, int64_t src_n, const double2* __restrict__ pfx,
+               const QueryDesc* __restrict__ desc, int q_begin, int q_end, int64_t row_first,
+               FusedTables tab, float2* __restrict__ out) {
+    typedef Cfg<LOGN> C;
+    constexpr int N = C::N, T = C::T, B = C::N, NB = B + 1;
+    constexpr int NT2 = C::R2 * 32, NT3 = C::R3 * 32;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* buf = reinterpret_cast<float2*>(smem_raw);
+    float2* s_t2 = buf + pad(N) + 1;
+    float2* s_a3 = s_t2 + NT2;
+    float2* s_b3 = s_a3 + NT3;
+    __shared__ int s_q;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < NT2; i += T) s_t2[i] = __ldg(tab.t2 + i);
+    for (int i = tid; i < NT3; i += T) { s_a3[i] = __ldg(tab.a3 + i); s_b3[i] = __ldg(tab.b3 + i); }
+
+    int64_t off, len;          // samples [off, off+len) of src, zero beyond
+    float centre;
+    const int64_t row = row_first + blockIdx.x;
+    if (MODE == 0) {
+        off = row * B;
+        len = src_n - off; if (len > 2 * B) len = 2 * B; if (len < 0) len = 0;
+        centre = Acc<S>::centre(pfx[src_n].x, (double)src_n);
+    } else {
+        if (tid == 0) {        // largest q with partBase <= row
+            int lo = q_begin, hi = q_end - 1;
+            while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (desc[mid].partBase <= row) lo = mid; else hi = mid - 1; }
+            s_q = lo;
+        }
+        __syncthreads();
+        const QueryDesc d = desc[s_q];
+        const int64_t seg0 = (row - d.partBase) * B;
+        off = d.toff + seg0;
+        len = d.tlen - seg0; if (len > B) len = B;
+        centre = Acc<S>::centre(pfx[d.toff + d.tlen].x - pfx[d.toff].x, (double)d.tlen);
+    }
+    const S* x = src + off;
+#pragma unroll 4
+    for (int n = tid; n < B; n += T) {
+        const int64_t i0 = 2 * (int64_t)n;
+        const float a = i0 < len ? (float)x[i0] - centre : 0.f;
+        const float b = i0 + 1 < len ? (float)x[i0 + 1] - centre : 0.f;
+        buf[pad(n)] = make_float2(a, -b);            // conj(z[n])
+    }
+    __syncthreads();
+    ifft_smem<LOGN, false>(buf, s_t2, s_a3, s_b3);   // buf = conj(Z)
+    float2* o = out + (int64_t)blockIdx.x * NB;
+    for (int k = tid; k <= B / 2; k += T) {
+        const float2 zk = buf[pad(k)];
+        const float2 zp = buf[pad(k == 0 ? 0 : B - k)];
+        const float2 A = make_float2(zk.x, -zk.y), P = make_float2(zp.x, zp.y);     // Z[k], conj(Z[B-k])
+        const float2 xe = make_float2(0.5f * (A.x + P.x), 0.5f * (A.y + P.y));
+        const float2 dd = make_float2(A.x - P.x, A.y - P.y);
+        const float2 xo = make_float2(0.5f * dd.y, -0.5f * dd.x);                   // -i*dd/2
+        const float2 w = __ldg(tab.w + k);
+        const float2 tv = cmul(make_float2(w.x, -w.y), xo);
+        o[k] = make_float2(xe.x + tv.x, xe.y + tv.y);
+        if (k != B / 2) o[B - k] = make_float2(xe.x - tv.x, -(xe.y - tv.y));
+    }
+}
+
+template <int LOGN> size_t forward_smem_bytes() {
+    typedef Cfg<LOGN> C;
+    return ((size_t)(C::N + (C::N >> 5) + 1) + C::R2 * 32 + 2 * C::R3 * 32) * sizeof(float2) + 64;
+}
+
 // ---------------------------------------------------------------- host side
 template <int LOGN> size_t fused_smem_bytes() {
     typedef Cfg<LOGN> C;
@@ -456,6 +548,38 @@ int launch_typed(const sb_stream* image, const sb_stream* tmpl, const float2* d_
     return SB_OK;
 }
 
+template <int LOGN, typename S, int MODE>
+int launch_forward_typed(const sb_stream* src, const QueryDesc* d_desc, int q_begin, int q_end,
+                         int64_t row_first, int64_t rows, float2* out) {
+    Ctx& c = ctx();
+    FusedTables tab;
+    SB_TRY(ensure_tables<LOGN>(&tab));
+    static bool attr_set = false;
+    const size_t smem = forward_smem_bytes<LOGN>();
+    if (!attr_set) {
+        SB_CUDA(cudaFuncSetAttribute(k_forward_rows<LOGN, S, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    k_forward_rows<LOGN, S, MODE><<<(unsigned)rows, Cfg<LOGN>::T, smem, c.stream>>>(
+        static_cast<const S*>(src->d_raw), src->n, src->d_pfx, d_desc, q_begin, q_end, row_first, tab, out);
+    SB_CUDA(cudaGetLastError());
+    return SB_OK;
+}
+
+template <int MODE>
+int launch_forward(const sb_stream* src, const QueryDesc* d_desc, int q_begin, int q_end,
+                   int64_t row_first, int64_t rows, float2* out) {
+    const int B = ctx().B;
+    const bool u8 = src->dtype == SB_U8;
+    if (B == 16384)
+        return u8 ? launch_forward_typed<14, uint8_t, MODE>(src, d_desc, q_begin, q_end, row_first, rows, out)
+                  : launch_forward_typed<14, float, MODE>(src, d_desc, q_begin, q_end, row_first, rows, out);
+    if (B == 8192)
+        return u8 ? launch_forward_typed<13, uint8_t, MODE>(src, d_desc, q_begin, q_end, row_first, rows, out)
+                  : launch_forward_typed<13, float, MODE>(src, d_desc, q_begin, q_end, row_first, rows, out);
+    SB_FAIL(SB_EINVAL, "fused engine supports lag blocks of 8192 or 16384 samples, not %d", B);
+}
+
 }  // namespace
 
 namespace sb {
@@ -474,6 +598,16 @@ int launch_match_fused(const sb_stream* image, const sb_stream* tmpl, const floa
         return u8 ? launch_typed<13, uint8_t>(image, tmpl, d_parts, part_first, d_desc, q_begin, q_end, item_first, n_items, d_keys, d_curve)
                   : launch_typed<13, float>(image, tmpl, d_parts, part_first, d_desc, q_begin, q_end, item_first, n_items, d_keys, d_curve);
     SB_FAIL(SB_EINVAL, "fused engine supports lag blocks of 8192 or 16384 samples, not %d", B);
+}
+
+// Block spectra of a stream: rows [k_first, k_first + rows) into out (row stride B+1)
+int launch_block_spectra(const sb_stream* s, int64_t k_first, int64_t rows, float2* out) {
+    return launch_forward<0>(s, nullptr, 0, 0, k_first, rows, out);
+}
+// Partition spectra of the templates of queries [q_begin, q_end): global part rows [part_first, +rows)
+int launch_part_spectra(const sb_stream* tmpl, const QueryDesc* d_desc, int q_begin, int q_end,
+                        int64_t part_first, int64_t rows, float2* out) {
+    return launch_forward<1>(tmpl, d_desc, q_begin, q_end, part_first, rows, out);
 }
 
 void fused_release_tables() {

@@ -101,6 +101,9 @@ bool fused_supports(int B);
 int launch_match_fused(const sb_stream* image, const sb_stream* tmpl, const float2* d_parts, int64_t part_first,
                        const QueryDesc* d_desc, int q_begin, int q_end, int64_t item_first, int64_t n_items,
                        unsigned long long* d_keys, float* d_curve);
+int launch_block_spectra(const sb_stream* s, int64_t k_first, int64_t rows, float2* out);
+int launch_part_spectra(const sb_stream* tmpl, const QueryDesc* d_desc, int q_begin, int q_end,
+                        int64_t part_first, int64_t rows, float2* out);
 void fused_release_tables();
 
 int get_plan(int type, int64_t batch, cufftHandle* out);
@@ -117,5 +120,6 @@ struct sb_stream {
     // block spectra for lag-block size specB: [nblk][specB+1] complex64
     float2* d_spec = nullptr;
     int specB = 0;
+    int specEngine = -1;          // engine that built d_spec (rebuilt when the engine changes)
     int64_t nblk = 0;
 };

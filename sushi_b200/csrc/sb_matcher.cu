@@ -359,6 +359,10 @@ int run_batch(const sb_stream* image_c, const sb_stream* tmpl, int64_t count,
         const int64_t part_first = c.h_desc[qb].partBase;
         // 1. template partitions -> spectra (in place)
         const int64_t sub = 4096;
+        if (use_fused) {                             // hand-written gather + forward FFT, one launch
+            ProfScope ps("part_spectra");
+            SB_TRY(launch_part_spectra(tmpl, c.d_desc, (int)qb, (int)qe, part_first, np, c.d_parts));
+        } else
         for (int64_t p0 = 0; p0 < np; p0 += sub) {
             const int64_t rows = std::min<int64_t>(sub, np - p0);
             float* dst = reinterpret_cast<float*>(c.d_parts + p0 * nb);

@@ -196,11 +196,19 @@ int stream_finish_public(sb_stream* s) { return stream_finish(s); }
 // Build (or fetch) the block spectra of `s` for the current block size.
 int ensure_spectra(sb_stream* s) {
     Ctx& c = ctx();
-    if (s->d_spec && s->specB == c.B) return SB_OK;
+    if (s->d_spec && s->specB == c.B && s->specEngine == c.engine) return SB_OK;
     if (s->d_spec) { pool_free(s->d_spec); s->d_spec = nullptr; }
     const int B = c.B;
     const int64_t nblk = (s->n + B - 1) / B;
     SB_TRY(pool_alloc((void**)&s->d_spec, sizeof(float2) * (size_t)nblk * (B + 1)));
+    if (c.engine == 1 && fused_supports(B)) {        // hand-written gather + forward FFT, one launch
+        {
+            ProfScope ps("block_spectra");
+            SB_TRY(launch_block_spectra(s, 0, nblk, s->d_spec));
+        }
+        s->specB = B; s->nblk = nblk; s->specEngine = c.engine;
+        return SB_OK;
+    }
     const int chunks = (2 * B + 2047) / 2048;
     const int64_t sub = 1024;                        // rows per cuFFT call
     for (int64_t k = 0; k < nblk; k += sub) {
@@ -223,7 +231,7 @@ int ensure_spectra(sb_stream* s) {
         }
     }
     SB_CUDA(cudaGetLastError());
-    s->specB = B; s->nblk = nblk;
+    s->specB = B; s->nblk = nblk; s->specEngine = c.engine;
     return SB_OK;
 }
 
