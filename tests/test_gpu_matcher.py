@@ -368,3 +368,23 @@ def test_float32_stream_with_arbitrary_range(gpu_lib):
     got = s.match_curve(s, 20000, 5000, 2000, 30000)
     assert np.abs(got - want).max() <= 1e-5
     assert int(got.argmin()) == 18000 and got.min() <= 1e-6
+
+
+def test_values_do_not_depend_on_the_query_range(gpu_lib, pair):
+    """The property the curve cache, the sharding and the batching rest on: a lag's value depends only
+    on (template, absolute position).  Any sub-range query returns exactly min / first argmin of the
+    corresponding slice of one wide curve -- bit for bit, for ranges cut at arbitrary offsets."""
+    rs, rd, src, dst = pair['uint8']
+    toff, n = src._get_sample_for_time(9.0), 20000
+    lo, count = 30000, 200000
+    wide = dst.match_curve(src, toff, n, lo, count)
+    rng = np.random.default_rng(8)
+    a = rng.integers(0, count - 1, 40)
+    b = np.minimum(a + rng.integers(1, 60000, 40), count)
+    d, i = dst.find_planned(src, np.full(40, toff), np.full(40, n), lo + a, b - a)
+    for q in range(40):
+        part = wide[a[q]:b[q]]
+        assert d[q] == part.min() and i[q] == int(part.argmin()), q
+    # whole curves of sub-ranges are slices of the wide curve
+    curves = dst.match_curves(src, [toff, toff], [n, n], [lo + 5, lo + 77777], [1000, 40001])
+    assert np.array_equal(curves[0], wide[5:1005]) and np.array_equal(curves[1], wide[77777:77777 + 40001])
