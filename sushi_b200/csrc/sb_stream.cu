@@ -77,14 +77,18 @@ k_scan_tile_totals(double* __restrict__ tsum, double* __restrict__ tsq, int64_t 
     }
 }
 
-// Phase C: in-tile inclusive scan + tile offset -> psum[i+1], psq[i+1].
-// Thread t owns SCAN_ITEMS consecutive samples (vector load for u8).
+// Phase C: in-tile inclusive scan + tile offset -> pfx[i+1] = (sum, sum of squares).
+// Thread t scans SCAN_ITEMS consecutive samples; the results go through shared memory so that the
+// 16-byte stores to HBM are coalesced (a blocked arrangement would scatter them 256 bytes apart).
 template <typename T>
 __global__ void __launch_bounds__(SCAN_THREADS)
 k_tile_scan(const T* __restrict__ x, int64_t n, const double* __restrict__ osum, const double* __restrict__ osq,
             double2* __restrict__ pfx) {
     __shared__ double s_a[SCAN_THREADS / 32], s_b[SCAN_THREADS / 32];
-    const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+    extern __shared__ __align__(16) unsigned char scan_smem[];
+    double2* s_out = reinterpret_cast<double2*>(scan_smem);             // [SCAN_TILE + SCAN_TILE/16] padded
+    const int64_t tile0 = (int64_t)blockIdx.x * SCAN_TILE;
+    const int64_t base = tile0 + (int64_t)threadIdx.x * SCAN_ITEMS;
     double va[SCAN_ITEMS], vb[SCAN_ITEMS];
     double a = 0.0, b = 0.0;
 #pragma unroll
@@ -109,8 +113,14 @@ k_tile_scan(const T* __restrict__ x, int64_t n, const double* __restrict__ osum,
     const double offb = osq[blockIdx.x] + wb + (ib - b);
 #pragma unroll
     for (int i = 0; i < SCAN_ITEMS; ++i) {
-        int64_t j = base + i;
-        if (j < n) pfx[j + 1] = make_double2(offa + va[i], offb + vb[i]);
+        const int e = threadIdx.x * SCAN_ITEMS + i;
+        s_out[e + (e >> 4)] = make_double2(offa + va[i], offb + vb[i]);   // +1 slot per 16: conflict-free
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int e = threadIdx.x; e < SCAN_TILE; e += SCAN_THREADS) {
+        const int64_t j = tile0 + e;
+        if (j < n) pfx[j + 1] = s_out[e + (e >> 4)];
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) pfx[0] = make_double2(0.0, 0.0);
 }
@@ -159,7 +169,13 @@ int build_prefix(sb_stream* s) {
     }
     {
         ProfScope ps("scan_tiles");
-        k_tile_scan<T><<<(unsigned)ntiles, SCAN_THREADS, 0, c.stream>>>(x, n, tsum, tsq, s->d_pfx);
+        const size_t smem = sizeof(double2) * (SCAN_TILE + SCAN_TILE / 16);
+        static bool attr_set = false;
+        if (!attr_set) {
+            SB_CUDA(cudaFuncSetAttribute(k_tile_scan<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_set = true;
+        }
+        k_tile_scan<T><<<(unsigned)ntiles, SCAN_THREADS, smem, c.stream>>>(x, n, tsum, tsq, s->d_pfx);
     }
     SB_CUDA(cudaGetLastError());
     pool_free(d_t);            // reused only by later work on the same stream
