@@ -143,7 +143,8 @@ k_match_fused(const float2* __restrict__ That, int64_t part_first,
     double2* s_base = reinterpret_cast<double2*>(stage);                // [ROUNDS][NW][2] exact running sums
     unsigned char* s_lo = reinterpret_cast<unsigned char*>(s_base + ROUNDS * NW * 2);   // image[j_blk .. +B+16)
     unsigned char* s_hi = s_lo + B + 16;                                // image[(j_blk+n)&~15 .. +B+48)
-    unsigned long long* s_best = reinterpret_cast<unsigned long long*>(s_hi + B + 48);  // [NW]
+    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_hi + B + 48);   // mbarrier of the TMA copies
+    unsigned long long* s_best = s_bar + 1;                             // [NW]
     float* s_min = reinterpret_cast<float*>(s_best + NW);               // [NW]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -156,18 +157,23 @@ k_match_fused(const float2* __restrict__ That, int64_t part_first,
     const int64_t k = d.k0 + (item - d.itemBase);
 
     // ---------------- 0. stage what the epilogue needs (uint8 streams) ----------------------
-    // The two byte windows the sliding sums read (image[j] and image[j+n] over this lag block)
-    // and one exact (sum, sum of squares) pair per warp-round from the fp64 running sums go to
-    // shared memory now, asynchronously; their latency hides behind the MAC and the FFT.
+    // The two byte windows the sliding sums read (image[j] and image[j+n] over this lag block) go to
+    // shared memory by TMA bulk copies, one exact (sum, sum of squares) pair per warp-round from the
+    // fp64 running sums by cp.async -- all issued now; their latency hides behind the MAC and the FFT.
     if (sizeof(S) == 1) {
         const unsigned char* img8 = reinterpret_cast<const unsigned char*>(img);
         const int64_t j_blk0 = k * B, hi0 = (j_blk0 + d.tlen) & ~(int64_t)15;
         const int64_t limit = (img_n + 16) & ~(int64_t)15;               // allocation has 16 bytes of slack
-        for (int ch = tid; ch < (B + 16) / 16; ch += T)
-            if (j_blk0 + 16 * (int64_t)ch + 16 <= limit) cp_async16(s_lo + 16 * ch, img8 + j_blk0 + 16 * (int64_t)ch);
-        for (int ch = tid; ch < (B + 48) / 16; ch += T)
-            if (hi0 + 16 * (int64_t)ch + 16 <= limit) cp_async16(s_hi + 16 * ch, img8 + hi0 + 16 * (int64_t)ch);
-        if (tid < ROUNDS * NW * 2) {
+        if (tid == 0) {
+            // the two windows: one TMA bulk copy each (1-D cp.async.bulk), completion on an mbarrier
+            int64_t lo_bytes = limit - j_blk0; if (lo_bytes > B + 16) lo_bytes = B + 16; if (lo_bytes < 0) lo_bytes = 0;
+            int64_t hi_bytes = limit - hi0;    if (hi_bytes > B + 48) hi_bytes = B + 48; if (hi_bytes < 0) hi_bytes = 0;
+            mbar_init(s_bar, 1);
+            mbar_expect_tx(s_bar, (unsigned)(lo_bytes + hi_bytes));
+            if (lo_bytes) tma_load_1d(s_lo, img8 + j_blk0, (unsigned)lo_bytes, s_bar);
+            if (hi_bytes) tma_load_1d(s_hi, img8 + hi0, (unsigned)hi_bytes, s_bar);
+        }
+        if (tid < ROUNDS * NW * 2) {                                      // 16-byte pieces: plain cp.async
             const int c = tid / (NW * 2), w = (tid >> 1) % NW, which = tid & 1;
             const int64_t jw = j_blk0 + c * LAGS_PER_ROUND + w * 256;    // first lag of warp w in round c
             if (jw < d.lag0 + d.nlags) cp_async16(s_base + tid, ipfx + jw + (which ? d.tlen : 0));
@@ -251,6 +257,7 @@ k_match_fused(const float2* __restrict__ That, int64_t part_first,
 
     float vf[ROUNDS][8];
     float tmin = 2.0f;
+    if (sizeof(S) == 1) mbar_wait(s_bar, 0);                          // TMA copies of step 0 (long done)
     if (sizeof(S) == 1) {
         // uint8: everything comes from shared memory.  Per round each warp covers 256 consecutive lags;
         // lane l owns the run of 8 lags starting at jw + 8l.  Window sums at the head of a run = exact
@@ -466,7 +473,7 @@ template <int LOGN> size_t fused_smem_bytes() {
     const size_t nw = C::T / 32;
     const size_t rounds = C::N / (C::T * 8);
     return (padded + C::R2 * 32 + 2 * C::R3 * 32) * sizeof(float2) + nw * sizeof(unsigned long long)
-         + 16 + rounds * nw * 2 * sizeof(double2) + (C::N + 16) + (C::N + 48) + nw * sizeof(float) + 64;
+         + 16 + rounds * nw * 2 * sizeof(double2) + (C::N + 16) + (C::N + 48) + 8 + nw * sizeof(float) + 64;
 }
 
 struct TableSet { float2* dev = nullptr; FusedTables tab; };
