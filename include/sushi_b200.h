@@ -75,6 +75,10 @@ int sb_get_block_size(void);
  * cuFFT-planned pipeline (any block size; kept as the cross-check and for odd block sizes). */
 int sb_set_engine(int engine);
 int sb_get_engine(void);
+/* Overlap-save geometry of the fused engine: 1 = hop B (half of each inverse FFT is valid lags),
+ * 2 = hop B/2 (three quarters valid, twice as many template partitions), 0 (default) = chosen per
+ * batch from the template lengths.  Results do not depend on it. */
+int sb_set_hop_mode(int mode);
 /* Lag blocks processed per multiply / inverse-FFT / normalise launch (>= 1). */
 int sb_set_chunk_items(int items);
 /* Template partition spectra kept resident per pass over a batch (>= 1); batches needing more are

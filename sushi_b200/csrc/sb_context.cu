@@ -217,6 +217,11 @@ int sb_set_engine(int engine) {
     return SB_OK;
 }
 int sb_get_engine(void) { return ctx().engine; }
+int sb_set_hop_mode(int mode) {
+    if (mode < 0 || mode > 2) SB_FAIL(SB_EINVAL, "sb_set_hop_mode: %d is not 0 (auto), 1 (hop B) or 2 (hop B/2)", mode);
+    ctx().hop_mode = mode;
+    return SB_OK;
+}
 int sb_set_max_parts(int64_t parts) {
     if (parts < 1) SB_FAIL(SB_EINVAL, "sb_set_max_parts: %lld < 1", (long long)parts);
     ctx().max_parts = parts;

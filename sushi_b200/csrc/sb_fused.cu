@@ -42,7 +42,7 @@ struct FusedTables {
 // k = j mod Ns, and writes out[(j-k)*R + k + r*Ns]; every value sits in a register between the two
 // barriers of a pass, so the transform is in place and the output is in natural order.
 // Must be entered after a barrier that made buf visible; ends with a barrier.
-template <int LOGN, bool HALF>
+template <int LOGN, int KEEP3, bool FUSED>
 __device__ __forceinline__ void ifft_smem(float2* __restrict__ buf, const float2* __restrict__ s_t2,
                                           const float2* __restrict__ s_a3, const float2* __restrict__ s_b3) {
     typedef Cfg<LOGN> C;
@@ -90,8 +90,8 @@ __device__ __forceinline__ void ifft_smem(float2* __restrict__ buf, const float2
         }
         __syncthreads();
     }
-    {   // pass 3: Ns = R1*R2, k = j (j < Ns).  HALF: only the first half of the outputs is needed
-        // (z[0 .. N/2) carries the B valid lags of the 2B-point real sequence)
+    {   // pass 3: Ns = R1*R2, k = j (j < Ns).  Only outputs r < KEEP3 of each butterfly are needed
+        // (the fused kernel reads z[0 .. LB/2): the valid lags of the 2B-point real sequence)
         constexpr int R = C::R3, Ns = C::R1 * C::R2, PER = (N / R) / T;
         static_assert(N / R == Ns, "pass 3 is the last pass");
         float2 v[PER][R];
@@ -107,17 +107,17 @@ __device__ __forceinline__ void ifft_smem(float2* __restrict__ buf, const float2
 #pragma unroll
             for (int r = 1; r < R; ++r)
                 v[b][r] = cmul(v[b][r], cmul(s_a3[r * 32 + lane], s_b3[r * 32 + kh]));
-            dft_dif<R, HALF>(v[b]);
+            dft_dif<R, KEEP3>(v[b]);
 #pragma unroll
-            for (int r = 0; r < (HALF ? R / 2 : R); ++r) buf[pad(tid) + (b * T + r * Ns) / 32 * 33] = v[b][brev<R>(r)];
+            for (int r = 0; r < KEEP3; ++r) buf[pad(tid) + (b * T + r * Ns) / 32 * 33] = v[b][brev<R>(r)];
         }
-        if (HALF) cp_async_commit_wait_all();       // the fused kernel's staged copies landed long ago; the barrier publishes them
+        if (FUSED) cp_async_commit_wait_all();      // the fused kernel's staged copies landed long ago; the barrier publishes them
         __syncthreads();
     }
 }
 
 // ---------------------------------------------------------------- the kernel
-template <int LOGN, typename S>
+template <int LOGN, typename S, int HD>
 __global__ void __launch_bounds__(Cfg<LOGN>::T, Cfg<LOGN>::MINB)
 k_match_fused(const float2* __restrict__ That, int64_t part_first,
               const float2* __restrict__ Xhat, int64_t nblk,
@@ -128,8 +128,13 @@ k_match_fused(const float2* __restrict__ That, int64_t part_first,
     typedef Cfg<LOGN> C;
     constexpr int N = C::N, T = C::T, B = C::N;
     constexpr int NB = B + 1;                       // bins per spectrum row
+    // geometry: real FFT of 2B points; hop = partition length H = B/HD; an item yields the
+    // LB = 2B - H lags that the circular correlation gets right (B for HD = 1, 3B/2 for HD = 2)
+    constexpr int H = B / HD, LB = 2 * B - H, RATIO = LB / H;
     constexpr int LAGS_PER_ROUND = T * 8;           // 8 consecutive lags per thread per round
-    constexpr int ROUNDS = B / LAGS_PER_ROUND;      // 4
+    constexpr int ROUNDS = LB / LAGS_PER_ROUND;     // 4 or 6
+    constexpr int KEEP3 = C::R3 * LB / (2 * B);     // outputs of a last-pass butterfly that carry valid lags
+    static_assert(LB % LAGS_PER_ROUND == 0 && ROUNDS * 8 <= 64, "epilogue tiling");
     constexpr int NW = T / 32;
     constexpr int NT2 = C::R2 * 32, NT3 = C::R3 * 32;
 
@@ -142,8 +147,8 @@ k_match_fused(const float2* __restrict__ That, int64_t part_first,
     unsigned char* stage = smem_raw + (((size_t)(pad(N) + 1 + NT2 + 2 * NT3) * sizeof(float2) + 15) & ~(size_t)15);
     double2* s_base = reinterpret_cast<double2*>(stage);                // [ROUNDS][NW][2] exact running sums
     unsigned char* s_lo = reinterpret_cast<unsigned char*>(s_base + ROUNDS * NW * 2);   // image[j_blk .. +B+16)
-    unsigned char* s_hi = s_lo + B + 16;                                // image[(j_blk+n)&~15 .. +B+48)
-    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_hi + B + 48);   // mbarrier of the TMA copies
+    unsigned char* s_hi = s_lo + LB + 16;                               // image[(j_blk+n)&~15 .. +LB+48)
+    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_hi + LB + 48);  // mbarrier of the TMA copies
     unsigned long long* s_best = s_bar + 1;                             // [NW]
     float* s_min = reinterpret_cast<float*>(s_best + NW);               // [NW]
 
@@ -162,12 +167,12 @@ k_match_fused(const float2* __restrict__ That, int64_t part_first,
     // fp64 running sums by cp.async -- all issued now; their latency hides behind the MAC and the FFT.
     if (sizeof(S) == 1) {
         const unsigned char* img8 = reinterpret_cast<const unsigned char*>(img);
-        const int64_t j_blk0 = k * B, hi0 = (j_blk0 + d.tlen) & ~(int64_t)15;
+        const int64_t j_blk0 = k * LB, hi0 = (j_blk0 + d.tlen) & ~(int64_t)15;
         const int64_t limit = (img_n + 16) & ~(int64_t)15;               // allocation has 16 bytes of slack
         if (tid == 0) {
             // the two windows: one TMA bulk copy each (1-D cp.async.bulk), completion on an mbarrier
-            int64_t lo_bytes = limit - j_blk0; if (lo_bytes > B + 16) lo_bytes = B + 16; if (lo_bytes < 0) lo_bytes = 0;
-            int64_t hi_bytes = limit - hi0;    if (hi_bytes > B + 48) hi_bytes = B + 48; if (hi_bytes < 0) hi_bytes = 0;
+            int64_t lo_bytes = limit - j_blk0; if (lo_bytes > LB + 16) lo_bytes = LB + 16; if (lo_bytes < 0) lo_bytes = 0;
+            int64_t hi_bytes = limit - hi0;    if (hi_bytes > LB + 48) hi_bytes = LB + 48; if (hi_bytes < 0) hi_bytes = 0;
             mbar_init(s_bar, 1);
             mbar_expect_tx(s_bar, (unsigned)(lo_bytes + hi_bytes));
             if (lo_bytes) tma_load_1d(s_lo, img8 + j_blk0, (unsigned)lo_bytes, s_bar);
@@ -183,9 +188,10 @@ k_match_fused(const float2* __restrict__ That, int64_t part_first,
     // ---------------- 1+2. spectral multiply-accumulate and Hermitian packing ---------------
     {
         int P = d.P;
-        if (k + P > nblk) P = (int)(nblk - k);      // blocks past the end of the stream are zero
+        const int64_t row0 = k * RATIO;             // block-spectrum row of partition 0 (rows are H apart)
+        if (row0 + P > nblk) P = (int)(nblk - row0);    // rows past the end of the stream are zero
         const float2* tp = That + (d.partBase - part_first) * (int64_t)NB;
-        const float2* xp = Xhat + k * (int64_t)NB;
+        const float2* xp = Xhat + row0 * (int64_t)NB;
         constexpr int U = 8;                        // bin pairs in flight per thread
         static_assert((B / 2) % (U * T) == 0, "pair loop must tile B/2");
         // pairs (m, B-m), m = 1 .. B/2-1, plus m = 0 whose partner is the Nyquist bin B
@@ -235,7 +241,7 @@ k_match_fused(const float2* __restrict__ That, int64_t part_first,
     __syncthreads();
 
     // ---------------- 3. inverse FFT of N complex points in shared memory -------------------
-    ifft_smem<LOGN, true>(buf, s_t2, s_a3, s_b3);
+    ifft_smem<LOGN, KEEP3, true>(buf, s_t2, s_a3, s_b3);
     // now buf[pad(i)] = (x[2i], x[2i+1]) for i < N/2: correlation at lags 2i, 2i+1 (times 2B)
 
     // ---------------- 4. window sums, fp32 screening, fp64 exact evaluation -----------------
@@ -244,7 +250,7 @@ k_match_fused(const float2* __restrict__ That, int64_t part_first,
     // the window slides on the raw samples: W[j+1] = W[j] + I[j+n]^k - I[j]^k.
     const int64_t n = d.tlen;
     const int64_t jlo = d.lag0, jhi = d.lag0 + d.nlags;
-    const int64_t j_blk = k * B;
+    const int64_t j_blk = k * LB;
     const double2 t_hi = tpfx[d.toff + n], t_lo = tpfx[d.toff];
     const double tsum = t_hi.x - t_lo.x, tsq = t_hi.y - t_lo.y;
     const double a = (double)Acc<S>::centre(ipfx[img_n].x, (double)img_n);
@@ -253,7 +259,7 @@ k_match_fused(const float2* __restrict__ That, int64_t part_first,
     const double scale = 1.0 / (double)(2 * B);
     const double k_const = a * tsum - n_ab;
     const float f_tsq = (float)tsq, f_b = (float)b, f_scale = (float)scale;
-    const bool interior = j_blk >= jlo && j_blk + B <= jhi;           // every lag of the item is valid
+    const bool interior = j_blk >= jlo && j_blk + LB <= jhi;          // every lag of the item is valid
 
     float vf[ROUNDS][8];
     float tmin = 2.0f;
@@ -355,16 +361,16 @@ k_match_fused(const float2* __restrict__ That, int64_t part_first,
     const float thr = curve_out ? 1.5f : bmin + kScreenMargin;       // debug curve: evaluate everything
 
     // lags that can still be the minimum (bit c*8+i), then ONE copy of the fp64 path
-    unsigned cand = 0;
+    unsigned long long cand = 0;
     if (my_min <= thr) {
 #pragma unroll
         for (int c = 0; c < ROUNDS; ++c)
 #pragma unroll
-            for (int i = 0; i < 8; ++i) cand |= (vf[c][i] <= thr) ? (1u << (c * 8 + i)) : 0u;
+            for (int i = 0; i < 8; ++i) cand |= (vf[c][i] <= thr) ? (1ull << (c * 8 + i)) : 0ull;
     }
     unsigned long long best = ~0ull;
     while (cand) {
-        const int bit = __ffs(cand) - 1;
+        const int bit = __ffsll((long long)cand) - 1;
         cand &= cand - 1;
         const int m = (bit >> 3) * LAGS_PER_ROUND + tid * 8 + (bit & 7);
         const int64_t j = j_blk + m;
@@ -398,13 +404,13 @@ k_match_fused(const float2* __restrict__ That, int64_t part_first,
 // Rows are either the lag blocks of a stream (MODE 0: samples [kB, kB+2B), centred on the stream
 // mean) or the partitions of the batch's templates (MODE 1: B samples + B zeros, centred on the
 // template's own mean) -- the gather, the centring and the FFT are one pass over the data.
-template <int LOGN, typename S, int MODE>
+template <int LOGN, typename S, int MODE, int HD>
 __global__ void __launch_bounds__(Cfg<LOGN>::T, Cfg<LOGN>::MINB)
 k_forward_rows(const S* __restrict__ src, int64_t src_n, const double2* __restrict__ pfx,
                const QueryDesc* __restrict__ desc, int q_begin, int q_end, int64_t row_first,
                FusedTables tab, float2* __restrict__ out) {
     typedef Cfg<LOGN> C;
-    constexpr int N = C::N, T = C::T, B = C::N, NB = B + 1;
+    constexpr int N = C::N, T = C::T, B = C::N, NB = B + 1, H = B / HD;   // rows are H samples apart
     constexpr int NT2 = C::R2 * 32, NT3 = C::R3 * 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* buf = reinterpret_cast<float2*>(smem_raw);
@@ -420,7 +426,7 @@ k_forward_rows(const S* __restrict__ src, int64_t src_n, const double2* __restri
     float centre;
     const int64_t row = row_first + blockIdx.x;
     if (MODE == 0) {
-        off = row * B;
+        off = row * H;
         len = src_n - off; if (len > 2 * B) len = 2 * B; if (len < 0) len = 0;
         centre = Acc<S>::centre(pfx[src_n].x, (double)src_n);
     } else {
@@ -431,9 +437,9 @@ k_forward_rows(const S* __restrict__ src, int64_t src_n, const double2* __restri
         }
         __syncthreads();
         const QueryDesc d = desc[s_q];
-        const int64_t seg0 = (row - d.partBase) * B;
+        const int64_t seg0 = (row - d.partBase) * H;
         off = d.toff + seg0;
-        len = d.tlen - seg0; if (len > B) len = B;
+        len = d.tlen - seg0; if (len > H) len = H;
         centre = Acc<S>::centre(pfx[d.toff + d.tlen].x - pfx[d.toff].x, (double)d.tlen);
     }
     const S* x = src + off;
@@ -445,7 +451,7 @@ k_forward_rows(const S* __restrict__ src, int64_t src_n, const double2* __restri
         buf[pad(n)] = make_float2(a, -b);            // conj(z[n])
     }
     __syncthreads();
-    ifft_smem<LOGN, false>(buf, s_t2, s_a3, s_b3);   // buf = conj(Z)
+    ifft_smem<LOGN, C::R3, false>(buf, s_t2, s_a3, s_b3);   // buf = conj(Z)
     float2* o = out + (int64_t)blockIdx.x * NB;
     for (int k = tid; k <= B / 2; k += T) {
         const float2 zk = buf[pad(k)];
@@ -467,13 +473,14 @@ template <int LOGN> size_t forward_smem_bytes() {
 }
 
 // ---------------------------------------------------------------- host side
-template <int LOGN> size_t fused_smem_bytes() {
+template <int LOGN, int HD> size_t fused_smem_bytes() {
     typedef Cfg<LOGN> C;
     const size_t padded = (size_t)(C::N + (C::N >> 5) + 1);
     const size_t nw = C::T / 32;
-    const size_t rounds = C::N / (C::T * 8);
+    const size_t LB = 2 * C::N - C::N / HD;
+    const size_t rounds = LB / (C::T * 8);
     return (padded + C::R2 * 32 + 2 * C::R3 * 32) * sizeof(float2) + nw * sizeof(unsigned long long)
-         + 16 + rounds * nw * 2 * sizeof(double2) + (C::N + 16) + (C::N + 48) + 8 + nw * sizeof(float) + 64;
+         + 16 + rounds * nw * 2 * sizeof(double2) + (LB + 16) + (LB + 48) + 8 + nw * sizeof(float) + 64;
 }
 
 struct TableSet { float2* dev = nullptr; FusedTables tab; };
@@ -519,7 +526,7 @@ __global__ void k_fill_item_query(const QueryDesc* __restrict__ desc, int q_begi
 int* g_item_query = nullptr;
 int64_t g_item_query_cap = 0;
 
-template <int LOGN, typename S>
+template <int LOGN, typename S, int HD>
 int launch_typed(const sb_stream* image, const sb_stream* tmpl, const float2* d_parts, int64_t part_first,
                  const QueryDesc* d_desc, int q_begin, int q_end, int64_t item_first, int64_t n_items,
                  unsigned long long* d_keys, float* d_curve) {
@@ -530,9 +537,9 @@ int launch_typed(const sb_stream* image, const sb_stream* tmpl, const float2* d_
     // SB_FUSED_EXTRA_SMEM (bytes): occupancy experiments only -- inflates the dynamic shared memory so
     // fewer CTAs fit on an SM
     static const size_t extra = getenv("SB_FUSED_EXTRA_SMEM") ? (size_t)atol(getenv("SB_FUSED_EXTRA_SMEM")) : 0;
-    const size_t smem = fused_smem_bytes<LOGN>() + extra;
+    const size_t smem = fused_smem_bytes<LOGN, HD>() + extra;
     if (!attr_set) {
-        SB_CUDA(cudaFuncSetAttribute(k_match_fused<LOGN, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SB_CUDA(cudaFuncSetAttribute(k_match_fused<LOGN, S, HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
     if (g_item_query_cap < n_items) {
@@ -546,7 +553,7 @@ int launch_typed(const sb_stream* image, const sb_stream* tmpl, const float2* d_
     const int64_t max_grid = 1 << 30;
     for (int64_t i0 = 0; i0 < n_items; i0 += max_grid) {
         const int64_t ni = std::min<int64_t>(max_grid, n_items - i0);
-        k_match_fused<LOGN, S><<<(unsigned)ni, Cfg<LOGN>::T, smem, c.stream>>>(
+        k_match_fused<LOGN, S, HD><<<(unsigned)ni, Cfg<LOGN>::T, smem, c.stream>>>(
             d_parts, part_first, image->d_spec, image->nblk, static_cast<const S*>(image->d_raw), image->n,
             image->d_pfx, tmpl->d_pfx, d_desc, g_item_query + i0, item_first + i0,
             tab, d_keys, d_curve);
@@ -555,7 +562,7 @@ int launch_typed(const sb_stream* image, const sb_stream* tmpl, const float2* d_
     return SB_OK;
 }
 
-template <int LOGN, typename S, int MODE>
+template <int LOGN, typename S, int MODE, int HD>
 int launch_forward_typed(const sb_stream* src, const QueryDesc* d_desc, int q_begin, int q_end,
                          int64_t row_first, int64_t rows, float2* out) {
     Ctx& c = ctx();
@@ -564,27 +571,25 @@ int launch_forward_typed(const sb_stream* src, const QueryDesc* d_desc, int q_be
     static bool attr_set = false;
     const size_t smem = forward_smem_bytes<LOGN>();
     if (!attr_set) {
-        SB_CUDA(cudaFuncSetAttribute(k_forward_rows<LOGN, S, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SB_CUDA(cudaFuncSetAttribute(k_forward_rows<LOGN, S, MODE, HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
-    k_forward_rows<LOGN, S, MODE><<<(unsigned)rows, Cfg<LOGN>::T, smem, c.stream>>>(
+    k_forward_rows<LOGN, S, MODE, HD><<<(unsigned)rows, Cfg<LOGN>::T, smem, c.stream>>>(
         static_cast<const S*>(src->d_raw), src->n, src->d_pfx, d_desc, q_begin, q_end, row_first, tab, out);
     SB_CUDA(cudaGetLastError());
     return SB_OK;
 }
 
 template <int MODE>
-int launch_forward(const sb_stream* src, const QueryDesc* d_desc, int q_begin, int q_end,
+int launch_forward(const sb_stream* src, int hd, const QueryDesc* d_desc, int q_begin, int q_end,
                    int64_t row_first, int64_t rows, float2* out) {
     const int B = ctx().B;
     const bool u8 = src->dtype == SB_U8;
-    if (B == 16384)
-        return u8 ? launch_forward_typed<14, uint8_t, MODE>(src, d_desc, q_begin, q_end, row_first, rows, out)
-                  : launch_forward_typed<14, float, MODE>(src, d_desc, q_begin, q_end, row_first, rows, out);
-    if (B == 8192)
-        return u8 ? launch_forward_typed<13, uint8_t, MODE>(src, d_desc, q_begin, q_end, row_first, rows, out)
-                  : launch_forward_typed<13, float, MODE>(src, d_desc, q_begin, q_end, row_first, rows, out);
-    SB_FAIL(SB_EINVAL, "fused engine supports lag blocks of 8192 or 16384 samples, not %d", B);
+#define SB_FWD(LOGN, S, HD) launch_forward_typed<LOGN, S, MODE, HD>(src, d_desc, q_begin, q_end, row_first, rows, out)
+    if (B == 16384) return hd == 2 ? (u8 ? SB_FWD(14, uint8_t, 2) : SB_FWD(14, float, 2)) : (u8 ? SB_FWD(14, uint8_t, 1) : SB_FWD(14, float, 1));
+    if (B == 8192)  return hd == 2 ? (u8 ? SB_FWD(13, uint8_t, 2) : SB_FWD(13, float, 2)) : (u8 ? SB_FWD(13, uint8_t, 1) : SB_FWD(13, float, 1));
+#undef SB_FWD
+    SB_FAIL(SB_EINVAL, "fused engine supports FFT half-sizes of 8192 or 16384 samples, not %d", B);
 }
 
 }  // namespace
@@ -593,28 +598,26 @@ namespace sb {
 
 bool fused_supports(int B) { return B == 16384 || B == 8192; }
 
-int launch_match_fused(const sb_stream* image, const sb_stream* tmpl, const float2* d_parts, int64_t part_first,
+int launch_match_fused(const sb_stream* image, const sb_stream* tmpl, int hd, const float2* d_parts, int64_t part_first,
                        const QueryDesc* d_desc, int q_begin, int q_end, int64_t item_first, int64_t n_items,
                        unsigned long long* d_keys, float* d_curve) {
     const int B = ctx().B;
     const bool u8 = image->dtype == SB_U8;
-    if (B == 16384)
-        return u8 ? launch_typed<14, uint8_t>(image, tmpl, d_parts, part_first, d_desc, q_begin, q_end, item_first, n_items, d_keys, d_curve)
-                  : launch_typed<14, float>(image, tmpl, d_parts, part_first, d_desc, q_begin, q_end, item_first, n_items, d_keys, d_curve);
-    if (B == 8192)
-        return u8 ? launch_typed<13, uint8_t>(image, tmpl, d_parts, part_first, d_desc, q_begin, q_end, item_first, n_items, d_keys, d_curve)
-                  : launch_typed<13, float>(image, tmpl, d_parts, part_first, d_desc, q_begin, q_end, item_first, n_items, d_keys, d_curve);
-    SB_FAIL(SB_EINVAL, "fused engine supports lag blocks of 8192 or 16384 samples, not %d", B);
+#define SB_FUSED(LOGN, S, HD) launch_typed<LOGN, S, HD>(image, tmpl, d_parts, part_first, d_desc, q_begin, q_end, item_first, n_items, d_keys, d_curve)
+    if (B == 16384) return hd == 2 ? (u8 ? SB_FUSED(14, uint8_t, 2) : SB_FUSED(14, float, 2)) : (u8 ? SB_FUSED(14, uint8_t, 1) : SB_FUSED(14, float, 1));
+    if (B == 8192)  return hd == 2 ? (u8 ? SB_FUSED(13, uint8_t, 2) : SB_FUSED(13, float, 2)) : (u8 ? SB_FUSED(13, uint8_t, 1) : SB_FUSED(13, float, 1));
+#undef SB_FUSED
+    SB_FAIL(SB_EINVAL, "fused engine supports FFT half-sizes of 8192 or 16384 samples, not %d", B);
 }
 
 // Block spectra of a stream: rows [k_first, k_first + rows) into out (row stride B+1)
-int launch_block_spectra(const sb_stream* s, int64_t k_first, int64_t rows, float2* out) {
-    return launch_forward<0>(s, nullptr, 0, 0, k_first, rows, out);
+int launch_block_spectra(const sb_stream* s, int hd, int64_t k_first, int64_t rows, float2* out) {
+    return launch_forward<0>(s, hd, nullptr, 0, 0, k_first, rows, out);
 }
 // Partition spectra of the templates of queries [q_begin, q_end): global part rows [part_first, +rows)
-int launch_part_spectra(const sb_stream* tmpl, const QueryDesc* d_desc, int q_begin, int q_end,
+int launch_part_spectra(const sb_stream* tmpl, int hd, const QueryDesc* d_desc, int q_begin, int q_end,
                         int64_t part_first, int64_t rows, float2* out) {
-    return launch_forward<1>(tmpl, d_desc, q_begin, q_end, part_first, rows, out);
+    return launch_forward<1>(tmpl, hd, d_desc, q_begin, q_end, part_first, rows, out);
 }
 
 void fused_release_tables() {

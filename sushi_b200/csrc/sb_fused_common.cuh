@@ -36,10 +36,18 @@ __device__ __forceinline__ float2 rot32(float2 d, int q) {
 
 // In-register inverse DFT of R points (sign +, unnormalised), decimation in frequency: natural
 // order in, bit-reversed order out (the caller indexes the outputs through brev<R>).
-// With FIRST_HALF only the outputs X[0 .. R/2) are produced (they sit at the even positions of
-// the bit-reversed result), so the subtractions of the last stage are skipped.
-template <int R, bool FIRST_HALF = false>
+template <int R> __device__ __forceinline__ constexpr int brev(int r) {
+    int o = 0;
+    for (int b = 1; b < R; b <<= 1) { o = (o << 1) | (r & 1); r >>= 1; }
+    return o;
+}
+
+// With KEEP < R only the outputs X[0 .. KEEP) are produced (KEEP >= R/2): position g of the
+// bit-reversed result holds X[brev(g)], so in the last stage the pair (g, g+1) holds X[r] and
+// X[r + R/2], r = brev(g), and the subtraction is skipped when r + R/2 >= KEEP.
+template <int R, int KEEP = R>
 __device__ __forceinline__ void dft_dif(float2 (&v)[R]) {
+    static_assert(KEEP >= R / 2 && KEEP <= R, "KEEP out of range");
 #pragma unroll
     for (int h = R / 2; h >= 1; h >>= 1) {
 #pragma unroll
@@ -48,15 +56,10 @@ __device__ __forceinline__ void dft_dif(float2 (&v)[R]) {
             for (int a = 0; a < h; ++a) {
                 const float2 x = v[g + a], y = v[g + a + h];
                 v[g + a] = cadd(x, y);
-                if (!(FIRST_HALF && h == 1)) v[g + a + h] = rot32(csub(x, y), a * (16 / h));
+                if (!(h == 1 && brev<R>(g) + R / 2 >= KEEP)) v[g + a + h] = rot32(csub(x, y), a * (16 / h));
             }
         }
     }
-}
-template <int R> __device__ __forceinline__ constexpr int brev(int r) {
-    int o = 0;
-    for (int b = 1; b < R; b <<= 1) { o = (o << 1) | (r & 1); r >>= 1; }
-    return o;
 }
 
 // one padding slot per 32 complex values keeps the radix-32 scatter of pass 1 conflict free

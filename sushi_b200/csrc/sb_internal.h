@@ -41,8 +41,8 @@ struct QueryDesc {
     int64_t itemBase;  // first item of this query in the batch-wide item list
     int64_t partBase;  // first partition spectrum of this query
     int64_t curveOff;  // where this query's curve starts in the curve buffer (curve mode only)
-    int32_t P;         // ceil(n / B)
-    int32_t k0;        // lag0 / B
+    int32_t P;         // ceil(n / H), H = hop = partition length
+    int32_t k0;        // lag0 / LB, LB = lags per item
     int32_t nk;        // number of lag blocks touched
     int32_t pad_;
 };
@@ -55,6 +55,7 @@ struct Ctx {
     int B = 16384;                 // lag-block size (samples); FFT size is 2B
     int chunk_items = 1024;        // items per MAC/C2R/normalise chunk (cuFFT engine)
     int engine = 1;                // 1: fused lag-block kernel (sb_fused.cu), 0: cuFFT pipeline
+    int hop_mode = 0;              // fused engine geometry: 1 = hop B (50 % of each FFT valid), 2 = hop B/2 (75 %), 0 = pick per batch
     int64_t max_parts = 16384;     // template partition spectra kept per super-chunk
 
     // scratch (grown on demand)
@@ -98,11 +99,11 @@ void pool_free(void* p);
 void pool_release_all();
 
 bool fused_supports(int B);
-int launch_match_fused(const sb_stream* image, const sb_stream* tmpl, const float2* d_parts, int64_t part_first,
+int launch_match_fused(const sb_stream* image, const sb_stream* tmpl, int hd, const float2* d_parts, int64_t part_first,
                        const QueryDesc* d_desc, int q_begin, int q_end, int64_t item_first, int64_t n_items,
                        unsigned long long* d_keys, float* d_curve);
-int launch_block_spectra(const sb_stream* s, int64_t k_first, int64_t rows, float2* out);
-int launch_part_spectra(const sb_stream* tmpl, const QueryDesc* d_desc, int q_begin, int q_end,
+int launch_block_spectra(const sb_stream* s, int hd, int64_t k_first, int64_t rows, float2* out);
+int launch_part_spectra(const sb_stream* tmpl, int hd, const QueryDesc* d_desc, int q_begin, int q_end,
                         int64_t part_first, int64_t rows, float2* out);
 void fused_release_tables();
 
@@ -120,6 +121,7 @@ struct sb_stream {
     // block spectra for lag-block size specB: [nblk][specB+1] complex64
     float2* d_spec = nullptr;
     int specB = 0;
+    int specHD = 1;               // hop divisor the rows were built with (row k starts at k * specB / specHD)
     int specEngine = -1;          // engine that built d_spec (rebuilt when the engine changes)
     int64_t nblk = 0;
 };

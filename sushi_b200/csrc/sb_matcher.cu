@@ -13,9 +13,10 @@
 // applied in the same kernel that reads the correlation back.
 #include "sb_internal.h"
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 
-namespace sb { int ensure_spectra(sb_stream* s); }
+namespace sb { int ensure_spectra(sb_stream* s, int hd); }
 using namespace sb;
 
 namespace {
@@ -291,10 +292,11 @@ int grow(T** p, int64_t* cap, int64_t need, bool pinned = false) {
 
 // Validate + plan a batch on the host. Fills c.h_desc[0..count).
 int plan_batch(const sb_stream* image, const sb_stream* tmpl, int64_t count,
-               const int64_t* toff, const int64_t* tlen, const int64_t* lag0, const int64_t* nlags,
+               const int64_t* toff, const int64_t* tlen, const int64_t* lag0, const int64_t* nlags, int hd,
                int64_t* total_items, int64_t* total_parts, int64_t* max_query_parts) {
     Ctx& c = ctx();
     const int B = c.B;
+    const int64_t H = B / hd, LB = 2 * (int64_t)B - H;     // partition length / hop, lags per item
     SB_CUDA(cudaEventSynchronize(c.ev_desc));       // previous batch has finished reading h_desc
     if (c.h_desc_cap < count) {
         if (c.h_desc) { cudaStreamSynchronize(c.stream); cudaFreeHost(c.h_desc); c.h_desc = nullptr; c.h_desc_cap = 0; }
@@ -310,9 +312,9 @@ int plan_batch(const sb_stream* image, const sb_stream* tmpl, int64_t count,
         if (L > 0xffffffffll) SB_FAIL(SB_EINVAL, "query %lld: more than 2^32 lags", (long long)q);
         QueryDesc& d = c.h_desc[q];
         d.toff = o; d.tlen = n; d.lag0 = s; d.nlags = L;
-        d.P = (int32_t)((n + B - 1) / B);
-        d.k0 = (int32_t)(s / B);
-        d.nk = (int32_t)((s + L - 1) / B - d.k0 + 1);
+        d.P = (int32_t)((n + H - 1) / H);
+        d.k0 = (int32_t)(s / LB);
+        d.nk = (int32_t)((s + L - 1) / LB - d.k0 + 1);
         d.itemBase = items; d.partBase = parts; d.pad_ = 0; d.curveOff = curve_total;
         curve_total += L;
         items += d.nk; parts += d.P;
@@ -330,9 +332,28 @@ int run_batch(const sb_stream* image_c, const sb_stream* tmpl, int64_t count,
     sb_stream* image = const_cast<sb_stream*>(image_c);
     if (image->dtype != tmpl->dtype) SB_FAIL(SB_EINVAL, "image and template streams differ in sample type");
     const int B = c.B, nb = B + 1;
+    const bool use_fused = c.engine == 1 && fused_supports(B);
+    // Geometry of the fused engine.  hop B: half of every 2B-point inverse FFT is valid lags, P = n/B
+    // partitions per item.  hop B/2: three quarters are valid (1.5x the lags per FFT) but there are
+    // twice as many, half as long, partitions to multiply.  Cost per lag in units of one classic item
+    // (measured shares, profiles/README.md): (0.76 + 0.104 P) / 1 against (0.885 + 0.104 P') / 1.5.
+    int hd = 1;
+    if (use_fused) {
+        if (c.hop_mode == 2) hd = 2;
+        else if (c.hop_mode == 0 && !d_curve) {
+            double w = 0, c1 = 0, c2 = 0;
+            for (int64_t q = 0; q < count; ++q) {
+                const double n = (double)tlen[q], L = (double)nlags[q];
+                c1 += L * (0.76 + 0.104 * ceil(n / B));
+                c2 += L * (0.885 + 0.104 * ceil(n / (B / 2))) / 1.5;
+                w += L;
+            }
+            if (w > 0 && c2 < c1) hd = 2;
+        }
+    }
     int64_t total_items = 0, total_parts = 0, maxp = 0;
-    SB_TRY(plan_batch(image, tmpl, count, toff, tlen, lag0, nlags, &total_items, &total_parts, &maxp));
-    SB_TRY(ensure_spectra(image));
+    SB_TRY(plan_batch(image, tmpl, count, toff, tlen, lag0, nlags, hd, &total_items, &total_parts, &maxp));
+    SB_TRY(ensure_spectra(image, hd));
 
     SB_TRY(grow(&c.d_desc, &c.desc_cap, count));
     SB_TRY(grow(&c.d_keys, &c.keys_cap, count));
@@ -342,7 +363,6 @@ int run_batch(const sb_stream* image_c, const sb_stream* tmpl, int64_t count,
 
     const int64_t parts_cap_want = std::max<int64_t>(std::min<int64_t>(total_parts, c.max_parts), maxp);
     SB_TRY(grow(&c.d_parts, &c.parts_cap, parts_cap_want * nb));
-    const bool use_fused = c.engine == 1 && fused_supports(B);
     const int64_t chunk = std::min<int64_t>(c.chunk_items, total_items);
     if (!use_fused) SB_TRY(grow(&c.d_items, &c.items_cap, chunk * nb));
 
@@ -361,7 +381,7 @@ int run_batch(const sb_stream* image_c, const sb_stream* tmpl, int64_t count,
         const int64_t sub = 4096;
         if (use_fused) {                             // hand-written gather + forward FFT, one launch
             ProfScope ps("part_spectra");
-            SB_TRY(launch_part_spectra(tmpl, c.d_desc, (int)qb, (int)qe, part_first, np, c.d_parts));
+            SB_TRY(launch_part_spectra(tmpl, hd, c.d_desc, (int)qb, (int)qe, part_first, np, c.d_parts));
         } else
         for (int64_t p0 = 0; p0 < np; p0 += sub) {
             const int64_t rows = std::min<int64_t>(sub, np - p0);
@@ -387,7 +407,7 @@ int run_batch(const sb_stream* image_c, const sb_stream* tmpl, int64_t count,
         const int64_t item_hi = (qe < count) ? c.h_desc[qe].itemBase : total_items;
         if (use_fused) {
             ProfScope ps("match_fused");
-            SB_TRY(launch_match_fused(image, tmpl, c.d_parts, part_first, c.d_desc, (int)qb, (int)qe,
+            SB_TRY(launch_match_fused(image, tmpl, hd, c.d_parts, part_first, c.d_desc, (int)qb, (int)qe,
                                       item_lo, item_hi - item_lo, c.d_keys, d_curve));
         } else
         for (int64_t i0 = item_lo; i0 < item_hi; i0 += chunk) {

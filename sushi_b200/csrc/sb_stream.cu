@@ -209,22 +209,23 @@ namespace sb {
 
 int stream_finish_public(sb_stream* s) { return stream_finish(s); }
 
-// Build (or fetch) the block spectra of `s` for the current block size.
-int ensure_spectra(sb_stream* s) {
+// Build (or fetch) the block spectra of `s`: row k = FFT_2B of samples [k*H, k*H + 2B), H = B/hd.
+int ensure_spectra(sb_stream* s, int hd) {
     Ctx& c = ctx();
-    if (s->d_spec && s->specB == c.B && s->specEngine == c.engine) return SB_OK;
+    if (s->d_spec && s->specB == c.B && s->specHD == hd && s->specEngine == c.engine) return SB_OK;
     if (s->d_spec) { pool_free(s->d_spec); s->d_spec = nullptr; }
-    const int B = c.B;
-    const int64_t nblk = (s->n + B - 1) / B;
+    const int B = c.B, H = B / hd;
+    const int64_t nblk = (s->n + H - 1) / H;
     SB_TRY(pool_alloc((void**)&s->d_spec, sizeof(float2) * (size_t)nblk * (B + 1)));
     if (c.engine == 1 && fused_supports(B)) {        // hand-written gather + forward FFT, one launch
         {
             ProfScope ps("block_spectra");
-            SB_TRY(launch_block_spectra(s, 0, nblk, s->d_spec));
+            SB_TRY(launch_block_spectra(s, hd, 0, nblk, s->d_spec));
         }
-        s->specB = B; s->nblk = nblk; s->specEngine = c.engine;
+        s->specB = B; s->specHD = hd; s->nblk = nblk; s->specEngine = c.engine;
         return SB_OK;
     }
+    if (hd != 1) SB_FAIL(SB_EINVAL, "internal: the cuFFT engine only builds spectra at hop B");
     const int chunks = (2 * B + 2047) / 2048;
     const int64_t sub = 1024;                        // rows per cuFFT call
     for (int64_t k = 0; k < nblk; k += sub) {
@@ -247,7 +248,7 @@ int ensure_spectra(sb_stream* s) {
         }
     }
     SB_CUDA(cudaGetLastError());
-    s->specB = B; s->nblk = nblk; s->specEngine = c.engine;
+    s->specB = B; s->specHD = 1; s->nblk = nblk; s->specEngine = c.engine;
     return SB_OK;
 }
 

@@ -91,21 +91,24 @@ def test_fused_engine_equals_cufft_engine(gpu_lib, pair, stype, block):
         toff, n = src._get_sample_for_time(6.1), 11400
         lag0, nlags = 70000, 150001
         curves, results = [], []
-        for engine in (0, 1):
+        # (engine, hop mode): the cuFFT pipeline, then the fused kernel in both overlap-save geometries
+        variants = [(0, 1), (1, 1), (1, 2)]
+        for engine, hop in variants:
             _native.check(gpu_lib.sb_set_engine(engine))
+            _native.check(gpu_lib.sb_set_hop_mode(hop))
             curves.append(dst.match_curve(src, toff, n, lag0, nlags))
             results.append(dst.find_planned(src, [toff, toff + 5000, 100], [n, 3000, 48000],
                                             [lag0, 1000, 0], [nlags, 300000, 200000]))
-        for e in (1,):
+            # the batch result is the first-index minimum of the variant's own curve
+            d, i = dst.find_planned(src, [toff], [n], [lag0], [nlags])
+            assert i[0] == int(curves[-1].argmin()) and d[0] == curves[-1].min()
+        for e in (1, 2):
             assert np.abs(curves[0] - curves[e]).max() <= 2e-6
             assert np.abs(results[0][0] - results[e][0]).max() <= 2e-6
             assert np.abs(results[0][1] - results[e][1]).max() <= 1
-            # the batch result is the first-index minimum of the engine's own curve
-            _native.check(gpu_lib.sb_set_engine(e))
-            d, i = dst.find_planned(src, [toff], [n], [lag0], [nlags])
-            assert i[0] == int(curves[e].argmin()) and d[0] == curves[e].min()
     finally:
         _native.check(gpu_lib.sb_set_engine(1))
+        _native.check(gpu_lib.sb_set_hop_mode(0))
         _native.check(gpu_lib.sb_set_block_size(16384))
 
 
@@ -309,12 +312,13 @@ def test_empty_batch_is_a_no_op(gpu_lib, pair):
     assert len(d) == 0 and len(i) == 0
 
 
-@pytest.mark.parametrize('engine', [0, 1])
+@pytest.mark.parametrize('engine', [0, 1, 2])
 def test_minimum_sizes_and_ragged_edges(gpu_lib, engine):
     """n = 1 templates, single-lag searches, streams shorter than one lag block, searches that end on
     the last sample, spans that straddle exactly one block boundary."""
     rng = np.random.default_rng(engine)
-    _native.check(gpu_lib.sb_set_engine(engine))
+    _native.check(gpu_lib.sb_set_engine(min(engine, 1)))          # 2 = fused kernel at hop B/2
+    _native.check(gpu_lib.sb_set_hop_mode(2 if engine == 2 else 1))
     try:
         for total in (7, 1000, 16384, 16385, 40000):
             img = rng.integers(0, 256, total, dtype=np.uint8)
@@ -338,6 +342,7 @@ def test_minimum_sizes_and_ragged_edges(gpu_lib, engine):
                 assert want[int(i[0])] - want.min() <= 2e-6          # a minimiser (ties on random data are rare)
     finally:
         _native.check(gpu_lib.sb_set_engine(1))
+        _native.check(gpu_lib.sb_set_hop_mode(0))
 
 
 def test_batch_split_into_several_passes(gpu_lib, pair):
