@@ -523,7 +523,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--block', type=int, default=0, help='lag-block size override')
     ap.add_argument('--chunk', type=int, default=0, help='items per launch override')
-    ap.add_argument('--hop-mode', type=int, default=-1, help='fused engine geometry: 0 auto (default), 1 hop B, 2 hop B/2')
+    ap.add_argument('--hop-mode', type=int, default=-1, help='fused engine geometry: 1 hop B (default), 2 hop B/2, 0 cost rule per batch')
     ap.add_argument('--engine', type=int, default=-1, help='0: cuFFT pipeline, 1: fused kernel (default)')
     args = ap.parse_args()
     if args.impl == 'reference':

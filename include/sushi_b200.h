@@ -75,9 +75,10 @@ int sb_get_block_size(void);
  * cuFFT-planned pipeline (any block size; kept as the cross-check and for odd block sizes). */
 int sb_set_engine(int engine);
 int sb_get_engine(void);
-/* Overlap-save geometry of the fused engine: 1 = hop B (half of each inverse FFT is valid lags),
- * 2 = hop B/2 (three quarters valid, twice as many template partitions), 0 (default) = chosen per
- * batch from the template lengths.  Results do not depend on it. */
+/* Overlap-save geometry of the fused engine: 1 (default) = hop B (half of each inverse FFT is valid
+ * lags), 2 = hop B/2 (three quarters valid, but twice as many template partitions to multiply:
+ * pays off only for templates shorter than B/2), 0 = chosen per batch by a cost rule.  Geometries
+ * agree to float32 FFT rounding (~1e-7), not bit for bit, so a run should stick to one. */
 int sb_set_hop_mode(int mode);
 /* Lag blocks processed per multiply / inverse-FFT / normalise launch (>= 1). */
 int sb_set_chunk_items(int items);

@@ -55,7 +55,7 @@ struct Ctx {
     int B = 16384;                 // lag-block size (samples); FFT size is 2B
     int chunk_items = 1024;        // items per MAC/C2R/normalise chunk (cuFFT engine)
     int engine = 1;                // 1: fused lag-block kernel (sb_fused.cu), 0: cuFFT pipeline
-    int hop_mode = 0;              // fused engine geometry: 1 = hop B (50 % of each FFT valid), 2 = hop B/2 (75 %), 0 = pick per batch
+    int hop_mode = 1;              // fused engine geometry: 1 = hop B (50 % of each FFT valid, default), 2 = hop B/2 (75 %), 0 = pick per batch
     int64_t max_parts = 16384;     // template partition spectra kept per super-chunk
 
     // scratch (grown on demand)

@@ -108,7 +108,7 @@ def test_fused_engine_equals_cufft_engine(gpu_lib, pair, stype, block):
             assert np.abs(results[0][1] - results[e][1]).max() <= 1
     finally:
         _native.check(gpu_lib.sb_set_engine(1))
-        _native.check(gpu_lib.sb_set_hop_mode(0))
+        _native.check(gpu_lib.sb_set_hop_mode(1))
         _native.check(gpu_lib.sb_set_block_size(16384))
 
 
@@ -342,7 +342,7 @@ def test_minimum_sizes_and_ragged_edges(gpu_lib, engine):
                 assert want[int(i[0])] - want.min() <= 2e-6          # a minimiser (ties on random data are rare)
     finally:
         _native.check(gpu_lib.sb_set_engine(1))
-        _native.check(gpu_lib.sb_set_hop_mode(0))
+        _native.check(gpu_lib.sb_set_hop_mode(1))
 
 
 def test_batch_split_into_several_passes(gpu_lib, pair):

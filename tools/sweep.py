@@ -21,6 +21,9 @@ ap.add_argument('--queries', type=int, default=256)
 ap.add_argument('--duration', type=float, default=1800.0)
 ap.add_argument('--sample-type', default='uint8')
 ap.add_argument('--reps', type=int, default=3)
+ap.add_argument('--hop-mode', type=int, default=1)
+ap.add_argument('--events', default='0.5,1,3,10,30')
+ap.add_argument('--windows', default='5,10,30,60,120,300,600')
 a = ap.parse_args()
 
 peak = 6650.0
@@ -32,14 +35,17 @@ src_pcm, dst_pcm = synth.make_pair(a.duration, 2, 1.5)
 src = WavStream.from_pcm(src_pcm, 12000, sample_type=a.sample_type)
 dst = WavStream.from_pcm(dst_pcm, 12000, sample_type=a.sample_type)
 lib = _native.lib()
+_native.check(lib.sb_set_hop_mode(a.hop_mode))
+EV = [float(x) for x in a.events.split(',')]
+WIN = [float(x) for x in a.windows.split(',')]
 bps = 1 if a.sample_type == 'uint8' else 4
 pd, pi = ctypes.c_void_p(), ctypes.c_void_p()
 _native.check(lib.sb_device_alloc(4 * a.queries, ctypes.byref(pd)))
 _native.check(lib.sb_device_alloc(8 * a.queries, ctypes.byref(pi)))
 rng = np.random.default_rng(5)
 rows = []
-for ev_len in (0.5, 1.0, 3.0, 10.0, 30.0):
-    for win in (5.0, 10.0, 30.0, 60.0, 120.0, 300.0, 600.0):
+for ev_len in EV:
+    for win in WIN:
         starts = np.sort(rng.uniform(win * 0.25, a.duration - ev_len - 2.0, a.queries))
         starts = np.round(starts * 100) / 100
         ends = starts + ev_len
@@ -66,8 +72,8 @@ for ev_len in (0.5, 1.0, 3.0, 10.0, 30.0):
 os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
 json.dump({'peak_hbm_gbs': peak, 'sample_type': a.sample_type, 'duration_s': a.duration, 'cells': rows},
           open(os.path.join(ROOT, 'gpurun_out', 'sweep.json'), 'w'), indent=1)
-print('\n| event \\ window | ' + ' | '.join('±%g s' % w for w in (5, 10, 30, 60, 120, 300, 600)) + ' |')
-print('|---|' + '---|' * 7)
-for ev_len in (0.5, 1.0, 3.0, 10.0, 30.0):
+print('\n| event \\ window | ' + ' | '.join('±%g s' % w for w in WIN) + ' |')
+print('|---|' + '---|' * len(WIN))
+for ev_len in EV:
     cells = [r for r in rows if r['event_s'] == ev_len]
     print('| %g s | ' % ev_len + ' | '.join('%.0f ev/s, %.0f GB/s (%.1f%%)' % (r['events_per_s'], r['alg_gbs'], 100 * r['frac_hbm']) for r in cells) + ' |')
