@@ -333,22 +333,18 @@ int run_batch(const sb_stream* image_c, const sb_stream* tmpl, int64_t count,
     if (image->dtype != tmpl->dtype) SB_FAIL(SB_EINVAL, "image and template streams differ in sample type");
     const int B = c.B, nb = B + 1;
     const bool use_fused = c.engine == 1 && fused_supports(B);
-    // Geometry of the fused engine.  hop B: half of every 2B-point inverse FFT is valid lags, P = n/B
-    // partitions per item.  hop B/2: three quarters are valid (1.5x the lags per FFT) but there are
-    // twice as many, half as long, partitions to multiply.  Cost per lag in units of one classic item
-    // (measured shares, profiles/README.md): (0.76 + 0.104 P) / 1 against (0.885 + 0.104 P') / 1.5.
+    // Geometry of the fused engine.  hop B (default): half of every 2B-point inverse FFT is valid lags,
+    // P = ceil(n/B) partitions per item.  hop B/2: three quarters are valid (1.5x the lags per FFT) but
+    // there are twice as many partition rows to multiply and twice as many block-spectrum rows competing
+    // for L2.  Measured (profiles/README.md): +21 % for templates up to B/2 samples, break-even around
+    // 1-2 s events, -12 % on config 2.  Mode 0 therefore switches only when every template is short.
     int hd = 1;
     if (use_fused) {
         if (c.hop_mode == 2) hd = 2;
-        else if (c.hop_mode == 0 && !d_curve) {
-            double w = 0, c1 = 0, c2 = 0;
-            for (int64_t q = 0; q < count; ++q) {
-                const double n = (double)tlen[q], L = (double)nlags[q];
-                c1 += L * (0.76 + 0.104 * ceil(n / B));
-                c2 += L * (0.885 + 0.104 * ceil(n / (B / 2))) / 1.5;
-                w += L;
-            }
-            if (w > 0 && c2 < c1) hd = 2;
+        else if (c.hop_mode == 0) {
+            int64_t longest = 0;
+            for (int64_t q = 0; q < count; ++q) longest = std::max<int64_t>(longest, tlen[q]);
+            if (longest <= B / 2) hd = 2;
         }
     }
     int64_t total_items = 0, total_parts = 0, maxp = 0;
