@@ -76,3 +76,12 @@ def test_product_does_not_import_the_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r'^\s*(from|import)\s+oracle\b', text, flags=re.M), f
                 assert 'import cv2' not in text, f
+
+
+def test_missing_library_is_an_error_not_a_fallback(monkeypatch):
+    """No .so -> SushiError that says how to build it; nothing falls back to a CPU implementation."""
+    monkeypatch.setattr(_native, '_lib', None)
+    monkeypatch.setattr(_native, 'LIB_PATH', '/nonexistent/libsushi_b200.so')
+    with pytest.raises(SushiError) as e:
+        _native.load_library()
+    assert 'no CPU fallback' in str(e.value)
