@@ -278,6 +278,8 @@ def run_b200(args):
         _native.check(lib.sb_set_engine(args.engine))
     if args.hop_mode >= 0:
         _native.check(lib.sb_set_hop_mode(args.hop_mode))
+    if args.premac_mode >= 0:
+        _native.check(lib.sb_set_premac_mode(args.premac_mode))
 
     dist = torch = None
     if world > 1:
@@ -523,6 +525,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--block', type=int, default=0, help='lag-block size override')
     ap.add_argument('--chunk', type=int, default=0, help='items per launch override')
+    ap.add_argument('--premac-mode', type=int, default=-1, help='blocked multiply kernel: 0 by template length (default), 1 never, 2 always')
     ap.add_argument('--hop-mode', type=int, default=-1, help='fused engine geometry: 1 hop B (default), 2 hop B/2, 0 cost rule per batch')
     ap.add_argument('--engine', type=int, default=-1, help='0: cuFFT pipeline, 1: fused kernel (default)')
     args = ap.parse_args()

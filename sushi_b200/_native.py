@@ -35,6 +35,7 @@ PROTOTYPES = {
     'sb_set_max_parts': (ctypes.c_int, [c_i64]),
     'sb_get_engine': (ctypes.c_int, []),
     'sb_set_hop_mode': (ctypes.c_int, [ctypes.c_int]),
+    'sb_set_premac_mode': (ctypes.c_int, [ctypes.c_int]),
     'sb_get_stream': (c_vp, []),
     'sb_pinned_alloc': (ctypes.c_int, [c_i64, ctypes.POINTER(c_vp)]),
     'sb_pinned_free': (ctypes.c_int, [c_vp]),

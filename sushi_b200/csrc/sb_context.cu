@@ -179,7 +179,7 @@ int sb_shutdown(void) {
     drop_plans();
     pool_release_all();
     fused_release_tables();
-    cudaFree(c.d_parts); cudaFree(c.d_items); cudaFree(c.d_desc); cudaFree(c.d_keys);
+    cudaFree(c.d_parts); cudaFree(c.d_items); cudaFree(c.d_desc); cudaFree(c.d_keys); cudaFree(c.d_groups);
     cudaFree(c.d_diff); cudaFree(c.d_idx);
     cudaFreeHost(c.h_desc); cudaFreeHost(c.h_diff); cudaFreeHost(c.h_idx);
     for (auto e : c.event_pool) cudaEventDestroy(e);
@@ -217,6 +217,11 @@ int sb_set_engine(int engine) {
     return SB_OK;
 }
 int sb_get_engine(void) { return ctx().engine; }
+int sb_set_premac_mode(int mode) {
+    if (mode < 0 || mode > 2) SB_FAIL(SB_EINVAL, "sb_set_premac_mode: %d is not 0 (by template length), 1 (never) or 2 (always)", mode);
+    ctx().premac_mode = mode;
+    return SB_OK;
+}
 int sb_set_hop_mode(int mode) {
     if (mode < 0 || mode > 2) SB_FAIL(SB_EINVAL, "sb_set_hop_mode: %d is not 0 (auto), 1 (hop B) or 2 (hop B/2)", mode);
     ctx().hop_mode = mode;

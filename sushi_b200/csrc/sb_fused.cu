@@ -119,7 +119,7 @@ __device__ __forceinline__ void ifft_smem(float2* __restrict__ buf, const float2
 // ---------------------------------------------------------------- the kernel
 template <int LOGN, typename S, int HD>
 __global__ void __launch_bounds__(Cfg<LOGN>::T, Cfg<LOGN>::MINB)
-k_match_fused(const float2* __restrict__ That, int64_t part_first,
+k_match_fused(const float2* __restrict__ That, int64_t part_first, const float2* __restrict__ Ypre,
               const float2* __restrict__ Xhat, int64_t nblk,
               const S* __restrict__ img, int64_t img_n,
               const double2* __restrict__ ipfx, const double2* __restrict__ tpfx,
@@ -199,6 +199,11 @@ k_match_fused(const float2* __restrict__ That, int64_t part_first,
             float2 ym[U], yp[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) { ym[u] = make_float2(0.f, 0.f); yp[u] = make_float2(0.f, 0.f); }
+            if (Ypre) {                             // products already formed by k_mac_blocked (long templates)
+                const float2* y = Ypre + (int64_t)blockIdx.x * NB;
+#pragma unroll
+                for (int u = 0; u < U; ++u) { const int m = m0 + u * T; ym[u] = __ldg(y + m); yp[u] = __ldg(y + (B - m)); }
+            } else
             for (int p = 0; p < P; ++p) {
                 const float2* t = tp + (int64_t)p * NB;
                 const float2* x = xp + (int64_t)p * NB;
@@ -229,6 +234,8 @@ k_match_fused(const float2* __restrict__ That, int64_t part_first,
         }
         if (tid < 32) {                             // the self-paired bin m = B/2 (w = i): Z = 2*conj(Y)
             float2 y = make_float2(0.f, 0.f);
+            if (Ypre) { if (lane == 0) y = __ldg(Ypre + (int64_t)blockIdx.x * NB + B / 2); }
+            else
             for (int p = lane; p < P; p += 32) {
                 const float2 t1 = __ldg(tp + (int64_t)p * NB + B / 2), x1 = __ldg(xp + (int64_t)p * NB + B / 2);
                 y.x += t1.x * x1.x + t1.y * x1.y;  y.y += t1.x * x1.y - t1.y * x1.x;
@@ -527,7 +534,7 @@ int* g_item_query = nullptr;
 int64_t g_item_query_cap = 0;
 
 template <int LOGN, typename S, int HD>
-int launch_typed(const sb_stream* image, const sb_stream* tmpl, const float2* d_parts, int64_t part_first,
+int launch_typed(const sb_stream* image, const sb_stream* tmpl, const float2* d_parts, int64_t part_first, const float2* d_premac,
                  const QueryDesc* d_desc, int q_begin, int q_end, int64_t item_first, int64_t n_items,
                  unsigned long long* d_keys, float* d_curve) {
     Ctx& c = ctx();
@@ -554,7 +561,8 @@ int launch_typed(const sb_stream* image, const sb_stream* tmpl, const float2* d_
     for (int64_t i0 = 0; i0 < n_items; i0 += max_grid) {
         const int64_t ni = std::min<int64_t>(max_grid, n_items - i0);
         k_match_fused<LOGN, S, HD><<<(unsigned)ni, Cfg<LOGN>::T, smem, c.stream>>>(
-            d_parts, part_first, image->d_spec, image->nblk, static_cast<const S*>(image->d_raw), image->n,
+            d_parts, part_first, d_premac ? d_premac + i0 * (int64_t)(Cfg<LOGN>::N + 1) : nullptr, image->d_spec, image->nblk,
+            static_cast<const S*>(image->d_raw), image->n,
             image->d_pfx, tmpl->d_pfx, d_desc, g_item_query + i0, item_first + i0,
             tab, d_keys, d_curve);
     }
@@ -598,12 +606,12 @@ namespace sb {
 
 bool fused_supports(int B) { return B == 16384 || B == 8192; }
 
-int launch_match_fused(const sb_stream* image, const sb_stream* tmpl, int hd, const float2* d_parts, int64_t part_first,
+int launch_match_fused(const sb_stream* image, const sb_stream* tmpl, int hd, const float2* d_parts, int64_t part_first, const float2* d_premac,
                        const QueryDesc* d_desc, int q_begin, int q_end, int64_t item_first, int64_t n_items,
                        unsigned long long* d_keys, float* d_curve) {
     const int B = ctx().B;
     const bool u8 = image->dtype == SB_U8;
-#define SB_FUSED(LOGN, S, HD) launch_typed<LOGN, S, HD>(image, tmpl, d_parts, part_first, d_desc, q_begin, q_end, item_first, n_items, d_keys, d_curve)
+#define SB_FUSED(LOGN, S, HD) launch_typed<LOGN, S, HD>(image, tmpl, d_parts, part_first, d_premac, d_desc, q_begin, q_end, item_first, n_items, d_keys, d_curve)
     if (B == 16384) return hd == 2 ? (u8 ? SB_FUSED(14, uint8_t, 2) : SB_FUSED(14, float, 2)) : (u8 ? SB_FUSED(14, uint8_t, 1) : SB_FUSED(14, float, 1));
     if (B == 8192)  return hd == 2 ? (u8 ? SB_FUSED(13, uint8_t, 2) : SB_FUSED(13, float, 2)) : (u8 ? SB_FUSED(13, uint8_t, 1) : SB_FUSED(13, float, 1));
 #undef SB_FUSED

@@ -41,11 +41,14 @@ struct QueryDesc {
     int64_t itemBase;  // first item of this query in the batch-wide item list
     int64_t partBase;  // first partition spectrum of this query
     int64_t curveOff;  // where this query's curve starts in the curve buffer (curve mode only)
+    int64_t groupBase; // first multiply group (MAC_GROUP consecutive lag blocks) of this query in the batch
     int32_t P;         // ceil(n / H), H = hop = partition length
     int32_t k0;        // lag0 / LB, LB = lags per item
     int32_t nk;        // number of lag blocks touched
-    int32_t pad_;
+    int32_t orig;      // index of this query in the caller's arrays (descriptors are in processing order)
 };
+
+constexpr int MAC_GROUP = 8;      // lag blocks per register-blocked multiply group (sb_matcher.cu: k_mac_blocked)
 
 struct Ctx {
     bool inited = false;
@@ -55,6 +58,7 @@ struct Ctx {
     int B = 16384;                 // lag-block size (samples); FFT size is 2B
     int chunk_items = 1024;        // items per MAC/C2R/normalise chunk (cuFFT engine)
     int engine = 1;                // 1: fused lag-block kernel (sb_fused.cu), 0: cuFFT pipeline
+    int premac_mode = 0;           // 0: register-blocked multiply kernel when a batch averages >= 3 partitions, 1: never, 2: always
     int hop_mode = 1;              // fused engine geometry: 1 = hop B (50 % of each FFT valid, default), 2 = hop B/2 (75 %), 0 = pick per batch
     int64_t max_parts = 16384;     // template partition spectra kept per super-chunk
 
@@ -62,6 +66,7 @@ struct Ctx {
     float2* d_parts = nullptr;  int64_t parts_cap = 0;     // [parts][B+1] complex (in-place R2C)
     float2* d_items = nullptr;  int64_t items_cap = 0;     // [items][B+1] complex (in-place C2R)
     QueryDesc* d_desc = nullptr; int64_t desc_cap = 0;
+    int2* d_groups = nullptr; int64_t groups_cap = 0;      // (query, first local lag block) per multiply group
     unsigned long long* d_keys = nullptr; int64_t keys_cap = 0;
     float* d_diff = nullptr; int64_t* d_idx = nullptr; int64_t res_cap = 0;
     // pinned staging
@@ -99,7 +104,7 @@ void pool_free(void* p);
 void pool_release_all();
 
 bool fused_supports(int B);
-int launch_match_fused(const sb_stream* image, const sb_stream* tmpl, int hd, const float2* d_parts, int64_t part_first,
+int launch_match_fused(const sb_stream* image, const sb_stream* tmpl, int hd, const float2* d_parts, int64_t part_first, const float2* d_premac,
                        const QueryDesc* d_desc, int q_begin, int q_end, int64_t item_first, int64_t n_items,
                        unsigned long long* d_keys, float* d_curve);
 int launch_block_spectra(const sb_stream* s, int hd, int64_t k_first, int64_t rows, float2* out);

@@ -120,6 +120,77 @@ k_spectral_mac(const float2* __restrict__ That, int64_t part_first, const float2
     }
 }
 
+// ---- register-blocked spectral multiply for long templates ------------------------------------
+// G = MAC_GROUP consecutive lag blocks of one query share every template row: block g at partition
+// step p needs spectrum row k0+g+p, so a ring of G row values slides by one row per step and each
+// step costs one template load and ONE new spectrum load per bin for G multiply-accumulates (the
+// per-item kernel loads 2 per multiply-accumulate).  Y[item][bin] goes to a buffer the fused kernel
+// then reads instead of multiplying itself.  Pays from about 3 partitions per template.
+__global__ void k_fill_groups(const QueryDesc* __restrict__ desc, int q_begin, int64_t group_first, int2* __restrict__ groups) {
+    const int q = q_begin + blockIdx.x;
+    const int64_t base = desc[q].groupBase - group_first;
+    const int ng = (desc[q].nk + MAC_GROUP - 1) / MAC_GROUP;
+    for (int i = threadIdx.x; i < ng; i += blockDim.x) groups[base + i] = make_int2(q, i * MAC_GROUP);
+}
+
+constexpr int MACB_THREADS = 256;
+constexpr int MACB_BINS = 2 * MACB_THREADS;         // two bins per thread
+__global__ void __launch_bounds__(MACB_THREADS)
+k_mac_blocked(const float2* __restrict__ That, int64_t part_first, const float2* __restrict__ Xhat, int64_t nblk,
+              const QueryDesc* __restrict__ desc, const int2* __restrict__ groups, int64_t item_first,
+              int B, float2* __restrict__ Y, int chunks_per_group) {
+    constexpr int G = MAC_GROUP;
+    const int2 grp = groups[blockIdx.x / chunks_per_group];
+    const int chunk = blockIdx.x % chunks_per_group;
+    const QueryDesc d = desc[grp.x];
+    const int64_t k0 = d.k0 + grp.y;
+    const int ng = min(G, d.nk - grp.y);
+    const int nb = B + 1;
+    const int b0 = chunk * MACB_BINS + threadIdx.x, b1 = b0 + MACB_THREADS;
+    const bool ok0 = b0 < nb, ok1 = b1 < nb;
+    const float2 zero = make_float2(0.f, 0.f);
+    const float2* tp = That + (d.partBase - part_first) * (int64_t)nb;
+    float2 acc0[G], acc1[G], x0[G], x1[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        acc0[g] = zero; acc1[g] = zero;
+        const int64_t row = k0 + g;
+        const float2* xr = Xhat + row * (int64_t)nb;
+        x0[g] = (ok0 && row < nblk) ? __ldg(xr + b0) : zero;
+        x1[g] = (ok1 && row < nblk) ? __ldg(xr + b1) : zero;
+    }
+    const int P = d.P;
+    for (int p0 = 0; p0 < P; p0 += G) {
+#pragma unroll
+        for (int s = 0; s < G; ++s) {
+            const int p = p0 + s;
+            if (p < P) {                               // uniform over the CTA
+                const float2* t = tp + (int64_t)p * nb;
+                const float2 t0 = ok0 ? __ldg(t + b0) : zero, t1 = ok1 ? __ldg(t + b1) : zero;
+                const int64_t nrow = k0 + p + G;       // the row that enters the ring after this step
+                const float2* xr = Xhat + nrow * (int64_t)nb;
+                const float2 n0 = (ok0 && nrow < nblk) ? __ldg(xr + b0) : zero;
+                const float2 n1 = (ok1 && nrow < nblk) ? __ldg(xr + b1) : zero;
+#pragma unroll
+                for (int g = 0; g < G; ++g) {          // slot (g+s)%G holds row k0+g+p
+                    const float2 a = x0[(g + s) % G], b = x1[(g + s) % G];
+                    acc0[g].x += t0.x * a.x + t0.y * a.y;  acc0[g].y += t0.x * a.y - t0.y * a.x;
+                    acc1[g].x += t1.x * b.x + t1.y * b.y;  acc1[g].y += t1.x * b.y - t1.y * b.x;
+                }
+                x0[s % G] = n0; x1[s % G] = n1;        // row k0+p leaves, row k0+p+G enters
+            }
+        }
+    }
+    float2* y = Y + (d.itemBase + grp.y - item_first) * (int64_t)nb;
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        if (g < ng) {
+            if (ok0) y[(int64_t)g * nb + b0] = acc0[g];
+            if (ok1) y[(int64_t)g * nb + b1] = acc1[g];
+        }
+    }
+}
+
 // ---- normalise + argmin ----------------------------------------------------------
 // OpenCV's rule for TM_SQDIFF_NORMED (imgproc/templmatch.cpp, common_matchTemplate;
 // behaviour pinned by tests/golden): with corr the float32-rounded sum(I*T),
@@ -267,13 +338,15 @@ k_normalise_argmin(const float* __restrict__ corr_rows, const T* __restrict__ im
     }
 }
 
-__global__ void k_unpack_results(const unsigned long long* __restrict__ keys, int64_t count,
-                                 float* __restrict__ diff, int64_t* __restrict__ idx) {
+// keys are in processing order; results go back in the caller's order
+__global__ void k_unpack_results(const unsigned long long* __restrict__ keys, const QueryDesc* __restrict__ desc,
+                                 int64_t count, float* __restrict__ diff, int64_t* __restrict__ idx) {
     int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q < count) {
-        unsigned long long k = keys[q];
-        diff[q] = __uint_as_float((unsigned int)(k >> 32));
-        idx[q] = (int64_t)(unsigned int)(k & 0xffffffffull);
+        const unsigned long long k = keys[q];
+        const int o = desc[q].orig;
+        diff[o] = __uint_as_float((unsigned int)(k >> 32));
+        idx[o] = (int64_t)(unsigned int)(k & 0xffffffffull);
     }
 }
 
@@ -290,10 +363,15 @@ int grow(T** p, int64_t* cap, int64_t need, bool pinned = false) {
     return SB_OK;
 }
 
-// Validate + plan a batch on the host. Fills c.h_desc[0..count).
+// Validate + plan a batch on the host.  Fills c.h_desc[0..count) in PROCESSING order: first the queries
+// whose multiply runs inside the fused kernel, then (from *n_direct on) those routed through the
+// register-blocked multiply kernel.  The route depends only on the query itself (its partition count),
+// never on what else is in the batch, so a given (template, position) always takes the same arithmetic
+// path.  QueryDesc::orig maps back to the caller's order; curve offsets follow the caller's order.
 int plan_batch(const sb_stream* image, const sb_stream* tmpl, int64_t count,
-               const int64_t* toff, const int64_t* tlen, const int64_t* lag0, const int64_t* nlags, int hd,
-               int64_t* total_items, int64_t* total_parts, int64_t* max_query_parts) {
+               const int64_t* toff, const int64_t* tlen, const int64_t* lag0, const int64_t* nlags,
+               int hd, bool allow_blocked, int64_t* n_direct_out,
+               int64_t* total_items, int64_t* total_parts, int64_t* total_groups, int64_t* max_query_parts) {
     Ctx& c = ctx();
     const int B = c.B;
     const int64_t H = B / hd, LB = 2 * (int64_t)B - H;     // partition length / hop, lags per item
@@ -303,24 +381,42 @@ int plan_batch(const sb_stream* image, const sb_stream* tmpl, int64_t count,
         SB_CUDA(cudaMallocHost((void**)&c.h_desc, sizeof(QueryDesc) * std::max<int64_t>(count, 64)));
         c.h_desc_cap = std::max<int64_t>(count, 64);
     }
-    int64_t items = 0, parts = 0, maxp = 0, curve_total = 0;
+    auto blocked = [&](int64_t n) {
+        if (!allow_blocked || c.premac_mode == 1) return false;
+        return c.premac_mode == 2 || (n + H - 1) / H >= 3;
+    };
+    int64_t n_direct = 0;
     for (int64_t q = 0; q < count; ++q) {
         const int64_t n = tlen[q], L = nlags[q], o = toff[q], s = lag0[q];
         if (n < 1 || L < 1) SB_FAIL(SB_EINVAL, "query %lld: template length %lld / lag count %lld must be >= 1", (long long)q, (long long)n, (long long)L);
         if (o < 0 || o + n > tmpl->n) SB_FAIL(SB_EINVAL, "query %lld: template [%lld,+%lld) outside template stream of %lld samples", (long long)q, (long long)o, (long long)n, (long long)tmpl->n);
         if (s < 0 || s + L - 1 + n > image->n) SB_FAIL(SB_EINVAL, "query %lld: search span [%lld,+%lld)+%lld outside image stream of %lld samples", (long long)q, (long long)s, (long long)L, (long long)n, (long long)image->n);
         if (L > 0xffffffffll) SB_FAIL(SB_EINVAL, "query %lld: more than 2^32 lags", (long long)q);
-        QueryDesc& d = c.h_desc[q];
-        d.toff = o; d.tlen = n; d.lag0 = s; d.nlags = L;
-        d.P = (int32_t)((n + H - 1) / H);
-        d.k0 = (int32_t)(s / LB);
-        d.nk = (int32_t)((s + L - 1) / LB - d.k0 + 1);
-        d.itemBase = items; d.partBase = parts; d.pad_ = 0; d.curveOff = curve_total;
-        curve_total += L;
-        items += d.nk; parts += d.P;
-        maxp = std::max<int64_t>(maxp, d.P);
+        if (!blocked(n)) ++n_direct;
     }
-    *total_items = items; *total_parts = parts; *max_query_parts = maxp;
+    int64_t items = 0, parts = 0, maxp = 0, groups = 0;
+    int64_t pos_direct = 0, pos_blocked = n_direct;
+    // two passes so that the running totals follow the processing order
+    for (int cls = 0; cls < 2; ++cls) {
+        int64_t curve_total = 0;
+        for (int64_t q = 0; q < count; ++q) {
+            const int64_t n = tlen[q], L = nlags[q], s = lag0[q];
+            if ((blocked(n) ? 1 : 0) == cls) {
+                QueryDesc& d = c.h_desc[cls == 0 ? pos_direct++ : pos_blocked++];
+                d.toff = toff[q]; d.tlen = n; d.lag0 = s; d.nlags = L;
+                d.P = (int32_t)((n + H - 1) / H);
+                d.k0 = (int32_t)(s / LB);
+                d.nk = (int32_t)((s + L - 1) / LB - d.k0 + 1);
+                d.itemBase = items; d.partBase = parts; d.orig = (int32_t)q; d.curveOff = curve_total; d.groupBase = groups;
+                groups += (d.nk + MAC_GROUP - 1) / MAC_GROUP;
+                items += d.nk; parts += d.P;
+                maxp = std::max<int64_t>(maxp, d.P);
+            }
+            curve_total += L;
+        }
+    }
+    *n_direct_out = n_direct;
+    *total_items = items; *total_parts = parts; *total_groups = groups; *max_query_parts = maxp;
     return SB_OK;
 }
 
@@ -331,6 +427,7 @@ int run_batch(const sb_stream* image_c, const sb_stream* tmpl, int64_t count,
     Ctx& c = ctx();
     sb_stream* image = const_cast<sb_stream*>(image_c);
     if (image->dtype != tmpl->dtype) SB_FAIL(SB_EINVAL, "image and template streams differ in sample type");
+    if (count > 0x7fffffffll) SB_FAIL(SB_EINVAL, "more than 2^31 queries in one batch");
     const int B = c.B, nb = B + 1;
     const bool use_fused = c.engine == 1 && fused_supports(B);
     // Geometry of the fused engine.  hop B (default): half of every 2B-point inverse FFT is valid lags,
@@ -347,8 +444,12 @@ int run_batch(const sb_stream* image_c, const sb_stream* tmpl, int64_t count,
             if (longest <= B / 2) hd = 2;
         }
     }
-    int64_t total_items = 0, total_parts = 0, maxp = 0;
-    SB_TRY(plan_batch(image, tmpl, count, toff, tlen, lag0, nlags, hd, &total_items, &total_parts, &maxp));
+    // Multiply strategy per query: inside the fused kernel (2 loads per multiply-accumulate, nothing through
+    // HBM), or -- from 3 partitions per template -- the register-blocked kernel k_mac_blocked over
+    // MAC_GROUP lag blocks, whose products the fused kernel then reads from a chunk buffer.
+    int64_t n_direct = 0, total_items = 0, total_parts = 0, total_groups = 0, maxp = 0;
+    SB_TRY(plan_batch(image, tmpl, count, toff, tlen, lag0, nlags, hd, use_fused && hd == 1, &n_direct,
+                      &total_items, &total_parts, &total_groups, &maxp));
     SB_TRY(ensure_spectra(image, hd));
 
     SB_TRY(grow(&c.d_desc, &c.desc_cap, count));
@@ -361,19 +462,23 @@ int run_batch(const sb_stream* image_c, const sb_stream* tmpl, int64_t count,
     SB_TRY(grow(&c.d_parts, &c.parts_cap, parts_cap_want * nb));
     const int64_t chunk = std::min<int64_t>(c.chunk_items, total_items);
     if (!use_fused) SB_TRY(grow(&c.d_items, &c.items_cap, chunk * nb));
+    const int64_t premac_chunk = 4096;               // items per product buffer (0.5 GB at B = 16384)
 
     const int gchunks = (2 * B + 2047) / 2048;
     const int mchunks = (nb + MAC_BINS - 1) / MAC_BINS;
     const int nchunks = (B + NORM_LAGS - 1) / NORM_LAGS;
 
-    // super-chunks of whole queries whose partition spectra fit the parts buffer
-    int64_t qb = 0;
-    while (qb < count) {
+    // the two query classes, each in super-chunks of whole queries whose partition spectra fit the buffer
+    for (int cls = 0; cls < 2; ++cls) {
+    const int64_t q_lo = cls == 0 ? 0 : n_direct, q_hi = cls == 0 ? n_direct : count;
+    const bool premac = cls == 1;
+    int64_t qb = q_lo;
+    while (qb < q_hi) {
         int64_t qe = qb, np = 0;
-        while (qe < count && np + c.h_desc[qe].P <= parts_cap_want) { np += c.h_desc[qe].P; ++qe; }
+        while (qe < q_hi && np + c.h_desc[qe].P <= parts_cap_want) { np += c.h_desc[qe].P; ++qe; }
         if (qe == qb) SB_FAIL(SB_ENOMEM, "internal: partition buffer too small");
         const int64_t part_first = c.h_desc[qb].partBase;
-        // 1. template partitions -> spectra (in place)
+        // 1. template partitions -> spectra
         const int64_t sub = 4096;
         if (use_fused) {                             // hand-written gather + forward FFT, one launch
             ProfScope ps("part_spectra");
@@ -401,10 +506,33 @@ int run_batch(const sb_stream* image_c, const sb_stream* tmpl, int64_t count,
         // 2. items of these queries
         const int64_t item_lo = c.h_desc[qb].itemBase;
         const int64_t item_hi = (qe < count) ? c.h_desc[qe].itemBase : total_items;
-        if (use_fused) {
+        if (use_fused && !premac) {
             ProfScope ps("match_fused");
-            SB_TRY(launch_match_fused(image, tmpl, hd, c.d_parts, part_first, c.d_desc, (int)qb, (int)qe,
+            SB_TRY(launch_match_fused(image, tmpl, hd, c.d_parts, part_first, nullptr, c.d_desc, (int)qb, (int)qe,
                                       item_lo, item_hi - item_lo, c.d_keys, d_curve));
+        } else if (use_fused) {
+            int64_t qa = qb;
+            while (qa < qe) {
+                int64_t qz = qa, ni = 0;
+                while (qz < qe && (qz == qa || ni + c.h_desc[qz].nk <= premac_chunk)) { ni += c.h_desc[qz].nk; ++qz; }
+                const int64_t i0 = c.h_desc[qa].itemBase, g0 = c.h_desc[qa].groupBase;
+                const int64_t ngroups = ((qz < count) ? c.h_desc[qz].groupBase : total_groups) - g0;
+                SB_TRY(grow(&c.d_items, &c.items_cap, ni * nb));
+                SB_TRY(grow(&c.d_groups, &c.groups_cap, ngroups));
+                const int gch = (nb + MACB_BINS - 1) / MACB_BINS;
+                {
+                    ProfScope ps("mac_blocked", 2);
+                    k_fill_groups<<<(unsigned)(qz - qa), 128, 0, c.stream>>>(c.d_desc, (int)qa, g0, c.d_groups);
+                    k_mac_blocked<<<(unsigned)(ngroups * gch), MACB_THREADS, 0, c.stream>>>(
+                        c.d_parts, part_first, image->d_spec, image->nblk, c.d_desc, c.d_groups, i0, B, c.d_items, gch);
+                }
+                {
+                    ProfScope ps("match_fused");
+                    SB_TRY(launch_match_fused(image, tmpl, hd, c.d_parts, part_first, c.d_items, c.d_desc, (int)qa, (int)qz,
+                                              i0, ni, c.d_keys, d_curve));
+                }
+                qa = qz;
+            }
         } else
         for (int64_t i0 = item_lo; i0 < item_hi; i0 += chunk) {
             const int64_t ni = std::min<int64_t>(chunk, item_hi - i0);
@@ -435,9 +563,10 @@ int run_batch(const sb_stream* image_c, const sb_stream* tmpl, int64_t count,
         }
         qb = qe;
     }
+    }
     {
         ProfScope ps("unpack_results");
-        k_unpack_results<<<(unsigned)((count + 255) / 256), 256, 0, c.stream>>>(c.d_keys, count, d_diff, d_idx);
+        k_unpack_results<<<(unsigned)((count + 255) / 256), 256, 0, c.stream>>>(c.d_keys, c.d_desc, count, d_diff, d_idx);
     }
     SB_CUDA(cudaGetLastError());
     return SB_OK;

@@ -92,23 +92,26 @@ def test_fused_engine_equals_cufft_engine(gpu_lib, pair, stype, block):
         lag0, nlags = 70000, 150001
         curves, results = [], []
         # (engine, hop mode): the cuFFT pipeline, then the fused kernel in both overlap-save geometries
-        variants = [(0, 1), (1, 1), (1, 2)]
-        for engine, hop in variants:
+        # + the fused kernel fed by the register-blocked multiply kernel (premac 2 = for every query)
+        variants = [(0, 1, 1), (1, 1, 1), (1, 2, 1), (1, 1, 2)]
+        for engine, hop, premac in variants:
             _native.check(gpu_lib.sb_set_engine(engine))
             _native.check(gpu_lib.sb_set_hop_mode(hop))
+            _native.check(gpu_lib.sb_set_premac_mode(premac))
             curves.append(dst.match_curve(src, toff, n, lag0, nlags))
             results.append(dst.find_planned(src, [toff, toff + 5000, 100], [n, 3000, 48000],
                                             [lag0, 1000, 0], [nlags, 300000, 200000]))
             # the batch result is the first-index minimum of the variant's own curve
             d, i = dst.find_planned(src, [toff], [n], [lag0], [nlags])
             assert i[0] == int(curves[-1].argmin()) and d[0] == curves[-1].min()
-        for e in (1, 2):
+        for e in (1, 2, 3):
             assert np.abs(curves[0] - curves[e]).max() <= 2e-6
             assert np.abs(results[0][0] - results[e][0]).max() <= 2e-6
             assert np.abs(results[0][1] - results[e][1]).max() <= 1
     finally:
         _native.check(gpu_lib.sb_set_engine(1))
         _native.check(gpu_lib.sb_set_hop_mode(1))
+        _native.check(gpu_lib.sb_set_premac_mode(0))
         _native.check(gpu_lib.sb_set_block_size(16384))
 
 
@@ -312,13 +315,14 @@ def test_empty_batch_is_a_no_op(gpu_lib, pair):
     assert len(d) == 0 and len(i) == 0
 
 
-@pytest.mark.parametrize('engine', [0, 1, 2])
+@pytest.mark.parametrize('engine', [0, 1, 2, 3])
 def test_minimum_sizes_and_ragged_edges(gpu_lib, engine):
     """n = 1 templates, single-lag searches, streams shorter than one lag block, searches that end on
     the last sample, spans that straddle exactly one block boundary."""
     rng = np.random.default_rng(engine)
-    _native.check(gpu_lib.sb_set_engine(min(engine, 1)))          # 2 = fused kernel at hop B/2
+    _native.check(gpu_lib.sb_set_engine(min(engine, 1)))          # 2 = fused kernel at hop B/2, 3 = blocked multiply
     _native.check(gpu_lib.sb_set_hop_mode(2 if engine == 2 else 1))
+    _native.check(gpu_lib.sb_set_premac_mode(2 if engine == 3 else 1))
     try:
         for total in (7, 1000, 16384, 16385, 40000):
             img = rng.integers(0, 256, total, dtype=np.uint8)
@@ -343,6 +347,7 @@ def test_minimum_sizes_and_ragged_edges(gpu_lib, engine):
     finally:
         _native.check(gpu_lib.sb_set_engine(1))
         _native.check(gpu_lib.sb_set_hop_mode(1))
+        _native.check(gpu_lib.sb_set_premac_mode(0))
 
 
 def test_batch_split_into_several_passes(gpu_lib, pair):
@@ -393,3 +398,24 @@ def test_values_do_not_depend_on_the_query_range(gpu_lib, pair):
     # whole curves of sub-ranges are slices of the wide curve
     curves = dst.match_curves(src, [toff, toff], [n, n], [lo + 5, lo + 77777], [1000, 40001])
     assert np.array_equal(curves[0], wide[5:1005]) and np.array_equal(curves[1], wide[77777:77777 + 40001])
+
+
+def test_mixed_batch_routes_per_query_and_keeps_caller_order(gpu_lib, pair):
+    """A batch mixing short templates (multiply inside the fused kernel) and long ones (>= 3 partitions:
+    register-blocked multiply kernel) is processed class by class but returns results in the caller's
+    order, and each query's answer equals its answer when asked alone."""
+    rs, rd, src, dst = pair['uint8']
+    starts = np.array([1.0, 2.0, 3.5, 5.0, 6.0, 8.0, 9.5, 11.0])
+    lens = np.array([0.5, 4.5, 1.0, 6.0, 0.2, 3.0, 9.0, 2.0])          # 4.5 s, 6 s, 9 s -> 4, 5, 7 partitions
+    ends = starts + lens
+    centers, windows = starts + 1.0, np.full(len(starts), 10.0)
+    batch = dst.find_substream_batch(src, starts, ends, centers, windows)
+    for q in range(len(starts)):
+        d, t = dst.find_substream(src.get_substream(starts[q], ends[q]), centers[q], windows[q])
+        assert d == batch[0][q] and t == batch[1][q], q
+        d_ref, t_ref = rd.find_substream(rs.get_substream(starts[q], ends[q]), centers[q], windows[q])
+        assert abs(float(d) - float(d_ref)) <= DIFF_TOL and abs(t - t_ref) <= SHIFT_TOL
+    toff, tlen, lag0, nlags, _ = dst.plan_queries(src, starts, ends, centers, windows)
+    curves = dst.match_curves(src, toff, tlen, lag0, nlags)
+    for q in range(len(starts)):
+        assert len(curves[q]) == nlags[q] and curves[q].min() == batch[0][q]

@@ -22,6 +22,7 @@ ap.add_argument('--duration', type=float, default=1800.0)
 ap.add_argument('--sample-type', default='uint8')
 ap.add_argument('--reps', type=int, default=3)
 ap.add_argument('--hop-mode', type=int, default=1)
+ap.add_argument('--premac-mode', type=int, default=0)
 ap.add_argument('--events', default='0.5,1,3,10,30')
 ap.add_argument('--windows', default='5,10,30,60,120,300,600')
 a = ap.parse_args()
@@ -36,6 +37,7 @@ src = WavStream.from_pcm(src_pcm, 12000, sample_type=a.sample_type)
 dst = WavStream.from_pcm(dst_pcm, 12000, sample_type=a.sample_type)
 lib = _native.lib()
 _native.check(lib.sb_set_hop_mode(a.hop_mode))
+_native.check(lib.sb_set_premac_mode(a.premac_mode))
 EV = [float(x) for x in a.events.split(',')]
 WIN = [float(x) for x in a.windows.split(',')]
 bps = 1 if a.sample_type == 'uint8' else 4
