@@ -134,61 +134,58 @@ __global__ void k_fill_groups(const QueryDesc* __restrict__ desc, int q_begin, i
 }
 
 constexpr int MACB_THREADS = 256;
-constexpr int MACB_BINS = 2 * MACB_THREADS;         // two bins per thread
-__global__ void __launch_bounds__(MACB_THREADS)
+constexpr int MACB_BINS = MACB_THREADS;             // one bin per thread: ~64 registers, 32 warps per SM
+constexpr int MACB_AHEAD = 3;                       // spectrum / template rows requested this many steps early
+__global__ void __launch_bounds__(MACB_THREADS, 4)
 k_mac_blocked(const float2* __restrict__ That, int64_t part_first, const float2* __restrict__ Xhat, int64_t nblk,
               const QueryDesc* __restrict__ desc, const int2* __restrict__ groups, int64_t item_first,
               int B, float2* __restrict__ Y, int chunks_per_group) {
-    constexpr int G = MAC_GROUP;
+    constexpr int G = MAC_GROUP, D = MACB_AHEAD, RS = G + D;     // ring of RS spectrum values: slot r % RS holds row k0 + r
     const int2 grp = groups[blockIdx.x / chunks_per_group];
     const int chunk = blockIdx.x % chunks_per_group;
     const QueryDesc d = desc[grp.x];
     const int64_t k0 = d.k0 + grp.y;
     const int ng = min(G, d.nk - grp.y);
     const int nb = B + 1;
-    const int b0 = chunk * MACB_BINS + threadIdx.x, b1 = b0 + MACB_THREADS;
-    const bool ok0 = b0 < nb, ok1 = b1 < nb;
+    const int b0 = chunk * MACB_BINS + threadIdx.x;
+    if (b0 >= nb) return;
     const float2 zero = make_float2(0.f, 0.f);
-    const float2* tp = That + (d.partBase - part_first) * (int64_t)nb;
-    float2 acc0[G], acc1[G], x0[G], x1[G];
-#pragma unroll
-    for (int g = 0; g < G; ++g) {
-        acc0[g] = zero; acc1[g] = zero;
-        const int64_t row = k0 + g;
-        const float2* xr = Xhat + row * (int64_t)nb;
-        x0[g] = (ok0 && row < nblk) ? __ldg(xr + b0) : zero;
-        x1[g] = (ok1 && row < nblk) ? __ldg(xr + b1) : zero;
-    }
+    const float2* tp = That + (d.partBase - part_first) * (int64_t)nb + b0;
+    const float2* xp = Xhat + k0 * (int64_t)nb + b0;
     const int P = d.P;
-    for (int p0 = 0; p0 < P; p0 += G) {
+    const int64_t rows_left = nblk - k0;               // rows k0 + r with r >= rows_left are past the stream: zero
+    float2 acc[G], x[RS], t[D + 1];
 #pragma unroll
-        for (int s = 0; s < G; ++s) {
+    for (int g = 0; g < G; ++g) acc[g] = zero;
+#pragma unroll
+    for (int r = 0; r < RS - 1; ++r) x[r] = r < rows_left ? __ldg(xp + (int64_t)r * nb) : zero;   // rows 0 .. G+D-2
+    x[RS - 1] = zero;
+#pragma unroll
+    for (int i = 0; i < D; ++i) t[i] = i < P ? __ldg(tp + (int64_t)i * nb) : zero;
+    t[D] = zero;
+    // steps are unrolled RS*(D+1) at a time so that every ring index is a compile-time constant
+    for (int p0 = 0; p0 < P; p0 += RS * (D + 1)) {
+#pragma unroll
+        for (int s = 0; s < RS * (D + 1); ++s) {
             const int p = p0 + s;
             if (p < P) {                               // uniform over the CTA
-                const float2* t = tp + (int64_t)p * nb;
-                const float2 t0 = ok0 ? __ldg(t + b0) : zero, t1 = ok1 ? __ldg(t + b1) : zero;
-                const int64_t nrow = k0 + p + G;       // the row that enters the ring after this step
-                const float2* xr = Xhat + nrow * (int64_t)nb;
-                const float2 n0 = (ok0 && nrow < nblk) ? __ldg(xr + b0) : zero;
-                const float2 n1 = (ok1 && nrow < nblk) ? __ldg(xr + b1) : zero;
+                // request what step p + D will need: row p+G+D-1 (into the slot of row p-1, now dead) and T^[p+D]
+                const int64_t nr = (int64_t)p + G + D - 1;
+                x[(s + G + D - 1) % RS] = nr < rows_left ? __ldg(xp + nr * nb) : zero;
+                t[(s + D) % (D + 1)] = p + D < P ? __ldg(tp + (int64_t)(p + D) * nb) : zero;
+                const float2 tv = t[s % (D + 1)];
 #pragma unroll
-                for (int g = 0; g < G; ++g) {          // slot (g+s)%G holds row k0+g+p
-                    const float2 a = x0[(g + s) % G], b = x1[(g + s) % G];
-                    acc0[g].x += t0.x * a.x + t0.y * a.y;  acc0[g].y += t0.x * a.y - t0.y * a.x;
-                    acc1[g].x += t1.x * b.x + t1.y * b.y;  acc1[g].y += t1.x * b.y - t1.y * b.x;
+                for (int g = 0; g < G; ++g) {          // block g at step p multiplies row k0 + g + p
+                    const float2 a = x[(s + g) % RS];
+                    acc[g].x += tv.x * a.x + tv.y * a.y;  acc[g].y += tv.x * a.y - tv.y * a.x;
                 }
-                x0[s % G] = n0; x1[s % G] = n1;        // row k0+p leaves, row k0+p+G enters
             }
         }
     }
-    float2* y = Y + (d.itemBase + grp.y - item_first) * (int64_t)nb;
+    float2* y = Y + (d.itemBase + grp.y - item_first) * (int64_t)nb + b0;
 #pragma unroll
-    for (int g = 0; g < G; ++g) {
-        if (g < ng) {
-            if (ok0) y[(int64_t)g * nb + b0] = acc0[g];
-            if (ok1) y[(int64_t)g * nb + b1] = acc1[g];
-        }
-    }
+    for (int g = 0; g < G; ++g)
+        if (g < ng) y[(int64_t)g * nb] = acc[g];
 }
 
 // ---- normalise + argmin ----------------------------------------------------------
