@@ -76,9 +76,9 @@ int sb_get_block_size(void);
 int sb_set_engine(int engine);
 int sb_get_engine(void);
 /* Spectral multiply of the fused engine: 0 (default) = per lag block inside the fused kernel, except for
- * batches whose templates average 3 or more partitions, which go through the register-blocked
- * multiply kernel (8 lag blocks share each template row); 1 = never blocked, 2 = always blocked.
- * Same arithmetic in a different summation layout: results agree to float32 rounding. */
+ * queries whose template spans 12 or more partitions (>= 16 s at the default block size), which go
+ * through the register-blocked multiply kernel (8 lag blocks share each template row); 1 = never
+ * blocked, 2 = always blocked.  The route depends only on the query, not on the rest of the batch. */
 int sb_set_premac_mode(int mode);
 /* Overlap-save geometry of the fused engine: 1 (default) = hop B (half of each inverse FFT is valid
  * lags), 2 = hop B/2 (three quarters valid, but twice as many template partitions to multiply:

@@ -125,7 +125,7 @@ k_spectral_mac(const float2* __restrict__ That, int64_t part_first, const float2
 // step p needs spectrum row k0+g+p, so a ring of G row values slides by one row per step and each
 // step costs one template load and ONE new spectrum load per bin for G multiply-accumulates (the
 // per-item kernel loads 2 per multiply-accumulate).  Y[item][bin] goes to a buffer the fused kernel
-// then reads instead of multiplying itself.  Pays from about 3 partitions per template.
+// then reads instead of multiplying itself.  Rows are requested MACB_AHEAD steps early.
 __global__ void k_fill_groups(const QueryDesc* __restrict__ desc, int q_begin, int64_t group_first, int2* __restrict__ groups) {
     const int q = q_begin + blockIdx.x;
     const int64_t base = desc[q].groupBase - group_first;
@@ -360,6 +360,12 @@ int grow(T** p, int64_t* cap, int64_t need, bool pinned = false) {
     return SB_OK;
 }
 
+// Partition count from which a query goes through k_mac_blocked.  The blocked kernel moves ~5x fewer
+// spectrum bytes per lag block, but its products make a round trip through HBM (2 x 131 KB per block)
+// before the FFT: measured break-even near 10 partitions (profiles/README.md: -28 % at 3, -9 % at 8,
+// +31 % at 22 partitions).
+constexpr int64_t kBlockedFromPartitions = 12;
+
 // Validate + plan a batch on the host.  Fills c.h_desc[0..count) in PROCESSING order: first the queries
 // whose multiply runs inside the fused kernel, then (from *n_direct on) those routed through the
 // register-blocked multiply kernel.  The route depends only on the query itself (its partition count),
@@ -380,7 +386,7 @@ int plan_batch(const sb_stream* image, const sb_stream* tmpl, int64_t count,
     }
     auto blocked = [&](int64_t n) {
         if (!allow_blocked || c.premac_mode == 1) return false;
-        return c.premac_mode == 2 || (n + H - 1) / H >= 3;
+        return c.premac_mode == 2 || (n + H - 1) / H >= kBlockedFromPartitions;
     };
     int64_t n_direct = 0;
     for (int64_t q = 0; q < count; ++q) {
@@ -442,8 +448,8 @@ int run_batch(const sb_stream* image_c, const sb_stream* tmpl, int64_t count,
         }
     }
     // Multiply strategy per query: inside the fused kernel (2 loads per multiply-accumulate, nothing through
-    // HBM), or -- from 3 partitions per template -- the register-blocked kernel k_mac_blocked over
-    // MAC_GROUP lag blocks, whose products the fused kernel then reads from a chunk buffer.
+    // HBM), or -- for very long templates (kBlockedFromPartitions) -- the register-blocked kernel
+    // k_mac_blocked over MAC_GROUP lag blocks, whose products the fused kernel then reads from a chunk buffer.
     int64_t n_direct = 0, total_items = 0, total_parts = 0, total_groups = 0, maxp = 0;
     SB_TRY(plan_batch(image, tmpl, count, toff, tlen, lag0, nlags, hd, use_fused && hd == 1, &n_direct,
                       &total_items, &total_parts, &total_groups, &maxp));

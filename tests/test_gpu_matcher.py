@@ -401,21 +401,25 @@ def test_values_do_not_depend_on_the_query_range(gpu_lib, pair):
 
 
 def test_mixed_batch_routes_per_query_and_keeps_caller_order(gpu_lib, pair):
-    """A batch mixing short templates (multiply inside the fused kernel) and long ones (>= 3 partitions:
-    register-blocked multiply kernel) is processed class by class but returns results in the caller's
-    order, and each query's answer equals its answer when asked alone."""
+    """A batch mixing short templates (multiply inside the fused kernel) and very long ones (>= 12
+    partitions: register-blocked multiply kernel) is processed class by class but returns results in
+    the caller's order, and each query's answer equals, bit for bit, its answer when asked alone."""
     rs, rd, src, dst = pair['uint8']
     starts = np.array([1.0, 2.0, 3.5, 5.0, 6.0, 8.0, 9.5, 11.0])
-    lens = np.array([0.5, 4.5, 1.0, 6.0, 0.2, 3.0, 9.0, 2.0])          # 4.5 s, 6 s, 9 s -> 4, 5, 7 partitions
+    lens = np.array([0.5, 9.0, 1.0, 10.5, 0.2, 3.0, 12.0, 2.0])        # at B = 8192: 9 / 10.5 / 12 s -> 14 / 16 / 18 partitions
     ends = starts + lens
     centers, windows = starts + 1.0, np.full(len(starts), 10.0)
-    batch = dst.find_substream_batch(src, starts, ends, centers, windows)
-    for q in range(len(starts)):
-        d, t = dst.find_substream(src.get_substream(starts[q], ends[q]), centers[q], windows[q])
-        assert d == batch[0][q] and t == batch[1][q], q
-        d_ref, t_ref = rd.find_substream(rs.get_substream(starts[q], ends[q]), centers[q], windows[q])
-        assert abs(float(d) - float(d_ref)) <= DIFF_TOL and abs(t - t_ref) <= SHIFT_TOL
-    toff, tlen, lag0, nlags, _ = dst.plan_queries(src, starts, ends, centers, windows)
-    curves = dst.match_curves(src, toff, tlen, lag0, nlags)
-    for q in range(len(starts)):
-        assert len(curves[q]) == nlags[q] and curves[q].min() == batch[0][q]
+    _native.check(gpu_lib.sb_set_block_size(8192))
+    try:
+        batch = dst.find_substream_batch(src, starts, ends, centers, windows)
+        for q in range(len(starts)):
+            d, t = dst.find_substream(src.get_substream(starts[q], ends[q]), centers[q], windows[q])
+            assert d == batch[0][q] and t == batch[1][q], q
+            d_ref, t_ref = rd.find_substream(rs.get_substream(starts[q], ends[q]), centers[q], windows[q])
+            assert abs(float(d) - float(d_ref)) <= DIFF_TOL and abs(t - t_ref) <= SHIFT_TOL
+        toff, tlen, lag0, nlags, _ = dst.plan_queries(src, starts, ends, centers, windows)
+        curves = dst.match_curves(src, toff, tlen, lag0, nlags)
+        for q in range(len(starts)):
+            assert len(curves[q]) == nlags[q] and curves[q].min() == batch[0][q]
+    finally:
+        _native.check(gpu_lib.sb_set_block_size(16384))
