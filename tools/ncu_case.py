@@ -20,6 +20,10 @@ ap.add_argument('--batches', type=int, default=3)
 ap.add_argument('--engine', type=int, default=1)
 ap.add_argument('--block', type=int, default=16384)
 ap.add_argument('--sample-type', default='uint8')
+ap.add_argument('--hop-mode', type=int, default=1)
+ap.add_argument('--premac-mode', type=int, default=0)
+ap.add_argument('--min-len', type=float, default=1.0)
+ap.add_argument('--max-len', type=float, default=4.0)
 a = ap.parse_args()
 
 src_pcm, dst_pcm = synth.make_pair(a.duration, 2, 1.5)
@@ -28,7 +32,9 @@ dst = WavStream.from_pcm(dst_pcm, 12000, sample_type=a.sample_type)
 lib = _native.lib()
 _native.check(lib.sb_set_block_size(a.block))
 _native.check(lib.sb_set_engine(a.engine))
-starts, ends = synth.make_events(a.events, a.duration, 2)
+_native.check(lib.sb_set_hop_mode(a.hop_mode))
+_native.check(lib.sb_set_premac_mode(a.premac_mode))
+starts, ends = synth.make_events(a.events, a.duration, 2, a.min_len, a.max_len)
 for _ in range(a.batches):
     d, t = dst.find_substream_batch(src, starts, ends, starts, np.full(len(starts), a.window))
 ok = (ends + 1.5 < a.duration)
