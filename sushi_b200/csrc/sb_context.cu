@@ -179,6 +179,7 @@ int sb_shutdown(void) {
     drop_plans();
     pool_release_all();
     fused_release_tables();
+    packed_release_tables();
     cudaFree(c.d_parts); cudaFree(c.d_items); cudaFree(c.d_desc); cudaFree(c.d_keys); cudaFree(c.d_groups);
     cudaFree(c.d_diff); cudaFree(c.d_idx);
     cudaFreeHost(c.h_desc); cudaFreeHost(c.h_diff); cudaFreeHost(c.h_idx);
@@ -212,7 +213,7 @@ int sb_set_block_size(int block) {
 }
 int sb_get_block_size(void) { return ctx().B; }
 int sb_set_engine(int engine) {
-    if (engine != 0 && engine != 1) SB_FAIL(SB_EINVAL, "sb_set_engine: %d is neither 0 (cuFFT pipeline) nor 1 (fused kernel)", engine);
+    if (engine < 0 || engine > 2) SB_FAIL(SB_EINVAL, "sb_set_engine: %d is not 0 (cuFFT pipeline), 1 (fused kernel) or 2 (packed fused kernel)", engine);
     ctx().engine = engine;
     return SB_OK;
 }

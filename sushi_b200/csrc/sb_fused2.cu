@@ -1,0 +1,708 @@
+// Packed fused lag-block kernel (engine 2): the same per-item pipeline as sb_fused.cu
+//   spectral multiply-accumulate -> Hermitian packing -> inverse FFT in shared memory -> window sums,
+//   fp32 screening, fp64 evaluation of the lags that can win -> one 64-bit atomicMin
+// rebuilt around Blackwell's two-wide fp32 instructions (FFMA2 / FADD2 / FMUL2).  sb_fused.cu is bound by
+// instruction issue in its FFT and epilogue phases; here every value the kernel touches is one half of a
+// float2 whose two halves go through identical arithmetic, so one issued instruction does the work of two:
+//
+//  * Spectra are stored in a "quad" layout: 16-byte chunks A[i] = (re X[i], re X[i+B/2], im X[i], im X[i+B/2])
+//    and M[i] = (re X[B-i], re X[B/2-i], im X[B-i], im X[B/2-i]), i = 0 .. B/4.  One LDG.128 per operand
+//    feeds four FFMA2 for two bins; the Hermitian packing of bins (i, B-i) and (i+B/2, B/2-i) is elementwise
+//    on those pairs.
+//  * The first radix-2 step of the inverse FFT (decimation in frequency) is done on the packed pair itself:
+//    u[i] = Z[i] + Z[i+B/2], v[i] = (Z[i] - Z[i+B/2]) * W^i.  u and v are two INDEPENDENT half-size
+//    transforms with identical twiddles, X[2o] = FFT(u)[o], X[2o+1] = FFT(v)[o]; they travel together as
+//    chunks (u.re, v.re, u.im, v.im) through three radix-16 Stockham passes (LDS.128 / STS.128, shared
+//    twiddles as scalar-broadcast operands), and the last radix-2 step (of which only the "+" half carries
+//    valid lags) is folded into the epilogue.
+//  * Twiddles of the packing stage are formed in registers from one per-thread base value, so the 64 KB
+//    table sb_fused.cu streams from L2 for every item is gone; spectrum rows are 128-byte aligned.
+// Values agree with sb_fused.cu / the cuFFT engine to fp32 FFT rounding (~1e-7 of the curve).
+#include "sb_internal.h"
+#include <cmath>
+#include <cstdlib>
+#include <vector>
+
+#include "sb_fused_common.cuh"
+#include "sb_fft_smem.cuh"
+
+using namespace sb;
+using namespace sbf;
+
+namespace {
+
+constexpr int QB = 16384;                 // lags per item = half the real FFT size
+constexpr int QT = 512;                   // threads per CTA
+constexpr int QNW = QT / 32;
+constexpr int QCH = QB / 2;               // chunks in the FFT buffer: u/v pairs of the two half-size transforms
+constexpr int Q4 = QB / 4;                // quads per spectrum row are i = 0 .. Q4
+constexpr int QOFF_M = 4104;              // float4 offset of the M chunks inside a row (128-byte aligned)
+constexpr int QROW = kQuadRowF2 / 2;      // float4 per row
+static_assert(QOFF_M >= Q4 + 1 && QROW >= QOFF_M + Q4 + 1 && (QROW * 16) % 128 == 0 && (QOFF_M * 16) % 128 == 0, "row layout");
+constexpr int QPHYS = QCH + QCH / 16;     // physical chunks of the padded FFT buffer
+
+struct PackedTables {
+    const float4* tw2;    // [8][16]   (W256^(2a*k), W256^((2a+1)*k)) as (c0, s0, c1, s1), k = 0..15   (pass 2)
+    const float4* tw3;    // [8][256]  same with W4096, k = 0..255                                  (pass 3)
+    const float2* w8;     // [4096]    W8192^j                                                       (last radix-2 step)
+    const float2* wb;     // [512]     exp(i*pi*t/B)                                                 (packing, per-thread base)
+};
+
+// exp(+i*pi*u/32), u = 0..7: the packing twiddle of quad i = t + 512u is wb[t] times this
+__device__ constexpr float kC64[8] = {1.0f, 0.99518472667219689f, 0.98078528040323043f, 0.95694033573220882f,
+                                      0.92387953251128674f, 0.88192126434835503f, 0.83146961230254524f, 0.77301045336273696f};
+__device__ constexpr float kS64[8] = {0.0f, 0.098017140329560602f, 0.19509032201612825f, 0.29028467725446233f,
+                                      0.38268343236508978f, 0.47139673682599764f, 0.55557023301960218f, 0.63439328416364549f};
+
+// ---------------------------------------------------------------- packed arithmetic
+struct C2 { float2 r, i; };     // two complex numbers (u, v): r = (u.re, v.re), i = (u.im, v.im)
+
+__device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) { return __fadd2_rn(a, neg2(b)); }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 bc(float s) { return make_float2(s, s); }      // scalar-broadcast operand
+
+__device__ __forceinline__ C2 cadd2(C2 a, C2 b) { return {add2(a.r, b.r), add2(a.i, b.i)}; }
+__device__ __forceinline__ C2 csub2(C2 a, C2 b) { return {sub2(a.r, b.r), sub2(a.i, b.i)}; }
+// both halves times the same complex number (c, s)
+__device__ __forceinline__ C2 cmul_s(C2 a, float c, float s) {
+    C2 o;
+    o.r = fma2(a.r, bc(c), mul2(a.i, bc(-s)));
+    o.i = fma2(a.r, bc(s), mul2(a.i, bc(c)));
+    return o;
+}
+__device__ __forceinline__ C2 from4(float4 v) { return {make_float2(v.x, v.y), make_float2(v.z, v.w)}; }
+__device__ __forceinline__ float4 to4(C2 v) { return make_float4(v.r.x, v.r.y, v.i.x, v.i.y); }
+
+// d * exp(+2*pi*i*q/32), q even and a compile-time constant after unrolling
+__device__ __forceinline__ C2 rot32p(C2 d, int q) {
+    if (q == 0) return d;
+    if (q == 8) return {neg2(d.i), d.r};
+    const float h = 0.70710678118654752f;
+    if (q == 4) return {mul2(sub2(d.r, d.i), bc(h)), mul2(add2(d.r, d.i), bc(h))};
+    if (q == 12) return {mul2(add2(d.r, d.i), bc(-h)), mul2(sub2(d.r, d.i), bc(h))};
+    return cmul_s(d, kC32[q], kS32[q]);
+}
+
+// In-register inverse DFT of 16 points on both halves at once; decimation in frequency, natural order in,
+// bit-reversed order out (index the result through brev<16>).
+__device__ __forceinline__ void dft16p(C2 (&v)[16]) {
+#pragma unroll
+    for (int h = 8; h >= 1; h >>= 1) {
+#pragma unroll
+        for (int g = 0; g < 16; g += 2 * h) {
+#pragma unroll
+            for (int a = 0; a < h; ++a) {
+                const C2 x = v[g + a], y = v[g + a + h];
+                v[g + a] = cadd2(x, y);
+                v[g + a + h] = rot32p(csub2(x, y), a * (16 / h));
+            }
+        }
+    }
+}
+
+// The FFT buffer is two arrays of float2, R[p] = (u.re, v.re) and I[p] = (u.im, v.im), p = phys(c) for chunk c
+// (the register allocator does not keep the two pairs in one aligned quad, so a 128-bit store would cost four
+// MOVs; 64-bit accesses cost none).  One padding slot per 16 chunks makes the stride-16 scatter of pass 1 and
+// the epilogue's reads of chunks 2t, 2t+1 hit sixteen distinct 8-byte banks per half warp.
+__device__ __forceinline__ constexpr int phys(int c) { return c + (c >> 4); }
+struct Buf {
+    float2* r; float2* i;
+    __device__ __forceinline__ C2 ld(int p) const { return {r[p], i[p]}; }
+    __device__ __forceinline__ void st(int p, C2 v) const { r[p] = v.r; i[p] = v.i; }
+};
+
+// spectrum rows are streamed once per item: keep them out of L1 so the twiddle tables stay there
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+
+// ---------------------------------------------------------------- packing of one quad
+// a = (Y[i], Y[i+B/2]), m = (Y[B-i], Y[B/2-i]) as packed pairs, (c, s) = exp(i*pi*i/B).
+// Hermitian packing (the 2B-point real inverse as a B-point complex one):
+//   Z[k] = (Y[k] + conj(Y[B-k])) + i*w^k*(Y[k] - conj(Y[B-k])),  Z[B-k] = conj(e) + i*conj(o)
+// then the first radix-2 step of the B-point inverse FFT, on the pair itself:
+//   u[k] = Z[k] + Z[k+B/2],  v[k] = (Z[k] - Z[k+B/2]) * W^k,  W = exp(2*pi*i/B) = w^2
+// for k = i (from the first slot pair) and k = B/2 - i (from the mirrored pair, W^(B/2-i) = -conj(W^i)).
+__device__ __forceinline__ void pack_quad(float2 aR, float2 aI, float2 mR, float2 mI, float c, float s,
+                                          C2& lo, C2& hi) {
+    const float2 eR = add2(aR, mR), eI = sub2(aI, mI);
+    const float2 dR = sub2(aR, mR), dI = add2(aI, mI);
+    // slot 0 uses w = (c, s), slot 1 uses w^(i+B/2) = i*w = (-s, c)
+    const float2 wR = make_float2(c, -s), wI = make_float2(s, c);
+    const float2 oR = fma2(dR, wR, neg2(mul2(dI, wI)));
+    const float2 oI = fma2(dR, wI, mul2(dI, wR));
+    const float2 zloR = sub2(eR, oI), zloI = add2(eI, oR);       // (Z[i],   Z[i+B/2])
+    const float2 zhiR = add2(eR, oI), zhiI = sub2(oR, eI);       // (Z[B-i], Z[B/2-i])
+    const float c2 = fmaf(c, c, -s * s), s2 = 2.0f * c * s;      // W^i
+    {
+        const float ur = zloR.x + zloR.y, ui = zloI.x + zloI.y;
+        const float dr = zloR.x - zloR.y, di = zloI.x - zloI.y;
+        lo.r = make_float2(ur, dr * c2 - di * s2);  lo.i = make_float2(ui, dr * s2 + di * c2);
+    }
+    {
+        const float ur = zhiR.y + zhiR.x, ui = zhiI.y + zhiI.x;
+        const float dr = zhiR.y - zhiR.x, di = zhiI.y - zhiI.x;
+        hi.r = make_float2(ur, -(dr * c2) - di * s2);  hi.i = make_float2(ui, dr * s2 - di * c2);   // times (-c2, s2)
+    }
+}
+
+// ---------------------------------------------------------------- the kernel
+template <typename S>
+__global__ void __launch_bounds__(QT, 1)
+k_match_packed(const float4* __restrict__ That, int64_t part_first,
+               const float4* __restrict__ Xhat, int64_t nblk,
+               const S* __restrict__ img, int64_t img_n,
+               const double2* __restrict__ ipfx, const double2* __restrict__ tpfx,
+               const QueryDesc* __restrict__ desc, const int* __restrict__ item_query, int64_t item_first,
+               PackedTables tab, unsigned long long* __restrict__ keys, float* __restrict__ curve_out) {
+    constexpr int B = QB, T = QT, NW = QNW, LB = QB;
+    constexpr bool is_u8 = sizeof(S) == 1;
+    const uint8_t* img8 = reinterpret_cast<const uint8_t*>(img);
+    const float* img32 = reinterpret_cast<const float*>(img);
+    constexpr int LAGS_PER_ROUND = T * 8, ROUNDS = LB / LAGS_PER_ROUND;    // 4096, 4
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const Buf buf = {reinterpret_cast<float2*>(smem_raw), reinterpret_cast<float2*>(smem_raw) + QPHYS};   // QPHYS chunks
+    double2* s_base = reinterpret_cast<double2*>(smem_raw + (size_t)QPHYS * 16);   // [ROUNDS][NW][2] exact running sums
+    unsigned char* s_lo = reinterpret_cast<unsigned char*>(s_base + ROUNDS * NW * 2);   // image[j_blk .. +LB+16)
+    unsigned char* s_hi = s_lo + LB + 16;                                  // image[(j_blk+n)&~15 .. +LB+48)
+    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_hi + LB + 48);
+    unsigned long long* s_best = s_bar + 1;                                // [NW]
+    float* s_min = reinterpret_cast<float*>(s_best + NW);                  // [NW]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t item = item_first + blockIdx.x;
+    const int q = __ldg(item_query + blockIdx.x);
+    const QueryDesc d = desc[q];
+    const int64_t k = d.k0 + (item - d.itemBase);
+    const int64_t j_blk = k * LB;
+
+    // ---------------- 0. stage what the epilogue needs (uint8 streams) ----------------------
+    if (is_u8) {
+        const int64_t hi0 = (j_blk + d.tlen) & ~(int64_t)15;
+        const int64_t limit = (img_n + 16) & ~(int64_t)15;               // allocation has 16 bytes of slack
+        if (tid == 0) {
+            int64_t lo_bytes = limit - j_blk; if (lo_bytes > LB + 16) lo_bytes = LB + 16; if (lo_bytes < 0) lo_bytes = 0;
+            int64_t hi_bytes = limit - hi0;   if (hi_bytes > LB + 48) hi_bytes = LB + 48; if (hi_bytes < 0) hi_bytes = 0;
+            mbar_init(s_bar, 1);
+            mbar_expect_tx(s_bar, (unsigned)(lo_bytes + hi_bytes));
+            if (lo_bytes) tma_load_1d(s_lo, img8 + j_blk, (unsigned)lo_bytes, s_bar);
+            if (hi_bytes) tma_load_1d(s_hi, img8 + hi0, (unsigned)hi_bytes, s_bar);
+        }
+        if (tid < ROUNDS * NW * 2) {
+            const int c = tid / (NW * 2), w = (tid >> 1) % NW, which = tid & 1;
+            const int64_t jw = j_blk + c * LAGS_PER_ROUND + w * 256;
+            if (jw < d.lag0 + d.nlags) cp_async16(s_base + tid, ipfx + jw + (which ? d.tlen : 0));
+        }
+    }
+
+    // ---------------- 1+2. spectral multiply-accumulate, packing, first radix-2 step --------
+    {
+        int P = d.P;
+        if (k + P > nblk) P = (int)(nblk - k);        // rows past the end of the stream are zero
+        const float4* tp = That + (d.partBase - part_first) * (int64_t)QROW;
+        const float4* xp = Xhat + k * (int64_t)QROW;
+        const float2 wbase = __ldg(tab.wb + tid);
+        const int tm = (T - tid) & (T - 1);           // mirrored chunks C[B/2 - i] live in thread tm's column
+        const int col = phys(tid), mcol = phys(tm);
+        constexpr int U = 4;                          // quads in flight per thread
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+            const int i0 = tid + half * (U * T);
+            float2 aR[U], aI[U], mR[U], mI[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) { aR[u] = aI[u] = mR[u] = mI[u] = make_float2(0.f, 0.f); }
+#pragma unroll 1
+            for (int p = 0; p < P; ++p) {
+                const float4* t = tp + (int64_t)p * QROW + i0;
+                const float4* x = xp + (int64_t)p * QROW + i0;
+                float4 ta[U], tmm[U], xa[U], xm[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    ta[u] = ldg_stream(t + u * T);  tmm[u] = ldg_stream(t + QOFF_M + u * T);
+                    xa[u] = ldg_stream(x + u * T);  xm[u] = ldg_stream(x + QOFF_M + u * T);
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {       // Y += conj(T) * X on both slots
+                    const C2 tA = from4(ta[u]), xA = from4(xa[u]), tM = from4(tmm[u]), xM = from4(xm[u]);
+                    aR[u] = fma2(tA.r, xA.r, aR[u]);  aR[u] = fma2(tA.i, xA.i, aR[u]);
+                    aI[u] = fma2(tA.r, xA.i, aI[u]);  aI[u] = fma2(neg2(tA.i), xA.r, aI[u]);
+                    mR[u] = fma2(tM.r, xM.r, mR[u]);  mR[u] = fma2(tM.i, xM.i, mR[u]);
+                    mI[u] = fma2(tM.r, xM.i, mI[u]);  mI[u] = fma2(neg2(tM.i), xM.r, mI[u]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int uu = half * U + u;          // i = tid + 512*uu
+                const float c = wbase.x * kC64[uu] - wbase.y * kS64[uu];
+                const float s = wbase.x * kS64[uu] + wbase.y * kC64[uu];
+                C2 lo, hi;
+                pack_quad(aR[u], aI[u], mR[u], mI[u], c, s, lo, hi);
+                buf.st(col + 544 * uu, lo);                       // C[i]
+                // C[B/2 - i]: chunk (T - tid) + 512*(15 - uu), or 512*(16 - uu) for tid = 0 (none for i = 0)
+                if (tid != 0) buf.st(mcol + 544 * (15 - uu), hi);
+                else if (uu != 0) buf.st(mcol + 544 * (16 - uu), hi);
+            }
+        }
+        if (warp == NW - 1) {                       // the self-mirrored quad i = B/4, partitions spread over the lanes
+            float2 aR = make_float2(0.f, 0.f), aI = aR, mR = aR, mI = aR;
+            for (int p = lane; p < P; p += 32) {
+                const C2 tA = from4(__ldg(tp + (int64_t)p * QROW + Q4)), tM = from4(__ldg(tp + (int64_t)p * QROW + QOFF_M + Q4));
+                const C2 xA = from4(__ldg(xp + (int64_t)p * QROW + Q4)), xM = from4(__ldg(xp + (int64_t)p * QROW + QOFF_M + Q4));
+                aR = fma2(tA.r, xA.r, aR);  aR = fma2(tA.i, xA.i, aR);
+                aI = fma2(tA.r, xA.i, aI);  aI = fma2(neg2(tA.i), xA.r, aI);
+                mR = fma2(tM.r, xM.r, mR);  mR = fma2(tM.i, xM.i, mR);
+                mI = fma2(tM.r, xM.i, mI);  mI = fma2(neg2(tM.i), xM.r, mI);
+            }
+            if (P > 1) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    aR.x += __shfl_xor_sync(0xffffffffu, aR.x, o); aR.y += __shfl_xor_sync(0xffffffffu, aR.y, o);
+                    aI.x += __shfl_xor_sync(0xffffffffu, aI.x, o); aI.y += __shfl_xor_sync(0xffffffffu, aI.y, o);
+                    mR.x += __shfl_xor_sync(0xffffffffu, mR.x, o); mR.y += __shfl_xor_sync(0xffffffffu, mR.y, o);
+                    mI.x += __shfl_xor_sync(0xffffffffu, mI.x, o); mI.y += __shfl_xor_sync(0xffffffffu, mI.y, o);
+                }
+            }
+            if (lane == 0) {
+                const float h = 0.70710678118654752f;       // exp(i*pi/4)
+                C2 lo, hi;
+                pack_quad(aR, aI, mR, mI, h, h, lo, hi);
+                buf.st(phys(Q4), lo);                        // C[B/4] (its mirror is itself)
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---------------- 3. three radix-16 Stockham passes over the 8192 (u, v) pairs ----------
+    // pass: butterfly j = tid reads chunk j + 512r, twiddles by exp(2*pi*i*r*k/(16*Ns)), k = j mod Ns,
+    // writes chunk (j-k)*16 + k + r*Ns.  phys(j + 512r) = phys(j) + 544r.
+    {
+        C2 v[16];
+        const int src = phys(tid);
+        {   // pass 1: Ns = 1, no twiddles; out chunk 16j + r -> 17j + r
+#pragma unroll
+            for (int r = 0; r < 16; ++r) v[r] = buf.ld(src + 544 * r);
+            __syncthreads();
+            dft16p(v);
+            const int dst = 17 * tid;
+#pragma unroll
+            for (int r = 0; r < 16; ++r) buf.st(dst + r, v[brev<16>(r)]);
+            __syncthreads();
+        }
+        {   // pass 2: Ns = 16, k = tid & 15; out chunk 256a + 16r + k -> 272a + 17r + k, a = tid >> 4
+            const int kk = tid & 15;
+            float4 tw[8];
+#pragma unroll
+            for (int a = 0; a < 8; ++a) tw[a] = __ldg(tab.tw2 + a * 16 + kk);
+#pragma unroll
+            for (int r = 0; r < 16; ++r) v[r] = buf.ld(src + 544 * r);
+            __syncthreads();
+#pragma unroll
+            for (int r = 1; r < 16; ++r) {
+                const float4 t = tw[r >> 1];
+                v[r] = (r & 1) ? cmul_s(v[r], t.z, t.w) : cmul_s(v[r], t.x, t.y);
+            }
+            dft16p(v);
+            const int dst = 272 * (tid >> 4) + kk;
+#pragma unroll
+            for (int r = 0; r < 16; ++r) buf.st(dst + 17 * r, v[brev<16>(r)]);
+            __syncthreads();
+        }
+        {   // pass 3: Ns = 256, k = tid & 255; out chunk 4096a + 256r + k -> 4352a + 272r + phys(k), a = tid >> 8
+            const int kk = tid & 255;
+            float4 tw[8];
+#pragma unroll
+            for (int a = 0; a < 8; ++a) tw[a] = __ldg(tab.tw3 + a * 256 + kk);
+#pragma unroll
+            for (int r = 0; r < 16; ++r) v[r] = buf.ld(src + 544 * r);
+            __syncthreads();
+#pragma unroll
+            for (int r = 1; r < 16; ++r) {
+                const float4 t = tw[r >> 1];
+                v[r] = (r & 1) ? cmul_s(v[r], t.z, t.w) : cmul_s(v[r], t.x, t.y);
+            }
+            dft16p(v);
+            const int dst = 4352 * (tid >> 8) + phys(kk);
+#pragma unroll
+            for (int r = 0; r < 16; ++r) buf.st(dst + 272 * r, v[brev<16>(r)]);
+            if (is_u8) cp_async_commit_wait_all();          // the staged running sums landed long ago
+            __syncthreads();
+        }
+    }
+    // now E = chunks [0, 4096), O = chunks [4096, 8192); the half-size transforms are
+    //   X'[j] = E[j] + W8192^j * O[j]   (j < 4096; the "-" half carries no valid lag)
+    // and chunk j of X' holds the correlation (times 2B) at lags 4j .. 4j+3 = (u.re, u.im, v.re, v.im)
+
+    // ---------------- 4. window sums, fp32 screening, fp64 exact evaluation -----------------
+    const int64_t n = d.tlen;
+    const int64_t jlo = d.lag0, jhi = d.lag0 + d.nlags;
+    const double2 t_hi = tpfx[d.toff + n], t_lo = tpfx[d.toff];
+    const double tsum = t_hi.x - t_lo.x, tsq = t_hi.y - t_lo.y;
+    const double a = (double)Acc<S>::centre(ipfx[img_n].x, (double)img_n);
+    const double b = (double)Acc<S>::centre(tsum, (double)n);
+    const double n_ab = (double)n * a * b;
+    const double scale = 1.0 / (double)(2 * B);
+    const double k_const = a * tsum - n_ab;
+    const float f_tsq = (float)tsq, f_b = (float)b, f_scale = (float)scale;
+    const bool interior = j_blk >= jlo && j_blk + LB <= jhi;
+
+    // chunks 2*tid, 2*tid+1 of every round: physical offsets and twiddles
+    const int ech = 2 * tid + (tid >> 3);                              // + 1088*c + e; O is 4352 further
+    const float4 wt = __ldg(reinterpret_cast<const float4*>(tab.w8) + tid);   // W8192^(2tid), W8192^(2tid+1)
+
+    float vf[ROUNDS][8];
+    float tmin = 2.0f;
+    if (is_u8) mbar_wait(s_bar, 0);
+#pragma unroll
+    for (int c = 0; c < ROUNDS; ++c) {
+        const int m0 = c * LAGS_PER_ROUND + tid * 8;
+        const int64_t j0 = j_blk + m0;
+        const int64_t jw = j_blk + c * LAGS_PER_ROUND + warp * 256;
+        if (jw >= jhi || jw + 256 <= jlo) {                            // no valid lag in this warp-round (warp-uniform)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) vf[c][i] = 2.0f;
+            continue;
+        }
+        // correlation at the 8 lags: last radix-2 step on chunks 1024c + 2tid + {0, 1}
+        float cc[8];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const C2 E = buf.ld(ech + 1088 * c + e), O = buf.ld(ech + 1088 * c + e + 4352);
+            float wc = e ? wt.z : wt.x, ws = e ? wt.w : wt.y;          // W8192^(2tid+e) ...
+            {                                                          // ... times exp(2*pi*i*c/8)
+                const float h = 0.70710678118654752f;
+                const float c0 = wc, s0 = ws;
+                if (c == 1) { wc = (c0 - s0) * h; ws = (c0 + s0) * h; }
+                if (c == 2) { wc = -s0; ws = c0; }
+                if (c == 3) { wc = -(c0 + s0) * h; ws = (c0 - s0) * h; }
+            }
+            const float2 xr = fma2(O.r, bc(wc), fma2(O.i, bc(-ws), E.r));
+            const float2 xi = fma2(O.r, bc(ws), fma2(O.i, bc(wc), E.i));
+            cc[4 * e + 0] = xr.x; cc[4 * e + 1] = xi.x; cc[4 * e + 2] = xr.y; cc[4 * e + 3] = xi.y;
+        }
+        float f_w0q, f_k0;
+        unsigned long long lo8 = 0, hi8 = 0;
+        if (is_u8) {
+            // everything comes from shared memory: lane l owns the run of 8 lags starting at jw + 8l.  Window
+            // sums at the head of a run = exact warp base + exclusive intra-warp scan of the runs' integer totals
+            const int hi_off = (int)((j_blk + n) & 15);
+            lo8 = *reinterpret_cast<const unsigned long long*>(s_lo + m0);
+            const int hb = hi_off + m0;
+            const unsigned long long h0 = *reinterpret_cast<const unsigned long long*>(s_hi + (hb & ~7));
+            const unsigned long long h1 = *reinterpret_cast<const unsigned long long*>(s_hi + (hb & ~7) + 8);
+            const unsigned sh = (unsigned)(hb & 7) * 8u;
+            hi8 = sh ? ((h0 >> sh) | (h1 << (64u - sh))) : h0;
+            const unsigned la = (unsigned)lo8, lb = (unsigned)(lo8 >> 32), ha = (unsigned)hi8, hb2 = (unsigned)(hi8 >> 32);
+            const int tq = (int)__dp4a(ha, ha, __dp4a(hb2, hb2, 0u)) - (int)__dp4a(la, la, __dp4a(lb, lb, 0u));
+            const int ts = (int)__dp4a(ha, 0x01010101u, __dp4a(hb2, 0x01010101u, 0u)) - (int)__dp4a(la, 0x01010101u, __dp4a(lb, 0x01010101u, 0u));
+            int iq = tq, is = ts;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int uq = __shfl_up_sync(0xffffffffu, iq, o), us = __shfl_up_sync(0xffffffffu, is, o);
+                if (lane >= o) { iq += uq; is += us; }
+            }
+            const double2 b_lo = s_base[(c * NW + warp) * 2], b_hi = s_base[(c * NW + warp) * 2 + 1];
+            const double w0s = (b_hi.x - b_lo.x) + (double)(is - ts);
+            const double w0q = (b_hi.y - b_lo.y) + (double)(iq - tq);
+            f_w0q = (float)w0q;
+            f_k0 = (float)(b * w0s + k_const);
+        } else {
+            if (!(j0 < jhi && j0 + 8 > jlo)) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) vf[c][i] = 2.0f;
+                continue;
+            }
+            const double2 p_hi = ipfx[j0 + n], p_lo = ipfx[j0];
+            f_w0q = (float)(p_hi.y - p_lo.y);
+            f_k0 = (float)(b * (p_hi.x - p_lo.x) + k_const);
+        }
+        int rq = 0, rs = 0;              // uint8: exact integer slide
+        double dq = 0.0, ds = 0.0;       // float32: fp64 slide
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float wq = f_w0q + (is_u8 ? (float)rq : (float)dq);
+            const float sit = fmaf(cc[i], f_scale, fmaf(f_b, is_u8 ? (float)rs : (float)ds, f_k0));
+            const float num = fmaxf((wq + f_tsq) - 2.0f * sit, 0.0f);
+            const float pr = wq * f_tsq;
+            // pr == 0 (silent window or template): rsqrt -> inf, num*inf -> inf or NaN, fminf(.,1) -> 1
+            const float v = fminf(num * rsqrt_fast(pr), 1.0f);
+            if (interior) { vf[c][i] = v; tmin = fminf(tmin, v); }
+            else if (j0 + i >= jlo && j0 + i < jhi) { vf[c][i] = v; tmin = fminf(tmin, v); }
+            else vf[c][i] = 2.0f;                                      // sentinel: not a valid lag
+            if (is_u8) {
+                const int lo = (int)((lo8 >> (8 * i)) & 0xffu), hi = (int)((hi8 >> (8 * i)) & 0xffu);
+                rq += hi * hi - lo * lo; rs += hi - lo;
+            } else if (j0 + i + n < img_n) {
+                const double lo = (double)img32[j0 + i], hi = (double)img32[j0 + i + n];
+                dq += hi * hi - lo * lo; ds += hi - lo;
+            }
+        }
+    }
+    const float my_min = tmin;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tmin = fminf(tmin, __shfl_xor_sync(0xffffffffu, tmin, o));
+    if (lane == 0) s_min[warp] = tmin;
+    __syncthreads();
+    float bmin = s_min[0];
+#pragma unroll
+    for (int w = 1; w < NW; ++w) bmin = fminf(bmin, s_min[w]);
+    const float thr = curve_out ? 1.5f : bmin + kScreenMargin;       // debug curve: evaluate everything
+
+    unsigned long long cand = 0;
+    if (my_min <= thr) {
+#pragma unroll
+        for (int c = 0; c < ROUNDS; ++c)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) cand |= (vf[c][i] <= thr) ? (1ull << (c * 8 + i)) : 0ull;
+    }
+    unsigned long long best = ~0ull;
+    while (cand) {
+        const int bit = __ffsll((long long)cand) - 1;
+        cand &= cand - 1;
+        const int m = (bit >> 3) * LAGS_PER_ROUND + tid * 8 + (bit & 7);
+        const int64_t j = j_blk + m;
+        const int jj = m >> 2;                                          // chunk of X'
+        const C2 E = buf.ld(phys(jj)), O = buf.ld(phys(jj) + 4352);
+        const float2 w = __ldg(tab.w8 + jj);
+        const bool second = (m & 2) != 0;                               // lags 4j+2, 4j+3 belong to v
+        const float er = second ? E.r.y : E.r.x, ei = second ? E.i.y : E.i.x, orr = second ? O.r.y : O.r.x, oi = second ? O.i.y : O.i.x;
+        const float xr = fmaf(orr, w.x, fmaf(oi, -w.y, er)), xi = fmaf(orr, w.y, fmaf(oi, w.x, ei));
+        const double cc = (double)((m & 1) ? xi : xr) * scale;
+        const double2 p_hi = ipfx[j + n], p_lo = ipfx[j];
+        const float v = sqdiff_exact(cc, p_hi.x - p_lo.x, p_hi.y - p_lo.y, a, b, tsum, tsq, n_ab);
+        if (curve_out) curve_out[d.curveOff + (j - jlo)] = v;
+        const unsigned long long key = ((unsigned long long)__float_as_uint(v) << 32) | (unsigned int)(j - jlo);
+        best = key < best ? key : best;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+        best = other < best ? other : best;
+    }
+    if (lane == 0) s_best[warp] = best;
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < NW; ++w) best = s_best[w] < best ? s_best[w] : best;
+        if (best != ~0ull) atomicMin(keys + q, best);
+    }
+}
+
+// ---------------------------------------------------------------- forward spectra, quad layout
+// Same transform as k_forward_rows in sb_fused.cu (gather + centring + 2B-point real FFT through the
+// shared-memory inverse passes run backwards); only the output stage differs: bins leave as the chunks
+// A[i] = (X[i], X[i+B/2]) and M[i] = (X[B-i], X[B/2-i]) the packed kernel multiplies.
+template <typename S, int MODE>
+__global__ void __launch_bounds__(Cfg<14>::T, 1)
+k_forward_quad(const S* __restrict__ src, int64_t src_n, const double2* __restrict__ pfx,
+               const QueryDesc* __restrict__ desc, int q_begin, int q_end, int64_t row_first,
+               FusedTables tab, float4* __restrict__ out) {
+    typedef Cfg<14> C;
+    constexpr int N = C::N, T = C::T, B = C::N;
+    constexpr int NT2 = C::R2 * 32, NT3 = C::R3 * 32;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* buf = reinterpret_cast<float2*>(smem_raw);
+    float2* s_t2 = buf + pad(N) + 1;
+    float2* s_a3 = s_t2 + NT2;
+    float2* s_b3 = s_a3 + NT3;
+    __shared__ int s_q;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < NT2; i += T) s_t2[i] = __ldg(tab.t2 + i);
+    for (int i = tid; i < NT3; i += T) { s_a3[i] = __ldg(tab.a3 + i); s_b3[i] = __ldg(tab.b3 + i); }
+
+    int64_t off, len;          // samples [off, off+len) of src, zero beyond
+    float centre;
+    const int64_t row = row_first + blockIdx.x;
+    if (MODE == 0) {
+        off = row * B;
+        len = src_n - off; if (len > 2 * B) len = 2 * B; if (len < 0) len = 0;
+        centre = Acc<S>::centre(pfx[src_n].x, (double)src_n);
+    } else {
+        if (tid == 0) {        // largest q with partBase <= row
+            int lo = q_begin, hi = q_end - 1;
+            while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (desc[mid].partBase <= row) lo = mid; else hi = mid - 1; }
+            s_q = lo;
+        }
+        __syncthreads();
+        const QueryDesc d = desc[s_q];
+        const int64_t seg0 = (row - d.partBase) * B;
+        off = d.toff + seg0;
+        len = d.tlen - seg0; if (len > B) len = B;
+        centre = Acc<S>::centre(pfx[d.toff + d.tlen].x - pfx[d.toff].x, (double)d.tlen);
+    }
+    const S* x = src + off;
+#pragma unroll 4
+    for (int n = tid; n < B; n += T) {
+        const int64_t i0 = 2 * (int64_t)n;
+        const float a = i0 < len ? (float)x[i0] - centre : 0.f;
+        const float b = i0 + 1 < len ? (float)x[i0 + 1] - centre : 0.f;
+        buf[pad(n)] = make_float2(a, -b);            // conj(z[n])
+    }
+    __syncthreads();
+    ifft_smem<14, C::R3, false>(buf, s_t2, s_a3, s_b3);   // buf = conj(Z)
+    // bins k and B-k from Z[k], Z[B-k]:  X[k] = Xe + conj(w^k)*Xo,  X[B-k] = conj(Xe - conj(w^k)*Xo)
+    auto bins = [&](int k, float2& xk, float2& xbk) {
+        const float2 zk = buf[pad(k)];
+        const float2 zp = buf[pad(k == 0 ? 0 : B - k)];
+        const float2 A = make_float2(zk.x, -zk.y), P = make_float2(zp.x, zp.y);     // Z[k], conj(Z[B-k])
+        const float2 xe = make_float2(0.5f * (A.x + P.x), 0.5f * (A.y + P.y));
+        const float2 dd = make_float2(A.x - P.x, A.y - P.y);
+        const float2 xo = make_float2(0.5f * dd.y, -0.5f * dd.x);                   // -i*dd/2
+        const float2 w = __ldg(tab.w + k);
+        const float2 tv = cmul(make_float2(w.x, -w.y), xo);
+        xk = make_float2(xe.x + tv.x, xe.y + tv.y);
+        xbk = make_float2(xe.x - tv.x, -(xe.y - tv.y));
+    };
+    float4* o = out + (int64_t)blockIdx.x * QROW;
+    for (int i = tid; i <= Q4; i += T) {
+        float2 x_i, x_bi, x_h, x_hb;
+        bins(i, x_i, x_bi);                          // X[i], X[B-i]
+        bins(B / 2 - i, x_h, x_hb);                  // X[B/2-i], X[B/2+i]
+        o[i] = make_float4(x_i.x, x_hb.x, x_i.y, x_hb.y);
+        o[QOFF_M + i] = make_float4(x_bi.x, x_h.x, x_bi.y, x_h.y);
+    }
+}
+
+size_t forward_smem_bytes14() {
+    typedef Cfg<14> C;
+    return ((size_t)(C::N + (C::N >> 5) + 1) + C::R2 * 32 + 2 * C::R3 * 32) * sizeof(float2) + 64;
+}
+
+size_t packed_smem_bytes() {
+    const size_t rounds = QB / (QT * 8);
+    return (size_t)QPHYS * sizeof(float4) + rounds * QNW * 2 * sizeof(double2) + (QB + 16) + (QB + 48)
+         + 8 + QNW * sizeof(unsigned long long) + QNW * sizeof(float) + 64;
+}
+
+float* g_ptab_dev = nullptr;
+PackedTables g_ptab;
+
+int ensure_packed_tables(PackedTables* out) {
+    if (!g_ptab_dev) {
+        const double pi = 3.14159265358979323846;
+        const size_t n2 = 8 * 16 * 4, n3 = 8 * 256 * 4, n8 = 4096 * 2, nb = 512 * 2;
+        std::vector<float> h(n2 + n3 + n8 + nb);
+        for (int a = 0; a < 8; ++a)
+            for (int k = 0; k < 16; ++k)
+                for (int e = 0; e < 2; ++e) {
+                    const double ang = 2.0 * pi * (2 * a + e) * k / 256.0;
+                    h[((size_t)a * 16 + k) * 4 + 2 * e] = (float)cos(ang); h[((size_t)a * 16 + k) * 4 + 2 * e + 1] = (float)sin(ang);
+                }
+        for (int a = 0; a < 8; ++a)
+            for (int k = 0; k < 256; ++k)
+                for (int e = 0; e < 2; ++e) {
+                    const double ang = 2.0 * pi * (2 * a + e) * k / 4096.0;
+                    h[n2 + ((size_t)a * 256 + k) * 4 + 2 * e] = (float)cos(ang); h[n2 + ((size_t)a * 256 + k) * 4 + 2 * e + 1] = (float)sin(ang);
+                }
+        for (int j = 0; j < 4096; ++j) { h[n2 + n3 + 2 * j] = (float)cos(2.0 * pi * j / 8192.0); h[n2 + n3 + 2 * j + 1] = (float)sin(2.0 * pi * j / 8192.0); }
+        for (int t = 0; t < 512; ++t) { h[n2 + n3 + n8 + 2 * t] = (float)cos(pi * t / QB); h[n2 + n3 + n8 + 2 * t + 1] = (float)sin(pi * t / QB); }
+        SB_CUDA(cudaMalloc(&g_ptab_dev, h.size() * sizeof(float)));
+        SB_CUDA(cudaMemcpy(g_ptab_dev, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
+        g_ptab.tw2 = reinterpret_cast<const float4*>(g_ptab_dev);
+        g_ptab.tw3 = reinterpret_cast<const float4*>(g_ptab_dev + n2);
+        g_ptab.w8 = reinterpret_cast<const float2*>(g_ptab_dev + n2 + n3);
+        g_ptab.wb = reinterpret_cast<const float2*>(g_ptab_dev + n2 + n3 + n8);
+    }
+    *out = g_ptab;
+    return SB_OK;
+}
+
+__global__ void k_fill_item_query2(const QueryDesc* __restrict__ desc, int q_begin, int64_t item_first,
+                                   int* __restrict__ item_query) {
+    const int q = q_begin + blockIdx.x;
+    const int64_t base = desc[q].itemBase - item_first;
+    const int nk = desc[q].nk;
+    for (int i = threadIdx.x; i < nk; i += blockDim.x) item_query[base + i] = q;
+}
+
+int* g_item_query2 = nullptr;
+int64_t g_item_query2_cap = 0;
+
+template <typename S, int MODE>
+int launch_forward_quad_typed(const sb_stream* src, const QueryDesc* d_desc, int q_begin, int q_end,
+                              int64_t row_first, int64_t rows, float2* out) {
+    Ctx& c = ctx();
+    FusedTables tab;
+    SB_TRY(fused_tables(14, &tab));
+    static bool attr_set = false;
+    const size_t smem = forward_smem_bytes14();
+    if (!attr_set) {
+        SB_CUDA(cudaFuncSetAttribute(k_forward_quad<S, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    k_forward_quad<S, MODE><<<(unsigned)rows, Cfg<14>::T, smem, c.stream>>>(
+        static_cast<const S*>(src->d_raw), src->n, src->d_pfx, d_desc, q_begin, q_end, row_first, tab,
+        reinterpret_cast<float4*>(out));
+    SB_CUDA(cudaGetLastError());
+    return SB_OK;
+}
+
+}  // namespace
+
+namespace sb {
+
+bool packed_supports(int B) { return B == QB; }
+
+int launch_match_packed(const sb_stream* image, const sb_stream* tmpl, const float2* d_parts, int64_t part_first,
+                        const QueryDesc* d_desc, int q_begin, int q_end, int64_t item_first, int64_t n_items,
+                        unsigned long long* d_keys, float* d_curve) {
+    Ctx& c = ctx();
+    PackedTables tab;
+    SB_TRY(ensure_packed_tables(&tab));
+    static bool attr_set = false;
+    const size_t smem = packed_smem_bytes();
+    if (!attr_set) {
+        SB_CUDA(cudaFuncSetAttribute(k_match_packed<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SB_CUDA(cudaFuncSetAttribute(k_match_packed<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    if (g_item_query2_cap < n_items) {
+        cudaStreamSynchronize(c.stream);
+        cudaFree(g_item_query2); g_item_query2 = nullptr; g_item_query2_cap = 0;
+        SB_CUDA(cudaMalloc(&g_item_query2, sizeof(int) * (size_t)n_items));
+        g_item_query2_cap = n_items;
+    }
+    k_fill_item_query2<<<(unsigned)(q_end - q_begin), 128, 0, c.stream>>>(d_desc, q_begin, item_first, g_item_query2);
+    c.launches += 1;
+    const bool u8 = image->dtype == SB_U8;
+    const int64_t max_grid = 1 << 30;
+    for (int64_t i0 = 0; i0 < n_items; i0 += max_grid) {
+        const int64_t ni = std::min<int64_t>(max_grid, n_items - i0);
+        if (u8)
+            k_match_packed<uint8_t><<<(unsigned)ni, QT, smem, c.stream>>>(
+                reinterpret_cast<const float4*>(d_parts), part_first, reinterpret_cast<const float4*>(image->d_spec), image->nblk,
+                static_cast<const uint8_t*>(image->d_raw), image->n, image->d_pfx, tmpl->d_pfx, d_desc, g_item_query2 + i0, item_first + i0,
+                tab, d_keys, d_curve);
+        else
+            k_match_packed<float><<<(unsigned)ni, QT, smem, c.stream>>>(
+                reinterpret_cast<const float4*>(d_parts), part_first, reinterpret_cast<const float4*>(image->d_spec), image->nblk,
+                static_cast<const float*>(image->d_raw), image->n, image->d_pfx, tmpl->d_pfx, d_desc, g_item_query2 + i0, item_first + i0,
+                tab, d_keys, d_curve);
+    }
+    SB_CUDA(cudaGetLastError());
+    return SB_OK;
+}
+
+int launch_block_spectra_quad(const sb_stream* s, int64_t k_first, int64_t rows, float2* out) {
+    return s->dtype == SB_U8 ? launch_forward_quad_typed<uint8_t, 0>(s, nullptr, 0, 0, k_first, rows, out)
+                             : launch_forward_quad_typed<float, 0>(s, nullptr, 0, 0, k_first, rows, out);
+}
+
+int launch_part_spectra_quad(const sb_stream* tmpl, const QueryDesc* d_desc, int q_begin, int q_end,
+                             int64_t part_first, int64_t rows, float2* out) {
+    return tmpl->dtype == SB_U8 ? launch_forward_quad_typed<uint8_t, 1>(tmpl, d_desc, q_begin, q_end, part_first, rows, out)
+                                : launch_forward_quad_typed<float, 1>(tmpl, d_desc, q_begin, q_end, part_first, rows, out);
+}
+
+void packed_release_tables() {
+    if (g_ptab_dev) cudaFree(g_ptab_dev);
+    g_ptab_dev = nullptr;
+    cudaFree(g_item_query2); g_item_query2 = nullptr; g_item_query2_cap = 0;
+}
+
+}  // namespace sb

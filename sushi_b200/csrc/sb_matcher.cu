@@ -432,8 +432,8 @@ int run_batch(const sb_stream* image_c, const sb_stream* tmpl, int64_t count,
     sb_stream* image = const_cast<sb_stream*>(image_c);
     if (image->dtype != tmpl->dtype) SB_FAIL(SB_EINVAL, "image and template streams differ in sample type");
     if (count > 0x7fffffffll) SB_FAIL(SB_EINVAL, "more than 2^31 queries in one batch");
-    const int B = c.B, nb = B + 1;
-    const bool use_fused = c.engine == 1 && fused_supports(B);
+    const int B = c.B;
+    const bool use_fused = c.engine >= 1 && fused_supports(B);
     // Geometry of the fused engine.  hop B (default): half of every 2B-point inverse FFT is valid lags,
     // P = ceil(n/B) partitions per item.  hop B/2: three quarters are valid (1.5x the lags per FFT) but
     // there are twice as many partition rows to multiply and twice as many block-spectrum rows competing
@@ -442,7 +442,7 @@ int run_batch(const sb_stream* image_c, const sb_stream* tmpl, int64_t count,
     int hd = 1;
     if (use_fused) {
         if (c.hop_mode == 2) hd = 2;
-        else if (c.hop_mode == 0) {
+        else if (c.hop_mode == 0 && c.engine == 1) {
             int64_t longest = 0;
             for (int64_t q = 0; q < count; ++q) longest = std::max<int64_t>(longest, tlen[q]);
             if (longest <= B / 2) hd = 2;
@@ -451,8 +451,11 @@ int run_batch(const sb_stream* image_c, const sb_stream* tmpl, int64_t count,
     // Multiply strategy per query: inside the fused kernel (2 loads per multiply-accumulate, nothing through
     // HBM), or -- for very long templates (kBlockedFromPartitions) -- the register-blocked kernel
     // k_mac_blocked over MAC_GROUP lag blocks, whose products the fused kernel then reads from a chunk buffer.
+    // Engine 2: the packed kernel (sb_fused2.cu) with quad-layout spectrum rows; it covers B = 16384 at hop B.
+    const bool use_packed = c.engine == 2 && packed_supports(B) && hd == 1;
+    const int nb = use_packed ? kQuadRowF2 : B + 1;          // float2 per spectrum row
     int64_t n_direct = 0, total_items = 0, total_parts = 0, total_groups = 0, maxp = 0;
-    SB_TRY(plan_batch(image, tmpl, count, toff, tlen, lag0, nlags, hd, use_fused && hd == 1, &n_direct,
+    SB_TRY(plan_batch(image, tmpl, count, toff, tlen, lag0, nlags, hd, use_fused && hd == 1 && !use_packed, &n_direct,
                       &total_items, &total_parts, &total_groups, &maxp));
     SB_TRY(ensure_spectra(image, hd));
 
@@ -485,7 +488,10 @@ int run_batch(const sb_stream* image_c, const sb_stream* tmpl, int64_t count,
         const int64_t part_first = c.h_desc[qb].partBase;
         // 1. template partitions -> spectra
         const int64_t sub = 4096;
-        if (use_fused) {                             // hand-written gather + forward FFT, one launch
+        if (use_packed) {
+            ProfScope ps("part_spectra");
+            SB_TRY(launch_part_spectra_quad(tmpl, c.d_desc, (int)qb, (int)qe, part_first, np, c.d_parts));
+        } else if (use_fused) {                      // hand-written gather + forward FFT, one launch
             ProfScope ps("part_spectra");
             SB_TRY(launch_part_spectra(tmpl, hd, c.d_desc, (int)qb, (int)qe, part_first, np, c.d_parts));
         } else
@@ -511,7 +517,11 @@ int run_batch(const sb_stream* image_c, const sb_stream* tmpl, int64_t count,
         // 2. items of these queries
         const int64_t item_lo = c.h_desc[qb].itemBase;
         const int64_t item_hi = (qe < count) ? c.h_desc[qe].itemBase : total_items;
-        if (use_fused && !premac) {
+        if (use_packed) {
+            ProfScope ps("match_fused");
+            SB_TRY(launch_match_packed(image, tmpl, c.d_parts, part_first, c.d_desc, (int)qb, (int)qe,
+                                       item_lo, item_hi - item_lo, c.d_keys, d_curve));
+        } else if (use_fused && !premac) {
             ProfScope ps("match_fused");
             SB_TRY(launch_match_fused(image, tmpl, hd, c.d_parts, part_first, nullptr, c.d_desc, (int)qb, (int)qe,
                                       item_lo, item_hi - item_lo, c.d_keys, d_curve));

@@ -212,17 +212,28 @@ int stream_finish_public(sb_stream* s) { return stream_finish(s); }
 // Build (or fetch) the block spectra of `s`: row k = FFT_2B of samples [k*H, k*H + 2B), H = B/hd.
 int ensure_spectra(sb_stream* s, int hd) {
     Ctx& c = ctx();
-    if (s->d_spec && s->specB == c.B && s->specHD == hd && s->specEngine == c.engine) return SB_OK;
+    // effective engine: the packed kernel covers B = 16384 at hop B; everything else falls to engine 1 / 0
+    const int eng = (c.engine == 2 && packed_supports(c.B) && hd == 1) ? 2 : (c.engine >= 1 && fused_supports(c.B)) ? 1 : 0;
+    if (s->d_spec && s->specB == c.B && s->specHD == hd && s->specEngine == eng) return SB_OK;
     if (s->d_spec) { pool_free(s->d_spec); s->d_spec = nullptr; }
     const int B = c.B, H = B / hd;
     const int64_t nblk = (s->n + H - 1) / H;
+    if (c.engine == 2 && packed_supports(B) && hd == 1) {   // quad-layout rows for the packed kernel
+        SB_TRY(pool_alloc((void**)&s->d_spec, sizeof(float2) * (size_t)nblk * kQuadRowF2));
+        {
+            ProfScope ps("block_spectra");
+            SB_TRY(launch_block_spectra_quad(s, 0, nblk, s->d_spec));
+        }
+        s->specB = B; s->specHD = 1; s->nblk = nblk; s->specEngine = 2;
+        return SB_OK;
+    }
     SB_TRY(pool_alloc((void**)&s->d_spec, sizeof(float2) * (size_t)nblk * (B + 1)));
-    if (c.engine == 1 && fused_supports(B)) {        // hand-written gather + forward FFT, one launch
+    if (c.engine >= 1 && fused_supports(B)) {        // hand-written gather + forward FFT, one launch
         {
             ProfScope ps("block_spectra");
             SB_TRY(launch_block_spectra(s, hd, 0, nblk, s->d_spec));
         }
-        s->specB = B; s->specHD = hd; s->nblk = nblk; s->specEngine = c.engine;
+        s->specB = B; s->specHD = hd; s->nblk = nblk; s->specEngine = 1;
         return SB_OK;
     }
     if (hd != 1) SB_FAIL(SB_EINVAL, "internal: the cuFFT engine only builds spectra at hop B");
@@ -248,7 +259,7 @@ int ensure_spectra(sb_stream* s, int hd) {
         }
     }
     SB_CUDA(cudaGetLastError());
-    s->specB = B; s->specHD = 1; s->nblk = nblk; s->specEngine = c.engine;
+    s->specB = B; s->specHD = 1; s->nblk = nblk; s->specEngine = 0;
     return SB_OK;
 }
 
