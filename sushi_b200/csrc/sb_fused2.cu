@@ -152,194 +152,173 @@ __device__ __forceinline__ void pack_quad(float2 aR, float2 aI, float2 mR, float
     }
 }
 
-// ---------------------------------------------------------------- the kernel
-template <typename S>
-__global__ void __launch_bounds__(QT, 1)
-k_match_packed(const float4* __restrict__ That, int64_t part_first,
-               const float4* __restrict__ Xhat, int64_t nblk,
-               const S* __restrict__ img, int64_t img_n,
-               const double2* __restrict__ ipfx, const double2* __restrict__ tpfx,
-               const QueryDesc* __restrict__ desc, const int* __restrict__ item_query, int64_t item_first,
-               PackedTables tab, unsigned long long* __restrict__ keys, float* __restrict__ curve_out) {
-    constexpr int B = QB, T = QT, NW = QNW, LB = QB;
+// ---------------------------------------------------------------- pieces shared by the two kernels
+// Both kernels run the FFT and the epilogue on exactly 512 threads; ID names their barrier (0 = the whole CTA
+// of k_match_packed, 1 = the consumer warps of k_match_ws).
+template <int ID> __device__ __forceinline__ void csync() { asm volatile("bar.sync %0, 512;" :: "n"(ID) : "memory"); }
+
+constexpr int kRounds = QB / (QT * 8);            // epilogue rounds: 8 consecutive lags per thread per round
+constexpr int kLagsPerRound = QT * 8;
+
+struct Smem {                                      // carve-up of the dynamic shared memory (both kernels)
+    Buf buf;                                       // QPHYS chunks, two float2 arrays
+    double2* base;                                 // [kRounds][QNW][2] exact running sums
+    unsigned char* lo;                             // image[j_blk .. +QB+16)
+    unsigned char* hi;                             // image[(j_blk+n)&~15 .. +QB+48)
+    unsigned char* end;                            // first byte after the common part (16-byte aligned)
+    __device__ __forceinline__ explicit Smem(unsigned char* raw) {
+        buf.r = reinterpret_cast<float2*>(raw); buf.i = buf.r + QPHYS;
+        base = reinterpret_cast<double2*>(raw + (size_t)QPHYS * 16);
+        lo = reinterpret_cast<unsigned char*>(base + kRounds * QNW * 2);
+        hi = lo + QB + 16;
+        end = hi + QB + 48;
+    }
+};
+constexpr size_t kSmemCommon = (size_t)QPHYS * 16 + kRounds * QNW * 2 * sizeof(double2) + (QB + 16) + (QB + 48);
+
+struct Item {                                      // one (query, lag block)
+    QueryDesc d; int q; int64_t k, j_blk;
+    __device__ __forceinline__ Item(const QueryDesc* desc, const int* item_query, int64_t item_first, int64_t local) {
+        q = __ldg(item_query + local);
+        d = desc[q];
+        k = d.k0 + (item_first + local - d.itemBase);
+        j_blk = k * QB;
+    }
+};
+
+// uint8 streams: the two byte windows the sliding sums read go to shared memory by TMA bulk copies (one
+// thread), one exact (sum, sum of squares) pair per warp-round from the fp64 running sums by cp.async.
+__device__ __forceinline__ void stage_inputs(const Item& it, int tid, const uint8_t* img8, int64_t img_n,
+                                             const double2* ipfx, const Smem& sm, unsigned long long* bar) {
+    const int64_t hi0 = (it.j_blk + it.d.tlen) & ~(int64_t)15;
+    const int64_t limit = (img_n + 16) & ~(int64_t)15;               // allocation has 16 bytes of slack
+    if (tid == 0) {
+        int64_t lo_bytes = limit - it.j_blk; if (lo_bytes > QB + 16) lo_bytes = QB + 16; if (lo_bytes < 0) lo_bytes = 0;
+        int64_t hi_bytes = limit - hi0;      if (hi_bytes > QB + 48) hi_bytes = QB + 48; if (hi_bytes < 0) hi_bytes = 0;
+        mbar_expect_tx(bar, (unsigned)(lo_bytes + hi_bytes));
+        if (lo_bytes) tma_load_1d(sm.lo, img8 + it.j_blk, (unsigned)lo_bytes, bar);
+        if (hi_bytes) tma_load_1d(sm.hi, img8 + hi0, (unsigned)hi_bytes, bar);
+    }
+    if (tid < kRounds * QNW * 2) {
+        const int c = tid / (QNW * 2), w = (tid >> 1) % QNW, which = tid & 1;
+        const int64_t jw = it.j_blk + c * kLagsPerRound + w * 256;
+        if (jw < it.d.lag0 + it.d.nlags) cp_async16(sm.base + tid, ipfx + jw + (which ? it.d.tlen : 0));
+    }
+}
+
+// Y += conj(T) * X on both slots of the A and the M chunk of one quad
+struct QuadAcc {
+    float2 aR, aI, mR, mI;
+    __device__ __forceinline__ void zero() { aR = aI = mR = mI = make_float2(0.f, 0.f); }
+    __device__ __forceinline__ void mac(float4 ta, float4 tm, float4 xa, float4 xm) {
+        const C2 tA = from4(ta), xA = from4(xa), tM = from4(tm), xM = from4(xm);
+        aR = fma2(tA.r, xA.r, aR);  aR = fma2(tA.i, xA.i, aR);
+        aI = fma2(tA.r, xA.i, aI);  aI = fma2(neg2(tA.i), xA.r, aI);
+        mR = fma2(tM.r, xM.r, mR);  mR = fma2(tM.i, xM.i, mR);
+        mI = fma2(tM.r, xM.i, mI);  mI = fma2(neg2(tM.i), xM.r, mI);
+    }
+    __device__ __forceinline__ void reduce_over_lanes() {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            aR.x += __shfl_xor_sync(0xffffffffu, aR.x, o); aR.y += __shfl_xor_sync(0xffffffffu, aR.y, o);
+            aI.x += __shfl_xor_sync(0xffffffffu, aI.x, o); aI.y += __shfl_xor_sync(0xffffffffu, aI.y, o);
+            mR.x += __shfl_xor_sync(0xffffffffu, mR.x, o); mR.y += __shfl_xor_sync(0xffffffffu, mR.y, o);
+            mI.x += __shfl_xor_sync(0xffffffffu, mI.x, o); mI.y += __shfl_xor_sync(0xffffffffu, mI.y, o);
+        }
+    }
+};
+
+// The self-mirrored quad i = B/4 of an item, by one warp: partitions spread over the lanes, result valid in lane 0
+__device__ __forceinline__ C2 special_quad(const float4* tp, const float4* xp, int P, int lane) {
+    QuadAcc acc; acc.zero();
+    for (int p = lane; p < P; p += 32)
+        acc.mac(__ldg(tp + (int64_t)p * QROW + Q4), __ldg(tp + (int64_t)p * QROW + QOFF_M + Q4),
+                __ldg(xp + (int64_t)p * QROW + Q4), __ldg(xp + (int64_t)p * QROW + QOFF_M + Q4));
+    acc.reduce_over_lanes();
+    const float h = 0.70710678118654752f;       // exp(i*pi/4)
+    C2 lo, hi;
+    pack_quad(acc.aR, acc.aI, acc.mR, acc.mI, h, h, lo, hi);
+    return lo;                                    // C[B/4] (its mirror is itself)
+}
+
+// Three radix-16 Stockham passes over the 8192 (u, v) pairs.  Butterfly j = tid reads chunk j + 512r, twiddles
+// by exp(2*pi*i*r*k/(16*Ns)), k = j mod Ns, writes chunk (j-k)*16 + k + r*Ns; phys(j + 512r) = phys(j) + 544r.
+// Entered after a barrier that published buf; ends with a barrier.  Afterwards E = chunks [0, 4096),
+// O = chunks [4096, 8192): the half-size transforms are X'[j] = E[j] + W8192^j * O[j] (j < 4096; the "-" half
+// carries no valid lag), and chunk j of X' holds the correlation (times 2B) at lags 4j .. 4j+3 =
+// (u.re, u.im, v.re, v.im).
+template <int ID>
+__device__ __forceinline__ void fft_passes(const Buf& buf, int tid, const PackedTables& tab, bool drain_cp_async) {
+    C2 v[16];
+    const int src = phys(tid);
+    {   // pass 1: Ns = 1, no twiddles; out chunk 16j + r -> 17j + r
+#pragma unroll
+        for (int r = 0; r < 16; ++r) v[r] = buf.ld(src + 544 * r);
+        csync<ID>();
+        dft16p(v);
+        const int dst = 17 * tid;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) buf.st(dst + r, v[brev<16>(r)]);
+        csync<ID>();
+    }
+    {   // pass 2: Ns = 16, k = tid & 15; out chunk 256a + 16r + k -> 272a + 17r + k, a = tid >> 4
+        const int kk = tid & 15;
+        float4 tw[8];
+#pragma unroll
+        for (int a = 0; a < 8; ++a) tw[a] = __ldg(tab.tw2 + a * 16 + kk);
+#pragma unroll
+        for (int r = 0; r < 16; ++r) v[r] = buf.ld(src + 544 * r);
+        csync<ID>();
+#pragma unroll
+        for (int r = 1; r < 16; ++r) {
+            const float4 t = tw[r >> 1];
+            v[r] = (r & 1) ? cmul_s(v[r], t.z, t.w) : cmul_s(v[r], t.x, t.y);
+        }
+        dft16p(v);
+        const int dst = 272 * (tid >> 4) + kk;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) buf.st(dst + 17 * r, v[brev<16>(r)]);
+        csync<ID>();
+    }
+    {   // pass 3: Ns = 256, k = tid & 255; out chunk 4096a + 256r + k -> 4352a + 272r + phys(k), a = tid >> 8
+        const int kk = tid & 255;
+        float4 tw[8];
+#pragma unroll
+        for (int a = 0; a < 8; ++a) tw[a] = __ldg(tab.tw3 + a * 256 + kk);
+#pragma unroll
+        for (int r = 0; r < 16; ++r) v[r] = buf.ld(src + 544 * r);
+        csync<ID>();
+#pragma unroll
+        for (int r = 1; r < 16; ++r) {
+            const float4 t = tw[r >> 1];
+            v[r] = (r & 1) ? cmul_s(v[r], t.z, t.w) : cmul_s(v[r], t.x, t.y);
+        }
+        dft16p(v);
+        const int dst = 4352 * (tid >> 8) + phys(kk);
+#pragma unroll
+        for (int r = 0; r < 16; ++r) buf.st(dst + 272 * r, v[brev<16>(r)]);
+        if (drain_cp_async) cp_async_commit_wait_all();     // the staged running sums landed long ago
+        csync<ID>();
+    }
+}
+
+// Window sums, fp32 screening of every lag, fp64 evaluation of the lags that can still be the minimum, merge
+// into the query's key.  after_read() runs (on all 512 threads) once every thread is done with the staged
+// windows -- k_match_ws starts the copies of its next item there.
+template <typename S, int ID, typename AfterRead>
+__device__ __forceinline__ void finish_item(const Item& it, int tid, const Smem& sm, unsigned long long* s_bar, unsigned bar_parity,
+                                            unsigned long long* s_best, float* s_min,
+                                            const S* __restrict__ img, int64_t img_n,
+                                            const double2* __restrict__ ipfx, const double2* __restrict__ tpfx,
+                                            const PackedTables& tab, unsigned long long* __restrict__ keys,
+                                            float* __restrict__ curve_out, AfterRead after_read) {
+    constexpr int B = QB, NW = QNW, LB = QB, ROUNDS = kRounds, LAGS_PER_ROUND = kLagsPerRound;
     constexpr bool is_u8 = sizeof(S) == 1;
-    const uint8_t* img8 = reinterpret_cast<const uint8_t*>(img);
     const float* img32 = reinterpret_cast<const float*>(img);
-    constexpr int LAGS_PER_ROUND = T * 8, ROUNDS = LB / LAGS_PER_ROUND;    // 4096, 4
-
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const Buf buf = {reinterpret_cast<float2*>(smem_raw), reinterpret_cast<float2*>(smem_raw) + QPHYS};   // QPHYS chunks
-    double2* s_base = reinterpret_cast<double2*>(smem_raw + (size_t)QPHYS * 16);   // [ROUNDS][NW][2] exact running sums
-    unsigned char* s_lo = reinterpret_cast<unsigned char*>(s_base + ROUNDS * NW * 2);   // image[j_blk .. +LB+16)
-    unsigned char* s_hi = s_lo + LB + 16;                                  // image[(j_blk+n)&~15 .. +LB+48)
-    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_hi + LB + 48);
-    unsigned long long* s_best = s_bar + 1;                                // [NW]
-    float* s_min = reinterpret_cast<float*>(s_best + NW);                  // [NW]
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int64_t item = item_first + blockIdx.x;
-    const int q = __ldg(item_query + blockIdx.x);
-    const QueryDesc d = desc[q];
-    const int64_t k = d.k0 + (item - d.itemBase);
-    const int64_t j_blk = k * LB;
-
-    // ---------------- 0. stage what the epilogue needs (uint8 streams) ----------------------
-    if (is_u8) {
-        const int64_t hi0 = (j_blk + d.tlen) & ~(int64_t)15;
-        const int64_t limit = (img_n + 16) & ~(int64_t)15;               // allocation has 16 bytes of slack
-        if (tid == 0) {
-            int64_t lo_bytes = limit - j_blk; if (lo_bytes > LB + 16) lo_bytes = LB + 16; if (lo_bytes < 0) lo_bytes = 0;
-            int64_t hi_bytes = limit - hi0;   if (hi_bytes > LB + 48) hi_bytes = LB + 48; if (hi_bytes < 0) hi_bytes = 0;
-            mbar_init(s_bar, 1);
-            mbar_expect_tx(s_bar, (unsigned)(lo_bytes + hi_bytes));
-            if (lo_bytes) tma_load_1d(s_lo, img8 + j_blk, (unsigned)lo_bytes, s_bar);
-            if (hi_bytes) tma_load_1d(s_hi, img8 + hi0, (unsigned)hi_bytes, s_bar);
-        }
-        if (tid < ROUNDS * NW * 2) {
-            const int c = tid / (NW * 2), w = (tid >> 1) % NW, which = tid & 1;
-            const int64_t jw = j_blk + c * LAGS_PER_ROUND + w * 256;
-            if (jw < d.lag0 + d.nlags) cp_async16(s_base + tid, ipfx + jw + (which ? d.tlen : 0));
-        }
-    }
-
-    // ---------------- 1+2. spectral multiply-accumulate, packing, first radix-2 step --------
-    {
-        int P = d.P;
-        if (k + P > nblk) P = (int)(nblk - k);        // rows past the end of the stream are zero
-        const float4* tp = That + (d.partBase - part_first) * (int64_t)QROW;
-        const float4* xp = Xhat + k * (int64_t)QROW;
-        const float2 wbase = __ldg(tab.wb + tid);
-        const int tm = (T - tid) & (T - 1);           // mirrored chunks C[B/2 - i] live in thread tm's column
-        const int col = phys(tid), mcol = phys(tm);
-        constexpr int U = 4;                          // quads in flight per thread
-#pragma unroll 1
-        for (int half = 0; half < 2; ++half) {
-            const int i0 = tid + half * (U * T);
-            float2 aR[U], aI[U], mR[U], mI[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) { aR[u] = aI[u] = mR[u] = mI[u] = make_float2(0.f, 0.f); }
-#pragma unroll 1
-            for (int p = 0; p < P; ++p) {
-                const float4* t = tp + (int64_t)p * QROW + i0;
-                const float4* x = xp + (int64_t)p * QROW + i0;
-                float4 ta[U], tmm[U], xa[U], xm[U];
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    ta[u] = ldg_stream(t + u * T);  tmm[u] = ldg_stream(t + QOFF_M + u * T);
-                    xa[u] = ldg_stream(x + u * T);  xm[u] = ldg_stream(x + QOFF_M + u * T);
-                }
-#pragma unroll
-                for (int u = 0; u < U; ++u) {       // Y += conj(T) * X on both slots
-                    const C2 tA = from4(ta[u]), xA = from4(xa[u]), tM = from4(tmm[u]), xM = from4(xm[u]);
-                    aR[u] = fma2(tA.r, xA.r, aR[u]);  aR[u] = fma2(tA.i, xA.i, aR[u]);
-                    aI[u] = fma2(tA.r, xA.i, aI[u]);  aI[u] = fma2(neg2(tA.i), xA.r, aI[u]);
-                    mR[u] = fma2(tM.r, xM.r, mR[u]);  mR[u] = fma2(tM.i, xM.i, mR[u]);
-                    mI[u] = fma2(tM.r, xM.i, mI[u]);  mI[u] = fma2(neg2(tM.i), xM.r, mI[u]);
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int uu = half * U + u;          // i = tid + 512*uu
-                const float c = wbase.x * kC64[uu] - wbase.y * kS64[uu];
-                const float s = wbase.x * kS64[uu] + wbase.y * kC64[uu];
-                C2 lo, hi;
-                pack_quad(aR[u], aI[u], mR[u], mI[u], c, s, lo, hi);
-                buf.st(col + 544 * uu, lo);                       // C[i]
-                // C[B/2 - i]: chunk (T - tid) + 512*(15 - uu), or 512*(16 - uu) for tid = 0 (none for i = 0)
-                if (tid != 0) buf.st(mcol + 544 * (15 - uu), hi);
-                else if (uu != 0) buf.st(mcol + 544 * (16 - uu), hi);
-            }
-        }
-        if (warp == NW - 1) {                       // the self-mirrored quad i = B/4, partitions spread over the lanes
-            float2 aR = make_float2(0.f, 0.f), aI = aR, mR = aR, mI = aR;
-            for (int p = lane; p < P; p += 32) {
-                const C2 tA = from4(__ldg(tp + (int64_t)p * QROW + Q4)), tM = from4(__ldg(tp + (int64_t)p * QROW + QOFF_M + Q4));
-                const C2 xA = from4(__ldg(xp + (int64_t)p * QROW + Q4)), xM = from4(__ldg(xp + (int64_t)p * QROW + QOFF_M + Q4));
-                aR = fma2(tA.r, xA.r, aR);  aR = fma2(tA.i, xA.i, aR);
-                aI = fma2(tA.r, xA.i, aI);  aI = fma2(neg2(tA.i), xA.r, aI);
-                mR = fma2(tM.r, xM.r, mR);  mR = fma2(tM.i, xM.i, mR);
-                mI = fma2(tM.r, xM.i, mI);  mI = fma2(neg2(tM.i), xM.r, mI);
-            }
-            if (P > 1) {
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    aR.x += __shfl_xor_sync(0xffffffffu, aR.x, o); aR.y += __shfl_xor_sync(0xffffffffu, aR.y, o);
-                    aI.x += __shfl_xor_sync(0xffffffffu, aI.x, o); aI.y += __shfl_xor_sync(0xffffffffu, aI.y, o);
-                    mR.x += __shfl_xor_sync(0xffffffffu, mR.x, o); mR.y += __shfl_xor_sync(0xffffffffu, mR.y, o);
-                    mI.x += __shfl_xor_sync(0xffffffffu, mI.x, o); mI.y += __shfl_xor_sync(0xffffffffu, mI.y, o);
-                }
-            }
-            if (lane == 0) {
-                const float h = 0.70710678118654752f;       // exp(i*pi/4)
-                C2 lo, hi;
-                pack_quad(aR, aI, mR, mI, h, h, lo, hi);
-                buf.st(phys(Q4), lo);                        // C[B/4] (its mirror is itself)
-            }
-        }
-    }
-    __syncthreads();
-
-    // ---------------- 3. three radix-16 Stockham passes over the 8192 (u, v) pairs ----------
-    // pass: butterfly j = tid reads chunk j + 512r, twiddles by exp(2*pi*i*r*k/(16*Ns)), k = j mod Ns,
-    // writes chunk (j-k)*16 + k + r*Ns.  phys(j + 512r) = phys(j) + 544r.
-    {
-        C2 v[16];
-        const int src = phys(tid);
-        {   // pass 1: Ns = 1, no twiddles; out chunk 16j + r -> 17j + r
-#pragma unroll
-            for (int r = 0; r < 16; ++r) v[r] = buf.ld(src + 544 * r);
-            __syncthreads();
-            dft16p(v);
-            const int dst = 17 * tid;
-#pragma unroll
-            for (int r = 0; r < 16; ++r) buf.st(dst + r, v[brev<16>(r)]);
-            __syncthreads();
-        }
-        {   // pass 2: Ns = 16, k = tid & 15; out chunk 256a + 16r + k -> 272a + 17r + k, a = tid >> 4
-            const int kk = tid & 15;
-            float4 tw[8];
-#pragma unroll
-            for (int a = 0; a < 8; ++a) tw[a] = __ldg(tab.tw2 + a * 16 + kk);
-#pragma unroll
-            for (int r = 0; r < 16; ++r) v[r] = buf.ld(src + 544 * r);
-            __syncthreads();
-#pragma unroll
-            for (int r = 1; r < 16; ++r) {
-                const float4 t = tw[r >> 1];
-                v[r] = (r & 1) ? cmul_s(v[r], t.z, t.w) : cmul_s(v[r], t.x, t.y);
-            }
-            dft16p(v);
-            const int dst = 272 * (tid >> 4) + kk;
-#pragma unroll
-            for (int r = 0; r < 16; ++r) buf.st(dst + 17 * r, v[brev<16>(r)]);
-            __syncthreads();
-        }
-        {   // pass 3: Ns = 256, k = tid & 255; out chunk 4096a + 256r + k -> 4352a + 272r + phys(k), a = tid >> 8
-            const int kk = tid & 255;
-            float4 tw[8];
-#pragma unroll
-            for (int a = 0; a < 8; ++a) tw[a] = __ldg(tab.tw3 + a * 256 + kk);
-#pragma unroll
-            for (int r = 0; r < 16; ++r) v[r] = buf.ld(src + 544 * r);
-            __syncthreads();
-#pragma unroll
-            for (int r = 1; r < 16; ++r) {
-                const float4 t = tw[r >> 1];
-                v[r] = (r & 1) ? cmul_s(v[r], t.z, t.w) : cmul_s(v[r], t.x, t.y);
-            }
-            dft16p(v);
-            const int dst = 4352 * (tid >> 8) + phys(kk);
-#pragma unroll
-            for (int r = 0; r < 16; ++r) buf.st(dst + 272 * r, v[brev<16>(r)]);
-            if (is_u8) cp_async_commit_wait_all();          // the staged running sums landed long ago
-            __syncthreads();
-        }
-    }
-    // now E = chunks [0, 4096), O = chunks [4096, 8192); the half-size transforms are
-    //   X'[j] = E[j] + W8192^j * O[j]   (j < 4096; the "-" half carries no valid lag)
-    // and chunk j of X' holds the correlation (times 2B) at lags 4j .. 4j+3 = (u.re, u.im, v.re, v.im)
-
-    // ---------------- 4. window sums, fp32 screening, fp64 exact evaluation -----------------
+    const Buf& buf = sm.buf;
+    const int lane = tid & 31, warp = tid >> 5;
+    const QueryDesc& d = it.d;
+    const int64_t j_blk = it.j_blk;
     const int64_t n = d.tlen;
     const int64_t jlo = d.lag0, jhi = d.lag0 + d.nlags;
     const double2 t_hi = tpfx[d.toff + n], t_lo = tpfx[d.toff];
@@ -358,7 +337,7 @@ k_match_packed(const float4* __restrict__ That, int64_t part_first,
 
     float vf[ROUNDS][8];
     float tmin = 2.0f;
-    if (is_u8) mbar_wait(s_bar, 0);
+    if (is_u8) mbar_wait(s_bar, bar_parity);
 #pragma unroll
     for (int c = 0; c < ROUNDS; ++c) {
         const int m0 = c * LAGS_PER_ROUND + tid * 8;
@@ -392,10 +371,10 @@ k_match_packed(const float4* __restrict__ That, int64_t part_first,
             // everything comes from shared memory: lane l owns the run of 8 lags starting at jw + 8l.  Window
             // sums at the head of a run = exact warp base + exclusive intra-warp scan of the runs' integer totals
             const int hi_off = (int)((j_blk + n) & 15);
-            lo8 = *reinterpret_cast<const unsigned long long*>(s_lo + m0);
+            lo8 = *reinterpret_cast<const unsigned long long*>(sm.lo + m0);
             const int hb = hi_off + m0;
-            const unsigned long long h0 = *reinterpret_cast<const unsigned long long*>(s_hi + (hb & ~7));
-            const unsigned long long h1 = *reinterpret_cast<const unsigned long long*>(s_hi + (hb & ~7) + 8);
+            const unsigned long long h0 = *reinterpret_cast<const unsigned long long*>(sm.hi + (hb & ~7));
+            const unsigned long long h1 = *reinterpret_cast<const unsigned long long*>(sm.hi + (hb & ~7) + 8);
             const unsigned sh = (unsigned)(hb & 7) * 8u;
             hi8 = sh ? ((h0 >> sh) | (h1 << (64u - sh))) : h0;
             const unsigned la = (unsigned)lo8, lb = (unsigned)(lo8 >> 32), ha = (unsigned)hi8, hb2 = (unsigned)(hi8 >> 32);
@@ -407,7 +386,7 @@ k_match_packed(const float4* __restrict__ That, int64_t part_first,
                 const int uq = __shfl_up_sync(0xffffffffu, iq, o), us = __shfl_up_sync(0xffffffffu, is, o);
                 if (lane >= o) { iq += uq; is += us; }
             }
-            const double2 b_lo = s_base[(c * NW + warp) * 2], b_hi = s_base[(c * NW + warp) * 2 + 1];
+            const double2 b_lo = sm.base[(c * NW + warp) * 2], b_hi = sm.base[(c * NW + warp) * 2 + 1];
             const double w0s = (b_hi.x - b_lo.x) + (double)(is - ts);
             const double w0q = (b_hi.y - b_lo.y) + (double)(iq - tq);
             f_w0q = (float)w0q;
@@ -448,7 +427,8 @@ k_match_packed(const float4* __restrict__ That, int64_t part_first,
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) tmin = fminf(tmin, __shfl_xor_sync(0xffffffffu, tmin, o));
     if (lane == 0) s_min[warp] = tmin;
-    __syncthreads();
+    csync<ID>();
+    after_read();
     float bmin = s_min[0];
 #pragma unroll
     for (int w = 1; w < NW; ++w) bmin = fminf(bmin, s_min[w]);
@@ -486,11 +466,338 @@ k_match_packed(const float4* __restrict__ That, int64_t part_first,
         best = other < best ? other : best;
     }
     if (lane == 0) s_best[warp] = best;
-    __syncthreads();
+    csync<ID>();
     if (tid == 0) {
         for (int w = 1; w < NW; ++w) best = s_best[w] < best ? s_best[w] : best;
-        if (best != ~0ull) atomicMin(keys + q, best);
+        if (best != ~0ull) atomicMin(keys + it.q, best);
     }
+}
+
+// ---------------------------------------------------------------- kernel A: one CTA per item
+template <typename S>
+__global__ void __launch_bounds__(QT, 1)
+k_match_packed(const float4* __restrict__ That, int64_t part_first,
+               const float4* __restrict__ Xhat, int64_t nblk,
+               const S* __restrict__ img, int64_t img_n,
+               const double2* __restrict__ ipfx, const double2* __restrict__ tpfx,
+               const QueryDesc* __restrict__ desc, const int* __restrict__ item_query, int64_t item_first,
+               PackedTables tab, unsigned long long* __restrict__ keys, float* __restrict__ curve_out) {
+    constexpr int T = QT, NW = QNW;
+    constexpr bool is_u8 = sizeof(S) == 1;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const Smem sm(smem_raw);
+    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(sm.end);
+    unsigned long long* s_best = s_bar + 1;                                // [NW]
+    float* s_min = reinterpret_cast<float*>(s_best + NW);                  // [NW]
+    const Buf& buf = sm.buf;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const Item it(desc, item_query, item_first, blockIdx.x);
+    const QueryDesc& d = it.d;
+
+    // ---------------- 0. stage what the epilogue needs; the latency hides behind the MAC and the FFT
+    if (is_u8) {
+        if (tid == 0) mbar_init(s_bar, 1);
+        stage_inputs(it, tid, reinterpret_cast<const uint8_t*>(img), img_n, ipfx, sm, s_bar);
+    }
+
+    // ---------------- 1+2. spectral multiply-accumulate, packing, first radix-2 step --------
+    {
+        int P = d.P;
+        if (it.k + P > nblk) P = (int)(nblk - it.k);      // rows past the end of the stream are zero
+        const float4* tp = That + (d.partBase - part_first) * (int64_t)QROW;
+        const float4* xp = Xhat + it.k * (int64_t)QROW;
+        const float2 wbase = __ldg(tab.wb + tid);
+        const int tm = (T - tid) & (T - 1);           // mirrored chunks C[B/2 - i] live in thread tm's column
+        const int col = phys(tid), mcol = phys(tm);
+        constexpr int U = 4;                          // quads in flight per thread
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+            const int i0 = tid + half * (U * T);
+            QuadAcc acc[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) acc[u].zero();
+#pragma unroll 1
+            for (int p = 0; p < P; ++p) {
+                const float4* t = tp + (int64_t)p * QROW + i0;
+                const float4* x = xp + (int64_t)p * QROW + i0;
+                float4 ta[U], tmm[U], xa[U], xm[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    ta[u] = ldg_stream(t + u * T);  tmm[u] = ldg_stream(t + QOFF_M + u * T);
+                    xa[u] = ldg_stream(x + u * T);  xm[u] = ldg_stream(x + QOFF_M + u * T);
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) acc[u].mac(ta[u], tmm[u], xa[u], xm[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int uu = half * U + u;          // i = tid + 512*uu
+                const float c = wbase.x * kC64[uu] - wbase.y * kS64[uu];
+                const float s = wbase.x * kS64[uu] + wbase.y * kC64[uu];
+                C2 lo, hi;
+                pack_quad(acc[u].aR, acc[u].aI, acc[u].mR, acc[u].mI, c, s, lo, hi);
+                buf.st(col + 544 * uu, lo);                       // C[i]
+                // C[B/2 - i]: chunk (T - tid) + 512*(15 - uu), or 512*(16 - uu) for tid = 0 (none for i = 0)
+                if (tid != 0) buf.st(mcol + 544 * (15 - uu), hi);
+                else if (uu != 0) buf.st(mcol + 544 * (16 - uu), hi);
+            }
+        }
+        if (warp == NW - 1) {                       // the self-mirrored quad i = B/4
+            const C2 lo = special_quad(tp, xp, P, lane);
+            if (lane == 0) buf.st(phys(Q4), lo);
+        }
+    }
+    csync<0>();
+
+    // ---------------- 3. inverse FFT, 4. epilogue ---------------------------------------------
+    fft_passes<0>(buf, tid, tab, is_u8);
+    finish_item<S, 0>(it, tid, sm, s_bar, 0u, s_best, s_min, img, img_n, ipfx, tpfx, tab, keys, curve_out, [] {});
+}
+
+// ---------------------------------------------------------------- kernel B: persistent, warp-specialised
+// k_match_packed runs its phases back to back on one CTA per SM: while it multiplies (loads from L2, issue
+// slots idle) nothing transforms, and while it transforms nothing loads.  Here one persistent CTA per SM
+// splits the work over two roles that overlap across consecutive items:
+//   4 multiply warps       thread L owns quads i = L + 128*seg.  Lane 0 of each warp keeps a private ring of
+//                          WS_STAGES stages (32 quads x {T^ A, T^ M, X^ A, X^ M} = 2 KB each) filled by TMA bulk
+//                          copies WS_STAGES-1 steps ahead -- across items, so the L2 latency never surfaces;
+//                          the warp multiply-accumulates from the ring, does the Hermitian packing + first
+//                          radix-2 step and parks the result in TENSOR MEMORY with tcgen05.st (the tensor
+//                          cores are idle, so their 256 KB of TMEM are a free second buffer: two items of
+//                          128 KB, double buffered);
+//   16 transform warps     tcgen05.ld the parked item into the FFT buffer, then exactly the passes and the
+//                          epilogue of k_match_packed.
+// Thread L of the multiply warps writes TMEM lane L (a warp reaches only the 32 lanes of its quarter), columns
+// b*256 + 8*seg + {0..3: C[i], 4..7: C[B/2 - i]}; transform thread t reads lane t & 127, 64 columns from
+// (t >> 7)*64, and scatters the 16 chunks to their places.
+constexpr int WS_THREADS = 640, WS_STAGES = 6, WS_SEG = 128, WS_SEGS = Q4 / WS_SEG;
+constexpr int WS_STAGE_F4 = 4 * 32;                      // float4 per ring stage of one multiply warp: 4 arrays x 32 quads
+constexpr unsigned WS_STAGE_BYTES = WS_STAGE_F4 * 16;
+
+// exp(+i*pi*s/128), s = 0..31: the packing twiddle of quad i = L + 128s is wb[L] times this
+__device__ constexpr float kC256[32] = {
+    1.0f, 0.99969881869620425f, 0.99879545620517241f, 0.99729045667869021f, 0.99518472667219693f, 0.99247953459870997f,
+    0.98917650996478101f, 0.98527764238894122f, 0.98078528040323043f, 0.97570213003852857f, 0.97003125319454397f,
+    0.96377606579543984f, 0.95694033573220882f, 0.94952818059303667f, 0.94154406518302081f, 0.93299279883473896f,
+    0.92387953251128674f, 0.91420975570353069f, 0.90398929312344334f, 0.89322430119551532f, 0.88192126434835505f,
+    0.87008699110871146f, 0.85772861000027212f, 0.84485356524970712f, 0.83146961230254524f, 0.81758481315158371f,
+    0.80320753148064494f, 0.78834642762660634f, 0.77301045336273699f, 0.75720884650648457f, 0.74095112535495911f,
+    0.724247082951467f};
+__device__ constexpr float kS256[32] = {
+    0.0f, 0.024541228522912288f, 0.049067674327418015f, 0.073564563599667426f, 0.098017140329560604f, 0.1224106751992162f,
+    0.14673047445536175f, 0.17096188876030122f, 0.19509032201612825f, 0.2191012401568698f, 0.24298017990326387f,
+    0.26671275747489837f, 0.29028467725446233f, 0.31368174039889152f, 0.33688985339222005f, 0.35989503653498811f,
+    0.38268343236508978f, 0.40524131400498986f, 0.42755509343028208f, 0.44961132965460654f, 0.47139673682599764f,
+    0.49289819222978404f, 0.51410274419322166f, 0.53499761988709715f, 0.55557023301960218f, 0.57580819141784534f,
+    0.59569930449243336f, 0.61523159058062682f, 0.63439328416364549f, 0.65317284295377676f, 0.67155895484701833f,
+    0.68954054473706683f};
+
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(b) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_slot, uint32_t ncols) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(smem_slot);
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(a), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, float v0, float v1, float v2, float v3, float v4, float v5, float v6, float v7) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 :: "r"(taddr), "f"(v0), "f"(v1), "f"(v2), "f"(v3), "f"(v4), "f"(v5), "f"(v6), "f"(v7) : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, float v0, float v1, float v2, float v3) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
+                 :: "r"(taddr), "f"(v0), "f"(v1), "f"(v2), "f"(v3) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]),
+                   "=f"(v[8]), "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+template <typename S>
+__global__ void __launch_bounds__(WS_THREADS, 1)
+k_match_ws(const float4* __restrict__ That, int64_t part_first,
+           const float4* __restrict__ Xhat, int64_t nblk,
+           const S* __restrict__ img, int64_t img_n,
+           const double2* __restrict__ ipfx, const double2* __restrict__ tpfx,
+           const QueryDesc* __restrict__ desc, const int* __restrict__ item_query, int64_t item_first, int64_t n_items,
+           PackedTables tab, unsigned long long* __restrict__ keys, float* __restrict__ curve_out) {
+    constexpr int NW = QNW;
+    constexpr bool is_u8 = sizeof(S) == 1;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const Smem sm(smem_raw);
+    float4* ring = reinterpret_cast<float4*>(sm.end);                              // [4 warps][WS_STAGES] stages
+    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(ring + 4 * WS_STAGES * WS_STAGE_F4);   // staged windows
+    unsigned long long* ring_full = s_bar + 1;                                     // [4][WS_STAGES]
+    unsigned long long* tm_full = ring_full + 4 * WS_STAGES;                       // [2]
+    unsigned long long* tm_empty = tm_full + 2;                                    // [2]
+    unsigned long long* s_best = tm_empty + 2;                                     // [NW]
+    float* s_min = reinterpret_cast<float*>(s_best + NW);                          // [NW]
+    uint32_t* s_taddr = reinterpret_cast<uint32_t*>(s_min + NW);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        mbar_init(s_bar, 1);
+        for (int i = 0; i < 4 * WS_STAGES; ++i) mbar_init(ring_full + i, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(tm_full + i, WS_SEG); mbar_init(tm_empty + i, QT); }
+    }
+    if (warp == 0) tmem_alloc(s_taddr, 512);
+    tmem_fence_before();
+    __syncthreads();
+    tmem_fence_after();
+    const uint32_t taddr = *s_taddr;
+
+    if (warp < NW) {
+        // ======================= transform warps =======================
+        const Buf& buf = sm.buf;
+        const int Lc = tid & 127, g = tid >> 7;
+        const uint32_t t_in = taddr + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(g * 64);
+        const int lo_base = phys(Lc) + 1088 * g;                                   // chunk Lc + 128m at phys(Lc) + 136m
+        const int hi_base = (Lc ? phys(128 - Lc) + 136 * 63 : 136 * 64) - 1088 * g;   // chunk B/2 - (Lc + 128m), minus 136m
+        if (is_u8 && (int64_t)blockIdx.x < n_items) {
+            const Item first(desc, item_query, item_first, blockIdx.x);
+            stage_inputs(first, tid, reinterpret_cast<const uint8_t*>(img), img_n, ipfx, sm, s_bar);
+        }
+        unsigned n = 0;
+        for (int64_t local = blockIdx.x; local < n_items; local += gridDim.x, ++n) {
+            const Item it(desc, item_query, item_first, local);
+            const unsigned b = n & 1u;
+            // ---- un-park: TMEM -> registers -> FFT buffer
+            mbar_wait(tm_full + b, (n >> 1) & 1u);
+            tmem_fence_after();
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+                float v[16];
+                tmem_ld16(t_in + b * 256u + (uint32_t)(c4 * 16), v);
+                tmem_wait_ld();
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int mm = 2 * c4 + h;                                   // quad m = 8g + mm of multiply thread Lc
+                    const C2 lo = {make_float2(v[8 * h + 0], v[8 * h + 1]), make_float2(v[8 * h + 2], v[8 * h + 3])};
+                    const C2 hi = {make_float2(v[8 * h + 4], v[8 * h + 5]), make_float2(v[8 * h + 6], v[8 * h + 7])};
+                    buf.st(lo_base + 136 * mm, lo);
+                    // quad 0 has no mirror: its second half carries the self-mirrored chunk C[B/4]
+                    const int hp = (mm == 0 && tid == 0) ? phys(Q4) : hi_base - 136 * mm;
+                    buf.st(hp, hi);
+                }
+            }
+            tmem_fence_before();
+            mbar_arrive(tm_empty + b);
+            csync<1>();
+            fft_passes<1>(buf, tid, tab, is_u8);
+            finish_item<S, 1>(it, tid, sm, s_bar, n & 1u, s_best, s_min, img, img_n, ipfx, tpfx, tab, keys, curve_out,
+                              [&] {   // every thread is done with the staged windows: start the next item's copies
+                                  if (is_u8 && local + gridDim.x < n_items) {
+                                      const Item nxt(desc, item_query, item_first, local + gridDim.x);
+                                      stage_inputs(nxt, tid, reinterpret_cast<const uint8_t*>(img), img_n, ipfx, sm, s_bar);
+                                  }
+                              });
+        }
+    } else {
+        // ======================= multiply warps (each feeds its own ring) =======================
+        const int mw = warp - NW;                                                 // 0 .. 3 = TMEM lane quarter
+        const int L = tid - QT;                                                   // 0 .. 127 = TMEM lane
+        const uint32_t t_out = taddr + ((uint32_t)(mw * 32) << 16);
+        const float2 wbase = __ldg(tab.wb + L);
+        float4* const myring = ring + mw * (WS_STAGES * WS_STAGE_F4);             // stages of 4 arrays x 32 quads
+        unsigned long long* const full = ring_full + mw * WS_STAGES;
+
+        // issue cursor: the (item, segment, partition) step whose rows are copied next; every lane tracks it
+        // (uniform values), lane 0 issues.  Steps are consumed in the same order, WS_STAGES - 1 steps later.
+        int64_t i_local = blockIdx.x;
+        int i_seg = 0, i_p = 0, i_P = 0;
+        const float4 *i_tp = nullptr, *i_xp = nullptr;
+        unsigned i_stage = 0;
+        auto cursor_load = [&]() {          // rows of item i_local (skips nothing: P >= 1 for every item)
+            if (i_local < n_items) {
+                const Item it(desc, item_query, item_first, i_local);
+                i_P = it.d.P;
+                if (it.k + i_P > nblk) i_P = (int)(nblk - it.k);
+                i_tp = That + (it.d.partBase - part_first) * (int64_t)QROW + mw * 32;
+                i_xp = Xhat + it.k * (int64_t)QROW + mw * 32;
+            }
+        };
+        auto issue = [&]() {
+            if (i_local >= n_items) return;
+            if (lane == 0) {
+                float4* st = myring + i_stage * WS_STAGE_F4;
+                const float4* t = i_tp + (int64_t)i_p * QROW + i_seg * WS_SEG;
+                const float4* x = i_xp + (int64_t)i_p * QROW + i_seg * WS_SEG;
+                mbar_expect_tx(full + i_stage, WS_STAGE_BYTES);
+                tma_load_1d(st, t, 512, full + i_stage);
+                tma_load_1d(st + 32, t + QOFF_M, 512, full + i_stage);
+                tma_load_1d(st + 64, x, 512, full + i_stage);
+                tma_load_1d(st + 96, x + QOFF_M, 512, full + i_stage);
+            }
+            if (++i_stage == WS_STAGES) i_stage = 0;
+            if (++i_p >= i_P) {
+                i_p = 0;
+                if (++i_seg == WS_SEGS) { i_seg = 0; i_local += gridDim.x; cursor_load(); }
+            }
+        };
+        cursor_load();
+        for (int s0 = 0; s0 < WS_STAGES - 1; ++s0) issue();
+
+        unsigned stage = 0, phase = 0, n = 0;
+        for (int64_t local = blockIdx.x; local < n_items; local += gridDim.x, ++n) {
+            const Item it(desc, item_query, item_first, local);
+            int P = it.d.P;
+            if (it.k + P > nblk) P = (int)(nblk - it.k);
+            const unsigned b = n & 1u;
+            mbar_wait(tm_empty + b, ((n >> 1) & 1u) ^ 1u);                         // the transform warps drained this half
+            tmem_fence_after();
+            float h0 = 0.f, h1 = 0.f, h2 = 0.f, h3 = 0.f;
+            for (int seg = 0; seg < WS_SEGS; ++seg) {
+                QuadAcc acc; acc.zero();
+                for (int p = 0; p < P; ++p) {
+                    issue();                                                       // refills the stage read one step ago
+                    mbar_wait(full + stage, phase);
+                    const float4* st = myring + stage * WS_STAGE_F4 + lane;
+                    acc.mac(st[0], st[32], st[64], st[96]);
+                    __syncwarp();                                                  // every lane has read this stage
+                    if (++stage == WS_STAGES) { stage = 0; phase ^= 1u; }
+                }
+                const float c = wbase.x * kC256[seg] - wbase.y * kS256[seg];
+                const float s = wbase.x * kS256[seg] + wbase.y * kC256[seg];
+                C2 lo, hi;
+                pack_quad(acc.aR, acc.aI, acc.mR, acc.mI, c, s, lo, hi);
+                if (seg == 0) {               // warp NW writes the second half of quad 0 later (see below)
+                    tmem_st4(t_out + b * 256u, lo.r.x, lo.r.y, lo.i.x, lo.i.y);
+                    h0 = hi.r.x; h1 = hi.r.y; h2 = hi.i.x; h3 = hi.i.y;
+                    if (warp != NW) tmem_st4(t_out + b * 256u + 4u, h0, h1, h2, h3);
+                } else {
+                    tmem_st8(t_out + b * 256u + (uint32_t)(seg * 8), lo.r.x, lo.r.y, lo.i.x, lo.i.y, hi.r.x, hi.r.y, hi.i.x, hi.i.y);
+                }
+            }
+            if (warp == NW) {                     // the self-mirrored quad i = B/4 rides in the unused half of quad 0 (lane 0)
+                const float4* tp = That + (it.d.partBase - part_first) * (int64_t)QROW;
+                const float4* xp = Xhat + it.k * (int64_t)QROW;
+                const C2 sp = special_quad(tp, xp, P, lane);
+                if (lane == 0) { h0 = sp.r.x; h1 = sp.r.y; h2 = sp.i.x; h3 = sp.i.y; }
+                tmem_st4(t_out + b * 256u + 4u, h0, h1, h2, h3);
+            }
+            tmem_wait_st();
+            tmem_fence_before();
+            mbar_arrive(tm_full + b);
+        }
+    }
+    tmem_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(taddr, 512);
+}
+
+size_t ws_smem_bytes() {
+    return kSmemCommon + (size_t)4 * WS_STAGES * WS_STAGE_BYTES + 8 * (1 + 4 * WS_STAGES + 4) + QNW * sizeof(unsigned long long)
+         + QNW * sizeof(float) + 16 + 64;
 }
 
 // ---------------------------------------------------------------- forward spectra, quad layout
@@ -574,9 +881,7 @@ size_t forward_smem_bytes14() {
 }
 
 size_t packed_smem_bytes() {
-    const size_t rounds = QB / (QT * 8);
-    return (size_t)QPHYS * sizeof(float4) + rounds * QNW * 2 * sizeof(double2) + (QB + 16) + (QB + 48)
-         + 8 + QNW * sizeof(unsigned long long) + QNW * sizeof(float) + 64;
+    return kSmemCommon + 8 + QNW * sizeof(unsigned long long) + QNW * sizeof(float) + 64;
 }
 
 float* g_ptab_dev = nullptr;
@@ -684,6 +989,42 @@ int launch_match_packed(const sb_stream* image, const sb_stream* tmpl, const flo
                 static_cast<const float*>(image->d_raw), image->n, image->d_pfx, tmpl->d_pfx, d_desc, g_item_query2 + i0, item_first + i0,
                 tab, d_keys, d_curve);
     }
+    SB_CUDA(cudaGetLastError());
+    return SB_OK;
+}
+
+int launch_match_ws(const sb_stream* image, const sb_stream* tmpl, const float2* d_parts, int64_t part_first,
+                    const QueryDesc* d_desc, int q_begin, int q_end, int64_t item_first, int64_t n_items,
+                    unsigned long long* d_keys, float* d_curve) {
+    Ctx& c = ctx();
+    PackedTables tab;
+    SB_TRY(ensure_packed_tables(&tab));
+    static bool attr_set = false;
+    const size_t smem = ws_smem_bytes();
+    if (!attr_set) {
+        SB_CUDA(cudaFuncSetAttribute(k_match_ws<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SB_CUDA(cudaFuncSetAttribute(k_match_ws<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    if (g_item_query2_cap < n_items) {
+        cudaStreamSynchronize(c.stream);
+        cudaFree(g_item_query2); g_item_query2 = nullptr; g_item_query2_cap = 0;
+        SB_CUDA(cudaMalloc(&g_item_query2, sizeof(int) * (size_t)n_items));
+        g_item_query2_cap = n_items;
+    }
+    k_fill_item_query2<<<(unsigned)(q_end - q_begin), 128, 0, c.stream>>>(d_desc, q_begin, item_first, g_item_query2);
+    c.launches += 1;
+    const unsigned grid = (unsigned)std::min<int64_t>(n_items, c.sm_count);     // one persistent CTA per SM
+    if (image->dtype == SB_U8)
+        k_match_ws<uint8_t><<<grid, WS_THREADS, smem, c.stream>>>(
+            reinterpret_cast<const float4*>(d_parts), part_first, reinterpret_cast<const float4*>(image->d_spec), image->nblk,
+            static_cast<const uint8_t*>(image->d_raw), image->n, image->d_pfx, tmpl->d_pfx, d_desc, g_item_query2, item_first, n_items,
+            tab, d_keys, d_curve);
+    else
+        k_match_ws<float><<<grid, WS_THREADS, smem, c.stream>>>(
+            reinterpret_cast<const float4*>(d_parts), part_first, reinterpret_cast<const float4*>(image->d_spec), image->nblk,
+            static_cast<const float*>(image->d_raw), image->n, image->d_pfx, tmpl->d_pfx, d_desc, g_item_query2, item_first, n_items,
+            tab, d_keys, d_curve);
     SB_CUDA(cudaGetLastError());
     return SB_OK;
 }

@@ -57,7 +57,7 @@ struct Ctx {
     cudaStream_t stream = nullptr;
     int B = 16384;                 // lag-block size (samples); FFT size is 2B
     int chunk_items = 1024;        // items per MAC/C2R/normalise chunk (cuFFT engine)
-    int engine = 2;                // 2: packed fused kernel (sb_fused2.cu, B = 16384), 1: fused lag-block kernel (sb_fused.cu), 0: cuFFT pipeline
+    int engine = 3;                // 3: warp-specialised packed kernel, 2: packed fused kernel (sb_fused2.cu, B = 16384), 1: fused lag-block kernel (sb_fused.cu), 0: cuFFT pipeline
     int premac_mode = 0;           // 0: register-blocked multiply kernel when a batch averages >= 3 partitions, 1: never, 2: always
     int hop_mode = 1;              // fused engine geometry: 1 = hop B (50 % of each FFT valid, default), 2 = hop B/2 (75 %), 0 = pick per batch
     int64_t max_parts = 16384;     // template partition spectra kept per super-chunk
@@ -109,6 +109,9 @@ bool packed_supports(int B);
 int launch_match_packed(const sb_stream* image, const sb_stream* tmpl, const float2* d_parts, int64_t part_first,
                         const QueryDesc* d_desc, int q_begin, int q_end, int64_t item_first, int64_t n_items,
                         unsigned long long* d_keys, float* d_curve);
+int launch_match_ws(const sb_stream* image, const sb_stream* tmpl, const float2* d_parts, int64_t part_first,
+                    const QueryDesc* d_desc, int q_begin, int q_end, int64_t item_first, int64_t n_items,
+                    unsigned long long* d_keys, float* d_curve);
 int launch_block_spectra_quad(const sb_stream* s, int64_t k_first, int64_t rows, float2* out);
 int launch_part_spectra_quad(const sb_stream* tmpl, const QueryDesc* d_desc, int q_begin, int q_end,
                              int64_t part_first, int64_t rows, float2* out);

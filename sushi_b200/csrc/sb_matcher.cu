@@ -452,7 +452,7 @@ int run_batch(const sb_stream* image_c, const sb_stream* tmpl, int64_t count,
     // HBM), or -- for very long templates (kBlockedFromPartitions) -- the register-blocked kernel
     // k_mac_blocked over MAC_GROUP lag blocks, whose products the fused kernel then reads from a chunk buffer.
     // Engine 2: the packed kernel (sb_fused2.cu) with quad-layout spectrum rows; it covers B = 16384 at hop B.
-    const bool use_packed = c.engine == 2 && packed_supports(B) && hd == 1;
+    const bool use_packed = c.engine >= 2 && packed_supports(B) && hd == 1;
     const int nb = use_packed ? kQuadRowF2 : B + 1;          // float2 per spectrum row
     int64_t n_direct = 0, total_items = 0, total_parts = 0, total_groups = 0, maxp = 0;
     SB_TRY(plan_batch(image, tmpl, count, toff, tlen, lag0, nlags, hd, use_fused && hd == 1 && !use_packed, &n_direct,
@@ -519,8 +519,12 @@ int run_batch(const sb_stream* image_c, const sb_stream* tmpl, int64_t count,
         const int64_t item_hi = (qe < count) ? c.h_desc[qe].itemBase : total_items;
         if (use_packed) {
             ProfScope ps("match_fused");
-            SB_TRY(launch_match_packed(image, tmpl, c.d_parts, part_first, c.d_desc, (int)qb, (int)qe,
+            if (c.engine == 3)
+                SB_TRY(launch_match_ws(image, tmpl, c.d_parts, part_first, c.d_desc, (int)qb, (int)qe,
                                        item_lo, item_hi - item_lo, c.d_keys, d_curve));
+            else
+                SB_TRY(launch_match_packed(image, tmpl, c.d_parts, part_first, c.d_desc, (int)qb, (int)qe,
+                                           item_lo, item_hi - item_lo, c.d_keys, d_curve));
         } else if (use_fused && !premac) {
             ProfScope ps("match_fused");
             SB_TRY(launch_match_fused(image, tmpl, hd, c.d_parts, part_first, nullptr, c.d_desc, (int)qb, (int)qe,

@@ -213,12 +213,12 @@ int stream_finish_public(sb_stream* s) { return stream_finish(s); }
 int ensure_spectra(sb_stream* s, int hd) {
     Ctx& c = ctx();
     // effective engine: the packed kernel covers B = 16384 at hop B; everything else falls to engine 1 / 0
-    const int eng = (c.engine == 2 && packed_supports(c.B) && hd == 1) ? 2 : (c.engine >= 1 && fused_supports(c.B)) ? 1 : 0;
+    const int eng = (c.engine >= 2 && packed_supports(c.B) && hd == 1) ? 2 : (c.engine >= 1 && fused_supports(c.B)) ? 1 : 0;
     if (s->d_spec && s->specB == c.B && s->specHD == hd && s->specEngine == eng) return SB_OK;
     if (s->d_spec) { pool_free(s->d_spec); s->d_spec = nullptr; }
     const int B = c.B, H = B / hd;
     const int64_t nblk = (s->n + H - 1) / H;
-    if (c.engine == 2 && packed_supports(B) && hd == 1) {   // quad-layout rows for the packed kernel
+    if (c.engine >= 2 && packed_supports(B) && hd == 1) {   // quad-layout rows for the packed kernels
         SB_TRY(pool_alloc((void**)&s->d_spec, sizeof(float2) * (size_t)nblk * kQuadRowF2));
         {
             ProfScope ps("block_spectra");

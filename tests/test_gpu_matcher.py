@@ -93,8 +93,9 @@ def test_fused_engine_equals_cufft_engine(gpu_lib, pair, stype, block):
         curves, results = [], []
         # (engine, hop mode): the cuFFT pipeline, then the fused kernel in both overlap-save geometries
         # + the fused kernel fed by the register-blocked multiply kernel (premac 2 = for every query)
-        # + the packed fused kernel (engine 2; it covers B = 16384 and falls back to engine 1 otherwise)
-        variants = [(0, 1, 1), (1, 1, 1), (1, 2, 1), (1, 1, 2), (2, 1, 1)]
+        # + the packed fused kernels (engine 2 one CTA per item, engine 3 persistent warp-specialised; they cover
+        # B = 16384 and fall back to engine 1 otherwise)
+        variants = [(0, 1, 1), (1, 1, 1), (1, 2, 1), (1, 1, 2), (2, 1, 1), (3, 1, 1)]
         for engine, hop, premac in variants:
             _native.check(gpu_lib.sb_set_engine(engine))
             _native.check(gpu_lib.sb_set_hop_mode(hop))
@@ -105,12 +106,12 @@ def test_fused_engine_equals_cufft_engine(gpu_lib, pair, stype, block):
             # the batch result is the first-index minimum of the variant's own curve
             d, i = dst.find_planned(src, [toff], [n], [lag0], [nlags])
             assert i[0] == int(curves[-1].argmin()) and d[0] == curves[-1].min()
-        for e in (1, 2, 3, 4):
+        for e in (1, 2, 3, 4, 5):
             assert np.abs(curves[0] - curves[e]).max() <= 2e-6
             assert np.abs(results[0][0] - results[e][0]).max() <= 2e-6
             assert np.abs(results[0][1] - results[e][1]).max() <= 1
     finally:
-        _native.check(gpu_lib.sb_set_engine(2))
+        _native.check(gpu_lib.sb_set_engine(3))
         _native.check(gpu_lib.sb_set_hop_mode(1))
         _native.check(gpu_lib.sb_set_premac_mode(0))
         _native.check(gpu_lib.sb_set_block_size(16384))
@@ -316,13 +317,13 @@ def test_empty_batch_is_a_no_op(gpu_lib, pair):
     assert len(d) == 0 and len(i) == 0
 
 
-@pytest.mark.parametrize('engine', [0, 1, 2, 3, 4])
+@pytest.mark.parametrize('engine', [0, 1, 2, 3, 4, 5])
 def test_minimum_sizes_and_ragged_edges(gpu_lib, engine):
     """n = 1 templates, single-lag searches, streams shorter than one lag block, searches that end on
     the last sample, spans that straddle exactly one block boundary."""
     rng = np.random.default_rng(engine)
-    # 2 = fused kernel at hop B/2, 3 = blocked multiply, 4 = packed fused kernel (library engine 2)
-    _native.check(gpu_lib.sb_set_engine(2 if engine == 4 else min(engine, 1)))
+    # 2 = fused kernel at hop B/2, 3 = blocked multiply, 4 / 5 = packed fused kernels (library engines 2 / 3)
+    _native.check(gpu_lib.sb_set_engine(engine - 2 if engine >= 4 else min(engine, 1)))
     _native.check(gpu_lib.sb_set_hop_mode(2 if engine == 2 else 1))
     _native.check(gpu_lib.sb_set_premac_mode(2 if engine == 3 else 1))
     try:
@@ -347,7 +348,7 @@ def test_minimum_sizes_and_ragged_edges(gpu_lib, engine):
                 assert abs(float(d[0]) - float(want.min())) <= 1e-5
                 assert want[int(i[0])] - want.min() <= 2e-6          # a minimiser (ties on random data are rare)
     finally:
-        _native.check(gpu_lib.sb_set_engine(2))
+        _native.check(gpu_lib.sb_set_engine(3))
         _native.check(gpu_lib.sb_set_hop_mode(1))
         _native.check(gpu_lib.sb_set_premac_mode(0))
 
