@@ -6,7 +6,7 @@
 // float2 whose two halves go through identical arithmetic, so one issued instruction does the work of two:
 //
 //  * Spectra are stored in a "quad" layout: 16-byte chunks A[i] = (re X[i], re X[i+B/2], im X[i], im X[i+B/2])
-//    and M[i] = (re X[B-i], re X[B/2-i], im X[B-i], im X[B/2-i]), i = 0 .. B/4.  One LDG.128 per operand
+//    and M[i] = (re X[B-i], re X[B/2-i], im X[B-i], im X[B/2-i]), i = 0 .. B/4 (blocks of 256 A + 256 M).  One LDG.128 per operand
 //    feeds four FFMA2 for two bins; the Hermitian packing of bins (i, B-i) and (i+B/2, B/2-i) is elementwise
 //    on those pairs.
 //  * The first radix-2 step of the inverse FFT (decimation in frequency) is done on the packed pair itself:
@@ -36,9 +36,14 @@ constexpr int QT = 512;                   // threads per CTA
 constexpr int QNW = QT / 32;
 constexpr int QCH = QB / 2;               // chunks in the FFT buffer: u/v pairs of the two half-size transforms
 constexpr int Q4 = QB / 4;                // quads per spectrum row are i = 0 .. Q4
-constexpr int QOFF_M = 4104;              // float4 offset of the M chunks inside a row (128-byte aligned)
+// Row layout (float4 units): blocks of 256 quads, each block = 256 A chunks followed by 256 M chunks (8 KB, so
+// one TMA bulk copy fetches both halves of 256 quads and a warp's LDG.128 stays fully coalesced); the
+// self-mirrored quad i = B/4 sits behind the 16 blocks.
+constexpr int QBLK = 256;                 // quads per block
 constexpr int QROW = kQuadRowF2 / 2;      // float4 per row
-static_assert(QOFF_M >= Q4 + 1 && QROW >= QOFF_M + Q4 + 1 && (QROW * 16) % 128 == 0 && (QOFF_M * 16) % 128 == 0, "row layout");
+__host__ __device__ constexpr int qa(int i) { return i < Q4 ? (i >> 8) * (2 * QBLK) + (i & (QBLK - 1)) : 2 * Q4; }       // A chunk of quad i
+__host__ __device__ constexpr int qm(int i) { return i < Q4 ? qa(i) + QBLK : 2 * Q4 + 1; }                              // M chunk of quad i
+static_assert(QROW >= 2 * Q4 + 2 && (QROW * 16) % 128 == 0, "row layout");
 constexpr int QPHYS = QCH + QCH / 16;     // physical chunks of the padded FFT buffer
 
 struct PackedTables {
@@ -232,8 +237,8 @@ struct QuadAcc {
 __device__ __forceinline__ C2 special_quad(const float4* tp, const float4* xp, int P, int lane) {
     QuadAcc acc; acc.zero();
     for (int p = lane; p < P; p += 32)
-        acc.mac(__ldg(tp + (int64_t)p * QROW + Q4), __ldg(tp + (int64_t)p * QROW + QOFF_M + Q4),
-                __ldg(xp + (int64_t)p * QROW + Q4), __ldg(xp + (int64_t)p * QROW + QOFF_M + Q4));
+        acc.mac(__ldg(tp + (int64_t)p * QROW + qa(Q4)), __ldg(tp + (int64_t)p * QROW + qm(Q4)),
+                __ldg(xp + (int64_t)p * QROW + qa(Q4)), __ldg(xp + (int64_t)p * QROW + qm(Q4)));
     acc.reduce_over_lanes();
     const float h = 0.70710678118654752f;       // exp(i*pi/4)
     C2 lo, hi;
@@ -427,6 +432,7 @@ __device__ __forceinline__ void finish_item(const Item& it, int tid, const Smem&
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) tmin = fminf(tmin, __shfl_xor_sync(0xffffffffu, tmin, o));
     if (lane == 0) s_min[warp] = tmin;
+    if (is_u8) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // window reads before the next item's TMA refill
     csync<ID>();
     after_read();
     float bmin = s_min[0];
@@ -513,7 +519,7 @@ k_match_packed(const float4* __restrict__ That, int64_t part_first,
         constexpr int U = 4;                          // quads in flight per thread
 #pragma unroll 1
         for (int half = 0; half < 2; ++half) {
-            const int i0 = tid + half * (U * T);
+            const int i0 = (tid >> 8) * (2 * QBLK) + (tid & (QBLK - 1)) + half * (U * 2 * T);   // qa(tid + 512*(half*U + u)) = i0 + 1024u
             QuadAcc acc[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) acc[u].zero();
@@ -524,8 +530,8 @@ k_match_packed(const float4* __restrict__ That, int64_t part_first,
                 float4 ta[U], tmm[U], xa[U], xm[U];
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    ta[u] = ldg_stream(t + u * T);  tmm[u] = ldg_stream(t + QOFF_M + u * T);
-                    xa[u] = ldg_stream(x + u * T);  xm[u] = ldg_stream(x + QOFF_M + u * T);
+                    ta[u] = ldg_stream(t + u * 2 * T);  tmm[u] = ldg_stream(t + QBLK + u * 2 * T);
+                    xa[u] = ldg_stream(x + u * 2 * T);  xm[u] = ldg_stream(x + QBLK + u * 2 * T);
                 }
 #pragma unroll
                 for (int u = 0; u < U; ++u) acc[u].mac(ta[u], tmm[u], xa[u], xm[u]);
@@ -559,10 +565,10 @@ k_match_packed(const float4* __restrict__ That, int64_t part_first,
 // k_match_packed runs its phases back to back on one CTA per SM: while it multiplies (loads from L2, issue
 // slots idle) nothing transforms, and while it transforms nothing loads.  Here one persistent CTA per SM
 // splits the work over two roles that overlap across consecutive items:
-//   4 multiply warps       thread L owns quads i = L + 128*seg.  Lane 0 of each warp keeps a private ring of
-//                          WS_STAGES stages (32 quads x {T^ A, T^ M, X^ A, X^ M} = 2 KB each) filled by TMA bulk
-//                          copies WS_STAGES-1 steps ahead -- across items, so the L2 latency never surfaces;
-//                          the warp multiply-accumulates from the ring, does the Hermitian packing + first
+//   4 multiply warps       thread L owns quads i = L + 128*m.  A ring of WS_STAGES stages (one 256-quad block of a
+//                          T^ row and of an X^ row, 16 KB) is filled by TMA bulk copies WS_STAGES-1 steps ahead
+//                          -- across items, so the L2 latency never surfaces; the warps take turns issuing;
+//                          they multiply-accumulate from the ring, do the Hermitian packing + first
 //                          radix-2 step and parks the result in TENSOR MEMORY with tcgen05.st (the tensor
 //                          cores are idle, so their 256 KB of TMEM are a free second buffer: two items of
 //                          128 KB, double buffered);
@@ -571,8 +577,8 @@ k_match_packed(const float4* __restrict__ That, int64_t part_first,
 // Thread L of the multiply warps writes TMEM lane L (a warp reaches only the 32 lanes of its quarter), columns
 // b*256 + 8*seg + {0..3: C[i], 4..7: C[B/2 - i]}; transform thread t reads lane t & 127, 64 columns from
 // (t >> 7)*64, and scatters the 16 chunks to their places.
-constexpr int WS_THREADS = 640, WS_STAGES = 6, WS_SEG = 128, WS_SEGS = Q4 / WS_SEG;
-constexpr int WS_STAGE_F4 = 4 * 32;                      // float4 per ring stage of one multiply warp: 4 arrays x 32 quads
+constexpr int WS_THREADS = 640, WS_STAGES = 3, WS_SEG = 128, WS_SEGS = Q4 / QBLK;
+constexpr int WS_STAGE_F4 = 2 * 2 * QBLK;                // float4 per ring stage: one block (256 A + 256 M) of a T^ row and of an X^ row
 constexpr unsigned WS_STAGE_BYTES = WS_STAGE_F4 * 16;
 
 // exp(+i*pi*s/128), s = 0..31: the packing twiddle of quad i = L + 128s is wb[L] times this
@@ -593,6 +599,18 @@ __device__ constexpr float kS256[32] = {
     0.59569930449243336f, 0.61523159058062682f, 0.63439328416364549f, 0.65317284295377676f, 0.67155895484701833f,
     0.68954054473706683f};
 
+// Wait with back-off: a hot try_wait loop on 16 warps starves the warps that produce what they wait for.
+__device__ __forceinline__ void mbar_wait_sleep(unsigned long long* bar, unsigned parity, unsigned ns) {
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    for (;;) {
+        unsigned done;
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done) : "r"(b), "r"(parity) : "memory");
+        if (done) break;
+        __nanosleep(ns);
+    }
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
     const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(b) : "memory");
@@ -635,10 +653,11 @@ k_match_ws(const float4* __restrict__ That, int64_t part_first,
     constexpr bool is_u8 = sizeof(S) == 1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const Smem sm(smem_raw);
-    float4* ring = reinterpret_cast<float4*>(sm.end);                              // [4 warps][WS_STAGES] stages
-    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(ring + 4 * WS_STAGES * WS_STAGE_F4);   // staged windows
-    unsigned long long* ring_full = s_bar + 1;                                     // [4][WS_STAGES]
-    unsigned long long* tm_full = ring_full + 4 * WS_STAGES;                       // [2]
+    float4* ring = reinterpret_cast<float4*>(sm.end);                              // [WS_STAGES] stages
+    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(ring + WS_STAGES * WS_STAGE_F4);   // staged windows
+    unsigned long long* ring_full = s_bar + 1;                                     // [WS_STAGES]  copies landed
+    unsigned long long* ring_empty = ring_full + WS_STAGES;                        // [WS_STAGES]  all four multiply warps have read
+    unsigned long long* tm_full = ring_empty + WS_STAGES;                          // [2]
     unsigned long long* tm_empty = tm_full + 2;                                    // [2]
     unsigned long long* s_best = tm_empty + 2;                                     // [NW]
     float* s_min = reinterpret_cast<float*>(s_best + NW);                          // [NW]
@@ -647,7 +666,7 @@ k_match_ws(const float4* __restrict__ That, int64_t part_first,
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
         mbar_init(s_bar, 1);
-        for (int i = 0; i < 4 * WS_STAGES; ++i) mbar_init(ring_full + i, 1);
+        for (int i = 0; i < WS_STAGES; ++i) { mbar_init(ring_full + i, 1); mbar_init(ring_empty + i, 4); }
         for (int i = 0; i < 2; ++i) { mbar_init(tm_full + i, WS_SEG); mbar_init(tm_empty + i, QT); }
     }
     if (warp == 0) tmem_alloc(s_taddr, 512);
@@ -671,8 +690,9 @@ k_match_ws(const float4* __restrict__ That, int64_t part_first,
         for (int64_t local = blockIdx.x; local < n_items; local += gridDim.x, ++n) {
             const Item it(desc, item_query, item_first, local);
             const unsigned b = n & 1u;
-            // ---- un-park: TMEM -> registers -> FFT buffer
-            mbar_wait(tm_full + b, (n >> 1) & 1u);
+            // ---- un-park: TMEM -> registers -> FFT buffer.  One warp polls; the others sleep in the barrier.
+            if (warp == 0) mbar_wait_sleep(tm_full + b, (n >> 1) & 1u, 32);
+            csync<1>();
             tmem_fence_after();
 #pragma unroll
             for (int c4 = 0; c4 < 4; ++c4) {
@@ -703,42 +723,40 @@ k_match_ws(const float4* __restrict__ That, int64_t part_first,
                               });
         }
     } else {
-        // ======================= multiply warps (each feeds its own ring) =======================
+        // ======================= multiply warps =======================
+        // Step = (item, block of 256 quads, partition); its stage holds that block of the T^ row and of the X^
+        // row (two 8 KB bulk copies).  Thread L owns quads L and L + 128 of the block.  Steps are copied
+        // WS_STAGES - 1 ahead, across items; the four warps take turns issuing (warp u % 4 issues step u).
         const int mw = warp - NW;                                                 // 0 .. 3 = TMEM lane quarter
         const int L = tid - QT;                                                   // 0 .. 127 = TMEM lane
         const uint32_t t_out = taddr + ((uint32_t)(mw * 32) << 16);
         const float2 wbase = __ldg(tab.wb + L);
-        float4* const myring = ring + mw * (WS_STAGES * WS_STAGE_F4);             // stages of 4 arrays x 32 quads
-        unsigned long long* const full = ring_full + mw * WS_STAGES;
 
-        // issue cursor: the (item, segment, partition) step whose rows are copied next; every lane tracks it
-        // (uniform values), lane 0 issues.  Steps are consumed in the same order, WS_STAGES - 1 steps later.
+        // issue cursor (every lane tracks it; values are warp-uniform)
         int64_t i_local = blockIdx.x;
         int i_seg = 0, i_p = 0, i_P = 0;
         const float4 *i_tp = nullptr, *i_xp = nullptr;
-        unsigned i_stage = 0;
-        auto cursor_load = [&]() {          // rows of item i_local (skips nothing: P >= 1 for every item)
+        unsigned i_step = 0;
+        auto cursor_load = [&]() {
             if (i_local < n_items) {
                 const Item it(desc, item_query, item_first, i_local);
                 i_P = it.d.P;
                 if (it.k + i_P > nblk) i_P = (int)(nblk - it.k);
-                i_tp = That + (it.d.partBase - part_first) * (int64_t)QROW + mw * 32;
-                i_xp = Xhat + it.k * (int64_t)QROW + mw * 32;
+                i_tp = That + (it.d.partBase - part_first) * (int64_t)QROW;
+                i_xp = Xhat + it.k * (int64_t)QROW;
             }
         };
         auto issue = [&]() {
             if (i_local >= n_items) return;
-            if (lane == 0) {
-                float4* st = myring + i_stage * WS_STAGE_F4;
-                const float4* t = i_tp + (int64_t)i_p * QROW + i_seg * WS_SEG;
-                const float4* x = i_xp + (int64_t)i_p * QROW + i_seg * WS_SEG;
-                mbar_expect_tx(full + i_stage, WS_STAGE_BYTES);
-                tma_load_1d(st, t, 512, full + i_stage);
-                tma_load_1d(st + 32, t + QOFF_M, 512, full + i_stage);
-                tma_load_1d(st + 64, x, 512, full + i_stage);
-                tma_load_1d(st + 96, x + QOFF_M, 512, full + i_stage);
+            const unsigned st_i = i_step % WS_STAGES, use = i_step / WS_STAGES;
+            if ((i_step & 3u) == (unsigned)mw && lane == 0) {
+                mbar_wait_sleep(ring_empty + st_i, (use & 1u) ^ 1u, 20);           // all four warps are done with its previous contents
+                float4* st = ring + st_i * WS_STAGE_F4;
+                mbar_expect_tx(ring_full + st_i, WS_STAGE_BYTES);
+                tma_load_1d(st, i_tp + (int64_t)i_p * QROW + i_seg * (2 * QBLK), 2 * QBLK * 16, ring_full + st_i);
+                tma_load_1d(st + 2 * QBLK, i_xp + (int64_t)i_p * QROW + i_seg * (2 * QBLK), 2 * QBLK * 16, ring_full + st_i);
             }
-            if (++i_stage == WS_STAGES) i_stage = 0;
+            ++i_step;
             if (++i_p >= i_P) {
                 i_p = 0;
                 if (++i_seg == WS_SEGS) { i_seg = 0; i_local += gridDim.x; cursor_load(); }
@@ -747,36 +765,45 @@ k_match_ws(const float4* __restrict__ That, int64_t part_first,
         cursor_load();
         for (int s0 = 0; s0 < WS_STAGES - 1; ++s0) issue();
 
-        unsigned stage = 0, phase = 0, n = 0;
+        unsigned step = 0, n = 0;
         for (int64_t local = blockIdx.x; local < n_items; local += gridDim.x, ++n) {
             const Item it(desc, item_query, item_first, local);
             int P = it.d.P;
             if (it.k + P > nblk) P = (int)(nblk - it.k);
             const unsigned b = n & 1u;
-            mbar_wait(tm_empty + b, ((n >> 1) & 1u) ^ 1u);                         // the transform warps drained this half
+            mbar_wait_sleep(tm_empty + b, ((n >> 1) & 1u) ^ 1u, 64);               // the transform warps drained this half
             tmem_fence_after();
             float h0 = 0.f, h1 = 0.f, h2 = 0.f, h3 = 0.f;
             for (int seg = 0; seg < WS_SEGS; ++seg) {
-                QuadAcc acc; acc.zero();
-                for (int p = 0; p < P; ++p) {
-                    issue();                                                       // refills the stage read one step ago
-                    mbar_wait(full + stage, phase);
-                    const float4* st = myring + stage * WS_STAGE_F4 + lane;
-                    acc.mac(st[0], st[32], st[64], st[96]);
+                QuadAcc acc0, acc1; acc0.zero(); acc1.zero();
+                for (int p = 0; p < P; ++p, ++step) {
+                    issue();                                                       // step + WS_STAGES - 1
+                    const unsigned st_c = step % WS_STAGES;
+                    mbar_wait_sleep(ring_full + st_c, (step / WS_STAGES) & 1u, 20);
+                    const float4* st = ring + st_c * WS_STAGE_F4 + L;              // T^: A at +0, M at +256; X^: 512 further
+                    acc0.mac(st[0], st[QBLK], st[2 * QBLK], st[3 * QBLK]);
+                    acc1.mac(st[WS_SEG], st[QBLK + WS_SEG], st[2 * QBLK + WS_SEG], st[3 * QBLK + WS_SEG]);
+                    // generic-proxy reads of this stage must be ordered before the async-proxy (TMA) refill:
+                    // the mbarrier hand-over alone does not do that (measured: stale quads without the fence)
+                    fence_proxy_async();
                     __syncwarp();                                                  // every lane has read this stage
-                    if (++stage == WS_STAGES) { stage = 0; phase ^= 1u; }
+                    if (lane == 0) mbar_arrive(ring_empty + st_c);
                 }
-                const float c = wbase.x * kC256[seg] - wbase.y * kS256[seg];
-                const float s = wbase.x * kS256[seg] + wbase.y * kC256[seg];
-                C2 lo, hi;
-                pack_quad(acc.aR, acc.aI, acc.mR, acc.mI, c, s, lo, hi);
+                // quads i = 256 seg + L (+128): twiddle exp(i*pi*i/B) = wb[L] * exp(i*pi*(2 seg [+1])/128)
+                const float c0 = wbase.x * kC256[2 * seg] - wbase.y * kS256[2 * seg], s0 = wbase.x * kS256[2 * seg] + wbase.y * kC256[2 * seg];
+                const float c1 = wbase.x * kC256[2 * seg + 1] - wbase.y * kS256[2 * seg + 1], s1 = wbase.x * kS256[2 * seg + 1] + wbase.y * kC256[2 * seg + 1];
+                C2 lo0, hi0, lo1, hi1;
+                pack_quad(acc0.aR, acc0.aI, acc0.mR, acc0.mI, c0, s0, lo0, hi0);
+                pack_quad(acc1.aR, acc1.aI, acc1.mR, acc1.mI, c1, s1, lo1, hi1);
+                const uint32_t col = t_out + b * 256u + (uint32_t)(seg * 16);
                 if (seg == 0) {               // warp NW writes the second half of quad 0 later (see below)
-                    tmem_st4(t_out + b * 256u, lo.r.x, lo.r.y, lo.i.x, lo.i.y);
-                    h0 = hi.r.x; h1 = hi.r.y; h2 = hi.i.x; h3 = hi.i.y;
-                    if (warp != NW) tmem_st4(t_out + b * 256u + 4u, h0, h1, h2, h3);
+                    tmem_st4(col, lo0.r.x, lo0.r.y, lo0.i.x, lo0.i.y);
+                    h0 = hi0.r.x; h1 = hi0.r.y; h2 = hi0.i.x; h3 = hi0.i.y;
+                    if (warp != NW) tmem_st4(col + 4u, h0, h1, h2, h3);
                 } else {
-                    tmem_st8(t_out + b * 256u + (uint32_t)(seg * 8), lo.r.x, lo.r.y, lo.i.x, lo.i.y, hi.r.x, hi.r.y, hi.i.x, hi.i.y);
+                    tmem_st8(col, lo0.r.x, lo0.r.y, lo0.i.x, lo0.i.y, hi0.r.x, hi0.r.y, hi0.i.x, hi0.i.y);
                 }
+                tmem_st8(col + 8u, lo1.r.x, lo1.r.y, lo1.i.x, lo1.i.y, hi1.r.x, hi1.r.y, hi1.i.x, hi1.i.y);
             }
             if (warp == NW) {                     // the self-mirrored quad i = B/4 rides in the unused half of quad 0 (lane 0)
                 const float4* tp = That + (it.d.partBase - part_first) * (int64_t)QROW;
@@ -796,7 +823,7 @@ k_match_ws(const float4* __restrict__ That, int64_t part_first,
 }
 
 size_t ws_smem_bytes() {
-    return kSmemCommon + (size_t)4 * WS_STAGES * WS_STAGE_BYTES + 8 * (1 + 4 * WS_STAGES + 4) + QNW * sizeof(unsigned long long)
+    return kSmemCommon + (size_t)WS_STAGES * WS_STAGE_BYTES + 8 * (1 + 2 * WS_STAGES + 4) + QNW * sizeof(unsigned long long)
          + QNW * sizeof(float) + 16 + 64;
 }
 
@@ -870,8 +897,8 @@ k_forward_quad(const S* __restrict__ src, int64_t src_n, const double2* __restri
         float2 x_i, x_bi, x_h, x_hb;
         bins(i, x_i, x_bi);                          // X[i], X[B-i]
         bins(B / 2 - i, x_h, x_hb);                  // X[B/2-i], X[B/2+i]
-        o[i] = make_float4(x_i.x, x_hb.x, x_i.y, x_hb.y);
-        o[QOFF_M + i] = make_float4(x_bi.x, x_h.x, x_bi.y, x_h.y);
+        o[qa(i)] = make_float4(x_i.x, x_hb.x, x_i.y, x_hb.y);
+        o[qm(i)] = make_float4(x_bi.x, x_h.x, x_bi.y, x_h.y);
     }
 }
 

@@ -104,7 +104,7 @@ void pool_free(void* p);
 void pool_release_all();
 
 // engine 2 (sb_fused2.cu): spectrum rows in the quad layout, kQuadRowF2 float2 per row (128-byte aligned)
-constexpr int kQuadRowF2 = 16416;
+constexpr int kQuadRowF2 = 16400;
 bool packed_supports(int B);
 int launch_match_packed(const sb_stream* image, const sb_stream* tmpl, const float2* d_parts, int64_t part_first,
                         const QueryDesc* d_desc, int q_begin, int q_end, int64_t item_first, int64_t n_items,
