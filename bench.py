@@ -527,7 +527,7 @@ def main():
     ap.add_argument('--chunk', type=int, default=0, help='items per launch override')
     ap.add_argument('--premac-mode', type=int, default=-1, help='blocked multiply kernel: 0 by template length (default), 1 never, 2 always')
     ap.add_argument('--hop-mode', type=int, default=-1, help='fused engine geometry: 1 hop B (default), 2 hop B/2, 0 cost rule per batch')
-    ap.add_argument('--engine', type=int, default=-1, help='0: cuFFT pipeline, 1: fused kernel, 2: packed fused kernel, 3: warp-specialised packed kernel (default)')
+    ap.add_argument('--engine', type=int, default=-1, help='0: cuFFT pipeline, 1: fused kernel, 2: packed fused kernel (default), 3: its warp-specialised persistent variant')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

@@ -70,17 +70,24 @@ int sb_sync(void);
  * chunk).  Changing the block size drops cached block spectra. */
 int sb_set_block_size(int block);
 int sb_get_block_size(void);
-/* Engine behind sb_find*: 1 (default) = the fused lag-block kernel (spectral multiply, inverse FFT
- * in shared memory, normalisation and argmin in one launch; lag blocks of 8192 or 16384), 0 = the
- * cuFFT-planned pipeline (any block size; kept as the cross-check and for odd block sizes). */
+/* Engine behind sb_find*:
+ *   2 (default) = the packed fused lag-block kernel (sb_fused2.cu): spectral multiply, inverse FFT in
+ *       shared memory, normalisation and argmin in one launch, written around the two-wide fp32
+ *       instructions of sm_100 (FFMA2/FADD2) on spectra stored in a paired layout; lag blocks of 16384
+ *       at hop B -- any other geometry silently runs engine 1;
+ *   3 = the same arithmetic as a persistent warp-specialised kernel (TMA-fed multiply warps park each
+ *       item's product spectrum in tensor memory while the other warps transform the previous one);
+ *   1 = the first fused lag-block kernel (sb_fused.cu; lag blocks of 8192 or 16384, hop B or B/2);
+ *   0 = the cuFFT-planned pipeline (any block size; kept as the cross-check and for odd block sizes).
+ * Engines agree to float32 FFT rounding (~2e-7 of the curve), not bit for bit. */
 int sb_set_engine(int engine);
 int sb_get_engine(void);
-/* Spectral multiply of the fused engine: 0 (default) = per lag block inside the fused kernel, except for
+/* Spectral multiply of engine 1: 0 (default) = per lag block inside the fused kernel, except for
  * queries whose template spans 12 or more partitions (>= 16 s at the default block size), which go
  * through the register-blocked multiply kernel (8 lag blocks share each template row); 1 = never
  * blocked, 2 = always blocked.  The route depends only on the query, not on the rest of the batch. */
 int sb_set_premac_mode(int mode);
-/* Overlap-save geometry of the fused engine: 1 (default) = hop B (half of each inverse FFT is valid
+/* Overlap-save geometry of the fused engines: 1 (default) = hop B (half of each inverse FFT is valid
  * lags), 2 = hop B/2 (three quarters valid, but twice as many template partitions to multiply:
  * pays off only for templates shorter than B/2), 0 = chosen per batch by a cost rule.  Geometries
  * agree to float32 FFT rounding (~1e-7), not bit for bit, so a run should stick to one. */

@@ -79,7 +79,6 @@ __device__ __forceinline__ C2 cmul_s(C2 a, float c, float s) {
     return o;
 }
 __device__ __forceinline__ C2 from4(float4 v) { return {make_float2(v.x, v.y), make_float2(v.z, v.w)}; }
-__device__ __forceinline__ float4 to4(C2 v) { return make_float4(v.r.x, v.r.y, v.i.x, v.i.y); }
 
 // d * exp(+2*pi*i*q/32), q even and a compile-time constant after unrolling
 __device__ __forceinline__ C2 rot32p(C2 d, int q) {
@@ -565,19 +564,18 @@ k_match_packed(const float4* __restrict__ That, int64_t part_first,
 // k_match_packed runs its phases back to back on one CTA per SM: while it multiplies (loads from L2, issue
 // slots idle) nothing transforms, and while it transforms nothing loads.  Here one persistent CTA per SM
 // splits the work over two roles that overlap across consecutive items:
-//   4 multiply warps       thread L owns quads i = L + 128*m.  A ring of WS_STAGES stages (one 256-quad block of a
+//   8 multiply warps       two threads per TMEM lane L own quads i = L + 128*m (even / odd m).  A ring of WS_STAGES stages (one 256-quad block of a
 //                          T^ row and of an X^ row, 16 KB) is filled by TMA bulk copies WS_STAGES-1 steps ahead
 //                          -- across items, so the L2 latency never surfaces; the warps take turns issuing;
-//                          they multiply-accumulate from the ring, do the Hermitian packing + first
-//                          radix-2 step and parks the result in TENSOR MEMORY with tcgen05.st (the tensor
-//                          cores are idle, so their 256 KB of TMEM are a free second buffer: two items of
-//                          128 KB, double buffered);
-//   16 transform warps     tcgen05.ld the parked item into the FFT buffer, then exactly the passes and the
-//                          epilogue of k_match_packed.
-// Thread L of the multiply warps writes TMEM lane L (a warp reaches only the 32 lanes of its quarter), columns
-// b*256 + 8*seg + {0..3: C[i], 4..7: C[B/2 - i]}; transform thread t reads lane t & 127, 64 columns from
-// (t >> 7)*64, and scatters the 16 chunks to their places.
-constexpr int WS_THREADS = 640, WS_STAGES = 3, WS_SEG = 128, WS_SEGS = Q4 / QBLK;
+//                          they multiply-accumulate from the ring and park the product spectrum in TENSOR
+//                          MEMORY with tcgen05.st (the tensor cores are idle, so their 256 KB of TMEM are a
+//                          free second buffer: two items of 128 KB, double buffered);
+//   16 transform warps     tcgen05.ld the parked item, Hermitian packing + first radix-2 step into the FFT
+//                          buffer, then exactly the passes and the epilogue of k_match_packed.
+// A multiply thread writes TMEM lane L (a warp reaches only the 32 lanes of its quarter), columns
+// b*256 + 8*m + {0..7} for quad L + 128m; transform thread t reads lane t & 127, 64 columns from (t >> 7)*64
+// (eight quads), packs them and scatters the 16 chunks to their places.
+constexpr int WS_THREADS = 768, WS_MACW = 8, WS_STAGES = 3, WS_SEG = 128, WS_SEGS = Q4 / QBLK;
 constexpr int WS_STAGE_F4 = 2 * 2 * QBLK;                // float4 per ring stage: one block (256 A + 256 M) of a T^ row and of an X^ row
 constexpr unsigned WS_STAGE_BYTES = WS_STAGE_F4 * 16;
 
@@ -627,10 +625,6 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, float v0, float v1, flo
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
                  :: "r"(taddr), "f"(v0), "f"(v1), "f"(v2), "f"(v3), "f"(v4), "f"(v5), "f"(v6), "f"(v7) : "memory");
 }
-__device__ __forceinline__ void tmem_st4(uint32_t taddr, float v0, float v1, float v2, float v3) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
-                 :: "r"(taddr), "f"(v0), "f"(v1), "f"(v2), "f"(v3) : "memory");
-}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
                  : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]),
@@ -666,8 +660,8 @@ k_match_ws(const float4* __restrict__ That, int64_t part_first,
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
         mbar_init(s_bar, 1);
-        for (int i = 0; i < WS_STAGES; ++i) { mbar_init(ring_full + i, 1); mbar_init(ring_empty + i, 4); }
-        for (int i = 0; i < 2; ++i) { mbar_init(tm_full + i, WS_SEG); mbar_init(tm_empty + i, QT); }
+        for (int i = 0; i < WS_STAGES; ++i) { mbar_init(ring_full + i, 1); mbar_init(ring_empty + i, WS_MACW); }
+        for (int i = 0; i < 2; ++i) { mbar_init(tm_full + i, WS_MACW * 32); mbar_init(tm_empty + i, QT); }
     }
     if (warp == 0) tmem_alloc(s_taddr, 512);
     tmem_fence_before();
@@ -675,13 +669,16 @@ k_match_ws(const float4* __restrict__ That, int64_t part_first,
     tmem_fence_after();
     const uint32_t taddr = *s_taddr;
 
+    // 768 threads start with 80 registers each; the CTA pool is fixed at launch: the multiply warps hand 16 each to the transform warps (88 / 64)
     if (warp < NW) {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
         // ======================= transform warps =======================
         const Buf& buf = sm.buf;
         const int Lc = tid & 127, g = tid >> 7;
         const uint32_t t_in = taddr + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(g * 64);
         const int lo_base = phys(Lc) + 1088 * g;                                   // chunk Lc + 128m at phys(Lc) + 136m
         const int hi_base = (Lc ? phys(128 - Lc) + 136 * 63 : 136 * 64) - 1088 * g;   // chunk B/2 - (Lc + 128m), minus 136m
+        const float2 wbase = __ldg(tab.wb + Lc);
         if (is_u8 && (int64_t)blockIdx.x < n_items) {
             const Item first(desc, item_query, item_first, blockIdx.x);
             stage_inputs(first, tid, reinterpret_cast<const uint8_t*>(img), img_n, ipfx, sm, s_bar);
@@ -690,7 +687,8 @@ k_match_ws(const float4* __restrict__ That, int64_t part_first,
         for (int64_t local = blockIdx.x; local < n_items; local += gridDim.x, ++n) {
             const Item it(desc, item_query, item_first, local);
             const unsigned b = n & 1u;
-            // ---- un-park: TMEM -> registers -> FFT buffer.  One warp polls; the others sleep in the barrier.
+            // ---- un-park: TMEM -> registers -> Hermitian packing + first radix-2 step -> FFT buffer.
+            // One warp polls; the others sleep in the barrier.
             if (warp == 0) mbar_wait_sleep(tm_full + b, (n >> 1) & 1u, 32);
             csync<1>();
             tmem_fence_after();
@@ -701,14 +699,21 @@ k_match_ws(const float4* __restrict__ That, int64_t part_first,
                 tmem_wait_ld();
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    const int mm = 2 * c4 + h;                                   // quad m = 8g + mm of multiply thread Lc
-                    const C2 lo = {make_float2(v[8 * h + 0], v[8 * h + 1]), make_float2(v[8 * h + 2], v[8 * h + 3])};
-                    const C2 hi = {make_float2(v[8 * h + 4], v[8 * h + 5]), make_float2(v[8 * h + 6], v[8 * h + 7])};
+                    const int mm = 2 * c4 + h;                                   // quad i = Lc + 128m, m = 8g + mm
+                    const float kc = kC256[8 * g + mm], ks = kS256[8 * g + mm];  // exp(i*pi*i/B) = wb[Lc] * exp(i*pi*m/128)
+                    const float c = wbase.x * kc - wbase.y * ks, s = wbase.x * ks + wbase.y * kc;
+                    C2 lo, hi;
+                    pack_quad(make_float2(v[8 * h + 0], v[8 * h + 1]), make_float2(v[8 * h + 2], v[8 * h + 3]),
+                              make_float2(v[8 * h + 4], v[8 * h + 5]), make_float2(v[8 * h + 6], v[8 * h + 7]), c, s, lo, hi);
                     buf.st(lo_base + 136 * mm, lo);
-                    // quad 0 has no mirror: its second half carries the self-mirrored chunk C[B/4]
-                    const int hp = (mm == 0 && tid == 0) ? phys(Q4) : hi_base - 136 * mm;
-                    buf.st(hp, hi);
+                    if (!(mm == 0 && tid == 0)) buf.st(hi_base - 136 * mm, hi);   // quad 0 has no mirror
                 }
+            }
+            if (warp == NW - 1) {                                                 // the self-mirrored quad i = B/4
+                int P = it.d.P;
+                if (it.k + P > nblk) P = (int)(nblk - it.k);
+                const C2 sp = special_quad(That + (it.d.partBase - part_first) * (int64_t)QROW, Xhat + it.k * (int64_t)QROW, P, lane);
+                if (lane == 0) buf.st(phys(Q4), sp);
             }
             tmem_fence_before();
             mbar_arrive(tm_empty + b);
@@ -723,49 +728,56 @@ k_match_ws(const float4* __restrict__ That, int64_t part_first,
                               });
         }
     } else {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
         // ======================= multiply warps =======================
         // Step = (item, block of 256 quads, partition); its stage holds that block of the T^ row and of the X^
-        // row (two 8 KB bulk copies).  Thread L owns quads L and L + 128 of the block.  Steps are copied
-        // WS_STAGES - 1 ahead, across items; the four warps take turns issuing (warp u % 4 issues step u).
-        const int mw = warp - NW;                                                 // 0 .. 3 = TMEM lane quarter
-        const int L = tid - QT;                                                   // 0 .. 127 = TMEM lane
-        const uint32_t t_out = taddr + ((uint32_t)(mw * 32) << 16);
-        const float2 wbase = __ldg(tab.wb + L);
+        // row (two 8 KB bulk copies).  Thread (quarter q, lane l, half h) owns TMEM lane L = 32q + l and quad
+        // L + 128h of the block, i.e. quads i = L + 128m with m = h (mod 2); its eight accumulators
+        // Y = sum_p conj(T^_p) X^_{k+p} of a quad go to columns 8m .. 8m+7 as they are (the transform warps do
+        // the packing when they take the item out).  Steps are copied WS_STAGES - 1 ahead, across items; the
+        // eight warps take turns issuing (warp u % 8 issues step u).
+        const int mw = warp - NW;                                                 // 0 .. 7
+        const int hf = mw >> 2;                                                   // which of the two quads per lane and block
+        const int L = (mw & 3) * 32 + lane;                                       // TMEM lane
+        const uint32_t t_out = taddr + ((uint32_t)((mw & 3) * 32) << 16) + (uint32_t)(hf * 8);
+        const float4* const my = ring + L + hf * WS_SEG;                          // this thread's chunk in stage 0
 
-        // issue cursor (every lane tracks it; values are warp-uniform)
+        // issue cursor (every lane tracks it; values are warp-uniform): row offsets in float4 units
         int64_t i_local = blockIdx.x;
-        int i_seg = 0, i_p = 0, i_P = 0;
-        const float4 *i_tp = nullptr, *i_xp = nullptr;
-        unsigned i_step = 0;
+        int i_seg = 0, i_p = 0, i_P = 1;
+        unsigned i_toff = 0, i_xoff = 0;                 // offset of (row p, block seg) from That / Xhat
+        unsigned i_stage = 0, i_use1 = 1, i_turn = 0;    // stage, parity to wait for on ring_empty, whose turn
         auto cursor_load = [&]() {
             if (i_local < n_items) {
                 const Item it(desc, item_query, item_first, i_local);
                 i_P = it.d.P;
                 if (it.k + i_P > nblk) i_P = (int)(nblk - it.k);
-                i_tp = That + (it.d.partBase - part_first) * (int64_t)QROW;
-                i_xp = Xhat + it.k * (int64_t)QROW;
+                i_toff = (unsigned)((it.d.partBase - part_first) * (int64_t)QROW);
+                i_xoff = (unsigned)(it.k * (int64_t)QROW);
             }
         };
         auto issue = [&]() {
             if (i_local >= n_items) return;
-            const unsigned st_i = i_step % WS_STAGES, use = i_step / WS_STAGES;
-            if ((i_step & 3u) == (unsigned)mw && lane == 0) {
-                mbar_wait_sleep(ring_empty + st_i, (use & 1u) ^ 1u, 20);           // all four warps are done with its previous contents
-                float4* st = ring + st_i * WS_STAGE_F4;
-                mbar_expect_tx(ring_full + st_i, WS_STAGE_BYTES);
-                tma_load_1d(st, i_tp + (int64_t)i_p * QROW + i_seg * (2 * QBLK), 2 * QBLK * 16, ring_full + st_i);
-                tma_load_1d(st + 2 * QBLK, i_xp + (int64_t)i_p * QROW + i_seg * (2 * QBLK), 2 * QBLK * 16, ring_full + st_i);
+            if (i_turn == (unsigned)mw && lane == 0) {
+                mbar_wait_sleep(ring_empty + i_stage, i_use1, 20);                 // every warp is done with its previous contents
+                float4* st = ring + i_stage * WS_STAGE_F4;
+                mbar_expect_tx(ring_full + i_stage, WS_STAGE_BYTES);
+                tma_load_1d(st, That + i_toff, 2 * QBLK * 16, ring_full + i_stage);
+                tma_load_1d(st + 2 * QBLK, Xhat + i_xoff, 2 * QBLK * 16, ring_full + i_stage);
             }
-            ++i_step;
+            i_turn = (i_turn + 1) & (WS_MACW - 1);
+            if (++i_stage == WS_STAGES) { i_stage = 0; i_use1 ^= 1u; }
+            i_toff += QROW; i_xoff += QROW;                                        // next partition, same block
             if (++i_p >= i_P) {
                 i_p = 0;
+                i_toff += 2 * QBLK - (unsigned)i_P * QROW; i_xoff += 2 * QBLK - (unsigned)i_P * QROW;   // next block, partition 0
                 if (++i_seg == WS_SEGS) { i_seg = 0; i_local += gridDim.x; cursor_load(); }
             }
         };
         cursor_load();
         for (int s0 = 0; s0 < WS_STAGES - 1; ++s0) issue();
 
-        unsigned step = 0, n = 0;
+        unsigned stage = 0, phase = 0, n = 0;
         for (int64_t local = blockIdx.x; local < n_items; local += gridDim.x, ++n) {
             const Item it(desc, item_query, item_first, local);
             int P = it.d.P;
@@ -773,44 +785,22 @@ k_match_ws(const float4* __restrict__ That, int64_t part_first,
             const unsigned b = n & 1u;
             mbar_wait_sleep(tm_empty + b, ((n >> 1) & 1u) ^ 1u, 64);               // the transform warps drained this half
             tmem_fence_after();
-            float h0 = 0.f, h1 = 0.f, h2 = 0.f, h3 = 0.f;
+            const uint32_t col0 = t_out + b * 256u;
             for (int seg = 0; seg < WS_SEGS; ++seg) {
-                QuadAcc acc0, acc1; acc0.zero(); acc1.zero();
-                for (int p = 0; p < P; ++p, ++step) {
-                    issue();                                                       // step + WS_STAGES - 1
-                    const unsigned st_c = step % WS_STAGES;
-                    mbar_wait_sleep(ring_full + st_c, (step / WS_STAGES) & 1u, 20);
-                    const float4* st = ring + st_c * WS_STAGE_F4 + L;              // T^: A at +0, M at +256; X^: 512 further
-                    acc0.mac(st[0], st[QBLK], st[2 * QBLK], st[3 * QBLK]);
-                    acc1.mac(st[WS_SEG], st[QBLK + WS_SEG], st[2 * QBLK + WS_SEG], st[3 * QBLK + WS_SEG]);
+                QuadAcc acc; acc.zero();
+                for (int p = 0; p < P; ++p) {
+                    issue();                                                       // WS_STAGES - 1 steps ahead
+                    mbar_wait_sleep(ring_full + stage, phase, 20);
+                    const float4* st = my + stage * WS_STAGE_F4;                   // T^: A at +0, M at +256; X^: 512 further
+                    acc.mac(st[0], st[QBLK], st[2 * QBLK], st[3 * QBLK]);
                     // generic-proxy reads of this stage must be ordered before the async-proxy (TMA) refill:
                     // the mbarrier hand-over alone does not do that (measured: stale quads without the fence)
                     fence_proxy_async();
                     __syncwarp();                                                  // every lane has read this stage
-                    if (lane == 0) mbar_arrive(ring_empty + st_c);
+                    if (lane == 0) mbar_arrive(ring_empty + stage);
+                    if (++stage == WS_STAGES) { stage = 0; phase ^= 1u; }
                 }
-                // quads i = 256 seg + L (+128): twiddle exp(i*pi*i/B) = wb[L] * exp(i*pi*(2 seg [+1])/128)
-                const float c0 = wbase.x * kC256[2 * seg] - wbase.y * kS256[2 * seg], s0 = wbase.x * kS256[2 * seg] + wbase.y * kC256[2 * seg];
-                const float c1 = wbase.x * kC256[2 * seg + 1] - wbase.y * kS256[2 * seg + 1], s1 = wbase.x * kS256[2 * seg + 1] + wbase.y * kC256[2 * seg + 1];
-                C2 lo0, hi0, lo1, hi1;
-                pack_quad(acc0.aR, acc0.aI, acc0.mR, acc0.mI, c0, s0, lo0, hi0);
-                pack_quad(acc1.aR, acc1.aI, acc1.mR, acc1.mI, c1, s1, lo1, hi1);
-                const uint32_t col = t_out + b * 256u + (uint32_t)(seg * 16);
-                if (seg == 0) {               // warp NW writes the second half of quad 0 later (see below)
-                    tmem_st4(col, lo0.r.x, lo0.r.y, lo0.i.x, lo0.i.y);
-                    h0 = hi0.r.x; h1 = hi0.r.y; h2 = hi0.i.x; h3 = hi0.i.y;
-                    if (warp != NW) tmem_st4(col + 4u, h0, h1, h2, h3);
-                } else {
-                    tmem_st8(col, lo0.r.x, lo0.r.y, lo0.i.x, lo0.i.y, hi0.r.x, hi0.r.y, hi0.i.x, hi0.i.y);
-                }
-                tmem_st8(col + 8u, lo1.r.x, lo1.r.y, lo1.i.x, lo1.i.y, hi1.r.x, hi1.r.y, hi1.i.x, hi1.i.y);
-            }
-            if (warp == NW) {                     // the self-mirrored quad i = B/4 rides in the unused half of quad 0 (lane 0)
-                const float4* tp = That + (it.d.partBase - part_first) * (int64_t)QROW;
-                const float4* xp = Xhat + it.k * (int64_t)QROW;
-                const C2 sp = special_quad(tp, xp, P, lane);
-                if (lane == 0) { h0 = sp.r.x; h1 = sp.r.y; h2 = sp.i.x; h3 = sp.i.y; }
-                tmem_st4(t_out + b * 256u + 4u, h0, h1, h2, h3);
+                tmem_st8(col0 + (uint32_t)(seg * 16), acc.aR.x, acc.aR.y, acc.aI.x, acc.aI.y, acc.mR.x, acc.mR.y, acc.mI.x, acc.mI.y);
             }
             tmem_wait_st();
             tmem_fence_before();

@@ -111,7 +111,7 @@ def test_fused_engine_equals_cufft_engine(gpu_lib, pair, stype, block):
             assert np.abs(results[0][0] - results[e][0]).max() <= 2e-6
             assert np.abs(results[0][1] - results[e][1]).max() <= 1
     finally:
-        _native.check(gpu_lib.sb_set_engine(3))
+        _native.check(gpu_lib.sb_set_engine(2))
         _native.check(gpu_lib.sb_set_hop_mode(1))
         _native.check(gpu_lib.sb_set_premac_mode(0))
         _native.check(gpu_lib.sb_set_block_size(16384))
@@ -348,7 +348,7 @@ def test_minimum_sizes_and_ragged_edges(gpu_lib, engine):
                 assert abs(float(d[0]) - float(want.min())) <= 1e-5
                 assert want[int(i[0])] - want.min() <= 2e-6          # a minimiser (ties on random data are rare)
     finally:
-        _native.check(gpu_lib.sb_set_engine(3))
+        _native.check(gpu_lib.sb_set_engine(2))
         _native.check(gpu_lib.sb_set_hop_mode(1))
         _native.check(gpu_lib.sb_set_premac_mode(0))
 

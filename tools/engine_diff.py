@@ -30,4 +30,4 @@ for stype in (sys.argv[5].split(',') if len(sys.argv) > 5 else ('uint8', 'float3
         bad = np.nonzero((dd > 2e-6) | (dt > 0.5))[0]
         print(stype, 'engine %d rep %d: max|ddiff| %.3e max|dshift| %.2f samples, %d of %d queries differ' % (
             key[0], key[1], dd.max(), dt.max(), len(bad), len(d)), bad[:12].tolist())
-_native.check(lib.sb_set_engine(3))
+_native.check(lib.sb_set_engine(2))

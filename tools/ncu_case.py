@@ -17,7 +17,7 @@ ap.add_argument('--events', type=int, default=300)
 ap.add_argument('--duration', type=float, default=600.0)
 ap.add_argument('--window', type=float, default=60.0)
 ap.add_argument('--batches', type=int, default=3)
-ap.add_argument('--engine', type=int, default=3)
+ap.add_argument('--engine', type=int, default=2)
 ap.add_argument('--block', type=int, default=16384)
 ap.add_argument('--sample-type', default='uint8')
 ap.add_argument('--hop-mode', type=int, default=1)

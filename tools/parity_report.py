@@ -35,4 +35,4 @@ for stype in ('uint8', 'float32'):
                 stype, '%gs' % ev_len, '+-%gs' % win, nlags, np.abs(gpu - ref).max(), np.abs(gpu - f64).max(),
                 np.abs(ref - f64).max(), 'same' if int(gpu.argmin()) == int(ref.argmin()) else 'DIFF(%d)' % (int(gpu.argmin()) - int(ref.argmin())),
                 {0: 'cufft', 1: 'fused', 2: 'packed', 3: 'packed_ws'}[engine]))
-    _native.check(lib.sb_set_engine(3))
+    _native.check(lib.sb_set_engine(2))
