@@ -25,6 +25,8 @@ ap.add_argument('--hop-mode', type=int, default=1)
 ap.add_argument('--premac-mode', type=int, default=0)
 ap.add_argument('--events', default='0.5,1,3,10,30')
 ap.add_argument('--windows', default='5,10,30,60,120,300,600')
+ap.add_argument('--engine', type=int, default=-1, help='library engine (default: the library default)')
+ap.add_argument('--out', default='sweep.json', help='file name under gpurun_out/')
 a = ap.parse_args()
 
 peak = 6650.0
@@ -36,6 +38,8 @@ src_pcm, dst_pcm = synth.make_pair(a.duration, 2, 1.5)
 src = WavStream.from_pcm(src_pcm, 12000, sample_type=a.sample_type)
 dst = WavStream.from_pcm(dst_pcm, 12000, sample_type=a.sample_type)
 lib = _native.lib()
+if a.engine >= 0:
+    _native.check(lib.sb_set_engine(a.engine))
 _native.check(lib.sb_set_hop_mode(a.hop_mode))
 _native.check(lib.sb_set_premac_mode(a.premac_mode))
 EV = [float(x) for x in a.events.split(',')]
@@ -72,8 +76,8 @@ for ev_len in EV:
                      'shift_recovered': good})
         print(rows[-1], flush=True)
 os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
-json.dump({'peak_hbm_gbs': peak, 'sample_type': a.sample_type, 'duration_s': a.duration, 'cells': rows},
-          open(os.path.join(ROOT, 'gpurun_out', 'sweep.json'), 'w'), indent=1)
+json.dump({'peak_hbm_gbs': peak, 'sample_type': a.sample_type, 'duration_s': a.duration, 'engine': lib.sb_get_engine(), 'cells': rows},
+          open(os.path.join(ROOT, 'gpurun_out', a.out), 'w'), indent=1)
 print('\n| event \\ window | ' + ' | '.join('±%g s' % w for w in WIN) + ' |')
 print('|---|' + '---|' * len(WIN))
 for ev_len in EV:
