@@ -997,12 +997,12 @@ int launch_match_packed(const sb_stream* image, const sb_stream* tmpl, const flo
         const int64_t ni = std::min<int64_t>(max_grid, n_items - i0);
         if (u8)
             k_match_packed<uint8_t><<<(unsigned)ni, QT, smem, c.stream>>>(
-                reinterpret_cast<const float4*>(d_parts), part_first, reinterpret_cast<const float4*>(image->d_spec), image->nblk,
+                reinterpret_cast<const float4*>(d_parts), part_first, reinterpret_cast<const float4*>(image->d_specq), image->nblkq,
                 static_cast<const uint8_t*>(image->d_raw), image->n, image->d_pfx, tmpl->d_pfx, d_desc, g_item_query2 + i0, item_first + i0,
                 tab, d_keys, d_curve);
         else
             k_match_packed<float><<<(unsigned)ni, QT, smem, c.stream>>>(
-                reinterpret_cast<const float4*>(d_parts), part_first, reinterpret_cast<const float4*>(image->d_spec), image->nblk,
+                reinterpret_cast<const float4*>(d_parts), part_first, reinterpret_cast<const float4*>(image->d_specq), image->nblkq,
                 static_cast<const float*>(image->d_raw), image->n, image->d_pfx, tmpl->d_pfx, d_desc, g_item_query2 + i0, item_first + i0,
                 tab, d_keys, d_curve);
     }
@@ -1034,12 +1034,12 @@ int launch_match_ws(const sb_stream* image, const sb_stream* tmpl, const float2*
     const unsigned grid = (unsigned)std::min<int64_t>(n_items, c.sm_count);     // one persistent CTA per SM
     if (image->dtype == SB_U8)
         k_match_ws<uint8_t><<<grid, WS_THREADS, smem, c.stream>>>(
-            reinterpret_cast<const float4*>(d_parts), part_first, reinterpret_cast<const float4*>(image->d_spec), image->nblk,
+            reinterpret_cast<const float4*>(d_parts), part_first, reinterpret_cast<const float4*>(image->d_specq), image->nblkq,
             static_cast<const uint8_t*>(image->d_raw), image->n, image->d_pfx, tmpl->d_pfx, d_desc, g_item_query2, item_first, n_items,
             tab, d_keys, d_curve);
     else
         k_match_ws<float><<<grid, WS_THREADS, smem, c.stream>>>(
-            reinterpret_cast<const float4*>(d_parts), part_first, reinterpret_cast<const float4*>(image->d_spec), image->nblk,
+            reinterpret_cast<const float4*>(d_parts), part_first, reinterpret_cast<const float4*>(image->d_specq), image->nblkq,
             static_cast<const float*>(image->d_raw), image->n, image->d_pfx, tmpl->d_pfx, d_desc, g_item_query2, item_first, n_items,
             tab, d_keys, d_curve);
     SB_CUDA(cudaGetLastError());

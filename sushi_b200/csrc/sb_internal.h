@@ -143,4 +143,7 @@ struct sb_stream {
     int specHD = 1;               // hop divisor the rows were built with (row k starts at k * specB / specHD)
     int specEngine = -1;          // engine that built d_spec (rebuilt when the engine changes)
     int64_t nblk = 0;
+    // the same rows in the quad layout of the packed kernels (B = 16384, hop B): [nblkq][kQuadRowF2] float2
+    float2* d_specq = nullptr;
+    int64_t nblkq = 0;
 };

@@ -17,7 +17,7 @@
 #include <cstdlib>
 #include <cstring>
 
-namespace sb { int ensure_spectra(sb_stream* s, int hd); }
+namespace sb { int ensure_spectra(sb_stream* s, int hd); int ensure_spectra_quad(sb_stream* s); }
 using namespace sb;
 
 namespace {
@@ -451,13 +451,16 @@ int run_batch(const sb_stream* image_c, const sb_stream* tmpl, int64_t count,
     // Multiply strategy per query: inside the fused kernel (2 loads per multiply-accumulate, nothing through
     // HBM), or -- for very long templates (kBlockedFromPartitions) -- the register-blocked kernel
     // k_mac_blocked over MAC_GROUP lag blocks, whose products the fused kernel then reads from a chunk buffer.
-    // Engine 2: the packed kernel (sb_fused2.cu) with quad-layout spectrum rows; it covers B = 16384 at hop B.
+    // Engines 2 / 3: the direct class runs the packed kernels (sb_fused2.cu) on quad-layout spectrum rows (they
+    // cover B = 16384 at hop B); the blocked class keeps engine 1's kernels and the classic row layout, so a
+    // stream may hold its block spectra in both layouts.
     const bool use_packed = c.engine >= 2 && packed_supports(B) && hd == 1;
-    const int nb = use_packed ? kQuadRowF2 : B + 1;          // float2 per spectrum row
+    const int nb = B + 1;                                    // float2 per classic spectrum row
     int64_t n_direct = 0, total_items = 0, total_parts = 0, total_groups = 0, maxp = 0;
-    SB_TRY(plan_batch(image, tmpl, count, toff, tlen, lag0, nlags, hd, use_fused && hd == 1 && !use_packed, &n_direct,
+    SB_TRY(plan_batch(image, tmpl, count, toff, tlen, lag0, nlags, hd, use_fused && hd == 1, &n_direct,
                       &total_items, &total_parts, &total_groups, &maxp));
-    SB_TRY(ensure_spectra(image, hd));
+    if (use_packed && n_direct > 0) SB_TRY(ensure_spectra_quad(image));
+    if (!use_packed || n_direct < count) SB_TRY(ensure_spectra(image, hd));
 
     SB_TRY(grow(&c.d_desc, &c.desc_cap, count));
     SB_TRY(grow(&c.d_keys, &c.keys_cap, count));
@@ -466,7 +469,7 @@ int run_batch(const sb_stream* image_c, const sb_stream* tmpl, int64_t count,
     SB_CUDA(cudaMemsetAsync(c.d_keys, 0xff, sizeof(unsigned long long) * count, c.stream));
 
     const int64_t parts_cap_want = std::max<int64_t>(std::min<int64_t>(total_parts, c.max_parts), maxp);
-    SB_TRY(grow(&c.d_parts, &c.parts_cap, parts_cap_want * nb));
+    SB_TRY(grow(&c.d_parts, &c.parts_cap, parts_cap_want * (use_packed ? kQuadRowF2 : nb)));
     const int64_t chunk = std::min<int64_t>(c.chunk_items, total_items);
     if (!use_fused) SB_TRY(grow(&c.d_items, &c.items_cap, chunk * nb));
     // lag blocks per product buffer (0.5 GB at B = 16384); SB_PREMAC_CHUNK overrides it for experiments
@@ -488,7 +491,7 @@ int run_batch(const sb_stream* image_c, const sb_stream* tmpl, int64_t count,
         const int64_t part_first = c.h_desc[qb].partBase;
         // 1. template partitions -> spectra
         const int64_t sub = 4096;
-        if (use_packed) {
+        if (use_packed && !premac) {
             ProfScope ps("part_spectra");
             SB_TRY(launch_part_spectra_quad(tmpl, c.d_desc, (int)qb, (int)qe, part_first, np, c.d_parts));
         } else if (use_fused) {                      // hand-written gather + forward FFT, one launch
@@ -517,7 +520,7 @@ int run_batch(const sb_stream* image_c, const sb_stream* tmpl, int64_t count,
         // 2. items of these queries
         const int64_t item_lo = c.h_desc[qb].itemBase;
         const int64_t item_hi = (qe < count) ? c.h_desc[qe].itemBase : total_items;
-        if (use_packed) {
+        if (use_packed && !premac) {
             ProfScope ps("match_fused");
             if (c.engine == 3)
                 SB_TRY(launch_match_ws(image, tmpl, c.d_parts, part_first, c.d_desc, (int)qb, (int)qe,

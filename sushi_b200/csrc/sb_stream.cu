@@ -209,24 +209,31 @@ namespace sb {
 
 int stream_finish_public(sb_stream* s) { return stream_finish(s); }
 
+// Block spectra in the quad layout of the packed kernels (sb_fused2.cu): B = 16384, hop B.
+int ensure_spectra_quad(sb_stream* s) {
+    Ctx& c = ctx();
+    if (!packed_supports(c.B)) SB_FAIL(SB_EINVAL, "internal: quad-layout spectra need a lag block of 16384");
+    if (s->d_specq) return SB_OK;
+    const int64_t nblk = (s->n + c.B - 1) / c.B;
+    SB_TRY(pool_alloc((void**)&s->d_specq, sizeof(float2) * (size_t)nblk * kQuadRowF2));
+    {
+        ProfScope ps("block_spectra");
+        SB_TRY(launch_block_spectra_quad(s, 0, nblk, s->d_specq));
+    }
+    s->nblkq = nblk;
+    return SB_OK;
+}
+
 // Build (or fetch) the block spectra of `s`: row k = FFT_2B of samples [k*H, k*H + 2B), H = B/hd.
 int ensure_spectra(sb_stream* s, int hd) {
     Ctx& c = ctx();
-    // effective engine: the packed kernel covers B = 16384 at hop B; everything else falls to engine 1 / 0
-    const int eng = (c.engine >= 2 && packed_supports(c.B) && hd == 1) ? 2 : (c.engine >= 1 && fused_supports(c.B)) ? 1 : 0;
+    // classic row layout ([B+1] complex per row): engine 1's kernels (also behind engines 2 / 3 for the
+    // queries routed through the blocked multiply) or the cuFFT pipeline
+    const int eng = (c.engine >= 1 && fused_supports(c.B)) ? 1 : 0;
     if (s->d_spec && s->specB == c.B && s->specHD == hd && s->specEngine == eng) return SB_OK;
     if (s->d_spec) { pool_free(s->d_spec); s->d_spec = nullptr; }
     const int B = c.B, H = B / hd;
     const int64_t nblk = (s->n + H - 1) / H;
-    if (c.engine >= 2 && packed_supports(B) && hd == 1) {   // quad-layout rows for the packed kernels
-        SB_TRY(pool_alloc((void**)&s->d_spec, sizeof(float2) * (size_t)nblk * kQuadRowF2));
-        {
-            ProfScope ps("block_spectra");
-            SB_TRY(launch_block_spectra_quad(s, 0, nblk, s->d_spec));
-        }
-        s->specB = B; s->specHD = 1; s->nblk = nblk; s->specEngine = 2;
-        return SB_OK;
-    }
     SB_TRY(pool_alloc((void**)&s->d_spec, sizeof(float2) * (size_t)nblk * (B + 1)));
     if (c.engine >= 1 && fused_supports(B)) {        // hand-written gather + forward FFT, one launch
         {
@@ -299,7 +306,7 @@ int sb_stream_destroy(sb_stream* s) {
     if (!s) return SB_OK;
     Ctx& c = ctx();
     (void)c;
-    pool_free(s->d_raw); pool_free(s->d_pfx); pool_free(s->d_spec);
+    pool_free(s->d_raw); pool_free(s->d_pfx); pool_free(s->d_spec); pool_free(s->d_specq);
     delete s;
     return SB_OK;
 }
