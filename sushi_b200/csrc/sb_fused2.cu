@@ -118,13 +118,10 @@ struct Buf {
     __device__ __forceinline__ void st(int p, C2 v) const { r[p] = v.r; i[p] = v.i; }
 };
 
-// spectrum rows are streamed once per item: keep them out of L1 so the twiddle tables stay there
-__device__ __forceinline__ float4 ldg_stream(const float4* p) {
-    float4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
-                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-    return v;
-}
+// Spectrum rows: plain read-only loads.  (Measured: ld.global.nc.L1::no_allocate, tried to keep the twiddle
+// tables in L1, drops the L2 hit rate of these rows from 98 % to 83 % and multiplies the DRAM traffic of the
+// kernel by 9 -- profiles/README.md.)
+__device__ __forceinline__ float4 ldg_stream(const float4* p) { return __ldg(p); }
 
 // ---------------------------------------------------------------- packing of one quad
 // a = (Y[i], Y[i+B/2]), m = (Y[B-i], Y[B/2-i]) as packed pairs, (c, s) = exp(i*pi*i/B).
