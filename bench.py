@@ -459,7 +459,7 @@ def run_b200(args):
             'higher_is_better': True, 'scaling': wl['scaling'], 'vs_baseline': None,
             'dtype': 'f32', 'data': 'synthetic',
             'config': {'workload': args.workload + ': ' + wl['text'], 'events_per_gpu': count, 'sample_type': stype,
-                       'sample_rate': SAMPLE_RATE, 'window_s': wl['window'], 'lag_block': lib.sb_get_block_size(), 'engine': {0: 'cufft', 1: 'fused', 2: 'fused_packed', 3: 'fused_packed_ws'}[lib.sb_get_engine()],
+                       'sample_rate': SAMPLE_RATE, 'window_s': wl['window'], 'lag_block': lib.sb_get_block_size(), 'engine': {0: 'cufft', 1: 'fused', 2: 'fused_packed', 3: 'fused_packed_ws', 4: 'fused_packed_pair'}[lib.sb_get_engine()],
                        'parallelism': 'events x%d' % world,
                        'l2': 'working set > L2: block spectra %.0f MB + running sums %.0f MB per stream, rebuilt every step'
                              % (n_dst * 8 / 1e6, n_dst * 16 / 1e6),

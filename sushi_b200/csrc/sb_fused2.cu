@@ -179,6 +179,7 @@ constexpr size_t kSmemCommon = (size_t)QPHYS * 16 + kRounds * QNW * 2 * sizeof(d
 
 struct Item {                                      // one (query, lag block)
     QueryDesc d; int q; int64_t k, j_blk;
+    __device__ __forceinline__ Item(const QueryDesc& dd, int qq, int64_t kk) : d(dd), q(qq), k(kk), j_blk(kk * QB) {}
     __device__ __forceinline__ Item(const QueryDesc* desc, const int* item_query, int64_t item_first, int64_t local) {
         q = __ldg(item_query + local);
         d = desc[q];
@@ -809,6 +810,156 @@ k_match_ws(const float4* __restrict__ That, int64_t part_first,
     if (warp == 0) tmem_dealloc(taddr, 512);
 }
 
+// ---------------------------------------------------------------- kernel A2: one CTA per PAIR of lag blocks
+// The multiply phase of k_match_packed runs at the SM's L2 read rate (each item pulls 2 x P rows of 131 KB).
+// Two consecutive lag blocks k, k+1 of one query use the same template rows T^_p and overlapping spectrum rows
+// (block k+1 at step p needs X^_{k+1+p}, which block k needs at step p+1): multiplying both at once costs
+// 2P + 1 row reads instead of 4P.  The second product spectrum has nowhere to wait in shared memory, so it is
+// parked in TENSOR MEMORY (tcgen05.st; every thread later reads back exactly what it wrote, so the 32-lane
+// window of a warp is no constraint) while the CTA transforms the first; then it is taken out again
+// (tcgen05.ld) and goes through the same passes and epilogue.
+template <typename S>
+__global__ void __launch_bounds__(QT, 1)
+k_match_pair(const float4* __restrict__ That, int64_t part_first,
+             const float4* __restrict__ Xhat, int64_t nblk,
+             const S* __restrict__ img, int64_t img_n,
+             const double2* __restrict__ ipfx, const double2* __restrict__ tpfx,
+             const QueryDesc* __restrict__ desc, const int* __restrict__ pair_query, int64_t pair_first,
+             PackedTables tab, unsigned long long* __restrict__ keys, float* __restrict__ curve_out) {
+    constexpr int T = QT, NW = QNW;
+    constexpr bool is_u8 = sizeof(S) == 1;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const Smem sm(smem_raw);
+    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(sm.end);
+    unsigned long long* s_best = s_bar + 1;                                // [NW]
+    float* s_min = reinterpret_cast<float*>(s_best + NW);                  // [NW]
+    uint32_t* s_taddr = reinterpret_cast<uint32_t*>(s_min + NW);
+    const Buf& buf = sm.buf;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int q = __ldg(pair_query + blockIdx.x);
+    const QueryDesc d = desc[q];
+    const int lp = (int)(pair_first + blockIdx.x - d.groupBase);          // pair number inside the query
+    const bool has2 = 2 * lp + 1 < d.nk;
+    const Item it0(d, q, d.k0 + 2 * lp), it1(d, q, d.k0 + 2 * lp + 1);
+
+    if (warp == 0) tmem_alloc(s_taddr, 256);
+    if (is_u8) {
+        if (tid == 0) mbar_init(s_bar, 1);
+        stage_inputs(it0, tid, reinterpret_cast<const uint8_t*>(img), img_n, ipfx, sm, s_bar);
+    }
+    tmem_fence_before();
+    csync<0>();
+    tmem_fence_after();
+    // this thread's 64 columns: lane quarter of its warp, column block of its warp group
+    const uint32_t tcol = *s_taddr + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 64);
+
+    const int tm = (T - tid) & (T - 1);               // mirrored chunks C[B/2 - i] live in thread tm's column
+    const int col = phys(tid), mcol = phys(tm);
+    C2 sp1 = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};             // C[B/4] of the second item (warp NW-1, lane 0)
+    // ---------------- 1+2. multiply-accumulate for both items, packing, first radix-2 step ----
+    {
+        const int64_t k = it0.k;
+        const float4* tp = That + (d.partBase - part_first) * (int64_t)QROW;
+        const float4* xp = Xhat + k * (int64_t)QROW;
+        const float2 wbase = __ldg(tab.wb + tid);
+        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        constexpr int U = 2;                          // quads in flight per thread (two accumulator sets each)
+#pragma unroll 1
+        for (int grp = 0; grp < 8 / U; ++grp) {
+            const int i0 = (tid >> 8) * (2 * QBLK) + (tid & (QBLK - 1)) + grp * (U * 2 * T);   // qa(tid + 512*(grp*U + u)) = i0 + 1024u
+            QuadAcc a0[U], a1[U];
+            float4 xa[U], xm[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                a0[u].zero(); a1[u].zero();
+                xa[u] = ldg_stream(xp + i0 + u * 2 * T); xm[u] = ldg_stream(xp + i0 + QBLK + u * 2 * T);   // row k < nblk
+            }
+#pragma unroll 1
+            for (int p = 0; p < d.P; ++p) {
+                const float4* t = tp + (int64_t)p * QROW + i0;
+                const float4* x = xp + (int64_t)(p + 1) * QROW + i0;
+                const bool next_row = k + p + 1 < nblk;           // rows past the end of the stream are zero
+                float4 ta[U], tmm[U], xna[U], xnm[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    ta[u] = ldg_stream(t + u * 2 * T);  tmm[u] = ldg_stream(t + QBLK + u * 2 * T);
+                    xna[u] = next_row ? ldg_stream(x + u * 2 * T) : zero4;  xnm[u] = next_row ? ldg_stream(x + QBLK + u * 2 * T) : zero4;
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    a0[u].mac(ta[u], tmm[u], xa[u], xm[u]);       // block k   : row k + p
+                    a1[u].mac(ta[u], tmm[u], xna[u], xnm[u]);     // block k+1 : row k + 1 + p
+                    xa[u] = xna[u]; xm[u] = xnm[u];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int uu = grp * U + u;           // i = tid + 512*uu
+                const float c = wbase.x * kC64[uu] - wbase.y * kS64[uu];
+                const float s = wbase.x * kS64[uu] + wbase.y * kC64[uu];
+                C2 lo, hi;
+                pack_quad(a0[u].aR, a0[u].aI, a0[u].mR, a0[u].mI, c, s, lo, hi);
+                buf.st(col + 544 * uu, lo);                       // C[i]
+                if (tid != 0) buf.st(mcol + 544 * (15 - uu), hi); // C[B/2 - i]
+                else if (uu != 0) buf.st(mcol + 544 * (16 - uu), hi);
+                pack_quad(a1[u].aR, a1[u].aI, a1[u].mR, a1[u].mI, c, s, lo, hi);
+                tmem_st8(tcol + (uint32_t)(uu * 8), lo.r.x, lo.r.y, lo.i.x, lo.i.y, hi.r.x, hi.r.y, hi.i.x, hi.i.y);
+            }
+        }
+        if (warp == NW - 1) {                         // the self-mirrored quad i = B/4 of both items
+            int P0 = d.P; if (k + P0 > nblk) P0 = (int)(nblk - k);
+            const C2 lo = special_quad(tp, xp, P0, lane);
+            if (lane == 0) buf.st(phys(Q4), lo);
+            if (has2) {
+                int P1 = d.P; if (k + 1 + P1 > nblk) P1 = (int)(nblk - k - 1);
+                sp1 = special_quad(tp, xp + QROW, P1, lane);
+            }
+        }
+        tmem_wait_st();
+    }
+    csync<0>();
+
+    // ---------------- first item: inverse FFT + epilogue ---------------------------------------
+    fft_passes<0>(buf, tid, tab, is_u8);
+    finish_item<S, 0>(it0, tid, sm, s_bar, 0u, s_best, s_min, img, img_n, ipfx, tpfx, tab, keys, curve_out,
+                      [&] { if (is_u8 && has2) stage_inputs(it1, tid, reinterpret_cast<const uint8_t*>(img), img_n, ipfx, sm, s_bar); });
+
+    // ---------------- second item: out of tensor memory, then the same ---------------------------
+    if (has2) {                                       // uniform over the CTA
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+            float v[16];
+            tmem_ld16(tcol + (uint32_t)(c4 * 16), v);
+            tmem_wait_ld();
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int uu = 2 * c4 + h;
+                const C2 lo = {make_float2(v[8 * h + 0], v[8 * h + 1]), make_float2(v[8 * h + 2], v[8 * h + 3])};
+                const C2 hi = {make_float2(v[8 * h + 4], v[8 * h + 5]), make_float2(v[8 * h + 6], v[8 * h + 7])};
+                buf.st(col + 544 * uu, lo);
+                if (tid != 0) buf.st(mcol + 544 * (15 - uu), hi);
+                else if (uu != 0) buf.st(mcol + 544 * (16 - uu), hi);
+            }
+        }
+        if (tid == (NW - 1) * 32) buf.st(phys(Q4), sp1);
+        csync<0>();
+        fft_passes<0>(buf, tid, tab, is_u8);
+        finish_item<S, 0>(it1, tid, sm, s_bar, 1u, s_best, s_min, img, img_n, ipfx, tpfx, tab, keys, curve_out, [] {});
+    }
+    tmem_fence_before();
+    csync<0>();
+    if (warp == 0) tmem_dealloc(*s_taddr, 256);
+}
+
+// pair_query[i] = query of pair (pair_first + i): one CTA per query fills its own range
+__global__ void k_fill_pair_query(const QueryDesc* __restrict__ desc, int q_begin, int64_t pair_first, int* __restrict__ pair_query) {
+    const int q = q_begin + blockIdx.x;
+    const int64_t base = desc[q].groupBase - pair_first;
+    const int np = (desc[q].nk + 1) / 2;
+    for (int i = threadIdx.x; i < np; i += blockDim.x) pair_query[base + i] = q;
+}
+
 size_t ws_smem_bytes() {
     return kSmemCommon + (size_t)WS_STAGES * WS_STAGE_BYTES + 8 * (1 + 2 * WS_STAGES + 4) + QNW * sizeof(unsigned long long)
          + QNW * sizeof(float) + 16 + 64;
@@ -1038,6 +1189,41 @@ int launch_match_ws(const sb_stream* image, const sb_stream* tmpl, const float2*
         k_match_ws<float><<<grid, WS_THREADS, smem, c.stream>>>(
             reinterpret_cast<const float4*>(d_parts), part_first, reinterpret_cast<const float4*>(image->d_specq), image->nblkq,
             static_cast<const float*>(image->d_raw), image->n, image->d_pfx, tmpl->d_pfx, d_desc, g_item_query2, item_first, n_items,
+            tab, d_keys, d_curve);
+    SB_CUDA(cudaGetLastError());
+    return SB_OK;
+}
+
+int launch_match_pair(const sb_stream* image, const sb_stream* tmpl, const float2* d_parts, int64_t part_first,
+                      const QueryDesc* d_desc, int q_begin, int q_end, int64_t pair_first, int64_t n_pairs,
+                      unsigned long long* d_keys, float* d_curve) {
+    Ctx& c = ctx();
+    PackedTables tab;
+    SB_TRY(ensure_packed_tables(&tab));
+    static bool attr_set = false;
+    const size_t smem = packed_smem_bytes() + 16;
+    if (!attr_set) {
+        SB_CUDA(cudaFuncSetAttribute(k_match_pair<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SB_CUDA(cudaFuncSetAttribute(k_match_pair<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    if (g_item_query2_cap < n_pairs) {
+        cudaStreamSynchronize(c.stream);
+        cudaFree(g_item_query2); g_item_query2 = nullptr; g_item_query2_cap = 0;
+        SB_CUDA(cudaMalloc(&g_item_query2, sizeof(int) * (size_t)n_pairs));
+        g_item_query2_cap = n_pairs;
+    }
+    k_fill_pair_query<<<(unsigned)(q_end - q_begin), 128, 0, c.stream>>>(d_desc, q_begin, pair_first, g_item_query2);
+    c.launches += 1;
+    if (image->dtype == SB_U8)
+        k_match_pair<uint8_t><<<(unsigned)n_pairs, QT, smem, c.stream>>>(
+            reinterpret_cast<const float4*>(d_parts), part_first, reinterpret_cast<const float4*>(image->d_specq), image->nblkq,
+            static_cast<const uint8_t*>(image->d_raw), image->n, image->d_pfx, tmpl->d_pfx, d_desc, g_item_query2, pair_first,
+            tab, d_keys, d_curve);
+    else
+        k_match_pair<float><<<(unsigned)n_pairs, QT, smem, c.stream>>>(
+            reinterpret_cast<const float4*>(d_parts), part_first, reinterpret_cast<const float4*>(image->d_specq), image->nblkq,
+            static_cast<const float*>(image->d_raw), image->n, image->d_pfx, tmpl->d_pfx, d_desc, g_item_query2, pair_first,
             tab, d_keys, d_curve);
     SB_CUDA(cudaGetLastError());
     return SB_OK;

@@ -41,7 +41,7 @@ struct QueryDesc {
     int64_t itemBase;  // first item of this query in the batch-wide item list
     int64_t partBase;  // first partition spectrum of this query
     int64_t curveOff;  // where this query's curve starts in the curve buffer (curve mode only)
-    int64_t groupBase; // first multiply group (MAC_GROUP consecutive lag blocks) of this query in the batch
+    int64_t groupBase; // first multiply group of this query in the batch: MAC_GROUP consecutive lag blocks (blocked class), pairs of lag blocks (direct class)
     int32_t P;         // ceil(n / H), H = hop = partition length
     int32_t k0;        // lag0 / LB, LB = lags per item
     int32_t nk;        // number of lag blocks touched
@@ -112,6 +112,9 @@ int launch_match_packed(const sb_stream* image, const sb_stream* tmpl, const flo
 int launch_match_ws(const sb_stream* image, const sb_stream* tmpl, const float2* d_parts, int64_t part_first,
                     const QueryDesc* d_desc, int q_begin, int q_end, int64_t item_first, int64_t n_items,
                     unsigned long long* d_keys, float* d_curve);
+int launch_match_pair(const sb_stream* image, const sb_stream* tmpl, const float2* d_parts, int64_t part_first,
+                      const QueryDesc* d_desc, int q_begin, int q_end, int64_t pair_first, int64_t n_pairs,
+                      unsigned long long* d_keys, float* d_curve);
 int launch_block_spectra_quad(const sb_stream* s, int64_t k_first, int64_t rows, float2* out);
 int launch_part_spectra_quad(const sb_stream* tmpl, const QueryDesc* d_desc, int q_begin, int q_end,
                              int64_t part_first, int64_t rows, float2* out);

@@ -412,7 +412,7 @@ int plan_batch(const sb_stream* image, const sb_stream* tmpl, int64_t count,
                 d.k0 = (int32_t)(s / LB);
                 d.nk = (int32_t)((s + L - 1) / LB - d.k0 + 1);
                 d.itemBase = items; d.partBase = parts; d.orig = (int32_t)q; d.curveOff = curve_total; d.groupBase = groups;
-                groups += (d.nk + MAC_GROUP - 1) / MAC_GROUP;
+                groups += cls == 0 ? (d.nk + 1) / 2 : (d.nk + MAC_GROUP - 1) / MAC_GROUP;
                 items += d.nk; parts += d.P;
                 maxp = std::max<int64_t>(maxp, d.P);
             }
@@ -522,7 +522,11 @@ int run_batch(const sb_stream* image_c, const sb_stream* tmpl, int64_t count,
         const int64_t item_hi = (qe < count) ? c.h_desc[qe].itemBase : total_items;
         if (use_packed && !premac) {
             ProfScope ps("match_fused");
-            if (c.engine == 3)
+            if (c.engine == 4) {
+                const int64_t g0 = c.h_desc[qb].groupBase;
+                const int64_t g1 = (qe < count) ? c.h_desc[qe].groupBase : total_groups;
+                SB_TRY(launch_match_pair(image, tmpl, c.d_parts, part_first, c.d_desc, (int)qb, (int)qe, g0, g1 - g0, c.d_keys, d_curve));
+            } else if (c.engine == 3)
                 SB_TRY(launch_match_ws(image, tmpl, c.d_parts, part_first, c.d_desc, (int)qb, (int)qe,
                                        item_lo, item_hi - item_lo, c.d_keys, d_curve));
             else
