@@ -71,10 +71,14 @@ int sb_sync(void);
 int sb_set_block_size(int block);
 int sb_get_block_size(void);
 /* Engine behind sb_find*:
- *   2 (default) = the packed fused lag-block kernel (sb_fused2.cu): spectral multiply, inverse FFT in
+ *   2 (default) = the packed fused lag-block kernels (sb_fused2.cu): spectral multiply, inverse FFT in
  *       shared memory, normalisation and argmin in one launch, written around the two-wide fp32
  *       instructions of sm_100 (FFMA2/FADD2) on spectra stored in a paired layout; lag blocks of 16384
- *       at hop B -- any other geometry silently runs engine 1;
+ *       at hop B -- any other geometry silently runs engine 1, and templates of 12+ partitions keep
+ *       engine 1's blocked multiply.  One CTA handles one lag block, or (batches averaging >= 1.5 template
+ *       partitions) a pair of consecutive lag blocks that share their template rows, the second product
+ *       spectrum waiting in tensor memory; both give bit-identical results;
+ *   4 / 5 = engine 2 with pairs always / never;
  *   3 = the same arithmetic as a persistent warp-specialised kernel (TMA-fed multiply warps park each
  *       item's product spectrum in tensor memory while the other warps transform the previous one);
  *   1 = the first fused lag-block kernel (sb_fused.cu; lag blocks of 8192 or 16384, hop B or B/2);

@@ -459,6 +459,16 @@ int run_batch(const sb_stream* image_c, const sb_stream* tmpl, int64_t count,
     int64_t n_direct = 0, total_items = 0, total_parts = 0, total_groups = 0, maxp = 0;
     SB_TRY(plan_batch(image, tmpl, count, toff, tlen, lag0, nlags, hd, use_fused && hd == 1, &n_direct,
                       &total_items, &total_parts, &total_groups, &maxp));
+    // Packed kernels: one CTA per lag block, or one per pair of consecutive lag blocks of a query (shared template
+    // rows, 2P+1 row reads instead of 4P, second product spectrum parked in tensor memory).  Both give bit-identical
+    // results; pairs pay from about two partitions per template (measured: +5 % on config 2, -8 % for 0.5 s events
+    // at +-10 s), so engine 2 picks per batch by the average partition count; engines 4 / 5 force one or the other.
+    bool use_pairs = c.engine == 4;
+    if (use_packed && c.engine == 2 && n_direct > 0) {
+        double rows = 0.0, blocks = 0.0;
+        for (int64_t q = 0; q < n_direct; ++q) { rows += (double)c.h_desc[q].nk * c.h_desc[q].P; blocks += (double)c.h_desc[q].nk; }
+        use_pairs = rows >= 1.5 * blocks;
+    }
     if (use_packed && n_direct > 0) SB_TRY(ensure_spectra_quad(image));
     if (!use_packed || n_direct < count) SB_TRY(ensure_spectra(image, hd));
 
@@ -522,7 +532,7 @@ int run_batch(const sb_stream* image_c, const sb_stream* tmpl, int64_t count,
         const int64_t item_hi = (qe < count) ? c.h_desc[qe].itemBase : total_items;
         if (use_packed && !premac) {
             ProfScope ps("match_fused");
-            if (c.engine == 4) {
+            if (use_pairs) {
                 const int64_t g0 = c.h_desc[qb].groupBase;
                 const int64_t g1 = (qe < count) ? c.h_desc[qe].groupBase : total_groups;
                 SB_TRY(launch_match_pair(image, tmpl, c.d_parts, part_first, c.d_desc, (int)qb, (int)qe, g0, g1 - g0, c.d_keys, d_curve));

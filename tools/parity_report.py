@@ -20,7 +20,7 @@ print('%-8s %-7s %-8s %9s %12s %12s %12s %8s' % ('type', 'event', 'window', 'lag
 for stype in ('uint8', 'float32'):
     src = WavStream.from_pcm(src_pcm, 12000, sample_type=stype)
     dst = WavStream.from_pcm(dst_pcm, 12000, sample_type=stype)
-    for engine in (4, 3, 2, 1, 0):
+    for engine in (5, 4, 3, 1, 0):
         _native.check(lib.sb_set_engine(engine))
         for ev_len, win in ((0.5, 10.0), (1.0, 10.0), (3.0, 10.0), (3.0, 60.0), (10.0, 10.0), (30.0, 10.0), (30.0, 60.0)):
             a = 100.0
@@ -34,5 +34,5 @@ for stype in ('uint8', 'float32'):
             print('%-8s %-7s %-8s %9d %12.3e %12.3e %12.3e %8s  engine=%s' % (
                 stype, '%gs' % ev_len, '+-%gs' % win, nlags, np.abs(gpu - ref).max(), np.abs(gpu - f64).max(),
                 np.abs(ref - f64).max(), 'same' if int(gpu.argmin()) == int(ref.argmin()) else 'DIFF(%d)' % (int(gpu.argmin()) - int(ref.argmin())),
-                {0: 'cufft', 1: 'fused', 2: 'packed', 3: 'packed_ws', 4: 'packed_pair'}[engine]))
+                {0: 'cufft', 1: 'fused', 2: 'packed', 3: 'packed_ws', 4: 'packed_pair', 5: 'packed_single'}[engine]))
     _native.check(lib.sb_set_engine(2))
