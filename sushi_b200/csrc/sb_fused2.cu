@@ -1,23 +1,31 @@
-// Packed fused lag-block kernel (engine 2): the same per-item pipeline as sb_fused.cu
+// Packed fused lag-block kernels (engines 2-5): the same per-lag-block pipeline as sb_fused.cu
 //   spectral multiply-accumulate -> Hermitian packing -> inverse FFT in shared memory -> window sums,
 //   fp32 screening, fp64 evaluation of the lags that can win -> one 64-bit atomicMin
 // rebuilt around Blackwell's two-wide fp32 instructions (FFMA2 / FADD2 / FMUL2).  sb_fused.cu is bound by
-// instruction issue in its FFT and epilogue phases; here every value the kernel touches is one half of a
+// instruction issue in its FFT and epilogue phases; here every value the kernels touch is one half of a
 // float2 whose two halves go through identical arithmetic, so one issued instruction does the work of two:
 //
 //  * Spectra are stored in a "quad" layout: 16-byte chunks A[i] = (re X[i], re X[i+B/2], im X[i], im X[i+B/2])
-//    and M[i] = (re X[B-i], re X[B/2-i], im X[B-i], im X[B/2-i]), i = 0 .. B/4 (blocks of 256 A + 256 M).  One LDG.128 per operand
-//    feeds four FFMA2 for two bins; the Hermitian packing of bins (i, B-i) and (i+B/2, B/2-i) is elementwise
-//    on those pairs.
+//    and M[i] = (re X[B-i], re X[B/2-i], im X[B-i], im X[B/2-i]), i = 0 .. B/4, in blocks of 256 A + 256 M.
+//    One LDG.128 per operand feeds four FFMA2 for two bins; the Hermitian packing of bins (i, B-i) and
+//    (i+B/2, B/2-i) is elementwise on those pairs.
 //  * The first radix-2 step of the inverse FFT (decimation in frequency) is done on the packed pair itself:
 //    u[i] = Z[i] + Z[i+B/2], v[i] = (Z[i] - Z[i+B/2]) * W^i.  u and v are two INDEPENDENT half-size
 //    transforms with identical twiddles, X[2o] = FFT(u)[o], X[2o+1] = FFT(v)[o]; they travel together as
-//    chunks (u.re, v.re, u.im, v.im) through three radix-16 Stockham passes (LDS.128 / STS.128, shared
-//    twiddles as scalar-broadcast operands), and the last radix-2 step (of which only the "+" half carries
-//    valid lags) is folded into the epilogue.
+//    pairs (u.re, v.re), (u.im, v.im) through three radix-16 Stockham passes (shared twiddles as
+//    scalar-broadcast operands), and the last radix-2 step (of which only the "+" half carries valid lags)
+//    is folded into the epilogue.
 //  * Twiddles of the packing stage are formed in registers from one per-thread base value, so the 64 KB
 //    table sb_fused.cu streams from L2 for every item is gone; spectrum rows are 128-byte aligned.
-// Values agree with sb_fused.cu / the cuFFT engine to fp32 FFT rounding (~1e-7 of the curve).
+//
+// Three kernels share these pieces:
+//   k_match_packed  one CTA per lag block;
+//   k_match_pair    one CTA per pair of consecutive lag blocks of a query: both are multiplied at once (2P+1
+//                   spectrum-row reads instead of 4P), the second product spectrum waits in tensor memory
+//                   while the first is transformed -- the default for templates of two or more partitions;
+//   k_match_ws      a persistent warp-specialised variant (experimental, engine 3).
+// Values agree with sb_fused.cu / the cuFFT engine to fp32 FFT rounding (~2e-7 of the curve); k_match_packed and
+// k_match_pair agree bit for bit.
 #include "sb_internal.h"
 #include <cmath>
 #include <cstdlib>
@@ -562,8 +570,9 @@ k_match_packed(const float4* __restrict__ That, int64_t part_first,
 // k_match_packed runs its phases back to back on one CTA per SM: while it multiplies (loads from L2, issue
 // slots idle) nothing transforms, and while it transforms nothing loads.  Here one persistent CTA per SM
 // splits the work over two roles that overlap across consecutive items:
-//   8 multiply warps       two threads per TMEM lane L own quads i = L + 128*m (even / odd m).  A ring of WS_STAGES stages (one 256-quad block of a
-//                          T^ row and of an X^ row, 16 KB) is filled by TMA bulk copies WS_STAGES-1 steps ahead
+//   8 multiply warps       two threads per TMEM lane L own quads i = L + 128*m (even / odd m).  A ring of
+//                          WS_STAGES stages (one 256-quad block of a T^ row and of an X^ row, 16 KB) is
+//                          filled by TMA bulk copies WS_STAGES-1 steps ahead
 //                          -- across items, so the L2 latency never surfaces; the warps take turns issuing;
 //                          they multiply-accumulate from the ring and park the product spectrum in TENSOR
 //                          MEMORY with tcgen05.st (the tensor cores are idle, so their 256 KB of TMEM are a
