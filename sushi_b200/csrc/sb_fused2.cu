@@ -582,6 +582,8 @@ k_match_packed(const float4* __restrict__ That, int64_t part_first,
 // A multiply thread writes TMEM lane L (a warp reaches only the 32 lanes of its quarter), columns
 // b*256 + 8*m + {0..7} for quad L + 128m; transform thread t reads lane t & 127, 64 columns from (t >> 7)*64
 // (eight quads), packs them and scatters the 16 chunks to their places.
+// Measured (profiles/README.md): correct, but 20.8 ms per config-2 step against 17.8 ms for k_match_pair -- the
+// multiply side is a latency-bound instruction stream on few warps -- so it is not the default.
 constexpr int WS_THREADS = 768, WS_MACW = 8, WS_STAGES = 3, WS_SEG = 128, WS_SEGS = Q4 / QBLK;
 constexpr int WS_STAGE_F4 = 2 * 2 * QBLK;                // float4 per ring stage: one block (256 A + 256 M) of a T^ row and of an X^ row
 constexpr unsigned WS_STAGE_BYTES = WS_STAGE_F4 * 16;
