@@ -96,6 +96,12 @@ int sb_set_premac_mode(int mode);
  * pays off only for templates shorter than B/2), 0 = chosen per batch by a cost rule.  Geometries
  * agree to float32 FFT rounding (~1e-7), not bit for bit, so a run should stick to one. */
 int sb_set_hop_mode(int mode);
+/* Screening loop of the packed kernels (engines 2, 4, 5) on uint8 streams: 1 (default) = the first version,
+ * 2 = a trimmed one (7 instead of 13 arithmetic instructions per lag, byte extraction by PRMT, border test
+ * hoisted).  Screening only selects the lags that get the exact fp64 evaluation, so results are identical
+ * bit for bit; float32 streams and the other engines ignore the setting. */
+int sb_set_epilogue(int variant);
+int sb_get_epilogue(void);
 /* Lag blocks processed per multiply / inverse-FFT / normalise launch (>= 1). */
 int sb_set_chunk_items(int items);
 /* Template partition spectra kept resident per pass over a batch (>= 1); batches needing more are

@@ -228,6 +228,12 @@ int sb_set_hop_mode(int mode) {
     ctx().hop_mode = mode;
     return SB_OK;
 }
+int sb_set_epilogue(int variant) {
+    if (variant < 1 || variant > 2) SB_FAIL(SB_EINVAL, "sb_set_epilogue: %d is not 1 (first screening loop) or 2 (trimmed screening loop)", variant);
+    ctx().epilogue = variant;
+    return SB_OK;
+}
+int sb_get_epilogue(void) { return ctx().epilogue; }
 int sb_set_max_parts(int64_t parts) {
     if (parts < 1) SB_FAIL(SB_EINVAL, "sb_set_max_parts: %lld < 1", (long long)parts);
     ctx().max_parts = parts;

@@ -69,6 +69,7 @@ __device__ constexpr float kS64[8] = {0.0f, 0.098017140329560602f, 0.19509032201
 
 // ---------------------------------------------------------------- packed arithmetic
 struct C2 { float2 r, i; };     // two complex numbers (u, v): r = (u.re, v.re), i = (u.im, v.im)
+template <bool V> struct BoolTag { static constexpr bool value = V; };
 
 __device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
 __device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
@@ -315,7 +316,7 @@ __device__ __forceinline__ void fft_passes(const Buf& buf, int tid, const Packed
 // Window sums, fp32 screening of every lag, fp64 evaluation of the lags that can still be the minimum, merge
 // into the query's key.  after_read() runs (on all 512 threads) once every thread is done with the staged
 // windows -- k_match_ws starts the copies of its next item there.
-template <typename S, int ID, typename AfterRead>
+template <typename S, int ID, int EPI, typename AfterRead>
 __device__ __forceinline__ void finish_item(const Item& it, int tid, const Smem& sm, unsigned long long* s_bar, unsigned bar_parity,
                                             unsigned long long* s_best, float* s_min,
                                             const S* __restrict__ img, int64_t img_n,
@@ -324,6 +325,8 @@ __device__ __forceinline__ void finish_item(const Item& it, int tid, const Smem&
                                             float* __restrict__ curve_out, AfterRead after_read) {
     constexpr int B = QB, NW = QNW, LB = QB, ROUNDS = kRounds, LAGS_PER_ROUND = kLagsPerRound;
     constexpr bool is_u8 = sizeof(S) == 1;
+    constexpr bool v2 = EPI == 2 && is_u8;                 // trimmed screening (see the comment at its loop)
+    constexpr float kSent = v2 ? 3.0e38f : 2.0f;           // screening value of a lag outside the query's range
     const float* img32 = reinterpret_cast<const float*>(img);
     const Buf& buf = sm.buf;
     const int lane = tid & 31, warp = tid >> 5;
@@ -346,7 +349,8 @@ __device__ __forceinline__ void finish_item(const Item& it, int tid, const Smem&
     const float4 wt = __ldg(reinterpret_cast<const float4*>(tab.w8) + tid);   // W8192^(2tid), W8192^(2tid+1)
 
     float vf[ROUNDS][8];
-    float tmin = 2.0f;
+    float tmin = kSent;
+    const float m2s = -2.0f * f_scale, m2b = -2.0f * f_b;             // v2 screening
     if (is_u8) mbar_wait(s_bar, bar_parity);
 #pragma unroll
     for (int c = 0; c < ROUNDS; ++c) {
@@ -355,7 +359,7 @@ __device__ __forceinline__ void finish_item(const Item& it, int tid, const Smem&
         const int64_t jw = j_blk + c * LAGS_PER_ROUND + warp * 256;
         if (jw >= jhi || jw + 256 <= jlo) {                            // no valid lag in this warp-round (warp-uniform)
 #pragma unroll
-            for (int i = 0; i < 8; ++i) vf[c][i] = 2.0f;
+            for (int i = 0; i < 8; ++i) vf[c][i] = kSent;
             continue;
         }
         // correlation at the 8 lags: last radix-2 step on chunks 1024c + 2tid + {0, 1}
@@ -376,6 +380,7 @@ __device__ __forceinline__ void finish_item(const Item& it, int tid, const Smem&
             cc[4 * e + 0] = xr.x; cc[4 * e + 1] = xi.x; cc[4 * e + 2] = xr.y; cc[4 * e + 3] = xi.y;
         }
         float f_w0q, f_k0;
+        float f_A = 0.f;                                               // v2: everything constant over the run
         unsigned long long lo8 = 0, hi8 = 0;
         if (is_u8) {
             // everything comes from shared memory: lane l owns the run of 8 lags starting at jw + 8l.  Window
@@ -399,17 +404,53 @@ __device__ __forceinline__ void finish_item(const Item& it, int tid, const Smem&
             const double2 b_lo = sm.base[(c * NW + warp) * 2], b_hi = sm.base[(c * NW + warp) * 2 + 1];
             const double w0s = (b_hi.x - b_lo.x) + (double)(is - ts);
             const double w0q = (b_hi.y - b_lo.y) + (double)(iq - tq);
-            f_w0q = (float)w0q;
-            f_k0 = (float)(b * w0s + k_const);
+            if (v2) {
+                // the 0.25 keeps a silent window (sum of squares 0) finite under rsqrt; it is below one ulp of any
+                // window sum that is not within 8 samples of silence
+                f_w0q = (float)(w0q + 0.25);
+                f_k0 = 0.f;
+                f_A = (float)(w0q + tsq - 2.0 * (b * w0s + k_const));
+            } else {
+                f_w0q = (float)w0q;
+                f_k0 = (float)(b * w0s + k_const);
+            }
         } else {
             if (!(j0 < jhi && j0 + 8 > jlo)) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) vf[c][i] = 2.0f;
+                for (int i = 0; i < 8; ++i) vf[c][i] = kSent;
                 continue;
             }
             const double2 p_hi = ipfx[j0 + n], p_lo = ipfx[j0];
             f_w0q = (float)(p_hi.y - p_lo.y);
             f_k0 = (float)(b * (p_hi.x - p_lo.x) + k_const);
+        }
+        if constexpr (v2) {
+            // Trimmed screening (uint8).  The screening values only select which lags get the exact fp64
+            // evaluation below, so they may be any quantity that (a) orders the lags like the true value to within
+            // the screening margin and (b) makes saturated / degenerate blocks fall back to "evaluate everything":
+            //   v' = (A + rq - 2b*rs - 2*scale*cc) * rsqrt(wq)  =  value * sqrt(sum T^2),
+            // A = w0q + sum T^2 - 2(b*w0s + k) rounded once from fp64 -- 7 instructions per lag instead of 13
+            // (no clamps, no product with sum T^2, the 2*sit doubling folded into the constants); bytes come out
+            // of the staged words by PRMT, and the interior / border distinction is hoisted out of the lag loop.
+            const unsigned la = (unsigned)lo8, lb = (unsigned)(lo8 >> 32), ha = (unsigned)hi8, hb2 = (unsigned)(hi8 >> 32);
+            auto run8 = [&](auto border_tag) {
+                constexpr bool BORDER = decltype(border_tag)::value;
+                int rq = 0, rs = 0;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float frq = (float)rq;
+                    const float num = fmaf(cc[i], m2s, fmaf(m2b, (float)rs, f_A + frq));
+                    const float v = num * rsqrt_fast(f_w0q + frq);
+                    if (!BORDER || (j0 + i >= jlo && j0 + i < jhi)) { vf[c][i] = v; tmin = fminf(tmin, v); }
+                    else vf[c][i] = kSent;
+                    const unsigned sel = 0x4440u | (unsigned)(i & 3);
+                    const int lo = (int)__byte_perm(i < 4 ? la : lb, 0u, sel), hi = (int)__byte_perm(i < 4 ? ha : hb2, 0u, sel);
+                    const int dd = hi - lo;
+                    rq += (hi + lo) * dd; rs += dd;
+                }
+            };
+            if (interior) run8(BoolTag<false>{}); else run8(BoolTag<true>{});
+            continue;
         }
         int rq = 0, rs = 0;              // uint8: exact integer slide
         double dq = 0.0, ds = 0.0;       // float32: fp64 slide
@@ -423,7 +464,7 @@ __device__ __forceinline__ void finish_item(const Item& it, int tid, const Smem&
             const float v = fminf(num * rsqrt_fast(pr), 1.0f);
             if (interior) { vf[c][i] = v; tmin = fminf(tmin, v); }
             else if (j0 + i >= jlo && j0 + i < jhi) { vf[c][i] = v; tmin = fminf(tmin, v); }
-            else vf[c][i] = 2.0f;                                      // sentinel: not a valid lag
+            else vf[c][i] = kSent;                                     // sentinel: not a valid lag
             if (is_u8) {
                 const int lo = (int)((lo8 >> (8 * i)) & 0xffu), hi = (int)((hi8 >> (8 * i)) & 0xffu);
                 rq += hi * hi - lo * lo; rs += hi - lo;
@@ -443,14 +484,22 @@ __device__ __forceinline__ void finish_item(const Item& it, int tid, const Smem&
     float bmin = s_min[0];
 #pragma unroll
     for (int w = 1; w < NW; ++w) bmin = fminf(bmin, s_min[w]);
-    const float thr = curve_out ? 1.5f : bmin + kScreenMargin;       // debug curve: evaluate everything
+    float thr = curve_out ? 1.5f : bmin + kScreenMargin;             // debug curve: evaluate everything
+    bool all = false;                // v2: every lag of the range is a candidate
+    if (v2) {
+        // screening values are scaled by sqrt(sum T^2) and not clamped at 1: a block whose minimum is (nearly)
+        // saturated -- or a zero template -- evaluates all its lags, like the clamped values of v1 would
+        const float rt = sqrtf(f_tsq);
+        thr = bmin + kScreenMargin * rt;
+        all = curve_out != nullptr || !(bmin < (1.0f - kScreenMargin) * rt);
+    }
 
     unsigned long long cand = 0;
-    if (my_min <= thr) {
+    if (my_min <= thr || all) {
 #pragma unroll
         for (int c = 0; c < ROUNDS; ++c)
 #pragma unroll
-            for (int i = 0; i < 8; ++i) cand |= (vf[c][i] <= thr) ? (1ull << (c * 8 + i)) : 0ull;
+            for (int i = 0; i < 8; ++i) cand |= (vf[c][i] <= thr || (all && vf[c][i] < kSent)) ? (1ull << (c * 8 + i)) : 0ull;
     }
     unsigned long long best = ~0ull;
     while (cand) {
@@ -485,7 +534,7 @@ __device__ __forceinline__ void finish_item(const Item& it, int tid, const Smem&
 }
 
 // ---------------------------------------------------------------- kernel A: one CTA per item
-template <typename S>
+template <typename S, int EPI>
 __global__ void __launch_bounds__(QT, 1)
 k_match_packed(const float4* __restrict__ That, int64_t part_first,
                const float4* __restrict__ Xhat, int64_t nblk,
@@ -563,7 +612,7 @@ k_match_packed(const float4* __restrict__ That, int64_t part_first,
 
     // ---------------- 3. inverse FFT, 4. epilogue ---------------------------------------------
     fft_passes<0>(buf, tid, tab, is_u8);
-    finish_item<S, 0>(it, tid, sm, s_bar, 0u, s_best, s_min, img, img_n, ipfx, tpfx, tab, keys, curve_out, [] {});
+    finish_item<S, 0, EPI>(it, tid, sm, s_bar, 0u, s_best, s_min, img, img_n, ipfx, tpfx, tab, keys, curve_out, [] {});
 }
 
 // ---------------------------------------------------------------- kernel B: persistent, warp-specialised
@@ -728,7 +777,7 @@ k_match_ws(const float4* __restrict__ That, int64_t part_first,
             mbar_arrive(tm_empty + b);
             csync<1>();
             fft_passes<1>(buf, tid, tab, is_u8);
-            finish_item<S, 1>(it, tid, sm, s_bar, n & 1u, s_best, s_min, img, img_n, ipfx, tpfx, tab, keys, curve_out,
+            finish_item<S, 1, 1>(it, tid, sm, s_bar, n & 1u, s_best, s_min, img, img_n, ipfx, tpfx, tab, keys, curve_out,
                               [&] {   // every thread is done with the staged windows: start the next item's copies
                                   if (is_u8 && local + gridDim.x < n_items) {
                                       const Item nxt(desc, item_query, item_first, local + gridDim.x);
@@ -829,7 +878,7 @@ k_match_ws(const float4* __restrict__ That, int64_t part_first,
 // parked in TENSOR MEMORY (tcgen05.st; every thread later reads back exactly what it wrote, so the 32-lane
 // window of a warp is no constraint) while the CTA transforms the first; then it is taken out again
 // (tcgen05.ld) and goes through the same passes and epilogue.
-template <typename S>
+template <typename S, int EPI>
 __global__ void __launch_bounds__(QT, 1)
 k_match_pair(const float4* __restrict__ That, int64_t part_first,
              const float4* __restrict__ Xhat, int64_t nblk,
@@ -933,7 +982,7 @@ k_match_pair(const float4* __restrict__ That, int64_t part_first,
 
     // ---------------- first item: inverse FFT + epilogue ---------------------------------------
     fft_passes<0>(buf, tid, tab, is_u8);
-    finish_item<S, 0>(it0, tid, sm, s_bar, 0u, s_best, s_min, img, img_n, ipfx, tpfx, tab, keys, curve_out,
+    finish_item<S, 0, EPI>(it0, tid, sm, s_bar, 0u, s_best, s_min, img, img_n, ipfx, tpfx, tab, keys, curve_out,
                       [&] { if (is_u8 && has2) stage_inputs(it1, tid, reinterpret_cast<const uint8_t*>(img), img_n, ipfx, sm, s_bar); });
 
     // ---------------- second item: out of tensor memory, then the same ---------------------------
@@ -956,7 +1005,7 @@ k_match_pair(const float4* __restrict__ That, int64_t part_first,
         if (tid == (NW - 1) * 32) buf.st(phys(Q4), sp1);
         csync<0>();
         fft_passes<0>(buf, tid, tab, is_u8);
-        finish_item<S, 0>(it1, tid, sm, s_bar, 1u, s_best, s_min, img, img_n, ipfx, tpfx, tab, keys, curve_out, [] {});
+        finish_item<S, 0, EPI>(it1, tid, sm, s_bar, 1u, s_best, s_min, img, img_n, ipfx, tpfx, tab, keys, curve_out, [] {});
     }
     tmem_fence_before();
     csync<0>();
@@ -1123,6 +1172,82 @@ int launch_forward_quad_typed(const sb_stream* src, const QueryDesc* d_desc, int
     return SB_OK;
 }
 
+// item -> query map of the current launch (one int per CTA), grown on demand
+int ensure_item_query(int64_t n) {
+    if (g_item_query2_cap < n) {
+        cudaStreamSynchronize(ctx().stream);
+        cudaFree(g_item_query2); g_item_query2 = nullptr; g_item_query2_cap = 0;
+        SB_CUDA(cudaMalloc(&g_item_query2, sizeof(int) * (size_t)n));
+        g_item_query2_cap = n;
+    }
+    return SB_OK;
+}
+
+// Launchers of the three match kernels.  `Kernel` is one instantiation (sample type x epilogue variant); its
+// dynamic shared memory limit is raised once.  The uint8 kernels exist with both epilogues (Ctx::epilogue),
+// float32 streams have the first one only.
+template <typename S, int EPI>
+int launch_packed_typed(const sb_stream* image, const sb_stream* tmpl, const float2* d_parts, int64_t part_first,
+                        const QueryDesc* d_desc, int64_t item_first, int64_t n_items, const PackedTables& tab,
+                        unsigned long long* d_keys, float* d_curve) {
+    Ctx& c = ctx();
+    static bool attr_set = false;
+    const size_t smem = packed_smem_bytes();
+    if (!attr_set) {
+        SB_CUDA(cudaFuncSetAttribute(k_match_packed<S, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    const int64_t max_grid = 1 << 30;
+    for (int64_t i0 = 0; i0 < n_items; i0 += max_grid) {
+        const int64_t ni = std::min<int64_t>(max_grid, n_items - i0);
+        k_match_packed<S, EPI><<<(unsigned)ni, QT, smem, c.stream>>>(
+            reinterpret_cast<const float4*>(d_parts), part_first, reinterpret_cast<const float4*>(image->d_specq), image->nblkq,
+            static_cast<const S*>(image->d_raw), image->n, image->d_pfx, tmpl->d_pfx, d_desc, g_item_query2 + i0, item_first + i0,
+            tab, d_keys, d_curve);
+    }
+    SB_CUDA(cudaGetLastError());
+    return SB_OK;
+}
+
+template <typename S, int EPI>
+int launch_pair_typed(const sb_stream* image, const sb_stream* tmpl, const float2* d_parts, int64_t part_first,
+                      const QueryDesc* d_desc, int64_t pair_first, int64_t n_pairs, const PackedTables& tab,
+                      unsigned long long* d_keys, float* d_curve) {
+    Ctx& c = ctx();
+    static bool attr_set = false;
+    const size_t smem = packed_smem_bytes() + 16;
+    if (!attr_set) {
+        SB_CUDA(cudaFuncSetAttribute(k_match_pair<S, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    k_match_pair<S, EPI><<<(unsigned)n_pairs, QT, smem, c.stream>>>(
+        reinterpret_cast<const float4*>(d_parts), part_first, reinterpret_cast<const float4*>(image->d_specq), image->nblkq,
+        static_cast<const S*>(image->d_raw), image->n, image->d_pfx, tmpl->d_pfx, d_desc, g_item_query2, pair_first,
+        tab, d_keys, d_curve);
+    SB_CUDA(cudaGetLastError());
+    return SB_OK;
+}
+
+template <typename S>
+int launch_ws_typed(const sb_stream* image, const sb_stream* tmpl, const float2* d_parts, int64_t part_first,
+                    const QueryDesc* d_desc, int64_t item_first, int64_t n_items, const PackedTables& tab,
+                    unsigned long long* d_keys, float* d_curve) {
+    Ctx& c = ctx();
+    static bool attr_set = false;
+    const size_t smem = ws_smem_bytes();
+    if (!attr_set) {
+        SB_CUDA(cudaFuncSetAttribute(k_match_ws<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    const unsigned grid = (unsigned)std::min<int64_t>(n_items, c.sm_count);     // one persistent CTA per SM
+    k_match_ws<S><<<grid, WS_THREADS, smem, c.stream>>>(
+        reinterpret_cast<const float4*>(d_parts), part_first, reinterpret_cast<const float4*>(image->d_specq), image->nblkq,
+        static_cast<const S*>(image->d_raw), image->n, image->d_pfx, tmpl->d_pfx, d_desc, g_item_query2, item_first, n_items,
+        tab, d_keys, d_curve);
+    SB_CUDA(cudaGetLastError());
+    return SB_OK;
+}
+
 }  // namespace
 
 namespace sb {
@@ -1135,38 +1260,14 @@ int launch_match_packed(const sb_stream* image, const sb_stream* tmpl, const flo
     Ctx& c = ctx();
     PackedTables tab;
     SB_TRY(ensure_packed_tables(&tab));
-    static bool attr_set = false;
-    const size_t smem = packed_smem_bytes();
-    if (!attr_set) {
-        SB_CUDA(cudaFuncSetAttribute(k_match_packed<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SB_CUDA(cudaFuncSetAttribute(k_match_packed<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
-    if (g_item_query2_cap < n_items) {
-        cudaStreamSynchronize(c.stream);
-        cudaFree(g_item_query2); g_item_query2 = nullptr; g_item_query2_cap = 0;
-        SB_CUDA(cudaMalloc(&g_item_query2, sizeof(int) * (size_t)n_items));
-        g_item_query2_cap = n_items;
-    }
+    SB_TRY(ensure_item_query(n_items));
     k_fill_item_query2<<<(unsigned)(q_end - q_begin), 128, 0, c.stream>>>(d_desc, q_begin, item_first, g_item_query2);
     c.launches += 1;
-    const bool u8 = image->dtype == SB_U8;
-    const int64_t max_grid = 1 << 30;
-    for (int64_t i0 = 0; i0 < n_items; i0 += max_grid) {
-        const int64_t ni = std::min<int64_t>(max_grid, n_items - i0);
-        if (u8)
-            k_match_packed<uint8_t><<<(unsigned)ni, QT, smem, c.stream>>>(
-                reinterpret_cast<const float4*>(d_parts), part_first, reinterpret_cast<const float4*>(image->d_specq), image->nblkq,
-                static_cast<const uint8_t*>(image->d_raw), image->n, image->d_pfx, tmpl->d_pfx, d_desc, g_item_query2 + i0, item_first + i0,
-                tab, d_keys, d_curve);
-        else
-            k_match_packed<float><<<(unsigned)ni, QT, smem, c.stream>>>(
-                reinterpret_cast<const float4*>(d_parts), part_first, reinterpret_cast<const float4*>(image->d_specq), image->nblkq,
-                static_cast<const float*>(image->d_raw), image->n, image->d_pfx, tmpl->d_pfx, d_desc, g_item_query2 + i0, item_first + i0,
-                tab, d_keys, d_curve);
-    }
-    SB_CUDA(cudaGetLastError());
-    return SB_OK;
+    if (image->dtype != SB_U8)
+        return launch_packed_typed<float, 1>(image, tmpl, d_parts, part_first, d_desc, item_first, n_items, tab, d_keys, d_curve);
+    return c.epilogue == 2
+        ? launch_packed_typed<uint8_t, 2>(image, tmpl, d_parts, part_first, d_desc, item_first, n_items, tab, d_keys, d_curve)
+        : launch_packed_typed<uint8_t, 1>(image, tmpl, d_parts, part_first, d_desc, item_first, n_items, tab, d_keys, d_curve);
 }
 
 int launch_match_ws(const sb_stream* image, const sb_stream* tmpl, const float2* d_parts, int64_t part_first,
@@ -1175,34 +1276,12 @@ int launch_match_ws(const sb_stream* image, const sb_stream* tmpl, const float2*
     Ctx& c = ctx();
     PackedTables tab;
     SB_TRY(ensure_packed_tables(&tab));
-    static bool attr_set = false;
-    const size_t smem = ws_smem_bytes();
-    if (!attr_set) {
-        SB_CUDA(cudaFuncSetAttribute(k_match_ws<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SB_CUDA(cudaFuncSetAttribute(k_match_ws<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
-    if (g_item_query2_cap < n_items) {
-        cudaStreamSynchronize(c.stream);
-        cudaFree(g_item_query2); g_item_query2 = nullptr; g_item_query2_cap = 0;
-        SB_CUDA(cudaMalloc(&g_item_query2, sizeof(int) * (size_t)n_items));
-        g_item_query2_cap = n_items;
-    }
+    SB_TRY(ensure_item_query(n_items));
     k_fill_item_query2<<<(unsigned)(q_end - q_begin), 128, 0, c.stream>>>(d_desc, q_begin, item_first, g_item_query2);
     c.launches += 1;
-    const unsigned grid = (unsigned)std::min<int64_t>(n_items, c.sm_count);     // one persistent CTA per SM
-    if (image->dtype == SB_U8)
-        k_match_ws<uint8_t><<<grid, WS_THREADS, smem, c.stream>>>(
-            reinterpret_cast<const float4*>(d_parts), part_first, reinterpret_cast<const float4*>(image->d_specq), image->nblkq,
-            static_cast<const uint8_t*>(image->d_raw), image->n, image->d_pfx, tmpl->d_pfx, d_desc, g_item_query2, item_first, n_items,
-            tab, d_keys, d_curve);
-    else
-        k_match_ws<float><<<grid, WS_THREADS, smem, c.stream>>>(
-            reinterpret_cast<const float4*>(d_parts), part_first, reinterpret_cast<const float4*>(image->d_specq), image->nblkq,
-            static_cast<const float*>(image->d_raw), image->n, image->d_pfx, tmpl->d_pfx, d_desc, g_item_query2, item_first, n_items,
-            tab, d_keys, d_curve);
-    SB_CUDA(cudaGetLastError());
-    return SB_OK;
+    return image->dtype == SB_U8
+        ? launch_ws_typed<uint8_t>(image, tmpl, d_parts, part_first, d_desc, item_first, n_items, tab, d_keys, d_curve)
+        : launch_ws_typed<float>(image, tmpl, d_parts, part_first, d_desc, item_first, n_items, tab, d_keys, d_curve);
 }
 
 int launch_match_pair(const sb_stream* image, const sb_stream* tmpl, const float2* d_parts, int64_t part_first,
@@ -1211,33 +1290,14 @@ int launch_match_pair(const sb_stream* image, const sb_stream* tmpl, const float
     Ctx& c = ctx();
     PackedTables tab;
     SB_TRY(ensure_packed_tables(&tab));
-    static bool attr_set = false;
-    const size_t smem = packed_smem_bytes() + 16;
-    if (!attr_set) {
-        SB_CUDA(cudaFuncSetAttribute(k_match_pair<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SB_CUDA(cudaFuncSetAttribute(k_match_pair<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
-    if (g_item_query2_cap < n_pairs) {
-        cudaStreamSynchronize(c.stream);
-        cudaFree(g_item_query2); g_item_query2 = nullptr; g_item_query2_cap = 0;
-        SB_CUDA(cudaMalloc(&g_item_query2, sizeof(int) * (size_t)n_pairs));
-        g_item_query2_cap = n_pairs;
-    }
+    SB_TRY(ensure_item_query(n_pairs));
     k_fill_pair_query<<<(unsigned)(q_end - q_begin), 128, 0, c.stream>>>(d_desc, q_begin, pair_first, g_item_query2);
     c.launches += 1;
-    if (image->dtype == SB_U8)
-        k_match_pair<uint8_t><<<(unsigned)n_pairs, QT, smem, c.stream>>>(
-            reinterpret_cast<const float4*>(d_parts), part_first, reinterpret_cast<const float4*>(image->d_specq), image->nblkq,
-            static_cast<const uint8_t*>(image->d_raw), image->n, image->d_pfx, tmpl->d_pfx, d_desc, g_item_query2, pair_first,
-            tab, d_keys, d_curve);
-    else
-        k_match_pair<float><<<(unsigned)n_pairs, QT, smem, c.stream>>>(
-            reinterpret_cast<const float4*>(d_parts), part_first, reinterpret_cast<const float4*>(image->d_specq), image->nblkq,
-            static_cast<const float*>(image->d_raw), image->n, image->d_pfx, tmpl->d_pfx, d_desc, g_item_query2, pair_first,
-            tab, d_keys, d_curve);
-    SB_CUDA(cudaGetLastError());
-    return SB_OK;
+    if (image->dtype != SB_U8)
+        return launch_pair_typed<float, 1>(image, tmpl, d_parts, part_first, d_desc, pair_first, n_pairs, tab, d_keys, d_curve);
+    return c.epilogue == 2
+        ? launch_pair_typed<uint8_t, 2>(image, tmpl, d_parts, part_first, d_desc, pair_first, n_pairs, tab, d_keys, d_curve)
+        : launch_pair_typed<uint8_t, 1>(image, tmpl, d_parts, part_first, d_desc, pair_first, n_pairs, tab, d_keys, d_curve);
 }
 
 int launch_block_spectra_quad(const sb_stream* s, int64_t k_first, int64_t rows, float2* out) {
