@@ -79,6 +79,8 @@ int sb_get_block_size(void);
  *       partitions) a pair of consecutive lag blocks that share their template rows, the second product
  *       spectrum waiting in tensor memory; both give bit-identical results;
  *   4 / 5 = engine 2 with pairs always / never;
+ *   6 = engine 2 over TRIPLES of consecutive lag blocks (2P + 2 spectrum-row reads per three blocks, two product
+ *       spectra parked in tensor memory); opt-in, not measured yet;
  *   3 = the same arithmetic as a persistent warp-specialised kernel (TMA-fed multiply warps park each
  *       item's product spectrum in tensor memory while the other warps transform the previous one);
  *   1 = the first fused lag-block kernel (sb_fused.cu; lag blocks of 8192 or 16384, hop B or B/2);

@@ -213,7 +213,7 @@ int sb_set_block_size(int block) {
 }
 int sb_get_block_size(void) { return ctx().B; }
 int sb_set_engine(int engine) {
-    if (engine < 0 || engine > 5) SB_FAIL(SB_EINVAL, "sb_set_engine: %d is not one of 0 (cuFFT pipeline), 1 (fused kernel), 2 (packed fused kernels), 3 (warp-specialised packed kernel), 4 / 5 (packed kernel always / never over pairs of lag blocks)", engine);
+    if (engine < 0 || engine > 6) SB_FAIL(SB_EINVAL, "sb_set_engine: %d is not one of 0 (cuFFT pipeline), 1 (fused kernel), 2 (packed fused kernels), 3 (warp-specialised packed kernel), 4 / 5 (packed kernel always / never over pairs of lag blocks), 6 (packed kernel over triples of lag blocks)", engine);
     ctx().engine = engine;
     return SB_OK;
 }

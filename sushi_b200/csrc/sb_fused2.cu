@@ -1012,11 +1012,159 @@ k_match_pair(const float4* __restrict__ That, int64_t part_first,
     if (warp == 0) tmem_dealloc(*s_taddr, 256);
 }
 
+// ---------------------------------------------------------------- kernel A3: one CTA per TRIPLE of lag blocks
+// (engine 6; written without GPU access at the end of round 1 -- opt-in until it has been measured.)
+// k_match_pair's multiply phase runs at the L2 -> SM rate, so only fewer bytes make it faster: three consecutive
+// lag blocks of a query share their template rows and overlap in their spectrum rows, 2P + 2 row reads instead
+// of 3P + 3/2 for pairs (P = 2: 2.0 instead of 2.5 rows per lag block).  Tensor memory holds exactly two parked
+// product spectra (2 x 256 columns), so the first block goes to shared memory and the other two wait there.
+// Three accumulator sets leave room for one quad per thread and step; to keep as many loads in flight as the pair
+// kernel has, the rows of step p + 1 are requested before the multiply-accumulates of step p.
+template <typename S, int EPI>
+__global__ void __launch_bounds__(QT, 1)
+k_match_triple(const float4* __restrict__ That, int64_t part_first,
+               const float4* __restrict__ Xhat, int64_t nblk,
+               const S* __restrict__ img, int64_t img_n,
+               const double2* __restrict__ ipfx, const double2* __restrict__ tpfx,
+               const QueryDesc* __restrict__ desc, const int* __restrict__ trip_query, int64_t trip_first,
+               PackedTables tab, unsigned long long* __restrict__ keys, float* __restrict__ curve_out) {
+    constexpr int T = QT, NW = QNW;
+    constexpr bool is_u8 = sizeof(S) == 1;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const Smem sm(smem_raw);
+    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(sm.end);
+    unsigned long long* s_best = s_bar + 1;                                // [NW]
+    float* s_min = reinterpret_cast<float*>(s_best + NW);                  // [NW]
+    uint32_t* s_taddr = reinterpret_cast<uint32_t*>(s_min + NW);
+    const Buf& buf = sm.buf;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int q = __ldg(trip_query + blockIdx.x);
+    const QueryDesc d = desc[q];
+    const int lt = (int)(trip_first + blockIdx.x - d.groupBase);          // triple number inside the query
+    const int nb = d.nk - 3 * lt < 3 ? d.nk - 3 * lt : 3;                 // lag blocks of this CTA (uniform)
+    const Item it0(d, q, d.k0 + 3 * lt), it1(d, q, d.k0 + 3 * lt + 1), it2(d, q, d.k0 + 3 * lt + 2);
+
+    if (warp == 0) tmem_alloc(s_taddr, 512);
+    if (is_u8) {
+        if (tid == 0) mbar_init(s_bar, 1);
+        stage_inputs(it0, tid, reinterpret_cast<const uint8_t*>(img), img_n, ipfx, sm, s_bar);
+    }
+    tmem_fence_before();
+    csync<0>();
+    tmem_fence_after();
+    // this thread's columns: lane quarter of its warp, column block of its warp group; second block at +0,
+    // third block at +256
+    const uint32_t tcol = *s_taddr + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 64);
+
+    const int tm = (T - tid) & (T - 1);               // mirrored chunks C[B/2 - i] live in thread tm's column
+    const int col = phys(tid), mcol = phys(tm);
+    C2 sp1 = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)}, sp2 = sp1;   // C[B/4] of blocks 2 and 3 (warp NW-1, lane 0)
+    {
+        const int64_t k = it0.k;
+        const float4* tp = That + (d.partBase - part_first) * (int64_t)QROW;
+        const float4* xp = Xhat + k * (int64_t)QROW;
+        const float2 wbase = __ldg(tab.wb + tid);
+        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+        for (int uu = 0; uu < 8; ++uu) {              // quad i = tid + 512*uu
+            const int i0 = (tid >> 8) * (2 * QBLK) + (tid & (QBLK - 1)) + uu * (2 * T);        // qa(i)
+            QuadAcc a0, a1, a2;
+            a0.zero(); a1.zero(); a2.zero();
+            const bool row1 = k + 1 < nblk;           // rows past the end of the stream are zero
+            float4 x0a = ldg_stream(xp + i0), x0m = ldg_stream(xp + i0 + QBLK);                  // row k < nblk
+            float4 x1a = row1 ? ldg_stream(xp + QROW + i0) : zero4, x1m = row1 ? ldg_stream(xp + QROW + i0 + QBLK) : zero4;
+            float4 ta = ldg_stream(tp + i0), tmm = ldg_stream(tp + i0 + QBLK);
+            const bool row2 = k + 2 < nblk;
+            float4 x2a = row2 ? ldg_stream(xp + 2 * (int64_t)QROW + i0) : zero4, x2m = row2 ? ldg_stream(xp + 2 * (int64_t)QROW + i0 + QBLK) : zero4;
+#pragma unroll 1
+            for (int p = 0; p < d.P; ++p) {
+                // request the rows of step p + 1 (template row p + 1, spectrum row k + p + 3) ...
+                // (predicated loads, not branches: the scheduler may then hoist them above the arithmetic)
+                const bool more = p + 1 < d.P, xrow = more && k + p + 3 < nblk;
+                const float4* t = tp + (int64_t)(p + 1) * QROW + i0;
+                const float4* x = xp + (int64_t)(p + 3) * QROW + i0;
+                const float4 na = more ? ldg_stream(t) : zero4, nm = more ? ldg_stream(t + QBLK) : zero4;
+                const float4 nxa = xrow ? ldg_stream(x) : zero4, nxm = xrow ? ldg_stream(x + QBLK) : zero4;
+                // ... then multiply step p: block k + j needs spectrum row k + j + p
+                a0.mac(ta, tmm, x0a, x0m);
+                a1.mac(ta, tmm, x1a, x1m);
+                a2.mac(ta, tmm, x2a, x2m);
+                x0a = x1a; x0m = x1m; x1a = x2a; x1m = x2m; x2a = nxa; x2m = nxm;
+                ta = na; tmm = nm;
+            }
+            const float c = wbase.x * kC64[uu & 7] - wbase.y * kS64[uu & 7];
+            const float s = wbase.x * kS64[uu & 7] + wbase.y * kC64[uu & 7];
+            C2 lo, hi;
+            pack_quad(a0.aR, a0.aI, a0.mR, a0.mI, c, s, lo, hi);
+            buf.st(col + 544 * uu, lo);                           // C[i]
+            if (tid != 0) buf.st(mcol + 544 * (15 - uu), hi);     // C[B/2 - i]
+            else if (uu != 0) buf.st(mcol + 544 * (16 - uu), hi);
+            pack_quad(a1.aR, a1.aI, a1.mR, a1.mI, c, s, lo, hi);
+            tmem_st8(tcol + (uint32_t)(uu * 8), lo.r.x, lo.r.y, lo.i.x, lo.i.y, hi.r.x, hi.r.y, hi.i.x, hi.i.y);
+            pack_quad(a2.aR, a2.aI, a2.mR, a2.mI, c, s, lo, hi);
+            tmem_st8(tcol + 256u + (uint32_t)(uu * 8), lo.r.x, lo.r.y, lo.i.x, lo.i.y, hi.r.x, hi.r.y, hi.i.x, hi.i.y);
+        }
+        if (warp == NW - 1) {                         // the self-mirrored quad i = B/4 of the three items
+            int P0 = d.P; if (k + P0 > nblk) P0 = (int)(nblk - k);
+            const C2 lo = special_quad(tp, xp, P0, lane);
+            if (lane == 0) buf.st(phys(Q4), lo);
+            if (nb > 1) {
+                int P1 = d.P; if (k + 1 + P1 > nblk) P1 = (int)(nblk - k - 1);
+                sp1 = special_quad(tp, xp + QROW, P1, lane);
+            }
+            if (nb > 2) {
+                int P2 = d.P; if (k + 2 + P2 > nblk) P2 = (int)(nblk - k - 2);
+                sp2 = special_quad(tp, xp + 2 * (int64_t)QROW, P2, lane);
+            }
+        }
+        tmem_wait_st();
+    }
+    csync<0>();
+
+    // ---------------- first item: inverse FFT + epilogue ---------------------------------------
+    fft_passes<0>(buf, tid, tab, is_u8);
+    finish_item<S, 0, EPI>(it0, tid, sm, s_bar, 0u, s_best, s_min, img, img_n, ipfx, tpfx, tab, keys, curve_out,
+                           [&] { if (is_u8 && nb > 1) stage_inputs(it1, tid, reinterpret_cast<const uint8_t*>(img), img_n, ipfx, sm, s_bar); });
+
+    // ---------------- second and third item: out of tensor memory, then the same ------------------
+#pragma unroll 1
+    for (int j = 1; j < nb; ++j) {                    // uniform over the CTA
+        const uint32_t tsrc = tcol + (j == 2 ? 256u : 0u);
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+            float v[16];
+            tmem_ld16(tsrc + (uint32_t)(c4 * 16), v);
+            tmem_wait_ld();
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int uu = 2 * c4 + h;
+                const C2 lo = {make_float2(v[8 * h + 0], v[8 * h + 1]), make_float2(v[8 * h + 2], v[8 * h + 3])};
+                const C2 hi = {make_float2(v[8 * h + 4], v[8 * h + 5]), make_float2(v[8 * h + 6], v[8 * h + 7])};
+                buf.st(col + 544 * uu, lo);
+                if (tid != 0) buf.st(mcol + 544 * (15 - uu), hi);
+                else if (uu != 0) buf.st(mcol + 544 * (16 - uu), hi);
+            }
+        }
+        if (tid == (NW - 1) * 32) buf.st(phys(Q4), j == 1 ? sp1 : sp2);
+        csync<0>();
+        fft_passes<0>(buf, tid, tab, is_u8);
+        if (j == 1)
+            finish_item<S, 0, EPI>(it1, tid, sm, s_bar, 1u, s_best, s_min, img, img_n, ipfx, tpfx, tab, keys, curve_out,
+                                   [&] { if (is_u8 && nb > 2) stage_inputs(it2, tid, reinterpret_cast<const uint8_t*>(img), img_n, ipfx, sm, s_bar); });
+        else
+            finish_item<S, 0, EPI>(it2, tid, sm, s_bar, 0u, s_best, s_min, img, img_n, ipfx, tpfx, tab, keys, curve_out, [] {});
+    }
+    tmem_fence_before();
+    csync<0>();
+    if (warp == 0) tmem_dealloc(*s_taddr, 512);
+}
+
 // pair_query[i] = query of pair (pair_first + i): one CTA per query fills its own range
-__global__ void k_fill_pair_query(const QueryDesc* __restrict__ desc, int q_begin, int64_t pair_first, int* __restrict__ pair_query) {
+__global__ void k_fill_pair_query(const QueryDesc* __restrict__ desc, int q_begin, int64_t pair_first, int* __restrict__ pair_query, int group) {
     const int q = q_begin + blockIdx.x;
     const int64_t base = desc[q].groupBase - pair_first;
-    const int np = (desc[q].nk + 1) / 2;
+    const int np = (desc[q].nk + group - 1) / group;           // pairs (group = 2) or triples (3) of lag blocks
     for (int i = threadIdx.x; i < np; i += blockDim.x) pair_query[base + i] = q;
 }
 
@@ -1228,6 +1376,25 @@ int launch_pair_typed(const sb_stream* image, const sb_stream* tmpl, const float
     return SB_OK;
 }
 
+template <typename S, int EPI>
+int launch_triple_typed(const sb_stream* image, const sb_stream* tmpl, const float2* d_parts, int64_t part_first,
+                        const QueryDesc* d_desc, int64_t trip_first, int64_t n_trips, const PackedTables& tab,
+                        unsigned long long* d_keys, float* d_curve) {
+    Ctx& c = ctx();
+    static bool attr_set = false;
+    const size_t smem = packed_smem_bytes() + 16;
+    if (!attr_set) {
+        SB_CUDA(cudaFuncSetAttribute(k_match_triple<S, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    k_match_triple<S, EPI><<<(unsigned)n_trips, QT, smem, c.stream>>>(
+        reinterpret_cast<const float4*>(d_parts), part_first, reinterpret_cast<const float4*>(image->d_specq), image->nblkq,
+        static_cast<const S*>(image->d_raw), image->n, image->d_pfx, tmpl->d_pfx, d_desc, g_item_query2, trip_first,
+        tab, d_keys, d_curve);
+    SB_CUDA(cudaGetLastError());
+    return SB_OK;
+}
+
 template <typename S>
 int launch_ws_typed(const sb_stream* image, const sb_stream* tmpl, const float2* d_parts, int64_t part_first,
                     const QueryDesc* d_desc, int64_t item_first, int64_t n_items, const PackedTables& tab,
@@ -1291,13 +1458,29 @@ int launch_match_pair(const sb_stream* image, const sb_stream* tmpl, const float
     PackedTables tab;
     SB_TRY(ensure_packed_tables(&tab));
     SB_TRY(ensure_item_query(n_pairs));
-    k_fill_pair_query<<<(unsigned)(q_end - q_begin), 128, 0, c.stream>>>(d_desc, q_begin, pair_first, g_item_query2);
+    k_fill_pair_query<<<(unsigned)(q_end - q_begin), 128, 0, c.stream>>>(d_desc, q_begin, pair_first, g_item_query2, 2);
     c.launches += 1;
     if (image->dtype != SB_U8)
         return launch_pair_typed<float, 1>(image, tmpl, d_parts, part_first, d_desc, pair_first, n_pairs, tab, d_keys, d_curve);
     return c.epilogue == 2
         ? launch_pair_typed<uint8_t, 2>(image, tmpl, d_parts, part_first, d_desc, pair_first, n_pairs, tab, d_keys, d_curve)
         : launch_pair_typed<uint8_t, 1>(image, tmpl, d_parts, part_first, d_desc, pair_first, n_pairs, tab, d_keys, d_curve);
+}
+
+int launch_match_triple(const sb_stream* image, const sb_stream* tmpl, const float2* d_parts, int64_t part_first,
+                        const QueryDesc* d_desc, int q_begin, int q_end, int64_t trip_first, int64_t n_trips,
+                        unsigned long long* d_keys, float* d_curve) {
+    Ctx& c = ctx();
+    PackedTables tab;
+    SB_TRY(ensure_packed_tables(&tab));
+    SB_TRY(ensure_item_query(n_trips));
+    k_fill_pair_query<<<(unsigned)(q_end - q_begin), 128, 0, c.stream>>>(d_desc, q_begin, trip_first, g_item_query2, 3);
+    c.launches += 1;
+    if (image->dtype != SB_U8)
+        return launch_triple_typed<float, 1>(image, tmpl, d_parts, part_first, d_desc, trip_first, n_trips, tab, d_keys, d_curve);
+    return c.epilogue == 2
+        ? launch_triple_typed<uint8_t, 2>(image, tmpl, d_parts, part_first, d_desc, trip_first, n_trips, tab, d_keys, d_curve)
+        : launch_triple_typed<uint8_t, 1>(image, tmpl, d_parts, part_first, d_desc, trip_first, n_trips, tab, d_keys, d_curve);
 }
 
 int launch_block_spectra_quad(const sb_stream* s, int64_t k_first, int64_t rows, float2* out) {

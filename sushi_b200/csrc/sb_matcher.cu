@@ -374,7 +374,7 @@ constexpr int64_t kBlockedFromPartitions = 12;
 // path.  QueryDesc::orig maps back to the caller's order; curve offsets follow the caller's order.
 int plan_batch(const sb_stream* image, const sb_stream* tmpl, int64_t count,
                const int64_t* toff, const int64_t* tlen, const int64_t* lag0, const int64_t* nlags,
-               int hd, bool allow_blocked, int64_t* n_direct_out,
+               int hd, bool allow_blocked, int direct_group, int64_t* n_direct_out,
                int64_t* total_items, int64_t* total_parts, int64_t* total_groups, int64_t* max_query_parts) {
     Ctx& c = ctx();
     const int B = c.B;
@@ -412,7 +412,7 @@ int plan_batch(const sb_stream* image, const sb_stream* tmpl, int64_t count,
                 d.k0 = (int32_t)(s / LB);
                 d.nk = (int32_t)((s + L - 1) / LB - d.k0 + 1);
                 d.itemBase = items; d.partBase = parts; d.orig = (int32_t)q; d.curveOff = curve_total; d.groupBase = groups;
-                groups += cls == 0 ? (d.nk + 1) / 2 : (d.nk + MAC_GROUP - 1) / MAC_GROUP;
+                groups += cls == 0 ? (d.nk + direct_group - 1) / direct_group : (d.nk + MAC_GROUP - 1) / MAC_GROUP;
                 items += d.nk; parts += d.P;
                 maxp = std::max<int64_t>(maxp, d.P);
             }
@@ -457,7 +457,8 @@ int run_batch(const sb_stream* image_c, const sb_stream* tmpl, int64_t count,
     const bool use_packed = c.engine >= 2 && packed_supports(B) && hd == 1;
     const int nb = B + 1;                                    // float2 per classic spectrum row
     int64_t n_direct = 0, total_items = 0, total_parts = 0, total_groups = 0, maxp = 0;
-    SB_TRY(plan_batch(image, tmpl, count, toff, tlen, lag0, nlags, hd, use_fused && hd == 1, &n_direct,
+    const bool use_triples = use_packed && c.engine == 6;     // lag blocks per CTA of the direct class: 3, else 2 or 1
+    SB_TRY(plan_batch(image, tmpl, count, toff, tlen, lag0, nlags, hd, use_fused && hd == 1, use_triples ? 3 : 2, &n_direct,
                       &total_items, &total_parts, &total_groups, &maxp));
     // Packed kernels: one CTA per lag block, or one per pair of consecutive lag blocks of a query (shared template
     // rows, 2P+1 row reads instead of 4P, second product spectrum parked in tensor memory).  Both give bit-identical
@@ -532,7 +533,11 @@ int run_batch(const sb_stream* image_c, const sb_stream* tmpl, int64_t count,
         const int64_t item_hi = (qe < count) ? c.h_desc[qe].itemBase : total_items;
         if (use_packed && !premac) {
             ProfScope ps("match_fused");
-            if (use_pairs) {
+            if (use_triples) {
+                const int64_t g0 = c.h_desc[qb].groupBase;
+                const int64_t g1 = (qe < count) ? c.h_desc[qe].groupBase : total_groups;
+                SB_TRY(launch_match_triple(image, tmpl, c.d_parts, part_first, c.d_desc, (int)qb, (int)qe, g0, g1 - g0, c.d_keys, d_curve));
+            } else if (use_pairs) {
                 const int64_t g0 = c.h_desc[qb].groupBase;
                 const int64_t g1 = (qe < count) ? c.h_desc[qe].groupBase : total_groups;
                 SB_TRY(launch_match_pair(image, tmpl, c.d_parts, part_first, c.d_desc, (int)qb, (int)qe, g0, g1 - g0, c.d_keys, d_curve));

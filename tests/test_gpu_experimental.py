@@ -6,7 +6,10 @@ round-end `pytest -m gpu` run judges the default path alone:
 
 sb_set_epilogue(2): trimmed screening loop of the packed kernels on uint8 streams.  Screening only selects
 the lags that get the exact fp64 evaluation, so every result must equal the first version's BIT FOR BIT --
-whole curves included (the debug curve path evaluates every lag exactly under both variants)."""
+whole curves included (the debug curve path evaluates every lag exactly under both variants).
+
+sb_set_engine(6): one CTA per triple of consecutive lag blocks (two product spectra parked in tensor memory).
+Same arithmetic in the same order as engines 4 / 5, so again bit for bit."""
 import os
 
 import numpy as np
@@ -100,3 +103,30 @@ def test_trimmed_epilogue_degenerate_inputs(gpu_lib, epilogue, golden_matcher):
                             gapped.find_planned(gapped, [12000, 100, 33000], [6000, 5000, 5000], [0, 8000, 0], [34001, 20000, 35001]))
         assert np.array_equal(res[1][0], res[2][0])
         assert np.array_equal(res[1][1][0], res[2][1][0]) and np.array_equal(res[1][1][1], res[2][1][1])
+
+
+@pytest.mark.parametrize('stype', ['uint8', 'float32'])
+@pytest.mark.parametrize('variant', [1, 2])
+def test_triples_are_bit_identical_to_single_lag_blocks(gpu_lib, epilogue, stype, variant):
+    """Engine 6 against engine 5 on whole curves and batch results: ranges of 1 .. 7 lag blocks (the last triple
+    of a query holds one, two or three), ranges that start / end inside a block, templates of 1 .. 5 partitions,
+    and searches that run into the end of the stream (spectrum rows past the last block are zero)."""
+    rs, rd, src, dst = _streams(60.0, 7, stype)
+    n_img = dst.data.shape[1]
+    cases = [(6000, 11400, 0, 16384), (6000, 11400, 5, 16384), (6000, 20000, 100, 2 * 16384), (100, 48000, 16384, 3 * 16384),
+             (100, 70000, 3, 4 * 16384 + 17), (40000, 3000, 16383, 5 * 16384 + 2), (7, 700, 1, 7 * 16384),
+             (30000, 36000, n_img - 36000 - 90000, 90001), (5000, 12000, n_img - 12000 - 40000, 40001)]
+    for toff, n, lag0, nlags in cases:
+        got = {}
+        for engine in (5, 6):
+            epilogue(variant, engine)
+            got[engine] = (dst.match_curve(src, toff, n, lag0, nlags), dst.find_planned(src, [toff], [n], [lag0], [nlags]))
+        assert np.array_equal(got[5][0], got[6][0]), (toff, n, lag0, nlags)
+        assert got[5][1][0][0] == got[6][1][0][0] and got[5][1][1][0] == got[6][1][1][0]
+    starts, ends = synth.make_events(120, 60.0, 8, 0.5, 5.0)
+    win = np.full(len(starts), 20.0)
+    res = {}
+    for engine in (5, 6):
+        epilogue(variant, engine)
+        res[engine] = dst.find_substream_batch(src, starts, ends, starts, win)
+    assert np.array_equal(res[5][0], res[6][0]) and np.array_equal(res[5][1], res[6][1])
