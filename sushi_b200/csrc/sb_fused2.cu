@@ -163,10 +163,6 @@ __device__ __forceinline__ void pack_quad(float2 aR, float2 aI, float2 mR, float
 }
 
 // ---------------------------------------------------------------- pieces shared by the two kernels
-// Both kernels run the FFT and the epilogue on exactly 512 threads; ID names their barrier (0 = the whole CTA
-// of k_match_packed, 1 = the consumer warps of k_match_ws).
-template <int ID> __device__ __forceinline__ void csync() { asm volatile("bar.sync %0, 512;" :: "n"(ID) : "memory"); }
-
 constexpr int kRounds = QB / (QT * 8);            // epilogue rounds: 8 consecutive lags per thread per round
 constexpr int kLagsPerRound = QT * 8;
 
@@ -478,7 +474,7 @@ __device__ __forceinline__ void finish_item(const Item& it, int tid, const Smem&
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) tmin = fminf(tmin, __shfl_xor_sync(0xffffffffu, tmin, o));
     if (lane == 0) s_min[warp] = tmin;
-    if (is_u8) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // window reads before the next item's TMA refill
+    if (is_u8) fence_proxy_async();   // window reads before the next item's TMA refill
     csync<ID>();
     after_read();
     float bmin = s_min[0];
@@ -655,44 +651,6 @@ __device__ constexpr float kS256[32] = {
     0.59569930449243336f, 0.61523159058062682f, 0.63439328416364549f, 0.65317284295377676f, 0.67155895484701833f,
     0.68954054473706683f};
 
-// Wait with back-off: a hot try_wait loop on 16 warps starves the warps that produce what they wait for.
-__device__ __forceinline__ void mbar_wait_sleep(unsigned long long* bar, unsigned parity, unsigned ns) {
-    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
-    for (;;) {
-        unsigned done;
-        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
-                     : "=r"(done) : "r"(b), "r"(parity) : "memory");
-        if (done) break;
-        __nanosleep(ns);
-    }
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
-    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(b) : "memory");
-}
-__device__ __forceinline__ void tmem_alloc(uint32_t* smem_slot, uint32_t ncols) {
-    const unsigned a = (unsigned)__cvta_generic_to_shared(smem_slot);
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(a), "r"(ncols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void tmem_st8(uint32_t taddr, float v0, float v1, float v2, float v3, float v4, float v5, float v6, float v7) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
-                 :: "r"(taddr), "f"(v0), "f"(v1), "f"(v2), "f"(v3), "f"(v4), "f"(v5), "f"(v6), "f"(v7) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]),
-                   "=f"(v[8]), "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15]) : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tmem_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
 template <typename S>
 __global__ void __launch_bounds__(WS_THREADS, 1)
 k_match_ws(const float4* __restrict__ That, int64_t part_first,
@@ -729,7 +687,7 @@ k_match_ws(const float4* __restrict__ That, int64_t part_first,
 
     // 768 threads start with 80 registers each; the CTA pool is fixed at launch: the multiply warps hand 16 each to the transform warps (88 / 64)
     if (warp < NW) {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
+        setmaxnreg_inc<88>();
         // ======================= transform warps =======================
         const Buf& buf = sm.buf;
         const int Lc = tid & 127, g = tid >> 7;
@@ -786,7 +744,7 @@ k_match_ws(const float4* __restrict__ That, int64_t part_first,
                               });
         }
     } else {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+        setmaxnreg_dec<64>();
         // ======================= multiply warps =======================
         // Step = (item, block of 256 quads, partition); its stage holds that block of the T^ row and of the X^
         // row (two 8 KB bulk copies).  Thread (quarter q, lane l, half h) owns TMEM lane L = 32q + l and quad
@@ -1257,34 +1215,49 @@ size_t packed_smem_bytes() {
     return kSmemCommon + 8 + QNW * sizeof(unsigned long long) + QNW * sizeof(float) + 64;
 }
 
+// Values of the four tables of PackedTables, in one array: offsets of tw2, tw3, w8, wb in `off` (floats)
+std::vector<float> packed_table_values(size_t (&off)[4]) {
+    const double pi = 3.14159265358979323846;
+    const size_t n2 = 8 * 16 * 4, n3 = 8 * 256 * 4, n8 = 4096 * 2, nb = 512 * 2;
+    off[0] = 0; off[1] = n2; off[2] = n2 + n3; off[3] = n2 + n3 + n8;
+    std::vector<float> h(n2 + n3 + n8 + nb);
+    for (int a = 0; a < 8; ++a)
+        for (int k = 0; k < 16; ++k)
+            for (int e = 0; e < 2; ++e) {
+                const double ang = 2.0 * pi * (2 * a + e) * k / 256.0;
+                h[((size_t)a * 16 + k) * 4 + 2 * e] = (float)cos(ang); h[((size_t)a * 16 + k) * 4 + 2 * e + 1] = (float)sin(ang);
+            }
+    for (int a = 0; a < 8; ++a)
+        for (int k = 0; k < 256; ++k)
+            for (int e = 0; e < 2; ++e) {
+                const double ang = 2.0 * pi * (2 * a + e) * k / 4096.0;
+                h[n2 + ((size_t)a * 256 + k) * 4 + 2 * e] = (float)cos(ang); h[n2 + ((size_t)a * 256 + k) * 4 + 2 * e + 1] = (float)sin(ang);
+            }
+    for (int j = 0; j < 4096; ++j) { h[n2 + n3 + 2 * j] = (float)cos(2.0 * pi * j / 8192.0); h[n2 + n3 + 2 * j + 1] = (float)sin(2.0 * pi * j / 8192.0); }
+    for (int t = 0; t < 512; ++t) { h[n2 + n3 + n8 + 2 * t] = (float)cos(pi * t / QB); h[n2 + n3 + n8 + 2 * t + 1] = (float)sin(pi * t / QB); }
+    return h;
+}
+
+PackedTables packed_tables_at(const float* base, const size_t (&off)[4]) {
+    PackedTables t;
+    t.tw2 = reinterpret_cast<const float4*>(base + off[0]);
+    t.tw3 = reinterpret_cast<const float4*>(base + off[1]);
+    t.w8 = reinterpret_cast<const float2*>(base + off[2]);
+    t.wb = reinterpret_cast<const float2*>(base + off[3]);
+    return t;
+}
+
+#ifndef SB_EMULATE      // ---- everything below launches kernels or calls the CUDA runtime (not part of tests/emu)
 float* g_ptab_dev = nullptr;
 PackedTables g_ptab;
 
 int ensure_packed_tables(PackedTables* out) {
     if (!g_ptab_dev) {
-        const double pi = 3.14159265358979323846;
-        const size_t n2 = 8 * 16 * 4, n3 = 8 * 256 * 4, n8 = 4096 * 2, nb = 512 * 2;
-        std::vector<float> h(n2 + n3 + n8 + nb);
-        for (int a = 0; a < 8; ++a)
-            for (int k = 0; k < 16; ++k)
-                for (int e = 0; e < 2; ++e) {
-                    const double ang = 2.0 * pi * (2 * a + e) * k / 256.0;
-                    h[((size_t)a * 16 + k) * 4 + 2 * e] = (float)cos(ang); h[((size_t)a * 16 + k) * 4 + 2 * e + 1] = (float)sin(ang);
-                }
-        for (int a = 0; a < 8; ++a)
-            for (int k = 0; k < 256; ++k)
-                for (int e = 0; e < 2; ++e) {
-                    const double ang = 2.0 * pi * (2 * a + e) * k / 4096.0;
-                    h[n2 + ((size_t)a * 256 + k) * 4 + 2 * e] = (float)cos(ang); h[n2 + ((size_t)a * 256 + k) * 4 + 2 * e + 1] = (float)sin(ang);
-                }
-        for (int j = 0; j < 4096; ++j) { h[n2 + n3 + 2 * j] = (float)cos(2.0 * pi * j / 8192.0); h[n2 + n3 + 2 * j + 1] = (float)sin(2.0 * pi * j / 8192.0); }
-        for (int t = 0; t < 512; ++t) { h[n2 + n3 + n8 + 2 * t] = (float)cos(pi * t / QB); h[n2 + n3 + n8 + 2 * t + 1] = (float)sin(pi * t / QB); }
+        size_t off[4];
+        const std::vector<float> h = packed_table_values(off);
         SB_CUDA(cudaMalloc(&g_ptab_dev, h.size() * sizeof(float)));
         SB_CUDA(cudaMemcpy(g_ptab_dev, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
-        g_ptab.tw2 = reinterpret_cast<const float4*>(g_ptab_dev);
-        g_ptab.tw3 = reinterpret_cast<const float4*>(g_ptab_dev + n2);
-        g_ptab.w8 = reinterpret_cast<const float2*>(g_ptab_dev + n2 + n3);
-        g_ptab.wb = reinterpret_cast<const float2*>(g_ptab_dev + n2 + n3 + n8);
+        g_ptab = packed_tables_at(g_ptab_dev, off);
     }
     *out = g_ptab;
     return SB_OK;
@@ -1501,3 +1474,6 @@ void packed_release_tables() {
 }
 
 }  // namespace sb
+#else
+}  // namespace (tests/emu includes this file and adds its entry points behind it)
+#endif  // SB_EMULATE

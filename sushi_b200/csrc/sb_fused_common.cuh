@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "sb_ptx.cuh"
+
 namespace sbf {
 
 // ---------------------------------------------------------------- small complex helpers
@@ -105,50 +107,5 @@ __device__ __forceinline__ unsigned long long load8(const uint8_t* __restrict__ 
     return (w0 >> sh) | (w1 << (64u - sh));
 }
 
-
-// single MUFU.RSQ (the operands here are ~1e18, never subnormal)
-__device__ __forceinline__ float rsqrt_fast(float x) {
-    float y;
-    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-
-// 16-byte asynchronous global->shared copy (LDGSTS); both addresses 16-byte aligned
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
-    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(s), "l"(gmem_src));
-}
-__device__ __forceinline__ void cp_async_commit_wait_all() {
-    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
-}
-
-// ---- TMA (bulk async copy engine), 1-D form: cp.async.bulk global -> shared with mbarrier completion
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
-    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(b), "r"(count));
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // make the init visible to the async proxy
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
-    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(b), "r"(bytes) : "memory");
-}
-// dst/src 16-byte aligned, bytes a multiple of 16
-__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst), b = (unsigned)__cvta_generic_to_shared(bar);
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 :: "r"(d), "l"(gmem_src), "r"(bytes), "r"(b) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" :: "r"(b), "r"(parity) : "memory");
-}
 
 }  // namespace sbf
