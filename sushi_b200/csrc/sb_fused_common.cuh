@@ -4,7 +4,11 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#ifdef SB_EMULATE
+#include "emu_ptx.h"      // tests/emu: host stand-ins for the inline PTX (test infrastructure)
+#else
 #include "sb_ptx.cuh"
+#endif
 
 namespace sbf {
 

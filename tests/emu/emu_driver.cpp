@@ -1,0 +1,69 @@
+// TEST INFRASTRUCTURE ONLY (see emu_cuda.h).  Compiles the match kernels of sushi_b200/csrc/sb_fused2.cu for the
+// host and runs CTAs of them, one OS thread per CUDA thread:
+//     g++ -std=c++20 -O1 -pthread -DSB_EMULATE -I tests/emu -I sushi_b200/csrc -I include -I /usr/local/cuda/include
+//         -shared -fPIC tests/emu/emu_driver.cpp -o tests/emu/_build/libsb_emu.so
+#include "emu_cuda.h"
+#include "../../sushi_b200/csrc/sb_fused2.cu"
+
+namespace {
+alignas(128) unsigned char smem_raw[232 * 1024];      // the kernels' `extern __shared__` array
+}
+
+extern "C" {
+
+int emu_table_floats(void) { size_t off[4]; return (int)packed_table_values(off).size(); }
+int emu_smem_bytes(void) { return (int)packed_smem_bytes() + 16; }
+int emu_query_desc_bytes(void) { return (int)sizeof(sb::QueryDesc); }
+int emu_quad_row_floats(void) { return QROW * 4; }
+
+// kernel: 0 = k_match_packed (one CTA per lag block), 1 = k_match_pair, 2 = k_match_triple; epi: 1 | 2;
+// is_u8: sample type of img.  Runs CTAs [0, n_ctas) one after the other.  Returns 0, or the number of
+// emulation errors (messages on stderr).
+int emu_run(int kernel, int epi, int is_u8, const float* That, int64_t part_first, const float* Xhat, int64_t nblk,
+            const void* img, int64_t img_n, const double* ipfx, const double* tpfx, const void* desc,
+            const int* cta_query, int64_t first, int n_ctas, unsigned long long* keys, float* curve_out) {
+    static size_t off[4];
+    static const std::vector<float> tables = packed_table_values(off);
+    const PackedTables tab = packed_tables_at(tables.data(), off);
+    const float4* T4 = reinterpret_cast<const float4*>(That);
+    const float4* X4 = reinterpret_cast<const float4*>(Xhat);
+    const double2* ip = reinterpret_cast<const double2*>(ipfx);
+    const double2* tp = reinterpret_cast<const double2*>(tpfx);
+    const sb::QueryDesc* d = static_cast<const sb::QueryDesc*>(desc);
+    int n_err = 0;
+    for (int b = 0; b < n_ctas; ++b) {
+        emu::Cta cta;
+        emu::cta() = &cta;
+        std::memset(smem_raw, 0xCD, sizeof(smem_raw));                      // uninitialised reads show up as garbage
+        for (auto& v : cta.tmem) v = std::nanf("");
+        auto body = [&](int t) {
+            threadIdx = {(unsigned)t, 0, 0};
+            blockIdx = {(unsigned)b, 0, 0};
+            emu::t_lane = t & 31; emu::t_warp = t >> 5;
+#define SB_EMU_CALL(K, S, E) K<S, E>(T4, part_first, X4, nblk, static_cast<const S*>(img), img_n, ip, tp, d, cta_query, first, tab, keys, curve_out)
+#define SB_EMU_KERNEL(K) do { if (!is_u8) SB_EMU_CALL(K, float, 1); else if (epi == 2) SB_EMU_CALL(K, uint8_t, 2); else SB_EMU_CALL(K, uint8_t, 1); } while (0)
+            if (kernel == 0) SB_EMU_KERNEL(k_match_packed);
+            else if (kernel == 1) SB_EMU_KERNEL(k_match_pair);
+            else SB_EMU_KERNEL(k_match_triple);
+        };
+        std::vector<std::thread> th;
+        th.reserve(emu::kThreads);
+        for (int t = 0; t < emu::kThreads; ++t) th.emplace_back(body, t);
+        for (auto& x : th) x.join();
+        for (const auto& e : cta.errors) { std::fprintf(stderr, "[emu] CTA %d: %s\n", b, e.c_str()); ++n_err; }
+        emu::cta() = nullptr;
+    }
+    return n_err;
+}
+
+}  // extern "C"
+
+#ifdef SB_EMU_DEBUG      // g++ ... -DSB_EMU_DEBUG -g -rdynamic: backtrace of the faulting thread on SIGSEGV
+#include <execinfo.h>
+#include <signal.h>
+#include <unistd.h>
+namespace {
+void on_segv(int) { void* bt[48]; const int n = backtrace(bt, 48); backtrace_symbols_fd(bt, n, 2); _exit(139); }
+struct InstallSegv { InstallSegv() { signal(SIGSEGV, on_segv); } } install_segv;
+}
+#endif

@@ -1,0 +1,229 @@
+"""The LOGIC of the packed match kernels (sushi_b200/csrc/sb_fused2.cu) on the CPU.
+
+tests/emu/ compiles the kernels' own source for the host (g++, -DSB_EMULATE: host stand-ins for the built-in
+variables, the intrinsics and the inline-PTX wrappers of sb_ptx.cuh) and runs CTAs with one OS thread per CUDA
+thread.  This is test infrastructure like oracle/: it is never loaded by the product path, and it proves nothing
+about races, fences, alignment rules of the copy engine or speed -- tests/test_gpu_*.py do that on a B200.  What it
+does pin, without a GPU: the index algebra (quad rows -> packing -> FFT passes -> epilogue), the bookkeeping of the
+pair / triple kernels (mbarrier phases, which thread parks what in which tensor-memory columns, the last group of
+a query holding fewer lag blocks, spectrum rows past the end of the stream), the candidate logic of both screening
+loops, and the first-index argmin -- against the fp64 closed form of TM_SQDIFF_NORMED and across kernels bit for
+bit.  Spectrum rows and running sums are prepared here in NumPy the way k_forward_quad / the scan kernels define
+them (layout: tests/test_packed_layout_model.py)."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle.ref_matcher import sqdiff_normed_fp64
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMU = os.path.join(ROOT, 'tests', 'emu')
+B = 16384
+Q4 = B // 4
+
+
+class QueryDesc(ctypes.Structure):            # sb_internal.h
+    _fields_ = [(n, ctypes.c_int64) for n in ('toff', 'tlen', 'lag0', 'nlags', 'itemBase', 'partBase', 'curveOff', 'groupBase')] + \
+               [(n, ctypes.c_int32) for n in ('P', 'k0', 'nk', 'orig')]
+
+
+@pytest.fixture(scope='module')
+def emu():
+    src = [os.path.join(EMU, f) for f in ('emu_driver.cpp', 'emu_cuda.h', 'emu_ptx.h')] + \
+          [os.path.join(ROOT, 'sushi_b200', 'csrc', f) for f in ('sb_fused2.cu', 'sb_fused_common.cuh', 'sb_fft_smem.cuh', 'sb_internal.h')]
+    out = os.path.join(EMU, '_build', 'libsb_emu.so')
+    if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(f) for f in src):
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        cuda_inc = os.path.join(os.environ.get('CUDA_HOME', '/usr/local/cuda'), 'include')
+        subprocess.check_call(['g++', '-std=c++20', '-O1', '-pthread', '-DSB_EMULATE', '-I', EMU,
+                               '-I', os.path.join(ROOT, 'sushi_b200', 'csrc'), '-I', os.path.join(ROOT, 'include'), '-I', cuda_inc,
+                               '-shared', '-fPIC', src[0], '-o', out])
+    lib = ctypes.CDLL(out)
+    assert lib.emu_query_desc_bytes() == ctypes.sizeof(QueryDesc)
+    return lib
+
+
+def aligned(n, dtype, fill=0):
+    """1-D array of n elements whose data pointer is a multiple of 128 (the copy engine wants 16)."""
+    item = np.dtype(dtype).itemsize
+    raw = np.zeros(n * item + 256, np.uint8)
+    off = (-raw.ctypes.data) % 128
+    a = raw[off:off + n * item].view(dtype)
+    a[:] = fill
+    return a
+
+
+def qa(i):
+    return (i >> 8) * 512 + (i & 255) if i < Q4 else 2 * Q4
+
+
+def quad_rows(blocks, row_floats):
+    """blocks: (rows, 2B) real -> rows in the quad layout of sb_fused2.cu (float32)."""
+    X = np.fft.rfft(blocks.astype(np.float64), axis=1)          # bins 0 .. B
+    out = aligned(blocks.shape[0] * row_floats, np.float32).reshape(blocks.shape[0], row_floats // 4, 4)
+    i = np.arange(Q4 + 1)
+    pa = np.array([qa(int(v)) for v in i])
+    pm = np.where(i < Q4, pa + 256, 2 * Q4 + 1)
+    out[:, pa, 0], out[:, pa, 1], out[:, pa, 2], out[:, pa, 3] = X[:, i].real, X[:, i + B // 2].real, X[:, i].imag, X[:, i + B // 2].imag
+    out[:, pm, 0], out[:, pm, 1], out[:, pm, 2], out[:, pm, 3] = X[:, B - i].real, X[:, B // 2 - i].real, X[:, B - i].imag, X[:, B // 2 - i].imag
+    return out.reshape(blocks.shape[0], row_floats)
+
+
+def prefix_sums(x):
+    p = aligned(2 * (x.size + 1), np.float64).reshape(x.size + 1, 2)
+    xf = x.astype(np.float64)
+    p[1:, 0], p[1:, 1] = np.cumsum(xf), np.cumsum(xf * xf)
+    return p
+
+
+class Case(object):
+    """One image stream, one template stream, a list of queries (toff, n, lag0, nlags)."""
+
+    def __init__(self, lib, img, src, queries, dtype):
+        self.lib, self.queries, self.dtype = lib, queries, dtype
+        rf = lib.emu_quad_row_floats()
+        n_img = img.size
+        self.img = aligned(n_img + 64, dtype)
+        self.img[:n_img] = img
+        self.n_img = n_img
+        self.ipfx, self.tpfx = prefix_sums(img), prefix_sums(src)
+        centre = (lambda s, c: np.rint(s / c)) if dtype == np.uint8 else (lambda s, c: np.float64(np.float32(s / c)))
+        a = centre(self.ipfx[n_img, 0], n_img)
+        self.nblk = (n_img + B - 1) // B
+        blocks = np.zeros((self.nblk, 2 * B))
+        for k in range(self.nblk):
+            seg = img[k * B:k * B + 2 * B].astype(np.float64)
+            blocks[k, :seg.size] = seg - a
+        self.Xhat = quad_rows(blocks, rf)
+        parts = []
+        for (toff, n, lag0, nlags) in queries:
+            t = src[toff:toff + n].astype(np.float64)
+            b = centre(t.sum(), n)
+            for p in range((n + B - 1) // B):
+                row = np.zeros(2 * B)
+                seg = t[p * B:(p + 1) * B]
+                row[:seg.size] = seg - b
+                parts.append(row)
+        self.That = quad_rows(np.array(parts), rf)
+        self.src = src
+
+    def run(self, kernel, epi, curves):
+        group = {0: 1, 1: 2, 2: 3}[kernel]
+        desc = (QueryDesc * len(self.queries))()
+        items = parts = groups = curve = 0
+        cta_query = []
+        for q, (toff, n, lag0, nlags) in enumerate(self.queries):
+            d = desc[q]
+            d.toff, d.tlen, d.lag0, d.nlags = toff, n, lag0, nlags
+            d.P, d.k0 = (n + B - 1) // B, lag0 // B
+            d.nk = (lag0 + nlags - 1) // B - d.k0 + 1
+            d.itemBase, d.partBase, d.curveOff, d.groupBase, d.orig = items, parts, curve, groups, q
+            ng = (d.nk + group - 1) // group
+            cta_query += [q] * ng
+            items += d.nk
+            parts += d.P
+            groups += ng
+            curve += nlags
+        cta_query = np.array(cta_query, np.int32)
+        keys = np.full(len(self.queries), 0xffffffffffffffff, np.uint64)
+        cur = np.full(curve, np.nan, np.float32) if curves else None
+        vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+        rc = self.lib.emu_run(kernel, epi, int(self.dtype == np.uint8), vp(self.That), ctypes.c_int64(0), vp(self.Xhat), ctypes.c_int64(self.nblk),
+                              vp(self.img), ctypes.c_int64(self.n_img), vp(self.ipfx), vp(self.tpfx), ctypes.byref(desc), vp(cta_query),
+                              ctypes.c_int64(0), len(cta_query), vp(keys), vp(cur) if curves else None)
+        assert rc == 0, 'emulation reported %d errors (see stderr)' % rc
+        diff = (keys >> np.uint64(32)).astype(np.uint32).view(np.float32)
+        idx = (keys & np.uint64(0xffffffff)).astype(np.int64)
+        return diff, idx, cur
+
+    def truth(self):
+        out = []
+        for (toff, n, lag0, nlags) in self.queries:
+            out.append(sqdiff_normed_fp64(self.img[lag0:lag0 + nlags + n - 1], self.src[toff:toff + n]))
+        return out
+
+
+def programme(n, seed):
+    rng = np.random.default_rng(seed)
+    x = np.convolve(rng.standard_normal(n + 8), np.hanning(9), 'valid') * np.repeat(rng.uniform(0.2, 1.0, n // 2400 + 1), 2400)[:n]
+    return np.clip(np.rint(128 + 70 * x), 0, 255).astype(np.uint8)
+
+
+@pytest.fixture(scope='module')
+def case_u8(emu):
+    n_img = 6 * B - 5000                                     # 6 block rows, the last one short
+    img = programme(n_img, 1)
+    rng = np.random.default_rng(2)
+    src = np.clip(np.roll(img, -700).astype(np.int32) + rng.integers(-5, 6, n_img), 0, 255).astype(np.uint8)   # src(t) = img(t + 700) + noise
+    queries = [(30000, 20000, B + 300, 4 * B - 17000),       # P = 2, 4 lag blocks, starts and ends inside a block; match at lag 30700
+               (1000, 5000, 100, 20000),                      # P = 1, 2 lag blocks; match at lag 1700
+               (8000, 40000, n_img - 40000 - 30000, 30001)]   # P = 3, 3 lag blocks, runs to the very end of the stream
+    return Case(emu, img, src, queries, np.uint8)
+
+
+def test_emulated_kernels_match_the_closed_form_and_each_other(case_u8):
+    c = case_u8
+    truth = c.truth()
+    ref = None
+    for kernel in (0, 1, 2):                                  # one CTA per lag block / pair / triple
+        for epi in (1, 2):
+            d_c, i_c, cur = c.run(kernel, epi, curves=True)   # every lag through the exact path
+            d_s, i_s, _ = c.run(kernel, epi, curves=False)    # screening decides which lags are evaluated
+            off = 0
+            for q, t in enumerate(truth):
+                got = cur[off:off + t.size]
+                off += t.size
+                assert not np.isnan(got).any()
+                assert np.abs(got - t).max() <= 3e-6
+                assert i_c[q] == int(got.argmin()) and d_c[q] == got.min()
+                assert abs(int(got.argmin()) - int(t.argmin())) <= 1
+            assert np.array_equal(d_s, d_c) and np.array_equal(i_s, i_c)     # screening lost nothing
+            if ref is None:
+                ref = (d_c, i_c, cur)
+            else:                                                            # same arithmetic in the same order
+                assert np.array_equal(ref[0], d_c) and np.array_equal(ref[1], i_c) and np.array_equal(ref[2], cur)
+    assert ref[1][0] == 30700 - (B + 300) and ref[1][1] == 1700 - 100
+
+
+def test_emulated_degenerate_blocks(emu):
+    """Silence inside programme material, a zero template, an exact copy: saturated blocks must evaluate every lag
+    under both screening loops and return the FIRST index of equal minima."""
+    n_img = 3 * B
+    img = programme(n_img, 5)
+    img[9000:31000] = 0
+    src = img.copy()
+    src[40000:41000] = 0
+    queries = [(12000, 6000, 0, 34001),        # template of silence (zero template): every value 1 -> index 0
+               (100, 5000, 8000, 20000),        # lags 9000..26000 see silent windows (value 1), the rest programme
+               (33000, 5000, 0, 2 * B + 1000),  # exact copy at lag 33000: value 0
+               (40000, 1000, 100, 1000)]        # zero template against programme
+    c = Case(emu, img, src, queries, np.uint8)
+    truth = c.truth()
+    ref = None
+    for kernel in (0, 2):
+        for epi in (1, 2):
+            d, i, _ = c.run(kernel, epi, curves=False)
+            for q, t in enumerate(truth):
+                assert i[q] == int(t.argmin()), (kernel, epi, q)
+                assert abs(float(d[q]) - float(t.min())) <= 3e-6
+            ref = ref or (d, i)
+            assert np.array_equal(ref[0], d) and np.array_equal(ref[1], i)
+    assert ref[0][0] == 1.0 and ref[1][0] == 0 and ref[0][2] <= 1e-6 and ref[1][2] == 33000 and ref[0][3] == 1.0 and ref[1][3] == 0
+
+
+def test_emulated_float32_stream(emu):
+    n_img = 4 * B - 3000
+    rng = np.random.default_rng(9)
+    img = (programme(n_img, 3).astype(np.float32) / 255.0).astype(np.float32)
+    src = (np.roll(img, -300) + rng.normal(0, 0.01, n_img)).astype(np.float32)
+    c = Case(emu, img, src, [(20000, 18000, 5, 2 * B + 5000)], np.float32)
+    t = c.truth()[0]
+    ref = None
+    for kernel in (0, 1, 2):
+        d, i, cur = c.run(kernel, 1, curves=True)
+        assert np.abs(cur - t).max() <= 3e-6 and i[0] == int(cur.argmin()) == 20300 - 5
+        ref = ref or (d, i, cur)
+        assert np.array_equal(ref[2], cur) and ref[0][0] == d[0]
