@@ -100,8 +100,10 @@ int sb_set_premac_mode(int mode);
 int sb_set_hop_mode(int mode);
 /* Screening loop of the packed kernels (engines 2, 4, 5) on uint8 streams: 1 (default) = the first version,
  * 2 = a trimmed one (7 instead of 13 arithmetic instructions per lag, byte extraction by PRMT, border test
- * hoisted).  Screening only selects the lags that get the exact fp64 evaluation, so results are identical
- * bit for bit; float32 streams and the other engines ignore the setting. */
+ * hoisted) whose exact evaluation takes the window sums from the staged sample windows instead of two
+ * dependent reads of the running sums in HBM.  Screening only selects the lags that get the exact fp64
+ * evaluation and the window sums are exact integers either way, so results are identical bit for bit;
+ * float32 streams and the other engines ignore the setting.  Opt-in until measured. */
 int sb_set_epilogue(int variant);
 int sb_get_epilogue(void);
 /* Lag blocks processed per multiply / inverse-FFT / normalise launch (>= 1). */

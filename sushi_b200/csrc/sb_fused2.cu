@@ -180,6 +180,7 @@ struct Smem {                                      // carve-up of the dynamic sh
         end = hi + QB + 48;
     }
 };
+constexpr int kSmallBytes = 512;                   // room behind Smem::end for the kernels' barriers, reduction scratch, TMEM address
 constexpr size_t kSmemCommon = (size_t)QPHYS * 16 + kRounds * QNW * 2 * sizeof(double2) + (QB + 16) + (QB + 48);
 
 struct Item {                                      // one (query, lag block)
@@ -314,7 +315,7 @@ __device__ __forceinline__ void fft_passes(const Buf& buf, int tid, const Packed
 // windows -- k_match_ws starts the copies of its next item there.
 template <typename S, int ID, int EPI, typename AfterRead>
 __device__ __forceinline__ void finish_item(const Item& it, int tid, const Smem& sm, unsigned long long* s_bar, unsigned bar_parity,
-                                            unsigned long long* s_best, float* s_min,
+                                            unsigned long long* s_best, float* s_min, double2* s_w0,
                                             const S* __restrict__ img, int64_t img_n,
                                             const double2* __restrict__ ipfx, const double2* __restrict__ tpfx,
                                             const PackedTables& tab, unsigned long long* __restrict__ keys,
@@ -406,6 +407,8 @@ __device__ __forceinline__ void finish_item(const Item& it, int tid, const Smem&
                 f_w0q = (float)(w0q + 0.25);
                 f_k0 = 0.f;
                 f_A = (float)(w0q + tsq - 2.0 * (b * w0s + k_const));
+                s_w0[c * QT + tid] = make_double2(w0s, w0q);          // exact sums at the head of the run, for the candidates
+
             } else {
                 f_w0q = (float)w0q;
                 f_k0 = (float)(b * w0s + k_const);
@@ -476,7 +479,7 @@ __device__ __forceinline__ void finish_item(const Item& it, int tid, const Smem&
     if (lane == 0) s_min[warp] = tmin;
     if (is_u8) fence_proxy_async();   // window reads before the next item's TMA refill
     csync<ID>();
-    after_read();
+    if (!v2) after_read();            // v2 evaluates its candidates from the staged windows first
     float bmin = s_min[0];
 #pragma unroll
     for (int w = 1; w < NW; ++w) bmin = fminf(bmin, s_min[w]);
@@ -510,8 +513,28 @@ __device__ __forceinline__ void finish_item(const Item& it, int tid, const Smem&
         const float er = second ? E.r.y : E.r.x, ei = second ? E.i.y : E.i.x, orr = second ? O.r.y : O.r.x, oi = second ? O.i.y : O.i.x;
         const float xr = fmaf(orr, w.x, fmaf(oi, -w.y, er)), xi = fmaf(orr, w.y, fmaf(oi, w.x, ei));
         const double cc = (double)((m & 1) ? xi : xr) * scale;
-        const double2 p_hi = ipfx[j + n], p_lo = ipfx[j];
-        const float v = sqdiff_exact(cc, p_hi.x - p_lo.x, p_hi.y - p_lo.y, a, b, tsum, tsq, n_ab);
+        double wsum, wsq;
+        if constexpr (v2) {
+            // exact window sums without touching HBM: the run's head sums (kept in shared memory by the screening
+            // loop) plus the integer slide over the first `bit & 7` samples of the staged windows
+            const int c = bit >> 3, i = bit & 7, m0 = c * LAGS_PER_ROUND + tid * 8;
+            const unsigned long long lo8 = *reinterpret_cast<const unsigned long long*>(sm.lo + m0);
+            const int hb = (int)((j_blk + n) & 15) + m0;
+            const unsigned long long h0 = *reinterpret_cast<const unsigned long long*>(sm.hi + (hb & ~7));
+            const unsigned long long h1 = *reinterpret_cast<const unsigned long long*>(sm.hi + (hb & ~7) + 8);
+            const unsigned sh = (unsigned)(hb & 7) * 8u;
+            const unsigned long long hi8 = sh ? ((h0 >> sh) | (h1 << (64u - sh))) : h0;
+            const unsigned long long keep = i ? (~0ull >> (8 * (8 - i))) : 0ull;      // samples 0 .. i-1
+            const unsigned la = (unsigned)(lo8 & keep), lb = (unsigned)((lo8 & keep) >> 32), ha = (unsigned)(hi8 & keep), hb2 = (unsigned)((hi8 & keep) >> 32);
+            const int rq = (int)__dp4a(ha, ha, __dp4a(hb2, hb2, 0u)) - (int)__dp4a(la, la, __dp4a(lb, lb, 0u));
+            const int rs = (int)__dp4a(ha, 0x01010101u, __dp4a(hb2, 0x01010101u, 0u)) - (int)__dp4a(la, 0x01010101u, __dp4a(lb, 0x01010101u, 0u));
+            const double2 w0 = s_w0[c * QT + tid];
+            wsum = w0.x + (double)rs; wsq = w0.y + (double)rq;
+        } else {
+            const double2 p_hi = ipfx[j + n], p_lo = ipfx[j];
+            wsum = p_hi.x - p_lo.x; wsq = p_hi.y - p_lo.y;
+        }
+        const float v = sqdiff_exact(cc, wsum, wsq, a, b, tsum, tsq, n_ab);
         if (curve_out) curve_out[d.curveOff + (j - jlo)] = v;
         const unsigned long long key = ((unsigned long long)__float_as_uint(v) << 32) | (unsigned int)(j - jlo);
         best = key < best ? key : best;
@@ -522,7 +545,9 @@ __device__ __forceinline__ void finish_item(const Item& it, int tid, const Smem&
         best = other < best ? other : best;
     }
     if (lane == 0) s_best[warp] = best;
+    if (v2) fence_proxy_async();      // the candidates' window reads, again before the refill
     csync<ID>();
+    if (v2) after_read();
     if (tid == 0) {
         for (int w = 1; w < NW; ++w) best = s_best[w] < best ? s_best[w] : best;
         if (best != ~0ull) atomicMin(keys + it.q, best);
@@ -545,6 +570,7 @@ k_match_packed(const float4* __restrict__ That, int64_t part_first,
     unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(sm.end);
     unsigned long long* s_best = s_bar + 1;                                // [NW]
     float* s_min = reinterpret_cast<float*>(s_best + NW);                  // [NW]
+    double2* s_w0 = EPI == 2 && is_u8 ? reinterpret_cast<double2*>(sm.end + kSmallBytes) : nullptr;   // [kRounds][QT]
     const Buf& buf = sm.buf;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -608,7 +634,7 @@ k_match_packed(const float4* __restrict__ That, int64_t part_first,
 
     // ---------------- 3. inverse FFT, 4. epilogue ---------------------------------------------
     fft_passes<0>(buf, tid, tab, is_u8);
-    finish_item<S, 0, EPI>(it, tid, sm, s_bar, 0u, s_best, s_min, img, img_n, ipfx, tpfx, tab, keys, curve_out, [] {});
+    finish_item<S, 0, EPI>(it, tid, sm, s_bar, 0u, s_best, s_min, s_w0, img, img_n, ipfx, tpfx, tab, keys, curve_out, [] {});
 }
 
 // ---------------------------------------------------------------- kernel B: persistent, warp-specialised
@@ -735,7 +761,7 @@ k_match_ws(const float4* __restrict__ That, int64_t part_first,
             mbar_arrive(tm_empty + b);
             csync<1>();
             fft_passes<1>(buf, tid, tab, is_u8);
-            finish_item<S, 1, 1>(it, tid, sm, s_bar, n & 1u, s_best, s_min, img, img_n, ipfx, tpfx, tab, keys, curve_out,
+            finish_item<S, 1, 1>(it, tid, sm, s_bar, n & 1u, s_best, s_min, nullptr, img, img_n, ipfx, tpfx, tab, keys, curve_out,
                               [&] {   // every thread is done with the staged windows: start the next item's copies
                                   if (is_u8 && local + gridDim.x < n_items) {
                                       const Item nxt(desc, item_query, item_first, local + gridDim.x);
@@ -852,6 +878,7 @@ k_match_pair(const float4* __restrict__ That, int64_t part_first,
     unsigned long long* s_best = s_bar + 1;                                // [NW]
     float* s_min = reinterpret_cast<float*>(s_best + NW);                  // [NW]
     uint32_t* s_taddr = reinterpret_cast<uint32_t*>(s_min + NW);
+    double2* s_w0 = EPI == 2 && is_u8 ? reinterpret_cast<double2*>(sm.end + kSmallBytes) : nullptr;   // [kRounds][QT]
     const Buf& buf = sm.buf;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -940,7 +967,7 @@ k_match_pair(const float4* __restrict__ That, int64_t part_first,
 
     // ---------------- first item: inverse FFT + epilogue ---------------------------------------
     fft_passes<0>(buf, tid, tab, is_u8);
-    finish_item<S, 0, EPI>(it0, tid, sm, s_bar, 0u, s_best, s_min, img, img_n, ipfx, tpfx, tab, keys, curve_out,
+    finish_item<S, 0, EPI>(it0, tid, sm, s_bar, 0u, s_best, s_min, s_w0, img, img_n, ipfx, tpfx, tab, keys, curve_out,
                       [&] { if (is_u8 && has2) stage_inputs(it1, tid, reinterpret_cast<const uint8_t*>(img), img_n, ipfx, sm, s_bar); });
 
     // ---------------- second item: out of tensor memory, then the same ---------------------------
@@ -963,7 +990,7 @@ k_match_pair(const float4* __restrict__ That, int64_t part_first,
         if (tid == (NW - 1) * 32) buf.st(phys(Q4), sp1);
         csync<0>();
         fft_passes<0>(buf, tid, tab, is_u8);
-        finish_item<S, 0, EPI>(it1, tid, sm, s_bar, 1u, s_best, s_min, img, img_n, ipfx, tpfx, tab, keys, curve_out, [] {});
+        finish_item<S, 0, EPI>(it1, tid, sm, s_bar, 1u, s_best, s_min, s_w0, img, img_n, ipfx, tpfx, tab, keys, curve_out, [] {});
     }
     tmem_fence_before();
     csync<0>();
@@ -994,6 +1021,7 @@ k_match_triple(const float4* __restrict__ That, int64_t part_first,
     unsigned long long* s_best = s_bar + 1;                                // [NW]
     float* s_min = reinterpret_cast<float*>(s_best + NW);                  // [NW]
     uint32_t* s_taddr = reinterpret_cast<uint32_t*>(s_min + NW);
+    double2* s_w0 = EPI == 2 && is_u8 ? reinterpret_cast<double2*>(sm.end + kSmallBytes) : nullptr;   // [kRounds][QT]
     const Buf& buf = sm.buf;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1082,7 +1110,7 @@ k_match_triple(const float4* __restrict__ That, int64_t part_first,
 
     // ---------------- first item: inverse FFT + epilogue ---------------------------------------
     fft_passes<0>(buf, tid, tab, is_u8);
-    finish_item<S, 0, EPI>(it0, tid, sm, s_bar, 0u, s_best, s_min, img, img_n, ipfx, tpfx, tab, keys, curve_out,
+    finish_item<S, 0, EPI>(it0, tid, sm, s_bar, 0u, s_best, s_min, s_w0, img, img_n, ipfx, tpfx, tab, keys, curve_out,
                            [&] { if (is_u8 && nb > 1) stage_inputs(it1, tid, reinterpret_cast<const uint8_t*>(img), img_n, ipfx, sm, s_bar); });
 
     // ---------------- second and third item: out of tensor memory, then the same ------------------
@@ -1108,10 +1136,10 @@ k_match_triple(const float4* __restrict__ That, int64_t part_first,
         csync<0>();
         fft_passes<0>(buf, tid, tab, is_u8);
         if (j == 1)
-            finish_item<S, 0, EPI>(it1, tid, sm, s_bar, 1u, s_best, s_min, img, img_n, ipfx, tpfx, tab, keys, curve_out,
+            finish_item<S, 0, EPI>(it1, tid, sm, s_bar, 1u, s_best, s_min, s_w0, img, img_n, ipfx, tpfx, tab, keys, curve_out,
                                    [&] { if (is_u8 && nb > 2) stage_inputs(it2, tid, reinterpret_cast<const uint8_t*>(img), img_n, ipfx, sm, s_bar); });
         else
-            finish_item<S, 0, EPI>(it2, tid, sm, s_bar, 0u, s_best, s_min, img, img_n, ipfx, tpfx, tab, keys, curve_out, [] {});
+            finish_item<S, 0, EPI>(it2, tid, sm, s_bar, 0u, s_best, s_min, s_w0, img, img_n, ipfx, tpfx, tab, keys, curve_out, [] {});
     }
     tmem_fence_before();
     csync<0>();
@@ -1211,8 +1239,9 @@ size_t forward_smem_bytes14() {
     return ((size_t)(C::N + (C::N >> 5) + 1) + C::R2 * 32 + 2 * C::R3 * 32) * sizeof(float2) + 64;
 }
 
-size_t packed_smem_bytes() {
-    return kSmemCommon + 8 + QNW * sizeof(unsigned long long) + QNW * sizeof(float) + 64;
+size_t packed_smem_bytes(int epi = 1) {      // epilogue 2 keeps the runs' exact head sums next to the small arrays
+    return epi == 2 ? kSmemCommon + kSmallBytes + (size_t)kRounds * QT * sizeof(double2)
+                    : kSmemCommon + 8 + QNW * sizeof(unsigned long long) + QNW * sizeof(float) + 64;
 }
 
 // Values of the four tables of PackedTables, in one array: offsets of tw2, tw3, w8, wb in `off` (floats)
@@ -1313,7 +1342,7 @@ int launch_packed_typed(const sb_stream* image, const sb_stream* tmpl, const flo
                         unsigned long long* d_keys, float* d_curve) {
     Ctx& c = ctx();
     static bool attr_set = false;
-    const size_t smem = packed_smem_bytes();
+    const size_t smem = packed_smem_bytes(EPI);
     if (!attr_set) {
         SB_CUDA(cudaFuncSetAttribute(k_match_packed<S, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
@@ -1336,7 +1365,7 @@ int launch_pair_typed(const sb_stream* image, const sb_stream* tmpl, const float
                       unsigned long long* d_keys, float* d_curve) {
     Ctx& c = ctx();
     static bool attr_set = false;
-    const size_t smem = packed_smem_bytes() + 16;
+    const size_t smem = packed_smem_bytes(EPI) + 16;
     if (!attr_set) {
         SB_CUDA(cudaFuncSetAttribute(k_match_pair<S, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
@@ -1355,7 +1384,7 @@ int launch_triple_typed(const sb_stream* image, const sb_stream* tmpl, const flo
                         unsigned long long* d_keys, float* d_curve) {
     Ctx& c = ctx();
     static bool attr_set = false;
-    const size_t smem = packed_smem_bytes() + 16;
+    const size_t smem = packed_smem_bytes(EPI) + 16;
     if (!attr_set) {
         SB_CUDA(cudaFuncSetAttribute(k_match_triple<S, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
