@@ -539,18 +539,25 @@ __device__ __forceinline__ void finish_item(const Item& it, int tid, const Smem&
         const unsigned long long key = ((unsigned long long)__float_as_uint(v) << 32) | (unsigned int)(j - jlo);
         best = key < best ? key : best;
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
-        best = other < best ? other : best;
-    }
-    if (lane == 0) s_best[warp] = best;
-    if (v2) fence_proxy_async();      // the candidates' window reads, again before the refill
-    csync<ID>();
-    if (v2) after_read();
-    if (tid == 0) {
-        for (int w = 1; w < NW; ++w) best = s_best[w] < best ? s_best[w] : best;
+    if constexpr (v2) {
+        // candidates are rare (usually one thread of the CTA has any): each merges its own best straight into the
+        // query's key instead of a shuffle tree, a round through shared memory and a serial merge by thread 0
         if (best != ~0ull) atomicMin(keys + it.q, best);
+        fence_proxy_async();          // the candidates' window reads, again before the refill
+        csync<ID>();                  // everyone is done with the FFT buffer and the staged windows
+        after_read();
+    } else {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+            best = other < best ? other : best;
+        }
+        if (lane == 0) s_best[warp] = best;
+        csync<ID>();
+        if (tid == 0) {
+            for (int w = 1; w < NW; ++w) best = s_best[w] < best ? s_best[w] : best;
+            if (best != ~0ull) atomicMin(keys + it.q, best);
+        }
     }
 }
 
