@@ -26,6 +26,7 @@ ap.add_argument('--premac-mode', type=int, default=0)
 ap.add_argument('--events', default='0.5,1,3,10,30')
 ap.add_argument('--windows', default='5,10,30,60,120,300,600')
 ap.add_argument('--engine', type=int, default=-1, help='library engine (default: the library default)')
+ap.add_argument('--epilogue', type=int, default=0, help='screening loop of the packed kernels: 1 | 2 (default: the library default)')
 ap.add_argument('--out', default='sweep.json', help='file name under gpurun_out/')
 a = ap.parse_args()
 
@@ -40,6 +41,8 @@ dst = WavStream.from_pcm(dst_pcm, 12000, sample_type=a.sample_type)
 lib = _native.lib()
 if a.engine >= 0:
     _native.check(lib.sb_set_engine(a.engine))
+if a.epilogue > 0:
+    _native.check(lib.sb_set_epilogue(a.epilogue))
 _native.check(lib.sb_set_hop_mode(a.hop_mode))
 _native.check(lib.sb_set_premac_mode(a.premac_mode))
 EV = [float(x) for x in a.events.split(',')]
