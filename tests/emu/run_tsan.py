@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """ThreadSanitizer pass over the CPU emulation of the match kernels (tests/emu, test infrastructure).
 
-    python tools/emu_tsan.py
+    python tests/emu/run_tsan.py
 
 Builds tests/emu/emu_driver.cpp with -fsanitize=thread and runs every kernel (one CTA per lag block / pair /
 triple) with both screening loops, with and without the debug curve, on the cases of
@@ -15,7 +15,7 @@ import os
 import subprocess
 import sys
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 LIB = os.path.join(ROOT, 'tests', 'emu', '_build', 'libsb_emu_tsan.so')
 LOG = os.path.join(ROOT, 'tests', 'emu', '_build', 'tsan.log')

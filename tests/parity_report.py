@@ -1,7 +1,8 @@
 #!/usr/bin/env python3
 """Numerical parity report: whole curves from the GPU against cv2.matchTemplate (the oracle's call) and
 against the fp64 closed form, over template lengths and both sample types.  Prints a table; the numbers
-go to profiles/parity_r1.txt."""
+go to profiles/parity_r1.txt.  It lives under tests/ because it calls the oracle (cv2, the fp64 closed
+form): only tests/, smoke() and bench.py's CPU leg may."""
 import os
 import sys
 

@@ -13,5 +13,5 @@ timeout 60 python bench.py --workload config1 --steps 20 --warmup 3 --no-cpu-bas
 timeout 120 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_r1b.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/ncu_launches.log 2>&1
 timeout 200 ncu --set full --clock-control none --import-source on -k regex:k_match_pair -s 3 -c 1 -o $O/pair_bench_r1b python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $O/ncu_full.log 2>&1; tail -2 $O/ncu_full.log
 for e in 2; do timeout 90 python tools/sweep.py --engine $e --queries 128 --reps 2 --events 0.5,1,3,10,30 --windows 10,60,120 --out sweep_r1b_engine$e.json > $O/sweep_engine$e.txt 2>&1; tail -5 $O/sweep_engine$e.txt; done
-timeout 120 python tools/parity_report.py > $O/parity_r1b.txt 2>&1; tail -4 $O/parity_r1b.txt
+timeout 120 python tests/parity_report.py > $O/parity_r1b.txt 2>&1; tail -4 $O/parity_r1b.txt
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv

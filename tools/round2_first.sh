@@ -24,5 +24,5 @@ timeout 60 python bench.py --workload config3 --steps 5 --warmup 3 --no-cpu-base
 timeout 150 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_r2_first.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --engine 6 --epilogue 2 > $O/ncu_launches.log 2>&1
 timeout 250 ncu --set full --clock-control none --import-source on -k regex:k_match_triple -s 3 -c 1 -o $O/triple_bench_r2 python bench.py --steps 1 --warmup 3 --no-cpu-baseline --engine 6 --epilogue 2 > $O/ncu_full.log 2>&1; tail -2 $O/ncu_full.log
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv
-SB_PARITY_EXPERIMENTAL=1 timeout 200 python tools/parity_report.py > $O/parity_r2_first.txt 2>&1; grep -c same $O/parity_r2_first.txt; grep DIFF $O/parity_r2_first.txt | head
+SB_PARITY_EXPERIMENTAL=1 timeout 200 python tests/parity_report.py > $O/parity_r2_first.txt 2>&1; grep -c same $O/parity_r2_first.txt; grep DIFF $O/parity_r2_first.txt | head
 timeout 120 python tools/sweep.py --engine 6 --epilogue 2 --queries 128 --reps 2 --events 0.5,1,3,10 --windows 10,60,120 --out sweep_r2_engine6_epi2.json > $O/sweep_engine6.txt 2>&1; tail -5 $O/sweep_engine6.txt
