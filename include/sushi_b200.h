@@ -106,6 +106,14 @@ int sb_set_hop_mode(int mode);
  * float32 streams and the other engines ignore the setting.  Opt-in until measured. */
 int sb_set_epilogue(int variant);
 int sb_get_epilogue(void);
+/* Storage of the spectrum rows the packed kernels multiply (engines 2, 4, 5, 6; block spectra of a stream and
+ * template partition spectra): 0 (default) = float32; 1 = 16-bit block floating point (int16 components, one
+ * float32 scale per bin family and group of eight quads): rows of 73 856 instead of 131 200 bytes for the
+ * L2-bound multiply phase.  All arithmetic stays float32; the quantisation moves the curve by ~5e-7 on programme
+ * audio (the float32 FFT's own rounding: 2e-7), so results agree with format 0 to ~1e-6, not bit for bit.  A
+ * stream's cached rows are rebuilt when the format changes.  Opt-in until measured. */
+int sb_set_spectra(int format);
+int sb_get_spectra(void);
 /* Lag blocks processed per multiply / inverse-FFT / normalise launch (>= 1). */
 int sb_set_chunk_items(int items);
 /* Template partition spectra kept resident per pass over a batch (>= 1); batches needing more are

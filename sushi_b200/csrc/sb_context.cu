@@ -228,6 +228,12 @@ int sb_set_hop_mode(int mode) {
     ctx().hop_mode = mode;
     return SB_OK;
 }
+int sb_set_spectra(int format) {
+    if (format < 0 || format > 1) SB_FAIL(SB_EINVAL, "sb_set_spectra: %d is not 0 (float32 rows) or 1 (16-bit block floating point rows)", format);
+    ctx().spectra_fmt = format;
+    return SB_OK;
+}
+int sb_get_spectra(void) { return ctx().spectra_fmt; }
 int sb_set_epilogue(int variant) {
     if (variant < 1 || variant > 2) SB_FAIL(SB_EINVAL, "sb_set_epilogue: %d is not 1 (first screening loop) or 2 (trimmed screening loop)", variant);
     ctx().epilogue = variant;

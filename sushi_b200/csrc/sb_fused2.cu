@@ -127,6 +127,57 @@ struct Buf {
     __device__ __forceinline__ void st(int p, C2 v) const { r[p] = v.r; i[p] = v.i; }
 };
 
+// ---------------------------------------------------------------- spectrum row formats
+// FMT 0 (measured default): float32, 16-byte units A[i] / M[i] in blocks of 256 + 256 as described above.
+// FMT 1 (opt-in, sb_set_spectra(1)): 16-bit block floating point.  Unit i (16 bytes) holds the eight components
+// of quad i as int16 -- (re X[i], re X[i+B/2]), (im X[i], im X[i+B/2]), (re X[B-i], re X[B/2-i]), (im .., im ..) --
+// and unit Q4+1+(i>>3) holds four float32 scales for the quads 8g .. 8g+7, one per bin family (X[i], X[i+B/2],
+// X[B-i], X[B/2-i]: eight consecutive bins each, so a scale never spans distant frequencies).  A row is 73 856
+// instead of 131 200 bytes: the multiply phase runs at the L2 -> SM rate, bytes are what it costs.  Quantisation
+// error of a component <= scale / 2 = max of its group / 65534; on programme audio the curve moves by ~5e-7
+// (fp32 FFT rounding itself: 2e-7; NumPy study in DESIGN.md section 8).
+constexpr int QROW16 = kQuad16RowF2 / 2;  // 16-byte units per FMT 1 row
+constexpr int QSCALE0 = Q4 + 1;           // first scale unit of a FMT 1 row
+static_assert(QROW16 >= QSCALE0 + (Q4 >> 3) + 1 && (QROW16 * 16) % 128 == 0, "16-bit row layout");
+
+__device__ __forceinline__ void dequant16(uint4 q, float4 s, float4& a, float4& m) {
+    a.x = (float)(short)(q.x & 0xffffu) * s.x;  a.y = (float)(short)(q.x >> 16) * s.y;
+    a.z = (float)(short)(q.y & 0xffffu) * s.x;  a.w = (float)(short)(q.y >> 16) * s.y;
+    m.x = (float)(short)(q.z & 0xffffu) * s.z;  m.y = (float)(short)(q.z >> 16) * s.w;
+    m.z = (float)(short)(q.w & 0xffffu) * s.z;  m.w = (float)(short)(q.w >> 16) * s.w;
+}
+
+// Addressing and loading of one quad of a row, in 16-byte units from the row's first unit.
+template <int FMT> struct Rows;
+template <> struct Rows<0> {
+    static constexpr int STRIDE = QROW;
+    // unit of quad tid + 512*uu's A chunk (its M chunk is QBLK further): qa() without the special case
+    static __device__ __forceinline__ int unit(int tid, int uu) { return (tid >> 8) * (2 * QBLK) + (tid & (QBLK - 1)) + uu * (2 * QT); }
+    static constexpr int USTEP = 2 * QT;             // units between the quads tid + 512*uu and tid + 512*(uu+1)
+    static __device__ __forceinline__ void load(const float4* row, int u, float4& a, float4& m) { a = __ldg(row + u); m = __ldg(row + u + QBLK); }
+    // predicated form (a row past the end of the stream reads as zero)
+    static __device__ __forceinline__ void loadp(const float4* row, int u, bool pred, float4& a, float4& m) {
+        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        a = pred ? __ldg(row + u) : zero4;  m = pred ? __ldg(row + u + QBLK) : zero4;
+    }
+    static __device__ __forceinline__ void load_special(const float4* row, float4& a, float4& m) { a = __ldg(row + qa(Q4)); m = __ldg(row + qm(Q4)); }
+};
+template <> struct Rows<1> {
+    static constexpr int STRIDE = QROW16;
+    static __device__ __forceinline__ int unit(int tid, int uu) { return tid + uu * QT; }          // the quad's own number
+    static constexpr int USTEP = QT;
+    static __device__ __forceinline__ void load(const float4* row, int u, float4& a, float4& m) {
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(row) + u);
+        dequant16(q, __ldg(row + QSCALE0 + (u >> 3)), a, m);
+    }
+    static __device__ __forceinline__ void loadp(const float4* row, int u, bool pred, float4& a, float4& m) {
+        const uint4 q = pred ? __ldg(reinterpret_cast<const uint4*>(row) + u) : make_uint4(0u, 0u, 0u, 0u);
+        const float4 sc = pred ? __ldg(row + QSCALE0 + (u >> 3)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        dequant16(q, sc, a, m);
+    }
+    static __device__ __forceinline__ void load_special(const float4* row, float4& a, float4& m) { load(row, Q4, a, m); }
+};
+
 // Spectrum rows: plain read-only loads.  (Measured: ld.global.nc.L1::no_allocate, tried to keep the twiddle
 // tables in L1, drops the L2 hit rate of these rows from 98 % to 83 % and multiplies the DRAM traffic of the
 // kernel by 9 -- profiles/README.md.)
@@ -237,11 +288,15 @@ struct QuadAcc {
 };
 
 // The self-mirrored quad i = B/4 of an item, by one warp: partitions spread over the lanes, result valid in lane 0
+template <int FMT = 0>
 __device__ __forceinline__ C2 special_quad(const float4* tp, const float4* xp, int P, int lane) {
     QuadAcc acc; acc.zero();
-    for (int p = lane; p < P; p += 32)
-        acc.mac(__ldg(tp + (int64_t)p * QROW + qa(Q4)), __ldg(tp + (int64_t)p * QROW + qm(Q4)),
-                __ldg(xp + (int64_t)p * QROW + qa(Q4)), __ldg(xp + (int64_t)p * QROW + qm(Q4)));
+    for (int p = lane; p < P; p += 32) {
+        float4 ta, tm, xa, xm;
+        Rows<FMT>::load_special(tp + (int64_t)p * Rows<FMT>::STRIDE, ta, tm);
+        Rows<FMT>::load_special(xp + (int64_t)p * Rows<FMT>::STRIDE, xa, xm);
+        acc.mac(ta, tm, xa, xm);
+    }
     acc.reduce_over_lanes();
     const float h = 0.70710678118654752f;       // exp(i*pi/4)
     C2 lo, hi;
@@ -562,7 +617,7 @@ __device__ __forceinline__ void finish_item(const Item& it, int tid, const Smem&
 }
 
 // ---------------------------------------------------------------- kernel A: one CTA per item
-template <typename S, int EPI>
+template <typename S, int EPI, int FMT>
 __global__ void __launch_bounds__(QT, 1)
 k_match_packed(const float4* __restrict__ That, int64_t part_first,
                const float4* __restrict__ Xhat, int64_t nblk,
@@ -594,27 +649,28 @@ k_match_packed(const float4* __restrict__ That, int64_t part_first,
     {
         int P = d.P;
         if (it.k + P > nblk) P = (int)(nblk - it.k);      // rows past the end of the stream are zero
-        const float4* tp = That + (d.partBase - part_first) * (int64_t)QROW;
-        const float4* xp = Xhat + it.k * (int64_t)QROW;
+        typedef Rows<FMT> R;
+        const float4* tp = That + (d.partBase - part_first) * (int64_t)R::STRIDE;
+        const float4* xp = Xhat + it.k * (int64_t)R::STRIDE;
         const float2 wbase = __ldg(tab.wb + tid);
         const int tm = (T - tid) & (T - 1);           // mirrored chunks C[B/2 - i] live in thread tm's column
         const int col = phys(tid), mcol = phys(tm);
         constexpr int U = 4;                          // quads in flight per thread
 #pragma unroll 1
         for (int half = 0; half < 2; ++half) {
-            const int i0 = (tid >> 8) * (2 * QBLK) + (tid & (QBLK - 1)) + half * (U * 2 * T);   // qa(tid + 512*(half*U + u)) = i0 + 1024u
+            const int i0 = R::unit(tid, half * U);    // unit of quad tid + 512*(half*U + u) = i0 + u*USTEP
             QuadAcc acc[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) acc[u].zero();
 #pragma unroll 1
             for (int p = 0; p < P; ++p) {
-                const float4* t = tp + (int64_t)p * QROW + i0;
-                const float4* x = xp + (int64_t)p * QROW + i0;
+                const float4* t = tp + (int64_t)p * R::STRIDE;
+                const float4* x = xp + (int64_t)p * R::STRIDE;
                 float4 ta[U], tmm[U], xa[U], xm[U];
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    ta[u] = ldg_stream(t + u * 2 * T);  tmm[u] = ldg_stream(t + QBLK + u * 2 * T);
-                    xa[u] = ldg_stream(x + u * 2 * T);  xm[u] = ldg_stream(x + QBLK + u * 2 * T);
+                    R::load(t, i0 + u * R::USTEP, ta[u], tmm[u]);
+                    R::load(x, i0 + u * R::USTEP, xa[u], xm[u]);
                 }
 #pragma unroll
                 for (int u = 0; u < U; ++u) acc[u].mac(ta[u], tmm[u], xa[u], xm[u]);
@@ -633,7 +689,7 @@ k_match_packed(const float4* __restrict__ That, int64_t part_first,
             }
         }
         if (warp == NW - 1) {                       // the self-mirrored quad i = B/4
-            const C2 lo = special_quad(tp, xp, P, lane);
+            const C2 lo = special_quad<FMT>(tp, xp, P, lane);
             if (lane == 0) buf.st(phys(Q4), lo);
         }
     }
@@ -869,7 +925,7 @@ k_match_ws(const float4* __restrict__ That, int64_t part_first,
 // parked in TENSOR MEMORY (tcgen05.st; every thread later reads back exactly what it wrote, so the 32-lane
 // window of a warp is no constraint) while the CTA transforms the first; then it is taken out again
 // (tcgen05.ld) and goes through the same passes and epilogue.
-template <typename S, int EPI>
+template <typename S, int EPI, int FMT>
 __global__ void __launch_bounds__(QT, 1)
 k_match_pair(const float4* __restrict__ That, int64_t part_first,
              const float4* __restrict__ Xhat, int64_t nblk,
@@ -911,32 +967,32 @@ k_match_pair(const float4* __restrict__ That, int64_t part_first,
     C2 sp1 = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};             // C[B/4] of the second item (warp NW-1, lane 0)
     // ---------------- 1+2. multiply-accumulate for both items, packing, first radix-2 step ----
     {
+        typedef Rows<FMT> R;
         const int64_t k = it0.k;
-        const float4* tp = That + (d.partBase - part_first) * (int64_t)QROW;
-        const float4* xp = Xhat + k * (int64_t)QROW;
+        const float4* tp = That + (d.partBase - part_first) * (int64_t)R::STRIDE;
+        const float4* xp = Xhat + k * (int64_t)R::STRIDE;
         const float2 wbase = __ldg(tab.wb + tid);
-        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
         constexpr int U = 2;                          // quads in flight per thread (two accumulator sets each)
 #pragma unroll 1
         for (int grp = 0; grp < 8 / U; ++grp) {
-            const int i0 = (tid >> 8) * (2 * QBLK) + (tid & (QBLK - 1)) + grp * (U * 2 * T);   // qa(tid + 512*(grp*U + u)) = i0 + 1024u
+            const int i0 = R::unit(tid, grp * U);     // unit of quad tid + 512*(grp*U + u) = i0 + u*USTEP
             QuadAcc a0[U], a1[U];
             float4 xa[U], xm[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 a0[u].zero(); a1[u].zero();
-                xa[u] = ldg_stream(xp + i0 + u * 2 * T); xm[u] = ldg_stream(xp + i0 + QBLK + u * 2 * T);   // row k < nblk
+                R::load(xp, i0 + u * R::USTEP, xa[u], xm[u]);     // row k < nblk
             }
 #pragma unroll 1
             for (int p = 0; p < d.P; ++p) {
-                const float4* t = tp + (int64_t)p * QROW + i0;
-                const float4* x = xp + (int64_t)(p + 1) * QROW + i0;
+                const float4* t = tp + (int64_t)p * R::STRIDE;
+                const float4* x = xp + (int64_t)(p + 1) * R::STRIDE;
                 const bool next_row = k + p + 1 < nblk;           // rows past the end of the stream are zero
                 float4 ta[U], tmm[U], xna[U], xnm[U];
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    ta[u] = ldg_stream(t + u * 2 * T);  tmm[u] = ldg_stream(t + QBLK + u * 2 * T);
-                    xna[u] = next_row ? ldg_stream(x + u * 2 * T) : zero4;  xnm[u] = next_row ? ldg_stream(x + QBLK + u * 2 * T) : zero4;
+                    R::load(t, i0 + u * R::USTEP, ta[u], tmm[u]);
+                    R::loadp(x, i0 + u * R::USTEP, next_row, xna[u], xnm[u]);
                 }
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
@@ -961,11 +1017,11 @@ k_match_pair(const float4* __restrict__ That, int64_t part_first,
         }
         if (warp == NW - 1) {                         // the self-mirrored quad i = B/4 of both items
             int P0 = d.P; if (k + P0 > nblk) P0 = (int)(nblk - k);
-            const C2 lo = special_quad(tp, xp, P0, lane);
+            const C2 lo = special_quad<FMT>(tp, xp, P0, lane);
             if (lane == 0) buf.st(phys(Q4), lo);
             if (has2) {
                 int P1 = d.P; if (k + 1 + P1 > nblk) P1 = (int)(nblk - k - 1);
-                sp1 = special_quad(tp, xp + QROW, P1, lane);
+                sp1 = special_quad<FMT>(tp, xp + R::STRIDE, P1, lane);
             }
         }
         tmem_wait_st();
@@ -1012,7 +1068,7 @@ k_match_pair(const float4* __restrict__ That, int64_t part_first,
 // product spectra (2 x 256 columns), so the first block goes to shared memory and the other two wait there.
 // Three accumulator sets leave room for one quad per thread and step; to keep as many loads in flight as the pair
 // kernel has, the rows of step p + 1 are requested before the multiply-accumulates of step p.
-template <typename S, int EPI>
+template <typename S, int EPI, int FMT>
 __global__ void __launch_bounds__(QT, 1)
 k_match_triple(const float4* __restrict__ That, int64_t part_first,
                const float4* __restrict__ Xhat, int64_t nblk,
@@ -1054,31 +1110,29 @@ k_match_triple(const float4* __restrict__ That, int64_t part_first,
     const int col = phys(tid), mcol = phys(tm);
     C2 sp1 = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)}, sp2 = sp1;   // C[B/4] of blocks 2 and 3 (warp NW-1, lane 0)
     {
+        typedef Rows<FMT> R;
         const int64_t k = it0.k;
-        const float4* tp = That + (d.partBase - part_first) * (int64_t)QROW;
-        const float4* xp = Xhat + k * (int64_t)QROW;
+        const float4* tp = That + (d.partBase - part_first) * (int64_t)R::STRIDE;
+        const float4* xp = Xhat + k * (int64_t)R::STRIDE;
         const float2 wbase = __ldg(tab.wb + tid);
-        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 1
         for (int uu = 0; uu < 8; ++uu) {              // quad i = tid + 512*uu
-            const int i0 = (tid >> 8) * (2 * QBLK) + (tid & (QBLK - 1)) + uu * (2 * T);        // qa(i)
+            const int i0 = R::unit(tid, uu);
             QuadAcc a0, a1, a2;
             a0.zero(); a1.zero(); a2.zero();
-            const bool row1 = k + 1 < nblk;           // rows past the end of the stream are zero
-            float4 x0a = ldg_stream(xp + i0), x0m = ldg_stream(xp + i0 + QBLK);                  // row k < nblk
-            float4 x1a = row1 ? ldg_stream(xp + QROW + i0) : zero4, x1m = row1 ? ldg_stream(xp + QROW + i0 + QBLK) : zero4;
-            float4 ta = ldg_stream(tp + i0), tmm = ldg_stream(tp + i0 + QBLK);
-            const bool row2 = k + 2 < nblk;
-            float4 x2a = row2 ? ldg_stream(xp + 2 * (int64_t)QROW + i0) : zero4, x2m = row2 ? ldg_stream(xp + 2 * (int64_t)QROW + i0 + QBLK) : zero4;
+            float4 x0a, x0m, x1a, x1m, ta, tmm, x2a, x2m;
+            R::load(xp, i0, x0a, x0m);                                             // row k < nblk
+            R::loadp(xp + R::STRIDE, i0, k + 1 < nblk, x1a, x1m);                  // rows past the end of the stream are zero
+            R::load(tp, i0, ta, tmm);
+            R::loadp(xp + 2 * (int64_t)R::STRIDE, i0, k + 2 < nblk, x2a, x2m);
 #pragma unroll 1
             for (int p = 0; p < d.P; ++p) {
                 // request the rows of step p + 1 (template row p + 1, spectrum row k + p + 3) ...
                 // (predicated loads, not branches: the scheduler may then hoist them above the arithmetic)
                 const bool more = p + 1 < d.P, xrow = more && k + p + 3 < nblk;
-                const float4* t = tp + (int64_t)(p + 1) * QROW + i0;
-                const float4* x = xp + (int64_t)(p + 3) * QROW + i0;
-                const float4 na = more ? ldg_stream(t) : zero4, nm = more ? ldg_stream(t + QBLK) : zero4;
-                const float4 nxa = xrow ? ldg_stream(x) : zero4, nxm = xrow ? ldg_stream(x + QBLK) : zero4;
+                float4 na, nm, nxa, nxm;
+                R::loadp(tp + (int64_t)(p + 1) * R::STRIDE, i0, more, na, nm);
+                R::loadp(xp + (int64_t)(p + 3) * R::STRIDE, i0, xrow, nxa, nxm);
                 // ... then multiply step p: block k + j needs spectrum row k + j + p
                 a0.mac(ta, tmm, x0a, x0m);
                 a1.mac(ta, tmm, x1a, x1m);
@@ -1100,15 +1154,15 @@ k_match_triple(const float4* __restrict__ That, int64_t part_first,
         }
         if (warp == NW - 1) {                         // the self-mirrored quad i = B/4 of the three items
             int P0 = d.P; if (k + P0 > nblk) P0 = (int)(nblk - k);
-            const C2 lo = special_quad(tp, xp, P0, lane);
+            const C2 lo = special_quad<FMT>(tp, xp, P0, lane);
             if (lane == 0) buf.st(phys(Q4), lo);
             if (nb > 1) {
                 int P1 = d.P; if (k + 1 + P1 > nblk) P1 = (int)(nblk - k - 1);
-                sp1 = special_quad(tp, xp + QROW, P1, lane);
+                sp1 = special_quad<FMT>(tp, xp + R::STRIDE, P1, lane);
             }
             if (nb > 2) {
                 int P2 = d.P; if (k + 2 + P2 > nblk) P2 = (int)(nblk - k - 2);
-                sp2 = special_quad(tp, xp + 2 * (int64_t)QROW, P2, lane);
+                sp2 = special_quad<FMT>(tp, xp + 2 * (int64_t)R::STRIDE, P2, lane);
             }
         }
         tmem_wait_st();
@@ -1170,7 +1224,27 @@ size_t ws_smem_bytes() {
 // Same transform as k_forward_rows in sb_fused.cu (gather + centring + 2B-point real FFT through the
 // shared-memory inverse passes run backwards); only the output stage differs: bins leave as the chunks
 // A[i] = (X[i], X[i+B/2]) and M[i] = (X[B-i], X[B/2-i]) the packed kernel multiplies.
-template <typename S, int MODE>
+// One quad in the 16-bit row format: components scaled by 32767 / (maximum of their bin family over the group of
+// eight quads), rounded to nearest; the lane of the group's first quad also writes the four scales.
+__device__ __forceinline__ void store_quad16(uint4* row, int i, float2 x_i, float2 x_hb, float2 x_bi, float2 x_h,
+                                             float m0, float m1, float m2, float m3) {
+    auto q = [](float v, float mx) -> unsigned {
+        const float inv = mx > 0.f ? 32767.0f / mx : 0.f;
+        int r = __float2int_rn(v * inv);
+        r = r > 32767 ? 32767 : (r < -32767 ? -32767 : r);
+        return (unsigned)r & 0xffffu;
+    };
+    uint4 o;
+    o.x = q(x_i.x, m0) | (q(x_hb.x, m1) << 16);      // re X[i],   re X[i+B/2]
+    o.y = q(x_i.y, m0) | (q(x_hb.y, m1) << 16);      // im X[i],   im X[i+B/2]
+    o.z = q(x_bi.x, m2) | (q(x_h.x, m3) << 16);      // re X[B-i], re X[B/2-i]
+    o.w = q(x_bi.y, m2) | (q(x_h.y, m3) << 16);      // im X[B-i], im X[B/2-i]
+    row[i] = o;
+    if ((i & 7) == 0)
+        reinterpret_cast<float4*>(row)[QSCALE0 + (i >> 3)] = make_float4(m0 / 32767.0f, m1 / 32767.0f, m2 / 32767.0f, m3 / 32767.0f);
+}
+
+template <typename S, int MODE, int FMT>
 __global__ void __launch_bounds__(Cfg<14>::T, 1)
 k_forward_quad(const S* __restrict__ src, int64_t src_n, const double2* __restrict__ pfx,
                const QueryDesc* __restrict__ desc, int q_begin, int q_end, int64_t row_first,
@@ -1231,13 +1305,37 @@ k_forward_quad(const S* __restrict__ src, int64_t src_n, const double2* __restri
         xk = make_float2(xe.x + tv.x, xe.y + tv.y);
         xbk = make_float2(xe.x - tv.x, -(xe.y - tv.y));
     };
-    float4* o = out + (int64_t)blockIdx.x * QROW;
-    for (int i = tid; i <= Q4; i += T) {
-        float2 x_i, x_bi, x_h, x_hb;
-        bins(i, x_i, x_bi);                          // X[i], X[B-i]
-        bins(B / 2 - i, x_h, x_hb);                  // X[B/2-i], X[B/2+i]
-        o[qa(i)] = make_float4(x_i.x, x_hb.x, x_i.y, x_hb.y);
-        o[qm(i)] = make_float4(x_bi.x, x_h.x, x_bi.y, x_h.y);
+    if constexpr (FMT == 0) {
+        float4* o = out + (int64_t)blockIdx.x * QROW;
+        for (int i = tid; i <= Q4; i += T) {
+            float2 x_i, x_bi, x_h, x_hb;
+            bins(i, x_i, x_bi);                          // X[i], X[B-i]
+            bins(B / 2 - i, x_h, x_hb);                  // X[B/2-i], X[B/2+i]
+            o[qa(i)] = make_float4(x_i.x, x_hb.x, x_i.y, x_hb.y);
+            o[qm(i)] = make_float4(x_bi.x, x_h.x, x_bi.y, x_h.y);
+        }
+    } else {
+        uint4* o = reinterpret_cast<uint4*>(out) + (int64_t)blockIdx.x * QROW16;
+        auto amax = [](float2 v) { return fmaxf(fabsf(v.x), fabsf(v.y)); };
+        for (int it = 0; it < Q4 / T; ++it) {            // every lane takes part: groups are 8 consecutive lanes
+            const int i = tid + it * T;
+            float2 x_i, x_bi, x_h, x_hb;
+            bins(i, x_i, x_bi);
+            bins(B / 2 - i, x_h, x_hb);
+            float m0 = amax(x_i), m1 = amax(x_hb), m2 = amax(x_bi), m3 = amax(x_h);
+#pragma unroll
+            for (int d = 1; d < 8; d <<= 1) {
+                m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, d)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, d));
+                m2 = fmaxf(m2, __shfl_xor_sync(0xffffffffu, m2, d)); m3 = fmaxf(m3, __shfl_xor_sync(0xffffffffu, m3, d));
+            }
+            store_quad16(o, i, x_i, x_hb, x_bi, x_h, m0, m1, m2, m3);
+        }
+        if (tid == 0) {                                  // the self-mirrored quad i = B/4: a group of its own
+            float2 x_i, x_bi, x_h, x_hb;
+            bins(Q4, x_i, x_bi);
+            bins(B / 2 - Q4, x_h, x_hb);
+            store_quad16(o, Q4, x_i, x_hb, x_bi, x_h, amax(x_i), amax(x_hb), amax(x_bi), amax(x_h));
+        }
     }
 }
 
@@ -1310,7 +1408,7 @@ __global__ void k_fill_item_query2(const QueryDesc* __restrict__ desc, int q_beg
 int* g_item_query2 = nullptr;
 int64_t g_item_query2_cap = 0;
 
-template <typename S, int MODE>
+template <typename S, int MODE, int FMT>
 int launch_forward_quad_typed(const sb_stream* src, const QueryDesc* d_desc, int q_begin, int q_end,
                               int64_t row_first, int64_t rows, float2* out) {
     Ctx& c = ctx();
@@ -1319,10 +1417,10 @@ int launch_forward_quad_typed(const sb_stream* src, const QueryDesc* d_desc, int
     static bool attr_set = false;
     const size_t smem = forward_smem_bytes14();
     if (!attr_set) {
-        SB_CUDA(cudaFuncSetAttribute(k_forward_quad<S, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SB_CUDA(cudaFuncSetAttribute(k_forward_quad<S, MODE, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
-    k_forward_quad<S, MODE><<<(unsigned)rows, Cfg<14>::T, smem, c.stream>>>(
+    k_forward_quad<S, MODE, FMT><<<(unsigned)rows, Cfg<14>::T, smem, c.stream>>>(
         static_cast<const S*>(src->d_raw), src->n, src->d_pfx, d_desc, q_begin, q_end, row_first, tab,
         reinterpret_cast<float4*>(out));
     SB_CUDA(cudaGetLastError());
@@ -1343,7 +1441,7 @@ int ensure_item_query(int64_t n) {
 // Launchers of the three match kernels.  `Kernel` is one instantiation (sample type x epilogue variant); its
 // dynamic shared memory limit is raised once.  The uint8 kernels exist with both epilogues (Ctx::epilogue),
 // float32 streams have the first one only.
-template <typename S, int EPI>
+template <typename S, int EPI, int FMT>
 int launch_packed_typed(const sb_stream* image, const sb_stream* tmpl, const float2* d_parts, int64_t part_first,
                         const QueryDesc* d_desc, int64_t item_first, int64_t n_items, const PackedTables& tab,
                         unsigned long long* d_keys, float* d_curve) {
@@ -1351,13 +1449,13 @@ int launch_packed_typed(const sb_stream* image, const sb_stream* tmpl, const flo
     static bool attr_set = false;
     const size_t smem = packed_smem_bytes(EPI);
     if (!attr_set) {
-        SB_CUDA(cudaFuncSetAttribute(k_match_packed<S, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SB_CUDA(cudaFuncSetAttribute(k_match_packed<S, EPI, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
     const int64_t max_grid = 1 << 30;
     for (int64_t i0 = 0; i0 < n_items; i0 += max_grid) {
         const int64_t ni = std::min<int64_t>(max_grid, n_items - i0);
-        k_match_packed<S, EPI><<<(unsigned)ni, QT, smem, c.stream>>>(
+        k_match_packed<S, EPI, FMT><<<(unsigned)ni, QT, smem, c.stream>>>(
             reinterpret_cast<const float4*>(d_parts), part_first, reinterpret_cast<const float4*>(image->d_specq), image->nblkq,
             static_cast<const S*>(image->d_raw), image->n, image->d_pfx, tmpl->d_pfx, d_desc, g_item_query2 + i0, item_first + i0,
             tab, d_keys, d_curve);
@@ -1366,7 +1464,7 @@ int launch_packed_typed(const sb_stream* image, const sb_stream* tmpl, const flo
     return SB_OK;
 }
 
-template <typename S, int EPI>
+template <typename S, int EPI, int FMT>
 int launch_pair_typed(const sb_stream* image, const sb_stream* tmpl, const float2* d_parts, int64_t part_first,
                       const QueryDesc* d_desc, int64_t pair_first, int64_t n_pairs, const PackedTables& tab,
                       unsigned long long* d_keys, float* d_curve) {
@@ -1374,10 +1472,10 @@ int launch_pair_typed(const sb_stream* image, const sb_stream* tmpl, const float
     static bool attr_set = false;
     const size_t smem = packed_smem_bytes(EPI) + 16;
     if (!attr_set) {
-        SB_CUDA(cudaFuncSetAttribute(k_match_pair<S, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SB_CUDA(cudaFuncSetAttribute(k_match_pair<S, EPI, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
-    k_match_pair<S, EPI><<<(unsigned)n_pairs, QT, smem, c.stream>>>(
+    k_match_pair<S, EPI, FMT><<<(unsigned)n_pairs, QT, smem, c.stream>>>(
         reinterpret_cast<const float4*>(d_parts), part_first, reinterpret_cast<const float4*>(image->d_specq), image->nblkq,
         static_cast<const S*>(image->d_raw), image->n, image->d_pfx, tmpl->d_pfx, d_desc, g_item_query2, pair_first,
         tab, d_keys, d_curve);
@@ -1385,7 +1483,7 @@ int launch_pair_typed(const sb_stream* image, const sb_stream* tmpl, const float
     return SB_OK;
 }
 
-template <typename S, int EPI>
+template <typename S, int EPI, int FMT>
 int launch_triple_typed(const sb_stream* image, const sb_stream* tmpl, const float2* d_parts, int64_t part_first,
                         const QueryDesc* d_desc, int64_t trip_first, int64_t n_trips, const PackedTables& tab,
                         unsigned long long* d_keys, float* d_curve) {
@@ -1393,16 +1491,24 @@ int launch_triple_typed(const sb_stream* image, const sb_stream* tmpl, const flo
     static bool attr_set = false;
     const size_t smem = packed_smem_bytes(EPI) + 16;
     if (!attr_set) {
-        SB_CUDA(cudaFuncSetAttribute(k_match_triple<S, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SB_CUDA(cudaFuncSetAttribute(k_match_triple<S, EPI, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
-    k_match_triple<S, EPI><<<(unsigned)n_trips, QT, smem, c.stream>>>(
+    k_match_triple<S, EPI, FMT><<<(unsigned)n_trips, QT, smem, c.stream>>>(
         reinterpret_cast<const float4*>(d_parts), part_first, reinterpret_cast<const float4*>(image->d_specq), image->nblkq,
         static_cast<const S*>(image->d_raw), image->n, image->d_pfx, tmpl->d_pfx, d_desc, g_item_query2, trip_first,
         tab, d_keys, d_curve);
     SB_CUDA(cudaGetLastError());
     return SB_OK;
 }
+
+// One instantiation per (sample type, epilogue, row format): float32 streams have epilogue 1 only; the row format
+// is the one the image stream's quad rows were built in (run_batch keeps it equal to Ctx::spectra_fmt, in which
+// the template partition rows of the batch are built).
+#define SB_DISPATCH_MATCH(FN, image, ...) \
+    ((image)->dtype != SB_U8 ? ((image)->specqFmt ? FN<float, 1, 1>(image, __VA_ARGS__) : FN<float, 1, 0>(image, __VA_ARGS__)) \
+     : ctx().epilogue == 2   ? ((image)->specqFmt ? FN<uint8_t, 2, 1>(image, __VA_ARGS__) : FN<uint8_t, 2, 0>(image, __VA_ARGS__)) \
+                             : ((image)->specqFmt ? FN<uint8_t, 1, 1>(image, __VA_ARGS__) : FN<uint8_t, 1, 0>(image, __VA_ARGS__)))
 
 template <typename S>
 int launch_ws_typed(const sb_stream* image, const sb_stream* tmpl, const float2* d_parts, int64_t part_first,
@@ -1439,11 +1545,7 @@ int launch_match_packed(const sb_stream* image, const sb_stream* tmpl, const flo
     SB_TRY(ensure_item_query(n_items));
     k_fill_item_query2<<<(unsigned)(q_end - q_begin), 128, 0, c.stream>>>(d_desc, q_begin, item_first, g_item_query2);
     c.launches += 1;
-    if (image->dtype != SB_U8)
-        return launch_packed_typed<float, 1>(image, tmpl, d_parts, part_first, d_desc, item_first, n_items, tab, d_keys, d_curve);
-    return c.epilogue == 2
-        ? launch_packed_typed<uint8_t, 2>(image, tmpl, d_parts, part_first, d_desc, item_first, n_items, tab, d_keys, d_curve)
-        : launch_packed_typed<uint8_t, 1>(image, tmpl, d_parts, part_first, d_desc, item_first, n_items, tab, d_keys, d_curve);
+    return SB_DISPATCH_MATCH(launch_packed_typed, image, tmpl, d_parts, part_first, d_desc, item_first, n_items, tab, d_keys, d_curve);
 }
 
 int launch_match_ws(const sb_stream* image, const sb_stream* tmpl, const float2* d_parts, int64_t part_first,
@@ -1469,11 +1571,7 @@ int launch_match_pair(const sb_stream* image, const sb_stream* tmpl, const float
     SB_TRY(ensure_item_query(n_pairs));
     k_fill_pair_query<<<(unsigned)(q_end - q_begin), 128, 0, c.stream>>>(d_desc, q_begin, pair_first, g_item_query2, 2);
     c.launches += 1;
-    if (image->dtype != SB_U8)
-        return launch_pair_typed<float, 1>(image, tmpl, d_parts, part_first, d_desc, pair_first, n_pairs, tab, d_keys, d_curve);
-    return c.epilogue == 2
-        ? launch_pair_typed<uint8_t, 2>(image, tmpl, d_parts, part_first, d_desc, pair_first, n_pairs, tab, d_keys, d_curve)
-        : launch_pair_typed<uint8_t, 1>(image, tmpl, d_parts, part_first, d_desc, pair_first, n_pairs, tab, d_keys, d_curve);
+    return SB_DISPATCH_MATCH(launch_pair_typed, image, tmpl, d_parts, part_first, d_desc, pair_first, n_pairs, tab, d_keys, d_curve);
 }
 
 int launch_match_triple(const sb_stream* image, const sb_stream* tmpl, const float2* d_parts, int64_t part_first,
@@ -1485,22 +1583,24 @@ int launch_match_triple(const sb_stream* image, const sb_stream* tmpl, const flo
     SB_TRY(ensure_item_query(n_trips));
     k_fill_pair_query<<<(unsigned)(q_end - q_begin), 128, 0, c.stream>>>(d_desc, q_begin, trip_first, g_item_query2, 3);
     c.launches += 1;
-    if (image->dtype != SB_U8)
-        return launch_triple_typed<float, 1>(image, tmpl, d_parts, part_first, d_desc, trip_first, n_trips, tab, d_keys, d_curve);
-    return c.epilogue == 2
-        ? launch_triple_typed<uint8_t, 2>(image, tmpl, d_parts, part_first, d_desc, trip_first, n_trips, tab, d_keys, d_curve)
-        : launch_triple_typed<uint8_t, 1>(image, tmpl, d_parts, part_first, d_desc, trip_first, n_trips, tab, d_keys, d_curve);
+    return SB_DISPATCH_MATCH(launch_triple_typed, image, tmpl, d_parts, part_first, d_desc, trip_first, n_trips, tab, d_keys, d_curve);
 }
 
-int launch_block_spectra_quad(const sb_stream* s, int64_t k_first, int64_t rows, float2* out) {
-    return s->dtype == SB_U8 ? launch_forward_quad_typed<uint8_t, 0>(s, nullptr, 0, 0, k_first, rows, out)
-                             : launch_forward_quad_typed<float, 0>(s, nullptr, 0, 0, k_first, rows, out);
+int launch_block_spectra_quad(const sb_stream* s, int64_t k_first, int64_t rows, float2* out, int fmt) {
+    if (fmt)
+        return s->dtype == SB_U8 ? launch_forward_quad_typed<uint8_t, 0, 1>(s, nullptr, 0, 0, k_first, rows, out)
+                                 : launch_forward_quad_typed<float, 0, 1>(s, nullptr, 0, 0, k_first, rows, out);
+    return s->dtype == SB_U8 ? launch_forward_quad_typed<uint8_t, 0, 0>(s, nullptr, 0, 0, k_first, rows, out)
+                             : launch_forward_quad_typed<float, 0, 0>(s, nullptr, 0, 0, k_first, rows, out);
 }
 
 int launch_part_spectra_quad(const sb_stream* tmpl, const QueryDesc* d_desc, int q_begin, int q_end,
-                             int64_t part_first, int64_t rows, float2* out) {
-    return tmpl->dtype == SB_U8 ? launch_forward_quad_typed<uint8_t, 1>(tmpl, d_desc, q_begin, q_end, part_first, rows, out)
-                                : launch_forward_quad_typed<float, 1>(tmpl, d_desc, q_begin, q_end, part_first, rows, out);
+                             int64_t part_first, int64_t rows, float2* out, int fmt) {
+    if (fmt)
+        return tmpl->dtype == SB_U8 ? launch_forward_quad_typed<uint8_t, 1, 1>(tmpl, d_desc, q_begin, q_end, part_first, rows, out)
+                                    : launch_forward_quad_typed<float, 1, 1>(tmpl, d_desc, q_begin, q_end, part_first, rows, out);
+    return tmpl->dtype == SB_U8 ? launch_forward_quad_typed<uint8_t, 1, 0>(tmpl, d_desc, q_begin, q_end, part_first, rows, out)
+                                : launch_forward_quad_typed<float, 1, 0>(tmpl, d_desc, q_begin, q_end, part_first, rows, out);
 }
 
 void packed_release_tables() {

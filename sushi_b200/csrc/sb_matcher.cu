@@ -470,6 +470,8 @@ int run_batch(const sb_stream* image_c, const sb_stream* tmpl, int64_t count,
         for (int64_t q = 0; q < n_direct; ++q) { rows += (double)c.h_desc[q].nk * c.h_desc[q].P; blocks += (double)c.h_desc[q].nk; }
         use_pairs = rows >= 1.5 * blocks;
     }
+    if (use_packed && c.engine == 3 && c.spectra_fmt != 0)
+        SB_FAIL(SB_EINVAL, "engine 3 (warp-specialised kernel) reads float32 spectrum rows only: sb_set_spectra(0) or another engine");
     if (use_packed && n_direct > 0) SB_TRY(ensure_spectra_quad(image));
     if (!use_packed || n_direct < count) SB_TRY(ensure_spectra(image, hd));
 
@@ -480,7 +482,9 @@ int run_batch(const sb_stream* image_c, const sb_stream* tmpl, int64_t count,
     SB_CUDA(cudaMemsetAsync(c.d_keys, 0xff, sizeof(unsigned long long) * count, c.stream));
 
     const int64_t parts_cap_want = std::max<int64_t>(std::min<int64_t>(total_parts, c.max_parts), maxp);
-    SB_TRY(grow(&c.d_parts, &c.parts_cap, parts_cap_want * (use_packed ? kQuadRowF2 : nb)));
+    // float2 per template partition row: quad layout (float32 or 16-bit block floating point) or classic
+    const int64_t part_row_f2 = use_packed ? (c.spectra_fmt ? kQuad16RowF2 : kQuadRowF2) : nb;
+    SB_TRY(grow(&c.d_parts, &c.parts_cap, parts_cap_want * part_row_f2));
     const int64_t chunk = std::min<int64_t>(c.chunk_items, total_items);
     if (!use_fused) SB_TRY(grow(&c.d_items, &c.items_cap, chunk * nb));
     // lag blocks per product buffer (0.5 GB at B = 16384); SB_PREMAC_CHUNK overrides it for experiments
@@ -504,7 +508,7 @@ int run_batch(const sb_stream* image_c, const sb_stream* tmpl, int64_t count,
         const int64_t sub = 4096;
         if (use_packed && !premac) {
             ProfScope ps("part_spectra");
-            SB_TRY(launch_part_spectra_quad(tmpl, c.d_desc, (int)qb, (int)qe, part_first, np, c.d_parts));
+            SB_TRY(launch_part_spectra_quad(tmpl, c.d_desc, (int)qb, (int)qe, part_first, np, c.d_parts, c.spectra_fmt));
         } else if (use_fused) {                      // hand-written gather + forward FFT, one launch
             ProfScope ps("part_spectra");
             SB_TRY(launch_part_spectra(tmpl, hd, c.d_desc, (int)qb, (int)qe, part_first, np, c.d_parts));

@@ -14,12 +14,12 @@ extern "C" {
 int emu_table_floats(void) { size_t off[4]; return (int)packed_table_values(off).size(); }
 int emu_smem_bytes(void) { return (int)packed_smem_bytes() + 16; }
 int emu_query_desc_bytes(void) { return (int)sizeof(sb::QueryDesc); }
-int emu_quad_row_floats(void) { return QROW * 4; }
+int emu_quad_row_floats(int fmt) { return (fmt ? QROW16 : QROW) * 4; }
 
 // kernel: 0 = k_match_packed (one CTA per lag block), 1 = k_match_pair, 2 = k_match_triple; epi: 1 | 2;
-// is_u8: sample type of img.  Runs CTAs [0, n_ctas) one after the other.  Returns 0, or the number of
-// emulation errors (messages on stderr).
-int emu_run(int kernel, int epi, int is_u8, const float* That, int64_t part_first, const float* Xhat, int64_t nblk,
+// is_u8: sample type of img; fmt: row format of That / Xhat (0 float32, 1 16-bit block floating point).  Runs CTAs
+// [0, n_ctas) one after the other.  Returns 0, or the number of emulation errors (messages on stderr).
+int emu_run(int kernel, int epi, int is_u8, int fmt, const float* That, int64_t part_first, const float* Xhat, int64_t nblk,
             const void* img, int64_t img_n, const double* ipfx, const double* tpfx, const void* desc,
             const int* cta_query, int64_t first, int n_ctas, unsigned long long* keys, float* curve_out) {
     static size_t off[4];
@@ -40,7 +40,8 @@ int emu_run(int kernel, int epi, int is_u8, const float* That, int64_t part_firs
             threadIdx = {(unsigned)t, 0, 0};
             blockIdx = {(unsigned)b, 0, 0};
             emu::t_lane = t & 31; emu::t_warp = t >> 5;
-#define SB_EMU_CALL(K, S, E) K<S, E>(T4, part_first, X4, nblk, static_cast<const S*>(img), img_n, ip, tp, d, cta_query, first, tab, keys, curve_out)
+#define SB_EMU_CALL(K, S, E) do { if (fmt) K<S, E, 1>(T4, part_first, X4, nblk, static_cast<const S*>(img), img_n, ip, tp, d, cta_query, first, tab, keys, curve_out); \
+                                  else K<S, E, 0>(T4, part_first, X4, nblk, static_cast<const S*>(img), img_n, ip, tp, d, cta_query, first, tab, keys, curve_out); } while (0)
 #define SB_EMU_KERNEL(K) do { if (!is_u8) SB_EMU_CALL(K, float, 1); else if (epi == 2) SB_EMU_CALL(K, uint8_t, 2); else SB_EMU_CALL(K, uint8_t, 1); } while (0)
             if (kernel == 0) SB_EMU_KERNEL(k_match_packed);
             else if (kernel == 1) SB_EMU_KERNEL(k_match_pair);

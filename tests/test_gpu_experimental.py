@@ -9,7 +9,10 @@ the lags that get the exact fp64 evaluation, so every result must equal the firs
 whole curves included (the debug curve path evaluates every lag exactly under both variants).
 
 sb_set_engine(6): one CTA per triple of consecutive lag blocks (two product spectra parked in tensor memory).
-Same arithmetic in the same order as engines 4 / 5, so again bit for bit."""
+Same arithmetic in the same order as engines 4 / 5, so again bit for bit.
+
+sb_set_spectra(1): spectrum rows as 16-bit block floating point.  Not bit-identical: the quantisation moves the
+curve by ~1e-6; the kernels still agree with each other bit for bit on the same rows."""
 import os
 
 import numpy as np
@@ -30,6 +33,7 @@ def epilogue(gpu_lib):
     yield use
     _native.check(gpu_lib.sb_set_engine(2))
     _native.check(gpu_lib.sb_set_epilogue(1))
+    _native.check(gpu_lib.sb_set_spectra(0))
 
 
 def _streams(dur, seed, stype='uint8'):
@@ -130,3 +134,39 @@ def test_triples_are_bit_identical_to_single_lag_blocks(gpu_lib, epilogue, stype
         epilogue(variant, engine)
         res[engine] = dst.find_substream_batch(src, starts, ends, starts, win)
     assert np.array_equal(res[5][0], res[6][0]) and np.array_equal(res[5][1], res[6][1])
+
+
+@pytest.mark.parametrize('stype', ['uint8', 'float32'])
+def test_16bit_spectrum_rows(gpu_lib, epilogue, stype):
+    """Whole curves and batch results on 16-bit block floating point rows against float32 rows (<= 2e-6), the
+    oracle (north_star's tolerances) and across the kernels (bit for bit)."""
+    rs, rd, src, dst = _streams(120.0, 13, stype)
+    cases = [(6000, 11400, 0, 16384), (6000, 20000, 100, 2 * 16384), (100, 48000, 16384, 3 * 16384), (40000, 3000, 16383, 5 * 16384 + 2),
+             (200000, 6000, 150000, 140001)]
+    starts, ends = synth.make_events(150, 120.0, 14, 0.5, 5.0)
+    win = np.full(len(starts), 20.0)
+    epilogue(1, 5)
+    _native.check(gpu_lib.sb_set_spectra(0))
+    base_curves = [dst.match_curve(src, *c) for c in cases]
+    base = dst.find_substream_batch(src, starts, ends, starts, win)
+    ref = None
+    for engine, variant in ((5, 1), (4, 2), (6, 2), (2, 1)):
+        epilogue(variant, engine)
+        _native.check(gpu_lib.sb_set_spectra(1))
+        assert gpu_lib.sb_get_spectra() == 1
+        curves = [dst.match_curve(src, *c) for c in cases]
+        res = dst.find_substream_batch(src, starts, ends, starts, win)
+        for c, cur, b in zip(cases, curves, base_curves):
+            assert np.abs(cur - b).max() <= 2e-6, c
+            toff, n, lag0, nlags = c
+            want = rd.match_curve(rs.data[:, toff:toff + n], lag0, nlags)
+            assert np.abs(cur - want).max() <= 1e-5 and abs(int(cur.argmin()) - int(want.argmin())) <= 1
+        assert np.abs(res[0] - base[0]).max() <= 2e-6 and np.abs(res[1] - base[1]).max() <= 1.0 / 12000 + 1e-9
+        ref = ref or (curves, res)
+        assert all(np.array_equal(a, b) for a, b in zip(ref[0], curves))
+        assert np.array_equal(ref[1][0], res[0]) and np.array_equal(ref[1][1], res[1])
+    # switching back rebuilds the float32 rows: bit-identical to before
+    epilogue(1, 5)
+    _native.check(gpu_lib.sb_set_spectra(0))
+    again = dst.find_substream_batch(src, starts, ends, starts, win)
+    assert np.array_equal(again[0], base[0]) and np.array_equal(again[1], base[1])

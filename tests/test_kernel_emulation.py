@@ -60,9 +60,12 @@ def qa(i):
     return (i >> 8) * 512 + (i & 255) if i < Q4 else 2 * Q4
 
 
-def quad_rows(blocks, row_floats):
-    """blocks: (rows, 2B) real -> rows in the quad layout of sb_fused2.cu (float32)."""
+def quad_rows(blocks, row_floats, fmt=0):
+    """blocks: (rows, 2B) real -> rows in the quad layout of sb_fused2.cu (fmt 0: float32; fmt 1: 16-bit block
+    floating point, the way k_forward_quad's store_quad16 writes them)."""
     X = np.fft.rfft(blocks.astype(np.float64), axis=1)          # bins 0 .. B
+    if fmt == 1:
+        return quad_rows16(X.astype(np.complex64), row_floats)
     out = aligned(blocks.shape[0] * row_floats, np.float32).reshape(blocks.shape[0], row_floats // 4, 4)
     i = np.arange(Q4 + 1)
     pa = np.array([qa(int(v)) for v in i])
@@ -70,6 +73,36 @@ def quad_rows(blocks, row_floats):
     out[:, pa, 0], out[:, pa, 1], out[:, pa, 2], out[:, pa, 3] = X[:, i].real, X[:, i + B // 2].real, X[:, i].imag, X[:, i + B // 2].imag
     out[:, pm, 0], out[:, pm, 1], out[:, pm, 2], out[:, pm, 3] = X[:, B - i].real, X[:, B // 2 - i].real, X[:, B - i].imag, X[:, B // 2 - i].imag
     return out.reshape(blocks.shape[0], row_floats)
+
+
+def quad_rows16(X, row_floats):
+    """Unit i (16 bytes): int16 x 8 = (re X[i], re X[i+B/2]), (im X[i], im X[i+B/2]), (re X[B-i], re X[B/2-i]), (im, im);
+    unit Q4+1+g: float32 x 4 = scales of the four bin families over quads 8g .. 8g+7 (the last quad alone)."""
+    rows = X.shape[0]
+    raw = aligned(rows * row_floats, np.float32).reshape(rows, row_floats)
+    i = np.arange(Q4 + 1)
+    fam = [X[:, i], X[:, i + B // 2], X[:, B - i], X[:, B // 2 - i]]               # (rows, Q4+1) complex64 each
+    grp = np.minimum(i >> 3, Q4 >> 3)
+    grp[Q4] = Q4 >> 3
+    ngrp = (Q4 >> 3) + 1
+    q16 = np.zeros((rows, Q4 + 1, 8), np.int16)
+    scales = np.zeros((rows, ngrp, 4), np.float32)
+    for f, Z in enumerate(fam):
+        comp = np.maximum(np.abs(Z.real), np.abs(Z.imag)).astype(np.float32)
+        mx = np.zeros((rows, ngrp), np.float32)
+        np.maximum.at(mx, (np.arange(rows)[:, None], grp[None, :]), comp)
+        with np.errstate(divide='ignore'):
+            inv = np.where(mx > 0, np.float32(32767.0) / mx, np.float32(0)).astype(np.float32)
+        scales[:, :, f] = mx / np.float32(32767.0)
+        re = np.clip(np.rint(Z.real.astype(np.float32) * inv[:, grp]), -32767, 32767).astype(np.int16)
+        im = np.clip(np.rint(Z.imag.astype(np.float32) * inv[:, grp]), -32767, 32767).astype(np.int16)
+        # component slots: family 0 -> 0 (re), 2 (im); 1 -> 1, 3; 2 -> 4, 6; 3 -> 5, 7
+        q16[:, :, [0, 1, 4, 5][f]] = re
+        q16[:, :, [2, 3, 6, 7][f]] = im
+    raw16 = raw.view(np.int16).reshape(rows, row_floats * 2)
+    raw16[:, :(Q4 + 1) * 8] = q16.reshape(rows, -1)
+    raw[:, (Q4 + 1) * 4:(Q4 + 1) * 4 + ngrp * 4] = scales.reshape(rows, -1)
+    return raw
 
 
 def prefix_sums(x):
@@ -82,9 +115,9 @@ def prefix_sums(x):
 class Case(object):
     """One image stream, one template stream, a list of queries (toff, n, lag0, nlags)."""
 
-    def __init__(self, lib, img, src, queries, dtype):
-        self.lib, self.queries, self.dtype = lib, queries, dtype
-        rf = lib.emu_quad_row_floats()
+    def __init__(self, lib, img, src, queries, dtype, fmt=0):
+        self.lib, self.queries, self.dtype, self.fmt = lib, queries, dtype, fmt
+        rf = lib.emu_quad_row_floats(fmt)
         n_img = img.size
         self.img = aligned(n_img + 64, dtype)
         self.img[:n_img] = img
@@ -97,7 +130,7 @@ class Case(object):
         for k in range(self.nblk):
             seg = img[k * B:k * B + 2 * B].astype(np.float64)
             blocks[k, :seg.size] = seg - a
-        self.Xhat = quad_rows(blocks, rf)
+        self.Xhat = quad_rows(blocks, rf, fmt)
         parts = []
         for (toff, n, lag0, nlags) in queries:
             t = src[toff:toff + n].astype(np.float64)
@@ -107,7 +140,7 @@ class Case(object):
                 seg = t[p * B:(p + 1) * B]
                 row[:seg.size] = seg - b
                 parts.append(row)
-        self.That = quad_rows(np.array(parts), rf)
+        self.That = quad_rows(np.array(parts), rf, fmt)
         self.src = src
 
     def run(self, kernel, epi, curves):
@@ -131,7 +164,7 @@ class Case(object):
         keys = np.full(len(self.queries), 0xffffffffffffffff, np.uint64)
         cur = np.full(curve, np.nan, np.float32) if curves else None
         vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
-        rc = self.lib.emu_run(kernel, epi, int(self.dtype == np.uint8), vp(self.That), ctypes.c_int64(0), vp(self.Xhat), ctypes.c_int64(self.nblk),
+        rc = self.lib.emu_run(kernel, epi, int(self.dtype == np.uint8), self.fmt, vp(self.That), ctypes.c_int64(0), vp(self.Xhat), ctypes.c_int64(self.nblk),
                               vp(self.img), ctypes.c_int64(self.n_img), vp(self.ipfx), vp(self.tpfx), ctypes.byref(desc), vp(cta_query),
                               ctypes.c_int64(0), len(cta_query), vp(keys), vp(cur) if curves else None)
         assert rc == 0, 'emulation reported %d errors (see stderr)' % rc
@@ -227,3 +260,29 @@ def test_emulated_float32_stream(emu):
         assert np.abs(cur - t).max() <= 3e-6 and i[0] == int(cur.argmin()) == 20300 - 5
         ref = ref or (d, i, cur)
         assert np.array_equal(ref[2], cur) and ref[0][0] == d[0]
+
+
+def test_emulated_16bit_block_floating_point_rows(emu, case_u8):
+    """sb_set_spectra(1): the same kernels on int16 rows with per-group scales.  Results move by the quantisation
+    (~5e-7 of the curve), so the comparison with the float32 rows and the closed form is by tolerance; the three
+    kernels and both epilogues still agree bit for bit with each other."""
+    c0 = case_u8
+    c1 = Case(emu, c0.img[:c0.n_img].copy(), c0.src, c0.queries, np.uint8, fmt=1)
+    truth = c0.truth()
+    d0, i0, cur0 = c0.run(1, 1, curves=True)
+    ref = None
+    for kernel, epi in ((0, 1), (1, 2), (2, 1), (2, 2)):
+        d, i, cur = c1.run(kernel, epi, curves=True)
+        d_s, i_s, _ = c1.run(kernel, epi, curves=False)
+        assert np.array_equal(d, d_s) and np.array_equal(i, i_s)
+        off = 0
+        for t in truth:
+            got = cur[off:off + t.size]
+            assert np.abs(got - t).max() <= 3e-6 and np.abs(got - cur0[off:off + t.size]).max() <= 2e-6
+            off += t.size
+        assert np.abs(i - i0).max() <= 1 and np.abs(d - d0).max() <= 2e-6
+        ref = ref or (d, i, cur)
+        assert np.array_equal(ref[0], d) and np.array_equal(ref[1], i) and np.array_equal(ref[2], cur)
+    err = np.abs(ref[2] - np.concatenate(truth)).max()
+    err0 = np.abs(cur0 - np.concatenate(truth)).max()
+    print('max |curve - fp64 closed form|: float32 rows %.2e, 16-bit rows %.2e' % (err0, err))

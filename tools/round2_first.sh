@@ -8,7 +8,8 @@ timeout 400 python -m pytest tests -x -q -m gpu > $O/pytest_gpu.txt 2>&1; tail -
 SB_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_experimental.py -q -m gpu > $O/pytest_experimental.txt 2>&1; tail -15 $O/pytest_experimental.txt
 B="--steps 10 --warmup 3 --no-cpu-baseline"
 for v in "engine4_epi1 --engine 4 --epilogue 1" "engine4_epi2 --engine 4 --epilogue 2" "engine5_epi2 --engine 5 --epilogue 2" \
-         "engine6_epi1 --engine 6 --epilogue 1" "engine6_epi2 --engine 6 --epilogue 2"; do
+         "engine6_epi1 --engine 6 --epilogue 1" "engine6_epi2 --engine 6 --epilogue 2" \
+         "engine4_epi1_bfp --engine 4 --epilogue 1 --spectra 1" "engine6_epi2_bfp --engine 6 --epilogue 2 --spectra 1" "engine5_epi2_bfp --engine 5 --epilogue 2 --spectra 1"; do
     set -- $v; name=$1; shift
     timeout 90 python bench.py $B "$@" > $O/bench_r2_$name.json 2> $O/bench_r2_$name.err
     python - "$O/bench_r2_$name.json" "$name" <<'PY'
