@@ -57,6 +57,58 @@ int emu_run(int kernel, int epi, int is_u8, int fmt, const float* That, int64_t 
     return n_err;
 }
 
+// Block spectra of a stream (k_forward_quad, MODE 0) in either row format: rows [row_first, row_first + rows) into
+// `out` (rows * emu_quad_row_floats(fmt) floats).  The twiddle tables are the ones sb_fused.cu's ensure_tables<14>
+// builds.
+int emu_forward_blocks(int is_u8, int fmt, const void* src, int64_t src_n, const double* pfx, int64_t row_first, int rows, float* out) {
+    typedef Cfg<14> C;
+    static std::vector<float2> h;
+    static FusedTables tab;
+    if (h.empty()) {
+        const int N = C::N;
+        const size_t nw = N / 2 + 1, n2 = (size_t)C::R2 * 32, n3 = (size_t)C::R3 * 32;
+        h.resize(nw + n2 + 2 * n3);
+        const double pi = 3.14159265358979323846;
+        for (size_t m = 0; m < nw; ++m) h[m] = make_float2((float)cos(pi * m / N), (float)sin(pi * m / N));
+        for (int r = 0; r < C::R2; ++r)
+            for (int k = 0; k < 32; ++k) {
+                const double ang = 2.0 * pi * r * k / (32.0 * C::R2);
+                h[nw + r * 32 + k] = make_float2((float)cos(ang), (float)sin(ang));
+            }
+        for (int r = 0; r < C::R3; ++r)
+            for (int k = 0; k < 32; ++k) {
+                const double al = 2.0 * pi * r * k / N, ah = 2.0 * pi * r * (k * 32.0) / N;
+                h[nw + n2 + r * 32 + k] = make_float2((float)cos(al), (float)sin(al));
+                h[nw + n2 + n3 + r * 32 + k] = make_float2((float)cos(ah), (float)sin(ah));
+            }
+        tab.w = h.data(); tab.t2 = h.data() + nw; tab.a3 = h.data() + nw + n2; tab.b3 = h.data() + nw + n2 + n3;
+    }
+    const double2* pf = reinterpret_cast<const double2*>(pfx);
+    float4* o4 = reinterpret_cast<float4*>(out);
+    int n_err = 0;
+    for (int b = 0; b < rows; ++b) {
+        emu::Cta cta;
+        emu::cta() = &cta;
+        std::memset(smem_raw, 0xCD, sizeof(smem_raw));
+        auto body = [&](int t) {
+            threadIdx = {(unsigned)t, 0, 0};
+            blockIdx = {(unsigned)b, 0, 0};
+            emu::t_lane = t & 31; emu::t_warp = t >> 5;
+            if (is_u8) { if (fmt) k_forward_quad<uint8_t, 0, 1>(static_cast<const uint8_t*>(src), src_n, pf, nullptr, 0, 0, row_first, tab, o4);
+                         else     k_forward_quad<uint8_t, 0, 0>(static_cast<const uint8_t*>(src), src_n, pf, nullptr, 0, 0, row_first, tab, o4); }
+            else       { if (fmt) k_forward_quad<float, 0, 1>(static_cast<const float*>(src), src_n, pf, nullptr, 0, 0, row_first, tab, o4);
+                         else     k_forward_quad<float, 0, 0>(static_cast<const float*>(src), src_n, pf, nullptr, 0, 0, row_first, tab, o4); }
+        };
+        std::vector<std::thread> th;
+        th.reserve(emu::kThreads);
+        for (int t = 0; t < emu::kThreads; ++t) th.emplace_back(body, t);
+        for (auto& x : th) x.join();
+        for (const auto& e : cta.errors) { std::fprintf(stderr, "[emu] forward CTA %d: %s\n", b, e.c_str()); ++n_err; }
+        emu::cta() = nullptr;
+    }
+    return n_err;
+}
+
 }  // extern "C"
 
 #ifdef SB_EMU_DEBUG      // g++ ... -DSB_EMU_DEBUG -g -rdynamic: backtrace of the faulting thread on SIGSEGV

@@ -286,3 +286,32 @@ def test_emulated_16bit_block_floating_point_rows(emu, case_u8):
     err = np.abs(ref[2] - np.concatenate(truth)).max()
     err0 = np.abs(cur0 - np.concatenate(truth)).max()
     print('max |curve - fp64 closed form|: float32 rows %.2e, 16-bit rows %.2e' % (err0, err))
+
+
+def test_emulated_forward_kernel_writes_both_row_formats(emu, case_u8):
+    """k_forward_quad (block spectra of a stream) in emulation against the NumPy rows the other tests feed the match
+    kernels: float32 rows agree to fp32 FFT rounding; 16-bit rows carry the same scales and integers (+-1 where the
+    two float32 spectra straddle a rounding boundary), and matching on the kernel's own rows gives the same answer."""
+    c = case_u8
+    vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    rows = {}
+    for fmt in (0, 1):
+        rf = emu.emu_quad_row_floats(fmt)
+        out = aligned(c.nblk * rf, np.float32)
+        assert emu.emu_forward_blocks(1, fmt, vp(c.img), ctypes.c_int64(c.n_img), vp(c.ipfx), ctypes.c_int64(0), c.nblk, vp(out)) == 0
+        rows[fmt] = out.reshape(c.nblk, rf)
+    used = 2 * Q4 + 2
+    want0 = c.Xhat[:, :used * 4]
+    scale = np.abs(want0).max()
+    assert np.abs(rows[0][:, :used * 4] - want0).max() <= 2e-6 * scale
+    c1 = Case(emu, c.img[:c.n_img].copy(), c.src, c.queries, np.uint8, fmt=1)
+    n16 = (Q4 + 1) * 8
+    got_q, want_q = rows[1].view(np.int16)[:, :n16].astype(np.int32), c1.Xhat.view(np.int16)[:, :n16].astype(np.int32)
+    assert np.abs(got_q - want_q).max() <= 1 and np.mean(got_q != want_q) < 0.02
+    ns = ((Q4 >> 3) + 1) * 4
+    got_s, want_s = rows[1][:, (Q4 + 1) * 4:(Q4 + 1) * 4 + ns], c1.Xhat[:, (Q4 + 1) * 4:(Q4 + 1) * 4 + ns]
+    assert np.abs(got_s - want_s).max() <= 2e-6 * np.abs(want_s).max()
+    d_ref, i_ref, _ = c1.run(2, 2, curves=False)
+    c1.Xhat = rows[1]
+    d, i, _ = c1.run(2, 2, curves=False)
+    assert np.array_equal(i, i_ref) and np.abs(d - d_ref).max() <= 1e-6
