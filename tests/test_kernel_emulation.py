@@ -315,3 +315,37 @@ def test_emulated_forward_kernel_writes_both_row_formats(emu, case_u8):
     c1.Xhat = rows[1]
     d, i, _ = c1.run(2, 2, curves=False)
     assert np.array_equal(i, i_ref) and np.abs(d - d_ref).max() <= 1e-6
+
+
+def test_emulated_edge_geometry(emu):
+    """Templates of 3, B and B + 1 samples, ranges of a single lag, ranges whose first / last lag is a block's first
+    / last lag, the last lags of the stream (staged windows clamped at the end of the allocation): every kernel,
+    both screening loops."""
+    n_img = 3 * B + 777
+    img = programme(n_img, 21)
+    rng = np.random.default_rng(22)
+    src = np.clip(np.roll(img, -50).astype(np.int32) + rng.integers(-3, 4, n_img), 0, 255).astype(np.uint8)
+    queries = [(500, 3, 0, 4000),                              # three samples
+               (1000, B, 900, 300),                            # exactly one partition; match at lag 1050
+               (1000, B + 1, 2 * B - 10, 20),                  # two partitions, the second holds one sample; straddles a block edge
+               (7000, 9000, B, 1),                             # one lag, the first of a block
+               (7000, 9000, 2 * B - 1, 1),                     # one lag, the last of a block
+               (20000, 12000, n_img - 12000 - 5000, 5001),     # up to the last possible lag of the stream
+               (123, 300, 3 * B - 3, 481)]                     # into the short last block, up to the last lag
+    c = Case(emu, img, src, queries, np.uint8)
+    truth = c.truth()
+    ref = None
+    for kernel in (0, 1, 2):
+        for epi in (1, 2):
+            d, i, cur = c.run(kernel, epi, curves=True)
+            d_s, i_s, _ = c.run(kernel, epi, curves=False)
+            assert np.array_equal(d, d_s) and np.array_equal(i, i_s)
+            off = 0
+            for q, t in enumerate(truth):
+                got = cur[off:off + t.size]
+                off += t.size
+                assert np.abs(got - t).max() <= 3e-6, (kernel, epi, q)
+                assert i[q] == int(got.argmin()) and d[q] == got.min()
+            ref = ref or (d, i, cur)
+            assert np.array_equal(ref[0], d) and np.array_equal(ref[1], i) and np.array_equal(ref[2], cur)
+    assert ref[1][1] == 1050 - 900
