@@ -138,7 +138,7 @@ def test_triples_are_bit_identical_to_single_lag_blocks(gpu_lib, epilogue, stype
 
 @pytest.mark.parametrize('stype', ['uint8', 'float32'])
 def test_16bit_spectrum_rows(gpu_lib, epilogue, stype):
-    """Whole curves and batch results on 16-bit block floating point rows against float32 rows (<= 2e-6), the
+    """Whole curves and batch results on 16-bit block floating point rows against float32 rows (<= 4e-6), the
     oracle (north_star's tolerances) and across the kernels (bit for bit)."""
     rs, rd, src, dst = _streams(120.0, 13, stype)
     cases = [(6000, 11400, 0, 16384), (6000, 20000, 100, 2 * 16384), (100, 48000, 16384, 3 * 16384), (40000, 3000, 16383, 5 * 16384 + 2),
@@ -157,11 +157,11 @@ def test_16bit_spectrum_rows(gpu_lib, epilogue, stype):
         curves = [dst.match_curve(src, *c) for c in cases]
         res = dst.find_substream_batch(src, starts, ends, starts, win)
         for c, cur, b in zip(cases, curves, base_curves):
-            assert np.abs(cur - b).max() <= 2e-6, c
+            assert np.abs(cur - b).max() <= 4e-6, c
             toff, n, lag0, nlags = c
             want = rd.match_curve(rs.data[:, toff:toff + n], lag0, nlags)
             assert np.abs(cur - want).max() <= 1e-5 and abs(int(cur.argmin()) - int(want.argmin())) <= 1
-        assert np.abs(res[0] - base[0]).max() <= 2e-6 and np.abs(res[1] - base[1]).max() <= 1.0 / 12000 + 1e-9
+        assert np.abs(res[0] - base[0]).max() <= 4e-6 and np.abs(res[1] - base[1]).max() <= 1.0 / 12000 + 1e-9
         ref = ref or (curves, res)
         assert all(np.array_equal(a, b) for a, b in zip(ref[0], curves))
         assert np.array_equal(ref[1][0], res[0]) and np.array_equal(ref[1][1], res[1])
