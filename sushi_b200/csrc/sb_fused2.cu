@@ -18,14 +18,19 @@
 //  * Twiddles of the packing stage are formed in registers from one per-thread base value, so the 64 KB
 //    table sb_fused.cu streams from L2 for every item is gone; spectrum rows are 128-byte aligned.
 //
-// Three kernels share these pieces:
+// Four kernels share these pieces:
 //   k_match_packed  one CTA per lag block;
 //   k_match_pair    one CTA per pair of consecutive lag blocks of a query: both are multiplied at once (2P+1
 //                   spectrum-row reads instead of 4P), the second product spectrum waits in tensor memory
 //                   while the first is transformed -- the default for templates of two or more partitions;
+//   k_match_triple  the same over three lag blocks (2P+2 reads, two spectra parked; engine 6, opt-in);
 //   k_match_ws      a persistent warp-specialised variant (experimental, engine 3).
-// Values agree with sb_fused.cu / the cuFFT engine to fp32 FFT rounding (~2e-7 of the curve); k_match_packed and
-// k_match_pair agree bit for bit.
+// Values agree with sb_fused.cu / the cuFFT engine to fp32 FFT rounding (~2e-7 of the curve); k_match_packed,
+// k_match_pair and k_match_triple agree bit for bit.
+// Template parameters of the first three: S = sample type of the stream (uint8_t | float); EPI = screening loop
+// of the epilogue (1 = measured default, 2 = trimmed, opt-in: sb_set_epilogue); FMT = format of the spectrum rows
+// (0 = float32, 1 = 16-bit block floating point, opt-in: sb_set_spectra).  EPI = 1, FMT = 0 are the kernels the
+// round-1 measurements were taken with; the other instantiations have only run in the CPU emulation (tests/emu).
 #include "sb_internal.h"
 #include <cmath>
 #include <cstdlib>
