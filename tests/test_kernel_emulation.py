@@ -349,3 +349,31 @@ def test_emulated_edge_geometry(emu):
             ref = ref or (d, i, cur)
             assert np.array_equal(ref[0], d) and np.array_equal(ref[1], i) and np.array_equal(ref[2], cur)
     assert ref[1][1] == 1050 - 900
+
+
+def test_emulated_variants_reproduce_the_reference_golden(emu, golden_matcher):
+    """The reference's own outputs (tests/golden/matcher.npz: find_substream of /root/reference/wav.py over cv2 on
+    12 queries, 10 of them here) through the opt-in variants that have not run on a GPU yet -- one CTA per triple of lag blocks,
+    trimmed screening loop, float32 and 16-bit rows -- within north_star's tolerances: shift +-1 sample, diff 1e-5."""
+    from tests.helpers import oracle_stream_from_pcm
+    g = golden_matcher
+    rs = oracle_stream_from_pcm(g['src_pcm'], 12000, 1, 12000, 'uint8')
+    rd = oracle_stream_from_pcm(g['dst_pcm'], 12000, 1, 12000, 'uint8')
+    clip = lambda v, lo, hi: max(min(v, hi), lo)
+    keep = [q for q in range(len(g['queries'])) if q not in (5, 10)]    # the +-30 s and the 12 s query: minutes of emulation
+    queries, t0s = [], []
+    for (a, b, c, w) in g['queries'][keep]:
+        toff = rs.sample_for_time(a)
+        n = rs.sample_for_time(b) - toff
+        start = clip(c - w, -10, rd.duration_seconds)                 # wav.py:178-182
+        end = clip(c + w, 0, rd.duration_seconds + 10)
+        lag0 = rd.sample_for_time(start)
+        nlags = rd.sample_for_time(end) + n - lag0 - n + 1
+        queries.append((toff, n, lag0, nlags))
+        t0s.append(start)
+    for fmt in (0, 1):
+        case = Case(emu, rd.data[0], rs.data[0], queries, np.uint8, fmt=fmt)
+        d, i, _ = case.run(2, 2, curves=False)
+        times = np.array(t0s) + i / 12000.0
+        assert np.abs(d - g['diff_uint8'][keep]).max() <= 1e-5, (fmt, np.abs(d - g['diff_uint8'][keep]).max())
+        assert np.abs(times - g['time_uint8'][keep]).max() <= 1.0 / 12000 + 1e-9, fmt
