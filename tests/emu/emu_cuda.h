@@ -3,8 +3,9 @@
 //
 // Host stand-ins for the CUDA device environment, so that g++ can compile the kernels of
 // sushi_b200/csrc/sb_fused2.cu unchanged and tests/test_kernel_emulation.py can run their LOGIC on the CPU:
-// one OS thread per CUDA thread of a CTA, std::barrier for bar.sync, a rendezvous per warp for shuffles, plain
-// arrays for shared and tensor memory.  It checks index algebra, bookkeeping (mbarrier phases, tensor-memory
+// the 512 CUDA threads of a CTA as fibers on one OS thread per warp (or as 512 OS threads, -DSB_EMU_THREADS, for
+// ThreadSanitizer), std::barrier for bar.sync, a rendezvous per warp for shuffles, plain arrays for shared and
+// tensor memory.  It checks index algebra, bookkeeping (mbarrier phases, tensor-memory
 // columns, which thread parks what) and the arithmetic of the screening loops; it says nothing about races,
 // memory-model fences, alignment rules of the copy engine or performance -- the GPU tests do that.
 #pragma once
@@ -16,6 +17,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -30,13 +32,26 @@ constexpr int kThreads = 512, kWarps = kThreads / 32;
 
 struct MBar { unsigned count = 0, pending = 0, phase = 0; long long tx = 0; };
 
+// Two ways to run the 512 CUDA threads of a CTA:
+//   default          16 OS threads (one per warp), each switching between its 32 lanes as fibers (ucontext) at
+//                    every rendezvous -- fast: no 512-thread futex storms;
+//   -DSB_EMU_THREADS 512 OS threads -- what ThreadSanitizer needs (tests/emu/run_tsan.py).
 struct Warp {
+#ifdef SB_EMU_THREADS
     std::barrier<> bar{32};
+#else
+    int count = 0, gen = 0;              // rendezvous of the 32 lanes (they run one at a time on one OS thread)
+    int bar_count = 0, bar_gen = 0;      // lanes waiting at the CTA barrier
+#endif
     unsigned long long slot[32];
 };
 
 struct Cta {
+#ifdef SB_EMU_THREADS
     std::barrier<> bar{kThreads};
+#else
+    std::barrier<> bar{kWarps};
+#endif
     std::unique_ptr<Warp> warps[kWarps];
     std::mutex mu;
     std::map<const void*, MBar> mbars;
@@ -50,19 +65,42 @@ struct Cta {
 inline Cta*& cta() { static Cta* c = nullptr; return c; }
 inline thread_local int t_lane = 0, t_warp = 0;
 
+#ifdef SB_EMU_THREADS
+inline void yield_lane() { std::this_thread::yield(); }
+inline void warp_rendezvous() { cta()->warps[t_warp]->bar.arrive_and_wait(); }
+inline void cta_barrier() { cta()->bar.arrive_and_wait(); }
+#else
+void yield_lane();                      // emu_driver.cpp: back to the warp's scheduler, which resumes the next lane
+inline void warp_rendezvous() {
+    Warp& w = *cta()->warps[t_warp];
+    const int gen = w.gen;
+    if (++w.count == 32) { w.count = 0; ++w.gen; }
+    else while (w.gen == gen) yield_lane();
+}
+inline void cta_barrier() {
+    Warp& w = *cta()->warps[t_warp];
+    const int gen = w.bar_gen;
+    if (++w.bar_count == 32) { cta()->bar.arrive_and_wait(); w.bar_count = 0; ++w.bar_gen; }   // the warp's last lane waits for the other warps
+    else while (w.bar_gen == gen) yield_lane();
+}
+#endif
+
 template <typename T> T shfl(T v, int src) {
     static_assert(sizeof(T) <= 8, "shuffle of up to 64 bits");
     Warp& w = *cta()->warps[t_warp];
     unsigned long long raw = 0;
     std::memcpy(&raw, &v, sizeof(T));
     w.slot[t_lane] = raw;
-    w.bar.arrive_and_wait();
+    warp_rendezvous();
     raw = w.slot[src];
-    w.bar.arrive_and_wait();
+    warp_rendezvous();
     T out;
     std::memcpy(&out, &raw, sizeof(T));
     return out;
 }
+
+// Runs body(t) for t = 0 .. 511 as the threads of the current CTA (emu_driver.cpp)
+void run_cta(const std::function<void(int)>& body);
 
 }  // namespace emu
 
@@ -97,9 +135,9 @@ inline int __float2int_rn(float f) { return (int)std::nearbyintf(f); }
 inline unsigned __float_as_uint(float f) { unsigned u; std::memcpy(&u, &f, 4); return u; }
 inline float __uint_as_float(unsigned u) { float f; std::memcpy(&f, &u, 4); return f; }
 inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
-inline void __nanosleep(unsigned) { std::this_thread::yield(); }
-inline void __syncthreads() { emu::cta()->bar.arrive_and_wait(); }
-inline void __syncwarp(unsigned = 0xffffffffu) { emu::cta()->warps[emu::t_warp]->bar.arrive_and_wait(); }
+inline void __nanosleep(unsigned) { emu::yield_lane(); }
+inline void __syncthreads() { emu::cta_barrier(); }
+inline void __syncwarp(unsigned = 0xffffffffu) { emu::warp_rendezvous(); }
 inline unsigned long long atomicMin(unsigned long long* p, unsigned long long v) {
     unsigned long long old = __atomic_load_n(p, __ATOMIC_RELAXED);
     while (v < old && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}

@@ -9,6 +9,76 @@ namespace {
 alignas(128) unsigned char smem_raw[232 * 1024];      // the kernels' `extern __shared__` array
 }
 
+// ---- running the 512 threads of a CTA ---------------------------------------------------------------------
+#ifdef SB_EMU_THREADS
+namespace emu {
+void run_cta(const std::function<void(int)>& body) {
+    std::vector<std::thread> th;
+    th.reserve(kThreads);
+    for (int t = 0; t < kThreads; ++t)
+        th.emplace_back([&body, t] { threadIdx = {(unsigned)t, 0, 0}; t_lane = t & 31; t_warp = t >> 5; body(t); });
+    for (auto& x : th) x.join();
+}
+}  // namespace emu
+#else
+#include <ucontext.h>
+namespace emu {
+namespace {
+constexpr size_t kStack = 512 * 1024;
+struct WarpRun {
+    ucontext_t sched;
+    ucontext_t lane[32];
+    bool done[32];
+    int cur = 0, warp = 0;
+    const std::function<void(int)>* body = nullptr;
+    std::vector<char> stacks;
+};
+thread_local WarpRun* t_run = nullptr;
+void lane_entry() {
+    WarpRun* r = t_run;
+    (*r->body)(r->warp * 32 + r->cur);
+    r->done[r->cur] = true;            // returning resumes uc_link = the scheduler
+}
+}  // namespace
+void yield_lane() {
+    WarpRun* r = t_run;
+    swapcontext(&r->lane[r->cur], &r->sched);
+}
+void run_cta(const std::function<void(int)>& body) {
+    std::vector<std::thread> th;
+    th.reserve(kWarps);
+    for (int w = 0; w < kWarps; ++w)
+        th.emplace_back([&body, w] {
+            WarpRun r;
+            r.warp = w; r.body = &body;
+            r.stacks.resize(32 * kStack);
+            t_run = &r;
+            t_warp = w;
+            for (int l = 0; l < 32; ++l) {
+                r.done[l] = false;
+                getcontext(&r.lane[l]);
+                r.lane[l].uc_stack.ss_sp = r.stacks.data() + (size_t)l * kStack;
+                r.lane[l].uc_stack.ss_size = kStack;
+                r.lane[l].uc_link = &r.sched;
+                makecontext(&r.lane[l], lane_entry, 0);
+            }
+            for (int left = 32; left > 0;) {
+                left = 0;
+                for (int l = 0; l < 32; ++l) {
+                    if (r.done[l]) continue;
+                    r.cur = l; t_lane = l;
+                    threadIdx = {(unsigned)(w * 32 + l), 0, 0};
+                    swapcontext(&r.sched, &r.lane[l]);
+                    if (!r.done[l]) ++left;
+                }
+            }
+            t_run = nullptr;
+        });
+    for (auto& x : th) x.join();
+}
+}  // namespace emu
+#endif
+
 extern "C" {
 
 int emu_table_floats(void) { size_t off[4]; return (int)packed_table_values(off).size(); }
@@ -37,9 +107,7 @@ int emu_run(int kernel, int epi, int is_u8, int fmt, const float* That, int64_t 
         std::memset(smem_raw, 0xCD, sizeof(smem_raw));                      // uninitialised reads show up as garbage
         for (auto& v : cta.tmem) v = std::nanf("");
         auto body = [&](int t) {
-            threadIdx = {(unsigned)t, 0, 0};
-            blockIdx = {(unsigned)b, 0, 0};
-            emu::t_lane = t & 31; emu::t_warp = t >> 5;
+            blockIdx = {(unsigned)b, 0, 0};       // threadIdx and the lane / warp numbers are set by run_cta
 #define SB_EMU_CALL(K, S, E) do { if (fmt) K<S, E, 1>(T4, part_first, X4, nblk, static_cast<const S*>(img), img_n, ip, tp, d, cta_query, first, tab, keys, curve_out); \
                                   else K<S, E, 0>(T4, part_first, X4, nblk, static_cast<const S*>(img), img_n, ip, tp, d, cta_query, first, tab, keys, curve_out); } while (0)
 #define SB_EMU_KERNEL(K) do { if (!is_u8) SB_EMU_CALL(K, float, 1); else if (epi == 2) SB_EMU_CALL(K, uint8_t, 2); else SB_EMU_CALL(K, uint8_t, 1); } while (0)
@@ -47,10 +115,7 @@ int emu_run(int kernel, int epi, int is_u8, int fmt, const float* That, int64_t 
             else if (kernel == 1) SB_EMU_KERNEL(k_match_pair);
             else SB_EMU_KERNEL(k_match_triple);
         };
-        std::vector<std::thread> th;
-        th.reserve(emu::kThreads);
-        for (int t = 0; t < emu::kThreads; ++t) th.emplace_back(body, t);
-        for (auto& x : th) x.join();
+        emu::run_cta(body);
         for (const auto& e : cta.errors) { std::fprintf(stderr, "[emu] CTA %d: %s\n", b, e.c_str()); ++n_err; }
         emu::cta() = nullptr;
     }
@@ -91,18 +156,13 @@ int emu_forward_blocks(int is_u8, int fmt, const void* src, int64_t src_n, const
         emu::cta() = &cta;
         std::memset(smem_raw, 0xCD, sizeof(smem_raw));
         auto body = [&](int t) {
-            threadIdx = {(unsigned)t, 0, 0};
-            blockIdx = {(unsigned)b, 0, 0};
-            emu::t_lane = t & 31; emu::t_warp = t >> 5;
+            blockIdx = {(unsigned)b, 0, 0};       // threadIdx and the lane / warp numbers are set by run_cta
             if (is_u8) { if (fmt) k_forward_quad<uint8_t, 0, 1>(static_cast<const uint8_t*>(src), src_n, pf, nullptr, 0, 0, row_first, tab, o4);
                          else     k_forward_quad<uint8_t, 0, 0>(static_cast<const uint8_t*>(src), src_n, pf, nullptr, 0, 0, row_first, tab, o4); }
             else       { if (fmt) k_forward_quad<float, 0, 1>(static_cast<const float*>(src), src_n, pf, nullptr, 0, 0, row_first, tab, o4);
                          else     k_forward_quad<float, 0, 0>(static_cast<const float*>(src), src_n, pf, nullptr, 0, 0, row_first, tab, o4); }
         };
-        std::vector<std::thread> th;
-        th.reserve(emu::kThreads);
-        for (int t = 0; t < emu::kThreads; ++t) th.emplace_back(body, t);
-        for (auto& x : th) x.join();
+        emu::run_cta(body);
         for (const auto& e : cta.errors) { std::fprintf(stderr, "[emu] forward CTA %d: %s\n", b, e.c_str()); ++n_err; }
         emu::cta() = nullptr;
     }

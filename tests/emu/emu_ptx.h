@@ -46,13 +46,14 @@ inline void mbar_wait(unsigned long long* bar, unsigned parity) {
             if (emu::cta()->mbars[bar].phase != parity) return;      // the phase with this parity has completed
         }
         if (spins > 20000000) { emu::cta()->fail("mbar_wait: never completed"); return; }
-        std::this_thread::yield();
+        emu::yield_lane();
+        if ((spins & 63) == 63) std::this_thread::yield();
     }
 }
 inline void mbar_wait_sleep(unsigned long long* bar, unsigned parity, unsigned) { mbar_wait(bar, parity); }
 inline void fence_proxy_async() {}
 
-template <int ID> inline void csync() { emu::cta()->bar.arrive_and_wait(); }     // one-role kernels only (ID 0)
+template <int ID> inline void csync() { emu::cta_barrier(); }     // one-role kernels only (ID 0)
 
 // ---- tensor memory: [128 lanes][512 columns] of 32-bit cells; a warp reaches the 32 lanes of its quarter
 inline void tmem_alloc(uint32_t* smem_slot, uint32_t ncols) {

@@ -5,7 +5,8 @@
 
 Builds tests/emu/emu_driver.cpp with -fsanitize=thread and runs every kernel (one CTA per lag block / pair /
 triple) with both screening loops, with and without the debug curve, on the cases of
-tests/test_kernel_emulation.py.  One OS thread stands for one CUDA thread and std::barrier for bar.sync, so a
+tests/test_kernel_emulation.py.  Built with -DSB_EMU_THREADS: one OS thread stands for one CUDA thread (the default build runs the lanes of a warp as
+fibers on one OS thread, which ThreadSanitizer cannot follow) and std::barrier for bar.sync, so a
 shared-memory access that is not ordered by the kernel's own barriers / mbarrier waits shows up as a data race:
 this checks the PLACEMENT of the barriers (re-use of the FFT buffer between the items of a pair / triple,
 re-staging of the sample windows, re-use of the reduction scratch), not the GPU memory model.  Exit code 0 and
@@ -24,7 +25,7 @@ LOG = os.path.join(ROOT, 'tests', 'emu', '_build', 'tsan.log')
 def main():
     if os.environ.get('SB_EMU_TSAN_CHILD') != '1':
         os.makedirs(os.path.dirname(LIB), exist_ok=True)
-        subprocess.check_call(['g++', '-std=c++20', '-O1', '-g', '-fsanitize=thread', '-pthread', '-DSB_EMULATE',
+        subprocess.check_call(['g++', '-std=c++20', '-O1', '-g', '-fsanitize=thread', '-pthread', '-DSB_EMULATE', '-DSB_EMU_THREADS',
                                '-I', os.path.join(ROOT, 'tests', 'emu'), '-I', os.path.join(ROOT, 'sushi_b200', 'csrc'),
                                '-I', os.path.join(ROOT, 'include'), '-I', '/usr/local/cuda/include', '-shared', '-fPIC',
                                os.path.join(ROOT, 'tests', 'emu', 'emu_driver.cpp'), '-o', LIB])
