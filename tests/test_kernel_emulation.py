@@ -377,3 +377,36 @@ def test_emulated_variants_reproduce_the_reference_golden(emu, golden_matcher):
         times = np.array(t0s) + i / 12000.0
         assert np.abs(d - g['diff_uint8'][keep]).max() <= 1e-5, (fmt, np.abs(d - g['diff_uint8'][keep]).max())
         assert np.abs(times - g['time_uint8'][keep]).max() <= 1.0 / 12000 + 1e-9, fmt
+
+
+def test_emulated_config1_against_the_live_oracle(emu):
+    """BASELINE config 1 (100 events, 2 x 60 s streams with a constant +1.5 s shift, +-10 s window) through the
+    emulated kernels -- the measured default (pairs, first screening loop, float32 rows) and the opt-in stack
+    (triples, trimmed loop, 16-bit rows) -- against the oracle's find_substream (cv2) on every event."""
+    from sushi_b200 import synth
+    from tests.helpers import oracle_stream_from_pcm
+    src_pcm, dst_pcm = synth.make_pair(60.0, 2, 1.5)
+    rs = oracle_stream_from_pcm(src_pcm, 12000, 1, 12000, 'uint8')
+    rd = oracle_stream_from_pcm(dst_pcm, 12000, 1, 12000, 'uint8')
+    starts, ends = synth.make_events(100, 60.0, 1002, 1.0, 4.0)
+    clip = lambda v, lo, hi: max(min(v, hi), lo)
+    queries, t0s, want = [], [], []
+    for a, b in zip(starts, ends):
+        toff = rs.sample_for_time(a)
+        n = rs.sample_for_time(b) - toff
+        start = clip(a - 10.0, -10, rd.duration_seconds)
+        end = clip(a + 10.0, 0, rd.duration_seconds + 10)
+        lag0 = rd.sample_for_time(start)
+        queries.append((toff, n, lag0, rd.sample_for_time(end) - lag0 + 1))
+        t0s.append(start)
+        want.append(rd.find_substream(rs.get_substream(a, b), a, 10.0))
+    want_d = np.array([w[0] for w in want], np.float64)
+    want_t = np.array([w[1] for w in want])
+    for kernel, epi, fmt in ((1, 1, 0), (2, 2, 1)):
+        case = Case(emu, rd.data[0], rs.data[0], queries, np.uint8, fmt=fmt)
+        d, i, _ = case.run(kernel, epi, curves=False)
+        times = np.array(t0s) + i / 12000.0
+        assert np.abs(d - want_d).max() <= 1e-5, (kernel, epi, fmt, np.abs(d - want_d).max())
+        assert np.abs(times - want_t).max() <= 1.0 / 12000 + 1e-9
+        ok = ends + 1.5 < 60.0
+        assert np.abs((times - starts)[ok] - 1.5).max() <= 1.0 / 12000 + 1e-9        # the known answer
