@@ -309,6 +309,43 @@ __device__ __forceinline__ C2 special_quad(const float4* tp, const float4* xp, i
     return lo;                                    // C[B/4] (its mirror is itself)
 }
 
+// EPI 2: the same quad without an L2 round trip (and a shuffle tree) at the end of the multiply phase, where the
+// other fifteen warps already wait at the barrier.  The last warp requests the 16-byte units it needs -- two per
+// row: the P template rows, then the spectrum rows k .. k+P+G-2 of the CTA's G lag blocks -- with cp.async before
+// its multiply loop; afterwards the partitions are spread over the lanes and summed by the same shuffle tree as
+// special_quad (same arithmetic in the same order: bit-identical), reading shared memory instead of L2.
+constexpr int kSpecialBytes = 1024;                // (2 * 11 + 2) rows x 32 bytes fit
+template <int FMT>
+__device__ __forceinline__ void special_prefetch(float4* s_sp, const float4* tp, const float4* xp, int P, int G,
+                                                 int64_t k, int64_t nblk, int lane) {
+    const int u0 = FMT ? Q4 : qa(Q4), u1 = FMT ? QSCALE0 + (Q4 >> 3) : qm(Q4);
+    for (int r = lane; r < 2 * P + G - 1; r += 32) {
+        const bool is_t = r < P;
+        const float4* row = is_t ? tp + (int64_t)r * Rows<FMT>::STRIDE : xp + (int64_t)(r - P) * Rows<FMT>::STRIDE;
+        if (is_t || k + (r - P) < nblk) { cp_async16(s_sp + 2 * r, row + u0); cp_async16(s_sp + 2 * r + 1, row + u1); }
+        else s_sp[2 * r] = s_sp[2 * r + 1] = make_float4(0.f, 0.f, 0.f, 0.f);     // rows past the end of the stream are zero
+    }
+}
+template <int FMT>
+__device__ __forceinline__ C2 special_from_smem(const float4* s_sp, int P, int g, int lane) {      // item g; result in lane 0
+    auto units = [&](int r, float4& a, float4& m) {
+        if (FMT) dequant16(*reinterpret_cast<const uint4*>(s_sp + 2 * r), s_sp[2 * r + 1], a, m);
+        else { a = s_sp[2 * r]; m = s_sp[2 * r + 1]; }
+    };
+    QuadAcc acc; acc.zero();
+    for (int p = lane; p < P; p += 32) {
+        float4 ta, tm, xa, xm;
+        units(p, ta, tm);
+        units(P + g + p, xa, xm);
+        acc.mac(ta, tm, xa, xm);
+    }
+    acc.reduce_over_lanes();
+    const float h = 0.70710678118654752f;       // exp(i*pi/4)
+    C2 lo, hi;
+    pack_quad(acc.aR, acc.aI, acc.mR, acc.mI, h, h, lo, hi);
+    return lo;
+}
+
 // Three radix-16 Stockham passes over the 8192 (u, v) pairs.  Butterfly j = tid reads chunk j + 512r, twiddles
 // by exp(2*pi*i*r*k/(16*Ns)), k = j mod Ns, writes chunk (j-k)*16 + k + r*Ns; phys(j + 512r) = phys(j) + 544r.
 // Entered after a barrier that published buf; ends with a barrier.  Afterwards E = chunks [0, 4096),
@@ -637,7 +674,8 @@ k_match_packed(const float4* __restrict__ That, int64_t part_first,
     unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(sm.end);
     unsigned long long* s_best = s_bar + 1;                                // [NW]
     float* s_min = reinterpret_cast<float*>(s_best + NW);                  // [NW]
-    double2* s_w0 = EPI == 2 && is_u8 ? reinterpret_cast<double2*>(sm.end + kSmallBytes) : nullptr;   // [kRounds][QT]
+    float4* s_sp = reinterpret_cast<float4*>(sm.end + kSmallBytes);        // EPI 2: units of the self-mirrored quads
+    double2* s_w0 = EPI == 2 && is_u8 ? reinterpret_cast<double2*>(sm.end + kSmallBytes + kSpecialBytes) : nullptr;   // [kRounds][QT]
     const Buf& buf = sm.buf;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -660,6 +698,7 @@ k_match_packed(const float4* __restrict__ That, int64_t part_first,
         const float2 wbase = __ldg(tab.wb + tid);
         const int tm = (T - tid) & (T - 1);           // mirrored chunks C[B/2 - i] live in thread tm's column
         const int col = phys(tid), mcol = phys(tm);
+        if (EPI == 2 && warp == NW - 1) special_prefetch<FMT>(s_sp, tp, xp, d.P, 1, it.k, nblk, lane);
         constexpr int U = 4;                          // quads in flight per thread
 #pragma unroll 1
         for (int half = 0; half < 2; ++half) {
@@ -694,8 +733,15 @@ k_match_packed(const float4* __restrict__ That, int64_t part_first,
             }
         }
         if (warp == NW - 1) {                       // the self-mirrored quad i = B/4
-            const C2 lo = special_quad<FMT>(tp, xp, P, lane);
-            if (lane == 0) buf.st(phys(Q4), lo);
+            if constexpr (EPI == 2) {
+                cp_async_commit_wait_all();
+                __syncwarp();
+                const C2 lo = special_from_smem<FMT>(s_sp, d.P, 0, lane);
+                if (lane == 0) buf.st(phys(Q4), lo);
+            } else {
+                const C2 lo = special_quad<FMT>(tp, xp, P, lane);
+                if (lane == 0) buf.st(phys(Q4), lo);
+            }
         }
     }
     csync<0>();
@@ -946,7 +992,8 @@ k_match_pair(const float4* __restrict__ That, int64_t part_first,
     unsigned long long* s_best = s_bar + 1;                                // [NW]
     float* s_min = reinterpret_cast<float*>(s_best + NW);                  // [NW]
     uint32_t* s_taddr = reinterpret_cast<uint32_t*>(s_min + NW);
-    double2* s_w0 = EPI == 2 && is_u8 ? reinterpret_cast<double2*>(sm.end + kSmallBytes) : nullptr;   // [kRounds][QT]
+    float4* s_sp = reinterpret_cast<float4*>(sm.end + kSmallBytes);        // EPI 2: units of the self-mirrored quads
+    double2* s_w0 = EPI == 2 && is_u8 ? reinterpret_cast<double2*>(sm.end + kSmallBytes + kSpecialBytes) : nullptr;   // [kRounds][QT]
     const Buf& buf = sm.buf;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -977,6 +1024,7 @@ k_match_pair(const float4* __restrict__ That, int64_t part_first,
         const float4* tp = That + (d.partBase - part_first) * (int64_t)R::STRIDE;
         const float4* xp = Xhat + k * (int64_t)R::STRIDE;
         const float2 wbase = __ldg(tab.wb + tid);
+        if (EPI == 2 && warp == NW - 1) special_prefetch<FMT>(s_sp, tp, xp, d.P, 2, k, nblk, lane);
         constexpr int U = 2;                          // quads in flight per thread (two accumulator sets each)
 #pragma unroll 1
         for (int grp = 0; grp < 8 / U; ++grp) {
@@ -1021,12 +1069,20 @@ k_match_pair(const float4* __restrict__ That, int64_t part_first,
             }
         }
         if (warp == NW - 1) {                         // the self-mirrored quad i = B/4 of both items
-            int P0 = d.P; if (k + P0 > nblk) P0 = (int)(nblk - k);
-            const C2 lo = special_quad<FMT>(tp, xp, P0, lane);
-            if (lane == 0) buf.st(phys(Q4), lo);
-            if (has2) {
-                int P1 = d.P; if (k + 1 + P1 > nblk) P1 = (int)(nblk - k - 1);
-                sp1 = special_quad<FMT>(tp, xp + R::STRIDE, P1, lane);
+            if constexpr (EPI == 2) {
+                cp_async_commit_wait_all();
+                __syncwarp();
+                const C2 lo = special_from_smem<FMT>(s_sp, d.P, 0, lane);
+                if (lane == 0) buf.st(phys(Q4), lo);
+                if (has2) sp1 = special_from_smem<FMT>(s_sp, d.P, 1, lane);
+            } else {
+                int P0 = d.P; if (k + P0 > nblk) P0 = (int)(nblk - k);
+                const C2 lo = special_quad<FMT>(tp, xp, P0, lane);
+                if (lane == 0) buf.st(phys(Q4), lo);
+                if (has2) {
+                    int P1 = d.P; if (k + 1 + P1 > nblk) P1 = (int)(nblk - k - 1);
+                    sp1 = special_quad<FMT>(tp, xp + R::STRIDE, P1, lane);
+                }
             }
         }
         tmem_wait_st();
@@ -1089,7 +1145,8 @@ k_match_triple(const float4* __restrict__ That, int64_t part_first,
     unsigned long long* s_best = s_bar + 1;                                // [NW]
     float* s_min = reinterpret_cast<float*>(s_best + NW);                  // [NW]
     uint32_t* s_taddr = reinterpret_cast<uint32_t*>(s_min + NW);
-    double2* s_w0 = EPI == 2 && is_u8 ? reinterpret_cast<double2*>(sm.end + kSmallBytes) : nullptr;   // [kRounds][QT]
+    float4* s_sp = reinterpret_cast<float4*>(sm.end + kSmallBytes);        // EPI 2: units of the self-mirrored quads
+    double2* s_w0 = EPI == 2 && is_u8 ? reinterpret_cast<double2*>(sm.end + kSmallBytes + kSpecialBytes) : nullptr;   // [kRounds][QT]
     const Buf& buf = sm.buf;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1120,6 +1177,7 @@ k_match_triple(const float4* __restrict__ That, int64_t part_first,
         const float4* tp = That + (d.partBase - part_first) * (int64_t)R::STRIDE;
         const float4* xp = Xhat + k * (int64_t)R::STRIDE;
         const float2 wbase = __ldg(tab.wb + tid);
+        if (EPI == 2 && warp == NW - 1) special_prefetch<FMT>(s_sp, tp, xp, d.P, 3, k, nblk, lane);
 #pragma unroll 1
         for (int uu = 0; uu < 8; ++uu) {              // quad i = tid + 512*uu
             const int i0 = R::unit(tid, uu);
@@ -1158,16 +1216,25 @@ k_match_triple(const float4* __restrict__ That, int64_t part_first,
             tmem_st8(tcol + 256u + (uint32_t)(uu * 8), lo.r.x, lo.r.y, lo.i.x, lo.i.y, hi.r.x, hi.r.y, hi.i.x, hi.i.y);
         }
         if (warp == NW - 1) {                         // the self-mirrored quad i = B/4 of the three items
-            int P0 = d.P; if (k + P0 > nblk) P0 = (int)(nblk - k);
-            const C2 lo = special_quad<FMT>(tp, xp, P0, lane);
-            if (lane == 0) buf.st(phys(Q4), lo);
-            if (nb > 1) {
-                int P1 = d.P; if (k + 1 + P1 > nblk) P1 = (int)(nblk - k - 1);
-                sp1 = special_quad<FMT>(tp, xp + R::STRIDE, P1, lane);
-            }
-            if (nb > 2) {
-                int P2 = d.P; if (k + 2 + P2 > nblk) P2 = (int)(nblk - k - 2);
-                sp2 = special_quad<FMT>(tp, xp + 2 * (int64_t)R::STRIDE, P2, lane);
+            if constexpr (EPI == 2) {
+                cp_async_commit_wait_all();
+                __syncwarp();
+                const C2 lo = special_from_smem<FMT>(s_sp, d.P, 0, lane);
+                if (lane == 0) buf.st(phys(Q4), lo);
+                if (nb > 1) sp1 = special_from_smem<FMT>(s_sp, d.P, 1, lane);
+                if (nb > 2) sp2 = special_from_smem<FMT>(s_sp, d.P, 2, lane);
+            } else {
+                int P0 = d.P; if (k + P0 > nblk) P0 = (int)(nblk - k);
+                const C2 lo = special_quad<FMT>(tp, xp, P0, lane);
+                if (lane == 0) buf.st(phys(Q4), lo);
+                if (nb > 1) {
+                    int P1 = d.P; if (k + 1 + P1 > nblk) P1 = (int)(nblk - k - 1);
+                    sp1 = special_quad<FMT>(tp, xp + R::STRIDE, P1, lane);
+                }
+                if (nb > 2) {
+                    int P2 = d.P; if (k + 2 + P2 > nblk) P2 = (int)(nblk - k - 2);
+                    sp2 = special_quad<FMT>(tp, xp + 2 * (int64_t)R::STRIDE, P2, lane);
+                }
             }
         }
         tmem_wait_st();
@@ -1350,7 +1417,7 @@ size_t forward_smem_bytes14() {
 }
 
 size_t packed_smem_bytes(int epi = 1) {      // epilogue 2 keeps the runs' exact head sums next to the small arrays
-    return epi == 2 ? kSmemCommon + kSmallBytes + (size_t)kRounds * QT * sizeof(double2)
+    return epi == 2 ? kSmemCommon + kSmallBytes + kSpecialBytes + (size_t)kRounds * QT * sizeof(double2)
                     : kSmemCommon + 8 + QNW * sizeof(unsigned long long) + QNW * sizeof(float) + 64;
 }
 
