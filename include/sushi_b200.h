@@ -101,7 +101,8 @@ int sb_set_hop_mode(int mode);
 /* Screening loop of the packed kernels (engines 2, 4, 5) on uint8 streams: 1 (default) = the first version,
  * 2 = a trimmed one (7 instead of 13 arithmetic instructions per lag, byte extraction by PRMT, border test
  * hoisted) whose exact evaluation takes the window sums from the staged sample windows instead of two
- * dependent reads of the running sums in HBM.  Screening only selects the lags that get the exact fp64
+ * dependent reads of the running sums in HBM, and whose multiply phase prefetches the one self-mirrored quad of
+ * each item instead of fetching it after the loop.  Screening only selects the lags that get the exact fp64
  * evaluation and the window sums are exact integers either way, so results are identical bit for bit;
  * float32 streams and the other engines ignore the setting.  Opt-in until measured. */
 int sb_set_epilogue(int variant);
