@@ -1135,7 +1135,7 @@ k_match_triple(const float4* __restrict__ That, int64_t part_first,
                const float4* __restrict__ Xhat, int64_t nblk,
                const S* __restrict__ img, int64_t img_n,
                const double2* __restrict__ ipfx, const double2* __restrict__ tpfx,
-               const QueryDesc* __restrict__ desc, const int* __restrict__ trip_query, int64_t trip_first,
+               const QueryDesc* __restrict__ desc, const int* __restrict__ trip_query, int64_t trip_first, int64_t n_trips,
                PackedTables tab, unsigned long long* __restrict__ keys, float* __restrict__ curve_out) {
     constexpr int T = QT, NW = QNW;
     constexpr bool is_u8 = sizeof(S) == 1;
@@ -1145,21 +1145,25 @@ k_match_triple(const float4* __restrict__ That, int64_t part_first,
     unsigned long long* s_best = s_bar + 1;                                // [NW]
     float* s_min = reinterpret_cast<float*>(s_best + NW);                  // [NW]
     uint32_t* s_taddr = reinterpret_cast<uint32_t*>(s_min + NW);
+    int* s_nq = reinterpret_cast<int*>(sm.end + 208);                      // [4] query of the triples i, i+1, i+2 (slot i % 3)
+    QueryDesc* s_nd = reinterpret_cast<QueryDesc*>(sm.end + 224);          // [2] descriptor of the triples i, i+1 (slot i & 1)
+    static_assert(224 + 2 * sizeof(QueryDesc) <= kSmallBytes && sizeof(QueryDesc) % 16 == 0, "small area");
     float4* s_sp = reinterpret_cast<float4*>(sm.end + kSmallBytes);        // EPI 2: units of the self-mirrored quads
     double2* s_w0 = EPI == 2 && is_u8 ? reinterpret_cast<double2*>(sm.end + kSmallBytes + kSpecialBytes) : nullptr;   // [kRounds][QT]
     const Buf& buf = sm.buf;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int q = __ldg(trip_query + blockIdx.x);
-    const QueryDesc d = desc[q];
-    const int lt = (int)(trip_first + blockIdx.x - d.groupBase);          // triple number inside the query
-    const int nb = d.nk - 3 * lt < 3 ? d.nk - 3 * lt : 3;                 // lag blocks of this CTA (uniform)
-    const Item it0(d, q, d.k0 + 3 * lt), it1(d, q, d.k0 + 3 * lt + 1), it2(d, q, d.k0 + 3 * lt + 2);
-
+    // Persistent: one CTA per SM walks the triples blockIdx.x, blockIdx.x + gridDim.x, ...  A fresh CTA per triple
+    // starts with two dependent global reads (its query, then the descriptor) before it can request a single
+    // spectrum row, and allocates / releases tensor memory and its barrier every time; here thread 0 fetches the
+    // query index two triples ahead and the descriptor one triple ahead with cp.async while the CTA works.
     if (warp == 0) tmem_alloc(s_taddr, 512);
-    if (is_u8) {
-        if (tid == 0) mbar_init(s_bar, 1);
-        stage_inputs(it0, tid, reinterpret_cast<const uint8_t*>(img), img_n, ipfx, sm, s_bar);
+    if (tid == 0) {
+        if (is_u8) mbar_init(s_bar, 1);
+        const int64_t t0 = blockIdx.x, t1 = t0 + gridDim.x;
+        s_nq[0] = __ldg(trip_query + t0);
+        s_nd[0] = desc[s_nq[0]];
+        if (t1 < n_trips) s_nq[1] = __ldg(trip_query + t1);
     }
     tmem_fence_before();
     csync<0>();
@@ -1167,9 +1171,31 @@ k_match_triple(const float4* __restrict__ That, int64_t part_first,
     // this thread's columns: lane quarter of its warp, column block of its warp group; second block at +0,
     // third block at +256
     const uint32_t tcol = *s_taddr + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 64);
-
     const int tm = (T - tid) & (T - 1);               // mirrored chunks C[B/2 - i] live in thread tm's column
     const int col = phys(tid), mcol = phys(tm);
+    unsigned ph = 0;                                  // phases of s_bar consumed so far (one per staged item)
+
+#pragma unroll 1
+    for (int trip = (int)blockIdx.x, iter = 0; trip < (int)n_trips; trip += (int)gridDim.x, ++iter) {     // n_trips < 2^31
+    if (iter) {
+        if (tid == 0) cp_async_commit_wait_all();     // this triple's descriptor has landed
+        csync<0>();                                   // ... and everyone is done with the previous triple
+    }
+    const int q = s_nq[iter % 3];
+    const QueryDesc d = s_nd[iter & 1];
+    if (tid == 0) {                                   // slots last read one triple ago: free since the barrier above
+        if (trip + (int)gridDim.x < (int)n_trips) {
+            const uint4* src = reinterpret_cast<const uint4*>(desc + s_nq[(iter + 1) % 3]);
+            uint4* dst = reinterpret_cast<uint4*>(s_nd + ((iter + 1) & 1));
+#pragma unroll
+            for (int c = 0; c < (int)(sizeof(QueryDesc) / 16); ++c) cp_async16(dst + c, src + c);
+        }
+        if ((int64_t)trip + 2 * (int64_t)gridDim.x < n_trips) cp_async4(s_nq + (iter + 2) % 3, trip_query + trip + 2 * (int)gridDim.x);
+    }
+    const int lt = (int)(trip_first + trip - d.groupBase);                // triple number inside the query
+    const int nb = d.nk - 3 * lt < 3 ? d.nk - 3 * lt : 3;                 // lag blocks of this triple (uniform)
+    const Item it0(d, q, d.k0 + 3 * lt), it1(d, q, d.k0 + 3 * lt + 1), it2(d, q, d.k0 + 3 * lt + 2);
+    if (is_u8) stage_inputs(it0, tid, reinterpret_cast<const uint8_t*>(img), img_n, ipfx, sm, s_bar);
     C2 sp1 = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)}, sp2 = sp1;   // C[B/4] of blocks 2 and 3 (warp NW-1, lane 0)
     {
         typedef Rows<FMT> R;
@@ -1243,7 +1269,7 @@ k_match_triple(const float4* __restrict__ That, int64_t part_first,
 
     // ---------------- first item: inverse FFT + epilogue ---------------------------------------
     fft_passes<0>(buf, tid, tab, is_u8);
-    finish_item<S, 0, EPI>(it0, tid, sm, s_bar, 0u, s_best, s_min, s_w0, img, img_n, ipfx, tpfx, tab, keys, curve_out,
+    finish_item<S, 0, EPI>(it0, tid, sm, s_bar, ph & 1u, s_best, s_min, s_w0, img, img_n, ipfx, tpfx, tab, keys, curve_out,
                            [&] { if (is_u8 && nb > 1) stage_inputs(it1, tid, reinterpret_cast<const uint8_t*>(img), img_n, ipfx, sm, s_bar); });
 
     // ---------------- second and third item: out of tensor memory, then the same ------------------
@@ -1269,11 +1295,13 @@ k_match_triple(const float4* __restrict__ That, int64_t part_first,
         csync<0>();
         fft_passes<0>(buf, tid, tab, is_u8);
         if (j == 1)
-            finish_item<S, 0, EPI>(it1, tid, sm, s_bar, 1u, s_best, s_min, s_w0, img, img_n, ipfx, tpfx, tab, keys, curve_out,
+            finish_item<S, 0, EPI>(it1, tid, sm, s_bar, (ph + 1u) & 1u, s_best, s_min, s_w0, img, img_n, ipfx, tpfx, tab, keys, curve_out,
                                    [&] { if (is_u8 && nb > 2) stage_inputs(it2, tid, reinterpret_cast<const uint8_t*>(img), img_n, ipfx, sm, s_bar); });
         else
-            finish_item<S, 0, EPI>(it2, tid, sm, s_bar, 0u, s_best, s_min, s_w0, img, img_n, ipfx, tpfx, tab, keys, curve_out, [] {});
+            finish_item<S, 0, EPI>(it2, tid, sm, s_bar, (ph + 2u) & 1u, s_best, s_min, s_w0, img, img_n, ipfx, tpfx, tab, keys, curve_out, [] {});
     }
+    ph += (unsigned)nb;
+    }   // next triple of this CTA
     tmem_fence_before();
     csync<0>();
     if (warp == 0) tmem_dealloc(*s_taddr, 512);
@@ -1566,9 +1594,10 @@ int launch_triple_typed(const sb_stream* image, const sb_stream* tmpl, const flo
         SB_CUDA(cudaFuncSetAttribute(k_match_triple<S, EPI, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
-    k_match_triple<S, EPI, FMT><<<(unsigned)n_trips, QT, smem, c.stream>>>(
+    const unsigned grid = (unsigned)std::min<int64_t>(n_trips, c.sm_count);      // one persistent CTA per SM
+    k_match_triple<S, EPI, FMT><<<grid, QT, smem, c.stream>>>(
         reinterpret_cast<const float4*>(d_parts), part_first, reinterpret_cast<const float4*>(image->d_specq), image->nblkq,
-        static_cast<const S*>(image->d_raw), image->n, image->d_pfx, tmpl->d_pfx, d_desc, g_item_query2, trip_first,
+        static_cast<const S*>(image->d_raw), image->n, image->d_pfx, tmpl->d_pfx, d_desc, g_item_query2, trip_first, n_trips,
         tab, d_keys, d_curve);
     SB_CUDA(cudaGetLastError());
     return SB_OK;

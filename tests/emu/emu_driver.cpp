@@ -101,19 +101,23 @@ int emu_run(int kernel, int epi, int is_u8, int fmt, const float* That, int64_t 
     const double2* tp = reinterpret_cast<const double2*>(tpfx);
     const sb::QueryDesc* d = static_cast<const sb::QueryDesc*>(desc);
     int n_err = 0;
-    for (int b = 0; b < n_ctas; ++b) {
+    const int grid = kernel == 2 ? (n_ctas < 3 ? n_ctas : 3) : n_ctas;      // the triple kernel is persistent: 3 CTAs share the triples
+    gridDim = dim3((unsigned)grid, 1, 1);
+    for (int b = 0; b < grid; ++b) {
         emu::Cta cta;
         emu::cta() = &cta;
         std::memset(smem_raw, 0xCD, sizeof(smem_raw));                      // uninitialised reads show up as garbage
         for (auto& v : cta.tmem) v = std::nanf("");
         auto body = [&](int t) {
             blockIdx = {(unsigned)b, 0, 0};       // threadIdx and the lane / warp numbers are set by run_cta
-#define SB_EMU_CALL(K, S, E) do { if (fmt) K<S, E, 1>(T4, part_first, X4, nblk, static_cast<const S*>(img), img_n, ip, tp, d, cta_query, first, tab, keys, curve_out); \
-                                  else K<S, E, 0>(T4, part_first, X4, nblk, static_cast<const S*>(img), img_n, ip, tp, d, cta_query, first, tab, keys, curve_out); } while (0)
-#define SB_EMU_KERNEL(K) do { if (!is_u8) SB_EMU_CALL(K, float, 1); else if (epi == 2) SB_EMU_CALL(K, uint8_t, 2); else SB_EMU_CALL(K, uint8_t, 1); } while (0)
+#define SB_EMU_ARGS(S) T4, part_first, X4, nblk, static_cast<const S*>(img), img_n, ip, tp, d, cta_query, first
+#define SB_EMU_CALL(K, S, E, ...) do { if (fmt) K<S, E, 1>(SB_EMU_ARGS(S), ##__VA_ARGS__, tab, keys, curve_out); \
+                                       else K<S, E, 0>(SB_EMU_ARGS(S), ##__VA_ARGS__, tab, keys, curve_out); } while (0)
+#define SB_EMU_KERNEL(K, ...) do { if (!is_u8) SB_EMU_CALL(K, float, 1, ##__VA_ARGS__); else if (epi == 2) SB_EMU_CALL(K, uint8_t, 2, ##__VA_ARGS__); \
+                                   else SB_EMU_CALL(K, uint8_t, 1, ##__VA_ARGS__); } while (0)
             if (kernel == 0) SB_EMU_KERNEL(k_match_packed);
             else if (kernel == 1) SB_EMU_KERNEL(k_match_pair);
-            else SB_EMU_KERNEL(k_match_triple);
+            else SB_EMU_KERNEL(k_match_triple, (int64_t)n_ctas);       // persistent: n_ctas triples over `grid` CTAs
         };
         emu::run_cta(body);
         for (const auto& e : cta.errors) { std::fprintf(stderr, "[emu] CTA %d: %s\n", b, e.c_str()); ++n_err; }

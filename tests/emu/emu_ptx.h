@@ -8,6 +8,7 @@ namespace sbf {
 inline float rsqrt_fast(float x) { return 1.0f / std::sqrt(x); }
 
 inline void cp_async16(void* smem_dst, const void* gmem_src) { std::memcpy(smem_dst, gmem_src, 16); }
+inline void cp_async4(void* smem_dst, const void* gmem_src) { std::memcpy(smem_dst, gmem_src, 4); }
 inline void cp_async_commit_wait_all() {}
 
 // ---- mbarrier + bulk copies: phase completes when every expected arrival and every expected byte is in
