@@ -102,7 +102,8 @@ int sb_set_hop_mode(int mode);
  * 2 = a trimmed one (7 instead of 13 arithmetic instructions per lag, byte extraction by PRMT, border test
  * hoisted) whose exact evaluation takes the window sums from the staged sample windows instead of two
  * dependent reads of the running sums in HBM, and whose multiply phase prefetches the one self-mirrored quad of
- * each item instead of fetching it after the loop.  Screening only selects the lags that get the exact fp64
+ * each item instead of fetching it after the loop, and whose FFT passes place the barrier between loads and
+ * stores in the middle of the butterfly (loads and stores overlap arithmetic).  Screening only selects the lags that get the exact fp64
  * evaluation and the window sums are exact integers either way, so results are identical bit for bit;
  * float32 streams and the other engines ignore the setting.  Opt-in until measured. */
 int sb_set_epilogue(int variant);

@@ -106,9 +106,11 @@ __device__ __forceinline__ C2 rot32p(C2 d, int q) {
 
 // In-register inverse DFT of 16 points on both halves at once; decimation in frequency, natural order in,
 // bit-reversed order out (index the result through brev<16>).
+// Stages h = HI, HI/2, .., LO of the transform (the whole of it: HI = 8, LO = 1).
+template <int HI = 8, int LO = 1>
 __device__ __forceinline__ void dft16p(C2 (&v)[16]) {
 #pragma unroll
-    for (int h = 8; h >= 1; h >>= 1) {
+    for (int h = HI; h >= LO; h >>= 1) {
 #pragma unroll
         for (int g = 0; g < 16; g += 2 * h) {
 #pragma unroll
@@ -352,15 +354,21 @@ __device__ __forceinline__ C2 special_from_smem(const float4* s_sp, int P, int g
 // O = chunks [4096, 8192): the half-size transforms are X'[j] = E[j] + W8192^j * O[j] (j < 4096; the "-" half
 // carries no valid lag), and chunk j of X' holds the correlation (times 2B) at lags 4j .. 4j+3 =
 // (u.re, u.im, v.re, v.im).
-template <int ID>
+// The barrier in the middle of a pass separates every thread's loads from every thread's stores (the passes are in
+// place).  MIDBAR = false (measured default) puts it right after the loads: all sixteen warps then wait until the
+// last load of the slowest warp has come back before anyone computes, so the 1024 cycles the shared-memory pipe
+// needs for a pass's loads are not overlapped by arithmetic.  MIDBAR = true (opt-in with EPI 2) puts it between
+// the second and the third butterfly stage -- the latest loads overlap the first half of the arithmetic of the
+// warps served earlier, the earliest stores the second half of the others'.
+template <int ID, bool MIDBAR = false>
 __device__ __forceinline__ void fft_passes(const Buf& buf, int tid, const PackedTables& tab, bool drain_cp_async) {
     C2 v[16];
     const int src = phys(tid);
     {   // pass 1: Ns = 1, no twiddles; out chunk 16j + r -> 17j + r
 #pragma unroll
         for (int r = 0; r < 16; ++r) v[r] = buf.ld(src + 544 * r);
-        csync<ID>();
-        dft16p(v);
+        if (MIDBAR) { dft16p<8, 4>(v); csync<ID>(); dft16p<2, 1>(v); }
+        else { csync<ID>(); dft16p(v); }
         const int dst = 17 * tid;
 #pragma unroll
         for (int r = 0; r < 16; ++r) buf.st(dst + r, v[brev<16>(r)]);
@@ -373,13 +381,14 @@ __device__ __forceinline__ void fft_passes(const Buf& buf, int tid, const Packed
         for (int a = 0; a < 8; ++a) tw[a] = __ldg(tab.tw2 + a * 16 + kk);
 #pragma unroll
         for (int r = 0; r < 16; ++r) v[r] = buf.ld(src + 544 * r);
-        csync<ID>();
+        if (!MIDBAR) csync<ID>();
 #pragma unroll
         for (int r = 1; r < 16; ++r) {
             const float4 t = tw[r >> 1];
             v[r] = (r & 1) ? cmul_s(v[r], t.z, t.w) : cmul_s(v[r], t.x, t.y);
         }
-        dft16p(v);
+        if (MIDBAR) { dft16p<8, 4>(v); csync<ID>(); dft16p<2, 1>(v); }
+        else dft16p(v);
         const int dst = 272 * (tid >> 4) + kk;
 #pragma unroll
         for (int r = 0; r < 16; ++r) buf.st(dst + 17 * r, v[brev<16>(r)]);
@@ -392,13 +401,14 @@ __device__ __forceinline__ void fft_passes(const Buf& buf, int tid, const Packed
         for (int a = 0; a < 8; ++a) tw[a] = __ldg(tab.tw3 + a * 256 + kk);
 #pragma unroll
         for (int r = 0; r < 16; ++r) v[r] = buf.ld(src + 544 * r);
-        csync<ID>();
+        if (!MIDBAR) csync<ID>();
 #pragma unroll
         for (int r = 1; r < 16; ++r) {
             const float4 t = tw[r >> 1];
             v[r] = (r & 1) ? cmul_s(v[r], t.z, t.w) : cmul_s(v[r], t.x, t.y);
         }
-        dft16p(v);
+        if (MIDBAR) { dft16p<8, 4>(v); csync<ID>(); dft16p<2, 1>(v); }
+        else dft16p(v);
         const int dst = 4352 * (tid >> 8) + phys(kk);
 #pragma unroll
         for (int r = 0; r < 16; ++r) buf.st(dst + 272 * r, v[brev<16>(r)]);
@@ -747,7 +757,7 @@ k_match_packed(const float4* __restrict__ That, int64_t part_first,
     csync<0>();
 
     // ---------------- 3. inverse FFT, 4. epilogue ---------------------------------------------
-    fft_passes<0>(buf, tid, tab, is_u8);
+    fft_passes<0, EPI == 2>(buf, tid, tab, is_u8);
     finish_item<S, 0, EPI>(it, tid, sm, s_bar, 0u, s_best, s_min, s_w0, img, img_n, ipfx, tpfx, tab, keys, curve_out, [] {});
 }
 
@@ -1090,7 +1100,7 @@ k_match_pair(const float4* __restrict__ That, int64_t part_first,
     csync<0>();
 
     // ---------------- first item: inverse FFT + epilogue ---------------------------------------
-    fft_passes<0>(buf, tid, tab, is_u8);
+    fft_passes<0, EPI == 2>(buf, tid, tab, is_u8);
     finish_item<S, 0, EPI>(it0, tid, sm, s_bar, 0u, s_best, s_min, s_w0, img, img_n, ipfx, tpfx, tab, keys, curve_out,
                       [&] { if (is_u8 && has2) stage_inputs(it1, tid, reinterpret_cast<const uint8_t*>(img), img_n, ipfx, sm, s_bar); });
 
@@ -1113,7 +1123,7 @@ k_match_pair(const float4* __restrict__ That, int64_t part_first,
         }
         if (tid == (NW - 1) * 32) buf.st(phys(Q4), sp1);
         csync<0>();
-        fft_passes<0>(buf, tid, tab, is_u8);
+        fft_passes<0, EPI == 2>(buf, tid, tab, is_u8);
         finish_item<S, 0, EPI>(it1, tid, sm, s_bar, 1u, s_best, s_min, s_w0, img, img_n, ipfx, tpfx, tab, keys, curve_out, [] {});
     }
     tmem_fence_before();
@@ -1268,7 +1278,7 @@ k_match_triple(const float4* __restrict__ That, int64_t part_first,
     csync<0>();
 
     // ---------------- first item: inverse FFT + epilogue ---------------------------------------
-    fft_passes<0>(buf, tid, tab, is_u8);
+    fft_passes<0, EPI == 2>(buf, tid, tab, is_u8);
     finish_item<S, 0, EPI>(it0, tid, sm, s_bar, ph & 1u, s_best, s_min, s_w0, img, img_n, ipfx, tpfx, tab, keys, curve_out,
                            [&] { if (is_u8 && nb > 1) stage_inputs(it1, tid, reinterpret_cast<const uint8_t*>(img), img_n, ipfx, sm, s_bar); });
 
@@ -1293,7 +1303,7 @@ k_match_triple(const float4* __restrict__ That, int64_t part_first,
         }
         if (tid == (NW - 1) * 32) buf.st(phys(Q4), j == 1 ? sp1 : sp2);
         csync<0>();
-        fft_passes<0>(buf, tid, tab, is_u8);
+        fft_passes<0, EPI == 2>(buf, tid, tab, is_u8);
         if (j == 1)
             finish_item<S, 0, EPI>(it1, tid, sm, s_bar, (ph + 1u) & 1u, s_best, s_min, s_w0, img, img_n, ipfx, tpfx, tab, keys, curve_out,
                                    [&] { if (is_u8 && nb > 2) stage_inputs(it2, tid, reinterpret_cast<const uint8_t*>(img), img_n, ipfx, sm, s_bar); });
