@@ -311,7 +311,7 @@ __device__ __forceinline__ C2 special_quad(const float4* tp, const float4* xp, i
     return lo;                                    // C[B/4] (its mirror is itself)
 }
 
-// EPI 2: the same quad without an L2 round trip (and a shuffle tree) at the end of the multiply phase, where the
+// EPI 2: the same quad without an L2 round trip at the end of the multiply phase, where the
 // other fifteen warps already wait at the barrier.  The last warp requests the 16-byte units it needs -- two per
 // row: the P template rows, then the spectrum rows k .. k+P+G-2 of the CTA's G lag blocks -- with cp.async before
 // its multiply loop; afterwards the partitions are spread over the lanes and summed by the same shuffle tree as
