@@ -54,7 +54,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--obj', default=os.path.join(ROOT, 'sushi_b200', 'csrc', 'sb_fused2.o'))
     ap.add_argument('--src', default=os.path.join(ROOT, 'sushi_b200', 'csrc', 'sb_fused2.cu'))
-    ap.add_argument('--kernel', default='k_match_packedIhE', help='substring of the mangled kernel name')
+    ap.add_argument('--kernel', default='k_match_packedIhLi1ELi0E', help='substring of the mangled kernel name')
     ap.add_argument('--top', type=int, default=10, help='opcodes listed per region')
     args = ap.parse_args()
 
