@@ -42,6 +42,15 @@
 using namespace sb;
 using namespace sbf;
 
+// Parts of the second kernel body (EPI 2) that can be compiled out one by one to attribute a measured difference
+// (make NVCCFLAGS+=-DSB_V2_MIDBAR=0 ...): barrier placement in the FFT passes, prefetch of the self-mirrored quad.
+#ifndef SB_V2_MIDBAR
+#define SB_V2_MIDBAR 1
+#endif
+#ifndef SB_V2_SPECIAL_PREFETCH
+#define SB_V2_SPECIAL_PREFETCH 1
+#endif
+
 namespace {
 
 constexpr int QB = 16384;                 // lags per item = half the real FFT size
@@ -708,7 +717,7 @@ k_match_packed(const float4* __restrict__ That, int64_t part_first,
         const float2 wbase = __ldg(tab.wb + tid);
         const int tm = (T - tid) & (T - 1);           // mirrored chunks C[B/2 - i] live in thread tm's column
         const int col = phys(tid), mcol = phys(tm);
-        if (EPI == 2 && warp == NW - 1) special_prefetch<FMT>(s_sp, tp, xp, d.P, 1, it.k, nblk, lane);
+        if (EPI == 2 && SB_V2_SPECIAL_PREFETCH && warp == NW - 1) special_prefetch<FMT>(s_sp, tp, xp, d.P, 1, it.k, nblk, lane);
         constexpr int U = 4;                          // quads in flight per thread
 #pragma unroll 1
         for (int half = 0; half < 2; ++half) {
@@ -743,7 +752,7 @@ k_match_packed(const float4* __restrict__ That, int64_t part_first,
             }
         }
         if (warp == NW - 1) {                       // the self-mirrored quad i = B/4
-            if constexpr (EPI == 2) {
+            if constexpr (EPI == 2 && SB_V2_SPECIAL_PREFETCH) {
                 cp_async_commit_wait_all();
                 __syncwarp();
                 const C2 lo = special_from_smem<FMT>(s_sp, d.P, 0, lane);
@@ -757,7 +766,7 @@ k_match_packed(const float4* __restrict__ That, int64_t part_first,
     csync<0>();
 
     // ---------------- 3. inverse FFT, 4. epilogue ---------------------------------------------
-    fft_passes<0, EPI == 2>(buf, tid, tab, is_u8);
+    fft_passes<0, EPI == 2 && SB_V2_MIDBAR>(buf, tid, tab, is_u8);
     finish_item<S, 0, EPI>(it, tid, sm, s_bar, 0u, s_best, s_min, s_w0, img, img_n, ipfx, tpfx, tab, keys, curve_out, [] {});
 }
 
@@ -1034,7 +1043,7 @@ k_match_pair(const float4* __restrict__ That, int64_t part_first,
         const float4* tp = That + (d.partBase - part_first) * (int64_t)R::STRIDE;
         const float4* xp = Xhat + k * (int64_t)R::STRIDE;
         const float2 wbase = __ldg(tab.wb + tid);
-        if (EPI == 2 && warp == NW - 1) special_prefetch<FMT>(s_sp, tp, xp, d.P, 2, k, nblk, lane);
+        if (EPI == 2 && SB_V2_SPECIAL_PREFETCH && warp == NW - 1) special_prefetch<FMT>(s_sp, tp, xp, d.P, 2, k, nblk, lane);
         constexpr int U = 2;                          // quads in flight per thread (two accumulator sets each)
 #pragma unroll 1
         for (int grp = 0; grp < 8 / U; ++grp) {
@@ -1079,7 +1088,7 @@ k_match_pair(const float4* __restrict__ That, int64_t part_first,
             }
         }
         if (warp == NW - 1) {                         // the self-mirrored quad i = B/4 of both items
-            if constexpr (EPI == 2) {
+            if constexpr (EPI == 2 && SB_V2_SPECIAL_PREFETCH) {
                 cp_async_commit_wait_all();
                 __syncwarp();
                 const C2 lo = special_from_smem<FMT>(s_sp, d.P, 0, lane);
@@ -1100,7 +1109,7 @@ k_match_pair(const float4* __restrict__ That, int64_t part_first,
     csync<0>();
 
     // ---------------- first item: inverse FFT + epilogue ---------------------------------------
-    fft_passes<0, EPI == 2>(buf, tid, tab, is_u8);
+    fft_passes<0, EPI == 2 && SB_V2_MIDBAR>(buf, tid, tab, is_u8);
     finish_item<S, 0, EPI>(it0, tid, sm, s_bar, 0u, s_best, s_min, s_w0, img, img_n, ipfx, tpfx, tab, keys, curve_out,
                       [&] { if (is_u8 && has2) stage_inputs(it1, tid, reinterpret_cast<const uint8_t*>(img), img_n, ipfx, sm, s_bar); });
 
@@ -1123,7 +1132,7 @@ k_match_pair(const float4* __restrict__ That, int64_t part_first,
         }
         if (tid == (NW - 1) * 32) buf.st(phys(Q4), sp1);
         csync<0>();
-        fft_passes<0, EPI == 2>(buf, tid, tab, is_u8);
+        fft_passes<0, EPI == 2 && SB_V2_MIDBAR>(buf, tid, tab, is_u8);
         finish_item<S, 0, EPI>(it1, tid, sm, s_bar, 1u, s_best, s_min, s_w0, img, img_n, ipfx, tpfx, tab, keys, curve_out, [] {});
     }
     tmem_fence_before();
@@ -1213,7 +1222,7 @@ k_match_triple(const float4* __restrict__ That, int64_t part_first,
         const float4* tp = That + (d.partBase - part_first) * (int64_t)R::STRIDE;
         const float4* xp = Xhat + k * (int64_t)R::STRIDE;
         const float2 wbase = __ldg(tab.wb + tid);
-        if (EPI == 2 && warp == NW - 1) special_prefetch<FMT>(s_sp, tp, xp, d.P, 3, k, nblk, lane);
+        if (EPI == 2 && SB_V2_SPECIAL_PREFETCH && warp == NW - 1) special_prefetch<FMT>(s_sp, tp, xp, d.P, 3, k, nblk, lane);
 #pragma unroll 1
         for (int uu = 0; uu < 8; ++uu) {              // quad i = tid + 512*uu
             const int i0 = R::unit(tid, uu);
@@ -1252,7 +1261,7 @@ k_match_triple(const float4* __restrict__ That, int64_t part_first,
             tmem_st8(tcol + 256u + (uint32_t)(uu * 8), lo.r.x, lo.r.y, lo.i.x, lo.i.y, hi.r.x, hi.r.y, hi.i.x, hi.i.y);
         }
         if (warp == NW - 1) {                         // the self-mirrored quad i = B/4 of the three items
-            if constexpr (EPI == 2) {
+            if constexpr (EPI == 2 && SB_V2_SPECIAL_PREFETCH) {
                 cp_async_commit_wait_all();
                 __syncwarp();
                 const C2 lo = special_from_smem<FMT>(s_sp, d.P, 0, lane);
@@ -1278,7 +1287,7 @@ k_match_triple(const float4* __restrict__ That, int64_t part_first,
     csync<0>();
 
     // ---------------- first item: inverse FFT + epilogue ---------------------------------------
-    fft_passes<0, EPI == 2>(buf, tid, tab, is_u8);
+    fft_passes<0, EPI == 2 && SB_V2_MIDBAR>(buf, tid, tab, is_u8);
     finish_item<S, 0, EPI>(it0, tid, sm, s_bar, ph & 1u, s_best, s_min, s_w0, img, img_n, ipfx, tpfx, tab, keys, curve_out,
                            [&] { if (is_u8 && nb > 1) stage_inputs(it1, tid, reinterpret_cast<const uint8_t*>(img), img_n, ipfx, sm, s_bar); });
 
@@ -1303,7 +1312,7 @@ k_match_triple(const float4* __restrict__ That, int64_t part_first,
         }
         if (tid == (NW - 1) * 32) buf.st(phys(Q4), j == 1 ? sp1 : sp2);
         csync<0>();
-        fft_passes<0, EPI == 2>(buf, tid, tab, is_u8);
+        fft_passes<0, EPI == 2 && SB_V2_MIDBAR>(buf, tid, tab, is_u8);
         if (j == 1)
             finish_item<S, 0, EPI>(it1, tid, sm, s_bar, (ph + 1u) & 1u, s_best, s_min, s_w0, img, img_n, ipfx, tpfx, tab, keys, curve_out,
                                    [&] { if (is_u8 && nb > 2) stage_inputs(it2, tid, reinterpret_cast<const uint8_t*>(img), img_n, ipfx, sm, s_bar); });
