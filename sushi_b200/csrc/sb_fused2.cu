@@ -596,9 +596,17 @@ __device__ __forceinline__ void finish_item(const Item& it, int tid, const Smem&
     if (is_u8) fence_proxy_async();   // window reads before the next item's TMA refill
     csync<ID>();
     if (!v2) after_read();            // v2 evaluates its candidates from the staged windows first
-    float bmin = s_min[0];
+    float bmin;
+    if constexpr (v2) {               // one load and four shuffle steps instead of sixteen broadcast loads
+        static_assert(NW == 16, "block minimum over 16 warps");
+        bmin = s_min[lane & (NW - 1)];
 #pragma unroll
-    for (int w = 1; w < NW; ++w) bmin = fminf(bmin, s_min[w]);
+        for (int o = NW / 2; o > 0; o >>= 1) bmin = fminf(bmin, __shfl_xor_sync(0xffffffffu, bmin, o));
+    } else {
+        bmin = s_min[0];
+#pragma unroll
+        for (int w = 1; w < NW; ++w) bmin = fminf(bmin, s_min[w]);
+    }
     float thr = curve_out ? 1.5f : bmin + kScreenMargin;             // debug curve: evaluate everything
     bool all = false;                // v2: every lag of the range is a candidate
     if (v2) {
