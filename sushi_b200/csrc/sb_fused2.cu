@@ -426,6 +426,20 @@ __device__ __forceinline__ void fft_passes(const Buf& buf, int tid, const Packed
     }
 }
 
+// EPI 2: the constants of a query every thread needs in finish_item -- sums of the template (two reads of its
+// running sums) and the two centres (two fp64 divisions) -- by ONE thread at the start of the CTA's work on the
+// query, through shared memory; the first version has all 512 threads fetch and divide them after the last FFT
+// pass of every item, with the whole CTA waiting on those reads.  [0] = (sum T, sum T^2), [1] = (a, b).
+__device__ __forceinline__ constexpr int kQueryConstOff() { return 384; }      // bytes behind Smem::end (small area)
+template <typename S>
+__device__ __forceinline__ void query_constants(double2* s_qc, const QueryDesc& d, int64_t img_n,
+                                                const double2* __restrict__ ipfx, const double2* __restrict__ tpfx) {
+    const double2 t_hi = tpfx[d.toff + d.tlen], t_lo = tpfx[d.toff];
+    const double tsum = t_hi.x - t_lo.x, tsq = t_hi.y - t_lo.y;
+    s_qc[0] = make_double2(tsum, tsq);
+    s_qc[1] = make_double2((double)Acc<S>::centre(ipfx[img_n].x, (double)img_n), (double)Acc<S>::centre(tsum, (double)d.tlen));
+}
+
 // Window sums, fp32 screening of every lag, fp64 evaluation of the lags that can still be the minimum, merge
 // into the query's key.  after_read() runs (on all 512 threads) once every thread is done with the staged
 // windows -- k_match_ws starts the copies of its next item there.
@@ -447,10 +461,17 @@ __device__ __forceinline__ void finish_item(const Item& it, int tid, const Smem&
     const int64_t j_blk = it.j_blk;
     const int64_t n = d.tlen;
     const int64_t jlo = d.lag0, jhi = d.lag0 + d.nlags;
-    const double2 t_hi = tpfx[d.toff + n], t_lo = tpfx[d.toff];
-    const double tsum = t_hi.x - t_lo.x, tsq = t_hi.y - t_lo.y;
-    const double a = (double)Acc<S>::centre(ipfx[img_n].x, (double)img_n);
-    const double b = (double)Acc<S>::centre(tsum, (double)n);
+    double tsum, tsq, a, b;
+    if constexpr (v2) {               // computed once per query by one thread (query_constants)
+        const double2* s_qc = reinterpret_cast<const double2*>(sm.end + kQueryConstOff());
+        const double2 c0 = s_qc[0], c1 = s_qc[1];
+        tsum = c0.x; tsq = c0.y; a = c1.x; b = c1.y;
+    } else {
+        const double2 t_hi = tpfx[d.toff + n], t_lo = tpfx[d.toff];
+        tsum = t_hi.x - t_lo.x; tsq = t_hi.y - t_lo.y;
+        a = (double)Acc<S>::centre(ipfx[img_n].x, (double)img_n);
+        b = (double)Acc<S>::centre(tsum, (double)n);
+    }
     const double n_ab = (double)n * a * b;
     const double scale = 1.0 / (double)(2 * B);
     const double k_const = a * tsum - n_ab;
@@ -714,6 +735,7 @@ k_match_packed(const float4* __restrict__ That, int64_t part_first,
         if (tid == 0) mbar_init(s_bar, 1);
         stage_inputs(it, tid, reinterpret_cast<const uint8_t*>(img), img_n, ipfx, sm, s_bar);
     }
+    if (EPI == 2 && tid == 64) query_constants<S>(reinterpret_cast<double2*>(sm.end + kQueryConstOff()), d, img_n, ipfx, tpfx);
 
     // ---------------- 1+2. spectral multiply-accumulate, packing, first radix-2 step --------
     {
@@ -1035,6 +1057,7 @@ k_match_pair(const float4* __restrict__ That, int64_t part_first,
         if (tid == 0) mbar_init(s_bar, 1);
         stage_inputs(it0, tid, reinterpret_cast<const uint8_t*>(img), img_n, ipfx, sm, s_bar);
     }
+    if (EPI == 2 && tid == 64) query_constants<S>(reinterpret_cast<double2*>(sm.end + kQueryConstOff()), d, img_n, ipfx, tpfx);
     tmem_fence_before();
     csync<0>();
     tmem_fence_after();
@@ -1174,7 +1197,7 @@ k_match_triple(const float4* __restrict__ That, int64_t part_first,
     uint32_t* s_taddr = reinterpret_cast<uint32_t*>(s_min + NW);
     int* s_nq = reinterpret_cast<int*>(sm.end + 208);                      // [4] query of the triples i, i+1, i+2 (slot i % 3)
     QueryDesc* s_nd = reinterpret_cast<QueryDesc*>(sm.end + 224);          // [2] descriptor of the triples i, i+1 (slot i & 1)
-    static_assert(224 + 2 * sizeof(QueryDesc) <= kSmallBytes && sizeof(QueryDesc) % 16 == 0, "small area");
+    static_assert(224 + 2 * sizeof(QueryDesc) <= kQueryConstOff() && kQueryConstOff() + 32 <= kSmallBytes && sizeof(QueryDesc) % 16 == 0, "small area");
     float4* s_sp = reinterpret_cast<float4*>(sm.end + kSmallBytes);        // EPI 2: units of the self-mirrored quads
     double2* s_w0 = EPI == 2 && is_u8 ? reinterpret_cast<double2*>(sm.end + kSmallBytes + kSpecialBytes) : nullptr;   // [kRounds][QT]
     const Buf& buf = sm.buf;
@@ -1223,6 +1246,7 @@ k_match_triple(const float4* __restrict__ That, int64_t part_first,
     const int nb = d.nk - 3 * lt < 3 ? d.nk - 3 * lt : 3;                 // lag blocks of this triple (uniform)
     const Item it0(d, q, d.k0 + 3 * lt), it1(d, q, d.k0 + 3 * lt + 1), it2(d, q, d.k0 + 3 * lt + 2);
     if (is_u8) stage_inputs(it0, tid, reinterpret_cast<const uint8_t*>(img), img_n, ipfx, sm, s_bar);
+    if (EPI == 2 && tid == 64) query_constants<S>(reinterpret_cast<double2*>(sm.end + kQueryConstOff()), d, img_n, ipfx, tpfx);
     C2 sp1 = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)}, sp2 = sp1;   // C[B/4] of blocks 2 and 3 (warp NW-1, lane 0)
     {
         typedef Rows<FMT> R;
