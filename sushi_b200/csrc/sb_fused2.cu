@@ -445,7 +445,7 @@ __device__ __forceinline__ void query_constants(double2* s_qc, const QueryDesc& 
 // windows -- k_match_ws starts the copies of its next item there.
 template <typename S, int ID, int EPI, typename AfterRead>
 __device__ __forceinline__ void finish_item(const Item& it, int tid, const Smem& sm, unsigned long long* s_bar, unsigned bar_parity,
-                                            unsigned long long* s_best, float* s_min, double2* s_w0,
+                                            unsigned long long* s_best, float* s_min, int2* s_w0,
                                             const S* __restrict__ img, int64_t img_n,
                                             const double2* __restrict__ ipfx, const double2* __restrict__ tpfx,
                                             const PackedTables& tab, unsigned long long* __restrict__ keys,
@@ -544,7 +544,7 @@ __device__ __forceinline__ void finish_item(const Item& it, int tid, const Smem&
                 f_w0q = (float)(w0q + 0.25);
                 f_k0 = 0.f;
                 f_A = (float)(w0q + tsq - 2.0 * (b * w0s + k_const));
-                s_w0[c * QT + tid] = make_double2(w0s, w0q);          // exact sums at the head of the run, for the candidates
+                s_w0[c * QT + tid] = make_int2(is - ts, iq - tq);     // the run's offsets from the warp base, for the candidates
 
             } else {
                 f_w0q = (float)w0q;
@@ -673,8 +673,11 @@ __device__ __forceinline__ void finish_item(const Item& it, int tid, const Smem&
             const unsigned la = (unsigned)(lo8 & keep), lb = (unsigned)((lo8 & keep) >> 32), ha = (unsigned)(hi8 & keep), hb2 = (unsigned)((hi8 & keep) >> 32);
             const int rq = (int)__dp4a(ha, ha, __dp4a(hb2, hb2, 0u)) - (int)__dp4a(la, la, __dp4a(lb, lb, 0u));
             const int rs = (int)__dp4a(ha, 0x01010101u, __dp4a(hb2, 0x01010101u, 0u)) - (int)__dp4a(la, 0x01010101u, __dp4a(lb, 0x01010101u, 0u));
-            const double2 w0 = s_w0[c * QT + tid];
-            wsum = w0.x + (double)rs; wsq = w0.y + (double)rq;
+            // the run's head sums exactly as the screening loop formed them: warp base + intra-warp offsets
+            const double2 b_lo = sm.base[(c * NW + warp) * 2], b_hi = sm.base[(c * NW + warp) * 2 + 1];
+            const int2 off = s_w0[c * QT + tid];
+            const double w0s = (b_hi.x - b_lo.x) + (double)off.x, w0q = (b_hi.y - b_lo.y) + (double)off.y;
+            wsum = w0s + (double)rs; wsq = w0q + (double)rq;
         } else {
             const double2 p_hi = ipfx[j + n], p_lo = ipfx[j];
             wsum = p_hi.x - p_lo.x; wsq = p_hi.y - p_lo.y;
@@ -723,7 +726,7 @@ k_match_packed(const float4* __restrict__ That, int64_t part_first,
     unsigned long long* s_best = s_bar + 1;                                // [NW]
     float* s_min = reinterpret_cast<float*>(s_best + NW);                  // [NW]
     float4* s_sp = reinterpret_cast<float4*>(sm.end + kSmallBytes);        // EPI 2: units of the self-mirrored quads
-    double2* s_w0 = EPI == 2 && is_u8 ? reinterpret_cast<double2*>(sm.end + kSmallBytes + kSpecialBytes) : nullptr;   // [kRounds][QT]
+    int2* s_w0 = EPI == 2 && is_u8 ? reinterpret_cast<int2*>(sm.end + kSmallBytes + kSpecialBytes) : nullptr;   // [kRounds][QT]
     const Buf& buf = sm.buf;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1042,7 +1045,7 @@ k_match_pair(const float4* __restrict__ That, int64_t part_first,
     float* s_min = reinterpret_cast<float*>(s_best + NW);                  // [NW]
     uint32_t* s_taddr = reinterpret_cast<uint32_t*>(s_min + NW);
     float4* s_sp = reinterpret_cast<float4*>(sm.end + kSmallBytes);        // EPI 2: units of the self-mirrored quads
-    double2* s_w0 = EPI == 2 && is_u8 ? reinterpret_cast<double2*>(sm.end + kSmallBytes + kSpecialBytes) : nullptr;   // [kRounds][QT]
+    int2* s_w0 = EPI == 2 && is_u8 ? reinterpret_cast<int2*>(sm.end + kSmallBytes + kSpecialBytes) : nullptr;   // [kRounds][QT]
     const Buf& buf = sm.buf;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1199,7 +1202,7 @@ k_match_triple(const float4* __restrict__ That, int64_t part_first,
     QueryDesc* s_nd = reinterpret_cast<QueryDesc*>(sm.end + 224);          // [2] descriptor of the triples i, i+1 (slot i & 1)
     static_assert(224 + 2 * sizeof(QueryDesc) <= kQueryConstOff() && kQueryConstOff() + 32 <= kSmallBytes && sizeof(QueryDesc) % 16 == 0, "small area");
     float4* s_sp = reinterpret_cast<float4*>(sm.end + kSmallBytes);        // EPI 2: units of the self-mirrored quads
-    double2* s_w0 = EPI == 2 && is_u8 ? reinterpret_cast<double2*>(sm.end + kSmallBytes + kSpecialBytes) : nullptr;   // [kRounds][QT]
+    int2* s_w0 = EPI == 2 && is_u8 ? reinterpret_cast<int2*>(sm.end + kSmallBytes + kSpecialBytes) : nullptr;   // [kRounds][QT]
     const Buf& buf = sm.buf;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1496,7 +1499,7 @@ size_t forward_smem_bytes14() {
 }
 
 size_t packed_smem_bytes(int epi = 1) {      // epilogue 2 keeps the runs' exact head sums next to the small arrays
-    return epi == 2 ? kSmemCommon + kSmallBytes + kSpecialBytes + (size_t)kRounds * QT * sizeof(double2)
+    return epi == 2 ? kSmemCommon + kSmallBytes + kSpecialBytes + (size_t)kRounds * QT * sizeof(int2)
                     : kSmemCommon + 8 + QNW * sizeof(unsigned long long) + QNW * sizeof(float) + 64;
 }
 
