@@ -368,10 +368,15 @@ __device__ __forceinline__ C2 special_from_smem(const float4* s_sp, int P, int g
 // last load of the slowest warp has come back before anyone computes, so the 1024 cycles the shared-memory pipe
 // needs for a pass's loads are not overlapped by arithmetic.  MIDBAR = true (opt-in with EPI 2) puts it between
 // the second and the third butterfly stage -- the latest loads overlap the first half of the arithmetic of the
-// warps served earlier, the earliest stores the second half of the others'.
+// warps served earlier, the earliest stores the second half of the others'.  It also requests the twiddles of the
+// NEXT pass (and the epilogue's pair, which it returns) before the barrier that ends a pass, when the butterfly
+// registers are dead: the multiply phase streams hundreds of kilobytes through L1, so these table reads come from
+// L2, and the first thing a pass does with its data is multiply by them.
 template <int ID, bool MIDBAR = false>
-__device__ __forceinline__ void fft_passes(const Buf& buf, int tid, const PackedTables& tab, bool drain_cp_async) {
+__device__ __forceinline__ float4 fft_passes(const Buf& buf, int tid, const PackedTables& tab, bool drain_cp_async) {
     C2 v[16];
+    float4 tw[8];
+    float4 wt = make_float4(0.f, 0.f, 0.f, 0.f);
     const int src = phys(tid);
     {   // pass 1: Ns = 1, no twiddles; out chunk 16j + r -> 17j + r
 #pragma unroll
@@ -381,13 +386,18 @@ __device__ __forceinline__ void fft_passes(const Buf& buf, int tid, const Packed
         const int dst = 17 * tid;
 #pragma unroll
         for (int r = 0; r < 16; ++r) buf.st(dst + r, v[brev<16>(r)]);
+        if (MIDBAR) {
+#pragma unroll
+            for (int a = 0; a < 8; ++a) tw[a] = __ldg(tab.tw2 + a * 16 + (tid & 15));
+        }
         csync<ID>();
     }
     {   // pass 2: Ns = 16, k = tid & 15; out chunk 256a + 16r + k -> 272a + 17r + k, a = tid >> 4
         const int kk = tid & 15;
-        float4 tw[8];
+        if (!MIDBAR) {
 #pragma unroll
-        for (int a = 0; a < 8; ++a) tw[a] = __ldg(tab.tw2 + a * 16 + kk);
+            for (int a = 0; a < 8; ++a) tw[a] = __ldg(tab.tw2 + a * 16 + kk);
+        }
 #pragma unroll
         for (int r = 0; r < 16; ++r) v[r] = buf.ld(src + 544 * r);
         if (!MIDBAR) csync<ID>();
@@ -401,13 +411,18 @@ __device__ __forceinline__ void fft_passes(const Buf& buf, int tid, const Packed
         const int dst = 272 * (tid >> 4) + kk;
 #pragma unroll
         for (int r = 0; r < 16; ++r) buf.st(dst + 17 * r, v[brev<16>(r)]);
+        if (MIDBAR) {
+#pragma unroll
+            for (int a = 0; a < 8; ++a) tw[a] = __ldg(tab.tw3 + a * 256 + (tid & 255));
+        }
         csync<ID>();
     }
     {   // pass 3: Ns = 256, k = tid & 255; out chunk 4096a + 256r + k -> 4352a + 272r + phys(k), a = tid >> 8
         const int kk = tid & 255;
-        float4 tw[8];
+        if (!MIDBAR) {
 #pragma unroll
-        for (int a = 0; a < 8; ++a) tw[a] = __ldg(tab.tw3 + a * 256 + kk);
+            for (int a = 0; a < 8; ++a) tw[a] = __ldg(tab.tw3 + a * 256 + kk);
+        }
 #pragma unroll
         for (int r = 0; r < 16; ++r) v[r] = buf.ld(src + 544 * r);
         if (!MIDBAR) csync<ID>();
@@ -421,9 +436,11 @@ __device__ __forceinline__ void fft_passes(const Buf& buf, int tid, const Packed
         const int dst = 4352 * (tid >> 8) + phys(kk);
 #pragma unroll
         for (int r = 0; r < 16; ++r) buf.st(dst + 272 * r, v[brev<16>(r)]);
+        if (MIDBAR) wt = __ldg(reinterpret_cast<const float4*>(tab.w8) + tid);    // W8192^(2tid), W8192^(2tid+1) for the epilogue
         if (drain_cp_async) cp_async_commit_wait_all();     // the staged running sums landed long ago
         csync<ID>();
     }
+    return wt;
 }
 
 // EPI 2: the constants of a query every thread needs in finish_item -- sums of the template (two reads of its
@@ -449,7 +466,8 @@ __device__ __forceinline__ void finish_item(const Item& it, int tid, const Smem&
                                             const S* __restrict__ img, int64_t img_n,
                                             const double2* __restrict__ ipfx, const double2* __restrict__ tpfx,
                                             const PackedTables& tab, unsigned long long* __restrict__ keys,
-                                            float* __restrict__ curve_out, AfterRead after_read) {
+                                            float* __restrict__ curve_out, AfterRead after_read,
+                                            float4 wt_in = make_float4(0.f, 0.f, 0.f, 0.f)) {
     constexpr int B = QB, NW = QNW, LB = QB, ROUNDS = kRounds, LAGS_PER_ROUND = kLagsPerRound;
     constexpr bool is_u8 = sizeof(S) == 1;
     constexpr bool v2 = EPI == 2 && is_u8;                 // trimmed screening (see the comment at its loop)
@@ -480,7 +498,8 @@ __device__ __forceinline__ void finish_item(const Item& it, int tid, const Smem&
 
     // chunks 2*tid, 2*tid+1 of every round: physical offsets and twiddles
     const int ech = 2 * tid + (tid >> 3);                              // + 1088*c + e; O is 4352 further
-    const float4 wt = __ldg(reinterpret_cast<const float4*>(tab.w8) + tid);   // W8192^(2tid), W8192^(2tid+1)
+    // W8192^(2tid), W8192^(2tid+1): requested by the last FFT pass already when it ran with MIDBAR (EPI 2)
+    const float4 wt = (v2 && SB_V2_MIDBAR) ? wt_in : __ldg(reinterpret_cast<const float4*>(tab.w8) + tid);
 
     float vf[ROUNDS][8];
     float tmin = kSent;
@@ -799,8 +818,8 @@ k_match_packed(const float4* __restrict__ That, int64_t part_first,
     csync<0>();
 
     // ---------------- 3. inverse FFT, 4. epilogue ---------------------------------------------
-    fft_passes<0, EPI == 2 && SB_V2_MIDBAR>(buf, tid, tab, is_u8);
-    finish_item<S, 0, EPI>(it, tid, sm, s_bar, 0u, s_best, s_min, s_w0, img, img_n, ipfx, tpfx, tab, keys, curve_out, [] {});
+    const float4 wt0 = fft_passes<0, EPI == 2 && SB_V2_MIDBAR>(buf, tid, tab, is_u8);
+    finish_item<S, 0, EPI>(it, tid, sm, s_bar, 0u, s_best, s_min, s_w0, img, img_n, ipfx, tpfx, tab, keys, curve_out, [] {}, wt0);
 }
 
 // ---------------------------------------------------------------- kernel B: persistent, warp-specialised
@@ -1143,9 +1162,9 @@ k_match_pair(const float4* __restrict__ That, int64_t part_first,
     csync<0>();
 
     // ---------------- first item: inverse FFT + epilogue ---------------------------------------
-    fft_passes<0, EPI == 2 && SB_V2_MIDBAR>(buf, tid, tab, is_u8);
+    const float4 wt0 = fft_passes<0, EPI == 2 && SB_V2_MIDBAR>(buf, tid, tab, is_u8);
     finish_item<S, 0, EPI>(it0, tid, sm, s_bar, 0u, s_best, s_min, s_w0, img, img_n, ipfx, tpfx, tab, keys, curve_out,
-                      [&] { if (is_u8 && has2) stage_inputs(it1, tid, reinterpret_cast<const uint8_t*>(img), img_n, ipfx, sm, s_bar); });
+                      [&] { if (is_u8 && has2) stage_inputs(it1, tid, reinterpret_cast<const uint8_t*>(img), img_n, ipfx, sm, s_bar); }, wt0);
 
     // ---------------- second item: out of tensor memory, then the same ---------------------------
     if (has2) {                                       // uniform over the CTA
@@ -1166,8 +1185,8 @@ k_match_pair(const float4* __restrict__ That, int64_t part_first,
         }
         if (tid == (NW - 1) * 32) buf.st(phys(Q4), sp1);
         csync<0>();
-        fft_passes<0, EPI == 2 && SB_V2_MIDBAR>(buf, tid, tab, is_u8);
-        finish_item<S, 0, EPI>(it1, tid, sm, s_bar, 1u, s_best, s_min, s_w0, img, img_n, ipfx, tpfx, tab, keys, curve_out, [] {});
+        const float4 wtj = fft_passes<0, EPI == 2 && SB_V2_MIDBAR>(buf, tid, tab, is_u8);
+        finish_item<S, 0, EPI>(it1, tid, sm, s_bar, 1u, s_best, s_min, s_w0, img, img_n, ipfx, tpfx, tab, keys, curve_out, [] {}, wtj);
     }
     tmem_fence_before();
     csync<0>();
@@ -1322,9 +1341,9 @@ k_match_triple(const float4* __restrict__ That, int64_t part_first,
     csync<0>();
 
     // ---------------- first item: inverse FFT + epilogue ---------------------------------------
-    fft_passes<0, EPI == 2 && SB_V2_MIDBAR>(buf, tid, tab, is_u8);
+    const float4 wt0 = fft_passes<0, EPI == 2 && SB_V2_MIDBAR>(buf, tid, tab, is_u8);
     finish_item<S, 0, EPI>(it0, tid, sm, s_bar, ph & 1u, s_best, s_min, s_w0, img, img_n, ipfx, tpfx, tab, keys, curve_out,
-                           [&] { if (is_u8 && nb > 1) stage_inputs(it1, tid, reinterpret_cast<const uint8_t*>(img), img_n, ipfx, sm, s_bar); });
+                           [&] { if (is_u8 && nb > 1) stage_inputs(it1, tid, reinterpret_cast<const uint8_t*>(img), img_n, ipfx, sm, s_bar); }, wt0);
 
     // ---------------- second and third item: out of tensor memory, then the same ------------------
 #pragma unroll 1
@@ -1347,12 +1366,12 @@ k_match_triple(const float4* __restrict__ That, int64_t part_first,
         }
         if (tid == (NW - 1) * 32) buf.st(phys(Q4), j == 1 ? sp1 : sp2);
         csync<0>();
-        fft_passes<0, EPI == 2 && SB_V2_MIDBAR>(buf, tid, tab, is_u8);
+        const float4 wtj = fft_passes<0, EPI == 2 && SB_V2_MIDBAR>(buf, tid, tab, is_u8);
         if (j == 1)
             finish_item<S, 0, EPI>(it1, tid, sm, s_bar, (ph + 1u) & 1u, s_best, s_min, s_w0, img, img_n, ipfx, tpfx, tab, keys, curve_out,
-                                   [&] { if (is_u8 && nb > 2) stage_inputs(it2, tid, reinterpret_cast<const uint8_t*>(img), img_n, ipfx, sm, s_bar); });
+                                   [&] { if (is_u8 && nb > 2) stage_inputs(it2, tid, reinterpret_cast<const uint8_t*>(img), img_n, ipfx, sm, s_bar); }, wtj);
         else
-            finish_item<S, 0, EPI>(it2, tid, sm, s_bar, (ph + 2u) & 1u, s_best, s_min, s_w0, img, img_n, ipfx, tpfx, tab, keys, curve_out, [] {});
+            finish_item<S, 0, EPI>(it2, tid, sm, s_bar, (ph + 2u) & 1u, s_best, s_min, s_w0, img, img_n, ipfx, tpfx, tab, keys, curve_out, [] {}, wtj);
     }
     ph += (unsigned)nb;
     }   // next triple of this CTA
