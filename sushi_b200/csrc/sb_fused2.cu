@@ -1039,6 +1039,38 @@ k_match_ws(const float4* __restrict__ That, int64_t part_first,
     if (warp == 0) tmem_dealloc(taddr, 512);
 }
 
+// A parked product spectrum back into the FFT buffer: this thread's 64 tensor-memory columns hold, quad by quad,
+// the chunks C[i] and C[B/2 - i] it packed (i = tid + 512*uu).  BATCH = false (measured default): 16 columns at a
+// time, each load waited for before its stores; BATCH = true (opt-in with EPI 2): all four loads in flight, one wait.
+template <bool BATCH>
+__device__ __forceinline__ void unpark(uint32_t tsrc, const Buf& buf, int col, int mcol, int tid) {
+    auto put = [&](const float (&v)[16], int c4) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int uu = 2 * c4 + h;
+            const C2 lo = {make_float2(v[8 * h + 0], v[8 * h + 1]), make_float2(v[8 * h + 2], v[8 * h + 3])};
+            const C2 hi = {make_float2(v[8 * h + 4], v[8 * h + 5]), make_float2(v[8 * h + 6], v[8 * h + 7])};
+            buf.st(col + 544 * uu, lo);
+            if (tid != 0) buf.st(mcol + 544 * (15 - uu), hi);
+            else if (uu != 0) buf.st(mcol + 544 * (16 - uu), hi);
+        }
+    };
+    if (BATCH) {
+        float v0[16], v1[16], v2[16], v3[16];
+        tmem_ld16(tsrc, v0); tmem_ld16(tsrc + 16u, v1); tmem_ld16(tsrc + 32u, v2); tmem_ld16(tsrc + 48u, v3);
+        tmem_wait_ld();
+        put(v0, 0); put(v1, 1); put(v2, 2); put(v3, 3);
+    } else {
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+            float v[16];
+            tmem_ld16(tsrc + (uint32_t)(c4 * 16), v);
+            tmem_wait_ld();
+            put(v, c4);
+        }
+    }
+}
+
 // ---------------------------------------------------------------- kernel A2: one CTA per PAIR of lag blocks
 // The multiply phase of k_match_packed runs at the SM's L2 read rate (each item pulls 2 x P rows of 131 KB).
 // Two consecutive lag blocks k, k+1 of one query use the same template rows T^_p and overlapping spectrum rows
@@ -1168,21 +1200,7 @@ k_match_pair(const float4* __restrict__ That, int64_t part_first,
 
     // ---------------- second item: out of tensor memory, then the same ---------------------------
     if (has2) {                                       // uniform over the CTA
-#pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4) {
-            float v[16];
-            tmem_ld16(tcol + (uint32_t)(c4 * 16), v);
-            tmem_wait_ld();
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int uu = 2 * c4 + h;
-                const C2 lo = {make_float2(v[8 * h + 0], v[8 * h + 1]), make_float2(v[8 * h + 2], v[8 * h + 3])};
-                const C2 hi = {make_float2(v[8 * h + 4], v[8 * h + 5]), make_float2(v[8 * h + 6], v[8 * h + 7])};
-                buf.st(col + 544 * uu, lo);
-                if (tid != 0) buf.st(mcol + 544 * (15 - uu), hi);
-                else if (uu != 0) buf.st(mcol + 544 * (16 - uu), hi);
-            }
-        }
+        unpark<EPI == 2>(tcol, buf, col, mcol, tid);
         if (tid == (NW - 1) * 32) buf.st(phys(Q4), sp1);
         csync<0>();
         const float4 wtj = fft_passes<0, EPI == 2 && SB_V2_MIDBAR>(buf, tid, tab, is_u8);
@@ -1349,21 +1367,7 @@ k_match_triple(const float4* __restrict__ That, int64_t part_first,
 #pragma unroll 1
     for (int j = 1; j < nb; ++j) {                    // uniform over the CTA
         const uint32_t tsrc = tcol + (j == 2 ? 256u : 0u);
-#pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4) {
-            float v[16];
-            tmem_ld16(tsrc + (uint32_t)(c4 * 16), v);
-            tmem_wait_ld();
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int uu = 2 * c4 + h;
-                const C2 lo = {make_float2(v[8 * h + 0], v[8 * h + 1]), make_float2(v[8 * h + 2], v[8 * h + 3])};
-                const C2 hi = {make_float2(v[8 * h + 4], v[8 * h + 5]), make_float2(v[8 * h + 6], v[8 * h + 7])};
-                buf.st(col + 544 * uu, lo);
-                if (tid != 0) buf.st(mcol + 544 * (15 - uu), hi);
-                else if (uu != 0) buf.st(mcol + 544 * (16 - uu), hi);
-            }
-        }
+        unpark<EPI == 2>(tsrc, buf, col, mcol, tid);
         if (tid == (NW - 1) * 32) buf.st(phys(Q4), j == 1 ? sp1 : sp2);
         csync<0>();
         const float4 wtj = fft_passes<0, EPI == 2 && SB_V2_MIDBAR>(buf, tid, tab, is_u8);
