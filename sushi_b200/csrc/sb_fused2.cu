@@ -47,6 +47,9 @@ using namespace sbf;
 #ifndef SB_V2_MIDBAR
 #define SB_V2_MIDBAR 1
 #endif
+#ifndef SB_V2_MIDBAR_SPLIT      // last butterfly stage (h) in front of the barrier in passes 2 and 3: 4 (default) or 8
+#define SB_V2_MIDBAR_SPLIT 4
+#endif
 #ifndef SB_V2_SPECIAL_PREFETCH
 #define SB_V2_SPECIAL_PREFETCH 1
 #endif
@@ -406,7 +409,7 @@ __device__ __forceinline__ float4 fft_passes(const Buf& buf, int tid, const Pack
             const float4 t = tw[r >> 1];
             v[r] = (r & 1) ? cmul_s(v[r], t.z, t.w) : cmul_s(v[r], t.x, t.y);
         }
-        if (MIDBAR) { dft16p<8, 4>(v); csync<ID>(); dft16p<2, 1>(v); }
+        if (MIDBAR) { dft16p<8, SB_V2_MIDBAR_SPLIT>(v); csync<ID>(); dft16p<SB_V2_MIDBAR_SPLIT / 2, 1>(v); }
         else dft16p(v);
         const int dst = 272 * (tid >> 4) + kk;
 #pragma unroll
@@ -431,7 +434,7 @@ __device__ __forceinline__ float4 fft_passes(const Buf& buf, int tid, const Pack
             const float4 t = tw[r >> 1];
             v[r] = (r & 1) ? cmul_s(v[r], t.z, t.w) : cmul_s(v[r], t.x, t.y);
         }
-        if (MIDBAR) { dft16p<8, 4>(v); csync<ID>(); dft16p<2, 1>(v); }
+        if (MIDBAR) { dft16p<8, SB_V2_MIDBAR_SPLIT>(v); csync<ID>(); dft16p<SB_V2_MIDBAR_SPLIT / 2, 1>(v); }
         else dft16p(v);
         const int dst = 4352 * (tid >> 8) + phys(kk);
 #pragma unroll
