@@ -2,6 +2,9 @@
 # First GPU pass of round 2 (run under gpurun from the repo root, one B200): does the default path still pass,
 # do the two opt-in variants written blind at the end of round 1 (sb_set_epilogue(2), engine 6) give bit-identical
 # results, and what do they cost.  Everything lands in gpurun_out/.
+# Parts of the second kernel body can be compiled out to attribute a difference (rebuild HERE, the .so travels):
+#   touch sushi_b200/csrc/sb_fused2.cu && make -C sushi_b200/csrc EXTRA="-DSB_V2_MIDBAR=0"            (or =1 default)
+#   EXTRA="-DSB_V2_MIDBAR_SPLIT=8"   EXTRA="-DSB_V2_SPECIAL_PREFETCH=0"
 O=gpurun_out
 mkdir -p $O
 timeout 400 python -m pytest tests -x -q -m gpu > $O/pytest_gpu.txt 2>&1; tail -3 $O/pytest_gpu.txt
