@@ -410,3 +410,29 @@ def test_emulated_config1_against_the_live_oracle(emu):
         assert np.abs(times - want_t).max() <= 1.0 / 12000 + 1e-9
         ok = ends + 1.5 < 60.0
         assert np.abs((times - starts)[ok] - 1.5).max() <= 1.0 / 12000 + 1e-9        # the known answer
+
+
+@pytest.mark.parametrize('seed', [101, 102, 103, 104])
+def test_emulated_random_queries_all_variants_agree(emu, seed):
+    """Random template lengths (all residues of the window alignment), random ranges: the measured default (one CTA
+    per lag block, first screening loop) against the opt-in stack on float32 rows, bit for bit, and against the
+    closed form."""
+    rng = np.random.default_rng(seed)
+    n_img = int(rng.integers(2 * B + 100, 5 * B))
+    img = programme(n_img, seed)
+    src = np.clip(np.roll(img, -int(rng.integers(0, 4000))).astype(np.int32) + rng.integers(-4, 5, n_img), 0, 255).astype(np.uint8)
+    queries = []
+    for _ in range(5):
+        n = int(rng.integers(1, min(3 * B, n_img - 10)))
+        toff = int(rng.integers(0, n_img - n + 1))
+        lag0 = int(rng.integers(0, n_img - n + 1))
+        nlags = int(rng.integers(1, n_img - n - lag0 + 2))
+        queries.append((toff, n, lag0, min(nlags, 2 * B + 5000)))
+    c = Case(emu, img, src, queries, np.uint8)
+    truth = c.truth()
+    d0, i0, _ = c.run(0, 1, curves=False)
+    for kernel, epi in ((1, 2), (2, 2)):
+        d, i, _ = c.run(kernel, epi, curves=False)
+        assert np.array_equal(d, d0) and np.array_equal(i, i0), (seed, kernel, epi, queries)
+    for q, t in enumerate(truth):
+        assert abs(float(d0[q]) - float(t.min())) <= 3e-6 and abs(int(i0[q]) - int(t.argmin())) <= 1, (seed, q, queries[q])
