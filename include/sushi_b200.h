@@ -211,6 +211,36 @@ int sb_load_pcm(const void* pcm_host, int64_t frames, int channels, int sample_w
 int sb_normalise(const sb_stream* raw_f32, int dtype, sb_stream** out,
                  float* min3_out, float* max3_out);
 
+/* ---- multi-GPU: events shard across ranks ---------------- */
+
+/* One process per GPU.  The library owns an NCCL communicator (libnccl is opened with dlopen on the first
+ * of these calls; single-GPU users never need it).  The path has exactly two collectives, both outside the
+ * kernels: a broadcast of the normalised streams (the reference's WavStream.data, wav.py:119-156, which every
+ * rank needs) and an all-gather of the per-event (diff, idx) pairs find_substream returns (wav.py:188).
+ * Rendezvous is the caller's business: rank 0 obtains SB_COMM_ID_BYTES opaque bytes from sb_comm_unique_id,
+ * hands them to the other ranks by any means, then every rank calls sb_comm_init (collective). */
+#define SB_COMM_ID_BYTES 128
+int sb_comm_unique_id(void* id_out);
+int sb_comm_init(const void* id, int world_size, int rank);
+int sb_comm_destroy(void);
+int sb_comm_world_size(void);                 /* 1 without a communicator */
+int sb_comm_rank(void);
+int sb_comm_nccl_version(void);               /* e.g. 22703; -1 if libnccl cannot be opened */
+/* Broadcast `bytes` bytes of device memory in place from `root`.  Runs on the library's communication
+ * stream, ordered behind everything the library stream has been given so far; `slot` (0..3) names the
+ * completion event.  sb_comm_wait(slot) makes the library stream wait for that broadcast only, so the
+ * broadcast of one stream overlaps the running sums and spectra of another. */
+int sb_comm_broadcast(void* dev_buf, int64_t bytes, int root, int slot);
+int sb_comm_wait(int slot);
+/* All-gather on the library stream: every rank contributes bytes_per_rank bytes of device memory,
+ * dev_recv receives world_size * bytes_per_rank bytes in rank order. */
+int sb_comm_all_gather(const void* dev_send, void* dev_recv, int64_t bytes_per_rank);
+/* Blocking helpers for measurement: element-wise maximum over ranks of up to 32 host floats (device
+ * times are reported as the maximum over ranks), and a barrier that returns once every rank's
+ * library and communication streams have drained. */
+int sb_comm_max_f32(float* host_inout, int count);
+int sb_comm_barrier(void);
+
 /* ---- measurement ------------------------------------------------------- */
 
 /* Device timer on the library stream (CUDA events). */

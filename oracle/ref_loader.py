@@ -49,6 +49,11 @@ def parse_header(f, path):
     raise ValueError('Invalid WAV file')
 
 
+def _py2_round(x):
+    """The reference runs under Python 2, whose round() goes half away from zero (wav.py:127)."""
+    return math.floor(x + 0.5) if x >= 0 else -math.floor(-x + 0.5)
+
+
 def readframes(raw, sample_width, channels):          # wav.py:64-91
     if sample_width == 2:
         unpacked = np.frombuffer(raw, dtype=np.int16)
@@ -82,7 +87,7 @@ def load_stream(read_raw, frames_count, framerate, sample_width, channels, sampl
     samples_read = padding_size
     while seconds_read < total_seconds:
         chunk = readframes(read_raw(int(1 * framerate)), sample_width, channels)
-        new_length = int(round(len(chunk) * downsample_rate))
+        new_length = int(_py2_round(len(chunk) * downsample_rate))
         dst_view = data[0][samples_read:samples_read + new_length]
         if downsample_rate != 1:
             chunk = chunk.reshape((1, len(chunk)))

@@ -61,6 +61,17 @@ PROTOTYPES = {
     'sb_load_pcm': (ctypes.c_int, [c_vp, c_i64, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                    c_i64, c_i64, ctypes.POINTER(c_vp)]),
     'sb_normalise': (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.POINTER(c_vp), c_f32p, c_f32p]),
+    'sb_comm_unique_id': (ctypes.c_int, [c_vp]),
+    'sb_comm_init': (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int]),
+    'sb_comm_destroy': (ctypes.c_int, []),
+    'sb_comm_world_size': (ctypes.c_int, []),
+    'sb_comm_rank': (ctypes.c_int, []),
+    'sb_comm_nccl_version': (ctypes.c_int, []),
+    'sb_comm_broadcast': (ctypes.c_int, [c_vp, c_i64, ctypes.c_int, ctypes.c_int]),
+    'sb_comm_wait': (ctypes.c_int, [ctypes.c_int]),
+    'sb_comm_all_gather': (ctypes.c_int, [c_vp, c_vp, c_i64]),
+    'sb_comm_max_f32': (ctypes.c_int, [c_f32p, ctypes.c_int]),
+    'sb_comm_barrier': (ctypes.c_int, []),
     'sb_timer_start': (ctypes.c_int, []),
     'sb_timer_stop': (ctypes.c_int, [c_f32p]),
     'sb_profile_enable': (ctypes.c_int, [ctypes.c_int]),

@@ -12,7 +12,14 @@ def clip(value, minimum, maximum):
     return max(min(value, maximum), minimum)
 
 
+def py2_round(x):
+    """round() as Python 2 does it (half away from zero): the reference is py2 code
+    (wav.py:127, common.py:33, subs.py:116)."""
+    import math
+    return math.floor(x + 0.5) if x >= 0 else -math.floor(-x + 0.5)
+
+
 def format_time(seconds):
-    cs = round(seconds * 100)
+    cs = py2_round(seconds * 100)
     return '{0}:{1:02d}:{2:02d}.{3:02d}'.format(
         int(cs // 360000), int((cs // 6000) % 60), int((cs // 100) % 60), int(cs % 100))

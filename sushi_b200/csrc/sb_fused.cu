@@ -446,10 +446,7 @@ int launch_typed(const sb_stream* image, const sb_stream* tmpl, const float2* d_
     FusedTables tab;
     SB_TRY(ensure_tables<LOGN>(&tab));
     static bool attr_set = false;
-    // SB_FUSED_EXTRA_SMEM (bytes): occupancy experiments only -- inflates the dynamic shared memory so
-    // fewer CTAs fit on an SM
-    static const size_t extra = getenv("SB_FUSED_EXTRA_SMEM") ? (size_t)atol(getenv("SB_FUSED_EXTRA_SMEM")) : 0;
-    const size_t smem = fused_smem_bytes<LOGN, HD>() + extra;
+    const size_t smem = fused_smem_bytes<LOGN, HD>();
     if (!attr_set) {
         SB_CUDA(cudaFuncSetAttribute(k_match_fused<LOGN, S, HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;

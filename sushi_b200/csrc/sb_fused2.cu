@@ -43,7 +43,7 @@ using namespace sb;
 using namespace sbf;
 
 // Parts of the second kernel body (EPI 2) that can be compiled out one by one to attribute a measured difference
-// (make NVCCFLAGS+=-DSB_V2_MIDBAR=0 ...): barrier placement in the FFT passes, prefetch of the self-mirrored quad.
+// (make EXTRA=-DSB_V2_MIDBAR=0 ...): barrier placement in the FFT passes, prefetch of the self-mirrored quad.
 #ifndef SB_V2_MIDBAR
 #define SB_V2_MIDBAR 1
 #endif

@@ -58,7 +58,7 @@ struct Ctx {
     int B = 16384;                 // lag-block size (samples); FFT size is 2B
     int chunk_items = 1024;        // items per MAC/C2R/normalise chunk (cuFFT engine)
     int engine = 2;                // 2: packed fused kernels (sb_fused2.cu, B = 16384; default), 3: persistent warp-specialised variant, 4 / 5: always / never pairs of lag blocks, 6: triples (opt-in), 1: fused lag-block kernel (sb_fused.cu), 0: cuFFT pipeline
-    int premac_mode = 0;           // 0: register-blocked multiply kernel when a batch averages >= 3 partitions, 1: never, 2: always
+    int premac_mode = 0;           // 0: register-blocked multiply kernel for queries whose template spans >= 12 partitions, 1: never, 2: always
     int epilogue = 1;              // screening loop of the packed kernels on uint8 streams: 1 = first version (default), 2 = trimmed (sb_set_epilogue)
     int spectra_fmt = 0;           // quad rows of the packed kernels: 0 = float32 (default), 1 = 16-bit block floating point (sb_set_spectra)
     int hop_mode = 1;              // fused engine geometry: 1 = hop B (50 % of each FFT valid, default), 2 = hop B/2 (75 %), 0 = pick per batch

@@ -487,8 +487,8 @@ int run_batch(const sb_stream* image_c, const sb_stream* tmpl, int64_t count,
     SB_TRY(grow(&c.d_parts, &c.parts_cap, parts_cap_want * part_row_f2));
     const int64_t chunk = std::min<int64_t>(c.chunk_items, total_items);
     if (!use_fused) SB_TRY(grow(&c.d_items, &c.items_cap, chunk * nb));
-    // lag blocks per product buffer (0.5 GB at B = 16384); SB_PREMAC_CHUNK overrides it for experiments
-    static const int64_t premac_chunk = getenv("SB_PREMAC_CHUNK") ? atoll(getenv("SB_PREMAC_CHUNK")) : 4096;
+    // lag blocks per product buffer (0.5 GB at B = 16384)
+    const int64_t premac_chunk = 4096;
 
     const int gchunks = (2 * B + 2047) / 2048;
     const int mchunks = (nb + MAC_BINS - 1) / MAC_BINS;

@@ -297,8 +297,8 @@ int sb_stream_create_device(const void* dev_samples, int64_t n, int dtype, sb_st
     sb_stream* s = *out;
     Ctx& c = ctx();
     const size_t esz = dtype == SB_U8 ? 1 : 4;
+    // enqueue only: the caller may have ordered the library stream behind a broadcast that is still in flight
     cudaError_t e = cudaMemcpyAsync(s->d_raw, dev_samples, esz * n, cudaMemcpyDeviceToDevice, c.stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(c.stream);
     if (e != cudaSuccess) { sb_stream_destroy(s); *out = nullptr; SB_FAIL(SB_ECUDA, "sb_stream_create_device: D2D copy: %s", cudaGetErrorString(e)); }
     int rc = stream_finish(s);
     if (rc != SB_OK) { sb_stream_destroy(s); *out = nullptr; }

@@ -62,18 +62,31 @@ def smooth_events(events, radius):
         e.set_shift(s, e.diff)
 
 
+def _column(events, attr):
+    """One attribute of many events as an array, or None when the values are not all of one numeric
+    type (then NumPy's array promotion would differ from the reference's scalar-by-scalar arithmetic
+    and the callers fall back to their scalar loops).  Same-typed values keep their type: matcher
+    diffs are np.float32 and are compared / divided in float32 exactly like the scalars are."""
+    values = [getattr(e, attr) for e in events]
+    kinds = set(map(type, values))
+    if len(kinds) != 1 or not issubclass(next(iter(kinds)), (float, int, np.floating, np.integer)):
+        return None
+    return np.array(values)
+
+
 def detect_groups(events_iter):
-    """Split at every jump of more than ALLOWED_ERROR between neighbours (sushi.py:120-127)."""
-    groups = []
-    last = None
-    for e in events_iter:
-        if last is None or abs(e.shift - last.shift) > ALLOWED_ERROR:
-            groups.append([])
-        groups[-1].append(e)
-        last = e
-    if not groups:
+    """Split at every jump of more than ALLOWED_ERROR between neighbours (sushi.py:120-127).  One
+    vectorised difference over the shift column gives the cut points."""
+    events = events_iter if isinstance(events_iter, list) else list(events_iter)
+    if not events:
         raise StopIteration      # the reference calls next() on an empty iterator here
-    return groups
+    shifts = _column(events, 'shift')
+    if shifts is None:
+        cuts = [i for i in range(1, len(events)) if abs(events[i].shift - events[i - 1].shift) > ALLOWED_ERROR]
+    else:
+        cuts = (np.flatnonzero(np.abs(shifts[1:] - shifts[:-1]) > ALLOWED_ERROR) + 1).tolist()
+    bounds = [0] + cuts + [len(events)]
+    return [events[a:b] for a, b in zip(bounds[:-1], bounds[1:])]
 
 
 def groups_from_chapters(events, times):
@@ -132,22 +145,30 @@ def split_broken_groups(groups):
 def fix_near_borders(events):
     """Events at either end whose diff is far from the typical one are linked to the first sane
     event inwards (sushi.py:190-215)."""
-    def sweep(seq, median_diff):
-        limit = min(np.median([e.diff for e in seq[:10]]), median_diff)
-        broken = []
-        for e in seq:
-            if 0.2 < (e.diff / limit) < 5:
-                for b in broken:
-                    b.link_event(e)
-                return len(broken)
-            broken.append(e)
-        return 0
+    def sweep(seq, diffs, median_diff):
+        # the first event whose diff is within [0.2, 5] x the typical one ends the broken run; found
+        # with one vectorised ratio test over the diff column (same float type as the scalars)
+        limit = min(np.median(diffs[:10]), median_diff)
+        if isinstance(diffs, np.ndarray):
+            ratio = diffs / limit
+            sane = np.flatnonzero((0.2 < ratio) & (ratio < 5))
+            first = int(sane[0]) if sane.size else None
+        else:
+            first = next((i for i, d in enumerate(diffs) if 0.2 < (d / limit) < 5), None)
+        if first is None:
+            return 0
+        for b in seq[:first]:
+            b.link_event(seq[first])
+        return first
 
-    median_diff = np.median([e.diff for e in events])
-    n = sweep(events, median_diff)
+    diffs = _column(events, 'diff')
+    if diffs is None:
+        diffs = [e.diff for e in events]
+    median_diff = np.median(diffs)
+    n = sweep(events, diffs, median_diff)
     if n:
         logging.info('Fixing {0} border events right after {1}'.format(n, format_time(events[0].start)))
-    n = sweep(list(reversed(events)), median_diff)
+    n = sweep(events[::-1], diffs[::-1], median_diff)
     if n:
         logging.info('Fixing {0} border events right before {1}'.format(n, format_time(events[-1].end)))
 
@@ -155,7 +176,12 @@ def fix_near_borders(events):
 def average_shifts(events):
     """Weighted mean shift of the unlinked events, weights 1 - diff (sushi.py:309-316)."""
     events = [e for e in events if not e.linked]
-    avg = np.average([e.shift for e in events], weights=[1 - e.diff for e in events])
+    shifts, diffs = _column(events, 'shift'), _column(events, 'diff')
+    if shifts is None or diffs is None:
+        shifts, weights = [e.shift for e in events], [1 - e.diff for e in events]
+    else:
+        weights = 1 - diffs                   # elementwise in the diffs' own float type, like the scalars
+    avg = np.average(shifts, weights=weights)
     for e in events:
         e.set_shift(avg, e.diff)
     return avg

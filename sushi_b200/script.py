@@ -7,7 +7,7 @@ import io
 import os
 import re
 
-from .common import SushiError, format_time
+from .common import SushiError, format_time, py2_round
 from .events import ScriptEvent
 
 
@@ -17,7 +17,7 @@ def parse_ass_time(text):
 
 
 def format_srt_time(seconds):
-    ms = round(seconds * 1000)
+    ms = py2_round(seconds * 1000)
     return '{0:02d}:{1:02d}:{2:02d},{3:03d}'.format(int(ms // 3600000), int((ms // 60000) % 60),
                                                     int((ms // 1000) % 60), int(ms % 1000))
 

@@ -24,7 +24,7 @@ from time import time
 import numpy as np
 
 from . import _native
-from .common import SushiError, clip
+from .common import SushiError, clip, py2_round
 
 WAVE_FORMAT_PCM = 0x0001
 WAVE_FORMAT_EXTENSIBLE = 0xFFFE
@@ -142,9 +142,6 @@ def nearest_index_map(n_in, n_out):
     return idx
 
 
-def py2_round(x):
-    """round() as Python 2 does it (half away from zero) -- the reference is py2 code (wav.py:127)."""
-    return math.floor(x + 0.5) if x >= 0 else -math.floor(-x + 0.5)
 
 
 def normalise_host(data, sample_type):
@@ -163,9 +160,66 @@ def normalise_host(data, sample_type):
     return data, float(min_value), float(max_value)
 
 
-class WavStream(object):
-    READ_CHUNK_SIZE = 1  # seconds per resample chunk (wav.py:105)
+class StreamGeometry(object):
+    """What the time -> sample arithmetic of the reference needs to know about a stream (wav.py:164-184):
+    rate, padding, sample count and the length of the padded array.  WavStream derives from it; the
+    multi-GPU path plans every rank's queries from these four numbers alone (sushi_b200/parallel.py)."""
     PADDING_SECONDS = 10
+
+    def __init__(self, sample_rate, padding_size, sample_count, total_samples):
+        self.sample_rate, self.padding_size, self.sample_count = sample_rate, int(padding_size), sample_count
+        self._total = int(total_samples)
+
+    @property
+    def total_samples(self):
+        data = getattr(self, 'data', None)
+        return data.shape[1] if data is not None else self._total
+
+    @property
+    def duration_seconds(self):
+        return self.sample_count / self.sample_rate
+
+    def _get_sample_for_time(self, timestamp):
+        # REAL sample for a time, padding included (wav.py:173-175); int() truncates toward zero
+        return int(self.sample_rate * timestamp) + self.padding_size
+
+    def plan_queries(self, src_stream, starts, ends, centers, windows):
+        """Integer descriptors of many find_substream calls at once.
+
+        Query q searches src_stream.get_substream(starts[q], ends[q]) in this stream around
+        centers[q] +- windows[q].  Returns (tmpl_off, tmpl_len, lag0, nlags, start_times) as
+        int64/float64 arrays.  Vectorised, but operation for operation the scalar code of
+        get_substream / find_substream (wav.py:168-184): float64 product, truncation toward zero,
+        min-then-max clipping, NumPy slice clamping -- so the integers are identical
+        (tests/test_host_logic.py checks this against the scalar path).
+        """
+        starts = np.asarray(starts, np.float64); ends = np.asarray(ends, np.float64)
+        centers = np.asarray(centers, np.float64); windows = np.asarray(windows, np.float64)
+
+        def sample_for_time(stream, t):                       # wav.py:173-175
+            return np.trunc(stream.sample_rate * t).astype(np.int64) + stream.padding_size
+
+        def slice_bounds(lo, hi, total):                      # what data[:, lo:hi] resolves to
+            lo = np.where(lo < 0, np.maximum(lo + total, 0), np.minimum(lo, total))
+            hi = np.where(hi < 0, np.maximum(hi + total, 0), np.minimum(hi, total))
+            return lo, np.maximum(hi - lo, 0)
+
+        toff, tlen = slice_bounds(sample_for_time(src_stream, starts), sample_for_time(src_stream, ends),
+                                  src_stream.total_samples)
+        dur = self.duration_seconds
+        t0 = np.maximum(np.minimum(centers - windows, dur), -self.PADDING_SECONDS)           # wav.py:178
+        t1 = np.maximum(np.minimum(centers + windows, dur + self.PADDING_SECONDS), 0)        # wav.py:179
+        lag0, span = slice_bounds(sample_for_time(self, t0), sample_for_time(self, t1) + tlen, self.total_samples)
+        bad = np.nonzero((tlen < 1) | (span < tlen))[0]
+        if len(bad):
+            q = int(bad[0])
+            raise SushiError('query {0}: pattern of {1} samples does not fit its search span of {2}'.format(
+                q, int(tlen[q]), int(span[q])))
+        return toff, tlen, lag0, span - tlen + 1, t0
+
+
+class WavStream(StreamGeometry):
+    READ_CHUNK_SIZE = 1  # seconds per resample chunk (wav.py:105)
 
     def __init__(self, path, sample_rate=12000, sample_type='uint8', device=None, loader='gpu'):
         """loader='gpu' (default): decode / resample / pad / normalise on the GPU (sb_load_pcm +
@@ -316,6 +370,7 @@ class WavStream(object):
         self = object.__new__(cls)
         self._handle = None
         self.data = host_mirror
+        self._total = int(n)
         self.sample_rate = sample_rate
         self.sample_type = sample_type
         self.padding_size = int(padding_size)
@@ -365,15 +420,7 @@ class WavStream(object):
         except Exception:
             pass
 
-    # -- the reference's surface ----------------------------------------------------------
-    @property
-    def duration_seconds(self):
-        return self.sample_count / self.sample_rate
-
-    def _get_sample_for_time(self, timestamp):
-        # REAL sample for a time, padding included (wav.py:173-175); int() truncates toward zero
-        return int(self.sample_rate * timestamp) + self.padding_size
-
+    # -- the reference's surface (duration_seconds, _get_sample_for_time: StreamGeometry) ----
     def get_substream(self, start, end):
         start_off = self._get_sample_for_time(start)
         end_off = self._get_sample_for_time(end)
@@ -385,7 +432,7 @@ class WavStream(object):
         end_time = clip(window_center + window_size, 0, self.duration_seconds + self.PADDING_SECONDS)
         start_sample = self._get_sample_for_time(start_time)
         end_sample = self._get_sample_for_time(end_time) + pattern_len
-        lo, hi, _ = slice(start_sample, end_sample).indices(self.data.shape[1])   # numpy slice rules (wav.py:184)
+        lo, hi, _ = slice(start_sample, end_sample).indices(self.total_samples)   # numpy slice rules (wav.py:184)
         return start_time, lo, max(hi - lo, 0)
 
     def _locate(self, pattern):
@@ -464,39 +511,15 @@ class WavStream(object):
         return [(np.float32(diff[q]), t0[q] + (int(idx[q]) / rate)) for q in range(len(plan))]
 
     # -- batched surface (what the sharded benchmark and the batched shift solver use) ------
-    def plan_queries(self, src_stream, starts, ends, centers, windows):
-        """Integer descriptors of many find_substream calls at once.
-
-        Query q searches src_stream.get_substream(starts[q], ends[q]) in this stream around
-        centers[q] +- windows[q].  Returns (tmpl_off, tmpl_len, lag0, nlags, start_times) as
-        int64/float64 arrays.  Vectorised, but operation for operation the scalar code of
-        get_substream / find_substream (wav.py:168-184): float64 product, truncation toward zero,
-        min-then-max clipping, NumPy slice clamping -- so the integers are identical
-        (tests/test_host_logic.py checks this against the scalar path).
-        """
-        starts = np.asarray(starts, np.float64); ends = np.asarray(ends, np.float64)
-        centers = np.asarray(centers, np.float64); windows = np.asarray(windows, np.float64)
-
-        def sample_for_time(stream, t):                       # wav.py:173-175
-            return np.trunc(stream.sample_rate * t).astype(np.int64) + stream.padding_size
-
-        def slice_bounds(lo, hi, total):                      # what data[:, lo:hi] resolves to
-            lo = np.where(lo < 0, np.maximum(lo + total, 0), np.minimum(lo, total))
-            hi = np.where(hi < 0, np.maximum(hi + total, 0), np.minimum(hi, total))
-            return lo, np.maximum(hi - lo, 0)
-
-        toff, tlen = slice_bounds(sample_for_time(src_stream, starts), sample_for_time(src_stream, ends),
-                                  src_stream.data.shape[1])
-        dur = self.duration_seconds
-        t0 = np.maximum(np.minimum(centers - windows, dur), -self.PADDING_SECONDS)           # wav.py:178
-        t1 = np.maximum(np.minimum(centers + windows, dur + self.PADDING_SECONDS), 0)        # wav.py:179
-        lag0, span = slice_bounds(sample_for_time(self, t0), sample_for_time(self, t1) + tlen, self.data.shape[1])
-        bad = np.nonzero((tlen < 1) | (span < tlen))[0]
-        if len(bad):
-            q = int(bad[0])
-            raise SushiError('query {0}: pattern of {1} samples does not fit its search span of {2}'.format(
-                q, int(tlen[q]), int(span[q])))
-        return toff, tlen, lag0, span - tlen + 1, t0
+    @staticmethod
+    def _template_ranges(src_stream, starts, ends):
+        """(offset, length) of get_substream(starts[q], ends[q]) on src_stream, NumPy slice clamping included."""
+        total = src_stream.total_samples
+        lo = np.trunc(src_stream.sample_rate * np.asarray(starts, np.float64)).astype(np.int64) + src_stream.padding_size
+        hi = np.trunc(src_stream.sample_rate * np.asarray(ends, np.float64)).astype(np.int64) + src_stream.padding_size
+        lo = np.where(lo < 0, np.maximum(lo + total, 0), np.minimum(lo, total))
+        hi = np.where(hi < 0, np.maximum(hi + total, 0), np.minimum(hi, total))
+        return lo, np.maximum(hi - lo, 0)
 
     def find_substream_batch(self, src_stream, starts, ends, centers, windows):
         """Batched find_substream: returns (diffs float32[count], times float64[count])."""
@@ -534,23 +557,36 @@ class WavStream(object):
         start + anchor with +-window (the fast path, sushi.py:431-432).  Precompute, in ONE launch, the
         curves of the next groups over a slightly wider span; find_substream then answers from them.
         A curve value depends only on (template, absolute position), so a cached curve answers any
-        contained range with exactly the value and first-index argmin a live call returns."""
+        contained range with exactly the value and first-index argmin a live call returns (the packed
+        engines at hop B, the default, compute a value the same way whatever the batch; the
+        first-generation engine with hop_mode 0 picks its geometry per batch and agrees only to ~1e-7)."""
         cache = self.__dict__.setdefault('_curve_cache', {})
-        first = groups[idx]
-        key0 = (src_stream._get_sample_for_time(first[0].start), src_stream._get_sample_for_time(first[-1].end))
-        if key0 in cache:
-            return
-        cache.clear()                                        # predictions made for an older anchor
         batch = groups[idx:idx + self.SPECULATE_GROUPS]
         starts = np.array([g[0].start for g in batch], np.float64)
         ends = np.array([g[-1].end for g in batch], np.float64)
+        windows = np.full(len(batch), window + self.SPECULATE_MARGIN)
+        # keys are the CLAMPED template ranges, the same integers find_substream derives from a view
+        k_off, k_len = self._template_ranges(src_stream, starts, ends)
+        if (int(k_off[0]), int(k_off[0] + k_len[0])) in cache:
+            return
+        cache.clear()                                        # predictions made for an older anchor
         try:
-            toff, tlen, lag0, nlags, _ = self.plan_queries(src_stream, starts, ends, starts + anchor,
-                                                           np.full(len(batch), window + self.SPECULATE_MARGIN))
+            toff, tlen, lag0, nlags, _ = self.plan_queries(src_stream, starts, ends, starts + anchor, windows)
         except SushiError:
-            return                                           # some group does not fit: let the live path decide
+            # some group does not fit its search span (end of the stream): keep the ones that do
+            keep = []
+            for q in range(len(batch)):
+                try:
+                    self.plan_queries(src_stream, starts[q:q + 1], ends[q:q + 1], starts[q:q + 1] + anchor, windows[q:q + 1])
+                    keep.append(q)
+                except SushiError:
+                    pass
+            if not keep:
+                return
+            toff, tlen, lag0, nlags, _ = self.plan_queries(src_stream, starts[keep], ends[keep], starts[keep] + anchor,
+                                                           windows[keep])
         curves = self.match_curves(src_stream, toff, tlen, lag0, nlags)
-        for q in range(len(batch)):
+        for q in range(len(toff)):
             cache[(int(toff[q]), int(toff[q] + tlen[q]))] = (src_stream, int(lag0[q]), curves[q])
 
     def _from_cache(self, where, n, lo, nlags):

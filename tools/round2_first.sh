@@ -30,3 +30,6 @@ timeout 250 ncu --set full --clock-control none --import-source on -k regex:k_ma
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv
 SB_PARITY_EXPERIMENTAL=1 timeout 200 python tests/parity_report.py > $O/parity_r2_first.txt 2>&1; grep -c same $O/parity_r2_first.txt; grep DIFF $O/parity_r2_first.txt | head
 timeout 120 python tools/sweep.py --engine 6 --epilogue 2 --queries 128 --reps 2 --events 0.5,1,3,10 --windows 10,60,120 --out sweep_r2_engine6_epi2.json > $O/sweep_engine6.txt 2>&1; tail -5 $O/sweep_engine6.txt
+timeout 60 python bench.py --workload config3 --steps 5 --warmup 3 --no-cpu-baseline > $O/bench_r2_config3_default.json 2>/dev/null
+timeout 60 python bench.py --workload config3 --steps 5 --warmup 3 --no-cpu-baseline --engine 4 --epilogue 2 > $O/bench_r2_config3_engine4_epi2.json 2>/dev/null
+head -c 600 $O/bench_r2_config3_*.json
