@@ -282,8 +282,6 @@ def run_b200(args):
         _native.check(lib.sb_set_premac_mode(args.premac_mode))
     if args.epilogue > 0:
         _native.check(lib.sb_set_epilogue(args.epilogue))
-    if args.spectra >= 0:
-        _native.check(lib.sb_set_spectra(args.spectra))
 
     dist = torch = None
     if world > 1:
@@ -463,7 +461,7 @@ def run_b200(args):
             'higher_is_better': True, 'scaling': wl['scaling'], 'vs_baseline': None,
             'dtype': 'f32', 'data': 'synthetic',
             'config': {'workload': args.workload + ': ' + wl['text'], 'events_per_gpu': count, 'sample_type': stype,
-                       'sample_rate': SAMPLE_RATE, 'window_s': wl['window'], 'lag_block': lib.sb_get_block_size(), 'epilogue': lib.sb_get_epilogue(), 'spectra': {0: 'f32', 1: 'bfp16'}[lib.sb_get_spectra()], 'engine': {0: 'cufft', 1: 'fused', 2: 'fused_packed', 3: 'fused_packed_ws', 4: 'fused_packed_pair', 5: 'fused_packed_single', 6: 'fused_packed_triple'}[lib.sb_get_engine()],
+                       'sample_rate': SAMPLE_RATE, 'window_s': wl['window'], 'lag_block': lib.sb_get_block_size(), 'epilogue': lib.sb_get_epilogue(), 'spectra': 'f32', 'engine': {0: 'cufft', 1: 'fused', 2: 'fused_packed', 4: 'fused_packed_pair', 5: 'fused_packed_single'}[lib.sb_get_engine()],
                        'parallelism': 'events x%d' % world,
                        'l2': 'working set > L2: block spectra %.0f MB + running sums %.0f MB per stream, rebuilt every step'
                              % (n_dst * 8 / 1e6, n_dst * 16 / 1e6),
@@ -531,9 +529,8 @@ def main():
     ap.add_argument('--chunk', type=int, default=0, help='items per launch override')
     ap.add_argument('--premac-mode', type=int, default=-1, help='blocked multiply kernel: 0 by template length (default), 1 never, 2 always')
     ap.add_argument('--hop-mode', type=int, default=-1, help='fused engine geometry: 1 hop B (default), 2 hop B/2, 0 cost rule per batch')
-    ap.add_argument('--spectra', type=int, default=-1, help='spectrum rows of the packed kernels: 0 float32 (default), 1 16-bit block floating point')
-    ap.add_argument('--epilogue', type=int, default=0, help='screening loop of the packed kernels on uint8 streams: 1 first version (default), 2 trimmed')
-    ap.add_argument('--engine', type=int, default=-1, help='0: cuFFT pipeline, 1: fused kernel, 2: packed fused kernels (default), 3: warp-specialised persistent variant, 4 / 5: always / never pairs of lag blocks, 6: triples (opt-in)')
+    ap.add_argument('--epilogue', type=int, default=0, help='body variant of the packed kernels on uint8 streams: 2 trimmed (default), 1 first version')
+    ap.add_argument('--engine', type=int, default=-1, help='0: cuFFT pipeline, 1: fused kernel, 2: packed fused kernels (default), 4 / 5: always / never pairs of lag blocks')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

@@ -79,10 +79,6 @@ int sb_get_block_size(void);
  *       partitions) a pair of consecutive lag blocks that share their template rows, the second product
  *       spectrum waiting in tensor memory; both give bit-identical results;
  *   4 / 5 = engine 2 with pairs always / never;
- *   6 = engine 2 over TRIPLES of consecutive lag blocks (2P + 2 spectrum-row reads per three blocks, two product
- *       spectra parked in tensor memory); opt-in, not measured yet;
- *   3 = the same arithmetic as a persistent warp-specialised kernel (TMA-fed multiply warps park each
- *       item's product spectrum in tensor memory while the other warps transform the previous one);
  *   1 = the first fused lag-block kernel (sb_fused.cu; lag blocks of 8192 or 16384, hop B or B/2);
  *   0 = the cuFFT-planned pipeline (any block size; kept as the cross-check and for odd block sizes).
  * Engines agree to float32 FFT rounding (~2e-7 of the curve), not bit for bit. */
@@ -98,24 +94,15 @@ int sb_set_premac_mode(int mode);
  * pays off only for templates shorter than B/2), 0 = chosen per batch by a cost rule.  Geometries
  * agree to float32 FFT rounding (~1e-7), not bit for bit, so a run should stick to one. */
 int sb_set_hop_mode(int mode);
-/* Screening loop of the packed kernels (engines 2, 4, 5) on uint8 streams: 1 (default) = the first version,
- * 2 = a trimmed one (7 instead of 13 arithmetic instructions per lag, byte extraction by PRMT, border test
- * hoisted) whose exact evaluation takes the window sums from the staged sample windows instead of two
- * dependent reads of the running sums in HBM, and whose multiply phase prefetches the one self-mirrored quad of
- * each item instead of fetching it after the loop, and whose FFT passes place the barrier between loads and
- * stores in the middle of the butterfly (loads and stores overlap arithmetic).  Screening only selects the lags that get the exact fp64
- * evaluation and the window sums are exact integers either way, so results are identical bit for bit;
- * float32 streams and the other engines ignore the setting.  Opt-in until measured. */
+/* Body variant of the packed kernels (engines 2, 4, 5) on uint8 streams: 2 (default) = trimmed screening loop
+ * (7 instead of 13 arithmetic instructions per lag), exact evaluation of the candidate lags from the staged
+ * sample windows instead of two dependent reads of the running sums in HBM, prefetched self-mirrored quad,
+ * barrier between loads and stores of an FFT pass in the middle of the butterfly; 1 = the first version.
+ * Screening only selects the lags that get the exact fp64 evaluation and the window sums are exact integers
+ * either way, so the two give identical results bit for bit (checked on the GPU by the test-suite); float32
+ * streams and the other engines ignore the setting. */
 int sb_set_epilogue(int variant);
 int sb_get_epilogue(void);
-/* Storage of the spectrum rows the packed kernels multiply (engines 2, 4, 5, 6; block spectra of a stream and
- * template partition spectra): 0 (default) = float32; 1 = 16-bit block floating point (int16 components, one
- * float32 scale per bin family and group of eight quads): rows of 73 856 instead of 131 200 bytes for the
- * L2-bound multiply phase.  All arithmetic stays float32; the quantisation moves the curve by ~5e-7 on programme
- * audio (the float32 FFT's own rounding: 2e-7), so results agree with format 0 to ~1e-6, not bit for bit.  A
- * stream's cached rows are rebuilt when the format changes.  Opt-in until measured. */
-int sb_set_spectra(int format);
-int sb_get_spectra(void);
 /* Lag blocks processed per multiply / inverse-FFT / normalise launch (>= 1). */
 int sb_set_chunk_items(int items);
 /* Template partition spectra kept resident per pass over a batch (>= 1); batches needing more are

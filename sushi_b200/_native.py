@@ -36,8 +36,6 @@ PROTOTYPES = {
     'sb_get_engine': (ctypes.c_int, []),
     'sb_set_hop_mode': (ctypes.c_int, [ctypes.c_int]),
     'sb_set_premac_mode': (ctypes.c_int, [ctypes.c_int]),
-    'sb_set_spectra': (ctypes.c_int, [ctypes.c_int]),
-    'sb_get_spectra': (ctypes.c_int, []),
     'sb_set_epilogue': (ctypes.c_int, [ctypes.c_int]),
     'sb_get_epilogue': (ctypes.c_int, []),
     'sb_get_stream': (c_vp, []),

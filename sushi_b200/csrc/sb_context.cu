@@ -213,7 +213,7 @@ int sb_set_block_size(int block) {
 }
 int sb_get_block_size(void) { return ctx().B; }
 int sb_set_engine(int engine) {
-    if (engine < 0 || engine > 6) SB_FAIL(SB_EINVAL, "sb_set_engine: %d is not one of 0 (cuFFT pipeline), 1 (fused kernel), 2 (packed fused kernels), 3 (warp-specialised packed kernel), 4 / 5 (packed kernel always / never over pairs of lag blocks), 6 (packed kernel over triples of lag blocks)", engine);
+    if (engine < 0 || engine > 5 || engine == 3) SB_FAIL(SB_EINVAL, "sb_set_engine: %d is not one of 0 (cuFFT pipeline), 1 (fused kernel), 2 (packed fused kernels), 4 / 5 (packed kernel always / never over pairs of lag blocks)", engine);
     ctx().engine = engine;
     return SB_OK;
 }
@@ -228,14 +228,8 @@ int sb_set_hop_mode(int mode) {
     ctx().hop_mode = mode;
     return SB_OK;
 }
-int sb_set_spectra(int format) {
-    if (format < 0 || format > 1) SB_FAIL(SB_EINVAL, "sb_set_spectra: %d is not 0 (float32 rows) or 1 (16-bit block floating point rows)", format);
-    ctx().spectra_fmt = format;
-    return SB_OK;
-}
-int sb_get_spectra(void) { return ctx().spectra_fmt; }
 int sb_set_epilogue(int variant) {
-    if (variant < 1 || variant > 2) SB_FAIL(SB_EINVAL, "sb_set_epilogue: %d is not 1 (first screening loop) or 2 (trimmed screening loop)", variant);
+    if (variant < 1 || variant > 2) SB_FAIL(SB_EINVAL, "sb_set_epilogue: %d is not 1 (first screening loop) or 2 (trimmed screening loop, the default)", variant);
     ctx().epilogue = variant;
     return SB_OK;
 }

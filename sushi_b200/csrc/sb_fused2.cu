@@ -18,19 +18,19 @@
 //  * Twiddles of the packing stage are formed in registers from one per-thread base value, so the 64 KB
 //    table sb_fused.cu streams from L2 for every item is gone; spectrum rows are 128-byte aligned.
 //
-// Four kernels share these pieces:
+// Two kernels share these pieces:
 //   k_match_packed  one CTA per lag block;
 //   k_match_pair    one CTA per pair of consecutive lag blocks of a query: both are multiplied at once (2P+1
 //                   spectrum-row reads instead of 4P), the second product spectrum waits in tensor memory
-//                   while the first is transformed -- the default for templates of two or more partitions;
-//   k_match_triple  the same over three lag blocks (2P+2 reads, two spectra parked; engine 6, opt-in);
-//   k_match_ws      a persistent warp-specialised variant (experimental, engine 3).
-// Values agree with sb_fused.cu / the cuFFT engine to fp32 FFT rounding (~2e-7 of the curve); k_match_packed,
-// k_match_pair and k_match_triple agree bit for bit.
-// Template parameters of the first three: S = sample type of the stream (uint8_t | float); EPI = screening loop
-// of the epilogue (1 = measured default, 2 = trimmed, opt-in: sb_set_epilogue); FMT = format of the spectrum rows
-// (0 = float32, 1 = 16-bit block floating point, opt-in: sb_set_spectra).  EPI = 1, FMT = 0 are the kernels the
-// round-1 measurements were taken with; the other instantiations have only run in the CPU emulation (tests/emu).
+//                   while the first is transformed -- the default for templates of two or more partitions.
+// Values agree with sb_fused.cu / the cuFFT engine to fp32 FFT rounding (~2e-7 of the curve); k_match_packed and
+// k_match_pair agree bit for bit.
+// Template parameters: S = sample type of the stream (uint8_t | float); EPI = body variant on uint8 streams
+// (2 = default: trimmed screening loop, candidates evaluated from the staged windows, mid-butterfly barriers,
+// prefetched self-mirrored quad; 1 = the first version, kept as the bit-identical cross-check: sb_set_epilogue).
+// Measured and dropped in round 2 (profiles/README.md): triples of lag blocks (slower than pairs: one quad in
+// flight per thread), 16-bit block-floating-point spectrum rows (the dequantisation costs more issue slots than
+// the halved L2 traffic returns), a persistent warp-specialised variant (multiply warps latency-bound).
 #include "sb_internal.h"
 #include <cmath>
 #include <cstdlib>
@@ -146,29 +146,9 @@ struct Buf {
     __device__ __forceinline__ void st(int p, C2 v) const { r[p] = v.r; i[p] = v.i; }
 };
 
-// ---------------------------------------------------------------- spectrum row formats
-// FMT 0 (measured default): float32, 16-byte units A[i] / M[i] in blocks of 256 + 256 as described above.
-// FMT 1 (opt-in, sb_set_spectra(1)): 16-bit block floating point.  Unit i (16 bytes) holds the eight components
-// of quad i as int16 -- (re X[i], re X[i+B/2]), (im X[i], im X[i+B/2]), (re X[B-i], re X[B/2-i]), (im .., im ..) --
-// and unit Q4+1+(i>>3) holds four float32 scales for the quads 8g .. 8g+7, one per bin family (X[i], X[i+B/2],
-// X[B-i], X[B/2-i]: eight consecutive bins each, so a scale never spans distant frequencies).  A row is 73 856
-// instead of 131 200 bytes: the multiply phase runs at the L2 -> SM rate, bytes are what it costs.  Quantisation
-// error of a component <= scale / 2 = max of its group / 65534; on programme audio the curve moves by ~5e-7
-// (fp32 FFT rounding itself: 2e-7; NumPy study in DESIGN.md section 8).
-constexpr int QROW16 = kQuad16RowF2 / 2;  // 16-byte units per FMT 1 row
-constexpr int QSCALE0 = Q4 + 1;           // first scale unit of a FMT 1 row
-static_assert(QROW16 >= QSCALE0 + (Q4 >> 3) + 1 && (QROW16 * 16) % 128 == 0, "16-bit row layout");
-
-__device__ __forceinline__ void dequant16(uint4 q, float4 s, float4& a, float4& m) {
-    a.x = (float)(short)(q.x & 0xffffu) * s.x;  a.y = (float)(short)(q.x >> 16) * s.y;
-    a.z = (float)(short)(q.y & 0xffffu) * s.x;  a.w = (float)(short)(q.y >> 16) * s.y;
-    m.x = (float)(short)(q.z & 0xffffu) * s.z;  m.y = (float)(short)(q.z >> 16) * s.w;
-    m.z = (float)(short)(q.w & 0xffffu) * s.z;  m.w = (float)(short)(q.w >> 16) * s.w;
-}
-
+// ---------------------------------------------------------------- spectrum rows
 // Addressing and loading of one quad of a row, in 16-byte units from the row's first unit.
-template <int FMT> struct Rows;
-template <> struct Rows<0> {
+struct Rows {
     static constexpr int STRIDE = QROW;
     // unit of quad tid + 512*uu's A chunk (its M chunk is QBLK further): qa() without the special case
     static __device__ __forceinline__ int unit(int tid, int uu) { return (tid >> 8) * (2 * QBLK) + (tid & (QBLK - 1)) + uu * (2 * QT); }
@@ -181,22 +161,6 @@ template <> struct Rows<0> {
     }
     static __device__ __forceinline__ void load_special(const float4* row, float4& a, float4& m) { a = __ldg(row + qa(Q4)); m = __ldg(row + qm(Q4)); }
 };
-template <> struct Rows<1> {
-    static constexpr int STRIDE = QROW16;
-    static __device__ __forceinline__ int unit(int tid, int uu) { return tid + uu * QT; }          // the quad's own number
-    static constexpr int USTEP = QT;
-    static __device__ __forceinline__ void load(const float4* row, int u, float4& a, float4& m) {
-        const uint4 q = __ldg(reinterpret_cast<const uint4*>(row) + u);
-        dequant16(q, __ldg(row + QSCALE0 + (u >> 3)), a, m);
-    }
-    static __device__ __forceinline__ void loadp(const float4* row, int u, bool pred, float4& a, float4& m) {
-        const uint4 q = pred ? __ldg(reinterpret_cast<const uint4*>(row) + u) : make_uint4(0u, 0u, 0u, 0u);
-        const float4 sc = pred ? __ldg(row + QSCALE0 + (u >> 3)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        dequant16(q, sc, a, m);
-    }
-    static __device__ __forceinline__ void load_special(const float4* row, float4& a, float4& m) { load(row, Q4, a, m); }
-};
-
 // Spectrum rows: plain read-only loads.  (Measured: ld.global.nc.L1::no_allocate, tried to keep the twiddle
 // tables in L1, drops the L2 hit rate of these rows from 98 % to 83 % and multiplies the DRAM traffic of the
 // kernel by 9 -- profiles/README.md.)
@@ -307,13 +271,12 @@ struct QuadAcc {
 };
 
 // The self-mirrored quad i = B/4 of an item, by one warp: partitions spread over the lanes, result valid in lane 0
-template <int FMT = 0>
 __device__ __forceinline__ C2 special_quad(const float4* tp, const float4* xp, int P, int lane) {
     QuadAcc acc; acc.zero();
     for (int p = lane; p < P; p += 32) {
         float4 ta, tm, xa, xm;
-        Rows<FMT>::load_special(tp + (int64_t)p * Rows<FMT>::STRIDE, ta, tm);
-        Rows<FMT>::load_special(xp + (int64_t)p * Rows<FMT>::STRIDE, xa, xm);
+        Rows::load_special(tp + (int64_t)p * Rows::STRIDE, ta, tm);
+        Rows::load_special(xp + (int64_t)p * Rows::STRIDE, xa, xm);
         acc.mac(ta, tm, xa, xm);
     }
     acc.reduce_over_lanes();
@@ -329,22 +292,19 @@ __device__ __forceinline__ C2 special_quad(const float4* tp, const float4* xp, i
 // its multiply loop; afterwards the partitions are spread over the lanes and summed by the same shuffle tree as
 // special_quad (same arithmetic in the same order: bit-identical), reading shared memory instead of L2.
 constexpr int kSpecialBytes = 1024;                // (2 * 11 + 2) rows x 32 bytes fit
-template <int FMT>
 __device__ __forceinline__ void special_prefetch(float4* s_sp, const float4* tp, const float4* xp, int P, int G,
                                                  int64_t k, int64_t nblk, int lane) {
-    const int u0 = FMT ? Q4 : qa(Q4), u1 = FMT ? QSCALE0 + (Q4 >> 3) : qm(Q4);
+    const int u0 = qa(Q4), u1 = qm(Q4);
     for (int r = lane; r < 2 * P + G - 1; r += 32) {
         const bool is_t = r < P;
-        const float4* row = is_t ? tp + (int64_t)r * Rows<FMT>::STRIDE : xp + (int64_t)(r - P) * Rows<FMT>::STRIDE;
+        const float4* row = is_t ? tp + (int64_t)r * Rows::STRIDE : xp + (int64_t)(r - P) * Rows::STRIDE;
         if (is_t || k + (r - P) < nblk) { cp_async16(s_sp + 2 * r, row + u0); cp_async16(s_sp + 2 * r + 1, row + u1); }
         else s_sp[2 * r] = s_sp[2 * r + 1] = make_float4(0.f, 0.f, 0.f, 0.f);     // rows past the end of the stream are zero
     }
 }
-template <int FMT>
 __device__ __forceinline__ C2 special_from_smem(const float4* s_sp, int P, int g, int lane) {      // item g; result in lane 0
     auto units = [&](int r, float4& a, float4& m) {
-        if (FMT) dequant16(*reinterpret_cast<const uint4*>(s_sp + 2 * r), s_sp[2 * r + 1], a, m);
-        else { a = s_sp[2 * r]; m = s_sp[2 * r + 1]; }
+        a = s_sp[2 * r]; m = s_sp[2 * r + 1];
     };
     QuadAcc acc; acc.zero();
     for (int p = lane; p < P; p += 32) {
@@ -462,7 +422,7 @@ __device__ __forceinline__ void query_constants(double2* s_qc, const QueryDesc& 
 
 // Window sums, fp32 screening of every lag, fp64 evaluation of the lags that can still be the minimum, merge
 // into the query's key.  after_read() runs (on all 512 threads) once every thread is done with the staged
-// windows -- k_match_ws starts the copies of its next item there.
+// windows.
 template <typename S, int ID, int EPI, typename AfterRead>
 __device__ __forceinline__ void finish_item(const Item& it, int tid, const Smem& sm, unsigned long long* s_bar, unsigned bar_parity,
                                             unsigned long long* s_best, float* s_min, int2* s_w0,
@@ -732,7 +692,7 @@ __device__ __forceinline__ void finish_item(const Item& it, int tid, const Smem&
 }
 
 // ---------------------------------------------------------------- kernel A: one CTA per item
-template <typename S, int EPI, int FMT>
+template <typename S, int EPI>
 __global__ void __launch_bounds__(QT, 1)
 k_match_packed(const float4* __restrict__ That, int64_t part_first,
                const float4* __restrict__ Xhat, int64_t nblk,
@@ -766,13 +726,13 @@ k_match_packed(const float4* __restrict__ That, int64_t part_first,
     {
         int P = d.P;
         if (it.k + P > nblk) P = (int)(nblk - it.k);      // rows past the end of the stream are zero
-        typedef Rows<FMT> R;
+        typedef Rows R;
         const float4* tp = That + (d.partBase - part_first) * (int64_t)R::STRIDE;
         const float4* xp = Xhat + it.k * (int64_t)R::STRIDE;
         const float2 wbase = __ldg(tab.wb + tid);
         const int tm = (T - tid) & (T - 1);           // mirrored chunks C[B/2 - i] live in thread tm's column
         const int col = phys(tid), mcol = phys(tm);
-        if (EPI == 2 && SB_V2_SPECIAL_PREFETCH && warp == NW - 1) special_prefetch<FMT>(s_sp, tp, xp, d.P, 1, it.k, nblk, lane);
+        if (EPI == 2 && SB_V2_SPECIAL_PREFETCH && warp == NW - 1) special_prefetch(s_sp, tp, xp, d.P, 1, it.k, nblk, lane);
         constexpr int U = 4;                          // quads in flight per thread
 #pragma unroll 1
         for (int half = 0; half < 2; ++half) {
@@ -810,10 +770,10 @@ k_match_packed(const float4* __restrict__ That, int64_t part_first,
             if constexpr (EPI == 2 && SB_V2_SPECIAL_PREFETCH) {
                 cp_async_commit_wait_all();
                 __syncwarp();
-                const C2 lo = special_from_smem<FMT>(s_sp, d.P, 0, lane);
+                const C2 lo = special_from_smem(s_sp, d.P, 0, lane);
                 if (lane == 0) buf.st(phys(Q4), lo);
             } else {
-                const C2 lo = special_quad<FMT>(tp, xp, P, lane);
+                const C2 lo = special_quad(tp, xp, P, lane);
                 if (lane == 0) buf.st(phys(Q4), lo);
             }
         }
@@ -823,223 +783,6 @@ k_match_packed(const float4* __restrict__ That, int64_t part_first,
     // ---------------- 3. inverse FFT, 4. epilogue ---------------------------------------------
     const float4 wt0 = fft_passes<0, EPI == 2 && SB_V2_MIDBAR>(buf, tid, tab, is_u8);
     finish_item<S, 0, EPI>(it, tid, sm, s_bar, 0u, s_best, s_min, s_w0, img, img_n, ipfx, tpfx, tab, keys, curve_out, [] {}, wt0);
-}
-
-// ---------------------------------------------------------------- kernel B: persistent, warp-specialised
-// k_match_packed runs its phases back to back on one CTA per SM: while it multiplies (loads from L2, issue
-// slots idle) nothing transforms, and while it transforms nothing loads.  Here one persistent CTA per SM
-// splits the work over two roles that overlap across consecutive items:
-//   8 multiply warps       two threads per TMEM lane L own quads i = L + 128*m (even / odd m).  A ring of
-//                          WS_STAGES stages (one 256-quad block of a T^ row and of an X^ row, 16 KB) is
-//                          filled by TMA bulk copies WS_STAGES-1 steps ahead
-//                          -- across items, so the L2 latency never surfaces; the warps take turns issuing;
-//                          they multiply-accumulate from the ring and park the product spectrum in TENSOR
-//                          MEMORY with tcgen05.st (the tensor cores are idle, so their 256 KB of TMEM are a
-//                          free second buffer: two items of 128 KB, double buffered);
-//   16 transform warps     tcgen05.ld the parked item, Hermitian packing + first radix-2 step into the FFT
-//                          buffer, then exactly the passes and the epilogue of k_match_packed.
-// A multiply thread writes TMEM lane L (a warp reaches only the 32 lanes of its quarter), columns
-// b*256 + 8*m + {0..7} for quad L + 128m; transform thread t reads lane t & 127, 64 columns from (t >> 7)*64
-// (eight quads), packs them and scatters the 16 chunks to their places.
-// Measured (profiles/README.md): correct, but 20.8 ms per config-2 step against 17.8 ms for k_match_pair -- the
-// multiply side is a latency-bound instruction stream on few warps -- so it is not the default.
-constexpr int WS_THREADS = 768, WS_MACW = 8, WS_STAGES = 3, WS_SEG = 128, WS_SEGS = Q4 / QBLK;
-constexpr int WS_STAGE_F4 = 2 * 2 * QBLK;                // float4 per ring stage: one block (256 A + 256 M) of a T^ row and of an X^ row
-constexpr unsigned WS_STAGE_BYTES = WS_STAGE_F4 * 16;
-
-// exp(+i*pi*s/128), s = 0..31: the packing twiddle of quad i = L + 128s is wb[L] times this
-__device__ constexpr float kC256[32] = {
-    1.0f, 0.99969881869620425f, 0.99879545620517241f, 0.99729045667869021f, 0.99518472667219693f, 0.99247953459870997f,
-    0.98917650996478101f, 0.98527764238894122f, 0.98078528040323043f, 0.97570213003852857f, 0.97003125319454397f,
-    0.96377606579543984f, 0.95694033573220882f, 0.94952818059303667f, 0.94154406518302081f, 0.93299279883473896f,
-    0.92387953251128674f, 0.91420975570353069f, 0.90398929312344334f, 0.89322430119551532f, 0.88192126434835505f,
-    0.87008699110871146f, 0.85772861000027212f, 0.84485356524970712f, 0.83146961230254524f, 0.81758481315158371f,
-    0.80320753148064494f, 0.78834642762660634f, 0.77301045336273699f, 0.75720884650648457f, 0.74095112535495911f,
-    0.724247082951467f};
-__device__ constexpr float kS256[32] = {
-    0.0f, 0.024541228522912288f, 0.049067674327418015f, 0.073564563599667426f, 0.098017140329560604f, 0.1224106751992162f,
-    0.14673047445536175f, 0.17096188876030122f, 0.19509032201612825f, 0.2191012401568698f, 0.24298017990326387f,
-    0.26671275747489837f, 0.29028467725446233f, 0.31368174039889152f, 0.33688985339222005f, 0.35989503653498811f,
-    0.38268343236508978f, 0.40524131400498986f, 0.42755509343028208f, 0.44961132965460654f, 0.47139673682599764f,
-    0.49289819222978404f, 0.51410274419322166f, 0.53499761988709715f, 0.55557023301960218f, 0.57580819141784534f,
-    0.59569930449243336f, 0.61523159058062682f, 0.63439328416364549f, 0.65317284295377676f, 0.67155895484701833f,
-    0.68954054473706683f};
-
-template <typename S>
-__global__ void __launch_bounds__(WS_THREADS, 1)
-k_match_ws(const float4* __restrict__ That, int64_t part_first,
-           const float4* __restrict__ Xhat, int64_t nblk,
-           const S* __restrict__ img, int64_t img_n,
-           const double2* __restrict__ ipfx, const double2* __restrict__ tpfx,
-           const QueryDesc* __restrict__ desc, const int* __restrict__ item_query, int64_t item_first, int64_t n_items,
-           PackedTables tab, unsigned long long* __restrict__ keys, float* __restrict__ curve_out) {
-    constexpr int NW = QNW;
-    constexpr bool is_u8 = sizeof(S) == 1;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const Smem sm(smem_raw);
-    float4* ring = reinterpret_cast<float4*>(sm.end);                              // [WS_STAGES] stages
-    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(ring + WS_STAGES * WS_STAGE_F4);   // staged windows
-    unsigned long long* ring_full = s_bar + 1;                                     // [WS_STAGES]  copies landed
-    unsigned long long* ring_empty = ring_full + WS_STAGES;                        // [WS_STAGES]  all four multiply warps have read
-    unsigned long long* tm_full = ring_empty + WS_STAGES;                          // [2]
-    unsigned long long* tm_empty = tm_full + 2;                                    // [2]
-    unsigned long long* s_best = tm_empty + 2;                                     // [NW]
-    float* s_min = reinterpret_cast<float*>(s_best + NW);                          // [NW]
-    uint32_t* s_taddr = reinterpret_cast<uint32_t*>(s_min + NW);
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) {
-        mbar_init(s_bar, 1);
-        for (int i = 0; i < WS_STAGES; ++i) { mbar_init(ring_full + i, 1); mbar_init(ring_empty + i, WS_MACW); }
-        for (int i = 0; i < 2; ++i) { mbar_init(tm_full + i, WS_MACW * 32); mbar_init(tm_empty + i, QT); }
-    }
-    if (warp == 0) tmem_alloc(s_taddr, 512);
-    tmem_fence_before();
-    __syncthreads();
-    tmem_fence_after();
-    const uint32_t taddr = *s_taddr;
-
-    // 768 threads start with 80 registers each; the CTA pool is fixed at launch: the multiply warps hand 16 each to the transform warps (88 / 64)
-    if (warp < NW) {
-        setmaxnreg_inc<88>();
-        // ======================= transform warps =======================
-        const Buf& buf = sm.buf;
-        const int Lc = tid & 127, g = tid >> 7;
-        const uint32_t t_in = taddr + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(g * 64);
-        const int lo_base = phys(Lc) + 1088 * g;                                   // chunk Lc + 128m at phys(Lc) + 136m
-        const int hi_base = (Lc ? phys(128 - Lc) + 136 * 63 : 136 * 64) - 1088 * g;   // chunk B/2 - (Lc + 128m), minus 136m
-        const float2 wbase = __ldg(tab.wb + Lc);
-        if (is_u8 && (int64_t)blockIdx.x < n_items) {
-            const Item first(desc, item_query, item_first, blockIdx.x);
-            stage_inputs(first, tid, reinterpret_cast<const uint8_t*>(img), img_n, ipfx, sm, s_bar);
-        }
-        unsigned n = 0;
-        for (int64_t local = blockIdx.x; local < n_items; local += gridDim.x, ++n) {
-            const Item it(desc, item_query, item_first, local);
-            const unsigned b = n & 1u;
-            // ---- un-park: TMEM -> registers -> Hermitian packing + first radix-2 step -> FFT buffer.
-            // One warp polls; the others sleep in the barrier.
-            if (warp == 0) mbar_wait_sleep(tm_full + b, (n >> 1) & 1u, 32);
-            csync<1>();
-            tmem_fence_after();
-#pragma unroll
-            for (int c4 = 0; c4 < 4; ++c4) {
-                float v[16];
-                tmem_ld16(t_in + b * 256u + (uint32_t)(c4 * 16), v);
-                tmem_wait_ld();
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int mm = 2 * c4 + h;                                   // quad i = Lc + 128m, m = 8g + mm
-                    const float kc = kC256[8 * g + mm], ks = kS256[8 * g + mm];  // exp(i*pi*i/B) = wb[Lc] * exp(i*pi*m/128)
-                    const float c = wbase.x * kc - wbase.y * ks, s = wbase.x * ks + wbase.y * kc;
-                    C2 lo, hi;
-                    pack_quad(make_float2(v[8 * h + 0], v[8 * h + 1]), make_float2(v[8 * h + 2], v[8 * h + 3]),
-                              make_float2(v[8 * h + 4], v[8 * h + 5]), make_float2(v[8 * h + 6], v[8 * h + 7]), c, s, lo, hi);
-                    buf.st(lo_base + 136 * mm, lo);
-                    if (!(mm == 0 && tid == 0)) buf.st(hi_base - 136 * mm, hi);   // quad 0 has no mirror
-                }
-            }
-            if (warp == NW - 1) {                                                 // the self-mirrored quad i = B/4
-                int P = it.d.P;
-                if (it.k + P > nblk) P = (int)(nblk - it.k);
-                const C2 sp = special_quad(That + (it.d.partBase - part_first) * (int64_t)QROW, Xhat + it.k * (int64_t)QROW, P, lane);
-                if (lane == 0) buf.st(phys(Q4), sp);
-            }
-            tmem_fence_before();
-            mbar_arrive(tm_empty + b);
-            csync<1>();
-            fft_passes<1>(buf, tid, tab, is_u8);
-            finish_item<S, 1, 1>(it, tid, sm, s_bar, n & 1u, s_best, s_min, nullptr, img, img_n, ipfx, tpfx, tab, keys, curve_out,
-                              [&] {   // every thread is done with the staged windows: start the next item's copies
-                                  if (is_u8 && local + gridDim.x < n_items) {
-                                      const Item nxt(desc, item_query, item_first, local + gridDim.x);
-                                      stage_inputs(nxt, tid, reinterpret_cast<const uint8_t*>(img), img_n, ipfx, sm, s_bar);
-                                  }
-                              });
-        }
-    } else {
-        setmaxnreg_dec<64>();
-        // ======================= multiply warps =======================
-        // Step = (item, block of 256 quads, partition); its stage holds that block of the T^ row and of the X^
-        // row (two 8 KB bulk copies).  Thread (quarter q, lane l, half h) owns TMEM lane L = 32q + l and quad
-        // L + 128h of the block, i.e. quads i = L + 128m with m = h (mod 2); its eight accumulators
-        // Y = sum_p conj(T^_p) X^_{k+p} of a quad go to columns 8m .. 8m+7 as they are (the transform warps do
-        // the packing when they take the item out).  Steps are copied WS_STAGES - 1 ahead, across items; the
-        // eight warps take turns issuing (warp u % 8 issues step u).
-        const int mw = warp - NW;                                                 // 0 .. 7
-        const int hf = mw >> 2;                                                   // which of the two quads per lane and block
-        const int L = (mw & 3) * 32 + lane;                                       // TMEM lane
-        const uint32_t t_out = taddr + ((uint32_t)((mw & 3) * 32) << 16) + (uint32_t)(hf * 8);
-        const float4* const my = ring + L + hf * WS_SEG;                          // this thread's chunk in stage 0
-
-        // issue cursor (every lane tracks it; values are warp-uniform): row offsets in float4 units
-        int64_t i_local = blockIdx.x;
-        int i_seg = 0, i_p = 0, i_P = 1;
-        unsigned i_toff = 0, i_xoff = 0;                 // offset of (row p, block seg) from That / Xhat
-        unsigned i_stage = 0, i_use1 = 1, i_turn = 0;    // stage, parity to wait for on ring_empty, whose turn
-        auto cursor_load = [&]() {
-            if (i_local < n_items) {
-                const Item it(desc, item_query, item_first, i_local);
-                i_P = it.d.P;
-                if (it.k + i_P > nblk) i_P = (int)(nblk - it.k);
-                i_toff = (unsigned)((it.d.partBase - part_first) * (int64_t)QROW);
-                i_xoff = (unsigned)(it.k * (int64_t)QROW);
-            }
-        };
-        auto issue = [&]() {
-            if (i_local >= n_items) return;
-            if (i_turn == (unsigned)mw && lane == 0) {
-                mbar_wait_sleep(ring_empty + i_stage, i_use1, 20);                 // every warp is done with its previous contents
-                float4* st = ring + i_stage * WS_STAGE_F4;
-                mbar_expect_tx(ring_full + i_stage, WS_STAGE_BYTES);
-                tma_load_1d(st, That + i_toff, 2 * QBLK * 16, ring_full + i_stage);
-                tma_load_1d(st + 2 * QBLK, Xhat + i_xoff, 2 * QBLK * 16, ring_full + i_stage);
-            }
-            i_turn = (i_turn + 1) & (WS_MACW - 1);
-            if (++i_stage == WS_STAGES) { i_stage = 0; i_use1 ^= 1u; }
-            i_toff += QROW; i_xoff += QROW;                                        // next partition, same block
-            if (++i_p >= i_P) {
-                i_p = 0;
-                i_toff += 2 * QBLK - (unsigned)i_P * QROW; i_xoff += 2 * QBLK - (unsigned)i_P * QROW;   // next block, partition 0
-                if (++i_seg == WS_SEGS) { i_seg = 0; i_local += gridDim.x; cursor_load(); }
-            }
-        };
-        cursor_load();
-        for (int s0 = 0; s0 < WS_STAGES - 1; ++s0) issue();
-
-        unsigned stage = 0, phase = 0, n = 0;
-        for (int64_t local = blockIdx.x; local < n_items; local += gridDim.x, ++n) {
-            const Item it(desc, item_query, item_first, local);
-            int P = it.d.P;
-            if (it.k + P > nblk) P = (int)(nblk - it.k);
-            const unsigned b = n & 1u;
-            mbar_wait_sleep(tm_empty + b, ((n >> 1) & 1u) ^ 1u, 64);               // the transform warps drained this half
-            tmem_fence_after();
-            const uint32_t col0 = t_out + b * 256u;
-            for (int seg = 0; seg < WS_SEGS; ++seg) {
-                QuadAcc acc; acc.zero();
-                for (int p = 0; p < P; ++p) {
-                    issue();                                                       // WS_STAGES - 1 steps ahead
-                    mbar_wait_sleep(ring_full + stage, phase, 20);
-                    const float4* st = my + stage * WS_STAGE_F4;                   // T^: A at +0, M at +256; X^: 512 further
-                    acc.mac(st[0], st[QBLK], st[2 * QBLK], st[3 * QBLK]);
-                    // generic-proxy reads of this stage must be ordered before the async-proxy (TMA) refill:
-                    // the mbarrier hand-over alone does not do that (measured: stale quads without the fence)
-                    fence_proxy_async();
-                    __syncwarp();                                                  // every lane has read this stage
-                    if (lane == 0) mbar_arrive(ring_empty + stage);
-                    if (++stage == WS_STAGES) { stage = 0; phase ^= 1u; }
-                }
-                tmem_st8(col0 + (uint32_t)(seg * 16), acc.aR.x, acc.aR.y, acc.aI.x, acc.aI.y, acc.mR.x, acc.mR.y, acc.mI.x, acc.mI.y);
-            }
-            tmem_wait_st();
-            tmem_fence_before();
-            mbar_arrive(tm_full + b);
-        }
-    }
-    tmem_fence_before();
-    __syncthreads();
-    if (warp == 0) tmem_dealloc(taddr, 512);
 }
 
 // A parked product spectrum back into the FFT buffer: this thread's 64 tensor-memory columns hold, quad by quad,
@@ -1082,7 +825,7 @@ __device__ __forceinline__ void unpark(uint32_t tsrc, const Buf& buf, int col, i
 // parked in TENSOR MEMORY (tcgen05.st; every thread later reads back exactly what it wrote, so the 32-lane
 // window of a warp is no constraint) while the CTA transforms the first; then it is taken out again
 // (tcgen05.ld) and goes through the same passes and epilogue.
-template <typename S, int EPI, int FMT>
+template <typename S, int EPI>
 __global__ void __launch_bounds__(QT, 1)
 k_match_pair(const float4* __restrict__ That, int64_t part_first,
              const float4* __restrict__ Xhat, int64_t nblk,
@@ -1126,12 +869,12 @@ k_match_pair(const float4* __restrict__ That, int64_t part_first,
     C2 sp1 = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};             // C[B/4] of the second item (warp NW-1, lane 0)
     // ---------------- 1+2. multiply-accumulate for both items, packing, first radix-2 step ----
     {
-        typedef Rows<FMT> R;
+        typedef Rows R;
         const int64_t k = it0.k;
         const float4* tp = That + (d.partBase - part_first) * (int64_t)R::STRIDE;
         const float4* xp = Xhat + k * (int64_t)R::STRIDE;
         const float2 wbase = __ldg(tab.wb + tid);
-        if (EPI == 2 && SB_V2_SPECIAL_PREFETCH && warp == NW - 1) special_prefetch<FMT>(s_sp, tp, xp, d.P, 2, k, nblk, lane);
+        if (EPI == 2 && SB_V2_SPECIAL_PREFETCH && warp == NW - 1) special_prefetch(s_sp, tp, xp, d.P, 2, k, nblk, lane);
         constexpr int U = 2;                          // quads in flight per thread (two accumulator sets each)
 #pragma unroll 1
         for (int grp = 0; grp < 8 / U; ++grp) {
@@ -1179,16 +922,16 @@ k_match_pair(const float4* __restrict__ That, int64_t part_first,
             if constexpr (EPI == 2 && SB_V2_SPECIAL_PREFETCH) {
                 cp_async_commit_wait_all();
                 __syncwarp();
-                const C2 lo = special_from_smem<FMT>(s_sp, d.P, 0, lane);
+                const C2 lo = special_from_smem(s_sp, d.P, 0, lane);
                 if (lane == 0) buf.st(phys(Q4), lo);
-                if (has2) sp1 = special_from_smem<FMT>(s_sp, d.P, 1, lane);
+                if (has2) sp1 = special_from_smem(s_sp, d.P, 1, lane);
             } else {
                 int P0 = d.P; if (k + P0 > nblk) P0 = (int)(nblk - k);
-                const C2 lo = special_quad<FMT>(tp, xp, P0, lane);
+                const C2 lo = special_quad(tp, xp, P0, lane);
                 if (lane == 0) buf.st(phys(Q4), lo);
                 if (has2) {
                     int P1 = d.P; if (k + 1 + P1 > nblk) P1 = (int)(nblk - k - 1);
-                    sp1 = special_quad<FMT>(tp, xp + R::STRIDE, P1, lane);
+                    sp1 = special_quad(tp, xp + R::STRIDE, P1, lane);
                 }
             }
         }
@@ -1214,217 +957,19 @@ k_match_pair(const float4* __restrict__ That, int64_t part_first,
     if (warp == 0) tmem_dealloc(*s_taddr, 256);
 }
 
-// ---------------------------------------------------------------- kernel A3: one CTA per TRIPLE of lag blocks
-// (engine 6; written without GPU access at the end of round 1 -- opt-in until it has been measured.)
-// k_match_pair's multiply phase runs at the L2 -> SM rate, so only fewer bytes make it faster: three consecutive
-// lag blocks of a query share their template rows and overlap in their spectrum rows, 2P + 2 row reads instead
-// of 3P + 3/2 for pairs (P = 2: 2.0 instead of 2.5 rows per lag block).  Tensor memory holds exactly two parked
-// product spectra (2 x 256 columns), so the first block goes to shared memory and the other two wait there.
-// Three accumulator sets leave room for one quad per thread and step; to keep as many loads in flight as the pair
-// kernel has, the rows of step p + 1 are requested before the multiply-accumulates of step p.
-template <typename S, int EPI, int FMT>
-__global__ void __launch_bounds__(QT, 1)
-k_match_triple(const float4* __restrict__ That, int64_t part_first,
-               const float4* __restrict__ Xhat, int64_t nblk,
-               const S* __restrict__ img, int64_t img_n,
-               const double2* __restrict__ ipfx, const double2* __restrict__ tpfx,
-               const QueryDesc* __restrict__ desc, const int* __restrict__ trip_query, int64_t trip_first, int64_t n_trips,
-               PackedTables tab, unsigned long long* __restrict__ keys, float* __restrict__ curve_out) {
-    constexpr int T = QT, NW = QNW;
-    constexpr bool is_u8 = sizeof(S) == 1;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const Smem sm(smem_raw);
-    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(sm.end);
-    unsigned long long* s_best = s_bar + 1;                                // [NW]
-    float* s_min = reinterpret_cast<float*>(s_best + NW);                  // [NW]
-    uint32_t* s_taddr = reinterpret_cast<uint32_t*>(s_min + NW);
-    int* s_nq = reinterpret_cast<int*>(sm.end + 208);                      // [4] query of the triples i, i+1, i+2 (slot i % 3)
-    QueryDesc* s_nd = reinterpret_cast<QueryDesc*>(sm.end + 224);          // [2] descriptor of the triples i, i+1 (slot i & 1)
-    static_assert(224 + 2 * sizeof(QueryDesc) <= kQueryConstOff() && kQueryConstOff() + 32 <= kSmallBytes && sizeof(QueryDesc) % 16 == 0, "small area");
-    float4* s_sp = reinterpret_cast<float4*>(sm.end + kSmallBytes);        // EPI 2: units of the self-mirrored quads
-    int2* s_w0 = EPI == 2 && is_u8 ? reinterpret_cast<int2*>(sm.end + kSmallBytes + kSpecialBytes) : nullptr;   // [kRounds][QT]
-    const Buf& buf = sm.buf;
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // Persistent: one CTA per SM walks the triples blockIdx.x, blockIdx.x + gridDim.x, ...  A fresh CTA per triple
-    // starts with two dependent global reads (its query, then the descriptor) before it can request a single
-    // spectrum row, and allocates / releases tensor memory and its barrier every time; here thread 0 fetches the
-    // query index two triples ahead and the descriptor one triple ahead with cp.async while the CTA works.
-    if (warp == 0) tmem_alloc(s_taddr, 512);
-    if (tid == 0) {
-        if (is_u8) mbar_init(s_bar, 1);
-        const int64_t t0 = blockIdx.x, t1 = t0 + gridDim.x;
-        s_nq[0] = __ldg(trip_query + t0);
-        s_nd[0] = desc[s_nq[0]];
-        if (t1 < n_trips) s_nq[1] = __ldg(trip_query + t1);
-    }
-    tmem_fence_before();
-    csync<0>();
-    tmem_fence_after();
-    // this thread's columns: lane quarter of its warp, column block of its warp group; second block at +0,
-    // third block at +256
-    const uint32_t tcol = *s_taddr + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 64);
-    const int tm = (T - tid) & (T - 1);               // mirrored chunks C[B/2 - i] live in thread tm's column
-    const int col = phys(tid), mcol = phys(tm);
-    unsigned ph = 0;                                  // phases of s_bar consumed so far (one per staged item)
-
-#pragma unroll 1
-    for (int trip = (int)blockIdx.x, iter = 0; trip < (int)n_trips; trip += (int)gridDim.x, ++iter) {     // n_trips < 2^31
-    if (iter) {
-        if (tid == 0) cp_async_commit_wait_all();     // this triple's descriptor has landed
-        csync<0>();                                   // ... and everyone is done with the previous triple
-    }
-    const int q = s_nq[iter % 3];
-    const QueryDesc d = s_nd[iter & 1];
-    if (tid == 0) {                                   // slots last read one triple ago: free since the barrier above
-        if (trip + (int)gridDim.x < (int)n_trips) {
-            const uint4* src = reinterpret_cast<const uint4*>(desc + s_nq[(iter + 1) % 3]);
-            uint4* dst = reinterpret_cast<uint4*>(s_nd + ((iter + 1) & 1));
-#pragma unroll
-            for (int c = 0; c < (int)(sizeof(QueryDesc) / 16); ++c) cp_async16(dst + c, src + c);
-        }
-        if ((int64_t)trip + 2 * (int64_t)gridDim.x < n_trips) cp_async4(s_nq + (iter + 2) % 3, trip_query + trip + 2 * (int)gridDim.x);
-    }
-    const int lt = (int)(trip_first + trip - d.groupBase);                // triple number inside the query
-    const int nb = d.nk - 3 * lt < 3 ? d.nk - 3 * lt : 3;                 // lag blocks of this triple (uniform)
-    const Item it0(d, q, d.k0 + 3 * lt), it1(d, q, d.k0 + 3 * lt + 1), it2(d, q, d.k0 + 3 * lt + 2);
-    if (is_u8) stage_inputs(it0, tid, reinterpret_cast<const uint8_t*>(img), img_n, ipfx, sm, s_bar);
-    if (EPI == 2 && tid == 64) query_constants<S>(reinterpret_cast<double2*>(sm.end + kQueryConstOff()), d, img_n, ipfx, tpfx);
-    C2 sp1 = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)}, sp2 = sp1;   // C[B/4] of blocks 2 and 3 (warp NW-1, lane 0)
-    {
-        typedef Rows<FMT> R;
-        const int64_t k = it0.k;
-        const float4* tp = That + (d.partBase - part_first) * (int64_t)R::STRIDE;
-        const float4* xp = Xhat + k * (int64_t)R::STRIDE;
-        const float2 wbase = __ldg(tab.wb + tid);
-        if (EPI == 2 && SB_V2_SPECIAL_PREFETCH && warp == NW - 1) special_prefetch<FMT>(s_sp, tp, xp, d.P, 3, k, nblk, lane);
-#pragma unroll 1
-        for (int uu = 0; uu < 8; ++uu) {              // quad i = tid + 512*uu
-            const int i0 = R::unit(tid, uu);
-            QuadAcc a0, a1, a2;
-            a0.zero(); a1.zero(); a2.zero();
-            float4 x0a, x0m, x1a, x1m, ta, tmm, x2a, x2m;
-            R::load(xp, i0, x0a, x0m);                                             // row k < nblk
-            R::loadp(xp + R::STRIDE, i0, k + 1 < nblk, x1a, x1m);                  // rows past the end of the stream are zero
-            R::load(tp, i0, ta, tmm);
-            R::loadp(xp + 2 * (int64_t)R::STRIDE, i0, k + 2 < nblk, x2a, x2m);
-#pragma unroll 1
-            for (int p = 0; p < d.P; ++p) {
-                // request the rows of step p + 1 (template row p + 1, spectrum row k + p + 3) ...
-                // (predicated loads, not branches: the scheduler may then hoist them above the arithmetic)
-                const bool more = p + 1 < d.P, xrow = more && k + p + 3 < nblk;
-                float4 na, nm, nxa, nxm;
-                R::loadp(tp + (int64_t)(p + 1) * R::STRIDE, i0, more, na, nm);
-                R::loadp(xp + (int64_t)(p + 3) * R::STRIDE, i0, xrow, nxa, nxm);
-                // ... then multiply step p: block k + j needs spectrum row k + j + p
-                a0.mac(ta, tmm, x0a, x0m);
-                a1.mac(ta, tmm, x1a, x1m);
-                a2.mac(ta, tmm, x2a, x2m);
-                x0a = x1a; x0m = x1m; x1a = x2a; x1m = x2m; x2a = nxa; x2m = nxm;
-                ta = na; tmm = nm;
-            }
-            const float c = wbase.x * kC64[uu & 7] - wbase.y * kS64[uu & 7];
-            const float s = wbase.x * kS64[uu & 7] + wbase.y * kC64[uu & 7];
-            C2 lo, hi;
-            pack_quad(a0.aR, a0.aI, a0.mR, a0.mI, c, s, lo, hi);
-            buf.st(col + 544 * uu, lo);                           // C[i]
-            if (tid != 0) buf.st(mcol + 544 * (15 - uu), hi);     // C[B/2 - i]
-            else if (uu != 0) buf.st(mcol + 544 * (16 - uu), hi);
-            pack_quad(a1.aR, a1.aI, a1.mR, a1.mI, c, s, lo, hi);
-            tmem_st8(tcol + (uint32_t)(uu * 8), lo.r.x, lo.r.y, lo.i.x, lo.i.y, hi.r.x, hi.r.y, hi.i.x, hi.i.y);
-            pack_quad(a2.aR, a2.aI, a2.mR, a2.mI, c, s, lo, hi);
-            tmem_st8(tcol + 256u + (uint32_t)(uu * 8), lo.r.x, lo.r.y, lo.i.x, lo.i.y, hi.r.x, hi.r.y, hi.i.x, hi.i.y);
-        }
-        if (warp == NW - 1) {                         // the self-mirrored quad i = B/4 of the three items
-            if constexpr (EPI == 2 && SB_V2_SPECIAL_PREFETCH) {
-                cp_async_commit_wait_all();
-                __syncwarp();
-                const C2 lo = special_from_smem<FMT>(s_sp, d.P, 0, lane);
-                if (lane == 0) buf.st(phys(Q4), lo);
-                if (nb > 1) sp1 = special_from_smem<FMT>(s_sp, d.P, 1, lane);
-                if (nb > 2) sp2 = special_from_smem<FMT>(s_sp, d.P, 2, lane);
-            } else {
-                int P0 = d.P; if (k + P0 > nblk) P0 = (int)(nblk - k);
-                const C2 lo = special_quad<FMT>(tp, xp, P0, lane);
-                if (lane == 0) buf.st(phys(Q4), lo);
-                if (nb > 1) {
-                    int P1 = d.P; if (k + 1 + P1 > nblk) P1 = (int)(nblk - k - 1);
-                    sp1 = special_quad<FMT>(tp, xp + R::STRIDE, P1, lane);
-                }
-                if (nb > 2) {
-                    int P2 = d.P; if (k + 2 + P2 > nblk) P2 = (int)(nblk - k - 2);
-                    sp2 = special_quad<FMT>(tp, xp + 2 * (int64_t)R::STRIDE, P2, lane);
-                }
-            }
-        }
-        tmem_wait_st();
-    }
-    csync<0>();
-
-    // ---------------- first item: inverse FFT + epilogue ---------------------------------------
-    const float4 wt0 = fft_passes<0, EPI == 2 && SB_V2_MIDBAR>(buf, tid, tab, is_u8);
-    finish_item<S, 0, EPI>(it0, tid, sm, s_bar, ph & 1u, s_best, s_min, s_w0, img, img_n, ipfx, tpfx, tab, keys, curve_out,
-                           [&] { if (is_u8 && nb > 1) stage_inputs(it1, tid, reinterpret_cast<const uint8_t*>(img), img_n, ipfx, sm, s_bar); }, wt0);
-
-    // ---------------- second and third item: out of tensor memory, then the same ------------------
-#pragma unroll 1
-    for (int j = 1; j < nb; ++j) {                    // uniform over the CTA
-        const uint32_t tsrc = tcol + (j == 2 ? 256u : 0u);
-        unpark<EPI == 2>(tsrc, buf, col, mcol, tid);
-        if (tid == (NW - 1) * 32) buf.st(phys(Q4), j == 1 ? sp1 : sp2);
-        csync<0>();
-        const float4 wtj = fft_passes<0, EPI == 2 && SB_V2_MIDBAR>(buf, tid, tab, is_u8);
-        if (j == 1)
-            finish_item<S, 0, EPI>(it1, tid, sm, s_bar, (ph + 1u) & 1u, s_best, s_min, s_w0, img, img_n, ipfx, tpfx, tab, keys, curve_out,
-                                   [&] { if (is_u8 && nb > 2) stage_inputs(it2, tid, reinterpret_cast<const uint8_t*>(img), img_n, ipfx, sm, s_bar); }, wtj);
-        else
-            finish_item<S, 0, EPI>(it2, tid, sm, s_bar, (ph + 2u) & 1u, s_best, s_min, s_w0, img, img_n, ipfx, tpfx, tab, keys, curve_out, [] {}, wtj);
-    }
-    ph += (unsigned)nb;
-    }   // next triple of this CTA
-    tmem_fence_before();
-    csync<0>();
-    if (warp == 0) tmem_dealloc(*s_taddr, 512);
-}
-
 // pair_query[i] = query of pair (pair_first + i): one CTA per query fills its own range
 __global__ void k_fill_pair_query(const QueryDesc* __restrict__ desc, int q_begin, int64_t pair_first, int* __restrict__ pair_query, int group) {
     const int q = q_begin + blockIdx.x;
     const int64_t base = desc[q].groupBase - pair_first;
-    const int np = (desc[q].nk + group - 1) / group;           // pairs (group = 2) or triples (3) of lag blocks
+    const int np = (desc[q].nk + group - 1) / group;           // pairs of lag blocks
     for (int i = threadIdx.x; i < np; i += blockDim.x) pair_query[base + i] = q;
-}
-
-size_t ws_smem_bytes() {
-    return kSmemCommon + (size_t)WS_STAGES * WS_STAGE_BYTES + 8 * (1 + 2 * WS_STAGES + 4) + QNW * sizeof(unsigned long long)
-         + QNW * sizeof(float) + 16 + 64;
 }
 
 // ---------------------------------------------------------------- forward spectra, quad layout
 // Same transform as k_forward_rows in sb_fused.cu (gather + centring + 2B-point real FFT through the
 // shared-memory inverse passes run backwards); only the output stage differs: bins leave as the chunks
 // A[i] = (X[i], X[i+B/2]) and M[i] = (X[B-i], X[B/2-i]) the packed kernel multiplies.
-// One quad in the 16-bit row format: components scaled by 32767 / (maximum of their bin family over the group of
-// eight quads), rounded to nearest; the lane of the group's first quad also writes the four scales.
-__device__ __forceinline__ void store_quad16(uint4* row, int i, float2 x_i, float2 x_hb, float2 x_bi, float2 x_h,
-                                             float m0, float m1, float m2, float m3) {
-    auto q = [](float v, float mx) -> unsigned {
-        const float inv = mx > 0.f ? 32767.0f / mx : 0.f;
-        int r = __float2int_rn(v * inv);
-        r = r > 32767 ? 32767 : (r < -32767 ? -32767 : r);
-        return (unsigned)r & 0xffffu;
-    };
-    uint4 o;
-    o.x = q(x_i.x, m0) | (q(x_hb.x, m1) << 16);      // re X[i],   re X[i+B/2]
-    o.y = q(x_i.y, m0) | (q(x_hb.y, m1) << 16);      // im X[i],   im X[i+B/2]
-    o.z = q(x_bi.x, m2) | (q(x_h.x, m3) << 16);      // re X[B-i], re X[B/2-i]
-    o.w = q(x_bi.y, m2) | (q(x_h.y, m3) << 16);      // im X[B-i], im X[B/2-i]
-    row[i] = o;
-    if ((i & 7) == 0)
-        reinterpret_cast<float4*>(row)[QSCALE0 + (i >> 3)] = make_float4(m0 / 32767.0f, m1 / 32767.0f, m2 / 32767.0f, m3 / 32767.0f);
-}
-
-template <typename S, int MODE, int FMT>
+template <typename S, int MODE>
 __global__ void __launch_bounds__(Cfg<14>::T, 1)
 k_forward_quad(const S* __restrict__ src, int64_t src_n, const double2* __restrict__ pfx,
                const QueryDesc* __restrict__ desc, int q_begin, int q_end, int64_t row_first,
@@ -1485,37 +1030,13 @@ k_forward_quad(const S* __restrict__ src, int64_t src_n, const double2* __restri
         xk = make_float2(xe.x + tv.x, xe.y + tv.y);
         xbk = make_float2(xe.x - tv.x, -(xe.y - tv.y));
     };
-    if constexpr (FMT == 0) {
-        float4* o = out + (int64_t)blockIdx.x * QROW;
-        for (int i = tid; i <= Q4; i += T) {
-            float2 x_i, x_bi, x_h, x_hb;
-            bins(i, x_i, x_bi);                          // X[i], X[B-i]
-            bins(B / 2 - i, x_h, x_hb);                  // X[B/2-i], X[B/2+i]
-            o[qa(i)] = make_float4(x_i.x, x_hb.x, x_i.y, x_hb.y);
-            o[qm(i)] = make_float4(x_bi.x, x_h.x, x_bi.y, x_h.y);
-        }
-    } else {
-        uint4* o = reinterpret_cast<uint4*>(out) + (int64_t)blockIdx.x * QROW16;
-        auto amax = [](float2 v) { return fmaxf(fabsf(v.x), fabsf(v.y)); };
-        for (int it = 0; it < Q4 / T; ++it) {            // every lane takes part: groups are 8 consecutive lanes
-            const int i = tid + it * T;
-            float2 x_i, x_bi, x_h, x_hb;
-            bins(i, x_i, x_bi);
-            bins(B / 2 - i, x_h, x_hb);
-            float m0 = amax(x_i), m1 = amax(x_hb), m2 = amax(x_bi), m3 = amax(x_h);
-#pragma unroll
-            for (int d = 1; d < 8; d <<= 1) {
-                m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, d)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, d));
-                m2 = fmaxf(m2, __shfl_xor_sync(0xffffffffu, m2, d)); m3 = fmaxf(m3, __shfl_xor_sync(0xffffffffu, m3, d));
-            }
-            store_quad16(o, i, x_i, x_hb, x_bi, x_h, m0, m1, m2, m3);
-        }
-        if (tid == 0) {                                  // the self-mirrored quad i = B/4: a group of its own
-            float2 x_i, x_bi, x_h, x_hb;
-            bins(Q4, x_i, x_bi);
-            bins(B / 2 - Q4, x_h, x_hb);
-            store_quad16(o, Q4, x_i, x_hb, x_bi, x_h, amax(x_i), amax(x_hb), amax(x_bi), amax(x_h));
-        }
+    float4* o = out + (int64_t)blockIdx.x * QROW;
+    for (int i = tid; i <= Q4; i += T) {
+        float2 x_i, x_bi, x_h, x_hb;
+        bins(i, x_i, x_bi);                          // X[i], X[B-i]
+        bins(B / 2 - i, x_h, x_hb);                  // X[B/2-i], X[B/2+i]
+        o[qa(i)] = make_float4(x_i.x, x_hb.x, x_i.y, x_hb.y);
+        o[qm(i)] = make_float4(x_bi.x, x_h.x, x_bi.y, x_h.y);
     }
 }
 
@@ -1588,7 +1109,7 @@ __global__ void k_fill_item_query2(const QueryDesc* __restrict__ desc, int q_beg
 int* g_item_query2 = nullptr;
 int64_t g_item_query2_cap = 0;
 
-template <typename S, int MODE, int FMT>
+template <typename S, int MODE>
 int launch_forward_quad_typed(const sb_stream* src, const QueryDesc* d_desc, int q_begin, int q_end,
                               int64_t row_first, int64_t rows, float2* out) {
     Ctx& c = ctx();
@@ -1597,10 +1118,10 @@ int launch_forward_quad_typed(const sb_stream* src, const QueryDesc* d_desc, int
     static bool attr_set = false;
     const size_t smem = forward_smem_bytes14();
     if (!attr_set) {
-        SB_CUDA(cudaFuncSetAttribute(k_forward_quad<S, MODE, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SB_CUDA(cudaFuncSetAttribute(k_forward_quad<S, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
-    k_forward_quad<S, MODE, FMT><<<(unsigned)rows, Cfg<14>::T, smem, c.stream>>>(
+    k_forward_quad<S, MODE><<<(unsigned)rows, Cfg<14>::T, smem, c.stream>>>(
         static_cast<const S*>(src->d_raw), src->n, src->d_pfx, d_desc, q_begin, q_end, row_first, tab,
         reinterpret_cast<float4*>(out));
     SB_CUDA(cudaGetLastError());
@@ -1621,7 +1142,7 @@ int ensure_item_query(int64_t n) {
 // Launchers of the three match kernels.  `Kernel` is one instantiation (sample type x epilogue variant); its
 // dynamic shared memory limit is raised once.  The uint8 kernels exist with both epilogues (Ctx::epilogue),
 // float32 streams have the first one only.
-template <typename S, int EPI, int FMT>
+template <typename S, int EPI>
 int launch_packed_typed(const sb_stream* image, const sb_stream* tmpl, const float2* d_parts, int64_t part_first,
                         const QueryDesc* d_desc, int64_t item_first, int64_t n_items, const PackedTables& tab,
                         unsigned long long* d_keys, float* d_curve) {
@@ -1629,13 +1150,13 @@ int launch_packed_typed(const sb_stream* image, const sb_stream* tmpl, const flo
     static bool attr_set = false;
     const size_t smem = packed_smem_bytes(EPI);
     if (!attr_set) {
-        SB_CUDA(cudaFuncSetAttribute(k_match_packed<S, EPI, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SB_CUDA(cudaFuncSetAttribute(k_match_packed<S, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
     const int64_t max_grid = 1 << 30;
     for (int64_t i0 = 0; i0 < n_items; i0 += max_grid) {
         const int64_t ni = std::min<int64_t>(max_grid, n_items - i0);
-        k_match_packed<S, EPI, FMT><<<(unsigned)ni, QT, smem, c.stream>>>(
+        k_match_packed<S, EPI><<<(unsigned)ni, QT, smem, c.stream>>>(
             reinterpret_cast<const float4*>(d_parts), part_first, reinterpret_cast<const float4*>(image->d_specq), image->nblkq,
             static_cast<const S*>(image->d_raw), image->n, image->d_pfx, tmpl->d_pfx, d_desc, g_item_query2 + i0, item_first + i0,
             tab, d_keys, d_curve);
@@ -1644,7 +1165,7 @@ int launch_packed_typed(const sb_stream* image, const sb_stream* tmpl, const flo
     return SB_OK;
 }
 
-template <typename S, int EPI, int FMT>
+template <typename S, int EPI>
 int launch_pair_typed(const sb_stream* image, const sb_stream* tmpl, const float2* d_parts, int64_t part_first,
                       const QueryDesc* d_desc, int64_t pair_first, int64_t n_pairs, const PackedTables& tab,
                       unsigned long long* d_keys, float* d_curve) {
@@ -1652,10 +1173,10 @@ int launch_pair_typed(const sb_stream* image, const sb_stream* tmpl, const float
     static bool attr_set = false;
     const size_t smem = packed_smem_bytes(EPI) + 16;
     if (!attr_set) {
-        SB_CUDA(cudaFuncSetAttribute(k_match_pair<S, EPI, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SB_CUDA(cudaFuncSetAttribute(k_match_pair<S, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
-    k_match_pair<S, EPI, FMT><<<(unsigned)n_pairs, QT, smem, c.stream>>>(
+    k_match_pair<S, EPI><<<(unsigned)n_pairs, QT, smem, c.stream>>>(
         reinterpret_cast<const float4*>(d_parts), part_first, reinterpret_cast<const float4*>(image->d_specq), image->nblkq,
         static_cast<const S*>(image->d_raw), image->n, image->d_pfx, tmpl->d_pfx, d_desc, g_item_query2, pair_first,
         tab, d_keys, d_curve);
@@ -1663,53 +1184,10 @@ int launch_pair_typed(const sb_stream* image, const sb_stream* tmpl, const float
     return SB_OK;
 }
 
-template <typename S, int EPI, int FMT>
-int launch_triple_typed(const sb_stream* image, const sb_stream* tmpl, const float2* d_parts, int64_t part_first,
-                        const QueryDesc* d_desc, int64_t trip_first, int64_t n_trips, const PackedTables& tab,
-                        unsigned long long* d_keys, float* d_curve) {
-    Ctx& c = ctx();
-    static bool attr_set = false;
-    const size_t smem = packed_smem_bytes(EPI) + 16;
-    if (!attr_set) {
-        SB_CUDA(cudaFuncSetAttribute(k_match_triple<S, EPI, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
-    const unsigned grid = (unsigned)std::min<int64_t>(n_trips, c.sm_count);      // one persistent CTA per SM
-    k_match_triple<S, EPI, FMT><<<grid, QT, smem, c.stream>>>(
-        reinterpret_cast<const float4*>(d_parts), part_first, reinterpret_cast<const float4*>(image->d_specq), image->nblkq,
-        static_cast<const S*>(image->d_raw), image->n, image->d_pfx, tmpl->d_pfx, d_desc, g_item_query2, trip_first, n_trips,
-        tab, d_keys, d_curve);
-    SB_CUDA(cudaGetLastError());
-    return SB_OK;
-}
-
-// One instantiation per (sample type, epilogue, row format): float32 streams have epilogue 1 only; the row format
-// is the one the image stream's quad rows were built in (run_batch keeps it equal to Ctx::spectra_fmt, in which
-// the template partition rows of the batch are built).
+// One instantiation per (sample type, epilogue): float32 streams have the first screening loop only.
 #define SB_DISPATCH_MATCH(FN, image, ...) \
-    ((image)->dtype != SB_U8 ? ((image)->specqFmt ? FN<float, 1, 1>(image, __VA_ARGS__) : FN<float, 1, 0>(image, __VA_ARGS__)) \
-     : ctx().epilogue == 2   ? ((image)->specqFmt ? FN<uint8_t, 2, 1>(image, __VA_ARGS__) : FN<uint8_t, 2, 0>(image, __VA_ARGS__)) \
-                             : ((image)->specqFmt ? FN<uint8_t, 1, 1>(image, __VA_ARGS__) : FN<uint8_t, 1, 0>(image, __VA_ARGS__)))
-
-template <typename S>
-int launch_ws_typed(const sb_stream* image, const sb_stream* tmpl, const float2* d_parts, int64_t part_first,
-                    const QueryDesc* d_desc, int64_t item_first, int64_t n_items, const PackedTables& tab,
-                    unsigned long long* d_keys, float* d_curve) {
-    Ctx& c = ctx();
-    static bool attr_set = false;
-    const size_t smem = ws_smem_bytes();
-    if (!attr_set) {
-        SB_CUDA(cudaFuncSetAttribute(k_match_ws<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
-    const unsigned grid = (unsigned)std::min<int64_t>(n_items, c.sm_count);     // one persistent CTA per SM
-    k_match_ws<S><<<grid, WS_THREADS, smem, c.stream>>>(
-        reinterpret_cast<const float4*>(d_parts), part_first, reinterpret_cast<const float4*>(image->d_specq), image->nblkq,
-        static_cast<const S*>(image->d_raw), image->n, image->d_pfx, tmpl->d_pfx, d_desc, g_item_query2, item_first, n_items,
-        tab, d_keys, d_curve);
-    SB_CUDA(cudaGetLastError());
-    return SB_OK;
-}
+    ((image)->dtype != SB_U8 ? FN<float, 1>(image, __VA_ARGS__) \
+     : ctx().epilogue == 2   ? FN<uint8_t, 2>(image, __VA_ARGS__) : FN<uint8_t, 1>(image, __VA_ARGS__))
 
 }  // namespace
 
@@ -1729,20 +1207,6 @@ int launch_match_packed(const sb_stream* image, const sb_stream* tmpl, const flo
     return SB_DISPATCH_MATCH(launch_packed_typed, image, tmpl, d_parts, part_first, d_desc, item_first, n_items, tab, d_keys, d_curve);
 }
 
-int launch_match_ws(const sb_stream* image, const sb_stream* tmpl, const float2* d_parts, int64_t part_first,
-                    const QueryDesc* d_desc, int q_begin, int q_end, int64_t item_first, int64_t n_items,
-                    unsigned long long* d_keys, float* d_curve) {
-    Ctx& c = ctx();
-    PackedTables tab;
-    SB_TRY(ensure_packed_tables(&tab));
-    SB_TRY(ensure_item_query(n_items));
-    k_fill_item_query2<<<(unsigned)(q_end - q_begin), 128, 0, c.stream>>>(d_desc, q_begin, item_first, g_item_query2);
-    c.launches += 1;
-    return image->dtype == SB_U8
-        ? launch_ws_typed<uint8_t>(image, tmpl, d_parts, part_first, d_desc, item_first, n_items, tab, d_keys, d_curve)
-        : launch_ws_typed<float>(image, tmpl, d_parts, part_first, d_desc, item_first, n_items, tab, d_keys, d_curve);
-}
-
 int launch_match_pair(const sb_stream* image, const sb_stream* tmpl, const float2* d_parts, int64_t part_first,
                       const QueryDesc* d_desc, int q_begin, int q_end, int64_t pair_first, int64_t n_pairs,
                       unsigned long long* d_keys, float* d_curve) {
@@ -1755,33 +1219,15 @@ int launch_match_pair(const sb_stream* image, const sb_stream* tmpl, const float
     return SB_DISPATCH_MATCH(launch_pair_typed, image, tmpl, d_parts, part_first, d_desc, pair_first, n_pairs, tab, d_keys, d_curve);
 }
 
-int launch_match_triple(const sb_stream* image, const sb_stream* tmpl, const float2* d_parts, int64_t part_first,
-                        const QueryDesc* d_desc, int q_begin, int q_end, int64_t trip_first, int64_t n_trips,
-                        unsigned long long* d_keys, float* d_curve) {
-    Ctx& c = ctx();
-    PackedTables tab;
-    SB_TRY(ensure_packed_tables(&tab));
-    SB_TRY(ensure_item_query(n_trips));
-    k_fill_pair_query<<<(unsigned)(q_end - q_begin), 128, 0, c.stream>>>(d_desc, q_begin, trip_first, g_item_query2, 3);
-    c.launches += 1;
-    return SB_DISPATCH_MATCH(launch_triple_typed, image, tmpl, d_parts, part_first, d_desc, trip_first, n_trips, tab, d_keys, d_curve);
-}
-
-int launch_block_spectra_quad(const sb_stream* s, int64_t k_first, int64_t rows, float2* out, int fmt) {
-    if (fmt)
-        return s->dtype == SB_U8 ? launch_forward_quad_typed<uint8_t, 0, 1>(s, nullptr, 0, 0, k_first, rows, out)
-                                 : launch_forward_quad_typed<float, 0, 1>(s, nullptr, 0, 0, k_first, rows, out);
-    return s->dtype == SB_U8 ? launch_forward_quad_typed<uint8_t, 0, 0>(s, nullptr, 0, 0, k_first, rows, out)
-                             : launch_forward_quad_typed<float, 0, 0>(s, nullptr, 0, 0, k_first, rows, out);
+int launch_block_spectra_quad(const sb_stream* s, int64_t k_first, int64_t rows, float2* out) {
+    return s->dtype == SB_U8 ? launch_forward_quad_typed<uint8_t, 0>(s, nullptr, 0, 0, k_first, rows, out)
+                             : launch_forward_quad_typed<float, 0>(s, nullptr, 0, 0, k_first, rows, out);
 }
 
 int launch_part_spectra_quad(const sb_stream* tmpl, const QueryDesc* d_desc, int q_begin, int q_end,
-                             int64_t part_first, int64_t rows, float2* out, int fmt) {
-    if (fmt)
-        return tmpl->dtype == SB_U8 ? launch_forward_quad_typed<uint8_t, 1, 1>(tmpl, d_desc, q_begin, q_end, part_first, rows, out)
-                                    : launch_forward_quad_typed<float, 1, 1>(tmpl, d_desc, q_begin, q_end, part_first, rows, out);
-    return tmpl->dtype == SB_U8 ? launch_forward_quad_typed<uint8_t, 1, 0>(tmpl, d_desc, q_begin, q_end, part_first, rows, out)
-                                : launch_forward_quad_typed<float, 1, 0>(tmpl, d_desc, q_begin, q_end, part_first, rows, out);
+                             int64_t part_first, int64_t rows, float2* out) {
+    return tmpl->dtype == SB_U8 ? launch_forward_quad_typed<uint8_t, 1>(tmpl, d_desc, q_begin, q_end, part_first, rows, out)
+                                : launch_forward_quad_typed<float, 1>(tmpl, d_desc, q_begin, q_end, part_first, rows, out);
 }
 
 void packed_release_tables() {

@@ -41,7 +41,7 @@ struct QueryDesc {
     int64_t itemBase;  // first item of this query in the batch-wide item list
     int64_t partBase;  // first partition spectrum of this query
     int64_t curveOff;  // where this query's curve starts in the curve buffer (curve mode only)
-    int64_t groupBase; // first multiply group of this query in the batch: MAC_GROUP consecutive lag blocks (blocked class), pairs -- engine 6: triples -- of lag blocks (direct class)
+    int64_t groupBase; // first multiply group of this query in the batch: MAC_GROUP consecutive lag blocks (blocked class), pairs of lag blocks (direct class)
     int32_t P;         // ceil(n / H), H = hop = partition length
     int32_t k0;        // lag0 / LB, LB = lags per item
     int32_t nk;        // number of lag blocks touched
@@ -57,10 +57,9 @@ struct Ctx {
     cudaStream_t stream = nullptr;
     int B = 16384;                 // lag-block size (samples); FFT size is 2B
     int chunk_items = 1024;        // items per MAC/C2R/normalise chunk (cuFFT engine)
-    int engine = 2;                // 2: packed fused kernels (sb_fused2.cu, B = 16384; default), 3: persistent warp-specialised variant, 4 / 5: always / never pairs of lag blocks, 6: triples (opt-in), 1: fused lag-block kernel (sb_fused.cu), 0: cuFFT pipeline
+    int engine = 2;                // 2: packed fused kernels (sb_fused2.cu, B = 16384; default), 4 / 5: always / never pairs of lag blocks, 1: fused lag-block kernel (sb_fused.cu), 0: cuFFT pipeline
     int premac_mode = 0;           // 0: register-blocked multiply kernel for queries whose template spans >= 12 partitions, 1: never, 2: always
-    int epilogue = 1;              // screening loop of the packed kernels on uint8 streams: 1 = first version (default), 2 = trimmed (sb_set_epilogue)
-    int spectra_fmt = 0;           // quad rows of the packed kernels: 0 = float32 (default), 1 = 16-bit block floating point (sb_set_spectra)
+    int epilogue = 2;              // screening loop of the packed kernels on uint8 streams: 2 = trimmed (default), 1 = first version (sb_set_epilogue)
     int hop_mode = 1;              // fused engine geometry: 1 = hop B (50 % of each FFT valid, default), 2 = hop B/2 (75 %), 0 = pick per batch
     int64_t max_parts = 16384;     // template partition spectra kept per super-chunk
 
@@ -107,26 +106,16 @@ void pool_release_all();
 
 // engine 2 (sb_fused2.cu): spectrum rows in the quad layout, kQuadRowF2 float2 per row (128-byte aligned)
 constexpr int kQuadRowF2 = 16400;
-// the same rows as 16-bit block floating point (sb_set_spectra(1)): 4097 quads of 8 x int16 + 513 x 4 float32 scales,
-// padded to a multiple of 128 bytes
-constexpr int kQuad16RowF2 = 9232;
 bool packed_supports(int B);
 int launch_match_packed(const sb_stream* image, const sb_stream* tmpl, const float2* d_parts, int64_t part_first,
                         const QueryDesc* d_desc, int q_begin, int q_end, int64_t item_first, int64_t n_items,
                         unsigned long long* d_keys, float* d_curve);
-int launch_match_ws(const sb_stream* image, const sb_stream* tmpl, const float2* d_parts, int64_t part_first,
-                    const QueryDesc* d_desc, int q_begin, int q_end, int64_t item_first, int64_t n_items,
-                    unsigned long long* d_keys, float* d_curve);
 int launch_match_pair(const sb_stream* image, const sb_stream* tmpl, const float2* d_parts, int64_t part_first,
                       const QueryDesc* d_desc, int q_begin, int q_end, int64_t pair_first, int64_t n_pairs,
                       unsigned long long* d_keys, float* d_curve);
-int launch_match_triple(const sb_stream* image, const sb_stream* tmpl, const float2* d_parts, int64_t part_first,
-                        const QueryDesc* d_desc, int q_begin, int q_end, int64_t trip_first, int64_t n_trips,
-                        unsigned long long* d_keys, float* d_curve);
-// fmt: row format written (0 = float32 rows of kQuadRowF2, 1 = 16-bit block floating point rows of kQuad16RowF2)
-int launch_block_spectra_quad(const sb_stream* s, int64_t k_first, int64_t rows, float2* out, int fmt);
+int launch_block_spectra_quad(const sb_stream* s, int64_t k_first, int64_t rows, float2* out);
 int launch_part_spectra_quad(const sb_stream* tmpl, const QueryDesc* d_desc, int q_begin, int q_end,
-                             int64_t part_first, int64_t rows, float2* out, int fmt);
+                             int64_t part_first, int64_t rows, float2* out);
 void packed_release_tables();
 
 bool fused_supports(int B);
@@ -158,5 +147,4 @@ struct sb_stream {
     // the same rows in the quad layout of the packed kernels (B = 16384, hop B): [nblkq][kQuadRowF2] float2
     float2* d_specq = nullptr;
     int64_t nblkq = 0;
-    int specqFmt = 0;             // row format of d_specq: 0 = float32 (kQuadRowF2), 1 = 16-bit block floating point (kQuad16RowF2)
 };

@@ -457,8 +457,7 @@ int run_batch(const sb_stream* image_c, const sb_stream* tmpl, int64_t count,
     const bool use_packed = c.engine >= 2 && packed_supports(B) && hd == 1;
     const int nb = B + 1;                                    // float2 per classic spectrum row
     int64_t n_direct = 0, total_items = 0, total_parts = 0, total_groups = 0, maxp = 0;
-    const bool use_triples = use_packed && c.engine == 6;     // lag blocks per CTA of the direct class: 3, else 2 or 1
-    SB_TRY(plan_batch(image, tmpl, count, toff, tlen, lag0, nlags, hd, use_fused && hd == 1, use_triples ? 3 : 2, &n_direct,
+    SB_TRY(plan_batch(image, tmpl, count, toff, tlen, lag0, nlags, hd, use_fused && hd == 1, 2, &n_direct,
                       &total_items, &total_parts, &total_groups, &maxp));
     // Packed kernels: one CTA per lag block, or one per pair of consecutive lag blocks of a query (shared template
     // rows, 2P+1 row reads instead of 4P, second product spectrum parked in tensor memory).  Both give bit-identical
@@ -470,8 +469,6 @@ int run_batch(const sb_stream* image_c, const sb_stream* tmpl, int64_t count,
         for (int64_t q = 0; q < n_direct; ++q) { rows += (double)c.h_desc[q].nk * c.h_desc[q].P; blocks += (double)c.h_desc[q].nk; }
         use_pairs = rows >= 1.5 * blocks;
     }
-    if (use_packed && c.engine == 3 && c.spectra_fmt != 0)
-        SB_FAIL(SB_EINVAL, "engine 3 (warp-specialised kernel) reads float32 spectrum rows only: sb_set_spectra(0) or another engine");
     if (use_packed && n_direct > 0) SB_TRY(ensure_spectra_quad(image));
     if (!use_packed || n_direct < count) SB_TRY(ensure_spectra(image, hd));
 
@@ -482,8 +479,8 @@ int run_batch(const sb_stream* image_c, const sb_stream* tmpl, int64_t count,
     SB_CUDA(cudaMemsetAsync(c.d_keys, 0xff, sizeof(unsigned long long) * count, c.stream));
 
     const int64_t parts_cap_want = std::max<int64_t>(std::min<int64_t>(total_parts, c.max_parts), maxp);
-    // float2 per template partition row: quad layout (float32 or 16-bit block floating point) or classic
-    const int64_t part_row_f2 = use_packed ? (c.spectra_fmt ? kQuad16RowF2 : kQuadRowF2) : nb;
+    // float2 per template partition row: quad layout or classic
+    const int64_t part_row_f2 = use_packed ? kQuadRowF2 : nb;
     SB_TRY(grow(&c.d_parts, &c.parts_cap, parts_cap_want * part_row_f2));
     const int64_t chunk = std::min<int64_t>(c.chunk_items, total_items);
     if (!use_fused) SB_TRY(grow(&c.d_items, &c.items_cap, chunk * nb));
@@ -508,7 +505,7 @@ int run_batch(const sb_stream* image_c, const sb_stream* tmpl, int64_t count,
         const int64_t sub = 4096;
         if (use_packed && !premac) {
             ProfScope ps("part_spectra");
-            SB_TRY(launch_part_spectra_quad(tmpl, c.d_desc, (int)qb, (int)qe, part_first, np, c.d_parts, c.spectra_fmt));
+            SB_TRY(launch_part_spectra_quad(tmpl, c.d_desc, (int)qb, (int)qe, part_first, np, c.d_parts));
         } else if (use_fused) {                      // hand-written gather + forward FFT, one launch
             ProfScope ps("part_spectra");
             SB_TRY(launch_part_spectra(tmpl, hd, c.d_desc, (int)qb, (int)qe, part_first, np, c.d_parts));
@@ -537,18 +534,11 @@ int run_batch(const sb_stream* image_c, const sb_stream* tmpl, int64_t count,
         const int64_t item_hi = (qe < count) ? c.h_desc[qe].itemBase : total_items;
         if (use_packed && !premac) {
             ProfScope ps("match_fused");
-            if (use_triples) {
-                const int64_t g0 = c.h_desc[qb].groupBase;
-                const int64_t g1 = (qe < count) ? c.h_desc[qe].groupBase : total_groups;
-                SB_TRY(launch_match_triple(image, tmpl, c.d_parts, part_first, c.d_desc, (int)qb, (int)qe, g0, g1 - g0, c.d_keys, d_curve));
-            } else if (use_pairs) {
+            if (use_pairs) {
                 const int64_t g0 = c.h_desc[qb].groupBase;
                 const int64_t g1 = (qe < count) ? c.h_desc[qe].groupBase : total_groups;
                 SB_TRY(launch_match_pair(image, tmpl, c.d_parts, part_first, c.d_desc, (int)qb, (int)qe, g0, g1 - g0, c.d_keys, d_curve));
-            } else if (c.engine == 3)
-                SB_TRY(launch_match_ws(image, tmpl, c.d_parts, part_first, c.d_desc, (int)qb, (int)qe,
-                                       item_lo, item_hi - item_lo, c.d_keys, d_curve));
-            else
+            } else
                 SB_TRY(launch_match_packed(image, tmpl, c.d_parts, part_first, c.d_desc, (int)qb, (int)qe,
                                            item_lo, item_hi - item_lo, c.d_keys, d_curve));
         } else if (use_fused && !premac) {

@@ -213,17 +213,14 @@ int stream_finish_public(sb_stream* s) { return stream_finish(s); }
 int ensure_spectra_quad(sb_stream* s) {
     Ctx& c = ctx();
     if (!packed_supports(c.B)) SB_FAIL(SB_EINVAL, "internal: quad-layout spectra need a lag block of 16384");
-    const int fmt = c.spectra_fmt;                   // 0: float32 rows (default), 1: 16-bit block floating point
-    if (s->d_specq && s->specqFmt == fmt) return SB_OK;
-    if (s->d_specq) { pool_free(s->d_specq); s->d_specq = nullptr; }      // built in the other format: rebuild
+    if (s->d_specq) return SB_OK;
     const int64_t nblk = (s->n + c.B - 1) / c.B;
-    SB_TRY(pool_alloc((void**)&s->d_specq, sizeof(float2) * (size_t)nblk * (fmt ? kQuad16RowF2 : kQuadRowF2)));
+    SB_TRY(pool_alloc((void**)&s->d_specq, sizeof(float2) * (size_t)nblk * kQuadRowF2));
     {
         ProfScope ps("block_spectra");
-        SB_TRY(launch_block_spectra_quad(s, 0, nblk, s->d_specq, fmt));
+        SB_TRY(launch_block_spectra_quad(s, 0, nblk, s->d_specq));
     }
     s->nblkq = nblk;
-    s->specqFmt = fmt;
     return SB_OK;
 }
 

@@ -82,14 +82,13 @@ void run_cta(const std::function<void(int)>& body) {
 extern "C" {
 
 int emu_table_floats(void) { size_t off[4]; return (int)packed_table_values(off).size(); }
-int emu_smem_bytes(void) { return (int)packed_smem_bytes() + 16; }
+int emu_smem_bytes(void) { return (int)packed_smem_bytes(2) + 16; }
 int emu_query_desc_bytes(void) { return (int)sizeof(sb::QueryDesc); }
-int emu_quad_row_floats(int fmt) { return (fmt ? QROW16 : QROW) * 4; }
+int emu_quad_row_floats(void) { return QROW * 4; }
 
-// kernel: 0 = k_match_packed (one CTA per lag block), 1 = k_match_pair, 2 = k_match_triple; epi: 1 | 2;
-// is_u8: sample type of img; fmt: row format of That / Xhat (0 float32, 1 16-bit block floating point).  Runs CTAs
-// [0, n_ctas) one after the other.  Returns 0, or the number of emulation errors (messages on stderr).
-int emu_run(int kernel, int epi, int is_u8, int fmt, const float* That, int64_t part_first, const float* Xhat, int64_t nblk,
+// kernel: 0 = k_match_packed (one CTA per lag block), 1 = k_match_pair; epi: 1 | 2; is_u8: sample type of img.
+// Runs CTAs [0, n_ctas) one after the other.  Returns 0, or the number of emulation errors (messages on stderr).
+int emu_run(int kernel, int epi, int is_u8, const float* That, int64_t part_first, const float* Xhat, int64_t nblk,
             const void* img, int64_t img_n, const double* ipfx, const double* tpfx, const void* desc,
             const int* cta_query, int64_t first, int n_ctas, unsigned long long* keys, float* curve_out) {
     static size_t off[4];
@@ -101,7 +100,7 @@ int emu_run(int kernel, int epi, int is_u8, int fmt, const float* That, int64_t 
     const double2* tp = reinterpret_cast<const double2*>(tpfx);
     const sb::QueryDesc* d = static_cast<const sb::QueryDesc*>(desc);
     int n_err = 0;
-    const int grid = kernel == 2 ? (n_ctas < 3 ? n_ctas : 3) : n_ctas;      // the triple kernel is persistent: 3 CTAs share the triples
+    const int grid = n_ctas;
     gridDim = dim3((unsigned)grid, 1, 1);
     for (int b = 0; b < grid; ++b) {
         emu::Cta cta;
@@ -111,13 +110,11 @@ int emu_run(int kernel, int epi, int is_u8, int fmt, const float* That, int64_t 
         auto body = [&](int t) {
             blockIdx = {(unsigned)b, 0, 0};       // threadIdx and the lane / warp numbers are set by run_cta
 #define SB_EMU_ARGS(S) T4, part_first, X4, nblk, static_cast<const S*>(img), img_n, ip, tp, d, cta_query, first
-#define SB_EMU_CALL(K, S, E, ...) do { if (fmt) K<S, E, 1>(SB_EMU_ARGS(S), ##__VA_ARGS__, tab, keys, curve_out); \
-                                       else K<S, E, 0>(SB_EMU_ARGS(S), ##__VA_ARGS__, tab, keys, curve_out); } while (0)
+#define SB_EMU_CALL(K, S, E, ...) K<S, E>(SB_EMU_ARGS(S), ##__VA_ARGS__, tab, keys, curve_out)
 #define SB_EMU_KERNEL(K, ...) do { if (!is_u8) SB_EMU_CALL(K, float, 1, ##__VA_ARGS__); else if (epi == 2) SB_EMU_CALL(K, uint8_t, 2, ##__VA_ARGS__); \
                                    else SB_EMU_CALL(K, uint8_t, 1, ##__VA_ARGS__); } while (0)
             if (kernel == 0) SB_EMU_KERNEL(k_match_packed);
-            else if (kernel == 1) SB_EMU_KERNEL(k_match_pair);
-            else SB_EMU_KERNEL(k_match_triple, (int64_t)n_ctas);       // persistent: n_ctas triples over `grid` CTAs
+            else SB_EMU_KERNEL(k_match_pair);
         };
         emu::run_cta(body);
         for (const auto& e : cta.errors) { std::fprintf(stderr, "[emu] CTA %d: %s\n", b, e.c_str()); ++n_err; }
@@ -126,10 +123,10 @@ int emu_run(int kernel, int epi, int is_u8, int fmt, const float* That, int64_t 
     return n_err;
 }
 
-// Block spectra of a stream (k_forward_quad, MODE 0) in either row format: rows [row_first, row_first + rows) into
-// `out` (rows * emu_quad_row_floats(fmt) floats).  The twiddle tables are the ones sb_fused.cu's ensure_tables<14>
+// Block spectra of a stream (k_forward_quad, MODE 0): rows [row_first, row_first + rows) into
+// `out` (rows * emu_quad_row_floats() floats).  The twiddle tables are the ones sb_fused.cu's ensure_tables<14>
 // builds.
-int emu_forward_blocks(int is_u8, int fmt, const void* src, int64_t src_n, const double* pfx, int64_t row_first, int rows, float* out) {
+int emu_forward_blocks(int is_u8, const void* src, int64_t src_n, const double* pfx, int64_t row_first, int rows, float* out) {
     typedef Cfg<14> C;
     static std::vector<float2> h;
     static FusedTables tab;
@@ -161,10 +158,8 @@ int emu_forward_blocks(int is_u8, int fmt, const void* src, int64_t src_n, const
         std::memset(smem_raw, 0xCD, sizeof(smem_raw));
         auto body = [&](int t) {
             blockIdx = {(unsigned)b, 0, 0};       // threadIdx and the lane / warp numbers are set by run_cta
-            if (is_u8) { if (fmt) k_forward_quad<uint8_t, 0, 1>(static_cast<const uint8_t*>(src), src_n, pf, nullptr, 0, 0, row_first, tab, o4);
-                         else     k_forward_quad<uint8_t, 0, 0>(static_cast<const uint8_t*>(src), src_n, pf, nullptr, 0, 0, row_first, tab, o4); }
-            else       { if (fmt) k_forward_quad<float, 0, 1>(static_cast<const float*>(src), src_n, pf, nullptr, 0, 0, row_first, tab, o4);
-                         else     k_forward_quad<float, 0, 0>(static_cast<const float*>(src), src_n, pf, nullptr, 0, 0, row_first, tab, o4); }
+            if (is_u8) k_forward_quad<uint8_t, 0>(static_cast<const uint8_t*>(src), src_n, pf, nullptr, 0, 0, row_first, tab, o4);
+            else       k_forward_quad<float, 0>(static_cast<const float*>(src), src_n, pf, nullptr, 0, 0, row_first, tab, o4);
         };
         emu::run_cta(body);
         for (const auto& e : cta.errors) { std::fprintf(stderr, "[emu] forward CTA %d: %s\n", b, e.c_str()); ++n_err; }

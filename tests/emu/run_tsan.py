@@ -4,11 +4,11 @@
     python tests/emu/run_tsan.py
 
 Builds tests/emu/emu_driver.cpp with -fsanitize=thread and runs every kernel (one CTA per lag block / pair /
-triple) with both screening loops, with and without the debug curve, on the cases of
+pair) with both screening loops, with and without the debug curve, on the cases of
 tests/test_kernel_emulation.py.  Built with -DSB_EMU_THREADS: one OS thread stands for one CUDA thread (the default build runs the lanes of a warp as
 fibers on one OS thread, which ThreadSanitizer cannot follow) and std::barrier for bar.sync, so a
 shared-memory access that is not ordered by the kernel's own barriers / mbarrier waits shows up as a data race:
-this checks the PLACEMENT of the barriers (re-use of the FFT buffer between the items of a pair / triple,
+this checks the PLACEMENT of the barriers (re-use of the FFT buffer between the items of a pair,
 re-staging of the sample windows, re-use of the reduction scratch), not the GPU memory model.  Exit code 0 and
 "0 races" expected.  Re-executes itself under LD_PRELOAD=libtsan.so (the interpreter is not instrumented)."""
 import ctypes
@@ -53,7 +53,7 @@ def main():
     case = T.Case(lib, img, src, [(30000, 20000, B + 300, 4 * B - 17000), (1000, 5000, 100, 20000),
                                   (8000, 40000, n_img - 40000 - 30000, 30001)], np.uint8)
     ref = None
-    for kernel in (0, 1, 2):
+    for kernel in (0, 1):
         for epi in (1, 2):
             for curves in (False, True):
                 d, i, _ = case.run(kernel, epi, curves)
@@ -62,7 +62,7 @@ def main():
                 print('kernel %d epilogue %d curves %d ok' % (kernel, epi, curves), flush=True)
     img32 = (T.programme(4 * B - 3000, 3).astype(np.float32) / 255.0).astype(np.float32)
     case32 = T.Case(lib, img32, np.roll(img32, -300).copy(), [(20000, 18000, 5, 2 * B + 5000)], np.float32)
-    for kernel in (0, 1, 2):
+    for kernel in (0, 1):
         d, i, _ = case32.run(kernel, 1, False)
         assert i[0] == 20295
         print('float32 kernel %d ok' % kernel, flush=True)

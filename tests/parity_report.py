@@ -21,14 +21,11 @@ print('%-8s %-7s %-8s %9s %12s %12s %12s %8s' % ('type', 'event', 'window', 'lag
 for stype in ('uint8', 'float32'):
     src = WavStream.from_pcm(src_pcm, 12000, sample_type=stype)
     dst = WavStream.from_pcm(dst_pcm, 12000, sample_type=stype)
-    # (engine, screening loop); SB_PARITY_EXPERIMENTAL=1 adds the opt-in variants (engine 6, epilogue 2)
-    variants = [(5, 1, 0), (4, 1, 0), (3, 1, 0), (1, 1, 0), (0, 1, 0)]
-    if os.environ.get('SB_PARITY_EXPERIMENTAL') == '1':
-        variants = [(6, 2, 1), (5, 1, 1), (6, 2, 0), (6, 1, 0), (4, 2, 0), (5, 2, 0)] + variants
-    for engine, epilogue, spectra in variants:
+    # (engine, body variant of the packed kernels)
+    variants = [(4, 2), (5, 2), (4, 1), (5, 1), (1, 1), (0, 1)]
+    for engine, epilogue in variants:
         _native.check(lib.sb_set_engine(engine))
         _native.check(lib.sb_set_epilogue(epilogue))
-        _native.check(lib.sb_set_spectra(spectra))
         for ev_len, win in ((0.5, 10.0), (1.0, 10.0), (3.0, 10.0), (3.0, 60.0), (10.0, 10.0), (30.0, 10.0), (30.0, 60.0)):
             a = 100.0
             toff, tlen, lag0, nlags, _ = dst.plan_queries(src, [a], [a + ev_len], [a], [win])
@@ -41,8 +38,7 @@ for stype in ('uint8', 'float32'):
             print('%-8s %-7s %-8s %9d %12.3e %12.3e %12.3e %8s  engine=%s' % (
                 stype, '%gs' % ev_len, '+-%gs' % win, nlags, np.abs(gpu - ref).max(), np.abs(gpu - f64).max(),
                 np.abs(ref - f64).max(), 'same' if int(gpu.argmin()) == int(ref.argmin()) else 'DIFF(%d)' % (int(gpu.argmin()) - int(ref.argmin())),
-                {0: 'cufft', 1: 'fused', 2: 'packed', 3: 'packed_ws', 4: 'packed_pair', 5: 'packed_single', 6: 'packed_triple'}[engine]
-                + ('/epilogue2' if epilogue == 2 else '') + ('/bfp16' if spectra else '')))
+                {0: 'cufft', 1: 'fused', 2: 'packed', 4: 'packed_pair', 5: 'packed_single'}[engine]
+                + ('/body1' if epilogue == 1 and engine >= 2 else '')))
     _native.check(lib.sb_set_engine(2))
-    _native.check(lib.sb_set_epilogue(1))
-    _native.check(lib.sb_set_spectra(0))
+    _native.check(lib.sb_set_epilogue(2))
