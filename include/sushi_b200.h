@@ -120,6 +120,8 @@ int sb_pinned_free(void* p);
 int sb_device_alloc(int64_t bytes, void** out);
 int sb_device_free(void* p);
 int sb_copy_to_host(void* host_dst, const void* dev_src, int64_t bytes);   /* ordered on the library stream, blocking */
+int sb_copy_to_device(void* dev_dst, const void* host_src, int64_t bytes); /* ordered on the library stream, blocking */
+int sb_copy_on_device(void* dev_dst, const void* dev_src, int64_t bytes);  /* enqueued on the library stream */
 
 /* ---- resident streams:  WavStream.data  (wav.py:119,140-156) ----------- */
 

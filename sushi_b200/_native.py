@@ -44,6 +44,8 @@ PROTOTYPES = {
     'sb_device_alloc': (ctypes.c_int, [c_i64, ctypes.POINTER(c_vp)]),
     'sb_device_free': (ctypes.c_int, [c_vp]),
     'sb_copy_to_host': (ctypes.c_int, [c_vp, c_vp, c_i64]),
+    'sb_copy_to_device': (ctypes.c_int, [c_vp, c_vp, c_i64]),
+    'sb_copy_on_device': (ctypes.c_int, [c_vp, c_vp, c_i64]),
     'sb_stream_device_ptr': (c_vp, [c_vp]),
     'sb_stream_create': (ctypes.c_int, [c_vp, c_i64, ctypes.c_int, ctypes.POINTER(c_vp)]),
     'sb_stream_create_device': (ctypes.c_int, [c_vp, c_i64, ctypes.c_int, ctypes.POINTER(c_vp)]),

@@ -272,6 +272,22 @@ int sb_copy_to_host(void* host_dst, const void* dev_src, int64_t bytes) {
     return SB_OK;
 }
 
+int sb_copy_to_device(void* dev_dst, const void* host_src, int64_t bytes) {
+    Ctx& c = ctx();
+    if (!c.inited) SB_FAIL(SB_ESTATE, "sb_copy_to_device: library not initialised");
+    if (!dev_dst || !host_src || bytes < 0) SB_FAIL(SB_EINVAL, "sb_copy_to_device: bad argument");
+    SB_CUDA(cudaMemcpyAsync(dev_dst, host_src, (size_t)bytes, cudaMemcpyHostToDevice, c.stream));
+    SB_CUDA(cudaStreamSynchronize(c.stream));      // the caller may reuse the host buffer
+    return SB_OK;
+}
+int sb_copy_on_device(void* dev_dst, const void* dev_src, int64_t bytes) {
+    Ctx& c = ctx();
+    if (!c.inited) SB_FAIL(SB_ESTATE, "sb_copy_on_device: library not initialised");
+    if (!dev_dst || !dev_src || bytes < 0) SB_FAIL(SB_EINVAL, "sb_copy_on_device: bad argument");
+    SB_CUDA(cudaMemcpyAsync(dev_dst, dev_src, (size_t)bytes, cudaMemcpyDeviceToDevice, c.stream));
+    return SB_OK;
+}
+
 int sb_timer_start(void) {
     Ctx& c = ctx();
     if (!c.inited) SB_FAIL(SB_ESTATE, "sb_timer_start: library not initialised");

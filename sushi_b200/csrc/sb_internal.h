@@ -136,6 +136,10 @@ void drop_plans();
 struct sb_stream {
     int64_t n = 0;
     int dtype = SB_U8;
+    // streams produced by sb_load_pcm: channel count of the PCM they came from and the coarse value histogram the
+    // decode kernel accumulated (sb_normalise selects the medians from it)
+    int pcm_channels = 0;
+    unsigned long long* d_loadhist = nullptr;
     void* d_raw = nullptr;        // n samples (u8 or f32)
     double2* d_pfx = nullptr;     // [n+1] running sums: .x = sum of samples, .y = sum of squares (exact for u8)
     // block spectra for lag-block size specB: [nblk][specB+1] complex64
@@ -147,4 +151,5 @@ struct sb_stream {
     // the same rows in the quad layout of the packed kernels (B = 16384, hop B): [nblkq][kQuadRowF2] float2
     float2* d_specq = nullptr;
     int64_t nblkq = 0;
+    int64_t specq_lo = 0, specq_hi = 0;   // rows [specq_lo, specq_hi) of d_specq are built (on demand, per batch)
 };

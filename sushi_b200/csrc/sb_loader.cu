@@ -5,8 +5,9 @@
 // Everything is float32 with explicitly rounded operations (no FMA contraction), in the order the
 // reference applies them, so the result is bit-identical to the NumPy/OpenCV loader.
 #include "sb_internal.h"
-#include <vector>
+#include <cmath>
 #include <cstring>
+#include <vector>
 
 using namespace sb;
 
@@ -29,169 +30,255 @@ struct ResampleGeom {
     int64_t written;       // samples produced by the chunk loop
 };
 
-__device__ __forceinline__ float decode_frame(const unsigned char* __restrict__ pcm, int64_t frame,
-                                              int channels, int width) {
+// One frame -> the integer numerator of the reference's float32 sample: int16 values (int24: bytes 1,2,
+// wav.py:71-74) summed over the channels.  The reference sums float32 values left to right (wav.py:88-89);
+// every partial sum is an integer below 2^24, hence exact, so the float32 sum IS (float)acc.
+__device__ __forceinline__ int decode_acc(const unsigned char* __restrict__ pcm, int64_t frame, int channels, int width) {
     const unsigned char* p = pcm + frame * (int64_t)channels * width;
-    float acc = 0.f;
-    for (int c = 0; c < channels; ++c) {
-        const unsigned char* q = p + c * width + (width == 3 ? 1 : 0);     // int24: bytes 1,2 (wav.py:71-74)
-        const short v = (short)((unsigned short)q[0] | ((unsigned short)q[1] << 8));
-        acc = c == 0 ? (float)v : __fadd_rn(acc, (float)v);                // left-to-right float32 sum (wav.py:88-89)
-    }
-    return channels == 1 ? acc : __fdiv_rn(acc, (float)channels);          // wav.py:90
-}
-
-// content sample o (o in [0, written)) of the resampled stream
-__device__ __forceinline__ float content_sample(const unsigned char* __restrict__ pcm, const ResampleGeom g,
-                                                int64_t o, int channels, int width) {
-    int64_t c; int x, len; double ifx;
-    if (g.out_full > 0 && o < g.nfull * (int64_t)g.out_full) {
-        c = o / g.out_full; x = (int)(o - c * g.out_full); len = g.framerate; ifx = g.ifx_full;
+    int acc = 0;
+    if (width == 2) {
+        const short* q = reinterpret_cast<const short*>(p);            // frames are 2-byte aligned
+        for (int c = 0; c < channels; ++c) acc += (int)q[c];
     } else {
-        c = g.nfull; x = (int)(o - g.nfull * (int64_t)g.out_full); len = g.len_last; ifx = g.ifx_last;
-    }
-    int sx = x;
-    if (g.resample) {
-        sx = (int)floor((double)x * ifx);                                    // OpenCV resizeNN: cvFloor(x * ifx)
-        if (sx > len - 1) sx = len - 1;
-    }
-    return decode_frame(pcm, c * (int64_t)g.framerate + sx, channels, width);
-}
-
-__global__ void __launch_bounds__(256)
-k_decode_resample_pad(const unsigned char* __restrict__ pcm, ResampleGeom g, int channels, int width,
-                      float* __restrict__ out) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= g.total) return;
-    const int64_t tail0 = g.total - g.padding;          // first sample of the tail padding
-    float v;
-    if (i < g.padding) {                                 // head: repeat the first content sample (wav.py:140)
-        v = g.written > 0 ? content_sample(pcm, g, 0, channels, width) : 0.f;
-    } else if (i < tail0) {
-        const int64_t o = i - g.padding;
-        v = o < g.written ? content_sample(pcm, g, o, channels, width) : 0.f;   // gap: np.empty -> 0
-    } else {                                             // tail: repeat data[-padding-1] (wav.py:141)
-        const int64_t o = tail0 - 1 - g.padding;
-        v = (o >= 0 && o < g.written) ? content_sample(pcm, g, o, channels, width) : 0.f;
-    }
-    out[i] = v;
-}
-
-// ---- medians by radix select ----------------------------------------------------------------
-__device__ __forceinline__ unsigned int float_key(float f) {      // order-preserving map float -> uint
-    const unsigned int b = __float_as_uint(f);
-    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
-}
-float key_float(unsigned int k) {                                  // host-side inverse of float_key
-    const unsigned int b = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
-    float f; memcpy(&f, &b, sizeof(f)); return f;
-}
-// subset 0: x >= 0, subset 1: x <= 0  (both contain the zeros, wav.py:145-146)
-__device__ __forceinline__ bool in_subset(float f, int subset) { return subset == 0 ? f >= 0.f : f <= 0.f; }
-
-// histogram of byte `shift/8` of the keys of subset members whose higher bytes equal `prefix`
-__global__ void __launch_bounds__(256)
-k_select_hist(const float* __restrict__ x, int64_t n, int subset, unsigned int prefix, unsigned int mask, int shift,
-              unsigned long long* __restrict__ hist) {
-    __shared__ unsigned int s_h[256];
-    s_h[threadIdx.x] = 0;
-    __syncthreads();
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const float f = x[i];
-        if (in_subset(f, subset)) {
-            const unsigned int k = float_key(f);
-            if ((k & mask) == prefix) atomicAdd(&s_h[(k >> shift) & 0xffu], 1u);
+        for (int c = 0; c < channels; ++c) {
+            const unsigned char* q = p + c * 3 + 1;
+            acc += (int)(short)((unsigned short)q[0] | ((unsigned short)q[1] << 8));
         }
     }
-    __syncthreads();
-    if (s_h[threadIdx.x]) atomicAdd(hist + threadIdx.x, (unsigned long long)s_h[threadIdx.x]);
+    return acc;
+}
+__device__ __forceinline__ float acc_value(int acc, int channels) {
+    return channels == 1 ? (float)acc : __fdiv_rn((float)acc, (float)channels);      // wav.py:90
 }
 
-// smallest key strictly greater than `key` among subset members
+// ---- medians without sorting ---------------------------------------------------------------------
+// np.median over {x >= 0} and over {x <= 0} of the PADDED array (wav.py:145-146) needs two order statistics
+// each.  Every sample is (float)acc / channels with an integer acc, |acc| <= 32768 * channels, so selection can
+// run on integers: a coarse histogram (bins of 32 in sample value = 32 * channels in acc; 2048 bins) is
+// accumulated by the decode kernel itself while it writes the samples, and ONE further pass over the float32
+// data histograms acc inside the (at most four) coarse bins that hold the wanted ranks.  Two reads of the
+// float32 stream in all -- that pass and the normalisation -- where a radix select on float keys took ten.
+constexpr int kCoarseBins = 2048, kCoarseZero = 1024, kCoarseWidth = 32, kMaxChannels = 64;
+__device__ __forceinline__ int coarse_bin(float v) {
+    int b = (int)floorf(v * (1.0f / kCoarseWidth)) + kCoarseZero;       // exact: division by a power of two
+    return b < 0 ? 0 : (b > kCoarseBins - 1 ? kCoarseBins - 1 : b);
+}
+
+// Work items: [0, n_chunk_items) = (chunk, slab of 1024 output samples); then the head and the tail padding in
+// slabs of 1024.  A CTA takes items round robin; its coarse histogram lives in shared memory.
+struct LoadItems { int per_full; int per_last; int64_t n_content; int64_t n_head; int64_t n_tail; };
+
 __global__ void __launch_bounds__(256)
-k_select_next(const float* __restrict__ x, int64_t n, int subset, unsigned int key, unsigned int* __restrict__ out) {
-    unsigned int best = 0xffffffffu;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const float f = x[i];
-        if (in_subset(f, subset)) {
-            const unsigned int k = float_key(f);
-            if (k > key && k < best) best = k;
-        }
-    }
+k_decode_resample_pad(const unsigned char* __restrict__ pcm, ResampleGeom g, LoadItems li, int channels, int width,
+                      float* __restrict__ out, unsigned long long* __restrict__ hist) {
+    __shared__ unsigned s_h[kCoarseBins + 1];                            // [kCoarseBins] counts exact zeros
+    for (int i = threadIdx.x; i <= kCoarseBins; i += blockDim.x) s_h[i] = 0;
+    __syncthreads();
+    const int64_t n_items = li.n_content + li.n_head + li.n_tail;
+    const int64_t tail0 = g.total - g.padding;
+    auto count = [&](float v, int acc) { atomicAdd(&s_h[coarse_bin(v)], 1u); if (acc == 0) atomicAdd(&s_h[kCoarseBins], 1u); };
+    for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+        if (item < li.n_content) {
+            int64_t c; int slab, len, outn; double ifx;
+            if (item < g.nfull * (int64_t)li.per_full) { c = item / li.per_full; slab = (int)(item - c * li.per_full); len = g.framerate; outn = g.out_full; ifx = g.ifx_full; }
+            else { c = g.nfull; slab = (int)(item - g.nfull * (int64_t)li.per_full); len = g.len_last; outn = g.out_last; ifx = g.ifx_last; }
+            const int64_t frame0 = c * (int64_t)g.framerate;
+            const int64_t o0 = g.padding + c * (int64_t)g.out_full;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { unsigned int t = __shfl_xor_sync(0xffffffffu, best, o); best = t < best ? t : best; }
-    if ((threadIdx.x & 31) == 0 && best != 0xffffffffu) atomicMin(out, best);
+            for (int r = 0; r < 4; ++r) {
+                const int x = slab * 1024 + r * 256 + threadIdx.x;
+                if (x < outn) {
+                    int sx = x;
+                    if (g.resample) { sx = (int)floor((double)x * ifx); if (sx > len - 1) sx = len - 1; }   // OpenCV resizeNN: cvFloor(x * ifx)
+                    const int acc = decode_acc(pcm, frame0 + sx, channels, width);
+                    const float v = acc_value(acc, channels);
+                    out[o0 + x] = v;
+                    count(v, acc);
+                }
+            }
+        } else {
+            // padding: head repeats the first content sample (wav.py:140), tail repeats data[-padding-1] (wav.py:141);
+            // a gap between the last written sample and the tail (np.empty in the reference) reads as zero
+            const bool head = item < li.n_content + li.n_head;
+            const int64_t slab = head ? item - li.n_content : item - li.n_content - li.n_head;
+            const int64_t base = head ? 0 : tail0, limit = head ? g.padding : g.total;
+            // head: [0, padding); tail region also covers the gap [padding + written, tail0) first
+            int acc = 0;
+            if (head) { if (g.written > 0) acc = decode_acc(pcm, 0, channels, width); }
+            else {
+                const int64_t o = tail0 - 1 - g.padding;            // content index of data[-padding-1]
+                if (o >= 0 && o < g.written) {
+                    int64_t c; int x, len; double ifx;
+                    if (g.out_full > 0 && o < g.nfull * (int64_t)g.out_full) { c = o / g.out_full; x = (int)(o - c * g.out_full); len = g.framerate; ifx = g.ifx_full; }
+                    else { c = g.nfull; x = (int)(o - g.nfull * (int64_t)g.out_full); len = g.len_last; ifx = g.ifx_last; }
+                    int sx = x;
+                    if (g.resample) { sx = (int)floor((double)x * ifx); if (sx > len - 1) sx = len - 1; }
+                    acc = decode_acc(pcm, c * (int64_t)g.framerate + sx, channels, width);
+                }
+            }
+            const float v = acc_value(acc, channels);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int64_t i = base + slab * 1024 + r * 256 + threadIdx.x;
+                if (i < limit) { out[i] = v; count(v, acc); }
+            }
+        }
+    }
+    // the gap between the written content and the tail padding (float rounding of the sample count, wav.py:113-116)
+    const int64_t gap0 = g.padding + g.written, gap_n = tail0 - gap0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < gap_n; i += (int64_t)gridDim.x * blockDim.x) {
+        out[gap0 + i] = 0.f; count(0.f, 0);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i <= kCoarseBins; i += blockDim.x)
+        if (s_h[i]) atomicAdd(hist + i, (unsigned long long)s_h[i]);
+}
+
+// acc histograms inside up to four coarse bins: fine[t][acc - base[t]], base[t] = (bin[t] - kCoarseZero) * 32 * channels
+struct FineTargets { int bin[4]; int base[4]; int n; int width; };     // width = 32 * channels
+__global__ void __launch_bounds__(256)
+k_select_fine(const float* __restrict__ x, int64_t n, int channels, FineTargets ft, unsigned* __restrict__ fine) {
+    extern __shared__ unsigned s_f[];                                     // [ft.n][ft.width]
+    for (int i = threadIdx.x; i < ft.n * ft.width; i += blockDim.x) s_f[i] = 0;
+    __syncthreads();
+    const float fc = (float)channels;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float v = x[i];
+        const int b = coarse_bin(v);
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+            if (t < ft.n && b == ft.bin[t]) {
+                const int off = __float2int_rn(v * fc) - ft.base[t];      // acc, exactly (|acc| < 2^22)
+                if (off >= 0 && off < ft.width) atomicAdd(&s_f[t * ft.width + off], 1u);
+                else atomicAdd(fine + 4 * ft.width, 1u);                  // cannot happen for sb_load_pcm data: flagged
+            }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < ft.n * ft.width; i += blockDim.x)
+        if (s_f[i]) atomicAdd(fine + i, s_f[i]);
 }
 
 __global__ void __launch_bounds__(256)
 k_normalise(const float* __restrict__ x, int64_t n, float lo, float hi, float* __restrict__ out_f32,
             unsigned char* __restrict__ out_u8) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (i >= n) return;
-    float v = x[i];
-    v = fminf(fmaxf(v, lo), hi);                         // np.clip (wav.py:148)
-    v = __fsub_rn(v, lo);                                // wav.py:150
-    v = __fdiv_rn(v, __fsub_rn(hi, lo));                 // wav.py:151 (float32 difference, float32 divide)
-    if (out_u8) {
-        v = __fmul_rn(v, 255.0f);                        // wav.py:154
-        v = __fadd_rn(v, 0.5f);                          // wav.py:155
-        out_u8[i] = (unsigned char)(int)v;               // astype('uint8'): truncation (wav.py:156)
+    const float den = __fsub_rn(hi, lo);
+    auto one = [&](float v) {
+        v = fminf(fmaxf(v, lo), hi);                         // np.clip (wav.py:148)
+        v = __fsub_rn(v, lo);                                // wav.py:150
+        return __fdiv_rn(v, den);                            // wav.py:151 (float32 difference, float32 divide)
+    };
+    auto quant = [&](float v) {
+        v = __fmul_rn(v, 255.0f);                            // wav.py:154
+        v = __fadd_rn(v, 0.5f);                              // wav.py:155
+        return (unsigned)(unsigned char)(int)v;              // astype('uint8'): truncation (wav.py:156)
+    };
+    if (i + 4 <= n) {                                        // streams are 256-byte aligned: 16-byte loads, 4-byte stores
+        const float4 v = *reinterpret_cast<const float4*>(x + i);
+        const float a = one(v.x), b = one(v.y), c = one(v.z), d = one(v.w);
+        if (out_u8) *reinterpret_cast<unsigned*>(out_u8 + i) = quant(a) | (quant(b) << 8) | (quant(c) << 16) | (quant(d) << 24);
+        else *reinterpret_cast<float4*>(out_f32 + i) = make_float4(a, b, c, d);
     } else {
-        out_f32[i] = v;
+        for (int64_t j = i; j < n; ++j) {
+            const float v = one(x[j]);
+            if (out_u8) out_u8[j] = (unsigned char)quant(v); else out_f32[j] = v;
+        }
     }
 }
 
-// median of the subset as NumPy computes it: middle element, or the float32 mean of the two middle ones
-int subset_median(const float* d_x, int64_t n, int subset, unsigned long long* d_hist, unsigned int* d_next,
-                  float* median_out, int64_t* count_out) {
+// Rank r (0-based, ascending) of subset 0 = {x >= 0} or subset 1 = {x <= 0}, located on the coarse histogram:
+// `zero` = the value is exactly 0; else (bin, idx) = idx-th smallest non-zero member inside coarse bin `bin`.
+struct RankWhere { bool zero; int bin; long long idx; };
+RankWhere locate_rank(const unsigned long long* h, int subset, long long r) {
+    const long long zeros = (long long)h[kCoarseBins];
+    RankWhere w = {false, 0, 0};
+    if (subset == 0) {                        // zeros first, then the positives ascending
+        if (r < zeros) { w.zero = true; return w; }
+        long long left = r - zeros;
+        for (int b = kCoarseZero; b < kCoarseBins; ++b) {
+            const long long cnt = (long long)h[b] - (b == kCoarseZero ? zeros : 0);
+            if (left < cnt) { w.bin = b; w.idx = left; return w; }
+            left -= cnt;
+        }
+    } else {                                  // the negatives ascending, then the zeros
+        long long left = r;
+        for (int b = 0; b < kCoarseZero; ++b) {
+            if (left < (long long)h[b]) { w.bin = b; w.idx = left; return w; }
+            left -= (long long)h[b];
+        }
+        w.zero = true;
+    }
+    return w;
+}
+
+// Both medians (NumPy: middle element, or the float32 mean of the two middle ones) from the coarse histogram
+// the decode kernel left behind plus one pass over the data.
+int medians_from_histograms(const sb_stream* raw, float* med_pos, float* med_neg) {
     Ctx& c = ctx();
-    const int grid = c.sm_count * 8;
-    unsigned long long h[256];
-    unsigned int prefix = 0, mask = 0;
-    int64_t count = 0, k = 0, below = 0;      // k: rank searched; below: members with key < current prefix range
-    int64_t equal = 0;
-    for (int pass = 0; pass < 4; ++pass) {
-        const int shift = 24 - 8 * pass;
-        SB_CUDA(cudaMemsetAsync(d_hist, 0, sizeof(h), c.stream));
-        {
-            ProfScope ps("median_select_hist");
-            k_select_hist<<<grid, 256, 0, c.stream>>>(d_x, n, subset, prefix, mask, shift, d_hist);
-        }
-        SB_CUDA(cudaMemcpyAsync(h, d_hist, sizeof(h), cudaMemcpyDeviceToHost, c.stream));
-        SB_CUDA(cudaStreamSynchronize(c.stream));
-        if (pass == 0) {
-            for (int b = 0; b < 256; ++b) count += (int64_t)h[b];
-            if (count == 0) { *median_out = nanf(""); *count_out = 0; return SB_OK; }   // np.median([]) is nan
-            k = (count - 1) / 2;                 // lower middle element
-        }
-        int64_t acc = below;
-        int b = 0;
-        for (; b < 256; ++b) {
-            if (acc + (int64_t)h[b] > k) break;
-            acc += (int64_t)h[b];
-        }
-        below = acc; equal = (int64_t)h[b];
-        prefix |= (unsigned int)b << shift;
-        mask |= 0xffu << shift;
-    }
-    const unsigned int key_lo = prefix;          // key of the element of rank k
-    float med = key_float(key_lo);
-    if (count % 2 == 0) {                        // need rank k+1 as well
-        unsigned int key_hi = key_lo;
-        if (below + equal <= k + 1) {            // rank k+1 is the next distinct value
-            const unsigned int init = 0xffffffffu;
-            SB_CUDA(cudaMemcpyAsync(d_next, &init, sizeof(init), cudaMemcpyHostToDevice, c.stream));
-            {
-                ProfScope ps("median_select_next");
-                k_select_next<<<grid, 256, 0, c.stream>>>(d_x, n, subset, key_lo, d_next);
+    const int ch = raw->pcm_channels;
+    unsigned long long h[kCoarseBins + 1];
+    SB_CUDA(cudaMemcpyAsync(h, raw->d_loadhist, sizeof(h), cudaMemcpyDeviceToHost, c.stream));
+    SB_CUDA(cudaStreamSynchronize(c.stream));
+    const long long zeros = (long long)h[kCoarseBins];
+    long long pos = 0, neg = 0;
+    for (int b = 0; b < kCoarseZero; ++b) neg += (long long)h[b];
+    for (int b = kCoarseZero; b < kCoarseBins; ++b) pos += (long long)h[b];
+    const long long count[2] = {pos, neg + zeros};          // bin kCoarseZero holds the zeros: pos already includes them
+    RankWhere want[2][2];
+    int nwant[2];
+    FineTargets ft; ft.n = 0; ft.width = kCoarseWidth * ch;
+    for (int s = 0; s < 2; ++s) {
+        nwant[s] = count[s] == 0 ? 0 : (count[s] % 2 == 0 ? 2 : 1);
+        const long long k = (count[s] - 1) / 2;
+        for (int e = 0; e < nwant[s]; ++e) {
+            want[s][e] = locate_rank(h, s, k + e);
+            if (!want[s][e].zero) {
+                bool have = false;
+                for (int t = 0; t < ft.n; ++t) have = have || ft.bin[t] == want[s][e].bin;
+                if (!have) { ft.bin[ft.n] = want[s][e].bin; ft.base[ft.n] = (want[s][e].bin - kCoarseZero) * ft.width; ++ft.n; }
             }
-            SB_CUDA(cudaMemcpyAsync(&key_hi, d_next, sizeof(key_hi), cudaMemcpyDeviceToHost, c.stream));
-            SB_CUDA(cudaStreamSynchronize(c.stream));
         }
-        const float a = key_float(key_lo), b2 = key_float(key_hi);
-        med = (a + b2) * 0.5f;                   // np.mean of two float32 values, float32 arithmetic
     }
-    *median_out = med; *count_out = count;
+    std::vector<unsigned> fine((size_t)4 * ft.width + 1, 0u);
+    if (ft.n) {
+        unsigned* d_fine = nullptr;
+        SB_TRY(pool_alloc((void**)&d_fine, fine.size() * sizeof(unsigned)));
+        SB_CUDA(cudaMemsetAsync(d_fine, 0, fine.size() * sizeof(unsigned), c.stream));
+        {
+            ProfScope ps("median_select_fine");
+            k_select_fine<<<c.sm_count * 8, 256, (size_t)ft.n * ft.width * sizeof(unsigned), c.stream>>>(
+                static_cast<const float*>(raw->d_raw), raw->n, ch, ft, d_fine);
+        }
+        cudaError_t e = cudaMemcpyAsync(fine.data(), d_fine, fine.size() * sizeof(unsigned), cudaMemcpyDeviceToHost, c.stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c.stream);
+        pool_free(d_fine);
+        if (e != cudaSuccess) SB_FAIL(SB_ECUDA, "sb_normalise: median selection: %s", cudaGetErrorString(e));
+        if (fine[(size_t)4 * ft.width]) SB_FAIL(SB_EINVAL, "sb_normalise: samples are not int16 / channels values (not produced by sb_load_pcm?)");
+    }
+    float med[2] = {nanf(""), nanf("")};                     // np.median([]) is nan
+    for (int s = 0; s < 2; ++s) {
+        float v[2] = {0.f, 0.f};
+        for (int e = 0; e < nwant[s]; ++e) {
+            const RankWhere& w = want[s][e];
+            if (w.zero) { v[e] = 0.f; continue; }
+            int t = 0;
+            while (ft.bin[t] != w.bin) ++t;
+            long long left = w.idx;
+            int acc = 0; bool found = false;
+            for (int o = 0; o < ft.width && !found; ++o) {
+                const int a = ft.base[t] + o;
+                if (a == 0) continue;                        // zeros are counted apart
+                const long long cnt = fine[(size_t)t * ft.width + o];
+                if (left < cnt) { acc = a; found = true; } else left -= cnt;
+            }
+            if (!found) SB_FAIL(SB_ECUDA, "sb_normalise: internal: median rank not found in its histogram bin");
+            v[e] = ch == 1 ? (float)acc : (float)acc / (float)ch;
+        }
+        if (nwant[s] == 1) med[s] = v[0];
+        else if (nwant[s] == 2) med[s] = (v[0] + v[1]) * 0.5f;      // np.mean of two float32 values, float32 arithmetic
+    }
+    *med_pos = med[0]; *med_neg = med[1];
     return SB_OK;
 }
 
@@ -226,24 +313,31 @@ int sb_load_pcm(const void* pcm_host, int64_t frames, int channels, int sample_w
         SB_FAIL(SB_EINVAL, "sb_load_pcm: %lld resampled samples do not fit a buffer of %lld with %lld padding",
                 (long long)g.written, (long long)total_len, (long long)padding);
 
+    if (channels > kMaxChannels) SB_FAIL(SB_EINVAL, "sb_load_pcm: %d channels (at most %d)", channels, kMaxChannels);
     sb_stream* s = new (std::nothrow) sb_stream();
     if (!s) SB_FAIL(SB_ENOMEM, "sb_load_pcm: out of host memory");
-    s->n = total_len; s->dtype = SB_F32;
+    s->n = total_len; s->dtype = SB_F32; s->pcm_channels = channels;
     unsigned char* d_pcm = nullptr;
     const size_t pcm_bytes = (size_t)frames * channels * sample_width;
     int rc = pool_alloc(&s->d_raw, sizeof(float) * total_len + 16);
     if (rc == SB_OK) rc = pool_alloc((void**)&d_pcm, pcm_bytes + 16);
-    if (rc != SB_OK) { pool_free(s->d_raw); delete s; return rc; }
+    if (rc == SB_OK) rc = pool_alloc((void**)&s->d_loadhist, sizeof(unsigned long long) * (kCoarseBins + 1));
+    if (rc != SB_OK) { pool_free(s->d_raw); pool_free(d_pcm); delete s; return rc; }
+    LoadItems li;
+    li.per_full = (g.out_full + 1023) / 1024; li.per_last = (g.out_last + 1023) / 1024;
+    li.n_content = g.nfull * (int64_t)li.per_full + li.per_last;
+    li.n_head = (padding + 1023) / 1024; li.n_tail = (padding + 1023) / 1024;
     cudaError_t e = cudaMemcpyAsync(d_pcm, pcm_host, pcm_bytes, cudaMemcpyHostToDevice, c.stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(s->d_loadhist, 0, sizeof(unsigned long long) * (kCoarseBins + 1), c.stream);
     if (e == cudaSuccess) {
         ProfScope ps("decode_resample_pad");
-        k_decode_resample_pad<<<(unsigned)((total_len + 255) / 256), 256, 0, c.stream>>>(
-            d_pcm, g, channels, sample_width, static_cast<float*>(s->d_raw));
+        k_decode_resample_pad<<<c.sm_count * 8, 256, 0, c.stream>>>(
+            d_pcm, g, li, channels, sample_width, static_cast<float*>(s->d_raw), s->d_loadhist);
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(c.stream);            // pcm_host may be reused by the caller
     pool_free(d_pcm);
-    if (e != cudaSuccess) { pool_free(s->d_raw); delete s; SB_FAIL(SB_ECUDA, "sb_load_pcm: %s", cudaGetErrorString(e)); }
+    if (e != cudaSuccess) { sb_stream_destroy(s); SB_FAIL(SB_ECUDA, "sb_load_pcm: %s", cudaGetErrorString(e)); }
     *out_f32 = s;                 // no running sums yet: only sb_normalise / sb_stream_read accept it
     return SB_OK;
 }
@@ -256,13 +350,10 @@ int sb_normalise(const sb_stream* raw_f32, int dtype, sb_stream** out, float* mi
     if (dtype != SB_U8 && dtype != SB_F32) SB_FAIL(SB_EINVAL, "Unknown sample type of WAV stream, must be uint8 or float32");
     const int64_t n = raw_f32->n;
     const float* x = static_cast<const float*>(raw_f32->d_raw);
-    unsigned long long* d_hist = nullptr; unsigned int* d_next = nullptr;
-    SB_TRY(pool_alloc((void**)&d_hist, 256 * sizeof(unsigned long long)));
-    int rc = pool_alloc((void**)&d_next, 256);
-    float med_pos = 0.f, med_neg = 0.f; int64_t cnt = 0;
-    if (rc == SB_OK) rc = subset_median(x, n, 0, d_hist, d_next, &med_pos, &cnt);
-    if (rc == SB_OK) rc = subset_median(x, n, 1, d_hist, d_next, &med_neg, &cnt);
-    pool_free(d_hist); pool_free(d_next);
+    if (!raw_f32->d_loadhist || raw_f32->pcm_channels < 1)
+        SB_FAIL(SB_EINVAL, "sb_normalise: input was not produced by sb_load_pcm");
+    float med_pos = 0.f, med_neg = 0.f;
+    int rc = medians_from_histograms(raw_f32, &med_pos, &med_neg);
     if (rc != SB_OK) return rc;
     const float hi = med_pos * 3.0f, lo = med_neg * 3.0f;               // wav.py:145-146 (float32 products)
     if (min3_out) *min3_out = lo;
@@ -275,7 +366,7 @@ int sb_normalise(const sb_stream* raw_f32, int dtype, sb_stream** out, float* mi
     if (rc != SB_OK) { delete s; return rc; }
     {
         ProfScope ps("normalise_quantise");
-        k_normalise<<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(
+        k_normalise<<<(unsigned)((n + 1023) / 1024), 256, 0, c.stream>>>(
             x, n, lo, hi, dtype == SB_F32 ? static_cast<float*>(s->d_raw) : nullptr,
             dtype == SB_U8 ? static_cast<unsigned char*>(s->d_raw) : nullptr);
     }

@@ -17,7 +17,7 @@
 #include <cstdlib>
 #include <cstring>
 
-namespace sb { int ensure_spectra(sb_stream* s, int hd); int ensure_spectra_quad(sb_stream* s); }
+namespace sb { int ensure_spectra(sb_stream* s, int hd); int ensure_spectra_quad(sb_stream* s, int64_t k_lo, int64_t k_hi); }
 using namespace sb;
 
 namespace {
@@ -469,7 +469,16 @@ int run_batch(const sb_stream* image_c, const sb_stream* tmpl, int64_t count,
         for (int64_t q = 0; q < n_direct; ++q) { rows += (double)c.h_desc[q].nk * c.h_desc[q].P; blocks += (double)c.h_desc[q].nk; }
         use_pairs = rows >= 1.5 * blocks;
     }
-    if (use_packed && n_direct > 0) SB_TRY(ensure_spectra_quad(image));
+    if (use_packed && n_direct > 0) {
+        // spectrum rows the direct class reads: lag block k of a query multiplies rows k .. k+P-1 (a pair: .. k+P)
+        int64_t k_lo = INT64_MAX, k_hi = 0;
+        for (int64_t q = 0; q < n_direct; ++q) {
+            const QueryDesc& d = c.h_desc[q];
+            k_lo = std::min<int64_t>(k_lo, d.k0);
+            k_hi = std::max<int64_t>(k_hi, (int64_t)d.k0 + d.nk + d.P);
+        }
+        SB_TRY(ensure_spectra_quad(image, k_lo, k_hi));
+    }
     if (!use_packed || n_direct < count) SB_TRY(ensure_spectra(image, hd));
 
     SB_TRY(grow(&c.d_desc, &c.desc_cap, count));

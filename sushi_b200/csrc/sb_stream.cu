@@ -39,7 +39,9 @@ k_tile_totals(const T* __restrict__ x, int64_t n, double* __restrict__ tsum, dou
     }
 }
 
-// Phase B: exclusive scan of the tile totals (one CTA walks them in 1024-wide slabs).
+// Phase B: exclusive scan of the tile totals.  One CTA walks them in slabs of 1024 x TOT_ITEMS (a 90-minute
+// stream has 15 880 tiles: one slab), every thread scanning TOT_ITEMS consecutive totals in registers.
+constexpr int TOT_ITEMS = 16;
 __global__ void __launch_bounds__(1024)
 k_scan_tile_totals(double* __restrict__ tsum, double* __restrict__ tsq, int64_t ntiles) {
     __shared__ double s_a[32], s_b[32];
@@ -47,10 +49,16 @@ k_scan_tile_totals(double* __restrict__ tsum, double* __restrict__ tsq, int64_t 
     if (threadIdx.x == 0) { carry_a = 0.0; carry_b = 0.0; }
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int64_t base = 0; base < ntiles; base += 1024) {
-        int64_t j = base + threadIdx.x;
-        double a = j < ntiles ? tsum[j] : 0.0, b = j < ntiles ? tsq[j] : 0.0;
-        double ia = a, ib = b;                          // inclusive warp scan
+    for (int64_t base = 0; base < ntiles; base += 1024 * TOT_ITEMS) {
+        const int64_t j0 = base + (int64_t)threadIdx.x * TOT_ITEMS;
+        double va[TOT_ITEMS], vb[TOT_ITEMS];
+        double a = 0.0, b = 0.0;
+#pragma unroll
+        for (int i = 0; i < TOT_ITEMS; ++i) {
+            va[i] = j0 + i < ntiles ? tsum[j0 + i] : 0.0; vb[i] = j0 + i < ntiles ? tsq[j0 + i] : 0.0;
+            a += va[i]; b += vb[i];
+        }
+        double ia = a, ib = b;                          // inclusive warp scan of the threads' totals
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             double ta = __shfl_up_sync(0xffffffffu, ia, o), tb = __shfl_up_sync(0xffffffffu, ib, o);
@@ -70,9 +78,13 @@ k_scan_tile_totals(double* __restrict__ tsum, double* __restrict__ tsq, int64_t 
         }
         __syncthreads();
         double ea = carry_a + s_a[warp] + (ia - a), eb = carry_b + s_b[warp] + (ib - b);
-        if (j < ntiles) { tsum[j] = ea; tsq[j] = eb; }
+#pragma unroll
+        for (int i = 0; i < TOT_ITEMS; ++i) {
+            if (j0 + i < ntiles) { tsum[j0 + i] = ea; tsq[j0 + i] = eb; }
+            ea += va[i]; eb += vb[i];
+        }
         __syncthreads();
-        if (threadIdx.x == 1023) { carry_a = ea + a; carry_b = eb + b; }
+        if (threadIdx.x == 1023) { carry_a = ea; carry_b = eb; }
         __syncthreads();
     }
 }
@@ -125,6 +137,94 @@ k_tile_scan(const T* __restrict__ x, int64_t n, const double* __restrict__ osum,
     if (blockIdx.x == 0 && threadIdx.x == 0) pfx[0] = make_double2(0.0, 0.0);
 }
 
+// ---- uint8 streams: the same three phases on exact integers, written for HBM bandwidth -------------------
+// The running sums cost 16 bytes per sample to write against 1 byte to read, so the scan is a store stream:
+// phase C below gives every store instruction of a warp 512 contiguous bytes (lane l owns sample 32*it + l,
+// the scan across the lanes is five shuffle steps on 32-bit integers -- sums inside a 4096-sample tile fit:
+// 4096 * 255^2 < 2^31), with no trip through shared memory and no barrier between loads and stores, so the
+// 8 warps of a CTA stream independently.  Phase A reads 16 bytes per lane and sums with dp4a.
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_tile_totals_u8(const uint8_t* __restrict__ x, int64_t n, double* __restrict__ tsum, double* __restrict__ tsq) {
+    __shared__ unsigned s_a[SCAN_THREADS / 32], s_b[SCAN_THREADS / 32];
+    const int64_t j = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * 16;     // stream allocations carry 16 bytes of slack
+    unsigned a = 0, b = 0;
+    if (j < n) {
+        uint4 v = __ldg(reinterpret_cast<const uint4*>(x + j));
+        if (j + 16 > n) {                            // mask the bytes past the end
+            const int keep = (int)(n - j);
+            unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int kb = keep - 4 * k;
+                w[k] = kb >= 4 ? w[k] : (kb <= 0 ? 0u : (w[k] & (0xffffffffu >> (8 * (4 - kb)))));
+            }
+            v = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        a = __dp4a(v.x, 0x01010101u, __dp4a(v.y, 0x01010101u, __dp4a(v.z, 0x01010101u, __dp4a(v.w, 0x01010101u, 0u))));
+        b = __dp4a(v.x, v.x, __dp4a(v.y, v.y, __dp4a(v.z, v.z, __dp4a(v.w, v.w, 0u))));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+    if ((threadIdx.x & 31) == 0) { s_a[threadIdx.x >> 5] = a; s_b[threadIdx.x >> 5] = b; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned ta = 0, tb = 0;
+        for (int w = 0; w < SCAN_THREADS / 32; ++w) { ta += s_a[w]; tb += s_b[w]; }
+        tsum[blockIdx.x] = (double)ta; tsq[blockIdx.x] = (double)tb;
+    }
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_tile_scan_u8(const uint8_t* __restrict__ x, int64_t n, const double* __restrict__ osum, const double* __restrict__ osq,
+               double2* __restrict__ pfx) {
+    constexpr int NW = SCAN_THREADS / 32, PER_WARP = SCAN_TILE / NW;        // 512 samples per warp
+    __shared__ unsigned s_a[NW], s_b[NW];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t w0 = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)warp * PER_WARP;
+    {   // totals of the warps in front of this one inside the tile
+        unsigned a = 0, b = 0;
+        const int64_t j = w0 + lane * 16;
+        if (j < n) {
+            uint4 v = __ldg(reinterpret_cast<const uint4*>(x + j));
+            if (j + 16 > n) {
+                const int keep = (int)(n - j);
+                unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int kb = keep - 4 * k;
+                    w[k] = kb >= 4 ? w[k] : (kb <= 0 ? 0u : (w[k] & (0xffffffffu >> (8 * (4 - kb)))));
+                }
+                v = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+            a = __dp4a(v.x, 0x01010101u, __dp4a(v.y, 0x01010101u, __dp4a(v.z, 0x01010101u, __dp4a(v.w, 0x01010101u, 0u))));
+            b = __dp4a(v.x, v.x, __dp4a(v.y, v.y, __dp4a(v.z, v.z, __dp4a(v.w, v.w, 0u))));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+        if (lane == 0) { s_a[warp] = a; s_b[warp] = b; }
+    }
+    __syncthreads();
+    unsigned cs = 0, cq = 0;                           // integer carry inside the tile (exact)
+    for (int w = 0; w < warp; ++w) { cs += s_a[w]; cq += s_b[w]; }
+    const double bs = osum[blockIdx.x], bq = osq[blockIdx.x];
+    if (blockIdx.x == 0 && threadIdx.x == 0) pfx[0] = make_double2(0.0, 0.0);
+#pragma unroll 4
+    for (int it = 0; it < PER_WARP / 32; ++it) {
+        const int64_t j = w0 + it * 32 + lane;
+        if (w0 + it * 32 >= n) break;                  // warp-uniform
+        const unsigned v = j < n ? (unsigned)__ldg(x + j) : 0u;
+        unsigned s = v, q = v * v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned ts = __shfl_up_sync(0xffffffffu, s, o), tq = __shfl_up_sync(0xffffffffu, q, o);
+            if (lane >= o) { s += ts; q += tq; }
+        }
+        if (j < n) pfx[j + 1] = make_double2(bs + (double)(cs + s), bq + (double)(cq + q));
+        cs += __shfl_sync(0xffffffffu, s, 31);
+        cq += __shfl_sync(0xffffffffu, q, 31);
+    }
+}
+
 // Centred float rows for the block spectra: row k holds image[kB .. kB+2B) - c,
 // zero beyond the end of the stream; rows are (2B+2) floats apart (in-place R2C).
 template <typename T>
@@ -148,6 +248,31 @@ k_gather_blocks(const T* __restrict__ x, int64_t n, const double2* __restrict__ 
             *reinterpret_cast<float2*>(out + i) = v;
         }
     }
+}
+
+int build_prefix_u8(sb_stream* s) {
+    Ctx& c = ctx();
+    const int64_t n = s->n;
+    const int64_t ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    double* d_t = nullptr;
+    SB_TRY(pool_alloc((void**)&d_t, sizeof(double) * 2 * ntiles));
+    double* tsum = d_t; double* tsq = d_t + ntiles;
+    const uint8_t* x = static_cast<const uint8_t*>(s->d_raw);
+    {
+        ProfScope ps("scan_tile_totals");
+        k_tile_totals_u8<<<(unsigned)ntiles, SCAN_THREADS, 0, c.stream>>>(x, n, tsum, tsq);
+    }
+    {
+        ProfScope ps("scan_tile_offsets");
+        k_scan_tile_totals<<<1, 1024, 0, c.stream>>>(tsum, tsq, ntiles);
+    }
+    {
+        ProfScope ps("scan_tiles");
+        k_tile_scan_u8<<<(unsigned)ntiles, SCAN_THREADS, 0, c.stream>>>(x, n, tsum, tsq, s->d_pfx);
+    }
+    SB_CUDA(cudaGetLastError());
+    pool_free(d_t);            // reused only by later work on the same stream
+    return SB_OK;
 }
 
 template <typename T>
@@ -184,7 +309,7 @@ int build_prefix(sb_stream* s) {
 
 int stream_finish(sb_stream* s) {
     SB_TRY(pool_alloc((void**)&s->d_pfx, sizeof(double2) * (s->n + 1)));
-    if (s->dtype == SB_U8) return build_prefix<uint8_t>(s);
+    if (s->dtype == SB_U8) return build_prefix_u8(s);
     return build_prefix<float>(s);
 }
 
@@ -210,17 +335,33 @@ namespace sb {
 int stream_finish_public(sb_stream* s) { return stream_finish(s); }
 
 // Block spectra in the quad layout of the packed kernels (sb_fused2.cu): B = 16384, hop B.
-int ensure_spectra_quad(sb_stream* s) {
+// Rows are built on demand: [k_lo, k_hi) is what the batch at hand reads.  A rank of an event-sharded job
+// touches only the part of the destination stream its own events' search windows cover, so it transforms
+// that part only (the replicated stream preparation is the Amdahl term of strong scaling).
+int ensure_spectra_quad(sb_stream* s, int64_t k_lo, int64_t k_hi) {
     Ctx& c = ctx();
     if (!packed_supports(c.B)) SB_FAIL(SB_EINVAL, "internal: quad-layout spectra need a lag block of 16384");
-    if (s->d_specq) return SB_OK;
     const int64_t nblk = (s->n + c.B - 1) / c.B;
-    SB_TRY(pool_alloc((void**)&s->d_specq, sizeof(float2) * (size_t)nblk * kQuadRowF2));
-    {
-        ProfScope ps("block_spectra");
-        SB_TRY(launch_block_spectra_quad(s, 0, nblk, s->d_specq));
+    if (k_lo < 0) k_lo = 0;
+    if (k_hi > nblk) k_hi = nblk;
+    if (k_lo >= k_hi) return SB_OK;
+    if (!s->d_specq) {
+        SB_TRY(pool_alloc((void**)&s->d_specq, sizeof(float2) * (size_t)nblk * kQuadRowF2));
+        s->nblkq = nblk; s->specq_lo = s->specq_hi = k_lo;
     }
-    s->nblkq = nblk;
+    auto build = [&](int64_t a, int64_t b) -> int {
+        if (a >= b) return SB_OK;
+        ProfScope ps("block_spectra");
+        return launch_block_spectra_quad(s, a, b - a, s->d_specq + a * (int64_t)kQuadRowF2);
+    };
+    if (s->specq_lo == s->specq_hi) {                // nothing built yet
+        SB_TRY(build(k_lo, k_hi));
+        s->specq_lo = k_lo; s->specq_hi = k_hi;
+        return SB_OK;
+    }
+    // keep the built range contiguous: extend it on either side (a gap between an old and a new range is filled)
+    if (k_lo < s->specq_lo) { SB_TRY(build(k_lo, s->specq_lo)); s->specq_lo = k_lo; }
+    if (k_hi > s->specq_hi) { SB_TRY(build(s->specq_hi, k_hi)); s->specq_hi = k_hi; }
     return SB_OK;
 }
 
@@ -306,7 +447,7 @@ int sb_stream_destroy(sb_stream* s) {
     if (!s) return SB_OK;
     Ctx& c = ctx();
     (void)c;
-    pool_free(s->d_raw); pool_free(s->d_pfx); pool_free(s->d_spec); pool_free(s->d_specq);
+    pool_free(s->d_raw); pool_free(s->d_pfx); pool_free(s->d_spec); pool_free(s->d_specq); pool_free(s->d_loadhist);
     delete s;
     return SB_OK;
 }

@@ -121,7 +121,9 @@ def test_pairs_are_bit_identical_to_single_lag_blocks(gpu_lib, epilogue, stype):
         assert np.array_equal(got[5][0], got[4][0]), (toff, n, lag0, nlags)
         assert got[5][1][0][0] == got[4][1][0][0] and got[5][1][1][0] == got[4][1][1][0]
         want = rd.match_curve(rs.data[:, toff:toff + n], lag0, nlags)
-        assert np.abs(got[4][0] - want).max() <= 1e-5 and abs(int(got[4][0].argmin()) - int(want.argmin())) <= 1
+        assert np.abs(got[4][0] - want).max() <= 1e-5
+        # a minimiser of cv2's curve (searches that reach into the constant padding have long runs of equal values)
+        assert want[int(got[4][0].argmin())] - want.min() <= 2e-6
     starts, ends = synth.make_events(120, 60.0, 8, 0.5, 5.0)
     win = np.full(len(starts), 20.0)
     res = {}

@@ -1,9 +1,11 @@
 #!/usr/bin/env python3
 """Turn an `ncu --set full` report of the dominant kernel, captured on the bench workload, into
 profiles/traffic.json (DRAM bytes per launch) + a short text summary under profiles/.
-    ncu --set full --clock-control none --import-source on -k regex:k_match_fused -s 3 -c 1 \
-        -o gpurun_out/fused_bench python bench.py --steps 1 --warmup 3 --no-cpu-baseline     (GPU box)
-    python tools/ncu_traffic.py gpurun_out/fused_bench.ncu-rep config2 uint8 match_fused 16384   (here)
+    ncu --set full --clock-control none --import-source on -k regex:k_match_pair -s 3 -c 1 \
+        -o gpurun_out/pair_bench python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-load-leg    (GPU box)
+    python tools/ncu_traffic.py gpurun_out/pair_bench.ncu-rep config3 uint8 match_fused 1   (here, same source tree)
+The entry is stamped with the hash of the CUDA sources (bench.kernel_source_hash): bench.py uses a capture only
+for the source it was taken from and prints traffic = null with the reason otherwise.
 """
 import csv
 import io
@@ -13,7 +15,9 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-rep, workload, stype, kclass, block = sys.argv[1:6]
+rep, workload, stype, kclass, ngpus = sys.argv[1:6]
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
 raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units, vals = rows[0], rows[1], rows[-1]
@@ -34,7 +38,7 @@ try:
     tr = json.load(open(out_path))
 except (OSError, ValueError):
     tr = {}
-key = '%s/%s/%s/B%s' % (workload, stype, kclass, block)
+key = '%s/%s/%s/N%s' % (workload, stype, kclass, ngpus)
 keep = ['gpu__time_duration.sum', 'launch__grid_size', 'launch__registers_per_thread',
         'launch__shared_mem_per_block_dynamic', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
         'sm__warps_active.avg.pct_of_peak_sustained_active', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
@@ -44,7 +48,7 @@ keep = ['gpu__time_duration.sum', 'launch__grid_size', 'launch__registers_per_th
         'sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active',
         'sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active', 'smsp__inst_executed.sum',
         'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active']
-tr[key] = {'dram_bytes_per_launch': dram, 'report': os.path.basename(rep),
+tr[key] = {'dram_bytes_per_launch': dram, 'report': os.path.basename(rep), 'src_hash': bench.kernel_source_hash(),
            'metrics': {k: ' '.join(d[k]) for k in keep if k in d}}
 json.dump(tr, open(out_path, 'w'), indent=1, sort_keys=True)
 print(key, 'dram bytes/launch', dram)
