@@ -886,7 +886,7 @@ k_match_pair(const float4* __restrict__ That, int64_t part_first,
                 a0[u].zero(); a1[u].zero();
                 R::load(xp, i0 + u * R::USTEP, xa[u], xm[u]);     // row k < nblk
             }
-#pragma unroll 1
+#pragma unroll 2                               // two partition steps in flight: measured +0.3 % (128 registers, no spills)
             for (int p = 0; p < d.P; ++p) {
                 const float4* t = tp + (int64_t)p * R::STRIDE;
                 const float4* x = xp + (int64_t)(p + 1) * R::STRIDE;

@@ -142,8 +142,7 @@ k_select_fine(const float* __restrict__ x, int64_t n, int channels, FineTargets 
     for (int i = threadIdx.x; i < ft.n * ft.width; i += blockDim.x) s_f[i] = 0;
     __syncthreads();
     const float fc = (float)channels;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const float v = x[i];
+    auto one = [&](float v) {
         const int b = coarse_bin(v);
 #pragma unroll
         for (int t = 0; t < 4; ++t)
@@ -152,7 +151,13 @@ k_select_fine(const float* __restrict__ x, int64_t n, int channels, FineTargets 
                 if (off >= 0 && off < ft.width) atomicAdd(&s_f[t * ft.width + off], 1u);
                 else atomicAdd(fine + 4 * ft.width, 1u);                  // cannot happen for sb_load_pcm data: flagged
             }
+    };
+    const int64_t n4 = n >> 2;                                            // streams are 256-byte aligned
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+        one(v.x); one(v.y); one(v.z); one(v.w);
     }
+    if (blockIdx.x == 0 && threadIdx.x < (int)(n & 3)) one(x[(n4 << 2) + threadIdx.x]);
     __syncthreads();
     for (int i = threadIdx.x; i < ft.n * ft.width; i += blockDim.x)
         if (s_f[i]) atomicAdd(fine + i, s_f[i]);
@@ -161,8 +166,6 @@ k_select_fine(const float* __restrict__ x, int64_t n, int channels, FineTargets 
 __global__ void __launch_bounds__(256)
 k_normalise(const float* __restrict__ x, int64_t n, float lo, float hi, float* __restrict__ out_f32,
             unsigned char* __restrict__ out_u8) {
-    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    if (i >= n) return;
     const float den = __fsub_rn(hi, lo);
     auto one = [&](float v) {
         v = fminf(fmaxf(v, lo), hi);                         // np.clip (wav.py:148)
@@ -174,16 +177,23 @@ k_normalise(const float* __restrict__ x, int64_t n, float lo, float hi, float* _
         v = __fadd_rn(v, 0.5f);                              // wav.py:155
         return (unsigned)(unsigned char)(int)v;              // astype('uint8'): truncation (wav.py:156)
     };
-    if (i + 4 <= n) {                                        // streams are 256-byte aligned: 16-byte loads, 4-byte stores
-        const float4 v = *reinterpret_cast<const float4*>(x + i);
-        const float a = one(v.x), b = one(v.y), c = one(v.z), d = one(v.w);
-        if (out_u8) *reinterpret_cast<unsigned*>(out_u8 + i) = quant(a) | (quant(b) << 8) | (quant(c) << 16) | (quant(d) << 24);
-        else *reinterpret_cast<float4*>(out_f32 + i) = make_float4(a, b, c, d);
-    } else {
-        for (int64_t j = i; j < n; ++j) {
-            const float v = one(x[j]);
-            if (out_u8) out_u8[j] = (unsigned char)quant(v); else out_f32[j] = v;
+    // streams are 256-byte aligned: 16-byte loads, two of them in flight per thread, 8-byte / 16-byte stores
+    const int64_t n8 = n >> 3;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(x) + 2 * i), w = __ldg(reinterpret_cast<const float4*>(x) + 2 * i + 1);
+        const float a = one(v.x), b = one(v.y), c = one(v.z), d = one(v.w), e = one(w.x), f = one(w.y), g = one(w.z), h = one(w.w);
+        if (out_u8) {
+            *reinterpret_cast<uint2*>(out_u8 + 8 * i) = make_uint2(quant(a) | (quant(b) << 8) | (quant(c) << 16) | (quant(d) << 24),
+                                                                   quant(e) | (quant(f) << 8) | (quant(g) << 16) | (quant(h) << 24));
+        } else {
+            reinterpret_cast<float4*>(out_f32)[2 * i] = make_float4(a, b, c, d);
+            reinterpret_cast<float4*>(out_f32)[2 * i + 1] = make_float4(e, f, g, h);
         }
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (int)(n & 7)) {
+        const int64_t j = (n8 << 3) + threadIdx.x;
+        const float v = one(x[j]);
+        if (out_u8) out_u8[j] = (unsigned char)quant(v); else out_f32[j] = v;
     }
 }
 
@@ -366,7 +376,7 @@ int sb_normalise(const sb_stream* raw_f32, int dtype, sb_stream** out, float* mi
     if (rc != SB_OK) { delete s; return rc; }
     {
         ProfScope ps("normalise_quantise");
-        k_normalise<<<(unsigned)((n + 1023) / 1024), 256, 0, c.stream>>>(
+        k_normalise<<<c.sm_count * 16, 256, 0, c.stream>>>(
             x, n, lo, hi, dtype == SB_F32 ? static_cast<float*>(s->d_raw) : nullptr,
             dtype == SB_U8 ? static_cast<unsigned char*>(s->d_raw) : nullptr);
     }

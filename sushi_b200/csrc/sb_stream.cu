@@ -40,22 +40,35 @@ k_tile_totals(const T* __restrict__ x, int64_t n, double* __restrict__ tsum, dou
 }
 
 // Phase B: exclusive scan of the tile totals.  One CTA walks them in slabs of 1024 x TOT_ITEMS (a 90-minute
-// stream has 15 880 tiles: one slab), every thread scanning TOT_ITEMS consecutive totals in registers.
-constexpr int TOT_ITEMS = 16;
+// stream has 15 880 tiles: two slabs).  A slab goes to shared memory with coalesced loads, every thread scans
+// TOT_ITEMS consecutive totals there, the threads' totals are scanned across the CTA, and the slab goes back.
+constexpr int TOT_ITEMS = 8;
+constexpr int TOT_SLAB = 1024 * TOT_ITEMS;
 __global__ void __launch_bounds__(1024)
 k_scan_tile_totals(double* __restrict__ tsum, double* __restrict__ tsq, int64_t ntiles) {
+    extern __shared__ __align__(16) unsigned char tot_smem[];
+    double* s_va = reinterpret_cast<double*>(tot_smem);                   // [TOT_SLAB + TOT_SLAB / TOT_ITEMS] padded
+    double* s_vb = s_va + TOT_SLAB + TOT_SLAB / TOT_ITEMS;
     __shared__ double s_a[32], s_b[32];
     __shared__ double carry_a, carry_b;
     if (threadIdx.x == 0) { carry_a = 0.0; carry_b = 0.0; }
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int64_t base = 0; base < ntiles; base += 1024 * TOT_ITEMS) {
-        const int64_t j0 = base + (int64_t)threadIdx.x * TOT_ITEMS;
+    auto slot = [](int e) { return e + e / TOT_ITEMS; };                  // one padding slot per thread's run: conflict-free
+    for (int64_t base = 0; base < ntiles; base += TOT_SLAB) {
+#pragma unroll
+        for (int i = 0; i < TOT_ITEMS; ++i) {
+            const int e = i * 1024 + threadIdx.x;
+            const int64_t j = base + e;
+            s_va[slot(e)] = j < ntiles ? tsum[j] : 0.0;
+            s_vb[slot(e)] = j < ntiles ? tsq[j] : 0.0;
+        }
+        __syncthreads();
         double va[TOT_ITEMS], vb[TOT_ITEMS];
         double a = 0.0, b = 0.0;
 #pragma unroll
         for (int i = 0; i < TOT_ITEMS; ++i) {
-            va[i] = j0 + i < ntiles ? tsum[j0 + i] : 0.0; vb[i] = j0 + i < ntiles ? tsq[j0 + i] : 0.0;
+            va[i] = s_va[slot(threadIdx.x * TOT_ITEMS + i)]; vb[i] = s_vb[slot(threadIdx.x * TOT_ITEMS + i)];
             a += va[i]; b += vb[i];
         }
         double ia = a, ib = b;                          // inclusive warp scan of the threads' totals
@@ -80,11 +93,17 @@ k_scan_tile_totals(double* __restrict__ tsum, double* __restrict__ tsq, int64_t 
         double ea = carry_a + s_a[warp] + (ia - a), eb = carry_b + s_b[warp] + (ib - b);
 #pragma unroll
         for (int i = 0; i < TOT_ITEMS; ++i) {
-            if (j0 + i < ntiles) { tsum[j0 + i] = ea; tsq[j0 + i] = eb; }
+            s_va[slot(threadIdx.x * TOT_ITEMS + i)] = ea; s_vb[slot(threadIdx.x * TOT_ITEMS + i)] = eb;
             ea += va[i]; eb += vb[i];
         }
         __syncthreads();
         if (threadIdx.x == 1023) { carry_a = ea; carry_b = eb; }
+#pragma unroll
+        for (int i = 0; i < TOT_ITEMS; ++i) {
+            const int e = i * 1024 + threadIdx.x;
+            const int64_t j = base + e;
+            if (j < ntiles) { tsum[j] = s_va[slot(e)]; tsq[j] = s_vb[slot(e)]; }
+        }
         __syncthreads();
     }
 }
@@ -143,25 +162,34 @@ k_tile_scan(const T* __restrict__ x, int64_t n, const double* __restrict__ osum,
 // the scan across the lanes is five shuffle steps on 32-bit integers -- sums inside a 4096-sample tile fit:
 // 4096 * 255^2 < 2^31), with no trip through shared memory and no barrier between loads and stores, so the
 // 8 warps of a CTA stream independently.  Phase A reads 16 bytes per lane and sums with dp4a.
+// Tile offsets without a serial pass: phase A also adds every tile's totals into the accumulator of its GROUP of
+// 128 tiles (exact 64-bit integers); a tile of phase C then sums the accumulators of the groups in front of its
+// own (one warp, a few loads per lane) and the totals of the tiles in front of it inside its group (another warp).
+constexpr int SCAN_GROUP = 128;
+
+__device__ __forceinline__ uint4 mask_tail16(uint4 v, int keep) {         // zero the bytes from `keep` on (keep < 16)
+    unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int kb = keep - 4 * k;
+        w[k] = kb >= 4 ? w[k] : (kb <= 0 ? 0u : (w[k] & (0xffffffffu >> (8 * (4 - kb)))));
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+__device__ __forceinline__ void sums16(uint4 v, unsigned& a, unsigned& b) {
+    a = __dp4a(v.x, 0x01010101u, __dp4a(v.y, 0x01010101u, __dp4a(v.z, 0x01010101u, __dp4a(v.w, 0x01010101u, 0u))));
+    b = __dp4a(v.x, v.x, __dp4a(v.y, v.y, __dp4a(v.z, v.z, __dp4a(v.w, v.w, 0u))));
+}
+
 __global__ void __launch_bounds__(SCAN_THREADS)
-k_tile_totals_u8(const uint8_t* __restrict__ x, int64_t n, double* __restrict__ tsum, double* __restrict__ tsq) {
+k_tile_totals_u8(const uint8_t* __restrict__ x, int64_t n, uint2* __restrict__ tot, unsigned long long* __restrict__ grp) {
     __shared__ unsigned s_a[SCAN_THREADS / 32], s_b[SCAN_THREADS / 32];
     const int64_t j = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * 16;     // stream allocations carry 16 bytes of slack
     unsigned a = 0, b = 0;
     if (j < n) {
         uint4 v = __ldg(reinterpret_cast<const uint4*>(x + j));
-        if (j + 16 > n) {                            // mask the bytes past the end
-            const int keep = (int)(n - j);
-            unsigned w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int kb = keep - 4 * k;
-                w[k] = kb >= 4 ? w[k] : (kb <= 0 ? 0u : (w[k] & (0xffffffffu >> (8 * (4 - kb)))));
-            }
-            v = make_uint4(w[0], w[1], w[2], w[3]);
-        }
-        a = __dp4a(v.x, 0x01010101u, __dp4a(v.y, 0x01010101u, __dp4a(v.z, 0x01010101u, __dp4a(v.w, 0x01010101u, 0u))));
-        b = __dp4a(v.x, v.x, __dp4a(v.y, v.y, __dp4a(v.z, v.z, __dp4a(v.w, v.w, 0u))));
+        if (j + 16 > n) v = mask_tail16(v, (int)(n - j));
+        sums16(v, a, b);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
@@ -170,34 +198,41 @@ k_tile_totals_u8(const uint8_t* __restrict__ x, int64_t n, double* __restrict__ 
     if (threadIdx.x == 0) {
         unsigned ta = 0, tb = 0;
         for (int w = 0; w < SCAN_THREADS / 32; ++w) { ta += s_a[w]; tb += s_b[w]; }
-        tsum[blockIdx.x] = (double)ta; tsq[blockIdx.x] = (double)tb;
+        tot[blockIdx.x] = make_uint2(ta, tb);
+        atomicAdd(grp + 2 * (blockIdx.x / SCAN_GROUP), (unsigned long long)ta);
+        atomicAdd(grp + 2 * (blockIdx.x / SCAN_GROUP) + 1, (unsigned long long)tb);
     }
 }
 
 __global__ void __launch_bounds__(SCAN_THREADS)
-k_tile_scan_u8(const uint8_t* __restrict__ x, int64_t n, const double* __restrict__ osum, const double* __restrict__ osq,
+k_tile_scan_u8(const uint8_t* __restrict__ x, int64_t n, const uint2* __restrict__ tot, const unsigned long long* __restrict__ grp,
                double2* __restrict__ pfx) {
     constexpr int NW = SCAN_THREADS / 32, PER_WARP = SCAN_TILE / NW;        // 512 samples per warp
     __shared__ unsigned s_a[NW], s_b[NW];
+    __shared__ unsigned long long s_base[4];                                // group part and in-group part of (sum, sum of squares)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t w0 = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)warp * PER_WARP;
+    const int tile = blockIdx.x, g = tile / SCAN_GROUP;
+    const int64_t w0 = (int64_t)tile * SCAN_TILE + (int64_t)warp * PER_WARP;
+    if (warp == NW - 1) {                              // groups in front of this tile's group
+        unsigned long long a = 0, b = 0;
+        for (int i = lane; i < g; i += 32) { a += __ldg(grp + 2 * i); b += __ldg(grp + 2 * i + 1); }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+        if (lane == 0) { s_base[0] = a; s_base[1] = b; }
+    } else if (warp == NW - 2) {                       // tiles of the same group in front of this tile
+        unsigned long long a = 0, b = 0;
+        for (int i = g * SCAN_GROUP + lane; i < tile; i += 32) { const uint2 t = __ldg(tot + i); a += t.x; b += t.y; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+        if (lane == 0) { s_base[2] = a; s_base[3] = b; }
+    }
     {   // totals of the warps in front of this one inside the tile
         unsigned a = 0, b = 0;
         const int64_t j = w0 + lane * 16;
         if (j < n) {
             uint4 v = __ldg(reinterpret_cast<const uint4*>(x + j));
-            if (j + 16 > n) {
-                const int keep = (int)(n - j);
-                unsigned w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int kb = keep - 4 * k;
-                    w[k] = kb >= 4 ? w[k] : (kb <= 0 ? 0u : (w[k] & (0xffffffffu >> (8 * (4 - kb)))));
-                }
-                v = make_uint4(w[0], w[1], w[2], w[3]);
-            }
-            a = __dp4a(v.x, 0x01010101u, __dp4a(v.y, 0x01010101u, __dp4a(v.z, 0x01010101u, __dp4a(v.w, 0x01010101u, 0u))));
-            b = __dp4a(v.x, v.x, __dp4a(v.y, v.y, __dp4a(v.z, v.z, __dp4a(v.w, v.w, 0u))));
+            if (j + 16 > n) v = mask_tail16(v, (int)(n - j));
+            sums16(v, a, b);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
@@ -206,7 +241,7 @@ k_tile_scan_u8(const uint8_t* __restrict__ x, int64_t n, const double* __restric
     __syncthreads();
     unsigned cs = 0, cq = 0;                           // integer carry inside the tile (exact)
     for (int w = 0; w < warp; ++w) { cs += s_a[w]; cq += s_b[w]; }
-    const double bs = osum[blockIdx.x], bq = osq[blockIdx.x];
+    const double bs = (double)(s_base[0] + s_base[2]), bq = (double)(s_base[1] + s_base[3]);     // exact: < 2^53
     if (blockIdx.x == 0 && threadIdx.x == 0) pfx[0] = make_double2(0.0, 0.0);
 #pragma unroll 4
     for (int it = 0; it < PER_WARP / 32; ++it) {
@@ -250,25 +285,35 @@ k_gather_blocks(const T* __restrict__ x, int64_t n, const double2* __restrict__ 
     }
 }
 
+constexpr size_t kTotSmem = 2 * sizeof(double) * (TOT_SLAB + TOT_SLAB / TOT_ITEMS);
+int ensure_tot_smem() {
+    static bool attr_set = false;
+    if (!attr_set) {
+        SB_CUDA(cudaFuncSetAttribute(k_scan_tile_totals, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTotSmem));
+        attr_set = true;
+    }
+    return SB_OK;
+}
+
 int build_prefix_u8(sb_stream* s) {
     Ctx& c = ctx();
     const int64_t n = s->n;
     const int64_t ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
-    double* d_t = nullptr;
-    SB_TRY(pool_alloc((void**)&d_t, sizeof(double) * 2 * ntiles));
-    double* tsum = d_t; double* tsq = d_t + ntiles;
+    const int64_t ngroups = (ntiles + SCAN_GROUP - 1) / SCAN_GROUP;
+    unsigned char* d_t = nullptr;
+    const size_t grp_bytes = sizeof(unsigned long long) * 2 * ngroups;
+    SB_TRY(pool_alloc((void**)&d_t, grp_bytes + sizeof(uint2) * ntiles));
+    unsigned long long* grp = reinterpret_cast<unsigned long long*>(d_t);
+    uint2* tot = reinterpret_cast<uint2*>(d_t + grp_bytes);
     const uint8_t* x = static_cast<const uint8_t*>(s->d_raw);
+    SB_CUDA(cudaMemsetAsync(grp, 0, grp_bytes, c.stream));
     {
         ProfScope ps("scan_tile_totals");
-        k_tile_totals_u8<<<(unsigned)ntiles, SCAN_THREADS, 0, c.stream>>>(x, n, tsum, tsq);
-    }
-    {
-        ProfScope ps("scan_tile_offsets");
-        k_scan_tile_totals<<<1, 1024, 0, c.stream>>>(tsum, tsq, ntiles);
+        k_tile_totals_u8<<<(unsigned)ntiles, SCAN_THREADS, 0, c.stream>>>(x, n, tot, grp);
     }
     {
         ProfScope ps("scan_tiles");
-        k_tile_scan_u8<<<(unsigned)ntiles, SCAN_THREADS, 0, c.stream>>>(x, n, tsum, tsq, s->d_pfx);
+        k_tile_scan_u8<<<(unsigned)ntiles, SCAN_THREADS, 0, c.stream>>>(x, n, tot, grp, s->d_pfx);
     }
     SB_CUDA(cudaGetLastError());
     pool_free(d_t);            // reused only by later work on the same stream
@@ -288,9 +333,10 @@ int build_prefix(sb_stream* s) {
         ProfScope ps("scan_tile_totals");
         k_tile_totals<T><<<(unsigned)ntiles, SCAN_THREADS, 0, c.stream>>>(x, n, tsum, tsq);
     }
+    SB_TRY(ensure_tot_smem());
     {
         ProfScope ps("scan_tile_offsets");
-        k_scan_tile_totals<<<1, 1024, 0, c.stream>>>(tsum, tsq, ntiles);
+        k_scan_tile_totals<<<1, 1024, kTotSmem, c.stream>>>(tsum, tsq, ntiles);
     }
     {
         ProfScope ps("scan_tiles");
