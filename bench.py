@@ -395,6 +395,11 @@ def run_b200(args):
     bps = 1 if stype == 'uint8' else 4
     events_total = wl['events'] * (world if args.scaling == 'weak' else 1)
     root = rank == 0
+    if args.load_only:              # the loader leg alone (profiler captures of the HBM-bound kernels)
+        from sushi_b200 import _native
+        peaks = read_peaks()
+        print(json.dumps({'load': loader_leg(_native.lib(local_rank), float(peaks.get('hbm_gbs', 6650.0)), args)}), flush=True)
+        return
 
     src_h = dst_h = starts = ends = None
     if root:
@@ -601,6 +606,7 @@ def main():
     ap.add_argument('--cpu-budget', type=float, default=12.0, help='seconds of wall clock for the CPU baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-load-leg', action='store_true')
+    ap.add_argument('--load-only', action='store_true', help='run the loader leg alone')
     ap.add_argument('--load-minutes', type=float, default=90.0, help='length of the PCM the loader leg loads')
     ap.add_argument('--load-cpu-minutes', type=float, default=10.0, help='slice of it the oracle loader is timed on')
     ap.add_argument('--block', type=int, default=0, help='lag-block size override')

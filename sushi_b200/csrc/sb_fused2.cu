@@ -53,6 +53,11 @@ using namespace sbf;
 #ifndef SB_V2_SPECIAL_PREFETCH
 #define SB_V2_SPECIAL_PREFETCH 1
 #endif
+// Inverse FFT of the product spectrum: 1 = decimation in frequency with warp-local passes 2 and 3 (two CTA-wide
+// barriers per transform, see fft_passes_dif), 0 = the first version (Stockham passes, six barriers).
+#ifndef SB_V2_DIF
+#define SB_V2_DIF 1
+#endif
 
 namespace {
 
@@ -69,13 +74,25 @@ constexpr int QROW = kQuadRowF2 / 2;      // float4 per row
 __host__ __device__ constexpr int qa(int i) { return i < Q4 ? (i >> 8) * (2 * QBLK) + (i & (QBLK - 1)) : 2 * Q4; }       // A chunk of quad i
 __host__ __device__ constexpr int qm(int i) { return i < Q4 ? qa(i) + QBLK : 2 * Q4 + 1; }                              // M chunk of quad i
 static_assert(QROW >= 2 * Q4 + 2 && (QROW * 16) % 128 == 0, "row layout");
+#if SB_V2_DIF
+// FFT buffer as [16][16][32] chunks with strides (529, 33, 1): element n of the transform's input sits at
+// [n / 512][(n / 32) % 16][n % 32]; both strides are 1 mod 16, which makes every access pattern of the three passes
+// and of the epilogue hit sixteen distinct 8-byte banks per half warp (fft_passes_dif).
+constexpr int kDA = 529, kDB = 33;
+constexpr int QPHYS = 16 * kDA;           // physical chunks of the padded FFT buffer
+constexpr int kUU = kDA;                  // distance between elements n and n + 512
+#else
 constexpr int QPHYS = QCH + QCH / 16;     // physical chunks of the padded FFT buffer
+constexpr int kUU = 544;                  // distance between elements n and n + 512
+#endif
 
 struct PackedTables {
     const float4* tw2;    // [8][16]   (W256^(2a*k), W256^((2a+1)*k)) as (c0, s0, c1, s1), k = 0..15   (pass 2)
     const float4* tw3;    // [8][256]  same with W4096, k = 0..255                                  (pass 3)
     const float2* w8;     // [4096]    W8192^j                                                       (last radix-2 step)
     const float2* wb;     // [512]     exp(i*pi*t/B)                                                 (packing, per-thread base)
+    const float4* d1;     // [8][512]  (W8192^(2a*t), W8192^((2a+1)*t)), t = 0..511                  (DIF pass 1, after the butterfly)
+    const float4* d2;     // [8][32]   (W512^(2a*l), W512^((2a+1)*l)), l = 0..31                      (DIF pass 2, after the butterfly)
 };
 
 // exp(+i*pi*u/32), u = 0..7: the packing twiddle of quad i = t + 512u is wb[t] times this
@@ -139,7 +156,11 @@ __device__ __forceinline__ void dft16p(C2 (&v)[16]) {
 // (the register allocator does not keep the two pairs in one aligned quad, so a 128-bit store would cost four
 // MOVs; 64-bit accesses cost none).  One padding slot per 16 chunks makes the stride-16 scatter of pass 1 and
 // the epilogue's reads of chunks 2t, 2t+1 hit sixteen distinct 8-byte banks per half warp.
+#if SB_V2_DIF
+__device__ __forceinline__ constexpr int phys(int n) { return (n >> 9) * kDA + ((n >> 5) & 15) * kDB + (n & 31); }
+#else
 __device__ __forceinline__ constexpr int phys(int c) { return c + (c >> 4); }
+#endif
 struct Buf {
     float2* r; float2* i;
     __device__ __forceinline__ C2 ld(int p) const { return {r[p], i[p]}; }
@@ -292,6 +313,10 @@ __device__ __forceinline__ C2 special_quad(const float4* tp, const float4* xp, i
 // its multiply loop; afterwards the partitions are spread over the lanes and summed by the same shuffle tree as
 // special_quad (same arithmetic in the same order: bit-identical), reading shared memory instead of L2.
 constexpr int kSpecialBytes = 1024;                // (2 * 11 + 2) rows x 32 bytes fit
+// Templates of twelve or more partitions normally take the blocked multiply route; when that route is switched off
+// (sb_set_premac_mode(1)) they arrive here and their rows do not fit the area: those CTAs read the quad from L2
+// (special_quad) like the first kernel body.
+__device__ __forceinline__ bool special_fits(int P, int G) { return (2 * P + G - 1) * 32 <= kSpecialBytes; }
 __device__ __forceinline__ void special_prefetch(float4* s_sp, const float4* tp, const float4* xp, int P, int G,
                                                  int64_t k, int64_t nblk, int lane) {
     const int u0 = qa(Q4), u1 = qm(Q4);
@@ -406,6 +431,80 @@ __device__ __forceinline__ float4 fft_passes(const Buf& buf, int tid, const Pack
     return wt;
 }
 
+#if SB_V2_DIF
+// The same transform by decimation in frequency, n = 512a + 32b + 2c + m  ->  k = k1 + 16 k2 + 256 k3 + 4096 k4:
+//   pass 1  thread t, over a:  y[k1][t]  = W8192^(t k1) * sum_a x[a][t] W16^(a k1)       t = 32b + 2c + m
+//   pass 2  warp k1, lane l, over b:  z[k2][l] = W512^(l k2) * sum_b y[b][l] W16^(b k2)   l = 2c + m
+//   pass 3  warp k1, lane (k2, m), over c:  r[k3][m] = sum_c z[c][m] W16^(c k3)           (its twiddle W32^(m k3) and
+//           the last radix-2 step, of which only k4 = 0 carries valid lags, are the epilogue's:
+//           X[k1 + 16 k2 + 256 k3] = r[k3][0] + W32^k3 r[k3][1])
+// Every thread writes each pass's results over its own inputs (buffer [a|k1][b|k2][2(c|k3) + m]), so no pass needs a
+// barrier between its loads and its stores, and after pass 1 the sixteen 512-point transforms belong to one warp
+// each: passes 2 and 3 synchronise with __syncwarp only.  Two CTA-wide barriers per transform instead of six --
+// and, more important, the warps drift apart between them: one warp's shared-memory loads and stores overlap the
+// others' arithmetic instead of all sixteen alternating between the two pipes in lock step (ncu, round 2: the
+// Stockham passes spend 40 % of their time with the shared-memory pipe saturated and the arithmetic pipes idle, and
+// 40 % the other way round).  Entered after a barrier that published buf; ends with a barrier.
+template <int ID>
+__device__ __forceinline__ void fft_passes_dif(const Buf& buf, int tid, const PackedTables& tab, bool drain_cp_async) {
+    C2 v[16];
+    float4 tw[8];
+    const int lane = tid & 31, warp = tid >> 5;
+    {   // pass 1
+#pragma unroll
+        for (int a = 0; a < 8; ++a) tw[a] = __ldg(tab.d1 + a * 512 + tid);
+        const int at = warp * kDB + lane;                                   // phys(tid)
+#pragma unroll
+        for (int a = 0; a < 16; ++a) v[a] = buf.ld(at + kDA * a);
+        dft16p(v);
+        buf.st(at, v[0]);
+#pragma unroll
+        for (int k = 1; k < 16; ++k) {
+            const float4 t = tw[k >> 1];
+            buf.st(at + kDA * k, (k & 1) ? cmul_s(v[brev<16>(k)], t.z, t.w) : cmul_s(v[brev<16>(k)], t.x, t.y));
+        }
+#pragma unroll
+        for (int a = 0; a < 8; ++a) tw[a] = __ldg(tab.d2 + a * 32 + lane);
+        csync<ID>();
+    }
+    {   // pass 2: this warp's 512 points
+        const int at = warp * kDA + lane;
+#pragma unroll
+        for (int b = 0; b < 16; ++b) v[b] = buf.ld(at + kDB * b);
+        dft16p(v);
+        buf.st(at, v[0]);
+#pragma unroll
+        for (int k = 1; k < 16; ++k) {
+            const float4 t = tw[k >> 1];
+            buf.st(at + kDB * k, (k & 1) ? cmul_s(v[brev<16>(k)], t.z, t.w) : cmul_s(v[brev<16>(k)], t.x, t.y));
+        }
+        __syncwarp();
+    }
+    {   // pass 3: lane (k2 = lane % 16, m = lane / 16) of this warp
+        const int at = warp * kDA + (lane & 15) * kDB + (lane >> 4);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) v[c] = buf.ld(at + 2 * c);
+        dft16p(v);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) buf.st(at + 2 * k, v[brev<16>(k)]);
+        if (drain_cp_async) cp_async_commit_wait_all();     // the staged running sums landed long ago
+        csync<ID>();
+    }
+}
+#endif
+
+// The inverse transform the kernels call; the value it returns is the epilogue's twiddle pair when the Stockham passes
+// fetched it early (EPI 2), unused otherwise.
+template <int ID, int EPI>
+__device__ __forceinline__ float4 inverse_fft(const Buf& buf, int tid, const PackedTables& tab, bool drain_cp_async) {
+#if SB_V2_DIF
+    fft_passes_dif<ID>(buf, tid, tab, drain_cp_async);
+    return make_float4(0.f, 0.f, 0.f, 0.f);
+#else
+    return fft_passes<ID, EPI == 2 && SB_V2_MIDBAR>(buf, tid, tab, drain_cp_async);
+#endif
+}
+
 // EPI 2: the constants of a query every thread needs in finish_item -- sums of the template (two reads of its
 // running sums) and the two centres (two fp64 divisions) -- by ONE thread at the start of the CTA's work on the
 // query, through shared memory; the first version has all 512 threads fetch and divide them after the last FFT
@@ -460,9 +559,17 @@ __device__ __forceinline__ void finish_item(const Item& it, int tid, const Smem&
     const bool interior = j_blk >= jlo && j_blk + LB <= jhi;
 
     // chunks 2*tid, 2*tid+1 of every round: physical offsets and twiddles
+#if SB_V2_DIF
+    // chunk 1024c + 2tid + e = k1 + 16 k2 + 256 k3: k1 = 2(tid % 8) + e, k2 = (tid / 8) % 16, k3 = 4c + tid / 128; its
+    // two halves r[k3][0], r[k3][1] are neighbours, and the twiddle W32^k3 = W32^(tid/128) * W8^c depends on the warp only
+    const int ech = 2 * (tid & 7) * kDA + ((tid >> 3) & 15) * kDB + 2 * (tid >> 7);      // + kDA*e + 8*c; second half 1 further
+    const float4 wt = make_float4(kC32[tid >> 7], kS32[tid >> 7], kC32[tid >> 7], kS32[tid >> 7]);
+    (void)wt_in;
+#else
     const int ech = 2 * tid + (tid >> 3);                              // + 1088*c + e; O is 4352 further
     // W8192^(2tid), W8192^(2tid+1): requested by the last FFT pass already when it ran with MIDBAR (EPI 2)
     const float4 wt = (v2 && SB_V2_MIDBAR) ? wt_in : __ldg(reinterpret_cast<const float4*>(tab.w8) + tid);
+#endif
 
     float vf[ROUNDS][8];
     float tmin = kSent;
@@ -473,7 +580,11 @@ __device__ __forceinline__ void finish_item(const Item& it, int tid, const Smem&
         const int m0 = c * LAGS_PER_ROUND + tid * 8;
         const int64_t j0 = j_blk + m0;
         const int64_t jw = j_blk + c * LAGS_PER_ROUND + warp * 256;
-        if (jw >= jhi || jw + 256 <= jlo) {                            // no valid lag in this warp-round (warp-uniform)
+        // A warp-round without a valid lag (first / last lag block of a range) is skipped -- except by the trimmed body,
+        // which lets its border path mark all eight lags invalid instead: with no branch in front of them the shuffles
+        // of the scan below compile to plain SHFL (behind a warp-uniform branch the compiler brackets each pair with
+        // WARPSYNC.COLLECTIVE / ENDCOLLECTIVE: 160 instructions per lag block).
+        if (!v2 && (jw >= jhi || jw + 256 <= jlo)) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) vf[c][i] = kSent;
             continue;
@@ -482,7 +593,11 @@ __device__ __forceinline__ void finish_item(const Item& it, int tid, const Smem&
         float cc[8];
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
+#if SB_V2_DIF
+            const C2 E = buf.ld(ech + kDA * e + 8 * c), O = buf.ld(ech + kDA * e + 8 * c + 1);
+#else
             const C2 E = buf.ld(ech + 1088 * c + e), O = buf.ld(ech + 1088 * c + e + 4352);
+#endif
             float wc = e ? wt.z : wt.x, ws = e ? wt.w : wt.y;          // W8192^(2tid+e) ...
             {                                                          // ... times exp(2*pi*i*c/8)
                 const float h = 0.70710678118654752f;
@@ -634,8 +749,14 @@ __device__ __forceinline__ void finish_item(const Item& it, int tid, const Smem&
         const int m = (bit >> 3) * LAGS_PER_ROUND + tid * 8 + (bit & 7);
         const int64_t j = j_blk + m;
         const int jj = m >> 2;                                          // chunk of X'
+#if SB_V2_DIF
+        const int ca = (jj & 15) * kDA + ((jj >> 4) & 15) * kDB + 2 * (jj >> 8);
+        const C2 E = buf.ld(ca), O = buf.ld(ca + 1);
+        const float2 w = make_float2(kC32[jj >> 8], kS32[jj >> 8]);
+#else
         const C2 E = buf.ld(phys(jj)), O = buf.ld(phys(jj) + 4352);
         const float2 w = __ldg(tab.w8 + jj);
+#endif
         const bool second = (m & 2) != 0;                               // lags 4j+2, 4j+3 belong to v
         const float er = second ? E.r.y : E.r.x, ei = second ? E.i.y : E.i.x, orr = second ? O.r.y : O.r.x, oi = second ? O.i.y : O.i.x;
         const float xr = fmaf(orr, w.x, fmaf(oi, -w.y, er)), xi = fmaf(orr, w.y, fmaf(oi, w.x, ei));
@@ -732,7 +853,8 @@ k_match_packed(const float4* __restrict__ That, int64_t part_first,
         const float2 wbase = __ldg(tab.wb + tid);
         const int tm = (T - tid) & (T - 1);           // mirrored chunks C[B/2 - i] live in thread tm's column
         const int col = phys(tid), mcol = phys(tm);
-        if (EPI == 2 && SB_V2_SPECIAL_PREFETCH && warp == NW - 1) special_prefetch(s_sp, tp, xp, d.P, 1, it.k, nblk, lane);
+        const bool sp_pref = EPI == 2 && SB_V2_SPECIAL_PREFETCH && special_fits(d.P, 1);
+        if (sp_pref && warp == NW - 1) special_prefetch(s_sp, tp, xp, d.P, 1, it.k, nblk, lane);
         constexpr int U = 4;                          // quads in flight per thread
 #pragma unroll 1
         for (int half = 0; half < 2; ++half) {
@@ -760,14 +882,14 @@ k_match_packed(const float4* __restrict__ That, int64_t part_first,
                 const float s = wbase.x * kS64[uu] + wbase.y * kC64[uu];
                 C2 lo, hi;
                 pack_quad(acc[u].aR, acc[u].aI, acc[u].mR, acc[u].mI, c, s, lo, hi);
-                buf.st(col + 544 * uu, lo);                       // C[i]
+                buf.st(col + kUU * uu, lo);                       // C[i]
                 // C[B/2 - i]: chunk (T - tid) + 512*(15 - uu), or 512*(16 - uu) for tid = 0 (none for i = 0)
-                if (tid != 0) buf.st(mcol + 544 * (15 - uu), hi);
-                else if (uu != 0) buf.st(mcol + 544 * (16 - uu), hi);
+                if (tid != 0) buf.st(mcol + kUU * (15 - uu), hi);
+                else if (uu != 0) buf.st(mcol + kUU * (16 - uu), hi);
             }
         }
         if (warp == NW - 1) {                       // the self-mirrored quad i = B/4
-            if constexpr (EPI == 2 && SB_V2_SPECIAL_PREFETCH) {
+            if (sp_pref) {
                 cp_async_commit_wait_all();
                 __syncwarp();
                 const C2 lo = special_from_smem(s_sp, d.P, 0, lane);
@@ -781,7 +903,7 @@ k_match_packed(const float4* __restrict__ That, int64_t part_first,
     csync<0>();
 
     // ---------------- 3. inverse FFT, 4. epilogue ---------------------------------------------
-    const float4 wt0 = fft_passes<0, EPI == 2 && SB_V2_MIDBAR>(buf, tid, tab, is_u8);
+    const float4 wt0 = inverse_fft<0, EPI>(buf, tid, tab, is_u8);
     finish_item<S, 0, EPI>(it, tid, sm, s_bar, 0u, s_best, s_min, s_w0, img, img_n, ipfx, tpfx, tab, keys, curve_out, [] {}, wt0);
 }
 
@@ -796,9 +918,9 @@ __device__ __forceinline__ void unpark(uint32_t tsrc, const Buf& buf, int col, i
             const int uu = 2 * c4 + h;
             const C2 lo = {make_float2(v[8 * h + 0], v[8 * h + 1]), make_float2(v[8 * h + 2], v[8 * h + 3])};
             const C2 hi = {make_float2(v[8 * h + 4], v[8 * h + 5]), make_float2(v[8 * h + 6], v[8 * h + 7])};
-            buf.st(col + 544 * uu, lo);
-            if (tid != 0) buf.st(mcol + 544 * (15 - uu), hi);
-            else if (uu != 0) buf.st(mcol + 544 * (16 - uu), hi);
+            buf.st(col + kUU * uu, lo);
+            if (tid != 0) buf.st(mcol + kUU * (15 - uu), hi);
+            else if (uu != 0) buf.st(mcol + kUU * (16 - uu), hi);
         }
     };
     if (BATCH) {
@@ -874,7 +996,8 @@ k_match_pair(const float4* __restrict__ That, int64_t part_first,
         const float4* tp = That + (d.partBase - part_first) * (int64_t)R::STRIDE;
         const float4* xp = Xhat + k * (int64_t)R::STRIDE;
         const float2 wbase = __ldg(tab.wb + tid);
-        if (EPI == 2 && SB_V2_SPECIAL_PREFETCH && warp == NW - 1) special_prefetch(s_sp, tp, xp, d.P, 2, k, nblk, lane);
+        const bool sp_pref = EPI == 2 && SB_V2_SPECIAL_PREFETCH && special_fits(d.P, 2);
+        if (sp_pref && warp == NW - 1) special_prefetch(s_sp, tp, xp, d.P, 2, k, nblk, lane);
         constexpr int U = 2;                          // quads in flight per thread (two accumulator sets each)
 #pragma unroll 1
         for (int grp = 0; grp < 8 / U; ++grp) {
@@ -911,15 +1034,15 @@ k_match_pair(const float4* __restrict__ That, int64_t part_first,
                 const float s = wbase.x * kS64[uu] + wbase.y * kC64[uu];
                 C2 lo, hi;
                 pack_quad(a0[u].aR, a0[u].aI, a0[u].mR, a0[u].mI, c, s, lo, hi);
-                buf.st(col + 544 * uu, lo);                       // C[i]
-                if (tid != 0) buf.st(mcol + 544 * (15 - uu), hi); // C[B/2 - i]
-                else if (uu != 0) buf.st(mcol + 544 * (16 - uu), hi);
+                buf.st(col + kUU * uu, lo);                       // C[i]
+                if (tid != 0) buf.st(mcol + kUU * (15 - uu), hi); // C[B/2 - i]
+                else if (uu != 0) buf.st(mcol + kUU * (16 - uu), hi);
                 pack_quad(a1[u].aR, a1[u].aI, a1[u].mR, a1[u].mI, c, s, lo, hi);
                 tmem_st8(tcol + (uint32_t)(uu * 8), lo.r.x, lo.r.y, lo.i.x, lo.i.y, hi.r.x, hi.r.y, hi.i.x, hi.i.y);
             }
         }
         if (warp == NW - 1) {                         // the self-mirrored quad i = B/4 of both items
-            if constexpr (EPI == 2 && SB_V2_SPECIAL_PREFETCH) {
+            if (sp_pref) {
                 cp_async_commit_wait_all();
                 __syncwarp();
                 const C2 lo = special_from_smem(s_sp, d.P, 0, lane);
@@ -940,7 +1063,7 @@ k_match_pair(const float4* __restrict__ That, int64_t part_first,
     csync<0>();
 
     // ---------------- first item: inverse FFT + epilogue ---------------------------------------
-    const float4 wt0 = fft_passes<0, EPI == 2 && SB_V2_MIDBAR>(buf, tid, tab, is_u8);
+    const float4 wt0 = inverse_fft<0, EPI>(buf, tid, tab, is_u8);
     finish_item<S, 0, EPI>(it0, tid, sm, s_bar, 0u, s_best, s_min, s_w0, img, img_n, ipfx, tpfx, tab, keys, curve_out,
                       [&] { if (is_u8 && has2) stage_inputs(it1, tid, reinterpret_cast<const uint8_t*>(img), img_n, ipfx, sm, s_bar); }, wt0);
 
@@ -949,7 +1072,7 @@ k_match_pair(const float4* __restrict__ That, int64_t part_first,
         unpark<EPI == 2>(tcol, buf, col, mcol, tid);
         if (tid == (NW - 1) * 32) buf.st(phys(Q4), sp1);
         csync<0>();
-        const float4 wtj = fft_passes<0, EPI == 2 && SB_V2_MIDBAR>(buf, tid, tab, is_u8);
+        const float4 wtj = inverse_fft<0, EPI>(buf, tid, tab, is_u8);
         finish_item<S, 0, EPI>(it1, tid, sm, s_bar, 1u, s_best, s_min, s_w0, img, img_n, ipfx, tpfx, tab, keys, curve_out, [] {}, wtj);
     }
     tmem_fence_before();
@@ -1050,35 +1173,39 @@ size_t packed_smem_bytes(int epi = 1) {      // epilogue 2 keeps the runs' exact
                     : kSmemCommon + 8 + QNW * sizeof(unsigned long long) + QNW * sizeof(float) + 64;
 }
 
-// Values of the four tables of PackedTables, in one array: offsets of tw2, tw3, w8, wb in `off` (floats)
-std::vector<float> packed_table_values(size_t (&off)[4]) {
+// Values of the tables of PackedTables, in one array: offsets of tw2, tw3, w8, wb, d1, d2 in `off` (floats)
+constexpr int kPackedTableCount = 6;
+std::vector<float> packed_table_values(size_t (&off)[kPackedTableCount]) {
     const double pi = 3.14159265358979323846;
-    const size_t n2 = 8 * 16 * 4, n3 = 8 * 256 * 4, n8 = 4096 * 2, nb = 512 * 2;
-    off[0] = 0; off[1] = n2; off[2] = n2 + n3; off[3] = n2 + n3 + n8;
-    std::vector<float> h(n2 + n3 + n8 + nb);
-    for (int a = 0; a < 8; ++a)
-        for (int k = 0; k < 16; ++k)
-            for (int e = 0; e < 2; ++e) {
-                const double ang = 2.0 * pi * (2 * a + e) * k / 256.0;
-                h[((size_t)a * 16 + k) * 4 + 2 * e] = (float)cos(ang); h[((size_t)a * 16 + k) * 4 + 2 * e + 1] = (float)sin(ang);
-            }
-    for (int a = 0; a < 8; ++a)
-        for (int k = 0; k < 256; ++k)
-            for (int e = 0; e < 2; ++e) {
-                const double ang = 2.0 * pi * (2 * a + e) * k / 4096.0;
-                h[n2 + ((size_t)a * 256 + k) * 4 + 2 * e] = (float)cos(ang); h[n2 + ((size_t)a * 256 + k) * 4 + 2 * e + 1] = (float)sin(ang);
-            }
-    for (int j = 0; j < 4096; ++j) { h[n2 + n3 + 2 * j] = (float)cos(2.0 * pi * j / 8192.0); h[n2 + n3 + 2 * j + 1] = (float)sin(2.0 * pi * j / 8192.0); }
-    for (int t = 0; t < 512; ++t) { h[n2 + n3 + n8 + 2 * t] = (float)cos(pi * t / QB); h[n2 + n3 + n8 + 2 * t + 1] = (float)sin(pi * t / QB); }
+    const size_t n2 = 8 * 16 * 4, n3 = 8 * 256 * 4, n8 = 4096 * 2, nb = 512 * 2, nd1 = 8 * 512 * 4, nd2 = 8 * 32 * 4;
+    off[0] = 0; off[1] = n2; off[2] = n2 + n3; off[3] = n2 + n3 + n8; off[4] = off[3] + nb; off[5] = off[4] + nd1;
+    std::vector<float> h(off[5] + nd2);
+    // (W_N^((2a)*k), W_N^((2a+1)*k)) as (c0, s0, c1, s1), a = 0..7, k = 0..K-1
+    auto pairs = [&](size_t at, int K, double N) {
+        for (int a = 0; a < 8; ++a)
+            for (int k = 0; k < K; ++k)
+                for (int e = 0; e < 2; ++e) {
+                    const double ang = 2.0 * pi * (double)((2 * a + e) * k) / N;
+                    h[at + ((size_t)a * K + k) * 4 + 2 * e] = (float)cos(ang); h[at + ((size_t)a * K + k) * 4 + 2 * e + 1] = (float)sin(ang);
+                }
+    };
+    pairs(off[0], 16, 256.0);
+    pairs(off[1], 256, 4096.0);
+    for (int j = 0; j < 4096; ++j) { h[off[2] + 2 * j] = (float)cos(2.0 * pi * j / 8192.0); h[off[2] + 2 * j + 1] = (float)sin(2.0 * pi * j / 8192.0); }
+    for (int t = 0; t < 512; ++t) { h[off[3] + 2 * t] = (float)cos(pi * t / QB); h[off[3] + 2 * t + 1] = (float)sin(pi * t / QB); }
+    pairs(off[4], 512, 8192.0);
+    pairs(off[5], 32, 512.0);
     return h;
 }
 
-PackedTables packed_tables_at(const float* base, const size_t (&off)[4]) {
+PackedTables packed_tables_at(const float* base, const size_t (&off)[kPackedTableCount]) {
     PackedTables t;
     t.tw2 = reinterpret_cast<const float4*>(base + off[0]);
     t.tw3 = reinterpret_cast<const float4*>(base + off[1]);
     t.w8 = reinterpret_cast<const float2*>(base + off[2]);
     t.wb = reinterpret_cast<const float2*>(base + off[3]);
+    t.d1 = reinterpret_cast<const float4*>(base + off[4]);
+    t.d2 = reinterpret_cast<const float4*>(base + off[5]);
     return t;
 }
 
@@ -1088,7 +1215,7 @@ PackedTables g_ptab;
 
 int ensure_packed_tables(PackedTables* out) {
     if (!g_ptab_dev) {
-        size_t off[4];
+        size_t off[kPackedTableCount];
         const std::vector<float> h = packed_table_values(off);
         SB_CUDA(cudaMalloc(&g_ptab_dev, h.size() * sizeof(float)));
         SB_CUDA(cudaMemcpy(g_ptab_dev, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));

@@ -312,25 +312,52 @@ class ShardedMatcher(object):
                               all=(toff, tlen, lag0, nlags))
         return self.last_plan
 
-    def run_planned(self):
-        """The timed part on device buffers: broadcast both streams, match this rank's shard, all-gather.
-        Results stay in the backend buffer (rank-major, padded); read them with gather_results()."""
-        p = self.last_plan
+    def open_resident(self):
+        """Broadcast both streams once and keep them open on every rank: later run_planned() calls match against
+        the resident streams (running sums and block spectra are built once).  This is how the sequential solver
+        and the window sweep (BASELINE config 5) issue many batches against one pair of streams."""
+        self.close_resident()
         comm, be = self.comm, self.backend
         comm.broadcast(self._bufs[0], self._nbytes[0], self.root, 0)
-        comm.broadcast(self._bufs[1], self._nbytes[1], self.root, 1)       # overlaps the source stream's running sums
+        comm.broadcast(self._bufs[1], self._nbytes[1], self.root, 1)
         comm.wait(0)
         src = be.open_stream(self._bufs[0], self.geom[0], self.sample_type)
         comm.wait(1)
         dst = be.open_stream(self._bufs[1], self.geom[1], self.sample_type)
+        self._resident = (src, dst)
+
+    def close_resident(self):
+        res = getattr(self, '_resident', None)
+        if res is not None:
+            self.backend.close_stream(res[0])
+            self.backend.close_stream(res[1])
+        self._resident = None
+
+    def run_planned(self):
+        """The timed part on device buffers: broadcast both streams, match this rank's shard, all-gather (with
+        resident streams, open_resident(): the last two only).  Results stay in the backend buffer (rank-major,
+        padded); read them with gather_results()."""
+        p = self.last_plan
+        comm, be = self.comm, self.backend
+        resident = getattr(self, '_resident', None)
+        if resident is not None:
+            src, dst = resident
+        else:
+            comm.broadcast(self._bufs[0], self._nbytes[0], self.root, 0)
+            comm.broadcast(self._bufs[1], self._nbytes[1], self.root, 1)       # overlaps the source stream's running sums
+            comm.wait(0)
+            src = be.open_stream(self._bufs[0], self.geom[0], self.sample_type)
+            comm.wait(1)
+            dst = be.open_stream(self._bufs[1], self.geom[1], self.sample_type)
         cap = p['cap']
         send = self._res                                                   # [cap x int64 idx][cap x float32 diff]
         if p['hi'] > p['lo']:
             be.match(dst, src, p['shard'], send, be.offset(send, 8 * cap))
         if cap:
             comm.all_gather(send, be.offset(self._res, 12 * cap), 12 * cap)
-        be.close_stream(src)
-        be.close_stream(dst)
+        if resident is None:
+            be.close_stream(src)
+            be.close_stream(dst)
 
     def gather_results(self):
         p = self.last_plan

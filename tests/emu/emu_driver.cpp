@@ -81,7 +81,7 @@ void run_cta(const std::function<void(int)>& body) {
 
 extern "C" {
 
-int emu_table_floats(void) { size_t off[4]; return (int)packed_table_values(off).size(); }
+int emu_table_floats(void) { size_t off[kPackedTableCount]; return (int)packed_table_values(off).size(); }
 int emu_smem_bytes(void) { return (int)packed_smem_bytes(2) + 16; }
 int emu_query_desc_bytes(void) { return (int)sizeof(sb::QueryDesc); }
 int emu_quad_row_floats(void) { return QROW * 4; }
@@ -91,7 +91,7 @@ int emu_quad_row_floats(void) { return QROW * 4; }
 int emu_run(int kernel, int epi, int is_u8, const float* That, int64_t part_first, const float* Xhat, int64_t nblk,
             const void* img, int64_t img_n, const double* ipfx, const double* tpfx, const void* desc,
             const int* cta_query, int64_t first, int n_ctas, unsigned long long* keys, float* curve_out) {
-    static size_t off[4];
+    static size_t off[kPackedTableCount];
     static const std::vector<float> tables = packed_table_values(off);
     const PackedTables tab = packed_tables_at(tables.data(), off);
     const float4* T4 = reinterpret_cast<const float4*>(That);

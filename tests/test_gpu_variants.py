@@ -131,3 +131,26 @@ def test_pairs_are_bit_identical_to_single_lag_blocks(gpu_lib, epilogue, stype):
         epilogue(2, engine)
         res[engine] = dst.find_substream_batch(src, starts, ends, starts, win)
     assert np.array_equal(res[5][0], res[4][0]) and np.array_equal(res[5][1], res[4][1])
+
+
+@pytest.mark.parametrize('engine', [4, 5])
+def test_many_partition_templates_without_the_blocked_route(gpu_lib, epilogue, engine):
+    """sb_set_premac_mode(1) sends templates of twelve and more partitions (here 30 s = 22 partitions) through the
+    packed kernels, whose staging area for the self-mirrored quad holds 32 rows: those CTAs must read the quad from
+    L2 instead of writing past the area.  Same answers as the default route to FFT rounding, and
+    the oracle's within the usual bar."""
+    rs, rd, src, dst = _streams(200.0, 13)
+    starts = np.array([20.5, 61.25, 110.0])
+    ends = starts + np.array([30.0, 17.0, 24.5])         # 22, 13 and 18 partitions
+    win = np.full(3, 40.0)
+    epilogue(2, engine)
+    want = dst.find_substream_batch(src, starts, ends, starts, win)
+    _native.check(gpu_lib.sb_set_premac_mode(1))
+    try:
+        got = dst.find_substream_batch(src, starts, ends, starts, win)
+    finally:
+        _native.check(gpu_lib.sb_set_premac_mode(0))
+    assert np.abs(got[0] - want[0]).max() <= 2e-6 and np.abs(got[1] - want[1]).max() <= 1.0 / 12000 + 1e-9
+    for q in range(3):
+        d_ref, t_ref = rd.find_substream(rs.get_substream(starts[q], ends[q]), starts[q], 40.0)
+        assert abs(float(got[0][q]) - float(d_ref)) <= 1e-5 and abs(got[1][q] - t_ref) <= 1.0 / 12000 + 1e-9

@@ -369,3 +369,23 @@ def test_emulated_random_queries_all_variants_agree(emu, seed):
         assert np.array_equal(d, d0) and np.array_equal(i, i0), (seed, kernel, epi, queries)
     for q, t in enumerate(truth):
         assert abs(float(d0[q]) - float(t.min())) <= 3e-6 and abs(int(i0[q]) - int(t.argmin())) <= 1, (seed, q, queries[q])
+
+
+def test_emulated_many_partitions_do_not_overrun_the_special_area(emu):
+    """A template of 13 partitions through the packed kernels (what sb_set_premac_mode(1) allows): 2P + G - 1 rows
+    do not fit the 32-row staging area of the self-mirrored quad, so these CTAs must read it from L2 -- same
+    answers as the first kernel body (which always does), bit for bit, and the closed form's."""
+    n_img = 16 * B
+    img = programme(n_img, 31)
+    rng = np.random.default_rng(32)
+    src = np.clip(np.roll(img, -500).astype(np.int32) + rng.integers(-4, 5, n_img), 0, 255).astype(np.uint8)
+    n = 12 * B + 1234                                           # P = 13
+    c = Case(emu, img, src, [(3000, n, 2000, 2 * B + 100)], np.uint8)
+    t = c.truth()[0]
+    ref = None
+    for kernel in (0, 1):
+        for epi in (1, 2):
+            d, i, cur = c.run(kernel, epi, curves=True)
+            assert np.abs(cur - t).max() <= 3e-6 and i[0] == int(t.argmin()) == 3500 - 2000
+            ref = ref or (d, i, cur)
+            assert np.array_equal(ref[2], cur) and ref[0][0] == d[0] and ref[1][0] == i[0]

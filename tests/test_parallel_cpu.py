@@ -86,10 +86,21 @@ def _worker(rank, world, port, out_path, count):
         diffs, times = m.find_batch(starts, ends, starts, np.full(len(starts), 2.0))
         want = [rd.find_substream(rs.get_substream(a, b), a, 2.0) for a, b in zip(starts, ends)]
         ok = all(float(d) == float(w[0]) and t == w[1] for d, t, w in zip(diffs, times, want)) and len(diffs) == count
+        # the same list again against RESIDENT streams (one broadcast, then batches): identical answers
+        m.open_resident()
+        d2, t2 = m.find_batch(starts, ends, starts, np.full(len(starts), 2.0))
+        d3, t3 = m.find_batch(starts[::-1].copy(), ends[::-1].copy(), starts[::-1].copy(), np.full(len(starts), 2.0))
+        m.close_resident()
+        ok = ok and np.array_equal(d2, diffs) and np.array_equal(t2, times) and np.array_equal(d3[::-1], diffs)
         np.savez(out_path, ok=np.array([ok]), shift=times - starts, lo_hi=np.array([m.last_plan['lo'], m.last_plan['hi']]))
     else:
         m.set_streams()
         diffs, times = m.find_batch()
+        m.open_resident()
+        d2, t2 = m.find_batch()
+        m.find_batch()
+        m.close_resident()
+        assert np.array_equal(d2, diffs) and np.array_equal(t2, times)
         assert len(diffs) == count and m.geom[1].total_samples == 16 * 12000 + 240000 and m.sample_type == 'uint8'
         np.savez(out_path + '.rank%d.npz' % rank, diffs=diffs, times=times, lo_hi=np.array([m.last_plan['lo'], m.last_plan['hi']]))
     dist.barrier()

@@ -1,13 +1,16 @@
 #!/bin/bash
 # One GPU pass (run under gpurun from the repo root, one B200): the -m gpu tests, the default bench line (config 3),
-# the config-2 line, the ncu launch list of the bench command and one full capture of the dominant kernel.
-# Everything lands in gpurun_out/ under the tag given as $1.
+# the config-2 line, the ncu launch list of the bench command, one full capture of the dominant kernel and one of
+# the loader / scan kernels.  Everything lands in gpurun_out/ under the tag given as $1.
 T=${1:-r2}
 O=gpurun_out
 mkdir -p $O
-timeout 900 python -m pytest tests -x -q -m gpu > $O/pytest_gpu_$T.txt 2>&1; tail -5 $O/pytest_gpu_$T.txt
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O/smi_$T.txt
+python -c 'import bench; print(bench.kernel_source_hash())' > $O/src_hash_$T.txt
+( time timeout 900 python -m pytest tests -x -q -m gpu ) > $O/pytest_gpu_$T.txt 2>&1; tail -4 $O/pytest_gpu_$T.txt
 timeout 600 python bench.py > $O/bench_${T}_config3.json 2> $O/bench_${T}_config3.err; tail -2 $O/bench_${T}_config3.err; head -c 1500 $O/bench_${T}_config3.json; echo
-timeout 300 python bench.py --workload config2 --steps 20 --no-load-leg > $O/bench_${T}_config2.json 2> $O/bench_${T}_config2.err; head -c 400 $O/bench_${T}_config2.json; echo
+timeout 300 python bench.py --workload config2 --steps 20 --no-load-leg --cpu-budget 6 > $O/bench_${T}_config2.json 2> $O/bench_${T}_config2.err; head -c 400 $O/bench_${T}_config2.json; echo
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file $O/launches_$T.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-load-leg > $O/ncu_launches_$T.log 2>&1
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_match_pair -s 3 -c 1 -o $O/pair_config3_$T python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-load-leg > $O/ncu_full_$T.log 2>&1; tail -2 $O/ncu_full_$T.log
-nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv
+timeout 300 ncu --set full --clock-control none --import-source on -k 'regex:k_decode_resample_pad|k_select_fine|k_normalise|k_tile_totals_u8|k_tile_scan_u8' -c 5 -o $O/loader_$T python bench.py --load-only --no-cpu-baseline > $O/ncu_loader_$T.log 2>&1; tail -2 $O/ncu_loader_$T.log
+ls -la $O | tail -20

@@ -3,7 +3,7 @@
 profiles/traffic.json (DRAM bytes per launch) + a short text summary under profiles/.
     ncu --set full --clock-control none --import-source on -k regex:k_match_pair -s 3 -c 1 \
         -o gpurun_out/pair_bench python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-load-leg    (GPU box)
-    python tools/ncu_traffic.py gpurun_out/pair_bench.ncu-rep config3 uint8 match_fused 1   (here, same source tree)
+    python tools/ncu_traffic.py gpurun_out/pair_bench.ncu-rep config3 uint8 match_fused 1 [src_hash]   (here)
 The entry is stamped with the hash of the CUDA sources (bench.kernel_source_hash): bench.py uses a capture only
 for the source it was taken from and prints traffic = null with the reason otherwise.
 """
@@ -16,6 +16,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 rep, workload, stype, kclass, ngpus = sys.argv[1:6]
+src_hash = sys.argv[6] if len(sys.argv) > 6 else None      # hash of the CUDA sources the capture was taken from (gpu_pass.sh writes it)
 sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
@@ -48,7 +49,7 @@ keep = ['gpu__time_duration.sum', 'launch__grid_size', 'launch__registers_per_th
         'sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active',
         'sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active', 'smsp__inst_executed.sum',
         'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active']
-tr[key] = {'dram_bytes_per_launch': dram, 'report': os.path.basename(rep), 'src_hash': bench.kernel_source_hash(),
+tr[key] = {'dram_bytes_per_launch': dram, 'report': os.path.basename(rep), 'src_hash': src_hash or bench.kernel_source_hash(),
            'metrics': {k: ' '.join(d[k]) for k in keep if k in d}}
 json.dump(tr, open(out_path, 'w'), indent=1, sort_keys=True)
 print(key, 'dram bytes/launch', dram)

@@ -29,7 +29,8 @@ REGIONS = [
     ('epilogue: block minimum', 'finish_item', 'const float my_min = tmin;', 'unsigned long long cand = 0;'),
     ('epilogue: candidates, exact, merge', 'finish_item', 'unsigned long long cand = 0;', '// ---------------------------------------------------------------- kernel A:'),
     ('epilogue: setup', 'finish_item', '__device__ __forceinline__ void finish_item', 'correlation at the 8 lags'),
-    ('fft passes', 'fft_passes', '__device__ __forceinline__ void fft_passes', '// Window sums, fp32 screening'),
+    ('fft passes (DIF)', 'fft_passes_dif', '__device__ __forceinline__ void fft_passes_dif', '// The inverse transform the kernels call'),
+    ('fft passes (Stockham)', 'fft_passes', '__device__ __forceinline__ float4 fft_passes', '// The same transform by decimation in frequency'),
     ('stage inputs', 'stage_inputs', '__device__ __forceinline__ void stage_inputs', '// Y += conj(T) * X on both slots'),
 ]
 
