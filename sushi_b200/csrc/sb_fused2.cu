@@ -501,7 +501,7 @@ __device__ __forceinline__ float4 inverse_fft(const Buf& buf, int tid, const Pac
     fft_passes_dif<ID>(buf, tid, tab, drain_cp_async);
     return make_float4(0.f, 0.f, 0.f, 0.f);
 #else
-    return fft_passes<ID, EPI == 2 && SB_V2_MIDBAR>(buf, tid, tab, drain_cp_async);
+    return fft_passes<ID, EPI >= 2 && SB_V2_MIDBAR>(buf, tid, tab, drain_cp_async);
 #endif
 }
 
@@ -532,7 +532,8 @@ __device__ __forceinline__ void finish_item(const Item& it, int tid, const Smem&
                                             float4 wt_in = make_float4(0.f, 0.f, 0.f, 0.f)) {
     constexpr int B = QB, NW = QNW, LB = QB, ROUNDS = kRounds, LAGS_PER_ROUND = kLagsPerRound;
     constexpr bool is_u8 = sizeof(S) == 1;
-    constexpr bool v2 = EPI == 2 && is_u8;                 // trimmed screening (see the comment at its loop)
+    constexpr bool v2 = EPI >= 2 && is_u8;                 // trimmed screening (see the comment at its loop)
+    constexpr bool v3 = EPI == 3 && is_u8;                 // run-level bounds first, per-lag screening only where a run can hold the minimum
     constexpr float kSent = v2 ? 3.0e38f : 2.0f;           // screening value of a lag outside the query's range
     const float* img32 = reinterpret_cast<const float*>(img);
     const Buf& buf = sm.buf;
@@ -574,6 +575,13 @@ __device__ __forceinline__ void finish_item(const Item& it, int tid, const Smem&
     float vf[ROUNDS][8];
     float tmin = kSent;
     const float m2s = -2.0f * f_scale, m2b = -2.0f * f_b;             // v2 screening
+    // v3: over the 8 lags of a run the window terms of the screening value, rq_i - 2b*rs_i = sum over the samples that
+    // left / entered the window of (hi - b)^2 - (lo - b)^2, move by at most 7 * max(b, 255 - b)^2 (f_delta, with 2 % and
+    // 1024 on top: that swallows every fp32 rounding of the loop); the window energy itself by at most kRunQ
+    constexpr float kRunQ = 7.0f * 255.0f * 255.0f;
+    const float f_bm = fmaxf(f_b, 255.0f - f_b);
+    const float f_delta = 1.02f * 7.0f * f_bm * f_bm + 1024.0f;
+    float run_lb[ROUNDS];                                                  // v3: lower bound of each run's screening values
     if (is_u8) mbar_wait(s_bar, bar_parity);
 #pragma unroll
     for (int c = 0; c < ROUNDS; ++c) {
@@ -657,6 +665,24 @@ __device__ __forceinline__ void finish_item(const Item& it, int tid, const Smem&
             f_w0q = (float)(p_hi.y - p_lo.y);
             f_k0 = (float)(b * (p_hi.x - p_lo.x) + k_const);
         }
+        if constexpr (v3) {
+            // Run-level bounds.  The screening value of lag i of this run is
+            //   v'_i = (A + rq_i - 2b*rs_i - 2*scale*cc_i) * rsqrt(w0q + rq_i),   |rq_i - 2b*rs_i| <= delta, |rq_i| <= kRunQ,
+            // so with cmax = max cc_i:   v'_i >= (A - delta - 2*scale*cmax) * rsqrt(w0q + kRunQ)   for every i  (lb), and
+            // at the lag of cmax          v'   <= (A + delta - 2*scale*cmax) * rsqrt(w0q - kRunQ)                  (ub).
+            // The block minimum of ub is an upper bound of the block's smallest screening value: only runs whose lb
+            // does not exceed it (plus the margin) can hold a candidate, and only those go through the per-lag loop
+            // -- a few per lag block instead of all 2048, which was 40 % of the instructions of this function.
+            const float cmax = fmaxf(fmaxf(fmaxf(cc[0], cc[1]), fmaxf(cc[2], cc[3])), fmaxf(fmaxf(cc[4], cc[5]), fmaxf(cc[6], cc[7])));
+            const bool some = interior || (j0 < jhi && j0 + 8 > jlo);          // the run has a lag of the range
+            const bool inside = interior || (j0 >= jlo && j0 + 8 <= jhi);      // all of its lags are
+            const float lbn = fmaf(cmax, m2s, f_A - f_delta), ubn = lbn + 2.0f * f_delta;
+            const float lbv = lbn * rsqrt_fast(f_w0q + kRunQ) * 0.999999f;
+            run_lb[c] = !some ? kSent : (lbn >= 0.f ? lbv : -kSent);
+            const float ubv = ubn * rsqrt_fast(f_w0q - kRunQ) * 1.000001f;
+            if (inside && f_w0q > 4.0f * kRunQ && ubn >= 0.f) tmin = fminf(tmin, ubv);
+            continue;
+        }
         if constexpr (v2) {
             // Trimmed screening (uint8).  The screening values only select which lags get the exact fp64
             // evaluation below, so they may be any quantity that (a) orders the lags like the true value to within
@@ -736,7 +762,65 @@ __device__ __forceinline__ void finish_item(const Item& it, int tid, const Smem&
     }
 
     unsigned long long cand = 0;
-    if (my_min <= thr || all) {
+    if constexpr (v3) {
+        // per-lag screening of the runs that can hold a candidate; everything is re-read from shared memory (the
+        // staged windows, the runs' head sums, the transform's output), the loop stays rolled: it runs for a few of
+        // the 64 warp-rounds of a lag block.  Within a warp-round the warp's own smallest value tightens the threshold.
+        const float rt = sqrtf(f_tsq);
+#pragma unroll 1
+        for (int c = 0; c < ROUNDS; ++c) {
+            const float l = c == 0 ? run_lb[0] : c == 1 ? run_lb[1] : c == 2 ? run_lb[2] : run_lb[3];
+            const bool sel = l <= thr || (all && l < kSent);
+            if (!__any_sync(0xffffffffu, sel)) continue;
+            const int m0 = c * LAGS_PER_ROUND + tid * 8;
+            const int64_t j0 = j_blk + m0;
+            float cc[8];
+            const float rc = kC32[4 * c], rs8 = kS32[4 * c];                     // W8^c
+            const float wc = wt.x * rc - wt.y * rs8, ws = wt.x * rs8 + wt.y * rc;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+#if SB_V2_DIF
+                const C2 E = buf.ld(ech + kDA * e + 8 * c), O = buf.ld(ech + kDA * e + 8 * c + 1);
+#else
+                const C2 E = buf.ld(ech + 1088 * c + e), O = buf.ld(ech + 1088 * c + e + 4352);
+#endif
+                const float2 xr = fma2(O.r, bc(wc), fma2(O.i, bc(-ws), E.r));
+                const float2 xi = fma2(O.r, bc(ws), fma2(O.i, bc(wc), E.i));
+                cc[4 * e + 0] = xr.x; cc[4 * e + 1] = xi.x; cc[4 * e + 2] = xr.y; cc[4 * e + 3] = xi.y;
+            }
+            const unsigned long long lo8 = *reinterpret_cast<const unsigned long long*>(sm.lo + m0);
+            const int hb = (int)((j_blk + n) & 15) + m0;
+            const unsigned long long h0 = *reinterpret_cast<const unsigned long long*>(sm.hi + (hb & ~7));
+            const unsigned long long h1 = *reinterpret_cast<const unsigned long long*>(sm.hi + (hb & ~7) + 8);
+            const unsigned sh = (unsigned)(hb & 7) * 8u;
+            const unsigned long long hi8 = sh ? ((h0 >> sh) | (h1 << (64u - sh))) : h0;
+            const double2 b_lo = sm.base[(c * NW + warp) * 2], b_hi = sm.base[(c * NW + warp) * 2 + 1];
+            const int2 off = s_w0[c * QT + tid];
+            const double w0s = (b_hi.x - b_lo.x) + (double)off.x, w0q = (b_hi.y - b_lo.y) + (double)off.y;
+            const float f_w0q = (float)(w0q + 0.25);
+            const float f_A = (float)(w0q + tsq - 2.0 * (b * w0s + k_const));
+            float v8[8];
+            float vmin = kSent;
+            int rq = 0, rs = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float frq = (float)rq;
+                const float num = fmaf(cc[i], m2s, fmaf(m2b, (float)rs, f_A + frq));
+                const float v = num * rsqrt_fast(f_w0q + frq);
+                const bool valid = sel && j0 + i >= jlo && j0 + i < jhi;
+                v8[i] = valid ? v : kSent;
+                vmin = fminf(vmin, v8[i]);
+                const int lo = (int)((lo8 >> (8 * i)) & 0xffu), hi = (int)((hi8 >> (8 * i)) & 0xffu);
+                const int dd = hi - lo;
+                rq += (hi + lo) * dd; rs += dd;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+            const float thrw = fminf(thr, vmin + kScreenMargin * rt);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) cand |= (v8[i] < kSent && (v8[i] <= thrw || all)) ? (1ull << (c * 8 + i)) : 0ull;   // (a block without a usable upper bound has thr = kSent)
+        }
+    } else if (my_min <= thr || all) {
 #pragma unroll
         for (int c = 0; c < ROUNDS; ++c)
 #pragma unroll
@@ -829,7 +913,7 @@ k_match_packed(const float4* __restrict__ That, int64_t part_first,
     unsigned long long* s_best = s_bar + 1;                                // [NW]
     float* s_min = reinterpret_cast<float*>(s_best + NW);                  // [NW]
     float4* s_sp = reinterpret_cast<float4*>(sm.end + kSmallBytes);        // EPI 2: units of the self-mirrored quads
-    int2* s_w0 = EPI == 2 && is_u8 ? reinterpret_cast<int2*>(sm.end + kSmallBytes + kSpecialBytes) : nullptr;   // [kRounds][QT]
+    int2* s_w0 = EPI >= 2 && is_u8 ? reinterpret_cast<int2*>(sm.end + kSmallBytes + kSpecialBytes) : nullptr;   // [kRounds][QT]
     const Buf& buf = sm.buf;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -841,7 +925,7 @@ k_match_packed(const float4* __restrict__ That, int64_t part_first,
         if (tid == 0) mbar_init(s_bar, 1);
         stage_inputs(it, tid, reinterpret_cast<const uint8_t*>(img), img_n, ipfx, sm, s_bar);
     }
-    if (EPI == 2 && tid == 64) query_constants<S>(reinterpret_cast<double2*>(sm.end + kQueryConstOff()), d, img_n, ipfx, tpfx);
+    if (EPI >= 2 && tid == 64) query_constants<S>(reinterpret_cast<double2*>(sm.end + kQueryConstOff()), d, img_n, ipfx, tpfx);
 
     // ---------------- 1+2. spectral multiply-accumulate, packing, first radix-2 step --------
     {
@@ -853,7 +937,7 @@ k_match_packed(const float4* __restrict__ That, int64_t part_first,
         const float2 wbase = __ldg(tab.wb + tid);
         const int tm = (T - tid) & (T - 1);           // mirrored chunks C[B/2 - i] live in thread tm's column
         const int col = phys(tid), mcol = phys(tm);
-        const bool sp_pref = EPI == 2 && SB_V2_SPECIAL_PREFETCH && special_fits(d.P, 1);
+        const bool sp_pref = EPI >= 2 && SB_V2_SPECIAL_PREFETCH && special_fits(d.P, 1);
         if (sp_pref && warp == NW - 1) special_prefetch(s_sp, tp, xp, d.P, 1, it.k, nblk, lane);
         constexpr int U = 4;                          // quads in flight per thread
 #pragma unroll 1
@@ -964,7 +1048,7 @@ k_match_pair(const float4* __restrict__ That, int64_t part_first,
     float* s_min = reinterpret_cast<float*>(s_best + NW);                  // [NW]
     uint32_t* s_taddr = reinterpret_cast<uint32_t*>(s_min + NW);
     float4* s_sp = reinterpret_cast<float4*>(sm.end + kSmallBytes);        // EPI 2: units of the self-mirrored quads
-    int2* s_w0 = EPI == 2 && is_u8 ? reinterpret_cast<int2*>(sm.end + kSmallBytes + kSpecialBytes) : nullptr;   // [kRounds][QT]
+    int2* s_w0 = EPI >= 2 && is_u8 ? reinterpret_cast<int2*>(sm.end + kSmallBytes + kSpecialBytes) : nullptr;   // [kRounds][QT]
     const Buf& buf = sm.buf;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -979,7 +1063,7 @@ k_match_pair(const float4* __restrict__ That, int64_t part_first,
         if (tid == 0) mbar_init(s_bar, 1);
         stage_inputs(it0, tid, reinterpret_cast<const uint8_t*>(img), img_n, ipfx, sm, s_bar);
     }
-    if (EPI == 2 && tid == 64) query_constants<S>(reinterpret_cast<double2*>(sm.end + kQueryConstOff()), d, img_n, ipfx, tpfx);
+    if (EPI >= 2 && tid == 64) query_constants<S>(reinterpret_cast<double2*>(sm.end + kQueryConstOff()), d, img_n, ipfx, tpfx);
     tmem_fence_before();
     csync<0>();
     tmem_fence_after();
@@ -996,7 +1080,7 @@ k_match_pair(const float4* __restrict__ That, int64_t part_first,
         const float4* tp = That + (d.partBase - part_first) * (int64_t)R::STRIDE;
         const float4* xp = Xhat + k * (int64_t)R::STRIDE;
         const float2 wbase = __ldg(tab.wb + tid);
-        const bool sp_pref = EPI == 2 && SB_V2_SPECIAL_PREFETCH && special_fits(d.P, 2);
+        const bool sp_pref = EPI >= 2 && SB_V2_SPECIAL_PREFETCH && special_fits(d.P, 2);
         if (sp_pref && warp == NW - 1) special_prefetch(s_sp, tp, xp, d.P, 2, k, nblk, lane);
         constexpr int U = 2;                          // quads in flight per thread (two accumulator sets each)
 #pragma unroll 1
@@ -1069,7 +1153,7 @@ k_match_pair(const float4* __restrict__ That, int64_t part_first,
 
     // ---------------- second item: out of tensor memory, then the same ---------------------------
     if (has2) {                                       // uniform over the CTA
-        unpark<EPI == 2>(tcol, buf, col, mcol, tid);
+        unpark<EPI >= 2>(tcol, buf, col, mcol, tid);
         if (tid == (NW - 1) * 32) buf.st(phys(Q4), sp1);
         csync<0>();
         const float4 wtj = inverse_fft<0, EPI>(buf, tid, tab, is_u8);
@@ -1169,7 +1253,7 @@ size_t forward_smem_bytes14() {
 }
 
 size_t packed_smem_bytes(int epi = 1) {      // epilogue 2 keeps the runs' exact head sums next to the small arrays
-    return epi == 2 ? kSmemCommon + kSmallBytes + kSpecialBytes + (size_t)kRounds * QT * sizeof(int2)
+    return epi >= 2 ? kSmemCommon + kSmallBytes + kSpecialBytes + (size_t)kRounds * QT * sizeof(int2)
                     : kSmemCommon + 8 + QNW * sizeof(unsigned long long) + QNW * sizeof(float) + 64;
 }
 
@@ -1314,6 +1398,7 @@ int launch_pair_typed(const sb_stream* image, const sb_stream* tmpl, const float
 // One instantiation per (sample type, epilogue): float32 streams have the first screening loop only.
 #define SB_DISPATCH_MATCH(FN, image, ...) \
     ((image)->dtype != SB_U8 ? FN<float, 1>(image, __VA_ARGS__) \
+     : ctx().epilogue == 3   ? FN<uint8_t, 3>(image, __VA_ARGS__) \
      : ctx().epilogue == 2   ? FN<uint8_t, 2>(image, __VA_ARGS__) : FN<uint8_t, 1>(image, __VA_ARGS__))
 
 }  // namespace

@@ -114,6 +114,11 @@ inline float2 __fadd2_rn(float2 a, float2 b) { return make_float2(a.x + b.x, a.y
 inline float2 __fmul2_rn(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
 inline float2 __ffma2_rn(float2 a, float2 b, float2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
 template <typename T> inline T __shfl_xor_sync(unsigned, T v, int o) { return emu::shfl(v, emu::t_lane ^ o); }
+inline int __any_sync(unsigned, int pred) {
+    int v = pred ? 1 : 0;
+    for (int o = 16; o > 0; o >>= 1) v |= emu::shfl(v, emu::t_lane ^ o);
+    return v;
+}
 template <typename T> inline T __shfl_up_sync(unsigned, T v, int o) { return emu::shfl(v, emu::t_lane >= o ? emu::t_lane - o : emu::t_lane); }
 inline unsigned __dp4a(unsigned a, unsigned b, unsigned c) {
     for (int i = 0; i < 4; ++i) c += ((a >> (8 * i)) & 0xffu) * ((b >> (8 * i)) & 0xffu);

@@ -38,12 +38,13 @@ def test_trimmed_epilogue_is_bit_identical_on_batches(gpu_lib, epilogue, engine)
     starts, ends = synth.make_events(300, 240.0, 12, 0.5, 6.0)
     win = np.full(len(starts), 30.0)
     out = {}
-    for variant in (1, 2):
+    for variant in (1, 2, 3):
         epilogue(variant, engine)
         assert gpu_lib.sb_get_epilogue() == variant
         out[variant] = dst.find_substream_batch(src, starts, ends, starts, win)
-    assert np.array_equal(out[1][0], out[2][0])
-    assert np.array_equal(out[1][1], out[2][1])
+    for variant in (2, 3):
+        assert np.array_equal(out[1][0], out[variant][0])
+        assert np.array_equal(out[1][1], out[variant][1])
     # and they are right: the known shift comes back
     ok = (ends + 1.5 < 240.0)
     assert np.abs((out[2][1] - starts)[ok] - 1.5).max() <= 1.0 / 12000 + 1e-9
@@ -57,11 +58,12 @@ def test_trimmed_epilogue_curves_and_ragged_ranges(gpu_lib, epilogue, engine):
              (5000, 3000, 16383, 16386), (7, 700, 1, 5), (40000, 20000, 32768, 16384)]
     for toff, n, lag0, nlags in cases:
         got = {}
-        for variant in (1, 2):
+        for variant in (1, 2, 3):
             epilogue(variant, engine)
             got[variant] = (dst.match_curve(src, toff, n, lag0, nlags), dst.find_planned(src, [toff], [n], [lag0], [nlags]))
-        assert np.array_equal(got[1][0], got[2][0])
-        assert got[1][1][0][0] == got[2][1][0][0] and got[1][1][1][0] == got[2][1][1][0]
+        for variant in (2, 3):
+            assert np.array_equal(got[1][0], got[variant][0])
+            assert got[1][1][0][0] == got[variant][1][0][0] and got[1][1][1][0] == got[variant][1][1][0]
         assert got[2][1][1][0] == int(got[2][0].argmin()) and got[2][1][0][0] == got[2][0].min()
 
 
@@ -78,8 +80,8 @@ def test_trimmed_epilogue_degenerate_inputs(gpu_lib, epilogue, golden_matcher):
     gap = rng.integers(0, 256, (1, 40000), dtype=np.uint8)
     gap[0, 9000:31000] = 0                                     # a long silent stretch inside programme material
     gapped = mk(gap)
-    for engine in (4, 5):
-        epilogue(2, engine)
+    for engine, body in ((4, 2), (5, 2), (4, 3), (5, 3)):
+        epilogue(body, engine)
         assert np.array_equal(z.match_curve(seven, 0, 8, 0, 57), g['deg_zero_window'])
         assert np.array_equal(nine.match_curve(z, 0, 8, 0, 57), g['deg_zero_template'])
         assert np.abs(nine.match_curve(seven, 0, 8, 0, 57) - g['deg_const_7_vs_9']).max() <= 1e-6
@@ -89,12 +91,13 @@ def test_trimmed_epilogue_degenerate_inputs(gpu_lib, epilogue, golden_matcher):
         diff, idx = z.find_planned(seven, [0], [8], [0], [57])
         assert idx[0] == 0 and diff[0] == 1.0                   # all saturated: FIRST index
         res = {}
-        for variant in (1, 2):
+        for variant in (1, 2, 3):
             epilogue(variant, engine)
             res[variant] = (gapped.match_curve(gapped, 12000, 6000, 0, 34001),
                             gapped.find_planned(gapped, [12000, 100, 33000], [6000, 5000, 5000], [0, 8000, 0], [34001, 20000, 35001]))
-        assert np.array_equal(res[1][0], res[2][0])
-        assert np.array_equal(res[1][1][0], res[2][1][0]) and np.array_equal(res[1][1][1], res[2][1][1])
+        for variant in (2, 3):
+            assert np.array_equal(res[1][0], res[variant][0])
+            assert np.array_equal(res[1][1][0], res[variant][1][0]) and np.array_equal(res[1][1][1], res[variant][1][1])
 
 
 def test_default_is_the_trimmed_body(gpu_lib):
