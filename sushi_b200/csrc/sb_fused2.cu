@@ -519,6 +519,19 @@ __device__ __forceinline__ void query_constants(double2* s_qc, const QueryDesc& 
     s_qc[1] = make_double2((double)Acc<S>::centre(ipfx[img_n].x, (double)img_n), (double)Acc<S>::centre(tsum, (double)d.tlen));
 }
 
+// EPI 3: runs of 8 lags that can hold a lag block's minimum leave the match kernel as records -- the query, the
+// run's first lag and the correlation at its 8 lags, rounded exactly like the in-kernel exact path rounds it -- and
+// k_finish_runs evaluates their lags in fp64 afterwards (window sums from the running sums: the same exact
+// integers).  The match kernel's epilogue then ends after the block minimum: no per-lag loop, no fp64 on the CTA's
+// critical path (ncu, round 2: with the exact evaluation inside, fifteen warps wait 1 800 cycles per lag block at the
+// closing barrier for the one warp that holds the candidate).  A CTA has kRunSlots slots; runs that find none
+// (degenerate data: silence, constant streams) and the debug curve take the in-kernel path.
+constexpr int kRunSlots = 8;
+struct RunRecord { int32_t q; int32_t valid; int64_t j0; float cc[8]; };     // 48 bytes
+static_assert(sizeof(RunRecord) == 48, "three 16-byte stores");
+struct RunSink { RunRecord* recs; int* s_cnt; };                              // recs = this CTA's kRunSlots records (or null)
+__device__ __forceinline__ constexpr int kRunCountOff() { return 256; }       // bytes behind Smem::end (small area)
+
 // Window sums, fp32 screening of every lag, fp64 evaluation of the lags that can still be the minimum, merge
 // into the query's key.  after_read() runs (on all 512 threads) once every thread is done with the staged
 // windows.
@@ -529,7 +542,7 @@ __device__ __forceinline__ void finish_item(const Item& it, int tid, const Smem&
                                             const double2* __restrict__ ipfx, const double2* __restrict__ tpfx,
                                             const PackedTables& tab, unsigned long long* __restrict__ keys,
                                             float* __restrict__ curve_out, AfterRead after_read,
-                                            float4 wt_in = make_float4(0.f, 0.f, 0.f, 0.f)) {
+                                            float4 wt_in = make_float4(0.f, 0.f, 0.f, 0.f), RunSink sink = RunSink{nullptr, nullptr}) {
     constexpr int B = QB, NW = QNW, LB = QB, ROUNDS = kRounds, LAGS_PER_ROUND = kLagsPerRound;
     constexpr bool is_u8 = sizeof(S) == 1;
     constexpr bool v2 = EPI >= 2 && is_u8;                 // trimmed screening (see the comment at its loop)
@@ -767,6 +780,40 @@ __device__ __forceinline__ void finish_item(const Item& it, int tid, const Smem&
         // staged windows, the runs' head sums, the transform's output), the loop stays rolled: it runs for a few of
         // the 64 warp-rounds of a lag block.  Within a warp-round the warp's own smallest value tightens the threshold.
         const float rt = sqrtf(f_tsq);
+        // the selected runs leave as records (see RunRecord); what finds no slot stays selected for the loop below
+        if (sink.recs != nullptr && !all) {
+#pragma unroll
+            for (int c = 0; c < ROUNDS; ++c) {
+                if (run_lb[c] <= thr) {
+                    const int slot = atomicAdd(sink.s_cnt, 1);
+                    if (slot < kRunSlots) {
+                        const int m0 = c * LAGS_PER_ROUND + tid * 8;
+                        float cc[8];
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {       // chunks jj = m0/4 + e, exactly as the exact path below forms them
+                            const int jj = (m0 >> 2) + e;
+#if SB_V2_DIF
+                            const int ca = (jj & 15) * kDA + ((jj >> 4) & 15) * kDB + 2 * (jj >> 8);
+                            const C2 E = buf.ld(ca), O = buf.ld(ca + 1);
+                            const float2 w = make_float2(kC32[jj >> 8], kS32[jj >> 8]);
+#else
+                            const C2 E = buf.ld(phys(jj)), O = buf.ld(phys(jj) + 4352);
+                            const float2 w = __ldg(tab.w8 + jj);
+#endif
+                            const float2 xr = fma2(O.r, bc(w.x), fma2(O.i, bc(-w.y), E.r));
+                            const float2 xi = fma2(O.r, bc(w.y), fma2(O.i, bc(w.x), E.i));
+                            cc[4 * e + 0] = xr.x; cc[4 * e + 1] = xi.x; cc[4 * e + 2] = xr.y; cc[4 * e + 3] = xi.y;
+                        }
+                        float4* r4 = reinterpret_cast<float4*>(sink.recs + slot);
+                        const int64_t j0 = j_blk + m0;
+                        *reinterpret_cast<int4*>(r4) = make_int4(it.q, 1, (int)(unsigned)(j0 & 0xffffffffll), (int)(j0 >> 32));
+                        r4[1] = make_float4(cc[0], cc[1], cc[2], cc[3]);
+                        r4[2] = make_float4(cc[4], cc[5], cc[6], cc[7]);
+                        run_lb[c] = kSent;                   // done
+                    }
+                }
+            }
+        }
 #pragma unroll 1
         for (int c = 0; c < ROUNDS; ++c) {
             const float l = c == 0 ? run_lb[0] : c == 1 ? run_lb[1] : c == 2 ? run_lb[2] : run_lb[3];
@@ -904,7 +951,8 @@ k_match_packed(const float4* __restrict__ That, int64_t part_first,
                const S* __restrict__ img, int64_t img_n,
                const double2* __restrict__ ipfx, const double2* __restrict__ tpfx,
                const QueryDesc* __restrict__ desc, const int* __restrict__ item_query, int64_t item_first,
-               PackedTables tab, unsigned long long* __restrict__ keys, float* __restrict__ curve_out) {
+               PackedTables tab, unsigned long long* __restrict__ keys, float* __restrict__ curve_out,
+               RunRecord* __restrict__ recs, int* __restrict__ rec_count) {
     constexpr int T = QT, NW = QNW;
     constexpr bool is_u8 = sizeof(S) == 1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -912,6 +960,8 @@ k_match_packed(const float4* __restrict__ That, int64_t part_first,
     unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(sm.end);
     unsigned long long* s_best = s_bar + 1;                                // [NW]
     float* s_min = reinterpret_cast<float*>(s_best + NW);                  // [NW]
+    int* s_cnt = reinterpret_cast<int*>(sm.end + kRunCountOff());          // EPI 3: records written by this CTA
+    const RunSink sink = {EPI == 3 && recs ? recs + (size_t)blockIdx.x * kRunSlots : nullptr, s_cnt};
     float4* s_sp = reinterpret_cast<float4*>(sm.end + kSmallBytes);        // EPI 2: units of the self-mirrored quads
     int2* s_w0 = EPI >= 2 && is_u8 ? reinterpret_cast<int2*>(sm.end + kSmallBytes + kSpecialBytes) : nullptr;   // [kRounds][QT]
     const Buf& buf = sm.buf;
@@ -925,6 +975,7 @@ k_match_packed(const float4* __restrict__ That, int64_t part_first,
         if (tid == 0) mbar_init(s_bar, 1);
         stage_inputs(it, tid, reinterpret_cast<const uint8_t*>(img), img_n, ipfx, sm, s_bar);
     }
+    if (EPI == 3 && tid == 96) *s_cnt = 0;
     if (EPI >= 2 && tid == 64) query_constants<S>(reinterpret_cast<double2*>(sm.end + kQueryConstOff()), d, img_n, ipfx, tpfx);
 
     // ---------------- 1+2. spectral multiply-accumulate, packing, first radix-2 step --------
@@ -988,7 +1039,8 @@ k_match_packed(const float4* __restrict__ That, int64_t part_first,
 
     // ---------------- 3. inverse FFT, 4. epilogue ---------------------------------------------
     const float4 wt0 = inverse_fft<0, EPI>(buf, tid, tab, is_u8);
-    finish_item<S, 0, EPI>(it, tid, sm, s_bar, 0u, s_best, s_min, s_w0, img, img_n, ipfx, tpfx, tab, keys, curve_out, [] {}, wt0);
+    finish_item<S, 0, EPI>(it, tid, sm, s_bar, 0u, s_best, s_min, s_w0, img, img_n, ipfx, tpfx, tab, keys, curve_out, [] {}, wt0, sink);
+    if (EPI == 3 && rec_count && tid == 0) rec_count[blockIdx.x] = *s_cnt < kRunSlots ? *s_cnt : kRunSlots;    // behind the closing barrier of finish_item
 }
 
 // A parked product spectrum back into the FFT buffer: this thread's 64 tensor-memory columns hold, quad by quad,
@@ -1038,7 +1090,8 @@ k_match_pair(const float4* __restrict__ That, int64_t part_first,
              const S* __restrict__ img, int64_t img_n,
              const double2* __restrict__ ipfx, const double2* __restrict__ tpfx,
              const QueryDesc* __restrict__ desc, const int* __restrict__ pair_query, int64_t pair_first,
-             PackedTables tab, unsigned long long* __restrict__ keys, float* __restrict__ curve_out) {
+             PackedTables tab, unsigned long long* __restrict__ keys, float* __restrict__ curve_out,
+             RunRecord* __restrict__ recs, int* __restrict__ rec_count) {
     constexpr int T = QT, NW = QNW;
     constexpr bool is_u8 = sizeof(S) == 1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1047,6 +1100,8 @@ k_match_pair(const float4* __restrict__ That, int64_t part_first,
     unsigned long long* s_best = s_bar + 1;                                // [NW]
     float* s_min = reinterpret_cast<float*>(s_best + NW);                  // [NW]
     uint32_t* s_taddr = reinterpret_cast<uint32_t*>(s_min + NW);
+    int* s_cnt = reinterpret_cast<int*>(sm.end + kRunCountOff());          // EPI 3: records written by this CTA (both items)
+    const RunSink sink = {EPI == 3 && recs ? recs + (size_t)blockIdx.x * kRunSlots : nullptr, s_cnt};
     float4* s_sp = reinterpret_cast<float4*>(sm.end + kSmallBytes);        // EPI 2: units of the self-mirrored quads
     int2* s_w0 = EPI >= 2 && is_u8 ? reinterpret_cast<int2*>(sm.end + kSmallBytes + kSpecialBytes) : nullptr;   // [kRounds][QT]
     const Buf& buf = sm.buf;
@@ -1063,6 +1118,7 @@ k_match_pair(const float4* __restrict__ That, int64_t part_first,
         if (tid == 0) mbar_init(s_bar, 1);
         stage_inputs(it0, tid, reinterpret_cast<const uint8_t*>(img), img_n, ipfx, sm, s_bar);
     }
+    if (EPI == 3 && tid == 96) *s_cnt = 0;
     if (EPI >= 2 && tid == 64) query_constants<S>(reinterpret_cast<double2*>(sm.end + kQueryConstOff()), d, img_n, ipfx, tpfx);
     tmem_fence_before();
     csync<0>();
@@ -1149,7 +1205,7 @@ k_match_pair(const float4* __restrict__ That, int64_t part_first,
     // ---------------- first item: inverse FFT + epilogue ---------------------------------------
     const float4 wt0 = inverse_fft<0, EPI>(buf, tid, tab, is_u8);
     finish_item<S, 0, EPI>(it0, tid, sm, s_bar, 0u, s_best, s_min, s_w0, img, img_n, ipfx, tpfx, tab, keys, curve_out,
-                      [&] { if (is_u8 && has2) stage_inputs(it1, tid, reinterpret_cast<const uint8_t*>(img), img_n, ipfx, sm, s_bar); }, wt0);
+                      [&] { if (is_u8 && has2) stage_inputs(it1, tid, reinterpret_cast<const uint8_t*>(img), img_n, ipfx, sm, s_bar); }, wt0, sink);
 
     // ---------------- second item: out of tensor memory, then the same ---------------------------
     if (has2) {                                       // uniform over the CTA
@@ -1157,11 +1213,51 @@ k_match_pair(const float4* __restrict__ That, int64_t part_first,
         if (tid == (NW - 1) * 32) buf.st(phys(Q4), sp1);
         csync<0>();
         const float4 wtj = inverse_fft<0, EPI>(buf, tid, tab, is_u8);
-        finish_item<S, 0, EPI>(it1, tid, sm, s_bar, 1u, s_best, s_min, s_w0, img, img_n, ipfx, tpfx, tab, keys, curve_out, [] {}, wtj);
+        finish_item<S, 0, EPI>(it1, tid, sm, s_bar, 1u, s_best, s_min, s_w0, img, img_n, ipfx, tpfx, tab, keys, curve_out, [] {}, wtj, sink);
     }
     tmem_fence_before();
     csync<0>();
     if (warp == 0) tmem_dealloc(*s_taddr, 256);
+    if (EPI == 3 && rec_count && tid == 32) rec_count[blockIdx.x] = *s_cnt < kRunSlots ? *s_cnt : kRunSlots;
+}
+
+// EPI 3, second step: one thread per record slot evaluates the 8 lags of its run exactly (fp64) and merges the best
+// into the query's key -- the arithmetic of finish_item's exact path, with the window sums taken from the running
+// sums (for uint8 streams the same exact integers the match kernel slides on its staged bytes).
+template <typename S>
+__global__ void __launch_bounds__(128)
+k_finish_runs(const RunRecord* __restrict__ recs, const int* __restrict__ rec_count, int64_t n_ctas,
+              const QueryDesc* __restrict__ desc, const double2* __restrict__ ipfx, int64_t img_n,
+              const double2* __restrict__ tpfx, unsigned long long* __restrict__ keys) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t cta = idx / kRunSlots;
+    const int slot = (int)(idx - cta * kRunSlots);
+    if (cta >= n_ctas || slot >= rec_count[cta]) return;
+    const float4* r4 = reinterpret_cast<const float4*>(recs + cta * kRunSlots + slot);
+    const int4 head = *reinterpret_cast<const int4*>(r4);
+    const float4 c0 = r4[1], c1 = r4[2];
+    const float cc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+    const int q = head.x;
+    const int64_t j0 = (int64_t)(unsigned)head.z | ((int64_t)head.w << 32);
+    const QueryDesc d = desc[q];
+    const int64_t n = d.tlen, jlo = d.lag0, jhi = d.lag0 + d.nlags;
+    const double2 t_hi = tpfx[d.toff + n], t_lo = tpfx[d.toff];
+    const double tsum = t_hi.x - t_lo.x, tsq = t_hi.y - t_lo.y;
+    const double a = (double)Acc<S>::centre(ipfx[img_n].x, (double)img_n);
+    const double b = (double)Acc<S>::centre(tsum, (double)n);
+    const double n_ab = (double)n * a * b;
+    const double scale = 1.0 / (double)(2 * QB);
+    unsigned long long best = ~0ull;
+#pragma unroll 1
+    for (int i = 0; i < 8; ++i) {
+        const int64_t j = j0 + i;
+        if (j < jlo || j >= jhi) continue;
+        const double2 p_hi = ipfx[j + n], p_lo = ipfx[j];
+        const float v = sqdiff_exact((double)cc[i] * scale, p_hi.x - p_lo.x, p_hi.y - p_lo.y, a, b, tsum, tsq, n_ab);
+        const unsigned long long key = ((unsigned long long)__float_as_uint(v) << 32) | (unsigned int)(j - jlo);
+        best = key < best ? key : best;
+    }
+    if (best != ~0ull) atomicMin(keys + q, best);
 }
 
 // pair_query[i] = query of pair (pair_first + i): one CTA per query fills its own range
@@ -1350,6 +1446,34 @@ int ensure_item_query(int64_t n) {
     return SB_OK;
 }
 
+// EPI 3: record slots of the current launch (kRunSlots per CTA) and the CTAs' record counts, grown on demand
+RunRecord* g_run_recs = nullptr;
+int* g_run_count = nullptr;
+int64_t g_run_cap = 0;          // CTAs
+constexpr int64_t kRunChunk = 1 << 19;    // CTAs per launch when records are written: 201 MB of slots
+
+int ensure_run_records(int64_t n_ctas) {
+    if (g_run_cap < n_ctas) {
+        cudaStreamSynchronize(ctx().stream);
+        cudaFree(g_run_recs); cudaFree(g_run_count); g_run_recs = nullptr; g_run_count = nullptr; g_run_cap = 0;
+        SB_CUDA(cudaMalloc(&g_run_recs, sizeof(RunRecord) * (size_t)n_ctas * kRunSlots));
+        SB_CUDA(cudaMalloc(&g_run_count, sizeof(int) * (size_t)n_ctas));
+        g_run_cap = n_ctas;
+    }
+    return SB_OK;
+}
+
+template <typename S>
+int launch_finish_runs(const sb_stream* image, const sb_stream* tmpl, const QueryDesc* d_desc, int64_t n_ctas, unsigned long long* d_keys) {
+    Ctx& c = ctx();
+    const int64_t threads = n_ctas * kRunSlots;
+    k_finish_runs<S><<<(unsigned)((threads + 127) / 128), 128, 0, c.stream>>>(g_run_recs, g_run_count, n_ctas, d_desc, image->d_pfx, image->n,
+                                                                            tmpl->d_pfx, d_keys);
+    c.launches += 1;
+    SB_CUDA(cudaGetLastError());
+    return SB_OK;
+}
+
 // Launchers of the three match kernels.  `Kernel` is one instantiation (sample type x epilogue variant); its
 // dynamic shared memory limit is raised once.  The uint8 kernels exist with both epilogues (Ctx::epilogue),
 // float32 streams have the first one only.
@@ -1364,13 +1488,16 @@ int launch_packed_typed(const sb_stream* image, const sb_stream* tmpl, const flo
         SB_CUDA(cudaFuncSetAttribute(k_match_packed<S, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
-    const int64_t max_grid = 1 << 30;
+    const bool records = EPI == 3 && d_curve == nullptr;             // the debug curve evaluates every lag in the kernel
+    const int64_t max_grid = records ? kRunChunk : (int64_t)1 << 30;
     for (int64_t i0 = 0; i0 < n_items; i0 += max_grid) {
         const int64_t ni = std::min<int64_t>(max_grid, n_items - i0);
+        if (records) SB_TRY(ensure_run_records(ni));
         k_match_packed<S, EPI><<<(unsigned)ni, QT, smem, c.stream>>>(
             reinterpret_cast<const float4*>(d_parts), part_first, reinterpret_cast<const float4*>(image->d_specq), image->nblkq,
             static_cast<const S*>(image->d_raw), image->n, image->d_pfx, tmpl->d_pfx, d_desc, g_item_query2 + i0, item_first + i0,
-            tab, d_keys, d_curve);
+            tab, d_keys, d_curve, records ? g_run_recs : nullptr, records ? g_run_count : nullptr);
+        if (records) SB_TRY(launch_finish_runs<S>(image, tmpl, d_desc, ni, d_keys));
     }
     SB_CUDA(cudaGetLastError());
     return SB_OK;
@@ -1387,11 +1514,18 @@ int launch_pair_typed(const sb_stream* image, const sb_stream* tmpl, const float
         SB_CUDA(cudaFuncSetAttribute(k_match_pair<S, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
-    k_match_pair<S, EPI><<<(unsigned)n_pairs, QT, smem, c.stream>>>(
-        reinterpret_cast<const float4*>(d_parts), part_first, reinterpret_cast<const float4*>(image->d_specq), image->nblkq,
-        static_cast<const S*>(image->d_raw), image->n, image->d_pfx, tmpl->d_pfx, d_desc, g_item_query2, pair_first,
-        tab, d_keys, d_curve);
-    SB_CUDA(cudaGetLastError());
+    const bool records = EPI == 3 && d_curve == nullptr;             // the debug curve evaluates every lag in the kernel
+    const int64_t max_grid = records ? kRunChunk : (int64_t)1 << 30;
+    for (int64_t i0 = 0; i0 < n_pairs; i0 += max_grid) {
+        const int64_t ni = std::min<int64_t>(max_grid, n_pairs - i0);
+        if (records) SB_TRY(ensure_run_records(ni));
+        k_match_pair<S, EPI><<<(unsigned)ni, QT, smem, c.stream>>>(
+            reinterpret_cast<const float4*>(d_parts), part_first, reinterpret_cast<const float4*>(image->d_specq), image->nblkq,
+            static_cast<const S*>(image->d_raw), image->n, image->d_pfx, tmpl->d_pfx, d_desc, g_item_query2 + i0, pair_first + i0,
+            tab, d_keys, d_curve, records ? g_run_recs : nullptr, records ? g_run_count : nullptr);
+        SB_CUDA(cudaGetLastError());
+        if (records) SB_TRY(launch_finish_runs<S>(image, tmpl, d_desc, ni, d_keys));
+    }
     return SB_OK;
 }
 
@@ -1446,6 +1580,7 @@ void packed_release_tables() {
     if (g_ptab_dev) cudaFree(g_ptab_dev);
     g_ptab_dev = nullptr;
     cudaFree(g_item_query2); g_item_query2 = nullptr; g_item_query2_cap = 0;
+    cudaFree(g_run_recs); cudaFree(g_run_count); g_run_recs = nullptr; g_run_count = nullptr; g_run_cap = 0;
 }
 
 }  // namespace sb

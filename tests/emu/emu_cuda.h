@@ -143,6 +143,7 @@ inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
 inline void __nanosleep(unsigned) { emu::yield_lane(); }
 inline void __syncthreads() { emu::cta_barrier(); }
 inline void __syncwarp(unsigned = 0xffffffffu) { emu::warp_rendezvous(); }
+inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 inline unsigned long long atomicMin(unsigned long long* p, unsigned long long v) {
     unsigned long long old = __atomic_load_n(p, __ATOMIC_RELAXED);
     while (v < old && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}

@@ -90,7 +90,8 @@ int emu_quad_row_floats(void) { return QROW * 4; }
 // Runs CTAs [0, n_ctas) one after the other.  Returns 0, or the number of emulation errors (messages on stderr).
 int emu_run(int kernel, int epi, int is_u8, const float* That, int64_t part_first, const float* Xhat, int64_t nblk,
             const void* img, int64_t img_n, const double* ipfx, const double* tpfx, const void* desc,
-            const int* cta_query, int64_t first, int n_ctas, unsigned long long* keys, float* curve_out) {
+            const int* cta_query, int64_t first, int n_ctas, unsigned long long* keys, float* curve_out,
+            void* run_recs, int* run_count) {
     static size_t off[kPackedTableCount];
     static const std::vector<float> tables = packed_table_values(off);
     const PackedTables tab = packed_tables_at(tables.data(), off);
@@ -110,7 +111,7 @@ int emu_run(int kernel, int epi, int is_u8, const float* That, int64_t part_firs
         auto body = [&](int t) {
             blockIdx = {(unsigned)b, 0, 0};       // threadIdx and the lane / warp numbers are set by run_cta
 #define SB_EMU_ARGS(S) T4, part_first, X4, nblk, static_cast<const S*>(img), img_n, ip, tp, d, cta_query, first
-#define SB_EMU_CALL(K, S, E, ...) K<S, E>(SB_EMU_ARGS(S), ##__VA_ARGS__, tab, keys, curve_out)
+#define SB_EMU_CALL(K, S, E, ...) K<S, E>(SB_EMU_ARGS(S), ##__VA_ARGS__, tab, keys, curve_out, static_cast<RunRecord*>(run_recs), run_count)
 #define SB_EMU_KERNEL(K, ...) do { if (!is_u8) SB_EMU_CALL(K, float, 1, ##__VA_ARGS__); else if (epi == 3) SB_EMU_CALL(K, uint8_t, 3, ##__VA_ARGS__); else if (epi == 2) SB_EMU_CALL(K, uint8_t, 2, ##__VA_ARGS__); \
                                    else SB_EMU_CALL(K, uint8_t, 1, ##__VA_ARGS__); } while (0)
             if (kernel == 0) SB_EMU_KERNEL(k_match_packed);
@@ -122,6 +123,23 @@ int emu_run(int kernel, int epi, int is_u8, const float* That, int64_t part_firs
     }
     return n_err;
 }
+
+// The second step of the third kernel body (k_finish_runs, uint8 streams): every record slot of CTAs [0, n_ctas).
+int emu_finish_runs(const void* run_recs, const int* run_count, int n_ctas, const void* desc, const double* ipfx, int64_t img_n,
+                    const double* tpfx, unsigned long long* keys) {
+    const int64_t threads = (int64_t)n_ctas * kRunSlots;
+    blockDim = dim3(128, 1, 1);
+    for (int64_t t = 0; t < threads; ++t) {
+        blockIdx = {(unsigned)(t / 128), 0, 0};
+        threadIdx = {(unsigned)(t % 128), 0, 0};
+        k_finish_runs<uint8_t>(static_cast<const RunRecord*>(run_recs), run_count, n_ctas, static_cast<const sb::QueryDesc*>(desc),
+                               reinterpret_cast<const double2*>(ipfx), img_n, reinterpret_cast<const double2*>(tpfx), keys);
+    }
+    blockDim = dim3(emu::kThreads, 1, 1);
+    return 0;
+}
+int emu_run_slots(void) { return kRunSlots; }
+int emu_run_record_bytes(void) { return (int)sizeof(RunRecord); }
 
 // Block spectra of a stream (k_forward_quad, MODE 0): rows [row_first, row_first + rows) into
 // `out` (rows * emu_quad_row_floats() floats).  The twiddle tables are the ones sb_fused.cu's ensure_tables<14>

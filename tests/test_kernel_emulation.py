@@ -110,7 +110,10 @@ class Case(object):
         self.That = quad_rows(np.array(parts), rf)
         self.src = src
 
-    def run(self, kernel, epi, curves):
+    def run(self, kernel, epi, curves, records=None):
+        """records: the third body hands its selected runs to k_finish_runs (default whenever epi == 3 and no curve
+        is asked for, like the library); False keeps everything in the match kernel."""
+        records = (epi == 3 and not curves) if records is None else records
         group = {0: 1, 1: 2}[kernel]
         desc = (QueryDesc * len(self.queries))()
         items = parts = groups = curve = 0
@@ -131,10 +134,20 @@ class Case(object):
         keys = np.full(len(self.queries), 0xffffffffffffffff, np.uint64)
         cur = np.full(curve, np.nan, np.float32) if curves else None
         vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+        recs = counts = None
+        if records:
+            recs = np.full(len(cta_query) * self.lib.emu_run_slots() * self.lib.emu_run_record_bytes(), 0xCD, np.uint8)
+            counts = np.full(len(cta_query), -1, np.int32)
         rc = self.lib.emu_run(kernel, epi, int(self.dtype == np.uint8), vp(self.That), ctypes.c_int64(0), vp(self.Xhat), ctypes.c_int64(self.nblk),
                               vp(self.img), ctypes.c_int64(self.n_img), vp(self.ipfx), vp(self.tpfx), ctypes.byref(desc), vp(cta_query),
-                              ctypes.c_int64(0), len(cta_query), vp(keys), vp(cur) if curves else None)
+                              ctypes.c_int64(0), len(cta_query), vp(keys), vp(cur) if curves else None,
+                              vp(recs) if records else None, vp(counts) if records else None)
         assert rc == 0, 'emulation reported %d errors (see stderr)' % rc
+        if records:
+            assert (counts >= 0).all() and (counts <= self.lib.emu_run_slots()).all()
+            self.last_record_counts = counts.copy()
+            self.lib.emu_finish_runs(vp(recs), vp(counts), len(cta_query), ctypes.byref(desc), vp(self.ipfx), ctypes.c_int64(self.n_img),
+                                     vp(self.tpfx), vp(keys))
         diff = (keys >> np.uint64(32)).astype(np.uint32).view(np.float32)
         idx = (keys & np.uint64(0xffffffff)).astype(np.int64)
         return diff, idx, cur
@@ -390,3 +403,27 @@ def test_emulated_many_partitions_do_not_overrun_the_special_area(emu):
             assert np.abs(cur - t).max() <= 3e-6 and i[0] == int(t.argmin()) == 3500 - 2000
             ref = ref or (d, i, cur)
             assert np.array_equal(ref[2], cur) and ref[0][0] == d[0] and ref[1][0] == i[0]
+
+
+def test_emulated_third_body_overflowing_record_slots(emu):
+    """A periodic stream: the template matches exactly every 1000 lags, so a lag block holds sixteen runs of equal
+    minimum -- more than a CTA's eight record slots.  Eight runs leave as records (k_finish_runs), the others are
+    finished inside the match kernel; both routes, and the all-in-kernel mode, must return what every other variant
+    returns."""
+    period = programme(1000, 77)
+    img = np.tile(period, 3 * B // 1000 + 2)[:3 * B]
+    src = img.copy()
+    queries = [(2000, 3000, 500, 2 * B + 300),        # exact copies at lags 1000, 2000, ...: the first one inside the range wins
+               (2345, 700, 0, B)]                      # lag 345, then every 1000
+    c = Case(emu, img, src, queries, np.uint8)
+    ref = None
+    for kernel in (0, 1):
+        for epi, records in ((1, False), (2, False), (3, False), (3, True)):
+            d, i, _ = c.run(kernel, epi, curves=False, records=records)
+            # every copy is a minimum up to fp32 FFT rounding (~1e-7): which one wins is decided by the exact path,
+            # so all variants must agree bit for bit
+            assert i[0] % 1000 == 500 and i[1] % 1000 == 345 and float(d.max()) <= 1e-6, (kernel, epi, records, i, d)
+            ref = ref or (d, i)
+            assert np.array_equal(ref[0], d) and np.array_equal(ref[1], i), (kernel, epi, records)
+            if records:
+                assert c.last_record_counts.max() == emu.emu_run_slots()        # the slots did overflow
