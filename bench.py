@@ -508,7 +508,8 @@ def run_b200(args):
                 'frac': round(achieved / peak, 5), 'traffic': cap['dram_bytes_per_launch'] if cap else None,
                 'peak_source': peak_src,
                 'launches_per_step': dom_n / args.steps, 'avg_launch_ms': round(dom_ms / max(dom_n, 1), 5),
-                'algorithmic_bytes_per_launch': my_bytes, 'algorithmic_bytes_per_step_all_ranks': step_bytes,
+                'algorithmic_bytes_per_launch': my_bytes * args.steps / max(dom_n, 1),
+                'algorithmic_bytes_per_step_this_rank': my_bytes, 'algorithmic_bytes_per_step_all_ranks': step_bytes,
                 'whole_step': {'achieved': round(step_bytes / (ms_step / 1e3) / 1e9, 2),
                                'frac': round(step_bytes / (ms_step / 1e3) / 1e9 / peak / world, 5)},
                 'kernel_ms_per_step': {k: round(v[0] / args.steps, 4) for k, v in sorted(prof.items())}}
@@ -612,7 +613,7 @@ def main():
     ap.add_argument('--block', type=int, default=0, help='lag-block size override')
     ap.add_argument('--premac-mode', type=int, default=-1, help='blocked multiply kernel: 0 by template length (default), 1 never, 2 always')
     ap.add_argument('--hop-mode', type=int, default=-1, help='fused engine geometry: 1 hop B (default), 2 hop B/2, 0 cost rule per batch')
-    ap.add_argument('--epilogue', type=int, default=0, help='body variant of the packed kernels on uint8 streams: 2 trimmed (default), 1 first version')
+    ap.add_argument('--epilogue', type=int, default=0, help='body variant of the packed kernels on uint8 streams: 3 run-level bounds + k_finish_runs (default), 1 first version')
     ap.add_argument('--engine', type=int, default=-1, help='0: cuFFT pipeline, 1: fused kernel, 2: packed fused kernels (default), 4 / 5: always / never pairs of lag blocks')
     args = ap.parse_args()
     if args.impl == 'reference':

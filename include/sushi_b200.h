@@ -94,13 +94,16 @@ int sb_set_premac_mode(int mode);
  * pays off only for templates shorter than B/2), 0 = chosen per batch by a cost rule.  Geometries
  * agree to float32 FFT rounding (~1e-7), not bit for bit, so a run should stick to one. */
 int sb_set_hop_mode(int mode);
-/* Body variant of the packed kernels (engines 2, 4, 5) on uint8 streams: 2 (default) = trimmed screening loop
- * (7 instead of 13 arithmetic instructions per lag), exact evaluation of the candidate lags from the staged
- * sample windows instead of two dependent reads of the running sums in HBM, prefetched self-mirrored quad,
- * barrier between loads and stores of an FFT pass in the middle of the butterfly; 1 = the first version.
- * Screening only selects the lags that get the exact fp64 evaluation and the window sums are exact integers
- * either way, so the two give identical results bit for bit (checked on the GPU by the test-suite); float32
- * streams and the other engines ignore the setting. */
+/* Body variant of the packed kernels (engines 2, 4, 5) on uint8 streams: 3 (default) = per run of 8 lags a lower
+ * and an upper bound of the screening values from the run's largest correlation value and its exact head sums; only
+ * the runs whose lower bound does not exceed the lag block's smallest upper bound can hold the minimum -- they leave
+ * the match kernel as records (query, first lag, 8 correlation values) and a second kernel evaluates their lags in
+ * fp64; window sums slide on the staged sample windows, per-query constants travel through shared memory, the
+ * self-mirrored quad is prefetched; 1 = the first version (fp32 screening of every lag and fp64 evaluation of the
+ * candidates inside the match kernel, running sums read from HBM).  Either way the result is the fp64 evaluation of
+ * every lag that can be the minimum, so the two agree bit for bit (checked on the GPU by the test-suite); float32
+ * streams and the other engines ignore the setting.  (2, the per-lag loop of 3 run over all lags, was measured and
+ * dropped in round 2.) */
 int sb_set_epilogue(int variant);
 int sb_get_epilogue(void);
 /* Lag blocks processed per multiply / inverse-FFT / normalise launch (>= 1). */

@@ -8,7 +8,9 @@ What runs unmodified from the reference:
     (wav.py:164-188) on instances built by the reference's own WavStream.__init__ (wav.py:108-162)
   * wav.WavStream.__init__ + DownmixedWavFile (wav.py:15-162) behind a bytes/str shim for the
     py2 string literals (wav.py:23,25,38,41) and np.fromstring -> np.frombuffer (wav.py:69);
-    int24 (wav.py:71-74) needs py2 integer division and is NOT covered by a golden vector.
+    the int24 branch (wav.py:71-74) divides two ints for an array length (`len(data) / 3`, an int under
+    Python 2): the module sees a numpy proxy whose zeros() accepts that float when it is a whole number
+    (gen_loader24 -> loader24.npz).
   * sushi.prepare_search_groups / calculate_shifts (sushi.py:319-508) after an in-memory, purely
     mechanical py2->py3 text transform listed in PY3_EDITS below (no reference source is copied
     into this repository; the transformed text only lives in memory).
@@ -62,6 +64,23 @@ refwav.Chunk = _ChunkCompat
 refwav.xrange = range
 refwav.reduce = functools.reduce
 np.fromstring = lambda data, dtype=float: np.frombuffer(bytes(data), dtype=dtype)   # wav.py:69
+
+
+class _NpPy2Division(object):
+    """numpy as wav.py sees it: identical, except that zeros() takes the float that `len(data) / 3` (wav.py:72) yields
+    under Python 3 -- under Python 2 that expression is an int; frames are whole, so the division is exact."""
+    def __getattr__(self, name):
+        return getattr(np, name)
+
+    @staticmethod
+    def zeros(shape, dtype=float):
+        if isinstance(shape, float):
+            assert shape.is_integer(), shape
+            shape = int(shape)
+        return np.zeros(shape, dtype)
+
+
+refwav.np = _NpPy2Division()
 
 PY3_EDITS = [
     ('from itertools import takewhile, izip, chain', 'from itertools import takewhile, chain\nizip = zip'),
@@ -133,6 +152,41 @@ def gen_loader():
         cases['{0}_spec'.format(name)] = np.array([fr, ch, sr], np.int64)
     np.savez_compressed(os.path.join(OUT, 'loader.npz'), **cases)
     print('loader.npz:', len(specs), 'cases')
+
+
+def write_wav24(path, values, framerate, channels):
+    """values: int array (frames, channels) of signed 24-bit samples -> RIFF/WAVE PCM with 3-byte samples."""
+    v = np.ascontiguousarray(values, np.int64) & 0xFFFFFF
+    raw = np.empty(v.shape + (3,), np.uint8)
+    raw[..., 0], raw[..., 1], raw[..., 2] = v & 0xFF, (v >> 8) & 0xFF, (v >> 16) & 0xFF
+    with wave.open(path, 'wb') as w:
+        w.setnchannels(channels)
+        w.setsampwidth(3)
+        w.setframerate(framerate)
+        w.writeframes(raw.tobytes())
+
+
+def gen_loader24():
+    """24-bit PCM through the reference's own readframes branch (wav.py:71-74: the top 16 bits of every sample):
+    the WAV files themselves are frozen (they are small), with the reference's WavStream.data for both sample types."""
+    rng = np.random.default_rng(24)
+    cases = {}
+    for name, fr, ch, secs in (('stereo48k_24', 48000, 2, 1.25), ('mono44k1_24', 44100, 1, 2.0), ('six48k_24', 48000, 6, 0.6)):
+        frames = int(round(secs * fr))
+        base = synth.programme_audio(frames, 240 + len(cases), rate=fr).astype(np.int64)
+        vals = np.empty((frames, ch), np.int64)
+        for c in range(ch):
+            vals[:, c] = np.clip(base * 256 * (c + 2) // (ch + 1) + rng.integers(-70000, 70000, frames), -2 ** 23, 2 ** 23 - 1)
+        tmp = '/tmp/_golden24.wav'
+        write_wav24(tmp, vals, fr, ch)
+        cases[name + '_wav'] = np.frombuffer(open(tmp, 'rb').read(), np.uint8)
+        for st in ('uint8', 'float32'):
+            s = refwav.WavStream(tmp, sample_rate=12000, sample_type=st)
+            cases['{0}_{1}_data'.format(name, st)] = s.data
+            cases['{0}_{1}_meta'.format(name, st)] = np.array([s.sample_rate, s.sample_count, s.padding_size], np.int64)
+        os.remove(tmp)
+    np.savez_compressed(os.path.join(OUT, 'loader24.npz'), **cases)
+    print('loader24.npz:', len(cases) // 5, 'cases')
 
 
 def gen_matcher():
@@ -247,9 +301,11 @@ def gen_shifts():
 
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ['loader', 'matcher', 'shifts']
+    which = sys.argv[1:] or ['loader', 'loader24', 'matcher', 'shifts']
     if 'loader' in which:
         gen_loader()
+    if 'loader24' in which:
+        gen_loader24()
     if 'matcher' in which:
         gen_matcher()
     if 'shifts' in which:

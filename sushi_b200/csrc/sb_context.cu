@@ -229,7 +229,7 @@ int sb_set_hop_mode(int mode) {
     return SB_OK;
 }
 int sb_set_epilogue(int variant) {
-    if (variant < 1 || variant > 3) SB_FAIL(SB_EINVAL, "sb_set_epilogue: %d is not 1 (first screening loop), 2 (trimmed screening loop) or 3 (run-level bounds, then the trimmed loop where needed)", variant);
+    if (variant != 1 && variant != 3) SB_FAIL(SB_EINVAL, "sb_set_epilogue: %d is not 1 (first version) or 3 (run-level bounds + k_finish_runs, the default); 2 was dropped in round 2", variant);
     ctx().epilogue = variant;
     return SB_OK;
 }

@@ -42,21 +42,9 @@
 using namespace sb;
 using namespace sbf;
 
-// Parts of the second kernel body (EPI 2) that can be compiled out one by one to attribute a measured difference
-// (make EXTRA=-DSB_V2_MIDBAR=0 ...): barrier placement in the FFT passes, prefetch of the self-mirrored quad.
-#ifndef SB_V2_MIDBAR
-#define SB_V2_MIDBAR 1
-#endif
-#ifndef SB_V2_MIDBAR_SPLIT      // last butterfly stage (h) in front of the barrier in passes 2 and 3: 4 (default) or 8
-#define SB_V2_MIDBAR_SPLIT 4
-#endif
+// The prefetch of the self-mirrored quad can be compiled out to attribute a measured difference (make EXTRA=-DSB_V2_SPECIAL_PREFETCH=0).
 #ifndef SB_V2_SPECIAL_PREFETCH
 #define SB_V2_SPECIAL_PREFETCH 1
-#endif
-// Inverse FFT of the product spectrum: 1 = decimation in frequency with warp-local passes 2 and 3 (two CTA-wide
-// barriers per transform, see fft_passes_dif), 0 = the first version (Stockham passes, six barriers).
-#ifndef SB_V2_DIF
-#define SB_V2_DIF 1
 #endif
 
 namespace {
@@ -74,25 +62,17 @@ constexpr int QROW = kQuadRowF2 / 2;      // float4 per row
 __host__ __device__ constexpr int qa(int i) { return i < Q4 ? (i >> 8) * (2 * QBLK) + (i & (QBLK - 1)) : 2 * Q4; }       // A chunk of quad i
 __host__ __device__ constexpr int qm(int i) { return i < Q4 ? qa(i) + QBLK : 2 * Q4 + 1; }                              // M chunk of quad i
 static_assert(QROW >= 2 * Q4 + 2 && (QROW * 16) % 128 == 0, "row layout");
-#if SB_V2_DIF
 // FFT buffer as [16][16][32] chunks with strides (529, 33, 1): element n of the transform's input sits at
 // [n / 512][(n / 32) % 16][n % 32]; both strides are 1 mod 16, which makes every access pattern of the three passes
 // and of the epilogue hit sixteen distinct 8-byte banks per half warp (fft_passes_dif).
 constexpr int kDA = 529, kDB = 33;
 constexpr int QPHYS = 16 * kDA;           // physical chunks of the padded FFT buffer
 constexpr int kUU = kDA;                  // distance between elements n and n + 512
-#else
-constexpr int QPHYS = QCH + QCH / 16;     // physical chunks of the padded FFT buffer
-constexpr int kUU = 544;                  // distance between elements n and n + 512
-#endif
 
 struct PackedTables {
-    const float4* tw2;    // [8][16]   (W256^(2a*k), W256^((2a+1)*k)) as (c0, s0, c1, s1), k = 0..15   (pass 2)
-    const float4* tw3;    // [8][256]  same with W4096, k = 0..255                                  (pass 3)
-    const float2* w8;     // [4096]    W8192^j                                                       (last radix-2 step)
     const float2* wb;     // [512]     exp(i*pi*t/B)                                                 (packing, per-thread base)
-    const float4* d1;     // [8][512]  (W8192^(2a*t), W8192^((2a+1)*t)), t = 0..511                  (DIF pass 1, after the butterfly)
-    const float4* d2;     // [8][32]   (W512^(2a*l), W512^((2a+1)*l)), l = 0..31                      (DIF pass 2, after the butterfly)
+    const float4* d1;     // [8][512]  (W8192^(2a*t), W8192^((2a+1)*t)) as (c0, s0, c1, s1), t = 0..511   (pass 1, after the butterfly)
+    const float4* d2;     // [8][32]   same with W512, l = 0..31                                           (pass 2, after the butterfly)
 };
 
 // exp(+i*pi*u/32), u = 0..7: the packing twiddle of quad i = t + 512u is wb[t] times this
@@ -156,11 +136,7 @@ __device__ __forceinline__ void dft16p(C2 (&v)[16]) {
 // (the register allocator does not keep the two pairs in one aligned quad, so a 128-bit store would cost four
 // MOVs; 64-bit accesses cost none).  One padding slot per 16 chunks makes the stride-16 scatter of pass 1 and
 // the epilogue's reads of chunks 2t, 2t+1 hit sixteen distinct 8-byte banks per half warp.
-#if SB_V2_DIF
 __device__ __forceinline__ constexpr int phys(int n) { return (n >> 9) * kDA + ((n >> 5) & 15) * kDB + (n & 31); }
-#else
-__device__ __forceinline__ constexpr int phys(int c) { return c + (c >> 4); }
-#endif
 struct Buf {
     float2* r; float2* i;
     __device__ __forceinline__ C2 ld(int p) const { return {r[p], i[p]}; }
@@ -345,94 +321,10 @@ __device__ __forceinline__ C2 special_from_smem(const float4* s_sp, int P, int g
     return lo;
 }
 
-// Three radix-16 Stockham passes over the 8192 (u, v) pairs.  Butterfly j = tid reads chunk j + 512r, twiddles
-// by exp(2*pi*i*r*k/(16*Ns)), k = j mod Ns, writes chunk (j-k)*16 + k + r*Ns; phys(j + 512r) = phys(j) + 544r.
-// Entered after a barrier that published buf; ends with a barrier.  Afterwards E = chunks [0, 4096),
-// O = chunks [4096, 8192): the half-size transforms are X'[j] = E[j] + W8192^j * O[j] (j < 4096; the "-" half
-// carries no valid lag), and chunk j of X' holds the correlation (times 2B) at lags 4j .. 4j+3 =
-// (u.re, u.im, v.re, v.im).
-// The barrier in the middle of a pass separates every thread's loads from every thread's stores (the passes are in
-// place).  MIDBAR = false (measured default) puts it right after the loads: all sixteen warps then wait until the
-// last load of the slowest warp has come back before anyone computes, so the 1024 cycles the shared-memory pipe
-// needs for a pass's loads are not overlapped by arithmetic.  MIDBAR = true (opt-in with EPI 2) puts it between
-// the second and the third butterfly stage -- the latest loads overlap the first half of the arithmetic of the
-// warps served earlier, the earliest stores the second half of the others'.  It also requests the twiddles of the
-// NEXT pass (and the epilogue's pair, which it returns) before the barrier that ends a pass, when the butterfly
-// registers are dead: the multiply phase streams hundreds of kilobytes through L1, so these table reads come from
-// L2, and the first thing a pass does with its data is multiply by them.
-template <int ID, bool MIDBAR = false>
-__device__ __forceinline__ float4 fft_passes(const Buf& buf, int tid, const PackedTables& tab, bool drain_cp_async) {
-    C2 v[16];
-    float4 tw[8];
-    float4 wt = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int src = phys(tid);
-    {   // pass 1: Ns = 1, no twiddles; out chunk 16j + r -> 17j + r
-#pragma unroll
-        for (int r = 0; r < 16; ++r) v[r] = buf.ld(src + 544 * r);
-        if (MIDBAR) { dft16p<8, 4>(v); csync<ID>(); dft16p<2, 1>(v); }
-        else { csync<ID>(); dft16p(v); }
-        const int dst = 17 * tid;
-#pragma unroll
-        for (int r = 0; r < 16; ++r) buf.st(dst + r, v[brev<16>(r)]);
-        if (MIDBAR) {
-#pragma unroll
-            for (int a = 0; a < 8; ++a) tw[a] = __ldg(tab.tw2 + a * 16 + (tid & 15));
-        }
-        csync<ID>();
-    }
-    {   // pass 2: Ns = 16, k = tid & 15; out chunk 256a + 16r + k -> 272a + 17r + k, a = tid >> 4
-        const int kk = tid & 15;
-        if (!MIDBAR) {
-#pragma unroll
-            for (int a = 0; a < 8; ++a) tw[a] = __ldg(tab.tw2 + a * 16 + kk);
-        }
-#pragma unroll
-        for (int r = 0; r < 16; ++r) v[r] = buf.ld(src + 544 * r);
-        if (!MIDBAR) csync<ID>();
-#pragma unroll
-        for (int r = 1; r < 16; ++r) {
-            const float4 t = tw[r >> 1];
-            v[r] = (r & 1) ? cmul_s(v[r], t.z, t.w) : cmul_s(v[r], t.x, t.y);
-        }
-        if (MIDBAR) { dft16p<8, SB_V2_MIDBAR_SPLIT>(v); csync<ID>(); dft16p<SB_V2_MIDBAR_SPLIT / 2, 1>(v); }
-        else dft16p(v);
-        const int dst = 272 * (tid >> 4) + kk;
-#pragma unroll
-        for (int r = 0; r < 16; ++r) buf.st(dst + 17 * r, v[brev<16>(r)]);
-        if (MIDBAR) {
-#pragma unroll
-            for (int a = 0; a < 8; ++a) tw[a] = __ldg(tab.tw3 + a * 256 + (tid & 255));
-        }
-        csync<ID>();
-    }
-    {   // pass 3: Ns = 256, k = tid & 255; out chunk 4096a + 256r + k -> 4352a + 272r + phys(k), a = tid >> 8
-        const int kk = tid & 255;
-        if (!MIDBAR) {
-#pragma unroll
-            for (int a = 0; a < 8; ++a) tw[a] = __ldg(tab.tw3 + a * 256 + kk);
-        }
-#pragma unroll
-        for (int r = 0; r < 16; ++r) v[r] = buf.ld(src + 544 * r);
-        if (!MIDBAR) csync<ID>();
-#pragma unroll
-        for (int r = 1; r < 16; ++r) {
-            const float4 t = tw[r >> 1];
-            v[r] = (r & 1) ? cmul_s(v[r], t.z, t.w) : cmul_s(v[r], t.x, t.y);
-        }
-        if (MIDBAR) { dft16p<8, SB_V2_MIDBAR_SPLIT>(v); csync<ID>(); dft16p<SB_V2_MIDBAR_SPLIT / 2, 1>(v); }
-        else dft16p(v);
-        const int dst = 4352 * (tid >> 8) + phys(kk);
-#pragma unroll
-        for (int r = 0; r < 16; ++r) buf.st(dst + 272 * r, v[brev<16>(r)]);
-        if (MIDBAR) wt = __ldg(reinterpret_cast<const float4*>(tab.w8) + tid);    // W8192^(2tid), W8192^(2tid+1) for the epilogue
-        if (drain_cp_async) cp_async_commit_wait_all();     // the staged running sums landed long ago
-        csync<ID>();
-    }
-    return wt;
-}
-
-#if SB_V2_DIF
-// The same transform by decimation in frequency, n = 512a + 32b + 2c + m  ->  k = k1 + 16 k2 + 256 k3 + 4096 k4:
+// Inverse FFT of the packed product spectrum: 8192 (u, v) pairs.  Afterwards chunk j of the half-size transforms
+// X'[j], j < 4096 (the other half carries no valid lag), holds the correlation (times 2B) at lags 4j .. 4j+3 =
+// (u.re, u.im, v.re, v.im), up to the last radix-2 step, which is the epilogue's.
+// Decimation in frequency, n = 512a + 32b + 2c + m  ->  k = k1 + 16 k2 + 256 k3 + 4096 k4:
 //   pass 1  thread t, over a:  y[k1][t]  = W8192^(t k1) * sum_a x[a][t] W16^(a k1)       t = 32b + 2c + m
 //   pass 2  warp k1, lane l, over b:  z[k2][l] = W512^(l k2) * sum_b y[b][l] W16^(b k2)   l = 2c + m
 //   pass 3  warp k1, lane (k2, m), over c:  r[k3][m] = sum_c z[c][m] W16^(c k3)           (its twiddle W32^(m k3) and
@@ -491,19 +383,6 @@ __device__ __forceinline__ void fft_passes_dif(const Buf& buf, int tid, const Pa
         csync<ID>();
     }
 }
-#endif
-
-// The inverse transform the kernels call; the value it returns is the epilogue's twiddle pair when the Stockham passes
-// fetched it early (EPI 2), unused otherwise.
-template <int ID, int EPI>
-__device__ __forceinline__ float4 inverse_fft(const Buf& buf, int tid, const PackedTables& tab, bool drain_cp_async) {
-#if SB_V2_DIF
-    fft_passes_dif<ID>(buf, tid, tab, drain_cp_async);
-    return make_float4(0.f, 0.f, 0.f, 0.f);
-#else
-    return fft_passes<ID, EPI >= 2 && SB_V2_MIDBAR>(buf, tid, tab, drain_cp_async);
-#endif
-}
 
 // EPI 2: the constants of a query every thread needs in finish_item -- sums of the template (two reads of its
 // running sums) and the two centres (two fp64 divisions) -- by ONE thread at the start of the CTA's work on the
@@ -542,11 +421,12 @@ __device__ __forceinline__ void finish_item(const Item& it, int tid, const Smem&
                                             const double2* __restrict__ ipfx, const double2* __restrict__ tpfx,
                                             const PackedTables& tab, unsigned long long* __restrict__ keys,
                                             float* __restrict__ curve_out, AfterRead after_read,
-                                            float4 wt_in = make_float4(0.f, 0.f, 0.f, 0.f), RunSink sink = RunSink{nullptr, nullptr}) {
+                                            RunSink sink = RunSink{nullptr, nullptr}) {
     constexpr int B = QB, NW = QNW, LB = QB, ROUNDS = kRounds, LAGS_PER_ROUND = kLagsPerRound;
     constexpr bool is_u8 = sizeof(S) == 1;
-    constexpr bool v2 = EPI >= 2 && is_u8;                 // trimmed screening (see the comment at its loop)
+    constexpr bool v2 = EPI >= 2 && is_u8;                 // second-generation body: everything from the staged windows, constants via shared memory
     constexpr bool v3 = EPI == 3 && is_u8;                 // run-level bounds first, per-lag screening only where a run can hold the minimum
+    static_assert(EPI == 1 || EPI == 3, "body variants: 1 (first version, all sample types) and 3 (uint8 streams); 2 was measured and dropped in round 2");
     constexpr float kSent = v2 ? 3.0e38f : 2.0f;           // screening value of a lag outside the query's range
     const float* img32 = reinterpret_cast<const float*>(img);
     const Buf& buf = sm.buf;
@@ -573,17 +453,10 @@ __device__ __forceinline__ void finish_item(const Item& it, int tid, const Smem&
     const bool interior = j_blk >= jlo && j_blk + LB <= jhi;
 
     // chunks 2*tid, 2*tid+1 of every round: physical offsets and twiddles
-#if SB_V2_DIF
     // chunk 1024c + 2tid + e = k1 + 16 k2 + 256 k3: k1 = 2(tid % 8) + e, k2 = (tid / 8) % 16, k3 = 4c + tid / 128; its
     // two halves r[k3][0], r[k3][1] are neighbours, and the twiddle W32^k3 = W32^(tid/128) * W8^c depends on the warp only
     const int ech = 2 * (tid & 7) * kDA + ((tid >> 3) & 15) * kDB + 2 * (tid >> 7);      // + kDA*e + 8*c; second half 1 further
     const float4 wt = make_float4(kC32[tid >> 7], kS32[tid >> 7], kC32[tid >> 7], kS32[tid >> 7]);
-    (void)wt_in;
-#else
-    const int ech = 2 * tid + (tid >> 3);                              // + 1088*c + e; O is 4352 further
-    // W8192^(2tid), W8192^(2tid+1): requested by the last FFT pass already when it ran with MIDBAR (EPI 2)
-    const float4 wt = (v2 && SB_V2_MIDBAR) ? wt_in : __ldg(reinterpret_cast<const float4*>(tab.w8) + tid);
-#endif
 
     float vf[ROUNDS][8];
     float tmin = kSent;
@@ -614,11 +487,7 @@ __device__ __forceinline__ void finish_item(const Item& it, int tid, const Smem&
         float cc[8];
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-#if SB_V2_DIF
             const C2 E = buf.ld(ech + kDA * e + 8 * c), O = buf.ld(ech + kDA * e + 8 * c + 1);
-#else
-            const C2 E = buf.ld(ech + 1088 * c + e), O = buf.ld(ech + 1088 * c + e + 4352);
-#endif
             float wc = e ? wt.z : wt.x, ws = e ? wt.w : wt.y;          // W8192^(2tid+e) ...
             {                                                          // ... times exp(2*pi*i*c/8)
                 const float h = 0.70710678118654752f;
@@ -696,34 +565,6 @@ __device__ __forceinline__ void finish_item(const Item& it, int tid, const Smem&
             if (inside && f_w0q > 4.0f * kRunQ && ubn >= 0.f) tmin = fminf(tmin, ubv);
             continue;
         }
-        if constexpr (v2) {
-            // Trimmed screening (uint8).  The screening values only select which lags get the exact fp64
-            // evaluation below, so they may be any quantity that (a) orders the lags like the true value to within
-            // the screening margin and (b) makes saturated / degenerate blocks fall back to "evaluate everything":
-            //   v' = (A + rq - 2b*rs - 2*scale*cc) * rsqrt(wq)  =  value * sqrt(sum T^2),
-            // A = w0q + sum T^2 - 2(b*w0s + k) rounded once from fp64 -- 7 instructions per lag instead of 13
-            // (no clamps, no product with sum T^2, the 2*sit doubling folded into the constants); bytes come out
-            // of the staged words by PRMT, and the interior / border distinction is hoisted out of the lag loop.
-            const unsigned la = (unsigned)lo8, lb = (unsigned)(lo8 >> 32), ha = (unsigned)hi8, hb2 = (unsigned)(hi8 >> 32);
-            auto run8 = [&](auto border_tag) {
-                constexpr bool BORDER = decltype(border_tag)::value;
-                int rq = 0, rs = 0;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const float frq = (float)rq;
-                    const float num = fmaf(cc[i], m2s, fmaf(m2b, (float)rs, f_A + frq));
-                    const float v = num * rsqrt_fast(f_w0q + frq);
-                    if (!BORDER || (j0 + i >= jlo && j0 + i < jhi)) { vf[c][i] = v; tmin = fminf(tmin, v); }
-                    else vf[c][i] = kSent;
-                    const unsigned sel = 0x4440u | (unsigned)(i & 3);
-                    const int lo = (int)__byte_perm(i < 4 ? la : lb, 0u, sel), hi = (int)__byte_perm(i < 4 ? ha : hb2, 0u, sel);
-                    const int dd = hi - lo;
-                    rq += (hi + lo) * dd; rs += dd;
-                }
-            };
-            if (interior) run8(BoolTag<false>{}); else run8(BoolTag<true>{});
-            continue;
-        }
         int rq = 0, rs = 0;              // uint8: exact integer slide
         double dq = 0.0, ds = 0.0;       // float32: fp64 slide
 #pragma unroll
@@ -792,14 +633,9 @@ __device__ __forceinline__ void finish_item(const Item& it, int tid, const Smem&
 #pragma unroll
                         for (int e = 0; e < 2; ++e) {       // chunks jj = m0/4 + e, exactly as the exact path below forms them
                             const int jj = (m0 >> 2) + e;
-#if SB_V2_DIF
                             const int ca = (jj & 15) * kDA + ((jj >> 4) & 15) * kDB + 2 * (jj >> 8);
                             const C2 E = buf.ld(ca), O = buf.ld(ca + 1);
                             const float2 w = make_float2(kC32[jj >> 8], kS32[jj >> 8]);
-#else
-                            const C2 E = buf.ld(phys(jj)), O = buf.ld(phys(jj) + 4352);
-                            const float2 w = __ldg(tab.w8 + jj);
-#endif
                             const float2 xr = fma2(O.r, bc(w.x), fma2(O.i, bc(-w.y), E.r));
                             const float2 xi = fma2(O.r, bc(w.y), fma2(O.i, bc(w.x), E.i));
                             cc[4 * e + 0] = xr.x; cc[4 * e + 1] = xi.x; cc[4 * e + 2] = xr.y; cc[4 * e + 3] = xi.y;
@@ -826,11 +662,7 @@ __device__ __forceinline__ void finish_item(const Item& it, int tid, const Smem&
             const float wc = wt.x * rc - wt.y * rs8, ws = wt.x * rs8 + wt.y * rc;
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-#if SB_V2_DIF
                 const C2 E = buf.ld(ech + kDA * e + 8 * c), O = buf.ld(ech + kDA * e + 8 * c + 1);
-#else
-                const C2 E = buf.ld(ech + 1088 * c + e), O = buf.ld(ech + 1088 * c + e + 4352);
-#endif
                 const float2 xr = fma2(O.r, bc(wc), fma2(O.i, bc(-ws), E.r));
                 const float2 xi = fma2(O.r, bc(ws), fma2(O.i, bc(wc), E.i));
                 cc[4 * e + 0] = xr.x; cc[4 * e + 1] = xi.x; cc[4 * e + 2] = xr.y; cc[4 * e + 3] = xi.y;
@@ -880,14 +712,9 @@ __device__ __forceinline__ void finish_item(const Item& it, int tid, const Smem&
         const int m = (bit >> 3) * LAGS_PER_ROUND + tid * 8 + (bit & 7);
         const int64_t j = j_blk + m;
         const int jj = m >> 2;                                          // chunk of X'
-#if SB_V2_DIF
         const int ca = (jj & 15) * kDA + ((jj >> 4) & 15) * kDB + 2 * (jj >> 8);
         const C2 E = buf.ld(ca), O = buf.ld(ca + 1);
         const float2 w = make_float2(kC32[jj >> 8], kS32[jj >> 8]);
-#else
-        const C2 E = buf.ld(phys(jj)), O = buf.ld(phys(jj) + 4352);
-        const float2 w = __ldg(tab.w8 + jj);
-#endif
         const bool second = (m & 2) != 0;                               // lags 4j+2, 4j+3 belong to v
         const float er = second ? E.r.y : E.r.x, ei = second ? E.i.y : E.i.x, orr = second ? O.r.y : O.r.x, oi = second ? O.i.y : O.i.x;
         const float xr = fmaf(orr, w.x, fmaf(oi, -w.y, er)), xi = fmaf(orr, w.y, fmaf(oi, w.x, ei));
@@ -1038,8 +865,8 @@ k_match_packed(const float4* __restrict__ That, int64_t part_first,
     csync<0>();
 
     // ---------------- 3. inverse FFT, 4. epilogue ---------------------------------------------
-    const float4 wt0 = inverse_fft<0, EPI>(buf, tid, tab, is_u8);
-    finish_item<S, 0, EPI>(it, tid, sm, s_bar, 0u, s_best, s_min, s_w0, img, img_n, ipfx, tpfx, tab, keys, curve_out, [] {}, wt0, sink);
+    fft_passes_dif<0>(buf, tid, tab, is_u8);
+    finish_item<S, 0, EPI>(it, tid, sm, s_bar, 0u, s_best, s_min, s_w0, img, img_n, ipfx, tpfx, tab, keys, curve_out, [] {}, sink);
     if (EPI == 3 && rec_count && tid == 0) rec_count[blockIdx.x] = *s_cnt < kRunSlots ? *s_cnt : kRunSlots;    // behind the closing barrier of finish_item
 }
 
@@ -1203,17 +1030,17 @@ k_match_pair(const float4* __restrict__ That, int64_t part_first,
     csync<0>();
 
     // ---------------- first item: inverse FFT + epilogue ---------------------------------------
-    const float4 wt0 = inverse_fft<0, EPI>(buf, tid, tab, is_u8);
+    fft_passes_dif<0>(buf, tid, tab, is_u8);
     finish_item<S, 0, EPI>(it0, tid, sm, s_bar, 0u, s_best, s_min, s_w0, img, img_n, ipfx, tpfx, tab, keys, curve_out,
-                      [&] { if (is_u8 && has2) stage_inputs(it1, tid, reinterpret_cast<const uint8_t*>(img), img_n, ipfx, sm, s_bar); }, wt0, sink);
+                      [&] { if (is_u8 && has2) stage_inputs(it1, tid, reinterpret_cast<const uint8_t*>(img), img_n, ipfx, sm, s_bar); }, sink);
 
     // ---------------- second item: out of tensor memory, then the same ---------------------------
     if (has2) {                                       // uniform over the CTA
         unpark<EPI >= 2>(tcol, buf, col, mcol, tid);
         if (tid == (NW - 1) * 32) buf.st(phys(Q4), sp1);
         csync<0>();
-        const float4 wtj = inverse_fft<0, EPI>(buf, tid, tab, is_u8);
-        finish_item<S, 0, EPI>(it1, tid, sm, s_bar, 1u, s_best, s_min, s_w0, img, img_n, ipfx, tpfx, tab, keys, curve_out, [] {}, wtj, sink);
+        fft_passes_dif<0>(buf, tid, tab, is_u8);
+        finish_item<S, 0, EPI>(it1, tid, sm, s_bar, 1u, s_best, s_min, s_w0, img, img_n, ipfx, tpfx, tab, keys, curve_out, [] {}, sink);
     }
     tmem_fence_before();
     csync<0>();
@@ -1353,13 +1180,13 @@ size_t packed_smem_bytes(int epi = 1) {      // epilogue 2 keeps the runs' exact
                     : kSmemCommon + 8 + QNW * sizeof(unsigned long long) + QNW * sizeof(float) + 64;
 }
 
-// Values of the tables of PackedTables, in one array: offsets of tw2, tw3, w8, wb, d1, d2 in `off` (floats)
-constexpr int kPackedTableCount = 6;
+// Values of the tables of PackedTables, in one array: offsets of wb, d1, d2 in `off` (floats)
+constexpr int kPackedTableCount = 3;
 std::vector<float> packed_table_values(size_t (&off)[kPackedTableCount]) {
     const double pi = 3.14159265358979323846;
-    const size_t n2 = 8 * 16 * 4, n3 = 8 * 256 * 4, n8 = 4096 * 2, nb = 512 * 2, nd1 = 8 * 512 * 4, nd2 = 8 * 32 * 4;
-    off[0] = 0; off[1] = n2; off[2] = n2 + n3; off[3] = n2 + n3 + n8; off[4] = off[3] + nb; off[5] = off[4] + nd1;
-    std::vector<float> h(off[5] + nd2);
+    const size_t nb = 512 * 2, nd1 = 8 * 512 * 4, nd2 = 8 * 32 * 4;
+    off[0] = 0; off[1] = nb; off[2] = nb + nd1;
+    std::vector<float> h(off[2] + nd2);
     // (W_N^((2a)*k), W_N^((2a+1)*k)) as (c0, s0, c1, s1), a = 0..7, k = 0..K-1
     auto pairs = [&](size_t at, int K, double N) {
         for (int a = 0; a < 8; ++a)
@@ -1369,23 +1196,17 @@ std::vector<float> packed_table_values(size_t (&off)[kPackedTableCount]) {
                     h[at + ((size_t)a * K + k) * 4 + 2 * e] = (float)cos(ang); h[at + ((size_t)a * K + k) * 4 + 2 * e + 1] = (float)sin(ang);
                 }
     };
-    pairs(off[0], 16, 256.0);
-    pairs(off[1], 256, 4096.0);
-    for (int j = 0; j < 4096; ++j) { h[off[2] + 2 * j] = (float)cos(2.0 * pi * j / 8192.0); h[off[2] + 2 * j + 1] = (float)sin(2.0 * pi * j / 8192.0); }
-    for (int t = 0; t < 512; ++t) { h[off[3] + 2 * t] = (float)cos(pi * t / QB); h[off[3] + 2 * t + 1] = (float)sin(pi * t / QB); }
-    pairs(off[4], 512, 8192.0);
-    pairs(off[5], 32, 512.0);
+    for (int t = 0; t < 512; ++t) { h[off[0] + 2 * t] = (float)cos(pi * t / QB); h[off[0] + 2 * t + 1] = (float)sin(pi * t / QB); }
+    pairs(off[1], 512, 8192.0);
+    pairs(off[2], 32, 512.0);
     return h;
 }
 
 PackedTables packed_tables_at(const float* base, const size_t (&off)[kPackedTableCount]) {
     PackedTables t;
-    t.tw2 = reinterpret_cast<const float4*>(base + off[0]);
-    t.tw3 = reinterpret_cast<const float4*>(base + off[1]);
-    t.w8 = reinterpret_cast<const float2*>(base + off[2]);
-    t.wb = reinterpret_cast<const float2*>(base + off[3]);
-    t.d1 = reinterpret_cast<const float4*>(base + off[4]);
-    t.d2 = reinterpret_cast<const float4*>(base + off[5]);
+    t.wb = reinterpret_cast<const float2*>(base + off[0]);
+    t.d1 = reinterpret_cast<const float4*>(base + off[1]);
+    t.d2 = reinterpret_cast<const float4*>(base + off[2]);
     return t;
 }
 
@@ -1532,8 +1353,7 @@ int launch_pair_typed(const sb_stream* image, const sb_stream* tmpl, const float
 // One instantiation per (sample type, epilogue): float32 streams have the first screening loop only.
 #define SB_DISPATCH_MATCH(FN, image, ...) \
     ((image)->dtype != SB_U8 ? FN<float, 1>(image, __VA_ARGS__) \
-     : ctx().epilogue == 3   ? FN<uint8_t, 3>(image, __VA_ARGS__) \
-     : ctx().epilogue == 2   ? FN<uint8_t, 2>(image, __VA_ARGS__) : FN<uint8_t, 1>(image, __VA_ARGS__))
+     : ctx().epilogue == 3   ? FN<uint8_t, 3>(image, __VA_ARGS__) : FN<uint8_t, 1>(image, __VA_ARGS__))
 
 }  // namespace
 

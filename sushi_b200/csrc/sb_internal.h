@@ -59,7 +59,7 @@ struct Ctx {
     int chunk_items = 1024;        // items per MAC/C2R/normalise chunk (cuFFT engine)
     int engine = 2;                // 2: packed fused kernels (sb_fused2.cu, B = 16384; default), 4 / 5: always / never pairs of lag blocks, 1: fused lag-block kernel (sb_fused.cu), 0: cuFFT pipeline
     int premac_mode = 0;           // 0: register-blocked multiply kernel for queries whose template spans >= 12 partitions, 1: never, 2: always
-    int epilogue = 2;              // screening loop of the packed kernels on uint8 streams: 2 = trimmed (default), 1 = first version (sb_set_epilogue)
+    int epilogue = 3;              // body of the packed kernels on uint8 streams: 3 = run-level bounds + k_finish_runs (default), 1 = first version (sb_set_epilogue)
     int hop_mode = 1;              // fused engine geometry: 1 = hop B (50 % of each FFT valid, default), 2 = hop B/2 (75 %), 0 = pick per batch
     int64_t max_parts = 16384;     // template partition spectra kept per super-chunk
 

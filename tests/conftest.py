@@ -24,6 +24,12 @@ def golden_loader():
 
 
 @pytest.fixture(scope='session')
+def golden_loader24():
+    """24-bit WAV files and what the reference's own loader makes of them (oracle/gen_golden.py gen_loader24)."""
+    return np.load(os.path.join(GOLDEN, 'loader24.npz'))
+
+
+@pytest.fixture(scope='session')
 def golden_matcher():
     return np.load(os.path.join(GOLDEN, 'matcher.npz'))
 

@@ -82,7 +82,7 @@ void run_cta(const std::function<void(int)>& body) {
 extern "C" {
 
 int emu_table_floats(void) { size_t off[kPackedTableCount]; return (int)packed_table_values(off).size(); }
-int emu_smem_bytes(void) { return (int)packed_smem_bytes(2) + 16; }
+int emu_smem_bytes(void) { return (int)packed_smem_bytes(3) + 16; }
 int emu_query_desc_bytes(void) { return (int)sizeof(sb::QueryDesc); }
 int emu_quad_row_floats(void) { return QROW * 4; }
 
@@ -112,7 +112,7 @@ int emu_run(int kernel, int epi, int is_u8, const float* That, int64_t part_firs
             blockIdx = {(unsigned)b, 0, 0};       // threadIdx and the lane / warp numbers are set by run_cta
 #define SB_EMU_ARGS(S) T4, part_first, X4, nblk, static_cast<const S*>(img), img_n, ip, tp, d, cta_query, first
 #define SB_EMU_CALL(K, S, E, ...) K<S, E>(SB_EMU_ARGS(S), ##__VA_ARGS__, tab, keys, curve_out, static_cast<RunRecord*>(run_recs), run_count)
-#define SB_EMU_KERNEL(K, ...) do { if (!is_u8) SB_EMU_CALL(K, float, 1, ##__VA_ARGS__); else if (epi == 3) SB_EMU_CALL(K, uint8_t, 3, ##__VA_ARGS__); else if (epi == 2) SB_EMU_CALL(K, uint8_t, 2, ##__VA_ARGS__); \
+#define SB_EMU_KERNEL(K, ...) do { if (!is_u8) SB_EMU_CALL(K, float, 1, ##__VA_ARGS__); else if (epi == 3) SB_EMU_CALL(K, uint8_t, 3, ##__VA_ARGS__); \
                                    else SB_EMU_CALL(K, uint8_t, 1, ##__VA_ARGS__); } while (0)
             if (kernel == 0) SB_EMU_KERNEL(k_match_packed);
             else SB_EMU_KERNEL(k_match_pair);

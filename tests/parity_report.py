@@ -41,4 +41,4 @@ for stype in ('uint8', 'float32'):
                 {0: 'cufft', 1: 'fused', 2: 'packed', 4: 'packed_pair', 5: 'packed_single'}[engine]
                 + ('/body1' if epilogue == 1 and engine >= 2 else '')))
     _native.check(lib.sb_set_engine(2))
-    _native.check(lib.sb_set_epilogue(2))
+    _native.check(lib.sb_set_epilogue(3))

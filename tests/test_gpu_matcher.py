@@ -290,6 +290,22 @@ def test_gpu_loader_equals_host_mirror_on_long_stream(gpu_lib):
         assert abs(a.min_value - b.min_value) == 0 and abs(a.max_value - b.max_value) == 0
 
 
+@pytest.mark.parametrize('name', ['stereo48k_24', 'mono44k1_24', 'six48k_24'])
+@pytest.mark.parametrize('stype', ['uint8', 'float32'])
+def test_gpu_loader_matches_reference_golden_int24(gpu_lib, golden_loader24, tmp_path, name, stype):
+    """24-bit files through the public constructor (GPU decode of bytes 1 and 2 of every sample) against the
+    reference's own WavStream.data, bit for bit."""
+    g = golden_loader24
+    p = str(tmp_path / 'x.wav')
+    open(p, 'wb').write(g[name + '_wav'].tobytes())
+    s = WavStream(p, 12000, stype)
+    ref = g['{0}_{1}_data'.format(name, stype)]
+    rate, count, pad = [int(v) for v in g['{0}_{1}_meta'.format(name, stype)]]
+    assert (s.sample_rate, int(s.sample_count), s.padding_size) == (rate, count, pad)
+    assert s.data.dtype == ref.dtype and np.array_equal(s.data, ref)
+    s.close()
+
+
 def test_wav_file_load_int24(gpu_lib, tmp_path):
     """RIFF file with 24-bit samples through the public constructor (GPU loader) vs the oracle."""
     import struct

@@ -1,10 +1,12 @@
-"""The two body variants of the packed kernels on uint8 streams (sb_set_epilogue): 2 is the default since
-round 2 (measured +6 % on BASELINE config 2), 1 is the first version.  Screening only selects the lags that get
-the exact fp64 evaluation, so every result must agree BIT FOR BIT -- whole curves included (the debug curve
-path evaluates every lag exactly under both variants) -- over pairs of lag blocks (engine 4) and single lag
-blocks (engine 5).  Runs with the plain `pytest -m gpu` (no opt-in gate): a variant that fails here is deleted,
-not skipped.  Dropped in round 2 after measurement: triples of lag blocks, 16-bit spectrum rows, the
-warp-specialised kernel (profiles/README.md)."""
+"""The body variants of the packed kernels on uint8 streams (sb_set_epilogue): 3 is the default since round 2 --
+run-level bounds pick the few runs of 8 lags that can hold a lag block's minimum, those leave the match kernel as
+records and k_finish_runs evaluates them in fp64 -- and 1 is the first version (everything inside the match kernel).
+Screening of either kind only selects the lags that get the exact fp64 evaluation, so every result must agree BIT FOR
+BIT -- whole curves included (the debug curve path evaluates every lag exactly under both variants) -- over pairs of
+lag blocks (engine 4) and single lag blocks (engine 5).  Runs with the plain `pytest -m gpu` (no opt-in gate): a
+variant that fails here is deleted, not skipped.  Dropped in round 2 after measurement: the trimmed per-lag loop over
+all lags (variant 2), triples of lag blocks, 16-bit spectrum rows, the warp-specialised kernel, the Stockham FFT passes
+(profiles/README.md)."""
 import numpy as np
 import pytest
 
@@ -21,7 +23,7 @@ def epilogue(gpu_lib):
         _native.check(gpu_lib.sb_set_epilogue(variant))
     yield use
     _native.check(gpu_lib.sb_set_engine(2))
-    _native.check(gpu_lib.sb_set_epilogue(2))
+    _native.check(gpu_lib.sb_set_epilogue(3))
 
 
 def _streams(dur, seed, stype='uint8'):
@@ -38,11 +40,11 @@ def test_trimmed_epilogue_is_bit_identical_on_batches(gpu_lib, epilogue, engine)
     starts, ends = synth.make_events(300, 240.0, 12, 0.5, 6.0)
     win = np.full(len(starts), 30.0)
     out = {}
-    for variant in (1, 2, 3):
+    for variant in (1, 3):
         epilogue(variant, engine)
         assert gpu_lib.sb_get_epilogue() == variant
         out[variant] = dst.find_substream_batch(src, starts, ends, starts, win)
-    for variant in (2, 3):
+    for variant in (3,):
         assert np.array_equal(out[1][0], out[variant][0])
         assert np.array_equal(out[1][1], out[variant][1])
     # and they are right: the known shift comes back
@@ -58,10 +60,10 @@ def test_trimmed_epilogue_curves_and_ragged_ranges(gpu_lib, epilogue, engine):
              (5000, 3000, 16383, 16386), (7, 700, 1, 5), (40000, 20000, 32768, 16384)]
     for toff, n, lag0, nlags in cases:
         got = {}
-        for variant in (1, 2, 3):
+        for variant in (1, 3):
             epilogue(variant, engine)
             got[variant] = (dst.match_curve(src, toff, n, lag0, nlags), dst.find_planned(src, [toff], [n], [lag0], [nlags]))
-        for variant in (2, 3):
+        for variant in (3,):
             assert np.array_equal(got[1][0], got[variant][0])
             assert got[1][1][0][0] == got[variant][1][0][0] and got[1][1][1][0] == got[variant][1][1][0]
         assert got[2][1][1][0] == int(got[2][0].argmin()) and got[2][1][0][0] == got[2][0].min()
@@ -80,7 +82,7 @@ def test_trimmed_epilogue_degenerate_inputs(gpu_lib, epilogue, golden_matcher):
     gap = rng.integers(0, 256, (1, 40000), dtype=np.uint8)
     gap[0, 9000:31000] = 0                                     # a long silent stretch inside programme material
     gapped = mk(gap)
-    for engine, body in ((4, 2), (5, 2), (4, 3), (5, 3)):
+    for engine, body in ((4, 3), (5, 3)):
         epilogue(body, engine)
         assert np.array_equal(z.match_curve(seven, 0, 8, 0, 57), g['deg_zero_window'])
         assert np.array_equal(nine.match_curve(z, 0, 8, 0, 57), g['deg_zero_template'])
@@ -91,17 +93,18 @@ def test_trimmed_epilogue_degenerate_inputs(gpu_lib, epilogue, golden_matcher):
         diff, idx = z.find_planned(seven, [0], [8], [0], [57])
         assert idx[0] == 0 and diff[0] == 1.0                   # all saturated: FIRST index
         res = {}
-        for variant in (1, 2, 3):
+        for variant in (1, 3):
             epilogue(variant, engine)
             res[variant] = (gapped.match_curve(gapped, 12000, 6000, 0, 34001),
                             gapped.find_planned(gapped, [12000, 100, 33000], [6000, 5000, 5000], [0, 8000, 0], [34001, 20000, 35001]))
-        for variant in (2, 3):
+        for variant in (3,):
             assert np.array_equal(res[1][0], res[variant][0])
             assert np.array_equal(res[1][1][0], res[variant][1][0]) and np.array_equal(res[1][1][1], res[variant][1][1])
 
 
-def test_default_is_the_trimmed_body(gpu_lib):
-    assert gpu_lib.sb_get_epilogue() == 2 and gpu_lib.sb_get_engine() == 2
+def test_default_is_the_third_body(gpu_lib):
+    assert gpu_lib.sb_get_epilogue() == 3 and gpu_lib.sb_get_engine() == 2
+    assert gpu_lib.sb_set_epilogue(2) != 0 and gpu_lib.sb_get_epilogue() == 3      # the dropped variant is refused
     assert gpu_lib.sb_set_engine(3) != 0 and gpu_lib.sb_set_engine(6) != 0      # dropped engines are refused
     assert gpu_lib.sb_get_engine() == 2
 
@@ -119,7 +122,7 @@ def test_pairs_are_bit_identical_to_single_lag_blocks(gpu_lib, epilogue, stype):
     for toff, n, lag0, nlags in cases:
         got = {}
         for engine in (5, 4):
-            epilogue(2, engine)
+            epilogue(3, engine)
             got[engine] = (dst.match_curve(src, toff, n, lag0, nlags), dst.find_planned(src, [toff], [n], [lag0], [nlags]))
         assert np.array_equal(got[5][0], got[4][0]), (toff, n, lag0, nlags)
         assert got[5][1][0][0] == got[4][1][0][0] and got[5][1][1][0] == got[4][1][1][0]
@@ -131,7 +134,7 @@ def test_pairs_are_bit_identical_to_single_lag_blocks(gpu_lib, epilogue, stype):
     win = np.full(len(starts), 20.0)
     res = {}
     for engine in (5, 4):
-        epilogue(2, engine)
+        epilogue(3, engine)
         res[engine] = dst.find_substream_batch(src, starts, ends, starts, win)
     assert np.array_equal(res[5][0], res[4][0]) and np.array_equal(res[5][1], res[4][1])
 
@@ -146,7 +149,7 @@ def test_many_partition_templates_without_the_blocked_route(gpu_lib, epilogue, e
     starts = np.array([20.5, 61.25, 110.0])
     ends = starts + np.array([30.0, 17.0, 24.5])         # 22, 13 and 18 partitions
     win = np.full(3, 40.0)
-    epilogue(2, engine)
+    epilogue(3, engine)
     want = dst.find_substream_batch(src, starts, ends, starts, win)
     _native.check(gpu_lib.sb_set_premac_mode(1))
     try:

@@ -55,6 +55,28 @@ def test_nearest_index_map_is_cv2_resize(n_in, n_out):
     assert np.array_equal(wavstream.nearest_index_map(n_in, n_out), want)
 
 
+@pytest.mark.parametrize('name', ['stereo48k_24', 'mono44k1_24', 'six48k_24'])
+@pytest.mark.parametrize('stype', ['uint8', 'float32'])
+def test_host_loader_matches_reference_golden_int24(golden_loader24, tmp_path, name, stype):
+    """The product's RIFF walk + readframes + NumPy loader mirror on the frozen 24-bit files against the reference's
+    own output (no GPU: the upload step is skipped)."""
+    g = golden_loader24
+    p = str(tmp_path / 'x.wav')
+    open(p, 'wb').write(g[name + '_wav'].tobytes())
+    f = wavstream.DownmixedWavFile(p)
+    try:
+        assert f.sample_width == 3
+        s = object.__new__(WavStream)
+        s._handle = None
+        s._load(f, 12000, stype)
+    finally:
+        f.close()
+    ref = g['{0}_{1}_data'.format(name, stype)]
+    rate, count, pad = [int(v) for v in g['{0}_{1}_meta'.format(name, stype)]]
+    assert (s.sample_rate, int(s.sample_count), s.padding_size) == (rate, count, pad)
+    assert s.data.dtype == ref.dtype and np.array_equal(s.data, ref)
+
+
 def test_int24_decode_takes_top_16_bits():
     vals = np.array([0x123456, -0x123456, 0x7FFFFF, -0x800000, 255, -256], np.int32)
     raw = b''.join(int(v & 0xFFFFFF).to_bytes(3, 'little') for v in vals)

@@ -25,6 +25,24 @@ def test_loader_restatement_matches_reference(golden_loader, name, stype):
     assert np.array_equal(s.data, ref)
 
 
+LOADER24_CASES = ['stereo48k_24', 'mono44k1_24', 'six48k_24']
+
+
+@pytest.mark.parametrize('name', LOADER24_CASES)
+@pytest.mark.parametrize('stype', ['uint8', 'float32'])
+def test_loader_restatement_matches_reference_int24(golden_loader24, tmp_path, name, stype):
+    """The int24 branch (wav.py:71-74), pinned since round 2: the oracle's load_wav on the frozen 24-bit files
+    against WavStream.data of the reference itself, bit for bit."""
+    g = golden_loader24
+    p = str(tmp_path / 'x.wav')
+    open(p, 'wb').write(g[name + '_wav'].tobytes())
+    data, count, pad = ref_loader.load_wav(p, 12000, stype)
+    ref = g['{0}_{1}_data'.format(name, stype)]
+    rate, rcount, rpad = [int(v) for v in g['{0}_{1}_meta'.format(name, stype)]]
+    assert (int(count), pad) == (rcount, rpad) and rate == 12000
+    assert data.dtype == ref.dtype and data.shape == ref.shape and np.array_equal(data, ref)
+
+
 @pytest.mark.parametrize('stype', ['uint8', 'float32'])
 def test_matcher_restatement_matches_reference(golden_matcher, stype):
     g = golden_matcher

@@ -1,7 +1,7 @@
 """NumPy restatement of the two fp32 screening loops of the packed kernels (sb_fused2.cu, finish_item) against
 the exact fp64 value (sb_fused_common.cuh, sqdiff_exact).  Screening only has to rank the lags of a block to
 within half the screening margin; the lags inside the margin are then evaluated exactly.  This file pins the
-algebra of the trimmed loop (sb_set_epilogue(2)):
+algebra of the trimmed per-lag loop (body 3 runs it on the runs its bounds select; as the loop over all lags it was variant 2, dropped in round 2):
 
     v' = (A + rq - 2b*rs - 2*scale*cc) * rsqrt(wq + 0.25),   A = w0q + sum T^2 - 2(b*w0s + k)   (one fp64 rounding)
 

@@ -24,13 +24,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 # (name, first line, last line) in sb_fused2.cu; first match wins, innermost location first
 REGIONS = [
     ('epilogue: last radix-2 step', 'finish_item', 'correlation at the 8 lags', 'float f_w0q, f_k0;'),
-    ('epilogue: windows, scan, bases', 'finish_item', 'float f_w0q, f_k0;', 'if constexpr (v2) {'),
-    ('epilogue: per-lag screening + slide', 'finish_item', 'if constexpr (v2) {', 'const float my_min = tmin;'),
+    ('epilogue: windows, scan, bases', 'finish_item', 'float f_w0q, f_k0;', 'if constexpr (v3) {'),
+    ('epilogue: run bounds', 'finish_item', 'if constexpr (v3) {', 'int rq = 0, rs = 0;              // uint8: exact integer slide'),
+    ('epilogue: first-version per-lag loop', 'finish_item', 'int rq = 0, rs = 0;              // uint8: exact integer slide', 'const float my_min = tmin;'),
     ('epilogue: block minimum', 'finish_item', 'const float my_min = tmin;', 'unsigned long long cand = 0;'),
-    ('epilogue: candidates, exact, merge', 'finish_item', 'unsigned long long cand = 0;', '// ---------------------------------------------------------------- kernel A:'),
+    ('epilogue: records / in-kernel screening of selected runs', 'finish_item', 'unsigned long long cand = 0;', 'unsigned long long best = ~0ull;'),
+    ('epilogue: exact evaluation in the kernel, merge', 'finish_item', 'unsigned long long best = ~0ull;', '// ---------------------------------------------------------------- kernel A:'),
     ('epilogue: setup', 'finish_item', '__device__ __forceinline__ void finish_item', 'correlation at the 8 lags'),
-    ('fft passes (DIF)', 'fft_passes_dif', '__device__ __forceinline__ void fft_passes_dif', '// The inverse transform the kernels call'),
-    ('fft passes (Stockham)', 'fft_passes', '__device__ __forceinline__ float4 fft_passes', '// The same transform by decimation in frequency'),
+    ('fft passes', 'fft_passes_dif', '__device__ __forceinline__ void fft_passes_dif', '// EPI 2: the constants of a query every thread needs in finish_item'),
     ('stage inputs', 'stage_inputs', '__device__ __forceinline__ void stage_inputs', '// Y += conj(T) * X on both slots'),
 ]
 
@@ -55,7 +56,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--obj', default=os.path.join(ROOT, 'sushi_b200', 'csrc', 'sb_fused2.o'))
     ap.add_argument('--src', default=os.path.join(ROOT, 'sushi_b200', 'csrc', 'sb_fused2.cu'))
-    ap.add_argument('--kernel', default='k_match_packedIhLi1ELi0E', help='substring of the mangled kernel name')
+    ap.add_argument('--kernel', default='k_match_pairIhLi3E', help='substring of the mangled kernel name')
     ap.add_argument('--top', type=int, default=10, help='opcodes listed per region')
     args = ap.parse_args()
 

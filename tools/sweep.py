@@ -36,7 +36,7 @@ ap.add_argument('--premac-mode', type=int, default=-1)
 ap.add_argument('--events', default='0.5,1,3,10,30')
 ap.add_argument('--windows', default='5,10,30,60,120,300,600')
 ap.add_argument('--engine', type=int, default=-1, help='library engine (default: the library default)')
-ap.add_argument('--epilogue', type=int, default=0, help='body variant of the packed kernels: 1 | 2 (default: the library default)')
+ap.add_argument('--epilogue', type=int, default=0, help='body variant of the packed kernels: 1 | 3 (default: the library default)')
 ap.add_argument('--no-oracle-check', action='store_true')
 ap.add_argument('--out', default='sweep.json', help='file name under gpurun_out/')
 a = ap.parse_args()
