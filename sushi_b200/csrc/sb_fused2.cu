@@ -52,7 +52,6 @@ namespace {
 constexpr int QB = 16384;                 // lags per item = half the real FFT size
 constexpr int QT = 512;                   // threads per CTA
 constexpr int QNW = QT / 32;
-constexpr int QCH = QB / 2;               // chunks in the FFT buffer: u/v pairs of the two half-size transforms
 constexpr int Q4 = QB / 4;                // quads per spectrum row are i = 0 .. Q4
 // Row layout (float4 units): blocks of 256 quads, each block = 256 A chunks followed by 256 M chunks (8 KB, so
 // one TMA bulk copy fetches both halves of 256 quads and a warp's LDG.128 stays fully coalesced); the
@@ -158,10 +157,9 @@ struct Rows {
     }
     static __device__ __forceinline__ void load_special(const float4* row, float4& a, float4& m) { a = __ldg(row + qa(Q4)); m = __ldg(row + qm(Q4)); }
 };
-// Spectrum rows: plain read-only loads.  (Measured: ld.global.nc.L1::no_allocate, tried to keep the twiddle
-// tables in L1, drops the L2 hit rate of these rows from 98 % to 83 % and multiplies the DRAM traffic of the
+// Spectrum rows are read with plain read-only loads.  (Measured: ld.global.nc.L1::no_allocate, tried to keep the
+// twiddle tables in L1, drops the L2 hit rate of these rows from 98 % to 83 % and multiplies the DRAM traffic of the
 // kernel by 9 -- profiles/README.md.)
-__device__ __forceinline__ float4 ldg_stream(const float4* p) { return __ldg(p); }
 
 // ---------------------------------------------------------------- packing of one quad
 // a = (Y[i], Y[i+B/2]), m = (Y[B-i], Y[B/2-i]) as packed pairs, (c, s) = exp(i*pi*i/B).
@@ -227,6 +225,8 @@ struct Item {                                      // one (query, lag block)
 
 // uint8 streams: the two byte windows the sliding sums read go to shared memory by TMA bulk copies (one
 // thread), one exact (sum, sum of squares) pair per warp-round from the fp64 running sums by cp.async.
+// WARP_BASES (body 3): one pair per warp instead -- a warp owns 1024 consecutive lags there.
+template <bool WARP_BASES = false>
 __device__ __forceinline__ void stage_inputs(const Item& it, int tid, const uint8_t* img8, int64_t img_n,
                                              const double2* ipfx, const Smem& sm, unsigned long long* bar) {
     const int64_t hi0 = (it.j_blk + it.d.tlen) & ~(int64_t)15;
@@ -238,7 +238,12 @@ __device__ __forceinline__ void stage_inputs(const Item& it, int tid, const uint
         if (lo_bytes) tma_load_1d(sm.lo, img8 + it.j_blk, (unsigned)lo_bytes, bar);
         if (hi_bytes) tma_load_1d(sm.hi, img8 + hi0, (unsigned)hi_bytes, bar);
     }
-    if (tid < kRounds * QNW * 2) {
+    if (WARP_BASES) {
+        if (tid < QNW * 2) {
+            const int64_t jw = it.j_blk + (tid >> 1) * (QB / QNW);
+            if (jw < it.d.lag0 + it.d.nlags) cp_async16(sm.base + tid, ipfx + jw + ((tid & 1) ? it.d.tlen : 0));
+        }
+    } else if (tid < kRounds * QNW * 2) {
         const int c = tid / (QNW * 2), w = (tid >> 1) % QNW, which = tid & 1;
         const int64_t jw = it.j_blk + c * kLagsPerRound + w * 256;
         if (jw < it.d.lag0 + it.d.nlags) cp_async16(sm.base + tid, ipfx + jw + (which ? it.d.tlen : 0));
@@ -411,23 +416,19 @@ static_assert(sizeof(RunRecord) == 48, "three 16-byte stores");
 struct RunSink { RunRecord* recs; int* s_cnt; };                              // recs = this CTA's kRunSlots records (or null)
 __device__ __forceinline__ constexpr int kRunCountOff() { return 256; }       // bytes behind Smem::end (small area)
 
-// Window sums, fp32 screening of every lag, fp64 evaluation of the lags that can still be the minimum, merge
-// into the query's key.  after_read() runs (on all 512 threads) once every thread is done with the staged
-// windows.
-template <typename S, int ID, int EPI, typename AfterRead>
+// First version of the epilogue (body 1; every sample type): window sums, fp32 screening of every lag, fp64
+// evaluation of the lags that can still be the minimum, merge into the query's key.  A thread takes 8 consecutive
+// lags in each of four rounds.  after_read() runs (on all 512 threads) once every thread is done with the staged windows.
+template <typename S, int ID, typename AfterRead>
 __device__ __forceinline__ void finish_item(const Item& it, int tid, const Smem& sm, unsigned long long* s_bar, unsigned bar_parity,
-                                            unsigned long long* s_best, float* s_min, int2* s_w0,
+                                            unsigned long long* s_best, float* s_min,
                                             const S* __restrict__ img, int64_t img_n,
                                             const double2* __restrict__ ipfx, const double2* __restrict__ tpfx,
-                                            const PackedTables& tab, unsigned long long* __restrict__ keys,
-                                            float* __restrict__ curve_out, AfterRead after_read,
-                                            RunSink sink = RunSink{nullptr, nullptr}) {
+                                            unsigned long long* __restrict__ keys,
+                                            float* __restrict__ curve_out, AfterRead after_read) {
     constexpr int B = QB, NW = QNW, LB = QB, ROUNDS = kRounds, LAGS_PER_ROUND = kLagsPerRound;
     constexpr bool is_u8 = sizeof(S) == 1;
-    constexpr bool v2 = EPI >= 2 && is_u8;                 // second-generation body: everything from the staged windows, constants via shared memory
-    constexpr bool v3 = EPI == 3 && is_u8;                 // run-level bounds first, per-lag screening only where a run can hold the minimum
-    static_assert(EPI == 1 || EPI == 3, "body variants: 1 (first version, all sample types) and 3 (uint8 streams); 2 was measured and dropped in round 2");
-    constexpr float kSent = v2 ? 3.0e38f : 2.0f;           // screening value of a lag outside the query's range
+    constexpr float kSent = 2.0f;                          // screening value of a lag outside the query's range
     const float* img32 = reinterpret_cast<const float*>(img);
     const Buf& buf = sm.buf;
     const int lane = tid & 31, warp = tid >> 5;
@@ -435,73 +436,51 @@ __device__ __forceinline__ void finish_item(const Item& it, int tid, const Smem&
     const int64_t j_blk = it.j_blk;
     const int64_t n = d.tlen;
     const int64_t jlo = d.lag0, jhi = d.lag0 + d.nlags;
-    double tsum, tsq, a, b;
-    if constexpr (v2) {               // computed once per query by one thread (query_constants)
-        const double2* s_qc = reinterpret_cast<const double2*>(sm.end + kQueryConstOff());
-        const double2 c0 = s_qc[0], c1 = s_qc[1];
-        tsum = c0.x; tsq = c0.y; a = c1.x; b = c1.y;
-    } else {
-        const double2 t_hi = tpfx[d.toff + n], t_lo = tpfx[d.toff];
-        tsum = t_hi.x - t_lo.x; tsq = t_hi.y - t_lo.y;
-        a = (double)Acc<S>::centre(ipfx[img_n].x, (double)img_n);
-        b = (double)Acc<S>::centre(tsum, (double)n);
-    }
+    const double2 t_hi = tpfx[d.toff + n], t_lo = tpfx[d.toff];
+    const double tsum = t_hi.x - t_lo.x, tsq = t_hi.y - t_lo.y;
+    const double a = (double)Acc<S>::centre(ipfx[img_n].x, (double)img_n);
+    const double b = (double)Acc<S>::centre(tsum, (double)n);
     const double n_ab = (double)n * a * b;
     const double scale = 1.0 / (double)(2 * B);
     const double k_const = a * tsum - n_ab;
     const float f_tsq = (float)tsq, f_b = (float)b, f_scale = (float)scale;
     const bool interior = j_blk >= jlo && j_blk + LB <= jhi;
 
-    // chunks 2*tid, 2*tid+1 of every round: physical offsets and twiddles
     // chunk 1024c + 2tid + e = k1 + 16 k2 + 256 k3: k1 = 2(tid % 8) + e, k2 = (tid / 8) % 16, k3 = 4c + tid / 128; its
     // two halves r[k3][0], r[k3][1] are neighbours, and the twiddle W32^k3 = W32^(tid/128) * W8^c depends on the warp only
     const int ech = 2 * (tid & 7) * kDA + ((tid >> 3) & 15) * kDB + 2 * (tid >> 7);      // + kDA*e + 8*c; second half 1 further
-    const float4 wt = make_float4(kC32[tid >> 7], kS32[tid >> 7], kC32[tid >> 7], kS32[tid >> 7]);
+    const float wc0 = kC32[tid >> 7], ws0 = kS32[tid >> 7];
 
     float vf[ROUNDS][8];
     float tmin = kSent;
-    const float m2s = -2.0f * f_scale, m2b = -2.0f * f_b;             // v2 screening
-    // v3: over the 8 lags of a run the window terms of the screening value, rq_i - 2b*rs_i = sum over the samples that
-    // left / entered the window of (hi - b)^2 - (lo - b)^2, move by at most 7 * max(b, 255 - b)^2 (f_delta, with 2 % and
-    // 1024 on top: that swallows every fp32 rounding of the loop); the window energy itself by at most kRunQ
-    constexpr float kRunQ = 7.0f * 255.0f * 255.0f;
-    const float f_bm = fmaxf(f_b, 255.0f - f_b);
-    const float f_delta = 1.02f * 7.0f * f_bm * f_bm + 1024.0f;
-    float run_lb[ROUNDS];                                                  // v3: lower bound of each run's screening values
     if (is_u8) mbar_wait(s_bar, bar_parity);
 #pragma unroll
     for (int c = 0; c < ROUNDS; ++c) {
         const int m0 = c * LAGS_PER_ROUND + tid * 8;
         const int64_t j0 = j_blk + m0;
         const int64_t jw = j_blk + c * LAGS_PER_ROUND + warp * 256;
-        // A warp-round without a valid lag (first / last lag block of a range) is skipped -- except by the trimmed body,
-        // which lets its border path mark all eight lags invalid instead: with no branch in front of them the shuffles
-        // of the scan below compile to plain SHFL (behind a warp-uniform branch the compiler brackets each pair with
-        // WARPSYNC.COLLECTIVE / ENDCOLLECTIVE: 160 instructions per lag block).
-        if (!v2 && (jw >= jhi || jw + 256 <= jlo)) {
+        if (jw >= jhi || jw + 256 <= jlo) {                            // no valid lag in this warp-round (warp-uniform)
 #pragma unroll
             for (int i = 0; i < 8; ++i) vf[c][i] = kSent;
             continue;
         }
         // correlation at the 8 lags: last radix-2 step on chunks 1024c + 2tid + {0, 1}
         float cc[8];
+        float wc = wc0, ws = ws0;                                      // W32^(tid/128) times exp(2*pi*i*c/8)
+        {
+            const float h = 0.70710678118654752f;
+            if (c == 1) { wc = (wc0 - ws0) * h; ws = (wc0 + ws0) * h; }
+            if (c == 2) { wc = -ws0; ws = wc0; }
+            if (c == 3) { wc = -(wc0 + ws0) * h; ws = (wc0 - ws0) * h; }
+        }
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
             const C2 E = buf.ld(ech + kDA * e + 8 * c), O = buf.ld(ech + kDA * e + 8 * c + 1);
-            float wc = e ? wt.z : wt.x, ws = e ? wt.w : wt.y;          // W8192^(2tid+e) ...
-            {                                                          // ... times exp(2*pi*i*c/8)
-                const float h = 0.70710678118654752f;
-                const float c0 = wc, s0 = ws;
-                if (c == 1) { wc = (c0 - s0) * h; ws = (c0 + s0) * h; }
-                if (c == 2) { wc = -s0; ws = c0; }
-                if (c == 3) { wc = -(c0 + s0) * h; ws = (c0 - s0) * h; }
-            }
             const float2 xr = fma2(O.r, bc(wc), fma2(O.i, bc(-ws), E.r));
             const float2 xi = fma2(O.r, bc(ws), fma2(O.i, bc(wc), E.i));
             cc[4 * e + 0] = xr.x; cc[4 * e + 1] = xi.x; cc[4 * e + 2] = xr.y; cc[4 * e + 3] = xi.y;
         }
         float f_w0q, f_k0;
-        float f_A = 0.f;                                               // v2: everything constant over the run
         unsigned long long lo8 = 0, hi8 = 0;
         if (is_u8) {
             // everything comes from shared memory: lane l owns the run of 8 lags starting at jw + 8l.  Window
@@ -525,18 +504,8 @@ __device__ __forceinline__ void finish_item(const Item& it, int tid, const Smem&
             const double2 b_lo = sm.base[(c * NW + warp) * 2], b_hi = sm.base[(c * NW + warp) * 2 + 1];
             const double w0s = (b_hi.x - b_lo.x) + (double)(is - ts);
             const double w0q = (b_hi.y - b_lo.y) + (double)(iq - tq);
-            if (v2) {
-                // the 0.25 keeps a silent window (sum of squares 0) finite under rsqrt; it is below one ulp of any
-                // window sum that is not within 8 samples of silence
-                f_w0q = (float)(w0q + 0.25);
-                f_k0 = 0.f;
-                f_A = (float)(w0q + tsq - 2.0 * (b * w0s + k_const));
-                s_w0[c * QT + tid] = make_int2(is - ts, iq - tq);     // the run's offsets from the warp base, for the candidates
-
-            } else {
-                f_w0q = (float)w0q;
-                f_k0 = (float)(b * w0s + k_const);
-            }
+            f_w0q = (float)w0q;
+            f_k0 = (float)(b * w0s + k_const);
         } else {
             if (!(j0 < jhi && j0 + 8 > jlo)) {
 #pragma unroll
@@ -546,24 +515,6 @@ __device__ __forceinline__ void finish_item(const Item& it, int tid, const Smem&
             const double2 p_hi = ipfx[j0 + n], p_lo = ipfx[j0];
             f_w0q = (float)(p_hi.y - p_lo.y);
             f_k0 = (float)(b * (p_hi.x - p_lo.x) + k_const);
-        }
-        if constexpr (v3) {
-            // Run-level bounds.  The screening value of lag i of this run is
-            //   v'_i = (A + rq_i - 2b*rs_i - 2*scale*cc_i) * rsqrt(w0q + rq_i),   |rq_i - 2b*rs_i| <= delta, |rq_i| <= kRunQ,
-            // so with cmax = max cc_i:   v'_i >= (A - delta - 2*scale*cmax) * rsqrt(w0q + kRunQ)   for every i  (lb), and
-            // at the lag of cmax          v'   <= (A + delta - 2*scale*cmax) * rsqrt(w0q - kRunQ)                  (ub).
-            // The block minimum of ub is an upper bound of the block's smallest screening value: only runs whose lb
-            // does not exceed it (plus the margin) can hold a candidate, and only those go through the per-lag loop
-            // -- a few per lag block instead of all 2048, which was 40 % of the instructions of this function.
-            const float cmax = fmaxf(fmaxf(fmaxf(cc[0], cc[1]), fmaxf(cc[2], cc[3])), fmaxf(fmaxf(cc[4], cc[5]), fmaxf(cc[6], cc[7])));
-            const bool some = interior || (j0 < jhi && j0 + 8 > jlo);          // the run has a lag of the range
-            const bool inside = interior || (j0 >= jlo && j0 + 8 <= jhi);      // all of its lags are
-            const float lbn = fmaf(cmax, m2s, f_A - f_delta), ubn = lbn + 2.0f * f_delta;
-            const float lbv = lbn * rsqrt_fast(f_w0q + kRunQ) * 0.999999f;
-            run_lb[c] = !some ? kSent : (lbn >= 0.f ? lbv : -kSent);
-            const float ubv = ubn * rsqrt_fast(f_w0q - kRunQ) * 1.000001f;
-            if (inside && f_w0q > 4.0f * kRunQ && ubn >= 0.f) tmin = fminf(tmin, ubv);
-            continue;
         }
         int rq = 0, rs = 0;              // uint8: exact integer slide
         double dq = 0.0, ds = 0.0;       // float32: fp64 slide
@@ -593,91 +544,231 @@ __device__ __forceinline__ void finish_item(const Item& it, int tid, const Smem&
     if (lane == 0) s_min[warp] = tmin;
     if (is_u8) fence_proxy_async();   // window reads before the next item's TMA refill
     csync<ID>();
-    if (!v2) after_read();            // v2 evaluates its candidates from the staged windows first
-    float bmin;
-    if constexpr (v2) {               // one load and four shuffle steps instead of sixteen broadcast loads
-        static_assert(NW == 16, "block minimum over 16 warps");
-        bmin = s_min[lane & (NW - 1)];
+    after_read();
+    float bmin = s_min[0];
 #pragma unroll
-        for (int o = NW / 2; o > 0; o >>= 1) bmin = fminf(bmin, __shfl_xor_sync(0xffffffffu, bmin, o));
-    } else {
-        bmin = s_min[0];
-#pragma unroll
-        for (int w = 1; w < NW; ++w) bmin = fminf(bmin, s_min[w]);
-    }
-    float thr = curve_out ? 1.5f : bmin + kScreenMargin;             // debug curve: evaluate everything
-    bool all = false;                // v2: every lag of the range is a candidate
-    if (v2) {
-        // screening values are scaled by sqrt(sum T^2) and not clamped at 1: a block whose minimum is (nearly)
-        // saturated -- or a zero template -- evaluates all its lags, like the clamped values of v1 would
-        const float rt = sqrtf(f_tsq);
-        thr = bmin + kScreenMargin * rt;
-        all = curve_out != nullptr || !(bmin < (1.0f - kScreenMargin) * rt);
-    }
+    for (int w = 1; w < NW; ++w) bmin = fminf(bmin, s_min[w]);
+    const float thr = curve_out ? 1.5f : bmin + kScreenMargin;       // debug curve: evaluate everything
 
     unsigned long long cand = 0;
-    if constexpr (v3) {
-        // per-lag screening of the runs that can hold a candidate; everything is re-read from shared memory (the
-        // staged windows, the runs' head sums, the transform's output), the loop stays rolled: it runs for a few of
-        // the 64 warp-rounds of a lag block.  Within a warp-round the warp's own smallest value tightens the threshold.
-        const float rt = sqrtf(f_tsq);
-        // the selected runs leave as records (see RunRecord); what finds no slot stays selected for the loop below
-        if (sink.recs != nullptr && !all) {
+    if (my_min <= thr) {
 #pragma unroll
-            for (int c = 0; c < ROUNDS; ++c) {
-                if (run_lb[c] <= thr) {
-                    const int slot = atomicAdd(sink.s_cnt, 1);
-                    if (slot < kRunSlots) {
-                        const int m0 = c * LAGS_PER_ROUND + tid * 8;
-                        float cc[8];
+        for (int c = 0; c < ROUNDS; ++c)
 #pragma unroll
-                        for (int e = 0; e < 2; ++e) {       // chunks jj = m0/4 + e, exactly as the exact path below forms them
-                            const int jj = (m0 >> 2) + e;
-                            const int ca = (jj & 15) * kDA + ((jj >> 4) & 15) * kDB + 2 * (jj >> 8);
-                            const C2 E = buf.ld(ca), O = buf.ld(ca + 1);
-                            const float2 w = make_float2(kC32[jj >> 8], kS32[jj >> 8]);
-                            const float2 xr = fma2(O.r, bc(w.x), fma2(O.i, bc(-w.y), E.r));
-                            const float2 xi = fma2(O.r, bc(w.y), fma2(O.i, bc(w.x), E.i));
-                            cc[4 * e + 0] = xr.x; cc[4 * e + 1] = xi.x; cc[4 * e + 2] = xr.y; cc[4 * e + 3] = xi.y;
-                        }
-                        float4* r4 = reinterpret_cast<float4*>(sink.recs + slot);
-                        const int64_t j0 = j_blk + m0;
-                        *reinterpret_cast<int4*>(r4) = make_int4(it.q, 1, (int)(unsigned)(j0 & 0xffffffffll), (int)(j0 >> 32));
-                        r4[1] = make_float4(cc[0], cc[1], cc[2], cc[3]);
-                        r4[2] = make_float4(cc[4], cc[5], cc[6], cc[7]);
-                        run_lb[c] = kSent;                   // done
-                    }
-                }
-            }
+            for (int i = 0; i < 8; ++i) cand |= (vf[c][i] <= thr) ? (1ull << (c * 8 + i)) : 0ull;
+    }
+    unsigned long long best = ~0ull;
+    while (cand) {
+        const int bit = __ffsll((long long)cand) - 1;
+        cand &= cand - 1;
+        const int m = (bit >> 3) * LAGS_PER_ROUND + tid * 8 + (bit & 7);
+        const int64_t j = j_blk + m;
+        const int jj = m >> 2;                                          // chunk of X'
+        const int ca = (jj & 15) * kDA + ((jj >> 4) & 15) * kDB + 2 * (jj >> 8);
+        const C2 E = buf.ld(ca), O = buf.ld(ca + 1);
+        const float2 w = make_float2(kC32[jj >> 8], kS32[jj >> 8]);
+        const bool second = (m & 2) != 0;                               // lags 4j+2, 4j+3 belong to v
+        const float er = second ? E.r.y : E.r.x, ei = second ? E.i.y : E.i.x, orr = second ? O.r.y : O.r.x, oi = second ? O.i.y : O.i.x;
+        const float xr = fmaf(orr, w.x, fmaf(oi, -w.y, er)), xi = fmaf(orr, w.y, fmaf(oi, w.x, ei));
+        const double cc = (double)((m & 1) ? xi : xr) * scale;
+        const double2 p_hi = ipfx[j + n], p_lo = ipfx[j];
+        const float v = sqdiff_exact(cc, p_hi.x - p_lo.x, p_hi.y - p_lo.y, a, b, tsum, tsq, n_ab);
+        if (curve_out) curve_out[d.curveOff + (j - jlo)] = v;
+        const unsigned long long key = ((unsigned long long)__float_as_uint(v) << 32) | (unsigned int)(j - jlo);
+        best = key < best ? key : best;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+        best = other < best ? other : best;
+    }
+    if (lane == 0) s_best[warp] = best;
+    csync<ID>();
+    if (tid == 0) {
+        for (int w = 1; w < NW; ++w) best = s_best[w] < best ? s_best[w] : best;
+        if (best != ~0ull) atomicMin(keys + it.q, best);
+    }
+}
+
+// Body 3 (uint8 streams).  A thread owns the 32 consecutive lags 32*tid .. 32*tid+31 of the lag block as four runs of
+// 8, a warp 1024 consecutive lags: ONE intra-warp scan per lag block gives every run its exact head sums (the first
+// version scans once per round of 8 lags), and the chunks 8*tid .. 8*tid+7 of the transform's output sit in sixteen
+// distinct banks per half warp (k1 = 8(tid%2) + i, k2 = (tid/2)%16, k3 = warp).  Per run: cmax = the largest correlation
+// value, lower / upper bound of the run's screening values (see the comment at the bounds); block minimum of the
+// upper bounds; the runs whose lower bound does not exceed it leave as records for k_finish_runs.  What cannot leave
+// (no slot, degenerate block, debug curve) is screened per lag and evaluated exactly here, like the first version.
+template <int ID, typename AfterRead>
+__device__ __forceinline__ void finish_item_v3(const Item& it, int tid, const Smem& sm, unsigned long long* s_bar, unsigned bar_parity,
+                                               float* s_min, int2* s_w0, int64_t img_n,
+                                               unsigned long long* __restrict__ keys, float* __restrict__ curve_out,
+                                               AfterRead after_read, RunSink sink) {
+    constexpr int NW = QNW, LB = QB, RUNS = 4;
+    constexpr float kSent = 3.0e38f;                       // bound / screening value of "no valid lag"
+    const Buf& buf = sm.buf;
+    const int lane = tid & 31, warp = tid >> 5;
+    const QueryDesc& d = it.d;
+    const int64_t j_blk = it.j_blk, n = d.tlen, jlo = d.lag0, jhi = d.lag0 + d.nlags;
+    const double2* s_qc = reinterpret_cast<const double2*>(sm.end + kQueryConstOff());     // query_constants
+    const double tsum = s_qc[0].x, tsq = s_qc[0].y, a = s_qc[1].x, b = s_qc[1].y;
+    const double n_ab = (double)n * a * b;
+    const double scale = 1.0 / (double)(2 * QB);
+    const double k_const = a * tsum - n_ab;
+    const float f_tsq = (float)tsq, f_b = (float)b;
+    const float m2s = -2.0f * (float)scale, m2b = -2.0f * f_b;
+    const bool interior = j_blk >= jlo && j_blk + LB <= jhi;
+    const int64_t jt = j_blk + 32 * tid;                   // this thread's first lag
+    // over the 8 lags of a run the window terms of the screening value, rq_i - 2b*rs_i = sum over the samples that
+    // left / entered the window of (hi - b)^2 - (lo - b)^2, move by at most 7 * max(b, 255 - b)^2 (f_delta, with 2 % and
+    // 1024 on top: that swallows every fp32 rounding); the window energy itself by at most kRunQ
+    constexpr float kRunQ = 7.0f * 255.0f * 255.0f;
+    const float f_bm = fmaxf(f_b, 255.0f - f_b);
+    const float f_delta = 1.02f * 7.0f * f_bm * f_bm + 1024.0f;
+    const float rt = sqrtf(f_tsq), m_rt = kScreenMargin * rt, sat = (1.0f - kScreenMargin) * rt;
+    const int ech = 8 * (tid & 1) * kDA + ((tid >> 1) & 15) * kDB + 2 * warp;            // chunk 8*tid + i: + kDA*i; its second half 1 further
+    const float wc = kC32[warp], ws = kS32[warp];                                        // W32^k3, k3 = warp
+
+    mbar_wait(s_bar, bar_parity);
+    // ---- the 32 + 32 window bytes of this thread, the runs' integer totals, one scan
+    unsigned lw[8], hw[8];
+    {
+        const uint4 l0 = *reinterpret_cast<const uint4*>(sm.lo + 32 * tid), l1 = *reinterpret_cast<const uint4*>(sm.lo + 32 * tid + 16);
+        lw[0] = l0.x; lw[1] = l0.y; lw[2] = l0.z; lw[3] = l0.w; lw[4] = l1.x; lw[5] = l1.y; lw[6] = l1.z; lw[7] = l1.w;
+        const int hi_off = (int)((j_blk + n) & 15);       // the staged copy starts at the 16-byte boundary below j_blk + n
+        const uint4 h0 = *reinterpret_cast<const uint4*>(sm.hi + 32 * tid), h1 = *reinterpret_cast<const uint4*>(sm.hi + 32 * tid + 16),
+                    h2 = *reinterpret_cast<const uint4*>(sm.hi + 32 * tid + 32);
+        unsigned w[12] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w, h2.x, h2.y, h2.z, h2.w};
+        unsigned v[10], u[9];
+#pragma unroll
+        for (int k = 0; k < 10; ++k) v[k] = (hi_off & 8) ? w[k + 2] : w[k];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) u[k] = (hi_off & 4) ? v[k + 1] : v[k];
+        const unsigned sh = (unsigned)(hi_off & 3) * 8u;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) hw[k] = __funnelshift_r(u[k], u[k + 1], sh);
+    }
+    int tq[RUNS], ts[RUNS];
+#pragma unroll
+    for (int r = 0; r < RUNS; ++r) {
+        tq[r] = (int)__dp4a(hw[2 * r], hw[2 * r], __dp4a(hw[2 * r + 1], hw[2 * r + 1], 0u)) - (int)__dp4a(lw[2 * r], lw[2 * r], __dp4a(lw[2 * r + 1], lw[2 * r + 1], 0u));
+        ts[r] = (int)__dp4a(hw[2 * r], 0x01010101u, __dp4a(hw[2 * r + 1], 0x01010101u, 0u)) - (int)__dp4a(lw[2 * r], 0x01010101u, __dp4a(lw[2 * r + 1], 0x01010101u, 0u));
+    }
+    const int Tq = (tq[0] + tq[1]) + (tq[2] + tq[3]), Ts = (ts[0] + ts[1]) + (ts[2] + ts[3]);
+    int iq = Tq, is = Ts;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int uq = __shfl_up_sync(0xffffffffu, iq, o), us = __shfl_up_sync(0xffffffffu, is, o);
+        if (lane >= o) { iq += uq; is += us; }
+    }
+    // exact sums of the window at the warp's first lag (staged from the running sums), everything else as integer offsets
+    const double2 b_lo = sm.base[warp * 2], b_hi = sm.base[warp * 2 + 1];
+    const double Wq = b_hi.y - b_lo.y, Ws = b_hi.x - b_lo.x;
+    const double Cw = Wq + tsq - 2.0 * (b * Ws + k_const);             // A at the warp's first lag
+    const int bi2 = 2 * (int)b;                                          // b is an integer (Acc<uint8_t>::centre)
+    float run_lb[RUNS];
+    float tmin = kSent;
+    int oq = iq - Tq, os = is - Ts;                                      // offsets of the run's head from the warp's first lag
+#pragma unroll
+    for (int r = 0; r < RUNS; ++r) {
+        s_w0[r * QT + tid] = make_int2(os, oq);                          // for the in-kernel paths below
+        // the 0.25 keeps a silent window (sum of squares 0) finite under rsqrt; it is below one ulp of any
+        // window sum that is not within 8 samples of silence
+        const float f_w0q = (float)(Wq + 0.25 + (double)oq);
+        const float f_A = (float)(Cw + (double)(oq - bi2 * os));
+        // correlation at the run's 8 lags: last radix-2 step on chunks 8*tid + 2r, + 1
+        float cc[8];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const C2 E = buf.ld(ech + kDA * (2 * r + e)), O = buf.ld(ech + kDA * (2 * r + e) + 1);
+            const float2 xr = fma2(O.r, bc(wc), fma2(O.i, bc(-ws), E.r));
+            const float2 xi = fma2(O.r, bc(ws), fma2(O.i, bc(wc), E.i));
+            cc[4 * e + 0] = xr.x; cc[4 * e + 1] = xi.x; cc[4 * e + 2] = xr.y; cc[4 * e + 3] = xi.y;
         }
+        // Run-level bounds.  The screening value of lag i of this run is
+        //   v'_i = (A + rq_i - 2b*rs_i - 2*scale*cc_i) * rsqrt(w0q + rq_i),   |rq_i - 2b*rs_i| <= delta, |rq_i| <= kRunQ,
+        // so with cmax = max cc_i:   v'_i >= (A - delta - 2*scale*cmax) * rsqrt(w0q + kRunQ)   for every i  (lower bound), and
+        // at the lag of cmax          v'   <= (A + delta - 2*scale*cmax) * rsqrt(w0q - kRunQ)                  (upper bound).
+        // The block minimum of the upper bounds is an upper bound of the block's smallest screening value: only runs
+        // whose lower bound does not exceed it (plus the margin) can hold a candidate.
+        const float cmax = fmaxf(fmaxf(fmaxf(cc[0], cc[1]), fmaxf(cc[2], cc[3])), fmaxf(fmaxf(cc[4], cc[5]), fmaxf(cc[6], cc[7])));
+        const int64_t j0 = jt + 8 * r;
+        const bool some = interior || (j0 < jhi && j0 + 8 > jlo);          // the run has a lag of the range
+        const bool inside = interior || (j0 >= jlo && j0 + 8 <= jhi);      // all of its lags are
+        const float lbn = fmaf(cmax, m2s, f_A - f_delta), ubn = lbn + 2.0f * f_delta;
+        const float lbv = lbn * rsqrt_fast(f_w0q + kRunQ) * 0.999999f;
+        run_lb[r] = !some ? kSent : (lbn >= 0.f ? lbv : -kSent);
+        const float ubv = ubn * rsqrt_fast(f_w0q - kRunQ) * 1.000001f;
+        if (inside && f_w0q > 4.0f * kRunQ && ubn >= 0.f) tmin = fminf(tmin, ubv);
+        oq += tq[r]; os += ts[r];
+    }
+    // ---- block minimum of the upper bounds
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tmin = fminf(tmin, __shfl_xor_sync(0xffffffffu, tmin, o));
+    if (lane == 0) s_min[warp] = tmin;
+    fence_proxy_async();              // window reads before the next item's TMA refill
+    csync<ID>();
+    static_assert(NW == 16, "block minimum over 16 warps");
+    float bmin = s_min[lane & (NW - 1)];
+#pragma unroll
+    for (int o = NW / 2; o > 0; o >>= 1) bmin = fminf(bmin, __shfl_xor_sync(0xffffffffu, bmin, o));
+    // a block whose minimum is (nearly) saturated -- silence, a zero template, no usable upper bound at all -- and the
+    // debug curve evaluate every lag of the range in the kernel
+    const float thr = bmin + m_rt;
+    const bool all = curve_out != nullptr || !(bmin < sat);
+    unsigned left = 0;                // runs of this thread that still need the in-kernel path
+#pragma unroll
+    for (int r = 0; r < RUNS; ++r) left |= (run_lb[r] <= thr || (all && run_lb[r] < kSent)) ? (1u << r) : 0u;
+    // the selected runs leave as records (see RunRecord); what finds no slot stays selected
+    if (left && sink.recs != nullptr && !all) {
 #pragma unroll 1
-        for (int c = 0; c < ROUNDS; ++c) {
-            const float l = c == 0 ? run_lb[0] : c == 1 ? run_lb[1] : c == 2 ? run_lb[2] : run_lb[3];
-            const bool sel = l <= thr || (all && l < kSent);
-            if (!__any_sync(0xffffffffu, sel)) continue;
-            const int m0 = c * LAGS_PER_ROUND + tid * 8;
-            const int64_t j0 = j_blk + m0;
+        for (int r = 0; r < RUNS; ++r) {
+            if (!((left >> r) & 1u)) continue;
+            const int slot = atomicAdd(sink.s_cnt, 1);
+            if (slot >= kRunSlots) break;
             float cc[8];
-            const float rc = kC32[4 * c], rs8 = kS32[4 * c];                     // W8^c
-            const float wc = wt.x * rc - wt.y * rs8, ws = wt.x * rs8 + wt.y * rc;
+            const int k3 = warp;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {       // exactly as the exact path below forms them
+                const C2 E = buf.ld(ech + kDA * (2 * r + e)), O = buf.ld(ech + kDA * (2 * r + e) + 1);
+                const float2 w = make_float2(kC32[k3], kS32[k3]);
+                const float2 xr = fma2(O.r, bc(w.x), fma2(O.i, bc(-w.y), E.r));
+                const float2 xi = fma2(O.r, bc(w.y), fma2(O.i, bc(w.x), E.i));
+                cc[4 * e + 0] = xr.x; cc[4 * e + 1] = xi.x; cc[4 * e + 2] = xr.y; cc[4 * e + 3] = xi.y;
+            }
+            float4* r4 = reinterpret_cast<float4*>(sink.recs + slot);
+            const int64_t j0 = jt + 8 * r;
+            *reinterpret_cast<int4*>(r4) = make_int4(it.q, 1, (int)(unsigned)(j0 & 0xffffffffll), (int)(j0 >> 32));
+            r4[1] = make_float4(cc[0], cc[1], cc[2], cc[3]);
+            r4[2] = make_float4(cc[4], cc[5], cc[6], cc[7]);
+            left &= ~(1u << r);
+        }
+    }
+    unsigned long long best = ~0ull;
+    if (__any_sync(0xffffffffu, left != 0u)) {
+        // per-lag screening of the runs that stayed (rare), everything re-read from shared memory; within a warp the
+        // warp's own smallest value tightens the threshold; then the exact fp64 evaluation of the candidates
+        unsigned cand = 0;            // bit 8r + i
+#pragma unroll 1
+        for (int r = 0; r < RUNS; ++r) {
+            const bool sel = (left >> r) & 1u;
+            if (!__any_sync(0xffffffffu, sel)) continue;
+            const int64_t j0 = jt + 8 * r;
+            float cc[8];
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                const C2 E = buf.ld(ech + kDA * e + 8 * c), O = buf.ld(ech + kDA * e + 8 * c + 1);
+                const C2 E = buf.ld(ech + kDA * (2 * r + e)), O = buf.ld(ech + kDA * (2 * r + e) + 1);
                 const float2 xr = fma2(O.r, bc(wc), fma2(O.i, bc(-ws), E.r));
                 const float2 xi = fma2(O.r, bc(ws), fma2(O.i, bc(wc), E.i));
                 cc[4 * e + 0] = xr.x; cc[4 * e + 1] = xi.x; cc[4 * e + 2] = xr.y; cc[4 * e + 3] = xi.y;
             }
-            const unsigned long long lo8 = *reinterpret_cast<const unsigned long long*>(sm.lo + m0);
-            const int hb = (int)((j_blk + n) & 15) + m0;
+            const unsigned long long lo8 = *reinterpret_cast<const unsigned long long*>(sm.lo + 32 * tid + 8 * r);
+            const int hb = (int)((j_blk + n) & 15) + 32 * tid + 8 * r;
             const unsigned long long h0 = *reinterpret_cast<const unsigned long long*>(sm.hi + (hb & ~7));
             const unsigned long long h1 = *reinterpret_cast<const unsigned long long*>(sm.hi + (hb & ~7) + 8);
-            const unsigned sh = (unsigned)(hb & 7) * 8u;
-            const unsigned long long hi8 = sh ? ((h0 >> sh) | (h1 << (64u - sh))) : h0;
-            const double2 b_lo = sm.base[(c * NW + warp) * 2], b_hi = sm.base[(c * NW + warp) * 2 + 1];
-            const int2 off = s_w0[c * QT + tid];
-            const double w0s = (b_hi.x - b_lo.x) + (double)off.x, w0q = (b_hi.y - b_lo.y) + (double)off.y;
-            const float f_w0q = (float)(w0q + 0.25);
-            const float f_A = (float)(w0q + tsq - 2.0 * (b * w0s + k_const));
+            const unsigned shb = (unsigned)(hb & 7) * 8u;
+            const unsigned long long hi8 = shb ? ((h0 >> shb) | (h1 << (64u - shb))) : h0;
+            const int2 off = s_w0[r * QT + tid];
+            const float f_w0q = (float)(Wq + 0.25 + (double)off.y);
+            const float f_A = (float)(Cw + (double)(off.y - bi2 * off.x));
             float v8[8];
             float vmin = kSent;
             int rq = 0, rs = 0;
@@ -695,79 +786,47 @@ __device__ __forceinline__ void finish_item(const Item& it, int tid, const Smem&
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
-            const float thrw = fminf(thr, vmin + kScreenMargin * rt);
+            const float thrw = fminf(thr, vmin + m_rt);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) cand |= (v8[i] < kSent && (v8[i] <= thrw || all)) ? (1ull << (c * 8 + i)) : 0ull;   // (a block without a usable upper bound has thr = kSent)
+            for (int i = 0; i < 8; ++i) cand |= (v8[i] < kSent && (v8[i] <= thrw || all)) ? (1u << (r * 8 + i)) : 0u;   // (a block without a usable upper bound has thr = kSent)
         }
-    } else if (my_min <= thr || all) {
-#pragma unroll
-        for (int c = 0; c < ROUNDS; ++c)
-#pragma unroll
-            for (int i = 0; i < 8; ++i) cand |= (vf[c][i] <= thr || (all && vf[c][i] < kSent)) ? (1ull << (c * 8 + i)) : 0ull;
-    }
-    unsigned long long best = ~0ull;
-    while (cand) {
-        const int bit = __ffsll((long long)cand) - 1;
-        cand &= cand - 1;
-        const int m = (bit >> 3) * LAGS_PER_ROUND + tid * 8 + (bit & 7);
-        const int64_t j = j_blk + m;
-        const int jj = m >> 2;                                          // chunk of X'
-        const int ca = (jj & 15) * kDA + ((jj >> 4) & 15) * kDB + 2 * (jj >> 8);
-        const C2 E = buf.ld(ca), O = buf.ld(ca + 1);
-        const float2 w = make_float2(kC32[jj >> 8], kS32[jj >> 8]);
-        const bool second = (m & 2) != 0;                               // lags 4j+2, 4j+3 belong to v
-        const float er = second ? E.r.y : E.r.x, ei = second ? E.i.y : E.i.x, orr = second ? O.r.y : O.r.x, oi = second ? O.i.y : O.i.x;
-        const float xr = fmaf(orr, w.x, fmaf(oi, -w.y, er)), xi = fmaf(orr, w.y, fmaf(oi, w.x, ei));
-        const double cc = (double)((m & 1) ? xi : xr) * scale;
-        double wsum, wsq;
-        if constexpr (v2) {
-            // exact window sums without touching HBM: the run's head sums (kept in shared memory by the screening
-            // loop) plus the integer slide over the first `bit & 7` samples of the staged windows
-            const int c = bit >> 3, i = bit & 7, m0 = c * LAGS_PER_ROUND + tid * 8;
-            const unsigned long long lo8 = *reinterpret_cast<const unsigned long long*>(sm.lo + m0);
-            const int hb = (int)((j_blk + n) & 15) + m0;
+        while (cand) {
+            const int bit = __ffs((int)cand) - 1;
+            cand &= cand - 1;
+            const int r = bit >> 3, i = bit & 7;
+            const int m = 32 * tid + bit;
+            const int64_t j = j_blk + m;
+            const int jj = m >> 2;                                          // chunk of X'
+            const int ca = (jj & 15) * kDA + ((jj >> 4) & 15) * kDB + 2 * (jj >> 8);
+            const C2 E = buf.ld(ca), O = buf.ld(ca + 1);
+            const float2 w = make_float2(kC32[jj >> 8], kS32[jj >> 8]);
+            const bool second = (m & 2) != 0;                               // lags 4j+2, 4j+3 belong to v
+            const float er = second ? E.r.y : E.r.x, ei = second ? E.i.y : E.i.x, orr = second ? O.r.y : O.r.x, oi = second ? O.i.y : O.i.x;
+            const float xr = fmaf(orr, w.x, fmaf(oi, -w.y, er)), xi = fmaf(orr, w.y, fmaf(oi, w.x, ei));
+            const double cc = (double)((m & 1) ? xi : xr) * scale;
+            // exact window sums without touching HBM: the run's head sums plus the integer slide over the first i samples
+            const unsigned long long lo8 = *reinterpret_cast<const unsigned long long*>(sm.lo + 32 * tid + 8 * r);
+            const int hb = (int)((j_blk + n) & 15) + 32 * tid + 8 * r;
             const unsigned long long h0 = *reinterpret_cast<const unsigned long long*>(sm.hi + (hb & ~7));
             const unsigned long long h1 = *reinterpret_cast<const unsigned long long*>(sm.hi + (hb & ~7) + 8);
-            const unsigned sh = (unsigned)(hb & 7) * 8u;
-            const unsigned long long hi8 = sh ? ((h0 >> sh) | (h1 << (64u - sh))) : h0;
+            const unsigned shb = (unsigned)(hb & 7) * 8u;
+            const unsigned long long hi8 = shb ? ((h0 >> shb) | (h1 << (64u - shb))) : h0;
             const unsigned long long keep = i ? (~0ull >> (8 * (8 - i))) : 0ull;      // samples 0 .. i-1
             const unsigned la = (unsigned)(lo8 & keep), lb = (unsigned)((lo8 & keep) >> 32), ha = (unsigned)(hi8 & keep), hb2 = (unsigned)((hi8 & keep) >> 32);
             const int rq = (int)__dp4a(ha, ha, __dp4a(hb2, hb2, 0u)) - (int)__dp4a(la, la, __dp4a(lb, lb, 0u));
             const int rs = (int)__dp4a(ha, 0x01010101u, __dp4a(hb2, 0x01010101u, 0u)) - (int)__dp4a(la, 0x01010101u, __dp4a(lb, 0x01010101u, 0u));
-            // the run's head sums exactly as the screening loop formed them: warp base + intra-warp offsets
-            const double2 b_lo = sm.base[(c * NW + warp) * 2], b_hi = sm.base[(c * NW + warp) * 2 + 1];
-            const int2 off = s_w0[c * QT + tid];
-            const double w0s = (b_hi.x - b_lo.x) + (double)off.x, w0q = (b_hi.y - b_lo.y) + (double)off.y;
-            wsum = w0s + (double)rs; wsq = w0q + (double)rq;
-        } else {
-            const double2 p_hi = ipfx[j + n], p_lo = ipfx[j];
-            wsum = p_hi.x - p_lo.x; wsq = p_hi.y - p_lo.y;
+            const int2 off = s_w0[r * QT + tid];
+            const double wsum = (Ws + (double)off.x) + (double)rs, wsq = (Wq + (double)off.y) + (double)rq;
+            const float v = sqdiff_exact(cc, wsum, wsq, a, b, tsum, tsq, n_ab);
+            if (curve_out) curve_out[d.curveOff + (j - jlo)] = v;
+            const unsigned long long key = ((unsigned long long)__float_as_uint(v) << 32) | (unsigned int)(j - jlo);
+            best = key < best ? key : best;
         }
-        const float v = sqdiff_exact(cc, wsum, wsq, a, b, tsum, tsq, n_ab);
-        if (curve_out) curve_out[d.curveOff + (j - jlo)] = v;
-        const unsigned long long key = ((unsigned long long)__float_as_uint(v) << 32) | (unsigned int)(j - jlo);
-        best = key < best ? key : best;
-    }
-    if constexpr (v2) {
-        // candidates are rare (usually one thread of the CTA has any): each merges its own best straight into the
-        // query's key instead of a shuffle tree, a round through shared memory and a serial merge by thread 0
         if (best != ~0ull) atomicMin(keys + it.q, best);
-        fence_proxy_async();          // the candidates' window reads, again before the refill
-        csync<ID>();                  // everyone is done with the FFT buffer and the staged windows
-        after_read();
-    } else {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
-            best = other < best ? other : best;
-        }
-        if (lane == 0) s_best[warp] = best;
-        csync<ID>();
-        if (tid == 0) {
-            for (int w = 1; w < NW; ++w) best = s_best[w] < best ? s_best[w] : best;
-            if (best != ~0ull) atomicMin(keys + it.q, best);
-        }
     }
+    fence_proxy_async();              // the in-kernel paths' window reads, again before the refill
+    csync<ID>();                      // everyone is done with the FFT buffer and the staged windows
+    after_read();
 }
 
 // ---------------------------------------------------------------- kernel A: one CTA per item
@@ -800,7 +859,7 @@ k_match_packed(const float4* __restrict__ That, int64_t part_first,
     // ---------------- 0. stage what the epilogue needs; the latency hides behind the MAC and the FFT
     if (is_u8) {
         if (tid == 0) mbar_init(s_bar, 1);
-        stage_inputs(it, tid, reinterpret_cast<const uint8_t*>(img), img_n, ipfx, sm, s_bar);
+        stage_inputs<EPI == 3>(it, tid, reinterpret_cast<const uint8_t*>(img), img_n, ipfx, sm, s_bar);
     }
     if (EPI == 3 && tid == 96) *s_cnt = 0;
     if (EPI >= 2 && tid == 64) query_constants<S>(reinterpret_cast<double2*>(sm.end + kQueryConstOff()), d, img_n, ipfx, tpfx);
@@ -866,7 +925,8 @@ k_match_packed(const float4* __restrict__ That, int64_t part_first,
 
     // ---------------- 3. inverse FFT, 4. epilogue ---------------------------------------------
     fft_passes_dif<0>(buf, tid, tab, is_u8);
-    finish_item<S, 0, EPI>(it, tid, sm, s_bar, 0u, s_best, s_min, s_w0, img, img_n, ipfx, tpfx, tab, keys, curve_out, [] {}, sink);
+    if constexpr (EPI == 3) finish_item_v3<0>(it, tid, sm, s_bar, 0u, s_min, s_w0, img_n, keys, curve_out, [] {}, sink);
+    else finish_item<S, 0>(it, tid, sm, s_bar, 0u, s_best, s_min, img, img_n, ipfx, tpfx, keys, curve_out, [] {});
     if (EPI == 3 && rec_count && tid == 0) rec_count[blockIdx.x] = *s_cnt < kRunSlots ? *s_cnt : kRunSlots;    // behind the closing barrier of finish_item
 }
 
@@ -943,7 +1003,7 @@ k_match_pair(const float4* __restrict__ That, int64_t part_first,
     if (warp == 0) tmem_alloc(s_taddr, 256);
     if (is_u8) {
         if (tid == 0) mbar_init(s_bar, 1);
-        stage_inputs(it0, tid, reinterpret_cast<const uint8_t*>(img), img_n, ipfx, sm, s_bar);
+        stage_inputs<EPI == 3>(it0, tid, reinterpret_cast<const uint8_t*>(img), img_n, ipfx, sm, s_bar);
     }
     if (EPI == 3 && tid == 96) *s_cnt = 0;
     if (EPI >= 2 && tid == 64) query_constants<S>(reinterpret_cast<double2*>(sm.end + kQueryConstOff()), d, img_n, ipfx, tpfx);
@@ -1031,8 +1091,9 @@ k_match_pair(const float4* __restrict__ That, int64_t part_first,
 
     // ---------------- first item: inverse FFT + epilogue ---------------------------------------
     fft_passes_dif<0>(buf, tid, tab, is_u8);
-    finish_item<S, 0, EPI>(it0, tid, sm, s_bar, 0u, s_best, s_min, s_w0, img, img_n, ipfx, tpfx, tab, keys, curve_out,
-                      [&] { if (is_u8 && has2) stage_inputs(it1, tid, reinterpret_cast<const uint8_t*>(img), img_n, ipfx, sm, s_bar); }, sink);
+    auto stage_second = [&] { if (is_u8 && has2) stage_inputs<EPI == 3>(it1, tid, reinterpret_cast<const uint8_t*>(img), img_n, ipfx, sm, s_bar); };
+    if constexpr (EPI == 3) finish_item_v3<0>(it0, tid, sm, s_bar, 0u, s_min, s_w0, img_n, keys, curve_out, stage_second, sink);
+    else finish_item<S, 0>(it0, tid, sm, s_bar, 0u, s_best, s_min, img, img_n, ipfx, tpfx, keys, curve_out, stage_second);
 
     // ---------------- second item: out of tensor memory, then the same ---------------------------
     if (has2) {                                       // uniform over the CTA
@@ -1040,7 +1101,8 @@ k_match_pair(const float4* __restrict__ That, int64_t part_first,
         if (tid == (NW - 1) * 32) buf.st(phys(Q4), sp1);
         csync<0>();
         fft_passes_dif<0>(buf, tid, tab, is_u8);
-        finish_item<S, 0, EPI>(it1, tid, sm, s_bar, 1u, s_best, s_min, s_w0, img, img_n, ipfx, tpfx, tab, keys, curve_out, [] {}, sink);
+        if constexpr (EPI == 3) finish_item_v3<0>(it1, tid, sm, s_bar, 1u, s_min, s_w0, img_n, keys, curve_out, [] {}, sink);
+        else finish_item<S, 0>(it1, tid, sm, s_bar, 1u, s_best, s_min, img, img_n, ipfx, tpfx, keys, curve_out, [] {});
     }
     tmem_fence_before();
     csync<0>();

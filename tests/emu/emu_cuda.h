@@ -136,6 +136,10 @@ inline unsigned __byte_perm(unsigned x, unsigned y, unsigned s) {
     return out;
 }
 inline int __ffsll(long long v) { return __builtin_ffsll(v); }
+inline int __ffs(int v) { return __builtin_ffs(v); }
+inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned shift) {
+    return (unsigned)(((((unsigned long long)hi) << 32) | lo) >> (shift & 31u));
+}
 inline int __float2int_rn(float f) { return (int)std::nearbyintf(f); }
 inline unsigned __float_as_uint(float f) { unsigned u; std::memcpy(&u, &f, 4); return u; }
 inline float __uint_as_float(unsigned u) { float f; std::memcpy(&f, &u, 4); return f; }

@@ -23,14 +23,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 # (name, first line, last line) in sb_fused2.cu; first match wins, innermost location first
 REGIONS = [
-    ('epilogue: last radix-2 step', 'finish_item', 'correlation at the 8 lags', 'float f_w0q, f_k0;'),
-    ('epilogue: windows, scan, bases', 'finish_item', 'float f_w0q, f_k0;', 'if constexpr (v3) {'),
-    ('epilogue: run bounds', 'finish_item', 'if constexpr (v3) {', 'int rq = 0, rs = 0;              // uint8: exact integer slide'),
-    ('epilogue: first-version per-lag loop', 'finish_item', 'int rq = 0, rs = 0;              // uint8: exact integer slide', 'const float my_min = tmin;'),
-    ('epilogue: block minimum', 'finish_item', 'const float my_min = tmin;', 'unsigned long long cand = 0;'),
-    ('epilogue: records / in-kernel screening of selected runs', 'finish_item', 'unsigned long long cand = 0;', 'unsigned long long best = ~0ull;'),
-    ('epilogue: exact evaluation in the kernel, merge', 'finish_item', 'unsigned long long best = ~0ull;', '// ---------------------------------------------------------------- kernel A:'),
-    ('epilogue: setup', 'finish_item', '__device__ __forceinline__ void finish_item', 'correlation at the 8 lags'),
+    ('epilogue 3: windows, totals, scan, bases', 'finish_item_v3', 'mbar_wait(s_bar, bar_parity);\n    // ---- the 32 + 32 window bytes', 'float run_lb[RUNS];'),
+    ('epilogue 3: per run radix-2 step + bounds', 'finish_item_v3', 'float run_lb[RUNS];', '// ---- block minimum of the upper bounds'),
+    ('epilogue 3: block minimum, selection', 'finish_item_v3', '// ---- block minimum of the upper bounds', '// the selected runs leave as records'),
+    ('epilogue 3: records', 'finish_item_v3', '// the selected runs leave as records', 'unsigned long long best = ~0ull;\n    if (__any_sync'),
+    ('epilogue 3: in-kernel path for what could not leave', 'finish_item_v3', 'unsigned long long best = ~0ull;\n    if (__any_sync', '// ---------------------------------------------------------------- kernel A:'),
+    ('epilogue 3: setup', 'finish_item_v3', '__device__ __forceinline__ void finish_item_v3', 'mbar_wait(s_bar, bar_parity);\n    // ---- the 32 + 32 window bytes'),
+    ('epilogue 1 (first version)', 'finish_item', '__device__ __forceinline__ void finish_item(', '// Body 3 (uint8 streams).  A thread owns'),
     ('fft passes', 'fft_passes_dif', '__device__ __forceinline__ void fft_passes_dif', '// EPI 2: the constants of a query every thread needs in finish_item'),
     ('stage inputs', 'stage_inputs', '__device__ __forceinline__ void stage_inputs', '// Y += conj(T) * X on both slots'),
 ]
@@ -39,11 +38,14 @@ REGIONS = [
 def resolve_regions(src_path):
     lines = open(src_path).read().split('\n')
 
+    text = '\n'.join(lines)
+
     def find(needle, start=0):
-        for i in range(start, len(lines)):
-            if needle in lines[i]:
-                return i + 1
-        raise SystemExit('marker not found in %s: %r' % (src_path, needle))
+        """1-based line of the first occurrence of `needle` (may span lines) at or after line index `start`."""
+        pos = text.find(needle, sum(len(l) + 1 for l in lines[:start]))
+        if pos < 0:
+            raise SystemExit('marker not found in %s: %r' % (src_path, needle))
+        return text.count('\n', 0, pos) + 1
     out = []
     for name, _, a, b in REGIONS:
         la = find(a)
