@@ -35,7 +35,7 @@ def _streams(dur, seed, stype='uint8'):
 
 
 @pytest.mark.parametrize('engine', [4, 5])          # pairs of lag blocks / single lag blocks
-def test_trimmed_epilogue_is_bit_identical_on_batches(gpu_lib, epilogue, engine):
+def test_body_variants_are_bit_identical_on_batches(gpu_lib, epilogue, engine):
     rs, rd, src, dst = _streams(240.0, 11)
     starts, ends = synth.make_events(300, 240.0, 12, 0.5, 6.0)
     win = np.full(len(starts), 30.0)
@@ -49,11 +49,11 @@ def test_trimmed_epilogue_is_bit_identical_on_batches(gpu_lib, epilogue, engine)
         assert np.array_equal(out[1][1], out[variant][1])
     # and they are right: the known shift comes back
     ok = (ends + 1.5 < 240.0)
-    assert np.abs((out[2][1] - starts)[ok] - 1.5).max() <= 1.0 / 12000 + 1e-9
+    assert np.abs((out[3][1] - starts)[ok] - 1.5).max() <= 1.0 / 12000 + 1e-9
 
 
 @pytest.mark.parametrize('engine', [4, 5])
-def test_trimmed_epilogue_curves_and_ragged_ranges(gpu_lib, epilogue, engine):
+def test_body_variants_curves_and_ragged_ranges(gpu_lib, epilogue, engine):
     """Whole curves (every lag evaluated exactly) and ranges that start / end inside a lag block."""
     rs, rd, src, dst = _streams(60.0, 5)
     cases = [(src._get_sample_for_time(6.1), 11400, 70000, 150001), (100, 48000, 0, 200000),
@@ -69,7 +69,7 @@ def test_trimmed_epilogue_curves_and_ragged_ranges(gpu_lib, epilogue, engine):
         assert got[2][1][1][0] == int(got[2][0].argmin()) and got[2][1][0][0] == got[2][0].min()
 
 
-def test_trimmed_epilogue_degenerate_inputs(gpu_lib, epilogue, golden_matcher):
+def test_third_body_degenerate_inputs(gpu_lib, epilogue, golden_matcher):
     """Silent windows, zero template, constants, ties: the blocks whose minimum is saturated must fall back to
     evaluating every lag, exactly like the clamped screening values of the first version."""
     g = golden_matcher
