@@ -22,7 +22,7 @@ for stype in ('uint8', 'float32'):
     src = WavStream.from_pcm(src_pcm, 12000, sample_type=stype)
     dst = WavStream.from_pcm(dst_pcm, 12000, sample_type=stype)
     # (engine, body variant of the packed kernels)
-    variants = [(4, 2), (5, 2), (4, 1), (5, 1), (1, 1), (0, 1)]
+    variants = [(4, 3), (5, 3), (4, 1), (5, 1), (1, 1), (0, 1)]
     for engine, epilogue in variants:
         _native.check(lib.sb_set_engine(engine))
         _native.check(lib.sb_set_epilogue(epilogue))
@@ -39,6 +39,6 @@ for stype in ('uint8', 'float32'):
                 stype, '%gs' % ev_len, '+-%gs' % win, nlags, np.abs(gpu - ref).max(), np.abs(gpu - f64).max(),
                 np.abs(ref - f64).max(), 'same' if int(gpu.argmin()) == int(ref.argmin()) else 'DIFF(%d)' % (int(gpu.argmin()) - int(ref.argmin())),
                 {0: 'cufft', 1: 'fused', 2: 'packed', 4: 'packed_pair', 5: 'packed_single'}[engine]
-                + ('/body1' if epilogue == 1 and engine >= 2 else '')))
+                + ('/body%d' % epilogue if engine >= 2 else '')))
     _native.check(lib.sb_set_engine(2))
     _native.check(lib.sb_set_epilogue(3))

@@ -66,7 +66,7 @@ def test_body_variants_curves_and_ragged_ranges(gpu_lib, epilogue, engine):
         for variant in (3,):
             assert np.array_equal(got[1][0], got[variant][0])
             assert got[1][1][0][0] == got[variant][1][0][0] and got[1][1][1][0] == got[variant][1][1][0]
-        assert got[2][1][1][0] == int(got[2][0].argmin()) and got[2][1][0][0] == got[2][0].min()
+        assert got[3][1][1][0] == int(got[3][0].argmin()) and got[3][1][0][0] == got[3][0].min()
 
 
 def test_third_body_degenerate_inputs(gpu_lib, epilogue, golden_matcher):
