@@ -49,7 +49,8 @@ keep = ['gpu__time_duration.sum', 'launch__grid_size', 'launch__registers_per_th
         'sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active',
         'sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active', 'smsp__inst_executed.sum',
         'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active']
-tr[key] = {'dram_bytes_per_launch': dram, 'report': os.path.basename(rep), 'src_hash': src_hash or bench.kernel_source_hash(),
+grid = float(d['launch__grid_size'][0])
+tr[key] = {'dram_bytes_per_launch': dram, 'grid_size': grid, 'dram_bytes_per_cta': dram / grid, 'report': os.path.basename(rep), 'src_hash': src_hash or bench.kernel_source_hash(),
            'metrics': {k: ' '.join(d[k]) for k in keep if k in d}}
 json.dump(tr, open(out_path, 'w'), indent=1, sort_keys=True)
 print(key, 'dram bytes/launch', dram)
