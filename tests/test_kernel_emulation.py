@@ -35,6 +35,10 @@ def emu():
     src = [os.path.join(EMU, f) for f in ('emu_driver.cpp', 'emu_cuda.h', 'emu_ptx.h')] + \
           [os.path.join(ROOT, 'sushi_b200', 'csrc', f) for f in ('sb_fused2.cu', 'sb_fused_common.cuh', 'sb_fft_smem.cuh', 'sb_internal.h')]
     out = os.path.join(EMU, '_build', 'libsb_emu.so')
+    if os.environ.get('SB_EMU_LIB'):                      # a prebuilt library (scratch builds of a kernel under development)
+        lib = ctypes.CDLL(os.environ['SB_EMU_LIB'])
+        assert lib.emu_query_desc_bytes() == ctypes.sizeof(QueryDesc)
+        return lib
     if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(f) for f in src):
         os.makedirs(os.path.dirname(out), exist_ok=True)
         cuda_inc = os.path.join(os.environ.get('CUDA_HOME', '/usr/local/cuda'), 'include')
