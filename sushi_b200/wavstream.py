@@ -561,14 +561,21 @@ class WavStream(StreamGeometry):
         engines at hop B, the default, compute a value the same way whatever the batch; the
         first-generation engine with hop_mode 0 picks its geometry per batch and agrees only to ~1e-7)."""
         cache = self.__dict__.setdefault('_curve_cache', {})
+        # keys are the CLAMPED template ranges, the same integers find_substream derives from a view.  This runs once
+        # per search group: the common case (the group's curve is there) must cost a few scalar operations, not arrays
+        # over the next 48 groups
+        if cache:
+            total, pad, rate = src_stream.total_samples, src_stream.padding_size, src_stream.sample_rate
+            lo = int(rate * float(groups[idx][0].start)) + pad          # trunc toward zero, like _template_ranges
+            hi = int(rate * float(groups[idx][-1].end)) + pad
+            lo = max(lo + total, 0) if lo < 0 else min(lo, total)
+            hi = max(hi + total, 0) if hi < 0 else min(hi, total)
+            if (lo, lo + max(hi - lo, 0)) in cache:
+                return
         batch = groups[idx:idx + self.SPECULATE_GROUPS]
         starts = np.array([g[0].start for g in batch], np.float64)
         ends = np.array([g[-1].end for g in batch], np.float64)
         windows = np.full(len(batch), window + self.SPECULATE_MARGIN)
-        # keys are the CLAMPED template ranges, the same integers find_substream derives from a view
-        k_off, k_len = self._template_ranges(src_stream, starts, ends)
-        if (int(k_off[0]), int(k_off[0] + k_len[0])) in cache:
-            return
         cache.clear()                                        # predictions made for an older anchor
         try:
             toff, tlen, lag0, nlags, _ = self.plan_queries(src_stream, starts, ends, starts + anchor, windows)
