@@ -245,14 +245,38 @@ class ClockSampler(object):
 # --------------------------------------------------------------------------------------
 # evidence from ncu captures (profiles/traffic.json), valid only for the source it was taken from
 # --------------------------------------------------------------------------------------
+def _strip_comments(text):
+    """C / C++ source without comments and without layout (string and character literals are kept intact)."""
+    out, i, n = [], 0, len(text)
+    while i < n:
+        c = text[i]
+        if c == '"' or c == "'":
+            j = i + 1
+            while j < n and text[j] != c:
+                j += 2 if text[j] == '\\' else 1
+            out.append(text[i:j + 1])
+            i = j + 1
+        elif text.startswith('//', i):
+            j = text.find('\n', i)
+            i = n if j < 0 else j
+        elif text.startswith('/*', i):
+            j = text.find('*/', i + 2)
+            i = n if j < 0 else j + 2
+        else:
+            out.append(c)
+            i += 1
+    return ' '.join(''.join(out).split())
+
+
 def kernel_source_hash():
-    """Hash of the CUDA sources: a capture is evidence for the kernels it was taken from, nothing else."""
+    """Hash of the CUDA sources, comments and layout ignored: a capture is evidence for the code it was taken from,
+    nothing else -- and rewording a comment does not change the code."""
     h = hashlib.sha1()
     csrc = os.path.join(ROOT, 'sushi_b200', 'csrc')
     for name in sorted(os.listdir(csrc)):
         if name.endswith(('.cu', '.cuh', '.h')):
             h.update(name.encode())
-            h.update(open(os.path.join(csrc, name), 'rb').read())
+            h.update(_strip_comments(open(os.path.join(csrc, name), encoding='utf-8').read()).encode())
     return h.hexdigest()[:16]
 
 

@@ -1,6 +1,6 @@
 // Packed fused lag-block kernels (engines 2-5): the same per-lag-block pipeline as sb_fused.cu
 //   spectral multiply-accumulate -> Hermitian packing -> inverse FFT in shared memory -> window sums,
-//   fp32 screening, fp64 evaluation of the lags that can win -> one 64-bit atomicMin
+//   selection of the lags that can win -> fp64 evaluation of those -> one 64-bit atomicMin
 // rebuilt around Blackwell's two-wide fp32 instructions (FFMA2 / FADD2 / FMUL2).  sb_fused.cu is bound by
 // instruction issue in its FFT and epilogue phases; here every value the kernels touch is one half of a
 // float2 whose two halves go through identical arithmetic, so one issued instruction does the work of two:
@@ -12,9 +12,9 @@
 //  * The first radix-2 step of the inverse FFT (decimation in frequency) is done on the packed pair itself:
 //    u[i] = Z[i] + Z[i+B/2], v[i] = (Z[i] - Z[i+B/2]) * W^i.  u and v are two INDEPENDENT half-size
 //    transforms with identical twiddles, X[2o] = FFT(u)[o], X[2o+1] = FFT(v)[o]; they travel together as
-//    pairs (u.re, v.re), (u.im, v.im) through three radix-16 Stockham passes (shared twiddles as
-//    scalar-broadcast operands), and the last radix-2 step (of which only the "+" half carries valid lags)
-//    is folded into the epilogue.
+//    pairs (u.re, v.re), (u.im, v.im) through three radix-16 passes by decimation in frequency -- the first
+//    across the CTA, the other two inside one warp each (fft_passes_dif) -- and the last radix-2 step (of
+//    which only the "+" half carries valid lags) is folded into the epilogue.
 //  * Twiddles of the packing stage are formed in registers from one per-thread base value, so the 64 KB
 //    table sb_fused.cu streams from L2 for every item is gone; spectrum rows are 128-byte aligned.
 //
@@ -25,12 +25,15 @@
 //                   while the first is transformed -- the default for templates of two or more partitions.
 // Values agree with sb_fused.cu / the cuFFT engine to fp32 FFT rounding (~2e-7 of the curve); k_match_packed and
 // k_match_pair agree bit for bit.
-// Template parameters: S = sample type of the stream (uint8_t | float); EPI = body variant on uint8 streams
-// (2 = default: trimmed screening loop, candidates evaluated from the staged windows, mid-butterfly barriers,
-// prefetched self-mirrored quad; 1 = the first version, kept as the bit-identical cross-check: sb_set_epilogue).
-// Measured and dropped in round 2 (profiles/README.md): triples of lag blocks (slower than pairs: one quad in
-// flight per thread), 16-bit block-floating-point spectrum rows (the dequantisation costs more issue slots than
-// the halved L2 traffic returns), a persistent warp-specialised variant (multiply warps latency-bound).
+// Template parameters: S = sample type of the stream (uint8_t | float); EPI = body of the epilogue on uint8 streams
+// (sb_set_epilogue): 3 = default since round 2 -- run-level bounds pick the runs of 8 lags that can hold a lag block's
+// minimum, those leave as records and k_finish_runs evaluates them in fp64 (prep_runs_v3 / finish_item_v3); 1 = the
+// first version, everything inside the match kernel (finish_item), also the only body for float32 streams and the
+// bit-identical cross-check.
+// Measured and dropped (profiles/README.md): triples of lag blocks (slower than pairs: one quad in flight per
+// thread), 16-bit block-floating-point spectrum rows (the dequantisation costs more issue slots than the halved L2
+// traffic returns), a persistent warp-specialised variant (multiply warps latency-bound), the Stockham form of the
+// FFT passes (six CTA barriers per transform), body 2 (fp32 screening of every lag in an unrolled loop).
 #include "sb_internal.h"
 #include <cmath>
 #include <cstdlib>
@@ -288,7 +291,7 @@ __device__ __forceinline__ C2 special_quad(const float4* tp, const float4* xp, i
     return lo;                                    // C[B/4] (its mirror is itself)
 }
 
-// EPI 2: the same quad without an L2 round trip at the end of the multiply phase, where the
+// Body 3: the same quad without an L2 round trip at the end of the multiply phase, where the
 // other fifteen warps already wait at the barrier.  The last warp requests the 16-byte units it needs -- two per
 // row: the P template rows, then the spectrum rows k .. k+P+G-2 of the CTA's G lag blocks -- with cp.async before
 // its multiply loop; afterwards the partitions are spread over the lanes and summed by the same shuffle tree as
@@ -389,7 +392,7 @@ __device__ __forceinline__ void fft_passes_dif(const Buf& buf, int tid, const Pa
     }
 }
 
-// EPI 2: the constants of a query every thread needs in finish_item -- sums of the template (two reads of its
+// Body 3: the constants of a query every thread needs in the epilogue -- sums of the template (two reads of its
 // running sums) and the two centres (two fp64 divisions) -- by ONE thread at the start of the CTA's work on the
 // query, through shared memory; the first version has all 512 threads fetch and divide them after the last FFT
 // pass of every item, with the whole CTA waiting on those reads.  [0] = (sum T, sum T^2), [1] = (a, b).
@@ -848,7 +851,7 @@ k_match_packed(const float4* __restrict__ That, int64_t part_first,
     float* s_min = reinterpret_cast<float*>(s_best + NW);                  // [NW]
     int* s_cnt = reinterpret_cast<int*>(sm.end + kRunCountOff());          // EPI 3: records written by this CTA
     const RunSink sink = {EPI == 3 && recs ? recs + (size_t)blockIdx.x * kRunSlots : nullptr, s_cnt};
-    float4* s_sp = reinterpret_cast<float4*>(sm.end + kSmallBytes);        // EPI 2: units of the self-mirrored quads
+    float4* s_sp = reinterpret_cast<float4*>(sm.end + kSmallBytes);        // body 3: units of the self-mirrored quads
     int2* s_w0 = EPI >= 2 && is_u8 ? reinterpret_cast<int2*>(sm.end + kSmallBytes + kSpecialBytes) : nullptr;   // [kRounds][QT]
     const Buf& buf = sm.buf;
 
@@ -932,7 +935,7 @@ k_match_packed(const float4* __restrict__ That, int64_t part_first,
 
 // A parked product spectrum back into the FFT buffer: this thread's 64 tensor-memory columns hold, quad by quad,
 // the chunks C[i] and C[B/2 - i] it packed (i = tid + 512*uu).  BATCH = false (measured default): 16 columns at a
-// time, each load waited for before its stores; BATCH = true (opt-in with EPI 2): all four loads in flight, one wait.
+// time, each load waited for before its stores; BATCH = true (body 3): all four loads in flight, one wait.
 template <bool BATCH>
 __device__ __forceinline__ void unpark(uint32_t tsrc, const Buf& buf, int col, int mcol, int tid) {
     auto put = [&](const float (&v)[16], int c4) {
@@ -989,7 +992,7 @@ k_match_pair(const float4* __restrict__ That, int64_t part_first,
     uint32_t* s_taddr = reinterpret_cast<uint32_t*>(s_min + NW);
     int* s_cnt = reinterpret_cast<int*>(sm.end + kRunCountOff());          // EPI 3: records written by this CTA (both items)
     const RunSink sink = {EPI == 3 && recs ? recs + (size_t)blockIdx.x * kRunSlots : nullptr, s_cnt};
-    float4* s_sp = reinterpret_cast<float4*>(sm.end + kSmallBytes);        // EPI 2: units of the self-mirrored quads
+    float4* s_sp = reinterpret_cast<float4*>(sm.end + kSmallBytes);        // body 3: units of the self-mirrored quads
     int2* s_w0 = EPI >= 2 && is_u8 ? reinterpret_cast<int2*>(sm.end + kSmallBytes + kSpecialBytes) : nullptr;   // [kRounds][QT]
     const Buf& buf = sm.buf;
 
@@ -1237,7 +1240,7 @@ size_t forward_smem_bytes14() {
     return ((size_t)(C::N + (C::N >> 5) + 1) + C::R2 * 32 + 2 * C::R3 * 32) * sizeof(float2) + 64;
 }
 
-size_t packed_smem_bytes(int epi = 1) {      // epilogue 2 keeps the runs' exact head sums next to the small arrays
+size_t packed_smem_bytes(int epi = 1) {      // body 3 keeps the runs' exact head sums next to the small arrays
     return epi >= 2 ? kSmemCommon + kSmallBytes + kSpecialBytes + (size_t)kRounds * QT * sizeof(int2)
                     : kSmemCommon + 8 + QNW * sizeof(unsigned long long) + QNW * sizeof(float) + 64;
 }

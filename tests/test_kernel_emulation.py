@@ -305,7 +305,7 @@ def test_emulated_edge_geometry(emu):
 
 def test_emulated_variants_reproduce_the_reference_golden(emu, golden_matcher):
     """The reference's own outputs (tests/golden/matcher.npz: find_substream of /root/reference/wav.py over cv2 on
-    12 queries) through the emulated default kernel (pairs of lag blocks, trimmed body) within north_star's
+    12 queries) through the emulated default kernel (pairs of lag blocks, body 3 with and without records) within north_star's
     tolerances: shift +-1 sample, diff 1e-5."""
     from tests.helpers import oracle_stream_from_pcm
     g = golden_matcher
@@ -333,7 +333,7 @@ def test_emulated_variants_reproduce_the_reference_golden(emu, golden_matcher):
 
 def test_emulated_config1_against_the_live_oracle(emu):
     """BASELINE config 1 (100 events, 2 x 60 s streams with a constant +1.5 s shift, +-10 s window) through the
-    emulated kernels -- pairs of lag blocks with the first body and with the trimmed (default) one -- against the
+    emulated kernels -- pairs of lag blocks with the first body and with the third (default) one -- against the
     oracle's find_substream (cv2) on every event."""
     from sushi_b200 import synth
     from tests.helpers import oracle_stream_from_pcm
@@ -367,7 +367,7 @@ def test_emulated_config1_against_the_live_oracle(emu):
 @pytest.mark.parametrize('seed', [101, 102, 103, 104])
 def test_emulated_random_queries_all_variants_agree(emu, seed):
     """Random template lengths (all residues of the window alignment), random ranges: one CTA per lag block with the
-    first body against both kernels with the trimmed body, bit for bit, and against the closed form."""
+    first body against both kernels with the third body, bit for bit, and against the closed form."""
     rng = np.random.default_rng(seed)
     n_img = int(rng.integers(2 * B + 100, 5 * B))
     img = programme(n_img, seed)

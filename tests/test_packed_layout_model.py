@@ -1,16 +1,19 @@
 """Executable specification of the index algebra of the packed kernels (sushi_b200/csrc/sb_fused2.cu), in NumPy:
-quad-layout chunks -> Hermitian packing + first radix-2 step (pack_quad) -> three radix-16 Stockham passes over
-the (u, v) pairs in the padded buffer (fft_passes) -> last radix-2 step in the epilogue (finish_item).  The
-addresses (phys(), the 544 / 17 / 272 / 4352 / 1088 strides, the mirrored-chunk rule) are the kernel's; the
-result must be the unnormalised inverse real FFT of the product spectrum.  CPU only: it guards the algebra,
-not the CUDA code (the GPU parity tests do that)."""
+quad-layout chunks -> Hermitian packing + first radix-2 step (pack_quad) -> three radix-16 passes by decimation in
+frequency over the (u, v) pairs in the [16][16][32] buffer with strides (529, 33, 1) (fft_passes_dif: pass 1 across the
+CTA, passes 2 and 3 inside one warp each, every thread writing over its own inputs) -> last radix-2 step with the
+twiddle W32^k3 in the epilogue, under both thread-to-lag mappings (finish_item: 8 lags in each of four rounds;
+finish_item_v3: 32 consecutive lags).  The addresses are the kernel's; the result must be the unnormalised inverse
+real FFT of the product spectrum, and every access pattern must hit sixteen distinct 8-byte banks per half warp.
+CPU only: it guards the algebra, not the CUDA code (the emulation and the GPU parity tests do that)."""
 import numpy as np
 
 B, T = 16384, 512
+DA, DB = 529, 33
 
 
-def phys(c):
-    return c + (c >> 4)
+def phys(n):
+    return (n >> 9) * DA + ((n >> 5) & 15) * DB + (n & 31)
 
 
 def pack_quad(a, m, c, s):
@@ -58,18 +61,18 @@ def test_packed_pipeline_is_the_inverse_real_fft():
     M = np.stack([Y[B - i], Y[B // 2 - i]], 1)
     (lo_u, lo_v), (hi_u, hi_v) = pack_quad(A, M, np.cos(np.pi * i / B), np.sin(np.pi * i / B))
 
-    n_phys = 8192 + 512
+    n_phys = 16 * DA
     bufs = [np.zeros(n_phys, complex), np.zeros(n_phys, complex)]      # u and v halves of every chunk
     for tid in range(T):
         tm = (T - tid) & (T - 1)
         for uu in range(8):
             q = tid + 512 * uu
             for b_, (lo, hi) in zip(bufs, ((lo_u, hi_u), (lo_v, hi_v))):
-                b_[phys(tid) + 544 * uu] = lo[q]
+                b_[phys(tid) + DA * uu] = lo[q]
                 if tid != 0:
-                    b_[phys(tm) + 544 * (15 - uu)] = hi[q]
+                    b_[phys(tm) + DA * (15 - uu)] = hi[q]
                 elif uu != 0:
-                    b_[phys(tm) + 544 * (16 - uu)] = hi[q]
+                    b_[phys(tm) + DA * (16 - uu)] = hi[q]
     bufs[0][phys(4096)], bufs[1][phys(4096)] = lo_u[4096], lo_v[4096]
 
     # the chunks are the two half-size sequences u, v of the decimation-in-frequency split
@@ -78,40 +81,85 @@ def test_packed_pipeline_is_the_inverse_real_fft():
     u = Z[:B // 2] + Z[B // 2:]
     v = (Z[:B // 2] - Z[B // 2:]) * np.exp(2j * np.pi * np.arange(B // 2) / B)
     c = np.arange(8192)
-    assert np.abs(bufs[0][phys(c)] - u).max() < 1e-9 * np.abs(u).max()
-    assert np.abs(bufs[1][phys(c)] - v).max() < 1e-9 * np.abs(v).max()
+    pc = np.array([phys(int(n)) for n in c])
+    assert np.abs(bufs[0][pc] - u).max() < 1e-9 * np.abs(u).max()
+    assert np.abs(bufs[1][pc] - v).max() < 1e-9 * np.abs(v).max()
 
     tid = np.arange(T)
+    lane, warp = tid & 31, tid >> 5
     for buf in bufs:
-        src = phys(tid)
-        vv = dft16_dif(np.stack([buf[src + 544 * r] for r in range(16)]))          # pass 1
-        for r in range(16):
-            buf[17 * tid + r] = vv[brev16(r)]
-        kk = tid & 15                                                              # pass 2
-        vv = np.stack([buf[src + 544 * r] for r in range(16)])
-        for r in range(1, 16):
-            vv[r] = vv[r] * np.exp(2j * np.pi * r * kk / 256)
-        vv = dft16_dif(vv)
-        for r in range(16):
-            buf[272 * (tid >> 4) + kk + 17 * r] = vv[brev16(r)]
-        kk = tid & 255                                                             # pass 3
-        vv = np.stack([buf[src + 544 * r] for r in range(16)])
-        for r in range(1, 16):
-            vv[r] = vv[r] * np.exp(2j * np.pi * r * kk / 4096)
-        vv = dft16_dif(vv)
-        for r in range(16):
-            buf[4352 * (tid >> 8) + phys(kk) + 272 * r] = vv[brev16(r)]
+        at = warp * DB + lane                                                      # pass 1: over a, position t = tid
+        vv = dft16_dif(np.stack([buf[at + DA * a] for a in range(16)]))
+        for k1 in range(16):
+            buf[at + DA * k1] = vv[brev16(k1)] * np.exp(2j * np.pi * tid * k1 / 8192)
+        at = warp * DA + lane                                                      # pass 2: warp k1, over b, position l = lane
+        vv = dft16_dif(np.stack([buf[at + DB * b_] for b_ in range(16)]))
+        for k2 in range(16):
+            buf[at + DB * k2] = vv[brev16(k2)] * np.exp(2j * np.pi * lane * k2 / 512)
+        at = warp * DA + (lane & 15) * DB + (lane >> 4)                            # pass 3: lane (k2, m), over c
+        vv = dft16_dif(np.stack([buf[at + 2 * c_] for c_ in range(16)]))
+        for k3 in range(16):
+            buf[at + 2 * k3] = vv[brev16(k3)]
 
+    # epilogue, first version: chunk 1024c + 2tid + e, twiddle W32^(tid/128) * W8^c
     out = np.zeros(B)
-    for c_ in range(4):                                                            # epilogue rounds
+    for c_ in range(4):
         for e in range(2):
-            p = 2 * tid + (tid >> 3) + 1088 * c_ + e
-            w = np.exp(2j * np.pi * (2 * tid + e) / 8192) * np.exp(2j * np.pi * c_ / 8)
-            xu = bufs[0][p] + w * bufs[0][p + 4352]
-            xv = bufs[1][p] + w * bufs[1][p + 4352]
+            p = 2 * (tid & 7) * DA + ((tid >> 3) & 15) * DB + 2 * (tid >> 7) + DA * e + 8 * c_
+            w = np.exp(2j * np.pi * (tid >> 7) / 32) * np.exp(2j * np.pi * c_ / 8)
+            xu = bufs[0][p] + w * bufs[0][p + 1]
+            xv = bufs[1][p] + w * bufs[1][p + 1]
             m0 = c_ * 4096 + tid * 8 + 4 * e
             out[m0], out[m0 + 1], out[m0 + 2], out[m0 + 3] = xu.real, xu.imag, xv.real, xv.imag
     assert np.abs(out - want[:B]).max() < 1e-9 * np.abs(want).max()
+
+    # epilogue, body 3: chunks 8*tid + i (32 consecutive lags per thread), twiddle W32^warp
+    out3 = np.zeros(B)
+    for i_ in range(8):
+        p = 8 * (tid & 1) * DA + ((tid >> 1) & 15) * DB + 2 * warp + DA * i_
+        w = np.exp(2j * np.pi * warp / 32)
+        xu = bufs[0][p] + w * bufs[0][p + 1]
+        xv = bufs[1][p] + w * bufs[1][p + 1]
+        m0 = 32 * tid + 4 * i_
+        out3[m0], out3[m0 + 1], out3[m0 + 2], out3[m0 + 3] = xu.real, xu.imag, xv.real, xv.imag
+    assert np.abs(out3 - want[:B]).max() < 1e-9 * np.abs(want).max()
+
+    # the exact path's general address of chunk jj: [jj % 16][(jj / 16) % 16][2 (jj / 256)], twiddle W32^(jj / 256)
+    jj = np.arange(4096)
+    p = (jj & 15) * DA + ((jj >> 4) & 15) * DB + 2 * (jj >> 8)
+    xu = bufs[0][p] + np.exp(2j * np.pi * (jj >> 8) / 32) * bufs[0][p + 1]
+    assert np.abs(xu.real - want[0:B:4]).max() < 1e-9 * np.abs(want).max()
+
+
+def test_buffer_strides_are_bank_conflict_free():
+    """Every warp-wide 64-bit access of the passes and of both epilogues: the sixteen lanes of a half warp hit sixteen
+    distinct 8-byte banks (addresses are in 8-byte units of the two float2 arrays)."""
+    def ok(addr):                            # addr: 32 element indices of one warp-wide access
+        return all(len(set(int(a) % 16 for a in addr[h:h + 16])) == 16 for h in (0, 16))
+    lane = np.arange(32)
+    for warp in range(16):
+        tid = warp * 32 + lane
+        for r in range(16):
+            assert ok(warp * DB + lane + DA * r)                                        # pass 1 loads / stores; packing stores
+            assert ok(warp * DA + lane + DB * r)                                        # pass 2
+            assert ok(warp * DA + (lane & 15) * DB + (lane >> 4) + 2 * r)               # pass 3
+        for c_ in range(4):
+            for e in range(2):
+                p = 2 * (tid & 7) * DA + ((tid >> 3) & 15) * DB + 2 * (tid >> 7) + DA * e + 8 * c_
+                assert ok(p) and ok(p + 1)                                              # epilogue, first version
+        for i_ in range(8):
+            p = 8 * (tid & 1) * DA + ((tid >> 1) & 15) * DB + 2 * warp + DA * i_
+            assert ok(p) and ok(p + 1)                                                  # epilogue, body 3
+    # mirrored chunks of the packing stage: thread tid writes C[B/2 - i] into column (512 - tid) % 512 -- descending
+    # addresses whose first lane sits in the next row of the buffer: one pair of lanes per warp shares a bank (2-way
+    # on one of the 32 stores' half warps), nothing worse
+    for warp in range(16):
+        tid = warp * 32 + lane
+        tm = (T - tid) & (T - 1)
+        col = np.array([phys(int(t)) for t in tm])
+        for h in (0, 16):
+            banks = [int(a) % 16 for a in col[h:h + 16]]
+            assert max(banks.count(b_) for b_ in set(banks)) <= 2
 
 
 def test_quad_row_layout_is_a_bijection():

@@ -30,7 +30,7 @@ REGIONS = [
     ('epilogue 3: in-kernel path for what could not leave', 'finish_item_v3', 'unsigned long long best = ~0ull;\n    if (__any_sync', '// ---------------------------------------------------------------- kernel A:'),
     ('epilogue 3: setup', 'finish_item_v3', '__device__ __forceinline__ void finish_item_v3', 'mbar_wait(s_bar, bar_parity);\n    // ---- the 32 + 32 window bytes'),
     ('epilogue 1 (first version)', 'finish_item', '__device__ __forceinline__ void finish_item(', '// Body 3 (uint8 streams).  A thread owns'),
-    ('fft passes', 'fft_passes_dif', '__device__ __forceinline__ void fft_passes_dif', '// EPI 2: the constants of a query every thread needs in finish_item'),
+    ('fft passes', 'fft_passes_dif', '__device__ __forceinline__ void fft_passes_dif', '// Body 3: the constants of a query every thread needs in the epilogue'),
     ('stage inputs', 'stage_inputs', '__device__ __forceinline__ void stage_inputs', '// Y += conj(T) * X on both slots'),
 ]
 
