@@ -418,6 +418,7 @@ struct RunRecord { int32_t q; int32_t valid; int64_t j0; float cc[8]; };     // 
 static_assert(sizeof(RunRecord) == 48, "three 16-byte stores");
 struct RunSink { RunRecord* recs; int* s_cnt; };                              // recs = this CTA's kRunSlots records (or null)
 __device__ __forceinline__ constexpr int kRunCountOff() { return 256; }       // bytes behind Smem::end (small area)
+__device__ __forceinline__ constexpr int kNextOff() { return 272; }           // 16 + 80 bytes: query and descriptor of the CTA's next pair (k_match_pair)
 
 // First version of the epilogue (body 1; every sample type): window sums, fp32 screening of every lag, fp64
 // evaluation of the lags that can still be the minimum, merge into the query's key.  A thread takes 8 consecutive
@@ -979,7 +980,7 @@ k_match_pair(const float4* __restrict__ That, int64_t part_first,
              const float4* __restrict__ Xhat, int64_t nblk,
              const S* __restrict__ img, int64_t img_n,
              const double2* __restrict__ ipfx, const double2* __restrict__ tpfx,
-             const QueryDesc* __restrict__ desc, const int* __restrict__ pair_query, int64_t pair_first,
+             const QueryDesc* __restrict__ desc, const int* __restrict__ pair_query, int64_t pair_first, int64_t n_pairs,
              PackedTables tab, unsigned long long* __restrict__ keys, float* __restrict__ curve_out,
              RunRecord* __restrict__ recs, int* __restrict__ rec_count) {
     constexpr int T = QT, NW = QNW;
@@ -990,34 +991,45 @@ k_match_pair(const float4* __restrict__ That, int64_t part_first,
     unsigned long long* s_best = s_bar + 1;                                // [NW]
     float* s_min = reinterpret_cast<float*>(s_best + NW);                  // [NW]
     uint32_t* s_taddr = reinterpret_cast<uint32_t*>(s_min + NW);
-    int* s_cnt = reinterpret_cast<int*>(sm.end + kRunCountOff());          // EPI 3: records written by this CTA (both items)
-    const RunSink sink = {EPI == 3 && recs ? recs + (size_t)blockIdx.x * kRunSlots : nullptr, s_cnt};
+    int* s_cnt = reinterpret_cast<int*>(sm.end + kRunCountOff());          // EPI 3: records written for the current pair (both items)
+    int* s_next_q = reinterpret_cast<int*>(sm.end + kNextOff());           // query of the CTA's next pair ...
+    QueryDesc* s_next_d = reinterpret_cast<QueryDesc*>(sm.end + kNextOff() + 16);     // ... and its descriptor (fetched during this pair)
     float4* s_sp = reinterpret_cast<float4*>(sm.end + kSmallBytes);        // body 3: units of the self-mirrored quads
     int2* s_w0 = EPI >= 2 && is_u8 ? reinterpret_cast<int2*>(sm.end + kSmallBytes + kSpecialBytes) : nullptr;   // [kRounds][QT]
     const Buf& buf = sm.buf;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int q = __ldg(pair_query + blockIdx.x);
-    const QueryDesc d = desc[q];
-    const int lp = (int)(pair_first + blockIdx.x - d.groupBase);          // pair number inside the query
-    const bool has2 = 2 * lp + 1 < d.nk;
-    const Item it0(d, q, d.k0 + 2 * lp), it1(d, q, d.k0 + 2 * lp + 1);
-
+    // The kernel is persistent: a CTA walks the pairs blockIdx.x, blockIdx.x + gridDim.x, ... (the launcher starts one
+    // CTA per SM).  Tensor memory, the barrier and the per-thread constants are set up once; the descriptor of the
+    // next pair is fetched while this one is transformed, so no pair but the first starts with two dependent global
+    // reads (ncu, round 2: those reads and the set-up were 2.7 % of the kernel with one CTA per pair).
     if (warp == 0) tmem_alloc(s_taddr, 256);
-    if (is_u8) {
-        if (tid == 0) mbar_init(s_bar, 1);
-        stage_inputs<EPI == 3>(it0, tid, reinterpret_cast<const uint8_t*>(img), img_n, ipfx, sm, s_bar);
-    }
-    if (EPI == 3 && tid == 96) *s_cnt = 0;
-    if (EPI >= 2 && tid == 64) query_constants<S>(reinterpret_cast<double2*>(sm.end + kQueryConstOff()), d, img_n, ipfx, tpfx);
+    if (is_u8 && tid == 0) mbar_init(s_bar, 1);
+    if (EPI == 3 && tid == 32) *s_cnt = 0;
     tmem_fence_before();
     csync<0>();
     tmem_fence_after();
     // this thread's 64 columns: lane quarter of its warp, column block of its warp group
     const uint32_t tcol = *s_taddr + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 64);
-
     const int tm = (T - tid) & (T - 1);               // mirrored chunks C[B/2 - i] live in thread tm's column
     const int col = phys(tid), mcol = phys(tm);
+    const float2 wbase = __ldg(tab.wb + tid);
+    unsigned phase = 0;                               // completed phases of s_bar (one per staged item)
+
+    for (int64_t pi = blockIdx.x; pi < n_pairs; pi += gridDim.x) {        // uniform over the CTA
+    const bool first = pi == (int64_t)blockIdx.x;
+    const int q = first ? __ldg(pair_query + pi) : *s_next_q;
+    const QueryDesc d = first ? desc[q] : *s_next_d;
+    const int64_t pi_next = pi + gridDim.x;
+    int q_next = 0;
+    if (tid == 32 && pi_next < n_pairs) q_next = __ldg(pair_query + pi_next);      // used after the multiply phase: no wait here
+    const int lp = (int)(pair_first + pi - d.groupBase);                  // pair number inside the query
+    const bool has2 = 2 * lp + 1 < d.nk;
+    const Item it0(d, q, d.k0 + 2 * lp), it1(d, q, d.k0 + 2 * lp + 1);
+    const RunSink sink = {EPI == 3 && recs ? recs + (size_t)pi * kRunSlots : nullptr, s_cnt};
+
+    if (is_u8) stage_inputs<EPI == 3>(it0, tid, reinterpret_cast<const uint8_t*>(img), img_n, ipfx, sm, s_bar);
+    if (EPI >= 2 && tid == 64) query_constants<S>(reinterpret_cast<double2*>(sm.end + kQueryConstOff()), d, img_n, ipfx, tpfx);
     C2 sp1 = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};             // C[B/4] of the second item (warp NW-1, lane 0)
     // ---------------- 1+2. multiply-accumulate for both items, packing, first radix-2 step ----
     {
@@ -1025,7 +1037,6 @@ k_match_pair(const float4* __restrict__ That, int64_t part_first,
         const int64_t k = it0.k;
         const float4* tp = That + (d.partBase - part_first) * (int64_t)R::STRIDE;
         const float4* xp = Xhat + k * (int64_t)R::STRIDE;
-        const float2 wbase = __ldg(tab.wb + tid);
         const bool sp_pref = EPI >= 2 && SB_V2_SPECIAL_PREFETCH && special_fits(d.P, 2);
         if (sp_pref && warp == NW - 1) special_prefetch(s_sp, tp, xp, d.P, 2, k, nblk, lane);
         constexpr int U = 2;                          // quads in flight per thread (two accumulator sets each)
@@ -1091,12 +1102,21 @@ k_match_pair(const float4* __restrict__ That, int64_t part_first,
         tmem_wait_st();
     }
     csync<0>();
+    // the next pair's descriptor travels while this pair is transformed (every reader of the slot is past the barrier)
+    if (tid == 32 && pi_next < n_pairs) {
+        *s_next_q = q_next;
+        const float4* src = reinterpret_cast<const float4*>(desc + q_next);
+        static_assert(sizeof(QueryDesc) == 80, "five 16-byte copies");
+#pragma unroll
+        for (int k = 0; k < 5; ++k) cp_async16(reinterpret_cast<float4*>(s_next_d) + k, src + k);
+    }
 
     // ---------------- first item: inverse FFT + epilogue ---------------------------------------
-    fft_passes_dif<0>(buf, tid, tab, is_u8);
+    fft_passes_dif<0>(buf, tid, tab, true);          // drains this thread's asynchronous copies in front of its last barrier
     auto stage_second = [&] { if (is_u8 && has2) stage_inputs<EPI == 3>(it1, tid, reinterpret_cast<const uint8_t*>(img), img_n, ipfx, sm, s_bar); };
-    if constexpr (EPI == 3) finish_item_v3<0>(it0, tid, sm, s_bar, 0u, s_min, s_w0, img_n, keys, curve_out, stage_second, sink);
-    else finish_item<S, 0>(it0, tid, sm, s_bar, 0u, s_best, s_min, img, img_n, ipfx, tpfx, keys, curve_out, stage_second);
+    if constexpr (EPI == 3) finish_item_v3<0>(it0, tid, sm, s_bar, phase & 1u, s_min, s_w0, img_n, keys, curve_out, stage_second, sink);
+    else finish_item<S, 0>(it0, tid, sm, s_bar, phase & 1u, s_best, s_min, img, img_n, ipfx, tpfx, keys, curve_out, stage_second);
+    ++phase;
 
     // ---------------- second item: out of tensor memory, then the same ---------------------------
     if (has2) {                                       // uniform over the CTA
@@ -1104,13 +1124,18 @@ k_match_pair(const float4* __restrict__ That, int64_t part_first,
         if (tid == (NW - 1) * 32) buf.st(phys(Q4), sp1);
         csync<0>();
         fft_passes_dif<0>(buf, tid, tab, is_u8);
-        if constexpr (EPI == 3) finish_item_v3<0>(it1, tid, sm, s_bar, 1u, s_min, s_w0, img_n, keys, curve_out, [] {}, sink);
-        else finish_item<S, 0>(it1, tid, sm, s_bar, 1u, s_best, s_min, img, img_n, ipfx, tpfx, keys, curve_out, [] {});
+        if constexpr (EPI == 3) finish_item_v3<0>(it1, tid, sm, s_bar, phase & 1u, s_min, s_w0, img_n, keys, curve_out, [] {}, sink);
+        else finish_item<S, 0>(it1, tid, sm, s_bar, phase & 1u, s_best, s_min, img, img_n, ipfx, tpfx, keys, curve_out, [] {});
+        ++phase;
     }
+    // end of the pair (behind the closing barrier of the last epilogue, which also separates this pair's readers of the
+    // shared arrays from the next pair's writers): the record count leaves.  The next descriptor became visible with
+    // the barrier that ended the first transform (thread 32 drained its copies in front of it).
+    if (EPI == 3 && rec_count && tid == 32) { rec_count[pi] = *s_cnt < kRunSlots ? *s_cnt : kRunSlots; *s_cnt = 0; }
+    }   // pairs of this CTA
     tmem_fence_before();
     csync<0>();
     if (warp == 0) tmem_dealloc(*s_taddr, 256);
-    if (EPI == 3 && rec_count && tid == 32) rec_count[blockIdx.x] = *s_cnt < kRunSlots ? *s_cnt : kRunSlots;
 }
 
 // EPI 3, second step: one thread per record slot evaluates the 8 lags of its run exactly (fp64) and merges the best
@@ -1405,9 +1430,10 @@ int launch_pair_typed(const sb_stream* image, const sb_stream* tmpl, const float
     for (int64_t i0 = 0; i0 < n_pairs; i0 += max_grid) {
         const int64_t ni = std::min<int64_t>(max_grid, n_pairs - i0);
         if (records) SB_TRY(ensure_run_records(ni));
-        k_match_pair<S, EPI><<<(unsigned)ni, QT, smem, c.stream>>>(
+        const int64_t grid = std::min<int64_t>(ni, c.sm_count);            // persistent: one CTA per SM walks the pairs
+        k_match_pair<S, EPI><<<(unsigned)grid, QT, smem, c.stream>>>(
             reinterpret_cast<const float4*>(d_parts), part_first, reinterpret_cast<const float4*>(image->d_specq), image->nblkq,
-            static_cast<const S*>(image->d_raw), image->n, image->d_pfx, tmpl->d_pfx, d_desc, g_item_query2 + i0, pair_first + i0,
+            static_cast<const S*>(image->d_raw), image->n, image->d_pfx, tmpl->d_pfx, d_desc, g_item_query2 + i0, pair_first + i0, ni,
             tab, d_keys, d_curve, records ? g_run_recs : nullptr, records ? g_run_count : nullptr);
         SB_CUDA(cudaGetLastError());
         if (records) SB_TRY(launch_finish_runs<S>(image, tmpl, d_desc, ni, d_keys));

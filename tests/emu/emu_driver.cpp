@@ -79,8 +79,11 @@ void run_cta(const std::function<void(int)>& body) {
 }  // namespace emu
 #endif
 
+namespace { int g_pair_grid = 0; }
+
 extern "C" {
 
+void emu_set_pair_grid(int g) { g_pair_grid = g; }
 int emu_table_floats(void) { size_t off[kPackedTableCount]; return (int)packed_table_values(off).size(); }
 int emu_smem_bytes(void) { return (int)packed_smem_bytes(3) + 16; }
 int emu_query_desc_bytes(void) { return (int)sizeof(sb::QueryDesc); }
@@ -101,7 +104,8 @@ int emu_run(int kernel, int epi, int is_u8, const float* That, int64_t part_firs
     const double2* tp = reinterpret_cast<const double2*>(tpfx);
     const sb::QueryDesc* d = static_cast<const sb::QueryDesc*>(desc);
     int n_err = 0;
-    const int grid = n_ctas;
+    // k_match_pair is persistent (a CTA walks the pairs b, b + grid, ...): g_pair_grid > 0 runs it with that many CTAs
+    const int grid = (kernel == 1 && g_pair_grid > 0 && g_pair_grid < n_ctas) ? g_pair_grid : n_ctas;
     gridDim = dim3((unsigned)grid, 1, 1);
     for (int b = 0; b < grid; ++b) {
         emu::Cta cta;
@@ -115,7 +119,7 @@ int emu_run(int kernel, int epi, int is_u8, const float* That, int64_t part_firs
 #define SB_EMU_KERNEL(K, ...) do { if (!is_u8) SB_EMU_CALL(K, float, 1, ##__VA_ARGS__); else if (epi == 3) SB_EMU_CALL(K, uint8_t, 3, ##__VA_ARGS__); \
                                    else SB_EMU_CALL(K, uint8_t, 1, ##__VA_ARGS__); } while (0)
             if (kernel == 0) SB_EMU_KERNEL(k_match_packed);
-            else SB_EMU_KERNEL(k_match_pair);
+            else SB_EMU_KERNEL(k_match_pair, (int64_t)n_ctas);
         };
         emu::run_cta(body);
         for (const auto& e : cta.errors) { std::fprintf(stderr, "[emu] CTA %d: %s\n", b, e.c_str()); ++n_err; }

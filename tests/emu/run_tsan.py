@@ -60,6 +60,13 @@ def main():
                 ref = ref or (d, i)
                 assert np.array_equal(ref[0], d) and np.array_equal(ref[1], i)
                 print('kernel %d epilogue %d curves %d ok' % (kernel, epi, curves), flush=True)
+    # the pair kernel is persistent: two CTAs walking all the pairs (state carried from one pair to the next)
+    lib.emu_set_pair_grid(2)
+    for epi in (1, 3):
+        d, i, _ = case.run(1, epi, False)
+        assert np.array_equal(ref[0], d) and np.array_equal(ref[1], i)
+        print('persistent pair kernel, 2 CTAs, epilogue %d ok' % epi, flush=True)
+    lib.emu_set_pair_grid(0)
     img32 = (T.programme(4 * B - 3000, 3).astype(np.float32) / 255.0).astype(np.float32)
     case32 = T.Case(lib, img32, np.roll(img32, -300).copy(), [(20000, 18000, 5, 2 * B + 5000)], np.float32)
     for kernel in (0, 1):

@@ -431,3 +431,33 @@ def test_emulated_third_body_overflowing_record_slots(emu):
             assert np.array_equal(ref[0], d) and np.array_equal(ref[1], i), (kernel, epi, records)
             if records:
                 assert c.last_record_counts.max() == emu.emu_run_slots()        # the slots did overflow
+
+
+def test_emulated_persistent_pair_kernel_walks_several_pairs(emu, case_u8):
+    """k_match_pair is persistent: with fewer CTAs than pairs every CTA walks several pairs -- the barrier's phase
+    counter, the record counter, the prefetched descriptor and the tensor-memory columns carry over from one pair to
+    the next.  Same answers as one CTA per pair, bit for bit: both bodies, curves, records, float32."""
+    c = case_u8
+    want = {(epi, curves): c.run(1, epi, curves) for epi in (1, 3) for curves in (False, True)}
+    try:
+        for grid in (1, 2, 3):
+            emu.emu_set_pair_grid(grid)
+            for (epi, curves), w in want.items():
+                d, i, cur = c.run(1, epi, curves)
+                assert np.array_equal(d, w[0]) and np.array_equal(i, w[1]), (grid, epi, curves)
+                if curves:
+                    assert np.array_equal(cur, w[2])
+    finally:
+        emu.emu_set_pair_grid(0)
+    n_img = 4 * B - 3000
+    rng = np.random.default_rng(9)
+    img = (programme(n_img, 3).astype(np.float32) / 255.0).astype(np.float32)
+    src = (np.roll(img, -300) + rng.normal(0, 0.01, n_img)).astype(np.float32)
+    cf = Case(emu, img, src, [(20000, 18000, 5, 2 * B + 5000), (100, 9000, B, 2 * B), (5000, 40000, 0, 3 * B - 44000)], np.float32)
+    w = cf.run(1, 1, curves=False)
+    try:
+        emu.emu_set_pair_grid(2)
+        d, i, _ = cf.run(1, 1, curves=False)
+    finally:
+        emu.emu_set_pair_grid(0)
+    assert np.array_equal(d, w[0]) and np.array_equal(i, w[1])
