@@ -1265,9 +1265,13 @@ size_t forward_smem_bytes14() {
     return ((size_t)(C::N + (C::N >> 5) + 1) + C::R2 * 32 + 2 * C::R3 * 32) * sizeof(float2) + 64;
 }
 
+// layout of the small area behind Smem::end: barrier (8) | s_best [16] (128) | s_min [16] (64) | TMEM address (4) ... |
+// record counter at 256 | next pair's query + descriptor at 272 (96) | query constants at 384 (32) | end at kSmallBytes
+static_assert(8 + QNW * 8 + QNW * 4 + 4 <= kRunCountOff() && kRunCountOff() + 4 <= kNextOff() &&
+              kNextOff() + 16 + (int)sizeof(QueryDesc) <= kQueryConstOff() && kQueryConstOff() + 32 <= kSmallBytes, "small shared-memory area");
 size_t packed_smem_bytes(int epi = 1) {      // body 3 keeps the runs' exact head sums next to the small arrays
     return epi >= 2 ? kSmemCommon + kSmallBytes + kSpecialBytes + (size_t)kRounds * QT * sizeof(int2)
-                    : kSmemCommon + 8 + QNW * sizeof(unsigned long long) + QNW * sizeof(float) + 64;
+                    : kSmemCommon + kSmallBytes;           // the small area holds the barrier, the reduction scratch, the TMEM address and (pair kernel) the next pair's descriptor
 }
 
 // Values of the tables of PackedTables, in one array: offsets of wb, d1, d2 in `off` (floats)

@@ -124,6 +124,14 @@ int emu_run(int kernel, int epi, int is_u8, const float* That, int64_t part_firs
         emu::run_cta(body);
         for (const auto& e : cta.errors) { std::fprintf(stderr, "[emu] CTA %d: %s\n", b, e.c_str()); ++n_err; }
         emu::cta() = nullptr;
+        // nothing may be written behind the dynamic shared memory the launchers ask for (the array here is larger)
+        const size_t limit = packed_smem_bytes(is_u8 ? epi : 1) + (kernel == 1 ? 16 : 0);
+        for (size_t k = limit; k < sizeof(smem_raw); ++k)
+            if (smem_raw[k] != 0xCD) {
+                std::fprintf(stderr, "[emu] CTA %d wrote shared memory at byte %zu, behind the %zu bytes its launcher allocates\n", b, k, limit);
+                ++n_err;
+                break;
+            }
     }
     return n_err;
 }
