@@ -531,14 +531,14 @@ def run_b200(args):
         if cap is None and world > 1:        # ncu never wraps a multi-rank command: the 1-GPU capture's bytes per CTA serve every N
             cap, why = capture_for('%s/%s/%s/N1' % (args.workload, stype, dom_name))
         # DRAM traffic per launch of the class: the capture holds ONE launch of the match kernel (launches are cut at
-        # 524 288 CTAs), so its bytes per CTA are scaled to this rank's CTAs per step (one CTA per pair of lag blocks)
+        # 524 288 pairs of lag blocks), so its bytes per pair are scaled to this rank's pairs per step
         B = lib.sb_get_block_size()
         lag0_s, nlags_s = plan['shard'][2], plan['shard'][3]
         nk = (lag0_s + nlags_s - 1) // B - lag0_s // B + 1
         ctas_step = int(np.sum((nk + 1) // 2))
         traffic = None
-        if cap and cap.get('dram_bytes_per_cta') and dom_n:
-            traffic = cap['dram_bytes_per_cta'] * ctas_step * args.steps / dom_n
+        if cap and cap.get('dram_bytes_per_pair') and dom_n:
+            traffic = cap['dram_bytes_per_pair'] * ctas_step * args.steps / dom_n
         roof = {'bound': 'hbm', 'kernel': dom_name, 'achieved': round(achieved, 2), 'peak': peak, 'unit': 'GB/s',
                 'frac': round(achieved / peak, 5), 'traffic': traffic,
                 'peak_source': peak_src,
@@ -550,8 +550,8 @@ def run_b200(args):
                 'kernel_ms_per_step': {k: round(v[0] / args.steps, 4) for k, v in sorted(prof.items())}}
         if cap:
             m = cap.get('metrics', {})
-            roof['traffic_basis'] = ('ncu dram__bytes_read+write of one captured launch (%d CTAs) / CTA x %d CTAs of this rank per step / %g launches per step'
-                                     % (int(cap.get('grid_size', 0)), ctas_step, dom_n / args.steps))
+            roof['traffic_basis'] = ('ncu dram__bytes_read+write of one captured launch (%d pairs of lag blocks) / pair x %d pairs of this rank per step / %g launches per step'
+                                     % (int(cap.get('pairs_in_launch', 0)), ctas_step, dom_n / args.steps))
             roof['limiter'] = {'note': 'the kernel keeps the correlation on chip and is not HBM-bound; what ncu shows it waits on',
                                'issue_slots_active_pct': m.get('smsp__issue_active.avg.pct_of_peak_sustained_active'),
                                'warps_active_pct': m.get('sm__warps_active.avg.pct_of_peak_sustained_active'),

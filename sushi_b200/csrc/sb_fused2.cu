@@ -1016,13 +1016,17 @@ k_match_pair(const float4* __restrict__ That, int64_t part_first,
     const float2 wbase = __ldg(tab.wb + tid);
     unsigned phase = 0;                               // completed phases of s_bar (one per staged item)
 
-    for (int64_t pi = blockIdx.x; pi < n_pairs; pi += gridDim.x) {        // uniform over the CTA
-    const bool first = pi == (int64_t)blockIdx.x;
+    // (body 3 only: the first-version instantiations sit at the register limit -- carrying the loop's state across a
+    // pair makes them spill -- and keep one CTA per pair; their launcher starts n_pairs CTAs)
+    constexpr bool kPersistent = EPI == 3, kPrefetch = kPersistent;
+    int64_t pi = blockIdx.x;                          // the grid never exceeds n_pairs
+    do {                                              // uniform over the CTA
+    const bool first = !kPrefetch || pi == (int64_t)blockIdx.x;
     const int q = first ? __ldg(pair_query + pi) : *s_next_q;
     const QueryDesc d = first ? desc[q] : *s_next_d;
     const int64_t pi_next = pi + gridDim.x;
     int q_next = 0;
-    if (tid == 32 && pi_next < n_pairs) q_next = __ldg(pair_query + pi_next);      // used after the multiply phase: no wait here
+    if (kPrefetch && tid == 32 && pi_next < n_pairs) q_next = __ldg(pair_query + pi_next);      // used after the multiply phase: no wait here
     const int lp = (int)(pair_first + pi - d.groupBase);                  // pair number inside the query
     const bool has2 = 2 * lp + 1 < d.nk;
     const Item it0(d, q, d.k0 + 2 * lp), it1(d, q, d.k0 + 2 * lp + 1);
@@ -1103,7 +1107,7 @@ k_match_pair(const float4* __restrict__ That, int64_t part_first,
     }
     csync<0>();
     // the next pair's descriptor travels while this pair is transformed (every reader of the slot is past the barrier)
-    if (tid == 32 && pi_next < n_pairs) {
+    if (kPrefetch && tid == 32 && pi_next < n_pairs) {
         *s_next_q = q_next;
         const float4* src = reinterpret_cast<const float4*>(desc + q_next);
         static_assert(sizeof(QueryDesc) == 80, "five 16-byte copies");
@@ -1132,7 +1136,7 @@ k_match_pair(const float4* __restrict__ That, int64_t part_first,
     // shared arrays from the next pair's writers): the record count leaves.  The next descriptor became visible with
     // the barrier that ended the first transform (thread 32 drained its copies in front of it).
     if (EPI == 3 && rec_count && tid == 32) { rec_count[pi] = *s_cnt < kRunSlots ? *s_cnt : kRunSlots; *s_cnt = 0; }
-    }   // pairs of this CTA
+    } while (kPersistent && (pi += gridDim.x) < n_pairs);   // pairs of this CTA
     tmem_fence_before();
     csync<0>();
     if (warp == 0) tmem_dealloc(*s_taddr, 256);
@@ -1434,7 +1438,7 @@ int launch_pair_typed(const sb_stream* image, const sb_stream* tmpl, const float
     for (int64_t i0 = 0; i0 < n_pairs; i0 += max_grid) {
         const int64_t ni = std::min<int64_t>(max_grid, n_pairs - i0);
         if (records) SB_TRY(ensure_run_records(ni));
-        const int64_t grid = std::min<int64_t>(ni, c.sm_count);            // persistent: one CTA per SM walks the pairs
+        const int64_t grid = EPI == 3 ? std::min<int64_t>(ni, c.sm_count) : ni;      // body 3 is persistent: one CTA per SM walks the pairs
         k_match_pair<S, EPI><<<(unsigned)grid, QT, smem, c.stream>>>(
             reinterpret_cast<const float4*>(d_parts), part_first, reinterpret_cast<const float4*>(image->d_specq), image->nblkq,
             static_cast<const S*>(image->d_raw), image->n, image->d_pfx, tmpl->d_pfx, d_desc, g_item_query2 + i0, pair_first + i0, ni,

@@ -104,8 +104,8 @@ int emu_run(int kernel, int epi, int is_u8, const float* That, int64_t part_firs
     const double2* tp = reinterpret_cast<const double2*>(tpfx);
     const sb::QueryDesc* d = static_cast<const sb::QueryDesc*>(desc);
     int n_err = 0;
-    // k_match_pair is persistent (a CTA walks the pairs b, b + grid, ...): g_pair_grid > 0 runs it with that many CTAs
-    const int grid = (kernel == 1 && g_pair_grid > 0 && g_pair_grid < n_ctas) ? g_pair_grid : n_ctas;
+    // k_match_pair<uint8, 3> is persistent (a CTA walks the pairs b, b + grid, ...): g_pair_grid > 0 runs it with that many CTAs
+    const int grid = (kernel == 1 && is_u8 && epi == 3 && g_pair_grid > 0 && g_pair_grid < n_ctas) ? g_pair_grid : n_ctas;   // like the launcher: body 3 only
     gridDim = dim3((unsigned)grid, 1, 1);
     for (int b = 0; b < grid; ++b) {
         emu::Cta cta;

@@ -434,9 +434,10 @@ def test_emulated_third_body_overflowing_record_slots(emu):
 
 
 def test_emulated_persistent_pair_kernel_walks_several_pairs(emu, case_u8):
-    """k_match_pair is persistent: with fewer CTAs than pairs every CTA walks several pairs -- the barrier's phase
-    counter, the record counter, the prefetched descriptor and the tensor-memory columns carry over from one pair to
-    the next.  Same answers as one CTA per pair, bit for bit: both bodies, curves, records, float32."""
+    """k_match_pair with body 3 is persistent: with fewer CTAs than pairs every CTA walks several pairs -- the barrier's
+    phase counter, the record counter, the prefetched descriptor and the tensor-memory columns carry over from one pair
+    to the next.  Same answers as one CTA per pair, bit for bit, curves and records included (the first-version
+    instantiations keep one CTA per pair: the grid setting does not touch them)."""
     c = case_u8
     want = {(epi, curves): c.run(1, epi, curves) for epi in (1, 3) for curves in (False, True)}
     try:
