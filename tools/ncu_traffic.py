@@ -17,7 +17,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 rep, workload, stype, kclass, ngpus = sys.argv[1:6]
 src_hash = sys.argv[6] if len(sys.argv) > 6 else None      # hash of the CUDA sources the capture was taken from (gpu_pass.sh writes it)
-units = float(sys.argv[7]) if len(sys.argv) > 7 else None  # pairs of lag blocks the captured launch processed (the kernel is persistent: its grid is the SM count)
+n_units = float(sys.argv[7]) if len(sys.argv) > 7 else None  # pairs of lag blocks the captured launch processed (the kernel is persistent: its grid is the SM count)
 sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
@@ -51,8 +51,8 @@ keep = ['gpu__time_duration.sum', 'launch__grid_size', 'launch__registers_per_th
         'sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active', 'smsp__inst_executed.sum',
         'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active']
 grid = float(d['launch__grid_size'][0])
-units = units or grid
-tr[key] = {'dram_bytes_per_launch': dram, 'grid_size': grid, 'pairs_in_launch': units, 'dram_bytes_per_pair': dram / units, 'report': os.path.basename(rep), 'src_hash': src_hash or bench.kernel_source_hash(),
+n_units = n_units or grid
+tr[key] = {'dram_bytes_per_launch': dram, 'grid_size': grid, 'pairs_in_launch': n_units, 'dram_bytes_per_pair': dram / n_units, 'report': os.path.basename(rep), 'src_hash': src_hash or bench.kernel_source_hash(),
            'metrics': {k: ' '.join(d[k]) for k in keep if k in d}}
 json.dump(tr, open(out_path, 'w'), indent=1, sort_keys=True)
 print(key, 'dram bytes/launch', dram)
