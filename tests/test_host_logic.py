@@ -165,3 +165,16 @@ def test_vectorised_planning_equals_scalar_path():
         lo, hi, _ = slice(a, b).indices(src.data.shape[1])
         st, l0, span = dst._window(hi - lo, centers[q], windows[q])
         assert (toff[q], tlen[q], lag0[q], nlags[q], t0[q]) == (lo, hi - lo, l0, span - (hi - lo) + 1, st)
+
+
+def test_kernel_source_hash_ignores_comments_and_layout():
+    """bench.kernel_source_hash stamps ncu captures: rewording a comment or re-indenting must not orphan a capture,
+    changing code must."""
+    import bench
+    a = 'int f(int x) {\n    // add one\n    return x + 1;   /* done */\n}\n'
+    b = 'int f(int x) {  // reworded\n\n  return x + 1;\n}'
+    c = 'int f(int x) { return x + 2; }'
+    s = 'const char* p = "// not a comment"; // a comment'
+    assert bench._strip_comments(a) == bench._strip_comments(b) != bench._strip_comments(c)
+    assert '"// not a comment"' in bench._strip_comments(s) and 'a comment' not in bench._strip_comments(s).replace('"// not a comment"', '')
+    assert len(bench.kernel_source_hash()) == 16
