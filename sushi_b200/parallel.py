@@ -23,6 +23,7 @@ import time
 
 import numpy as np
 
+from ._nvtx import nvtx_range
 from .common import SushiError
 from .wavstream import StreamGeometry
 
@@ -343,18 +344,21 @@ class ShardedMatcher(object):
         if resident is not None:
             src, dst = resident
         else:
-            comm.broadcast(self._bufs[0], self._nbytes[0], self.root, 0)
-            comm.broadcast(self._bufs[1], self._nbytes[1], self.root, 1)       # overlaps the source stream's running sums
-            comm.wait(0)
-            src = be.open_stream(self._bufs[0], self.geom[0], self.sample_type)
-            comm.wait(1)
-            dst = be.open_stream(self._bufs[1], self.geom[1], self.sample_type)
+            with nvtx_range('sushi_b200: broadcast + open streams'):
+                comm.broadcast(self._bufs[0], self._nbytes[0], self.root, 0)
+                comm.broadcast(self._bufs[1], self._nbytes[1], self.root, 1)       # overlaps the source stream's running sums
+                comm.wait(0)
+                src = be.open_stream(self._bufs[0], self.geom[0], self.sample_type)
+                comm.wait(1)
+                dst = be.open_stream(self._bufs[1], self.geom[1], self.sample_type)
         cap = p['cap']
         send = self._res                                                   # [cap x int64 idx][cap x float32 diff]
         if p['hi'] > p['lo']:
-            be.match(dst, src, p['shard'], send, be.offset(send, 8 * cap))
+            with nvtx_range('sushi_b200: match shard'):
+                be.match(dst, src, p['shard'], send, be.offset(send, 8 * cap))
         if cap:
-            comm.all_gather(send, be.offset(self._res, 12 * cap), 12 * cap)
+            with nvtx_range('sushi_b200: all-gather'):
+                comm.all_gather(send, be.offset(self._res, 12 * cap), 12 * cap)
         if resident is None:
             be.close_stream(src)
             be.close_stream(dst)

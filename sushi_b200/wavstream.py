@@ -24,6 +24,7 @@ from time import time
 import numpy as np
 
 from . import _native
+from ._nvtx import nvtx_range
 from .common import SushiError, clip, py2_round
 
 WAVE_FORMAT_PCM = 0x0001
@@ -261,13 +262,15 @@ class WavStream(StreamGeometry):
         lib = _native.lib(device)
         raw = ctypes.c_void_p()
         buf = np.frombuffer(pcm, dtype=np.uint8)
-        _native.check(lib.sb_load_pcm(buf.ctypes.data_as(ctypes.c_void_p), frames, channels, sample_width,
-                                      framerate, sample_rate, self.padding_size, total, ctypes.byref(raw)), 'sb_load_pcm')
+        with nvtx_range('sushi_b200: sb_load_pcm'):
+            _native.check(lib.sb_load_pcm(buf.ctypes.data_as(ctypes.c_void_p), frames, channels, sample_width,
+                                          framerate, sample_rate, self.padding_size, total, ctypes.byref(raw)), 'sb_load_pcm')
         h = ctypes.c_void_p()
         lo, hi = ctypes.c_float(), ctypes.c_float()
         try:
-            _native.check(lib.sb_normalise(raw, _DTYPES[sample_type][1], ctypes.byref(h), ctypes.byref(lo),
-                                           ctypes.byref(hi)), 'sb_normalise')
+            with nvtx_range('sushi_b200: sb_normalise'):
+                _native.check(lib.sb_normalise(raw, _DTYPES[sample_type][1], ctypes.byref(h), ctypes.byref(lo),
+                                               ctypes.byref(hi)), 'sb_normalise')
         finally:
             lib.sb_stream_destroy(raw)
         self.min_value, self.max_value = lo.value, hi.value
@@ -523,8 +526,9 @@ class WavStream(StreamGeometry):
 
     def find_substream_batch(self, src_stream, starts, ends, centers, windows):
         """Batched find_substream: returns (diffs float32[count], times float64[count])."""
-        toff, tlen, lag0, nlags, t0 = self.plan_queries(src_stream, starts, ends, centers, windows)
-        diff, idx = self.find_planned(src_stream, toff, tlen, lag0, nlags)
+        with nvtx_range('sushi_b200: find_substream_batch'):
+            toff, tlen, lag0, nlags, t0 = self.plan_queries(src_stream, starts, ends, centers, windows)
+            diff, idx = self.find_planned(src_stream, toff, tlen, lag0, nlags)
         return diff, t0 + idx / float(self.sample_rate)
 
     def find_planned(self, src_stream, toff, tlen, lag0, nlags):

@@ -178,3 +178,22 @@ def test_kernel_source_hash_ignores_comments_and_layout():
     assert bench._strip_comments(a) == bench._strip_comments(b) != bench._strip_comments(c)
     assert '"// not a comment"' in bench._strip_comments(s) and 'a comment' not in bench._strip_comments(s).replace('"// not a comment"', '')
     assert len(bench.kernel_source_hash()) == 16
+
+
+def test_nvtx_ranges_are_optional_and_harmless(monkeypatch):
+    """SUSHI_B200_NVTX=1 opens libnvToolsExt if there is one; without it, or with the variable unset, the ranges are
+    no-ops.  Either way the bracketed code runs exactly once and exceptions pass through."""
+    from sushi_b200 import _nvtx
+    for flag in ('0', '1'):
+        monkeypatch.setenv('SUSHI_B200_NVTX', flag)
+        monkeypatch.setattr(_nvtx, '_tried', False)
+        monkeypatch.setattr(_nvtx, '_lib', None)
+        ran = []
+        with _nvtx.nvtx_range('test range'):
+            ran.append(1)
+        assert ran == [1]
+        with pytest.raises(ValueError):
+            with _nvtx.nvtx_range('failing range'):
+                raise ValueError('through')
+        if flag == '0':
+            assert not _nvtx.enabled()
